@@ -1,0 +1,151 @@
+/*
+ * vipnerf.h - C ABI of the B200-native ViP-NeRF volumetric render path (libvipnerf_b200.so).
+ *
+ * The reference (NagabhushanSN95/ViP-NeRF) is pure Python; it has no FFI today.  The boundary a maintainer
+ * binds is its model plugin API (src/models/ModelFactory.py:10-22 -> VipNeRF.forward,
+ * src/models/VipNeRF01.py:34-41).  This header is what a ctypes stub for that path calls
+ * (see INTEGRATION.md); every entry point cites the reference function(s) it replaces.
+ *
+ * Conventions
+ *  - plain C: pointers + sizes, no torch / C++ types.  All array pointers are DEVICE pointers on the
+ *    current CUDA device unless a name ends in _host; arrays are fp32, row-major, contiguous, 16-byte aligned.
+ *  - ownership: the caller owns every buffer.  The library never allocates device memory, never
+ *    synchronises the device and launches only on the `stream` it is given (a cudaStream_t passed as
+ *    void*; NULL = legacy default stream).
+ *  - errors: 0 on success, a negative vipnerf_status otherwise; vipnerf_last_error() returns a
+ *    thread-local message.  Nothing throws or aborts.
+ *  - threading: re-entrant; no global mutable state besides a mutex-guarded per-device attribute cache.
+ *    (Under torch.nn.DataParallel, src/Tester01.py:42, one Python thread per GPU calls concurrently.)
+ */
+#ifndef VIPNERF_H_
+#define VIPNERF_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VIPNERF_ABI_VERSION 1
+
+typedef enum vipnerf_status {
+  VIPNERF_OK = 0,
+  VIPNERF_EINVAL = -1,        /* NULL / misaligned pointer, bad size                       */
+  VIPNERF_EUNSUPPORTED = -2,  /* configuration outside the shapes the kernels are built for */
+  VIPNERF_ECUDA = -3,         /* a CUDA runtime call failed (message has the CUDA error)    */
+  VIPNERF_EWORKSPACE = -4,    /* workspace too small                                        */
+  VIPNERF_EABI = -5           /* cfg->abi != VIPNERF_ABI_VERSION                            */
+} vipnerf_status;
+
+/* cfg.flags */
+#define VIPNERF_FLAG_NDC         (1u << 0) /* configs['data_loader']['ndc']   (VipNeRF01.py:16)          */
+#define VIPNERF_FLAG_WHITE_BKGD  (1u << 1) /* configs['model']['white_bkgd']  (VipNeRF01.py:363-364)     */
+#define VIPNERF_FLAG_LINDISP     (1u << 2) /* configs['model']['lindisp']     (VipNeRF01.py:183-190)     */
+
+/* cfg.precision: arithmetic of the 256-wide matmuls (trunk layers, feature_linear, feature columns of
+ * views_linears.0).  Everything else (encodings, heads, compositing, sampling) is always fp32. */
+#define VIPNERF_PRECISION_FP32    0 /* CUDA-core FFMA, staged kernels; the bit-for-bit-closest path      */
+#define VIPNERF_PRECISION_BF16    1 /* tcgen05.mma kind::f16, bf16 operands, fp32 accumulate in TMEM     */
+#define VIPNERF_PRECISION_BF16X3  2 /* tcgen05.mma, hi/lo bf16 split of both operands (3 MMAs / product) */
+
+typedef struct vipnerf_cfg {
+  int32_t abi;          /* VIPNERF_ABI_VERSION */
+  int32_t n_coarse;     /* coarse_mlp.num_samples (64)                                  */
+  int32_t n_fine;       /* fine_mlp.num_samples (128); 0 = no fine pass                 */
+  int32_t l_pts;        /* points_positional_encoding_degree (10)                       */
+  int32_t l_view;       /* views_positional_encoding_degree (4)                         */
+  int32_t depth;        /* netdepth (8)                                                 */
+  int32_t width;        /* netwidth (256)                                               */
+  int32_t skip;         /* skip layer index (4, VipNeRF01.py:466)                       */
+  int32_t n_sec_views;  /* V = secondary views evaluated per sample (0 = sec_views_vis off) */
+  uint32_t flags;       /* VIPNERF_FLAG_*                                               */
+  int32_t precision;    /* VIPNERF_PRECISION_*                                          */
+  int32_t reserved;
+} vipnerf_cfg;
+
+/* Inputs of VipNeRF.render_rays (VipNeRF01.py:74-98; key names of the reference's input dict). */
+typedef struct vipnerf_rays {
+  const float* rays_o;      /* [R,3] world origins                                            */
+  const float* rays_d;      /* [R,3] world directions (not normalised)                        */
+  const float* view_dirs;   /* [R,3] unit view directions fed to the view encoder             */
+  const float* near;        /* [R,1]  (world path)                                            */
+  const float* far;         /* [R,1]                                                          */
+  const float* rays_o_ndc;  /* [R,3]  NDC only                                                */
+  const float* rays_d_ndc;  /* [R,3]  NDC only                                                */
+  const float* near_ndc;    /* [R,1]  NDC only                                                */
+  const float* far_ndc;     /* [R,1]  NDC only                                                */
+  const float* rays_o2;     /* [R,V,3] secondary camera centres, n_sec_views > 0 only         */
+  const float* t_vals;      /* [n_coarse] torch.linspace(0,1,n_coarse) made by the host (:186) */
+  const float* u_vals;      /* [n_fine]   torch.linspace(0,1,n_fine) made by the host   (:239) */
+  const float* t_rand;      /* [R,n_coarse] stratified jitter (:200) or NULL = deterministic  */
+  const float* u_rand;      /* [R,n_fine]   random cdf samples (:242) or NULL = deterministic */
+} vipnerf_rays;
+
+/* Outputs of one sample set (coarse or fine) - the keys VipNeRF.volume_rendering returns
+ * (VipNeRF01.py:366-383) plus the raw network outputs (:128-133).  NULL = not wanted. */
+typedef struct vipnerf_pass_out {
+  float* rgb;            /* [R,3]            */
+  float* acc;            /* [R]              */
+  float* depth;          /* [R]              */
+  float* depth_var;      /* [R]              */
+  float* depth_ndc;      /* [R]   NDC only   */
+  float* depth_var_ndc;  /* [R]   NDC only   */
+  float* visibility2;    /* [R,V]            */
+  float* alpha;          /* [R,S]            */
+  float* z_vals;         /* [R,S]            */
+  float* visibility;     /* [R,S] transmittance                       */
+  float* weights;        /* [R,S]            */
+  float* raw_sigma;      /* [R,S]   (reference shape [R,S,1])         */
+  float* raw_rgb;        /* [R,S,3]          */
+  float* raw_visibility; /* [R,S]   (reference shape [R,S,1])         */
+  float* raw_visibility2;/* [R,S,V] (reference shape [R,S,V,1])       */
+} vipnerf_pass_out;
+
+typedef struct vipnerf_out {
+  vipnerf_pass_out coarse;  /* S = n_coarse          */
+  vipnerf_pass_out fine;    /* S = n_coarse + n_fine */
+} vipnerf_out;
+
+int vipnerf_abi_version(void);
+const char* vipnerf_last_error(void);
+
+/* 0 if this build can run cfg (else VIPNERF_EUNSUPPORTED with the reason in vipnerf_last_error). */
+int vipnerf_check_config(const vipnerf_cfg* cfg);
+
+/* --- weights: replaces MLP.__init__/load_state_dict's fp32 nn.Linear storage (VipNeRF01.py:472-491) with the
+ * kernel's packed layout.  params[24] = the tensors of ONE MLP in the reference's state_dict order:
+ * pts_linears.{0..7}.{weight,bias}, views_linears.0.{weight,bias}, pts_output_linear.{weight,bias},
+ * feature_linear.{weight,bias}, views_output_linear.{weight,bias} (device pointers, fp32). */
+size_t vipnerf_packed_weight_bytes(const vipnerf_cfg* cfg);
+int vipnerf_pack_weights(const vipnerf_cfg* cfg, const float* const params[24], void* packed, void* stream);
+
+/* --- the whole path: replaces VipNeRF.render_rays (VipNeRF01.py:74-171) for n_rays rays (any count; the
+ * reference's chunk / netchunk loops :47-72, :295-329 are subsumed).  packed_fine may be NULL iff n_fine == 0. */
+size_t vipnerf_workspace_bytes(const vipnerf_cfg* cfg, int64_t n_rays);
+int vipnerf_render_forward(const vipnerf_cfg* cfg, const vipnerf_rays* rays, int64_t n_rays,
+                           const void* packed_coarse, const void* packed_fine, const vipnerf_out* out,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
+/* --- stage entry points (used by the teacher-forced parity tests; each is also a piece of the path) --- */
+
+/* MLP.forward on sample points (VipNeRF01.py:509-535 through run_network :264-293):
+ * pts = pts_o + pts_d * z (:105-107).  z [R,S]; outputs raw_* of `out` only. */
+int vipnerf_mlp_forward(const vipnerf_cfg* cfg, const vipnerf_rays* rays, int64_t n_rays, int32_t n_samples,
+                        const float* z_vals, const void* packed, const vipnerf_pass_out* out,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* get_z_vals_coarse (VipNeRF01.py:173-203): near/far (+t_rand) -> z [R,n_coarse]. */
+int vipnerf_coarse_z(const vipnerf_cfg* cfg, const vipnerf_rays* rays, int64_t n_rays, float* z_vals, void* stream);
+
+/* volume_rendering (VipNeRF01.py:331-384) on given network outputs: sigma [R,S], rgb [R,S,3],
+ * vis2 [R,S,V] or NULL, z [R,S]; if z_fine_out != NULL additionally get_z_vals_fine (:205-216 =
+ * sample_pdf :229-262 + sort) -> [R, S + n_fine]. */
+int vipnerf_composite(const vipnerf_cfg* cfg, const vipnerf_rays* rays, int64_t n_rays, int32_t n_samples,
+                      const float* z_vals, const float* sigma, const float* rgb, const float* vis2,
+                      const vipnerf_pass_out* out, float* z_fine_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VIPNERF_H_ */

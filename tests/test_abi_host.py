@@ -1,0 +1,112 @@
+"""Host-side checks that need no GPU: the C-ABI library builds, loads and exports every symbol the header
+declares; configuration errors and the plugin's host logic behave like the reference's."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, 'include', 'vipnerf.h')).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    return sorted(set(re.findall(r'\b(vipnerf_[a-z0-9_]+)\s*\(', text)))
+
+
+def test_header_symbols_exported(built_library):
+    lib = ctypes.CDLL(built_library)
+    names = declared_symbols()
+    assert 'vipnerf_render_forward' in names and len(names) >= 10
+    for name in names:
+        assert hasattr(lib, name), f'{name} declared in include/vipnerf.h but not exported'
+
+
+def test_binding_covers_header(built_library):
+    from vipnerf_b200 import _lib
+    assert sorted(_lib.EXPORTS) == declared_symbols()
+    lib = _lib.load()
+    assert lib.vipnerf_abi_version() == _lib.ABI_VERSION
+
+
+def test_struct_sizes_match_header(built_library):
+    from vipnerf_b200 import _lib
+    assert ctypes.sizeof(_lib.Cfg) == 48
+    assert ctypes.sizeof(_lib.Rays) == 14 * 8
+    assert ctypes.sizeof(_lib.PassOut) == 15 * 8
+    assert ctypes.sizeof(_lib.Out) == 30 * 8
+
+
+def test_config_validation(built_library):
+    from vipnerf_b200 import _lib
+    lib = _lib.load()
+    ok = _lib.make_cfg(precision='bf16')
+    assert lib.vipnerf_check_config(ctypes.byref(ok)) == 0
+    assert lib.vipnerf_packed_weight_bytes(ctypes.byref(ok)) == 27648 + 72 * 16384
+    x3 = _lib.make_cfg(precision='bf16x3')
+    assert lib.vipnerf_packed_weight_bytes(ctypes.byref(x3)) == 27648 + 144 * 16384
+    f32 = _lib.make_cfg(precision='fp32')
+    assert lib.vipnerf_packed_weight_bytes(ctypes.byref(f32)) == 27648 + 589824 * 4
+    assert lib.vipnerf_workspace_bytes(ctypes.byref(ok), 4096) > 4096 * (64 + 192 * 6) * 4
+    bad = _lib.make_cfg(width=128)
+    assert lib.vipnerf_check_config(ctypes.byref(bad)) == -2
+    assert b'W=128' in lib.vipnerf_last_error()
+    with pytest.raises(NotImplementedError):
+        _lib.check(lib.vipnerf_check_config(ctypes.byref(bad)), 'check')
+    bad_abi = _lib.make_cfg()
+    bad_abi.abi = 99
+    assert lib.vipnerf_check_config(ctypes.byref(bad_abi)) == -5
+    sec_tc = _lib.make_cfg(precision='bf16', n_sec_views=2)
+    assert lib.vipnerf_check_config(ctypes.byref(sec_tc)) == -2
+    assert lib.vipnerf_check_config(None) == -1
+    # NULL arguments are reported, never dereferenced
+    assert lib.vipnerf_render_forward(ctypes.byref(ok), None, 16, None, None, None, None, 0, None) == -1
+
+
+def _configs(ndc=True, **model_over):
+    mlp = dict(num_samples=64, netdepth=8, netwidth=256, points_positional_encoding_degree=10,
+               views_positional_encoding_degree=4, use_view_dirs=True, view_dependent_rgb=True, predict_visibility=True)
+    model = dict(name='VipNeRFFused01', coarse_mlp=dict(mlp), fine_mlp=dict(mlp, num_samples=128), chunk=4096,
+                 lindisp=False, netchunk=16384, perturb=True, raw_noise_std=1.0, white_bkgd=False)
+    model.update(model_over)
+    return {'data_loader': {'ndc': ndc}, 'model': model}
+
+
+def test_plugin_factory_and_state_dict():
+    from oracle import vipnerf_oracle as O
+    from vipnerf_b200.ModelFactory import get_model
+    model = get_model(_configs(), None)
+    assert type(model).__name__ == 'VipNeRFFused'
+    sd = O.synth_state_dict(0)
+    assert set(model.state_dict().keys()) == set(sd.keys())          # reference checkpoint keys
+    model.load_state_dict(sd)
+    assert sum(p.numel() for p in model.parameters()) == 1191946
+    # DataParallel checkpoints carry a 'module.' prefix (Trainer01.py:357-362)
+    wrapped = torch.nn.DataParallel(model)
+    wrapped.load_state_dict({f'module.{k}': v for k, v in sd.items()})
+    with pytest.raises(RuntimeError):
+        get_model({'data_loader': {'ndc': True}, 'model': {'name': 'NoSuchModel01'}}, None)
+
+
+def test_plugin_rejects_cpu_and_training():
+    from oracle import vipnerf_oracle as O
+    from vipnerf_b200.ModelFactory import get_model
+    model = get_model(_configs(ndc=False), None).eval()
+    batch = O.make_rays('dtu', 8)
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        model(batch)
+    model.train()
+    with pytest.raises(NotImplementedError):
+        model(batch)
+    with pytest.raises(NotImplementedError):
+        get_model(_configs(coarse_mlp=dict(_configs()['model']['coarse_mlp'], netwidth=128)), None)
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    from vipnerf_b200 import _lib
+    monkeypatch.setattr(_lib, '_lib', None)
+    monkeypatch.setattr(_lib, 'LIB_PATH', str(tmp_path / 'libvipnerf_b200.so'))
+    with pytest.raises(_lib.VipNeRFLibraryError, match='no CPU fallback'):
+        _lib.load()

@@ -1,0 +1,76 @@
+"""Parity of the CUDA MLP evaluators against the oracle on identical sample points (teacher-forced z)."""
+import pytest
+import torch
+
+from oracle import vipnerf_oracle as O
+from tests.helpers import rel_err, to_cuda
+
+pytestmark = pytest.mark.gpu
+
+
+def _points(scene, n_rays, S, seed, n_sec_views=0):
+    ndc = O.SCENES[scene]['ndc']
+    batch = O.make_rays(scene, n_rays, seed=seed, n_sec_views=n_sec_views)
+    near, far = (batch['near_ndc'], batch['far_ndc']) if ndc else (batch['near'], batch['far'])
+    g = torch.Generator().manual_seed(seed)
+    z = torch.sort(near + (far - near) * torch.rand(n_rays, S, generator=g), dim=-1)[0]
+    return ndc, batch, z
+
+
+def _oracle_mlp(params, ndc, batch, z, mode='fp32', sec=False):
+    p_o, p_d = (batch['rays_o_ndc'], batch['rays_d_ndc']) if ndc else (batch['rays_o'], batch['rays_d'])
+    pts = p_o[:, None, :] + p_d[:, None, :] * z[..., None]
+    vd2 = O.other_view_dirs(z, batch['rays_o'], batch['rays_d'], batch['rays_o2'], ndc) if sec else None
+    with torch.no_grad():
+        return O._run_mlp(params, pts, batch['view_dirs'], vd2, mode, 16384)
+
+
+@pytest.mark.parametrize('scene,S', [('fern', 64), ('dtu', 192), ('re10k', 100)])
+def test_mlp_fp32_matches_oracle(scene, S, built_library):
+    """fp32 CUDA-core MLP vs the fp32 oracle: <= 1e-4 relative (the north-star tolerance); typical 1e-6."""
+    from vipnerf_b200 import renderpath
+    ndc, batch, z = _points(scene, 37, S, 3, n_sec_views=2)
+    params = O.split_state_dict(O.synth_state_dict(0), 'fine_model')
+    ref = _oracle_mlp(params, ndc, batch, z, sec=True)
+    packed = renderpath.pack_mlp({k: v.cuda() for k, v in params.items()}, 'fp32')
+    got = renderpath.mlp_forward(to_cuda(batch), z.cuda(), packed, ndc=ndc, precision='fp32', n_sec_views=2)
+    for k in ('sigma', 'rgb', 'visibility', 'visibility2'):
+        assert got[k].shape == ref[k].shape, k
+        err, med = rel_err(got[k], ref[k])
+        assert err <= 1e-4, (k, err, med)
+        assert med <= 2e-6, (k, err, med)
+
+
+@pytest.mark.parametrize('precision,tol_max,tol_med', [('bf16x3', 1e-4, 5e-6), ('bf16', 3e-2, 2e-3)])
+@pytest.mark.parametrize('scene,S', [('fern', 64), ('dtu', 192)])
+def test_mlp_tensor_core_matches_oracle(scene, S, precision, tol_max, tol_med, built_library):
+    """tcgen05 MLP vs the fp32 oracle.  bf16x3 (hi/lo split, 3 MMAs) is the parity mode: <= 1e-4 relative.
+    Plain bf16 cannot meet 1e-4 in max-norm (bf16-rounded operands give ~2e-3 on rgb), so it
+    is held to the error level of the bf16-emulating oracle instead (next test) and to loose absolute bounds."""
+    from vipnerf_b200 import renderpath
+    ndc, batch, z = _points(scene, 150, S, 5)
+    params = O.split_state_dict(O.synth_state_dict(0), 'coarse_model')
+    ref = _oracle_mlp(params, ndc, batch, z)
+    packed = renderpath.pack_mlp({k: v.cuda() for k, v in params.items()}, precision)
+    got = renderpath.mlp_forward(to_cuda(batch), z.cuda(), packed, ndc=ndc, precision=precision)
+    for k in ('sigma', 'rgb', 'visibility'):
+        err, med = rel_err(got[k], ref[k])
+        assert err <= tol_max, (k, err, med)
+        assert med <= tol_med, (k, err, med)
+
+
+@pytest.mark.parametrize('precision', ['bf16', 'bf16x3'])
+def test_mlp_tensor_core_matches_emulation(precision, built_library):
+    """Against the oracle run with the same operand rounding (bf16 operands / hi-lo split, fp32 accumulate) the
+    kernel must agree much more tightly than against fp32: what is left is accumulation order."""
+    from vipnerf_b200 import renderpath
+    ndc, batch, z = _points('dtu', 100, 64, 7)
+    params = O.split_state_dict(O.synth_state_dict(0), 'fine_model')
+    emu = _oracle_mlp(params, ndc, batch, z, mode=precision)
+    fp32 = _oracle_mlp(params, ndc, batch, z)
+    packed = renderpath.pack_mlp({k: v.cuda() for k, v in params.items()}, precision)
+    got = renderpath.mlp_forward(to_cuda(batch), z.cuda(), packed, ndc=ndc, precision=precision)
+    for k in ('sigma', 'rgb', 'visibility'):
+        err_emu = rel_err(got[k], emu[k])[1]
+        err_fp32 = rel_err(got[k], fp32[k])[1]
+        assert err_emu <= max(0.5 * err_fp32, 2e-6), (k, err_emu, err_fp32)

@@ -1,0 +1,138 @@
+"""Drop-in model plugin: the reference's `VipNeRF` module with `render_rays` executed by the B200-native
+CUDA library instead of the PyTorch graph.
+
+Plugin contract (reference src/models/ModelFactory.py:10-22): file `<Name>NN.py` holding class `<Name>`,
+constructed as `<Name>(configs, model_configs)`; here `configs['model']['name'] = 'VipNeRFFused01'`.
+Same `forward(input_batch, retraw=False, sec_views_vis=False) -> dict` signature, output keys and shapes
+as `VipNeRF.forward` (src/models/VipNeRF01.py:34-41, :128-133, :161-170, :366-383), same `state_dict` keys
+(`coarse_model.pts_linears.0.weight`, ... ) so reference checkpoints load unchanged
+(src/Tester01.py:45-49), usable under torch.nn.DataParallel (src/Tester01.py:42).
+
+Scope of this round: inference (`model.eval()` / `torch.no_grad()`).  Training forward+backward is the
+"next" row f1 of SURVEY.md section 8 and raises NotImplementedError.  There is no CPU fallback: inputs must be
+CUDA tensors and the shared library must be built.
+"""
+from __future__ import annotations
+
+import threading
+from typing import Dict, Optional
+
+import torch
+
+from . import renderpath
+
+
+class RadianceMLPParams(torch.nn.Module):
+    """Parameter container with the reference MLP's module names and shapes (VipNeRF01.py:472-491).  It owns the
+    fp32 master weights only; evaluation happens in the CUDA library on a packed copy."""
+
+    def __init__(self, mlp_configs: dict):
+        super().__init__()
+        W = mlp_configs['netwidth']
+        D = mlp_configs['netdepth']
+        pts_dim = 3 + 6 * mlp_configs['points_positional_encoding_degree']
+        views_dim = 3 + 6 * mlp_configs['views_positional_encoding_degree']
+        if not (mlp_configs['use_view_dirs'] and mlp_configs['view_dependent_rgb'] and mlp_configs['predict_visibility']):
+            raise NotImplementedError('VipNeRFFused is built for ViP-NeRF MLPs with use_view_dirs, view_dependent_rgb '
+                                      'and predict_visibility all enabled (every shipped config)')
+        skips = [4]
+        self.pts_linears = torch.nn.ModuleList(
+            [torch.nn.Linear(pts_dim, W)]
+            + [torch.nn.Linear(W + pts_dim if i in skips else W, W) for i in range(D - 1)])
+        self.views_linears = torch.nn.ModuleList([torch.nn.Linear(views_dim + W, W // 2)])
+        self.pts_output_linear = torch.nn.Linear(W, 1)
+        self.feature_linear = torch.nn.Linear(W, W)
+        self.views_output_linear = torch.nn.Linear(W // 2, 4)
+        self.mlp_configs = mlp_configs
+
+    def forward(self, *args, **kwargs):
+        raise RuntimeError('RadianceMLPParams holds parameters only; call VipNeRFFused.forward')
+
+    def named_tensors(self) -> Dict[str, torch.Tensor]:
+        return {k: v for k, v in self.state_dict(keep_vars=True).items()}
+
+
+class VipNeRFFused(torch.nn.Module):
+    def __init__(self, configs: dict, model_configs: Optional[dict] = None):
+        super().__init__()
+        self.configs = configs
+        self.model_configs = model_configs
+        model_cfg = configs['model']
+        self.ndc = configs['data_loader']['ndc']
+        self.coarse_mlp_needed = 'coarse_mlp' in model_cfg
+        self.fine_mlp_needed = 'fine_mlp' in model_cfg
+        if not self.coarse_mlp_needed:
+            raise NotImplementedError('a coarse MLP is required')
+        self.precision = model_cfg.get('precision', 'bf16')   # 'fp32' | 'bf16' | 'bf16x3'
+        if self.precision not in ('fp32', 'bf16', 'bf16x3'):
+            raise ValueError(f"configs['model']['precision'] = {self.precision!r}")
+        self.coarse_model = RadianceMLPParams(model_cfg['coarse_mlp'])
+        self.fine_model = RadianceMLPParams(model_cfg['fine_mlp']) if self.fine_mlp_needed else None
+        for name in ('coarse_mlp', 'fine_mlp'):
+            if name in model_cfg:
+                m = model_cfg[name]
+                shape = (m['netdepth'], m['netwidth'], m['points_positional_encoding_degree'],
+                         m['views_positional_encoding_degree'])
+                if shape != (8, 256, 10, 4):
+                    raise NotImplementedError(f'{name} shape {shape}: kernels are built for (8, 256, 10, 4)')
+        self._pack_lock = threading.Lock()
+        self._packed: Dict[tuple, tuple] = {}
+
+    # ------------------------------------------------------------------ packed-weight cache
+    def _packed_weights(self, which: str, precision: str, device) -> torch.Tensor:
+        mlp = self.coarse_model if which == 'coarse' else self.fine_model
+        tensors = mlp.named_tensors()
+        version = tuple((t.data_ptr(), t._version) for t in tensors.values())
+        key = (which, precision, str(device))
+        with self._pack_lock:
+            hit = self._packed.get(key)
+            if hit is not None and hit[0] == version:
+                return hit[1]
+            packed = renderpath.pack_mlp({k: v.detach() for k, v in tensors.items()}, precision)
+            self._packed[key] = (version, packed)
+            return packed
+
+    # ------------------------------------------------------------------ the reference's forward contract
+    def forward(self, input_batch: dict, retraw: bool = False, sec_views_vis: bool = False):
+        if 'common_data' in input_batch.keys():   # VipNeRF01.py:35-39
+            for key in input_batch['common_data'].keys():
+                if isinstance(input_batch['common_data'][key], torch.Tensor):
+                    input_batch['common_data'][key] = input_batch['common_data'][key][0]
+        if self.training:
+            raise NotImplementedError(
+                'VipNeRFFused: training-mode forward (stratified jitter, density noise, autograd) is not part of '
+                'this build; call model.eval() for validation / test renders')
+        return self.render(input_batch, retraw=retraw, sec_views_vis=sec_views_vis)
+
+    def render(self, input_dict: dict, retraw: bool, sec_views_vis: bool):
+        rays_o = input_dict['rays_o']
+        if not isinstance(rays_o, torch.Tensor) or not rays_o.is_cuda:
+            raise RuntimeError('VipNeRFFused needs CUDA tensors (move the batch with CommonUtils.move_to_device); '
+                               'there is no CPU fallback')
+        device = rays_o.device
+        model_cfg = self.configs['model']
+        batch = {k: input_dict[k] for k in ('rays_o', 'rays_d', 'view_dirs', 'near', 'far', 'rays_o_ndc',
+                                            'rays_d_ndc', 'near_ndc', 'far_ndc') if k in input_dict}
+        n_sec_views = 0
+        if sec_views_vis:   # VipNeRF01.py:84-98
+            if 'rays_o2' in input_dict:
+                rays_o2 = input_dict['rays_o2']
+            else:
+                poses = input_dict['common_data']['poses']
+                image_id = input_dict['pixel_id'][:, 0].long()
+                others = [poses[i + (i >= image_id).long()][:, :3, 3] for i in range(input_dict['num_frames'] - 1)]
+                rays_o2 = torch.stack(others, dim=1)
+            batch['rays_o2'] = rays_o2
+            n_sec_views = rays_o2.shape[1]
+        # visibility2 is evaluated per sample and per secondary view by the fp32 kernels
+        precision = 'fp32' if n_sec_views > 0 else self.precision
+        packed_c = self._packed_weights('coarse', precision, device)
+        packed_f = self._packed_weights('fine', precision, device) if self.fine_mlp_needed else None
+        if not self.fine_mlp_needed and not retraw:
+            raise KeyError('z_vals_fine')   # what the reference does for a coarse-only model, VipNeRF01.py:170
+        out = renderpath.render_rays(
+            batch, packed_c, packed_f, ndc=self.ndc, precision=precision,
+            n_coarse=model_cfg['coarse_mlp']['num_samples'],
+            n_fine=model_cfg['fine_mlp']['num_samples'] if self.fine_mlp_needed else 0,
+            retraw=retraw, n_sec_views=n_sec_views, white_bkgd=model_cfg['white_bkgd'], lindisp=model_cfg['lindisp'])
+        return out

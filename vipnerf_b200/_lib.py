@@ -1,0 +1,110 @@
+"""ctypes binding of libvipnerf_b200.so (C ABI declared in include/vipnerf.h).
+
+The library is the product: there is no Python / CPU fallback.  If the shared object is missing this module
+raises immediately with the command that builds it.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+from ctypes import POINTER, Structure, c_char_p, c_int, c_int32, c_int64, c_size_t, c_uint32, c_void_p
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, 'libvipnerf_b200.so')
+
+ABI_VERSION = 1
+FLAG_NDC, FLAG_WHITE_BKGD, FLAG_LINDISP = 1, 2, 4
+PRECISION = {'fp32': 0, 'bf16': 1, 'bf16x3': 2}
+STATUS_NAMES = {0: 'OK', -1: 'EINVAL', -2: 'EUNSUPPORTED', -3: 'ECUDA', -4: 'EWORKSPACE', -5: 'EABI'}
+
+c_float_p = c_void_p  # device pointers travel as integers
+
+
+class Cfg(Structure):
+    _fields_ = [('abi', c_int32), ('n_coarse', c_int32), ('n_fine', c_int32), ('l_pts', c_int32),
+                ('l_view', c_int32), ('depth', c_int32), ('width', c_int32), ('skip', c_int32),
+                ('n_sec_views', c_int32), ('flags', c_uint32), ('precision', c_int32), ('reserved', c_int32)]
+
+
+RAY_FIELDS = ('rays_o', 'rays_d', 'view_dirs', 'near', 'far', 'rays_o_ndc', 'rays_d_ndc', 'near_ndc', 'far_ndc',
+              'rays_o2', 't_vals', 'u_vals', 't_rand', 'u_rand')
+PASS_FIELDS = ('rgb', 'acc', 'depth', 'depth_var', 'depth_ndc', 'depth_var_ndc', 'visibility2', 'alpha', 'z_vals',
+               'visibility', 'weights', 'raw_sigma', 'raw_rgb', 'raw_visibility', 'raw_visibility2')
+
+
+class Rays(Structure):
+    _fields_ = [(name, c_float_p) for name in RAY_FIELDS]
+
+
+class PassOut(Structure):
+    _fields_ = [(name, c_float_p) for name in PASS_FIELDS]
+
+
+class Out(Structure):
+    _fields_ = [('coarse', PassOut), ('fine', PassOut)]
+
+
+EXPORTS = {
+    # name: (restype, argtypes)  -- must list every symbol include/vipnerf.h declares
+    'vipnerf_abi_version': (c_int, []),
+    'vipnerf_last_error': (c_char_p, []),
+    'vipnerf_check_config': (c_int, [POINTER(Cfg)]),
+    'vipnerf_packed_weight_bytes': (c_size_t, [POINTER(Cfg)]),
+    'vipnerf_pack_weights': (c_int, [POINTER(Cfg), POINTER(c_void_p), c_void_p, c_void_p]),
+    'vipnerf_workspace_bytes': (c_size_t, [POINTER(Cfg), c_int64]),
+    'vipnerf_render_forward': (c_int, [POINTER(Cfg), POINTER(Rays), c_int64, c_void_p, c_void_p, POINTER(Out),
+                                       c_void_p, c_size_t, c_void_p]),
+    'vipnerf_mlp_forward': (c_int, [POINTER(Cfg), POINTER(Rays), c_int64, c_int32, c_void_p, c_void_p,
+                                    POINTER(PassOut), c_void_p, c_size_t, c_void_p]),
+    'vipnerf_coarse_z': (c_int, [POINTER(Cfg), POINTER(Rays), c_int64, c_void_p, c_void_p]),
+    'vipnerf_composite': (c_int, [POINTER(Cfg), POINTER(Rays), c_int64, c_int32, c_void_p, c_void_p, c_void_p,
+                                  c_void_p, POINTER(PassOut), c_void_p, c_void_p]),
+}
+
+_lock = threading.Lock()
+_lib = None
+
+
+class VipNeRFLibraryError(RuntimeError):
+    pass
+
+
+def load() -> ctypes.CDLL:
+    """Loads the in-tree shared library (once).  Raises if it has not been built."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.isfile(LIB_PATH):
+            raise VipNeRFLibraryError(
+                f'{LIB_PATH} is missing: the CUDA extension has not been built. '
+                f'Run `python -m vipnerf_b200.build` (needs nvcc with sm_100a support). There is no CPU fallback.')
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (restype, argtypes) in EXPORTS.items():
+            fn = getattr(lib, name)
+            fn.restype = restype
+            fn.argtypes = argtypes
+        if lib.vipnerf_abi_version() != ABI_VERSION:
+            raise VipNeRFLibraryError(f'ABI mismatch: library {lib.vipnerf_abi_version()}, binding {ABI_VERSION}')
+        _lib = lib
+        return lib
+
+
+def check(status: int, what: str) -> None:
+    """Maps the C status to the exception types the reference raises for the same situations
+    (NotImplementedError for unsupported configurations, RuntimeError otherwise; VipNeRF01.py:292,311,321)."""
+    if status == 0:
+        return
+    msg = load().vipnerf_last_error().decode(errors='replace')
+    text = f'{what}: {STATUS_NAMES.get(status, status)}: {msg}'
+    if status == -2:
+        raise NotImplementedError(text)
+    raise VipNeRFLibraryError(text)
+
+
+def make_cfg(n_coarse=64, n_fine=128, n_sec_views=0, ndc=False, white_bkgd=False, lindisp=False, precision='bf16',
+             l_pts=10, l_view=4, depth=8, width=256, skip=4) -> Cfg:
+    flags = (FLAG_NDC if ndc else 0) | (FLAG_WHITE_BKGD if white_bkgd else 0) | (FLAG_LINDISP if lindisp else 0)
+    return Cfg(ABI_VERSION, n_coarse, n_fine, l_pts, l_view, depth, width, skip, n_sec_views, flags,
+               PRECISION[precision], 0)

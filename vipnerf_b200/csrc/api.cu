@@ -1,0 +1,274 @@
+// C ABI of libvipnerf_b200.so (declared in include/vipnerf.h): argument checking, workspace carving and the
+// launch sequence of the render path.  No device allocation, no device synchronisation, launches only on the
+// caller's stream.
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "kernels.h"
+#include "layout.cuh"
+
+using namespace vipnerf;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+int fail_cuda(cudaError_t e, const char* what) {
+  return fail(VIPNERF_ECUDA, "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+}
+
+bool is_tc(int precision) { return precision == VIPNERF_PRECISION_BF16 || precision == VIPNERF_PRECISION_BF16X3; }
+
+int check_cfg(const vipnerf_cfg* cfg) {
+  if (cfg == nullptr) return fail(VIPNERF_EINVAL, "cfg is NULL");
+  if (cfg->abi != VIPNERF_ABI_VERSION) return fail(VIPNERF_EABI, "cfg.abi=%d, library is %d", cfg->abi, VIPNERF_ABI_VERSION);
+  if (cfg->depth != 8 || cfg->width != kWidth || cfg->skip != 4 || cfg->l_pts != kLPts || cfg->l_view != kLView)
+    return fail(VIPNERF_EUNSUPPORTED,
+                "network shape D=%d W=%d skip=%d L_pts=%d L_view=%d: kernels are built for D=8 W=256 skip=4 L_pts=10 L_view=4",
+                cfg->depth, cfg->width, cfg->skip, cfg->l_pts, cfg->l_view);
+  if (cfg->n_coarse < 3 || cfg->n_coarse > 256) return fail(VIPNERF_EUNSUPPORTED, "n_coarse=%d outside [3,256]", cfg->n_coarse);
+  if (cfg->n_fine < 0 || cfg->n_coarse + cfg->n_fine > 256)
+    return fail(VIPNERF_EUNSUPPORTED, "n_coarse+n_fine=%d outside [n_coarse,256]", cfg->n_coarse + cfg->n_fine);
+  if (cfg->n_sec_views < 0 || cfg->n_sec_views > 16) return fail(VIPNERF_EUNSUPPORTED, "n_sec_views=%d outside [0,16]", cfg->n_sec_views);
+  if (cfg->precision != VIPNERF_PRECISION_FP32 && !is_tc(cfg->precision))
+    return fail(VIPNERF_EUNSUPPORTED, "precision=%d unknown", cfg->precision);
+  if (is_tc(cfg->precision)) {
+    if (cfg->n_sec_views != 0)
+      return fail(VIPNERF_EUNSUPPORTED, "secondary-view visibility (n_sec_views=%d) is only built for PRECISION_FP32", cfg->n_sec_views);
+    if (cfg->n_coarse != 64 || (cfg->n_fine != 0 && cfg->n_fine != 128))
+      return fail(VIPNERF_EUNSUPPORTED, "tensor-core path is built for 64 coarse + 128 fine samples (got %d + %d)", cfg->n_coarse, cfg->n_fine);
+  }
+  return VIPNERF_OK;
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct Workspace {
+  size_t off_z_coarse, off_z_fine, off_sigma, off_rgb, off_vis, off_vis2, total;
+};
+
+Workspace carve(const vipnerf_cfg* cfg, int64_t n_rays) {
+  Workspace w{};
+  const size_t R = (size_t)(n_rays > 0 ? n_rays : 0);
+  const size_t sf = (size_t)cfg->n_coarse + cfg->n_fine;
+  size_t off = 0;
+  auto take = [&](size_t floats) { size_t o = off; off = align_up(off + floats * sizeof(float), 256); return o; };
+  w.off_z_coarse = take(R * cfg->n_coarse);
+  w.off_z_fine = take(R * sf);
+  w.off_sigma = take(R * sf);
+  w.off_rgb = take(R * sf * 3);
+  w.off_vis = take(R * sf);
+  w.off_vis2 = take(R * sf * (size_t)cfg->n_sec_views);
+  w.total = off + 256;
+  return w;
+}
+
+bool misaligned(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) != 0; }
+
+int make_ray_ptrs(const vipnerf_cfg* cfg, const vipnerf_rays* r, RayPtrs* rp, bool need_near_far, bool need_u,
+                  bool need_o2 = true) {
+  if (r == nullptr) return fail(VIPNERF_EINVAL, "rays is NULL");
+  const bool ndc = cfg->flags & VIPNERF_FLAG_NDC;
+  if (!r->rays_o || !r->rays_d || !r->view_dirs) return fail(VIPNERF_EINVAL, "rays_o / rays_d / view_dirs must be non-NULL");
+  if (ndc && (!r->rays_o_ndc || !r->rays_d_ndc)) return fail(VIPNERF_EINVAL, "NDC flag set but rays_o_ndc / rays_d_ndc is NULL");
+  rp->rays_o = r->rays_o;
+  rp->rays_d = r->rays_d;
+  rp->view_dirs = r->view_dirs;
+  rp->pts_o = ndc ? r->rays_o_ndc : r->rays_o;
+  rp->pts_d = ndc ? r->rays_d_ndc : r->rays_d;
+  rp->near = ndc ? r->near_ndc : r->near;
+  rp->far = ndc ? r->far_ndc : r->far;
+  if (need_near_far && (!rp->near || !rp->far || !r->t_vals))
+    return fail(VIPNERF_EINVAL, "near / far (%s) and t_vals must be non-NULL", ndc ? "NDC" : "world");
+  rp->rays_o2 = r->rays_o2;
+  if (need_o2 && cfg->n_sec_views > 0 && !r->rays_o2) return fail(VIPNERF_EINVAL, "n_sec_views=%d but rays_o2 is NULL", cfg->n_sec_views);
+  rp->t_vals = r->t_vals;
+  rp->u_vals = r->u_vals;
+  rp->t_rand = r->t_rand;
+  rp->u_rand = r->u_rand;
+  if (need_u && cfg->n_fine > 0 && !r->u_vals && !r->u_rand) return fail(VIPNERF_EINVAL, "u_vals (or u_rand) must be non-NULL when n_fine > 0");
+  const void* ptrs[] = {r->rays_o, r->rays_d, r->view_dirs, r->near, r->far, r->rays_o_ndc, r->rays_d_ndc, r->near_ndc,
+                        r->far_ndc, r->rays_o2, r->t_vals, r->u_vals, r->t_rand, r->u_rand};
+  for (const void* p : ptrs)
+    if (misaligned(p)) return fail(VIPNERF_EINVAL, "input pointer %p is not 16-byte aligned", p);
+  return VIPNERF_OK;
+}
+
+RenderFlags make_flags(const vipnerf_cfg* cfg) {
+  RenderFlags f;
+  f.ndc = cfg->flags & VIPNERF_FLAG_NDC;
+  f.white_bkgd = cfg->flags & VIPNERF_FLAG_WHITE_BKGD;
+  f.lindisp = cfg->flags & VIPNERF_FLAG_LINDISP;
+  f.n_sec_views = cfg->n_sec_views;
+  return f;
+}
+
+PassOutPtrs to_dev(const vipnerf_pass_out* o) {
+  PassOutPtrs p{};
+  if (o == nullptr) return p;
+  p.rgb = o->rgb; p.acc = o->acc; p.depth = o->depth; p.depth_var = o->depth_var;
+  p.depth_ndc = o->depth_ndc; p.depth_var_ndc = o->depth_var_ndc; p.visibility2 = o->visibility2;
+  p.alpha = o->alpha; p.z_vals = o->z_vals; p.visibility = o->visibility; p.weights = o->weights;
+  p.raw_sigma = o->raw_sigma; p.raw_rgb = o->raw_rgb; p.raw_visibility = o->raw_visibility;
+  p.raw_visibility2 = o->raw_visibility2;
+  return p;
+}
+
+}  // namespace
+
+extern "C" {
+
+int vipnerf_abi_version(void) { return VIPNERF_ABI_VERSION; }
+
+const char* vipnerf_last_error(void) { return g_last_error.c_str(); }
+
+int vipnerf_check_config(const vipnerf_cfg* cfg) { return check_cfg(cfg); }
+
+size_t vipnerf_packed_weight_bytes(const vipnerf_cfg* cfg) {
+  if (check_cfg(cfg) != VIPNERF_OK) return 0;
+  switch (cfg->precision) {
+    case VIPNERF_PRECISION_FP32: return kSmallBytes + (size_t)kFp32BigFloats * sizeof(float);
+    case VIPNERF_PRECISION_BF16: return kSmallBytes + (size_t)kTcChunks * kChunkBytes;
+    default: return kSmallBytes + (size_t)2 * kTcChunks * kChunkBytes;
+  }
+}
+
+int vipnerf_pack_weights(const vipnerf_cfg* cfg, const float* const params[24], void* packed, void* stream) {
+  if (int rc = check_cfg(cfg)) return rc;
+  if (params == nullptr || packed == nullptr) return fail(VIPNERF_EINVAL, "params / packed is NULL");
+  for (int i = 0; i < 24; ++i)
+    if (params[i] == nullptr) return fail(VIPNERF_EINVAL, "params[%d] is NULL", i);
+  if (reinterpret_cast<uintptr_t>(packed) & 1023u) return fail(VIPNERF_EINVAL, "packed buffer must be 1024-byte aligned");
+  cudaError_t e = launch_pack_weights(cfg->precision, params, packed, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return fail_cuda(e, "pack_weights");
+  return VIPNERF_OK;
+}
+
+size_t vipnerf_workspace_bytes(const vipnerf_cfg* cfg, int64_t n_rays) {
+  if (check_cfg(cfg) != VIPNERF_OK || n_rays < 0) return 0;
+  return carve(cfg, n_rays).total;
+}
+
+int vipnerf_coarse_z(const vipnerf_cfg* cfg, const vipnerf_rays* rays, int64_t n_rays, float* z_vals, void* stream) {
+  if (int rc = check_cfg(cfg)) return rc;
+  RayPtrs rp{};
+  if (int rc = make_ray_ptrs(cfg, rays, &rp, true, false, false)) return rc;
+  if (n_rays < 0 || z_vals == nullptr) return fail(VIPNERF_EINVAL, "n_rays < 0 or z_vals NULL");
+  cudaError_t e = launch_coarse_z(rp, n_rays, cfg->n_coarse, cfg->flags & VIPNERF_FLAG_LINDISP, z_vals,
+                                  static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return fail_cuda(e, "coarse_z");
+  return VIPNERF_OK;
+}
+
+int vipnerf_mlp_forward(const vipnerf_cfg* cfg, const vipnerf_rays* rays, int64_t n_rays, int32_t n_samples,
+                        const float* z_vals, const void* packed, const vipnerf_pass_out* out, void* workspace,
+                        size_t workspace_bytes, void* stream) {
+  (void)workspace; (void)workspace_bytes;
+  if (int rc = check_cfg(cfg)) return rc;
+  RayPtrs rp{};
+  if (int rc = make_ray_ptrs(cfg, rays, &rp, false, false)) return rc;
+  if (n_rays < 0 || n_samples < 1 || n_samples > 256) return fail(VIPNERF_EINVAL, "n_rays=%lld n_samples=%d", (long long)n_rays, n_samples);
+  if (!z_vals || !packed || !out) return fail(VIPNERF_EINVAL, "z_vals / packed / out is NULL");
+  if (!out->raw_sigma || !out->raw_rgb || !out->raw_visibility) return fail(VIPNERF_EINVAL, "raw_sigma / raw_rgb / raw_visibility outputs are required");
+  if (cfg->n_sec_views > 0 && !out->raw_visibility2) return fail(VIPNERF_EINVAL, "n_sec_views > 0 needs raw_visibility2");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const RenderFlags fl = make_flags(cfg);
+  cudaError_t e;
+  if (cfg->precision == VIPNERF_PRECISION_FP32) {
+    e = launch_mlp_fp32(rp, fl, n_rays, n_samples, z_vals, packed, out->raw_sigma, out->raw_rgb, out->raw_visibility,
+                        out->raw_visibility2, s);
+  } else {
+    if (n_samples != 64 && n_samples != 192) return fail(VIPNERF_EUNSUPPORTED, "tensor-core MLP takes 64 or 192 samples per ray (got %d)", n_samples);
+    e = launch_mlp_tc(cfg->precision, rp, fl, n_rays, n_samples, z_vals, packed, out->raw_sigma, out->raw_rgb,
+                      out->raw_visibility, s);
+  }
+  if (e != cudaSuccess) return fail_cuda(e, "mlp_forward");
+  return VIPNERF_OK;
+}
+
+int vipnerf_composite(const vipnerf_cfg* cfg, const vipnerf_rays* rays, int64_t n_rays, int32_t n_samples,
+                      const float* z_vals, const float* sigma, const float* rgb, const float* vis2,
+                      const vipnerf_pass_out* out, float* z_fine_out, void* stream) {
+  if (int rc = check_cfg(cfg)) return rc;
+  RayPtrs rp{};
+  if (int rc = make_ray_ptrs(cfg, rays, &rp, false, z_fine_out != nullptr, false)) return rc;
+  if (n_rays < 0 || n_samples < 3 || n_samples > 256) return fail(VIPNERF_EINVAL, "n_rays=%lld n_samples=%d", (long long)n_rays, n_samples);
+  if (!z_vals || !sigma || !rgb || !out) return fail(VIPNERF_EINVAL, "z_vals / sigma / rgb / out is NULL");
+  if (z_fine_out && (cfg->n_fine < 1 || n_samples + cfg->n_fine > 256)) return fail(VIPNERF_EINVAL, "z_fine_out given but n_fine=%d", cfg->n_fine);
+  cudaError_t e = launch_composite(rp, make_flags(cfg), n_rays, n_samples, z_vals, sigma, rgb, vis2, to_dev(out),
+                                   cfg->n_fine, z_fine_out, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return fail_cuda(e, "composite");
+  return VIPNERF_OK;
+}
+
+int vipnerf_render_forward(const vipnerf_cfg* cfg, const vipnerf_rays* rays, int64_t n_rays, const void* packed_coarse,
+                           const void* packed_fine, const vipnerf_out* out, void* workspace, size_t workspace_bytes,
+                           void* stream) {
+  if (int rc = check_cfg(cfg)) return rc;
+  RayPtrs rp{};
+  if (int rc = make_ray_ptrs(cfg, rays, &rp, true, true)) return rc;
+  if (n_rays < 0) return fail(VIPNERF_EINVAL, "n_rays=%lld", (long long)n_rays);
+  if (!packed_coarse || !out) return fail(VIPNERF_EINVAL, "packed_coarse / out is NULL");
+  if (cfg->n_fine > 0 && !packed_fine) return fail(VIPNERF_EINVAL, "n_fine=%d but packed_fine is NULL", cfg->n_fine);
+  const Workspace w = carve(cfg, n_rays);
+  if (n_rays > 0 && (!workspace || workspace_bytes < w.total))
+    return fail(VIPNERF_EWORKSPACE, "workspace %zu bytes < required %zu", workspace_bytes, w.total);
+  if (n_rays == 0) return VIPNERF_OK;
+  if (reinterpret_cast<uintptr_t>(workspace) & 255u) return fail(VIPNERF_EINVAL, "workspace must be 256-byte aligned");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  auto at = [&](size_t off) { return reinterpret_cast<float*>(ws + off); };
+  const RenderFlags fl = make_flags(cfg);
+  const int Nc = cfg->n_coarse, Sf = cfg->n_coarse + cfg->n_fine;
+  const bool has_fine = cfg->n_fine > 0;
+  const PassOutPtrs oc = to_dev(&out->coarse), of = to_dev(&out->fine);
+  cudaError_t e;
+
+  if (is_tc(cfg->precision)) {
+    FusedArgs a{};
+    a.rp = rp; a.fl = fl; a.n_rays = n_rays; a.n_coarse = Nc; a.n_fine = cfg->n_fine;
+    a.packed_coarse = packed_coarse; a.packed_fine = packed_fine;
+    a.out_coarse = oc; a.out_fine = of;
+    a.ws_z_coarse = at(w.off_z_coarse); a.ws_z_fine = at(w.off_z_fine); a.ws_raw = at(w.off_sigma);
+    e = launch_render_fused_tc(cfg->precision, a, s);
+    if (e != cudaSuccess) return fail_cuda(e, "render_fused_tc");
+    return VIPNERF_OK;
+  }
+
+  // staged fp32 path: z_coarse -> MLP -> composite(+resample) -> MLP -> composite
+  float* z_c = oc.z_vals ? oc.z_vals : at(w.off_z_coarse);
+  float* z_f = of.z_vals ? of.z_vals : at(w.off_z_fine);
+  if ((e = launch_coarse_z(rp, n_rays, Nc, fl.lindisp, z_c, s)) != cudaSuccess) return fail_cuda(e, "coarse_z");
+  for (int pass = 0; pass < (has_fine ? 2 : 1); ++pass) {
+    const PassOutPtrs& o = pass ? of : oc;
+    const int S = pass ? Sf : Nc;
+    const float* z = pass ? z_f : z_c;
+    float* sig = o.raw_sigma ? o.raw_sigma : at(w.off_sigma);
+    float* rgb = o.raw_rgb ? o.raw_rgb : at(w.off_rgb);
+    float* vis = o.raw_visibility ? o.raw_visibility : at(w.off_vis);
+    float* vis2 = fl.n_sec_views ? (o.raw_visibility2 ? o.raw_visibility2 : at(w.off_vis2)) : nullptr;
+    e = launch_mlp_fp32(rp, fl, n_rays, S, z, pass ? packed_fine : packed_coarse, sig, rgb, vis, vis2, s);
+    if (e != cudaSuccess) return fail_cuda(e, "mlp_fp32");
+    PassOutPtrs oo = o;
+    oo.z_vals = nullptr;  // z already sits in its final place
+    e = launch_composite(rp, fl, n_rays, S, z, sig, rgb, vis2, oo, cfg->n_fine, (pass == 0 && has_fine) ? z_f : nullptr, s);
+    if (e != cudaSuccess) return fail_cuda(e, "composite");
+  }
+  return VIPNERF_OK;
+}
+
+}  // extern "C"

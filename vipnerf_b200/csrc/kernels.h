@@ -1,0 +1,62 @@
+// Internal launch interface between the C-ABI layer (api.cu) and the kernel translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/vipnerf.h"
+#include "stages.cuh"
+
+namespace vipnerf {
+
+// What every kernel needs to know about the rays of a launch (device pointers).
+struct RayPtrs {
+  const float* rays_o;
+  const float* rays_d;
+  const float* view_dirs;
+  const float* pts_o;     // origins used for sample points: rays_o (world) or rays_o_ndc
+  const float* pts_d;     // directions used for sample points and for delta scaling
+  const float* near;      // the pair matching pts_*: near/far or near_ndc/far_ndc
+  const float* far;
+  const float* rays_o2;   // [R,V,3] or null
+  const float* t_vals;
+  const float* u_vals;
+  const float* t_rand;
+  const float* u_rand;
+};
+
+struct RenderFlags {
+  bool ndc, white_bkgd, lindisp;
+  int n_sec_views;
+};
+
+// stage_kernels.cu
+cudaError_t launch_pack_weights(int precision, const float* const params_dev[24], void* packed, cudaStream_t s);
+cudaError_t launch_coarse_z(const RayPtrs& rp, int64_t n_rays, int n_coarse, bool lindisp, float* z, cudaStream_t s);
+cudaError_t launch_composite(const RayPtrs& rp, const RenderFlags& fl, int64_t n_rays, int S, const float* z,
+                             const float* sigma, const float* rgb, const float* vis2, const PassOutPtrs& out,
+                             int n_fine, float* z_fine_out, cudaStream_t s);
+
+// mlp_fp32.cu : CUDA-core evaluation of the MLP on R*S sample points (pts = pts_o + pts_d * z)
+cudaError_t launch_mlp_fp32(const RayPtrs& rp, const RenderFlags& fl, int64_t n_rays, int S, const float* z,
+                            const void* packed, float* sigma, float* rgb, float* vis, float* vis2, cudaStream_t s);
+
+// mlp_tc.cu : tcgen05 evaluation (precision = BF16 or BF16X3)
+cudaError_t launch_mlp_tc(int precision, const RayPtrs& rp, const RenderFlags& fl, int64_t n_rays, int S,
+                          const float* z, const void* packed, float* sigma, float* rgb, float* vis,
+                          cudaStream_t s);
+// mlp_tc.cu : the fused coarse+fine render of a ray batch in one launch
+struct FusedArgs {
+  RayPtrs rp;
+  RenderFlags fl;
+  int64_t n_rays;
+  int n_coarse, n_fine;
+  const void* packed_coarse;
+  const void* packed_fine;
+  PassOutPtrs out_coarse, out_fine;
+  float* ws_z_coarse;   // [R,Nc]      workspace
+  float* ws_z_fine;     // [R,Nc+Nf]
+  float* ws_raw;        // [R,(Nc+Nf),5] sigma,r,g,b,vis of the pass in flight (reused coarse -> fine)
+};
+cudaError_t launch_render_fused_tc(int precision, const FusedArgs& a, cudaStream_t s);
+
+}  // namespace vipnerf

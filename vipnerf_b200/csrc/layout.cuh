@@ -1,0 +1,78 @@
+// Packed-weight layout and network constants shared by every kernel of the render path.
+//
+// The network is the reference's MLP (src/models/VipNeRF01.py:451-492) at the one shape every shipped
+// config uses: D=8, W=256, skip after layer 4, L_pts=10 (63-d encoding), L_view=4 (27-d encoding),
+// view-dependent rgb + visibility head.  It is evaluated as ten "matrix layers" (M0..M9):
+//
+//   M0      pts_linears.0        K= 64 (63 encoding cols + 1 zero)          N=256  ReLU
+//   M1..M4  pts_linears.1..4     K=256                                       N=256  ReLU
+//   M5      pts_linears.5        K=320 (64 encoding cols first, then 256 h)  N=256  ReLU   (:543-544)
+//   M6,M7   pts_linears.6,7      K=256                                       N=256  ReLU
+//   M8      feature_linear       K=256                                       N=256  (no activation, :564)
+//   M9      views_linears.0      K=256 (feature columns only)                N=128  ReLU after adding the
+//                                                       view-direction columns' contribution in fp32 (:576-580)
+// plus three small fp32 heads done on CUDA cores: sigma (pts_output_linear, :546-553), the 27
+// view-encoding columns of views_linears.0, and views_output_linear (128->4, :582-594).
+#pragma once
+#include <stdint.h>
+
+namespace vipnerf {
+
+constexpr int kWidth = 256;
+constexpr int kHalfWidth = 128;
+constexpr int kLPts = 10;
+constexpr int kLView = 4;
+constexpr int kEncPts = 3 + 6 * kLPts;    // 63
+constexpr int kEncPtsPad = 64;
+constexpr int kEncView = 3 + 6 * kLView;  // 27
+constexpr int kNumMatLayers = 10;
+
+__host__ __device__ constexpr int layer_k(int l) { return l == 0 ? 64 : (l == 5 ? 320 : 256); }
+__host__ __device__ constexpr int layer_n(int l) { return l == 9 ? 128 : 256; }
+
+// ---- small fp32 parameters (first region of every packed buffer), offsets in floats
+constexpr int kOffBias = 0;                          // [9][256]: M0..M8 biases (M8 = feature_linear.bias)
+constexpr int kOffBiasViews = kOffBias + 9 * 256;    // [128]  views_linears.0.bias
+constexpr int kOffWSigma = kOffBiasViews + 128;      // [256]  pts_output_linear.weight
+constexpr int kOffBSigma = kOffWSigma + 256;         // [4]    pts_output_linear.bias (+pad)
+constexpr int kOffWViewDir = kOffBSigma + 4;         // [27][128] views_linears.0.weight[:, 256+j] transposed
+constexpr int kOffWOut = kOffWViewDir + 27 * 128;    // [128][4]  views_output_linear.weight transposed
+constexpr int kOffBOut = kOffWOut + 128 * 4;         // [4]    views_output_linear.bias
+constexpr int kSmallFloats = kOffBOut + 4;
+constexpr int kSmallBytes = ((kSmallFloats * 4 + 1023) / 1024) * 1024;  // keep the big region 1 KiB aligned
+
+// ---- fp32 big region: per matrix layer the transposed weight Wt[k][n] (k = A column), floats
+__host__ __device__ constexpr int fp32_layer_offset(int l) {
+  int off = 0;
+  for (int i = 0; i < l; ++i) off += layer_k(i) * layer_n(i);
+  return off;
+}
+constexpr int kFp32BigFloats = fp32_layer_offset(kNumMatLayers);  // 589,824
+
+// ---- tensor-core big region: 16 KiB "chunk images".  One chunk = 128 output rows (n) x 64 k-columns
+// of bf16 in the canonical K-major SWIZZLE_128B shared-memory layout tcgen05.mma reads:
+//   byte(n, k) = n*128 + ((((k & 63) >> 3) ^ (n & 7)) << 4) + (k & 7)*2
+// Chunks are stored in the order the kernel consumes them: layer, k-chunk, n-half; in BF16X3 mode every
+// chunk is followed by its "lo" image (bf16(w - float(bf16(w)))).
+constexpr int kChunkBytes = 16384;
+__host__ __device__ constexpr int layer_chunks(int l) { return (layer_k(l) / 64) * (layer_n(l) / 128); }
+__host__ __device__ constexpr int tc_layer_chunk_offset(int l) {
+  int off = 0;
+  for (int i = 0; i < l; ++i) off += layer_chunks(i);
+  return off;
+}
+constexpr int kTcChunks = tc_layer_chunk_offset(kNumMatLayers);  // 72
+
+// Maps A column k of matrix layer l to the source weight column (or -1 for a zero pad column).
+__host__ __device__ inline int source_col(int l, int k) {
+  if (l == 0) return k < kEncPts ? k : -1;
+  if (l == 5) return k < kEncPts ? k : (k == 63 ? -1 : k - 1);  // 64 + j -> 63 + j
+  return k;
+}
+// Source tensor (index into params[24]) and its in-features of matrix layer l.
+__host__ __device__ inline int source_param(int l) { return l < 8 ? 2 * l : (l == 8 ? 20 : 16); }
+__host__ __device__ inline int source_in_features(int l) {
+  return l == 0 ? kEncPts : (l == 5 ? kWidth + kEncPts : (l == 9 ? kWidth + kEncView : kWidth));
+}
+
+}  // namespace vipnerf

@@ -1,0 +1,155 @@
+// Weight packing, coarse sample placement and the stand-alone compositing / re-sampling kernel.
+#include <cuda_bf16.h>
+
+#include "kernels.h"
+#include "layout.cuh"
+
+namespace vipnerf {
+
+struct ParamPtrs { const float* p[24]; };
+
+// ---------------------------------------------------------------------------------------------------
+// pack: reference nn.Linear tensors (VipNeRF01.py:472-491, [out,in] row-major fp32) -> kernel layout
+__global__ void k_pack_small(ParamPtrs pp, float* __restrict__ small) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= kSmallFloats) return;
+  float v = 0.f;
+  if (i < kOffBiasViews) {
+    const int l = i / 256, n = i % 256;
+    v = (l < 8 ? pp.p[2 * l + 1] : pp.p[21])[n];
+  } else if (i < kOffWSigma) {
+    v = pp.p[17][i - kOffBiasViews];
+  } else if (i < kOffBSigma) {
+    v = pp.p[18][i - kOffWSigma];
+  } else if (i < kOffWViewDir) {
+    v = (i == kOffBSigma) ? pp.p[19][0] : 0.f;
+  } else if (i < kOffWOut) {
+    const int j = (i - kOffWViewDir) / 128, c = (i - kOffWViewDir) % 128;
+    v = pp.p[16][c * (kWidth + kEncView) + kWidth + j];
+  } else if (i < kOffBOut) {
+    const int c = (i - kOffWOut) / 4, k = (i - kOffWOut) % 4;
+    v = pp.p[22][k * 128 + c];
+  } else {
+    v = pp.p[23][i - kOffBOut];
+  }
+  small[i] = v;
+}
+
+__device__ __forceinline__ float source_weight(const ParamPtrs& pp, int l, int n, int k) {
+  const int sc = source_col(l, k);
+  return sc < 0 ? 0.f : pp.p[source_param(l)][(int64_t)n * source_in_features(l) + sc];
+}
+
+__global__ void k_pack_fp32(ParamPtrs pp, float* __restrict__ big) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= kFp32BigFloats) return;
+  int l = 0, off = 0;
+  while (l < kNumMatLayers - 1 && i >= off + layer_k(l) * layer_n(l)) { off += layer_k(l) * layer_n(l); ++l; }
+  const int N = layer_n(l);
+  const int k = (i - off) / N, n = (i - off) % N;
+  big[i] = source_weight(pp, l, n, k);
+}
+
+template <bool kSplit3>
+__global__ void k_pack_tc(ParamPtrs pp, uint8_t* __restrict__ big) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // one bf16 element of the hi image set
+  if (i >= kTcChunks * (kChunkBytes / 2)) return;
+  const int chunk = i / (kChunkBytes / 2), e = i % (kChunkBytes / 2);
+  int l = 0;
+  while (l < kNumMatLayers - 1 && chunk >= tc_layer_chunk_offset(l + 1)) ++l;
+  const int halves = layer_n(l) / 128;
+  const int cl = chunk - tc_layer_chunk_offset(l);
+  const int kc = cl / halves, nh = cl % halves;
+  const int n_local = e / 64, k_local = e % 64;
+  const float w = source_weight(pp, l, nh * 128 + n_local, kc * 64 + k_local);
+  const uint32_t byte = n_local * 128 + ((((k_local >> 3) ^ (n_local & 7))) << 4) + (k_local & 7) * 2;
+  const __nv_bfloat16 hi = __float2bfloat16_rn(w);
+  if (!kSplit3) {
+    *reinterpret_cast<__nv_bfloat16*>(big + (size_t)chunk * kChunkBytes + byte) = hi;
+  } else {
+    const __nv_bfloat16 lo = __float2bfloat16_rn(w - __bfloat162float(hi));
+    *reinterpret_cast<__nv_bfloat16*>(big + (size_t)(2 * chunk) * kChunkBytes + byte) = hi;
+    *reinterpret_cast<__nv_bfloat16*>(big + (size_t)(2 * chunk + 1) * kChunkBytes + byte) = lo;
+  }
+}
+
+cudaError_t launch_pack_weights(int precision, const float* const params_dev[24], void* packed, cudaStream_t s) {
+  ParamPtrs pp;
+  for (int i = 0; i < 24; ++i) pp.p[i] = params_dev[i];
+  float* small = reinterpret_cast<float*>(packed);
+  uint8_t* big = reinterpret_cast<uint8_t*>(packed) + kSmallBytes;
+  k_pack_small<<<(kSmallFloats + 255) / 256, 256, 0, s>>>(pp, small);
+  if (precision == VIPNERF_PRECISION_FP32) {
+    k_pack_fp32<<<(kFp32BigFloats + 255) / 256, 256, 0, s>>>(pp, reinterpret_cast<float*>(big));
+  } else {
+    const int n = kTcChunks * (kChunkBytes / 2);
+    if (precision == VIPNERF_PRECISION_BF16X3) k_pack_tc<true><<<(n + 255) / 256, 256, 0, s>>>(pp, big);
+    else k_pack_tc<false><<<(n + 255) / 256, 256, 0, s>>>(pp, big);
+  }
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------
+// get_z_vals_coarse (VipNeRF01.py:173-203)
+__global__ void k_coarse_z(const float* __restrict__ near, const float* __restrict__ far,
+                           const float* __restrict__ t_vals, const float* __restrict__ t_rand, int64_t n_rays,
+                           int n, bool lindisp, float* __restrict__ z) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_rays * n) return;
+  const int64_t ray = i / n;
+  const int s = (int)(i % n);
+  z[i] = coarse_z_at(near[ray], far[ray], t_vals, s, n, lindisp, t_rand ? t_rand + ray * n : nullptr);
+}
+
+cudaError_t launch_coarse_z(const RayPtrs& rp, int64_t n_rays, int n_coarse, bool lindisp, float* z, cudaStream_t s) {
+  const int64_t total = n_rays * n_coarse;
+  if (total == 0) return cudaSuccess;
+  k_coarse_z<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(rp.near, rp.far, rp.t_vals, rp.t_rand, n_rays, n_coarse,
+                                                             lindisp, z);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------
+// volume_rendering (+ get_z_vals_fine): one warp per ray, four rays per block
+template <int SPL>
+__global__ void __launch_bounds__(128) k_composite(RayPtrs rp, RenderFlags fl, int64_t n_rays, int S,
+                                                   const float* __restrict__ z, const float* __restrict__ sigma,
+                                                   const float* __restrict__ rgb, const float* __restrict__ vis2,
+                                                   PassOutPtrs out, int n_fine, float* __restrict__ z_fine_out) {
+  extern __shared__ float scratch_all[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t ray = (int64_t)blockIdx.x * 4 + warp;
+  if (ray >= n_rays) return;
+  RayConsts rc;
+  rc.dnorm = vec3_norm(rp.pts_d[3 * ray], rp.pts_d[3 * ray + 1], rp.pts_d[3 * ray + 2]);
+  rc.oz = rp.rays_o[3 * ray + 2];
+  rc.dz = rp.rays_d[3 * ray + 2];
+  float z_reg[SPL], w_reg[SPL];
+  composite_ray<SPL>(lane, S, z + ray * S, sigma + ray * S, rgb + ray * S * 3,
+                     vis2 ? vis2 + ray * S * fl.n_sec_views : nullptr, fl.n_sec_views, fl.ndc, fl.white_bkgd, rc, out,
+                     ray, z_reg, w_reg);
+  if (z_fine_out != nullptr) {
+    float* scratch = scratch_all + warp * resample_scratch_floats(S, n_fine);
+    const float* u = rp.u_rand ? rp.u_rand + ray * n_fine : rp.u_vals;
+    resample_ray<SPL>(lane, S, n_fine, z_reg, w_reg, u, rp.u_rand == nullptr, scratch,
+                      z_fine_out + ray * (S + n_fine));
+  }
+}
+
+cudaError_t launch_composite(const RayPtrs& rp, const RenderFlags& fl, int64_t n_rays, int S, const float* z,
+                             const float* sigma, const float* rgb, const float* vis2, const PassOutPtrs& out,
+                             int n_fine, float* z_fine_out, cudaStream_t s) {
+  if (n_rays == 0) return cudaSuccess;
+  const unsigned grid = (unsigned)((n_rays + 3) / 4);
+  const size_t smem = z_fine_out ? 4 * resample_scratch_floats(S, n_fine) * sizeof(float) : 0;
+  const int spl = (S + 31) / 32;
+#define VIPNERF_LAUNCH_COMPOSITE(SPL)                                                                          \
+  k_composite<SPL><<<grid, 128, smem, s>>>(rp, fl, n_rays, S, z, sigma, rgb, vis2, out, n_fine, z_fine_out)
+  if (spl <= 2) VIPNERF_LAUNCH_COMPOSITE(2);
+  else if (spl <= 6) VIPNERF_LAUNCH_COMPOSITE(6);
+  else VIPNERF_LAUNCH_COMPOSITE(8);
+#undef VIPNERF_LAUNCH_COMPOSITE
+  return cudaGetLastError();
+}
+
+}  // namespace vipnerf
