@@ -31,8 +31,8 @@ PER_RAY = ('rgb', 'acc', 'depth', 'depth_var', 'depth_ndc', 'depth_var_ndc', 'vi
 @pytest.mark.parametrize('scene', ['fern', 'dtu'])
 def test_fp32_render_matches_reference_golden_retraw(scene, built_library):
     """PRECISION_FP32, retraw + secondary views, 64 rays, every output key of the reference.
-    Tolerance: 1e-4 relative (north star) on the per-ray maps; the per-sample arrays downstream of the
-    re-sampling discontinuities are compared at the 99.9th percentile."""
+    Tolerance: 1e-4 relative (north star), max-norm, on every per-ray map and every coarse array; the
+    per-sample fine arrays are allowed <= 3 samples per ray above 1e-4 (see comment below)."""
     inputs, golden = split_io(load_npz(f'render_{scene}_retraw64.npz'))
     ndc = O.SCENES[scene]['ndc']
     with torch.no_grad():
@@ -46,8 +46,13 @@ def test_fp32_render_matches_reference_golden_retraw(scene, built_library):
             err = rel_err(out[k], g)[0]
             assert err <= 1e-4, (k, err)
         else:
-            d = ((out[k].cpu() - g).abs() / g.abs().max().clamp_min(1e-30)).flatten()
-            assert torch.quantile(d, 0.999).item() <= 1e-4, (k, torch.quantile(d, 0.999).item())
+            # per-sample fine arrays: the u = 1 sample of every ray sits on the cdf-total <= 1 / denom < 1e-5
+            # discontinuity of sample_pdf (:246-258), where the reference's own CPU and CUDA builds disagree
+            # (fp64- vs fp32-accumulated cumsum); it moves one of the 192 depths by up to a bin and with it the
+            # alpha/weight of itself and its neighbour.  Everything else must agree to 1e-4.
+            d = ((out[k].cpu() - g).abs() / g.abs().max().clamp_min(1e-30)).reshape(g.shape[0], -1)
+            per_ray = 3 * (d.shape[1] // 192)
+            assert ((d > 1e-4).sum(dim=1) <= per_ray).all(), (k, (d > 1e-4).sum(dim=1).max().item())
 
 
 @pytest.mark.parametrize('scene', ['fern', 'dtu'])

@@ -243,7 +243,8 @@ int vipnerf_render_forward(const vipnerf_cfg* cfg, const vipnerf_rays* rays, int
     a.rp = rp; a.fl = fl; a.n_rays = n_rays; a.n_coarse = Nc; a.n_fine = cfg->n_fine;
     a.packed_coarse = packed_coarse; a.packed_fine = packed_fine;
     a.out_coarse = oc; a.out_fine = of;
-    a.ws_z_coarse = at(w.off_z_coarse); a.ws_z_fine = at(w.off_z_fine); a.ws_raw = at(w.off_sigma);
+    a.ws_z_coarse = at(w.off_z_coarse); a.ws_z_fine = at(w.off_z_fine);
+    a.ws_sigma = at(w.off_sigma); a.ws_rgb = at(w.off_rgb); a.ws_vis = at(w.off_vis);
     e = launch_render_fused_tc(cfg->precision, a, s);
     if (e != cudaSuccess) return fail_cuda(e, "render_fused_tc");
     return VIPNERF_OK;

@@ -55,7 +55,9 @@ struct FusedArgs {
   PassOutPtrs out_coarse, out_fine;
   float* ws_z_coarse;   // [R,Nc]      workspace
   float* ws_z_fine;     // [R,Nc+Nf]
-  float* ws_raw;        // [R,(Nc+Nf),5] sigma,r,g,b,vis of the pass in flight (reused coarse -> fine)
+  float* ws_sigma;      // [R,Nc+Nf]   network outputs of the pass in flight (reused coarse -> fine)
+  float* ws_rgb;        // [R,Nc+Nf,3]
+  float* ws_vis;        // [R,Nc+Nf]
 };
 cudaError_t launch_render_fused_tc(int precision, const FusedArgs& a, cudaStream_t s);
 

@@ -1,6 +1,668 @@
-// placeholder - replaced by the tcgen05 implementation
+// tcgen05 (5th-generation tensor core) evaluation of the radiance/visibility MLP, and the fused
+// coarse+fine render of a ray batch in ONE launch.  sm_100a only.
+//
+// Reference being replaced: VipNeRF.render_rays (src/models/VipNeRF01.py:74-171) = get_z_vals_coarse :173,
+// PositionalEncoder :416, MLP.forward :509-596, volume_rendering :331, get_z_vals_fine/sample_pdf :205-262.
+//
+// One persistent CTA per SM, 320 threads:
+//   warps 0-3  epilogue group 0  (owns tile slot 0: TMEM columns [0,256),   A buffer 0, encoding buffer 0)
+//   warps 4-7  epilogue group 1  (owns tile slot 1: TMEM columns [256,512), A buffer 1, encoding buffer 1)
+//   warp  8    weight producer   (one lane: cp.async.bulk 16 KiB weight chunk images -> 4-stage smem ring)
+//   warp  9    MMA issuer        (one lane: tcgen05.mma M=128 N=128 K=16, bf16 x bf16 -> fp32 in TMEM)
+// A "tile" is 128 consecutive sample points (rows).  A row's activations live in shared memory as bf16 in the
+// canonical K-major SWIZZLE_128B layout (four 16 KiB k-blocks of 128 rows x 64 columns); the accumulator of a
+// layer lives in the slot's 256 TMEM columns.  Per layer: the MMA warp streams the layer's weight chunks
+// against the slot's A buffer; when the last MMA retires (tcgen05.commit -> d_ready) the slot's epilogue group
+// pulls the accumulator with tcgen05.ld, adds bias, applies ReLU, rounds to bf16 and overwrites the A buffer in
+// place (the MMAs that read it have completed), then signals a_ready.  Two slots ping-pong so the tensor pipe
+// works on one tile while the other tile's epilogue runs on the CUDA cores.
+// The sample points, their sinusoidal encodings, the density / colour / visibility heads, and (fused kernel)
+// alpha compositing and hierarchical re-sampling are all done by the epilogue groups, so no per-sample
+// intermediate other than the 5 network outputs per sample leaves the SM.
+//
+// BF16X3 mode (parity mode): every operand is split x = hi + lo (both bf16) and each product is evaluated as
+// hi*hi + lo*hi + hi*lo in the fp32 accumulator (3 MMAs).  Slot 1's buffers hold the lo parts, so only one
+// tile is in flight.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <mutex>
+
 #include "kernels.h"
+#include "layout.cuh"
+
 namespace vipnerf {
-cudaError_t launch_mlp_tc(int, const RayPtrs&, const RenderFlags&, int64_t, int, const float*, const void*, float*, float*, float*, cudaStream_t) { return cudaErrorNotSupported; }
-cudaError_t launch_render_fused_tc(int, const FusedArgs&, cudaStream_t) { return cudaErrorNotSupported; }
+namespace {
+
+constexpr int kTile = 128;
+constexpr int kStages = 4;
+constexpr int kNumThreads = 320;
+constexpr uint32_t kABytes = 65536;
+constexpr uint32_t kKBlockBytes = 16384;
+constexpr uint32_t kOffA = 0;                 // 2 x 64 KiB
+constexpr uint32_t kOffPe = 131072;           // 2 x 16 KiB
+constexpr uint32_t kOffW = 163840;            // 4 x 16 KiB
+constexpr uint32_t kOffTail = 229376;
+constexpr uint32_t kOffBar = kOffTail;        // 12 mbarriers
+constexpr uint32_t kOffTmemPtr = kOffTail + 128;
+constexpr uint32_t kOffVb = kOffTail + 256;   // [2 slots][2 rays][128] fp32: view-direction part of M9 + bias
+constexpr uint32_t kOffPev = kOffVb + 2048;   // [2 slots][2 rays][32]  fp32: view-direction encodings
+constexpr uint32_t kSmemBytes = kOffPev + 512;
+static_assert(kSmemBytes <= 232448, "exceeds the 227 KiB per-CTA shared memory limit");
+
+enum { kBarWFull = 0, kBarWEmpty = 4, kBarAReady = 8, kBarDReady = 10 };
+
+// tcgen05 instruction descriptor: D=F32, A=B=BF16, both K-major, N=128, M=128 (cute::UMMA::InstrDescriptor bits:
+// c_format[4,6)=1, a_format[7,10)=1, b_format[10,13)=1, n_dim[17,23)=N>>3, m_dim[24,29)=M>>4)
+constexpr uint32_t kInstrDesc = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+
+constexpr long long kTimeoutCycles = 4000000000ll;  // ~2 s: a protocol bug traps instead of hanging the GPU
+
+// ------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __noinline__ void mbar_timeout(uint32_t bar, uint32_t parity) {
+  printf("vipnerf: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x,
+         (bar - kOffBar) / 8 % 16, parity);
+  __trap();
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > kTimeoutCycles) mbar_timeout(bar, parity);
+  }
+}
+__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void group_sync(int group) {  // named barrier over one epilogue group (128 threads)
+  asm volatile("bar.sync %0, 128;" ::"r"(group + 1) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(kInstrDesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address >> 4 in
+// bits [0,14), LBO (ignored for swizzled K-major) = 1 in [16,30), SBO = 1024 B (8 rows x 128 B) in [32,46),
+// version 1 in [46,48), layout SWIZZLE_128B = 2 in [61,64).
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
+         (2ull << 61);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&p);
+}
+// residual of a packed bf16 pair: (lo, hi) - float(bf16(lo, hi)), packed to bf16 again
+__device__ __forceinline__ uint32_t pack_bf16_residual(float lo, float hi, uint32_t packed) {
+  const float rlo = lo - __uint_as_float(packed << 16);
+  const float rhi = hi - __uint_as_float(packed & 0xFFFF0000u);
+  return pack_bf16(rlo, rhi);
+}
+__device__ __forceinline__ float sigmoidf(float x) { return 1.f / (1.f + expf(-x)); }
+
+// ------------------------------------------------------------------------------------------ parameters
+struct PassDesc {
+  float* z;               // [R,S] sample depths: read, or (fused coarse pass) written by the encoding stage
+  const uint8_t* packed;  // packed weights of this pass's MLP
+  float* sigma;           // [R,S]   network outputs of the pass
+  float* rgb;             // [R,S,3]
+  float* vis;             // [R,S]
+  int64_t n_points;       // R*S
+  int S;
+  int compute_z;          // 1: z = get_z_vals_coarse(near, far) is generated here
+};
+
+struct TcParams {
+  RayPtrs rp;
+  RenderFlags fl;
+  PassDesc pass[2];
+  PassOutPtrs out[2];
+  int64_t n_rays;
+  int64_t n_units;  // staged: tiles of pass 0;  fused: ray pairs
+  int n_fine;
+  int has_fine;
+};
+
+// Work of one tile slot (sg = global slot index over the whole grid): item i -> (pass, tile)
+template <bool kFused>
+struct WorkList {
+  int64_t first, stride;
+  int n_first_pass;  // fused: ray pairs of this slot;  staged: tiles
+  int n_items;
+  __device__ WorkList(const TcParams& p, int sg, int n_slots) {
+    if (kFused) {
+      const int64_t per = (p.n_units + n_slots - 1) / n_slots;
+      first = (int64_t)sg * per;
+      stride = 1;
+      int64_t cnt = p.n_units - first;
+      cnt = cnt < 0 ? 0 : (cnt > per ? per : cnt);
+      n_first_pass = (int)cnt;
+      n_items = (int)cnt * (p.has_fine ? 4 : 1);
+    } else {
+      first = sg;
+      stride = n_slots;
+      n_first_pass = first < p.n_units ? (int)((p.n_units - first + stride - 1) / stride) : 0;
+      n_items = n_first_pass;
+    }
+  }
+  __device__ __forceinline__ int pass_of(int i) const { return kFused && i >= n_first_pass ? 1 : 0; }
+  __device__ __forceinline__ int64_t tile_of(int i) const {
+    if (!kFused) return first + (int64_t)i * stride;
+    if (i < n_first_pass) return first + i;
+    const int j = i - n_first_pass;
+    return 3 * (first + j / 3) + j % 3;
+  }
+};
+
+// ------------------------------------------------------------------------------------------ epilogue pieces
+// Row `row` of the slot's encoding buffer <- bf16(gamma(point)), 64 columns (63 + zero pad).
+template <bool kSplit3>
+__device__ __forceinline__ void write_point_encoding(uint8_t* smem, int slot, int row, float x, float y, float z) {
+  float v[64];
+  v[0] = x; v[1] = y; v[2] = z;
+  const float p[3] = {x, y, z};
+#pragma unroll
+  for (int k = 0; k < kLPts; ++k) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      float s, c;
+      sincosf(p[a] * (float)(1 << k), &s, &c);  // exact power-of-two scaling: same argument as the reference
+      v[3 + 6 * k + a] = s;
+      v[6 + 6 * k + a] = c;
+    }
+  }
+  v[63] = 0.f;
+  const uint32_t hi_base = smem_u32(smem + kOffPe + (kSplit3 ? 0 : slot) * kKBlockBytes) + row * 128;
+  const uint32_t lo_base = smem_u32(smem + kOffPe + kKBlockBytes) + row * 128;
+#pragma unroll
+  for (int ch = 0; ch < 8; ++ch) {
+    uint32_t w[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) w[q] = pack_bf16(v[8 * ch + 2 * q], v[8 * ch + 2 * q + 1]);
+    const uint32_t off = (uint32_t)((ch ^ (row & 7)) << 4);
+    st_shared_v4(hi_base + off, w[0], w[1], w[2], w[3]);
+    if (kSplit3) {
+      uint32_t r[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) r[q] = pack_bf16_residual(v[8 * ch + 2 * q], v[8 * ch + 2 * q + 1], w[q]);
+      st_shared_v4(lo_base + off, r[0], r[1], r[2], r[3]);
+    }
+  }
+}
+
+// One trunk / feature layer epilogue for one row: accumulator (256 fp32 TMEM columns) -> +bias (-> ReLU) -> bf16
+// -> A buffer (in place).  kSigma additionally accumulates the density head on the fp32 activations.
+template <bool kSplit3, bool kRelu, bool kSigma>
+__device__ __forceinline__ float layer_epilogue(uint8_t* smem, int slot, int row, uint32_t taddr,
+                                                const float* __restrict__ bias, const float* __restrict__ w_sigma) {
+  float sigma_acc = 0.f;
+  const uint32_t hi_base = smem_u32(smem + kOffA + (kSplit3 ? 0 : slot) * kABytes) + row * 128;
+  const uint32_t lo_base = smem_u32(smem + kOffA + kABytes) + row * 128;
+#pragma unroll 1
+  for (int cb = 0; cb < 8; ++cb) {
+    uint32_t v[32];
+    tmem_ld32(taddr + cb * 32, v);
+    float b[32];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(bias + cb * 32) + q);
+      b[4 * q] = t.x; b[4 * q + 1] = t.y; b[4 * q + 2] = t.z; b[4 * q + 3] = t.w;
+    }
+    tmem_ld_wait();
+    float h[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      h[j] = __uint_as_float(v[j]) + b[j];
+      if (kRelu) h[j] = fmaxf(h[j], 0.f);
+    }
+    if (kSigma) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(w_sigma + cb * 32) + q);
+        sigma_acc = fmaf(h[4 * q], t.x, sigma_acc);
+        sigma_acc = fmaf(h[4 * q + 1], t.y, sigma_acc);
+        sigma_acc = fmaf(h[4 * q + 2], t.z, sigma_acc);
+        sigma_acc = fmaf(h[4 * q + 3], t.w, sigma_acc);
+      }
+    }
+    const uint32_t kb_off = (uint32_t)(cb >> 1) * kKBlockBytes;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int ch = (cb & 1) * 4 + j;
+      uint32_t w[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) w[q] = pack_bf16(h[8 * j + 2 * q], h[8 * j + 2 * q + 1]);
+      const uint32_t off = kb_off + (uint32_t)((ch ^ (row & 7)) << 4);
+      st_shared_v4(hi_base + off, w[0], w[1], w[2], w[3]);
+      if (kSplit3) {
+        uint32_t r[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) r[q] = pack_bf16_residual(h[8 * j + 2 * q], h[8 * j + 2 * q + 1], w[q]);
+        st_shared_v4(lo_base + off, r[0], r[1], r[2], r[3]);
+      }
+    }
+  }
+  return sigma_acc;
+}
+
+// M9 epilogue for one row: relu(acc + (bias + view-direction part)) . views_output_linear -> 4 logits
+__device__ __forceinline__ void view_epilogue(uint32_t taddr, const float* vb_row, const float* __restrict__ w_out,
+                                              float (&o)[4]) {
+  o[0] = o[1] = o[2] = o[3] = 0.f;
+#pragma unroll 1
+  for (int cb = 0; cb < 4; ++cb) {
+    uint32_t v[32];
+    tmem_ld32(taddr + cb * 32, v);
+    float b[32];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 t = *reinterpret_cast<const float4*>(vb_row + cb * 32 + 4 * q);
+      b[4 * q] = t.x; b[4 * q + 1] = t.y; b[4 * q + 2] = t.z; b[4 * q + 3] = t.w;
+    }
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float h = fmaxf(__uint_as_float(v[j]) + b[j], 0.f);
+      const float4 w = __ldg(reinterpret_cast<const float4*>(w_out) + cb * 32 + j);
+      o[0] = fmaf(h, w.x, o[0]);
+      o[1] = fmaf(h, w.y, o[1]);
+      o[2] = fmaf(h, w.z, o[2]);
+      o[3] = fmaf(h, w.w, o[3]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ the kernel
+template <bool kSplit3, bool kFused>
+__global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  constexpr int kSlots = kSplit3 ? 1 : 2;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar0 = smem_u32(smem + kOffBar);
+  auto bar = [&](int idx) { return bar0 + 8u * idx; };
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + kOffTmemPtr);
+
+  if (threadIdx.x == 0) {
+    if ((smem_u32(smem) & 1023u) != 0) {
+      printf("vipnerf: dynamic shared memory base is not 1024-byte aligned\n");
+      __trap();
+    }
+    for (int s = 0; s < kStages; ++s) { mbar_init(bar(kBarWFull + s), 1); mbar_init(bar(kBarWEmpty + s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(bar(kBarAReady + s), 128); mbar_init(bar(kBarDReady + s), 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 9) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem + kOffTmemPtr)),
+                 "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  const int n_slots_total = gridDim.x * kSlots;
+
+  if (warp < 8) {
+    // =================================================================== epilogue groups
+    const int group = warp >> 2;
+    if (group < kSlots) {
+      const int slot = group;
+      const int row = threadIdx.x & 127;
+      const WorkList<kFused> work(p, blockIdx.x * kSlots + slot, n_slots_total);
+      const uint32_t taddr = tmem_base + (uint32_t)(slot * 256) + ((uint32_t)((warp & 3) * 32) << 16);
+      float* vb = reinterpret_cast<float*>(smem + kOffVb) + slot * 256;
+      float* pev = reinterpret_cast<float*>(smem + kOffPev) + slot * 64;
+      uint32_t d_parity = 0;
+      for (int it = 0; it < work.n_items; ++it) {
+        const int pi = work.pass_of(it);
+        const PassDesc& ps = p.pass[pi];
+        const int64_t tile = work.tile_of(it);
+        const int64_t pg = tile * kTile + row;
+        const bool valid = pg < ps.n_points;
+        const int64_t pc = valid ? pg : ps.n_points - 1;
+        const int64_t ray = pc / ps.S;
+        const int64_t ray_first = min((tile * kTile) / ps.S, p.n_rays - 1);
+        const float* small = reinterpret_cast<const float*>(ps.packed);
+        // ---- sample position and its encoding (VipNeRF01.py:105-107, :173-203, :439-448)
+        float zv;
+        if (ps.compute_z) {
+          const int s = (int)(pc - ray * ps.S);
+          zv = coarse_z_at(p.rp.near[ray], p.rp.far[ray], p.rp.t_vals, s, ps.S, p.fl.lindisp,
+                           p.rp.t_rand ? p.rp.t_rand + ray * ps.S : nullptr);
+          if (valid) ps.z[pg] = zv;
+        } else {
+          zv = ps.z[pc];
+        }
+        const float px = fadd(p.rp.pts_o[3 * ray + 0], fmul(p.rp.pts_d[3 * ray + 0], zv));
+        const float py = fadd(p.rp.pts_o[3 * ray + 1], fmul(p.rp.pts_d[3 * ray + 1], zv));
+        const float pz = fadd(p.rp.pts_o[3 * ray + 2], fmul(p.rp.pts_d[3 * ray + 2], zv));
+        write_point_encoding<kSplit3>(smem, slot, row, px, py, pz);
+        fence_proxy_async();
+        tc_fence_before();  // orders the previous tile's tcgen05.ld before the MMA that overwrites the slot
+        mbar_arrive(bar(kBarAReady + slot));
+        // ---- view-direction part of M9 for the (at most two) rays of this tile, in fp32
+        if (row < 2 * kEncView) {
+          const int rs = row / kEncView, j = row % kEncView;
+          const int64_t r2 = min(ray_first + rs, p.n_rays - 1);
+          float val;
+          if (j < 3) {
+            val = p.rp.view_dirs[3 * r2 + j];
+          } else {
+            const int k = (j - 3) / 6, r6 = (j - 3) % 6;
+            const float a = p.rp.view_dirs[3 * r2 + r6 % 3] * (float)(1 << k);
+            val = r6 < 3 ? sinf(a) : cosf(a);
+          }
+          pev[rs * 32 + j] = val;
+        }
+        group_sync(group);
+        {
+          const float* wvd = small + kOffWViewDir;
+          float a0 = small[kOffBiasViews + row], a1 = a0;
+#pragma unroll 1
+          for (int j = 0; j < kEncView; ++j) {
+            const float w = __ldg(wvd + j * 128 + row);
+            a0 = fmaf(w, pev[j], a0);
+            a1 = fmaf(w, pev[32 + j], a1);
+          }
+          vb[row] = a0;
+          vb[128 + row] = a1;
+        }
+        group_sync(group);
+
+        float sigma_lin = 0.f;
+#pragma unroll 1
+        for (int l = 0; l < 9; ++l) {
+          mbar_wait(bar(kBarDReady + slot), d_parity);
+          d_parity ^= 1;
+          tc_fence_after();
+          const float* bias = small + kOffBias + l * 256;
+          if (l == 7) sigma_lin = layer_epilogue<kSplit3, true, true>(smem, slot, row, taddr, bias, small + kOffWSigma);
+          else if (l == 8) layer_epilogue<kSplit3, false, false>(smem, slot, row, taddr, bias, nullptr);
+          else layer_epilogue<kSplit3, true, false>(smem, slot, row, taddr, bias, nullptr);
+          fence_proxy_async();
+          tc_fence_before();
+          mbar_arrive(bar(kBarAReady + slot));
+        }
+        mbar_wait(bar(kBarDReady + slot), d_parity);
+        d_parity ^= 1;
+        tc_fence_after();
+        float o[4];
+        view_epilogue(taddr, vb + (int)(ray - ray_first) * 128, small + kOffWOut, o);
+        if (valid) {
+          ps.sigma[pg] = fmaxf(sigma_lin + small[kOffBSigma], 0.f);  // :546-553 (eval: no noise)
+          ps.rgb[3 * pg + 0] = sigmoidf(o[0] + small[kOffBOut + 0]);   // :585-594
+          ps.rgb[3 * pg + 1] = sigmoidf(o[1] + small[kOffBOut + 1]);
+          ps.rgb[3 * pg + 2] = sigmoidf(o[2] + small[kOffBOut + 2]);
+          ps.vis[pg] = sigmoidf(o[3] + small[kOffBOut + 3]);
+        }
+        if (kFused) {
+          // ---- per-ray stages on the two rays a pair of tiles completes (one warp per ray)
+          const bool pair_done = pi == 0 || (tile % 3) == 2;
+          if (pair_done) {
+            group_sync(group);  // the rays' network outputs (global) are complete and visible to the group
+            const int64_t pair = pi == 0 ? tile : tile / 3;
+            const int wq = warp & 3;
+            const int64_t r = 2 * pair + wq;
+            if (wq < 2 && r < p.n_rays) {
+              RayConsts rc;
+              rc.dnorm = vec3_norm(p.rp.pts_d[3 * r], p.rp.pts_d[3 * r + 1], p.rp.pts_d[3 * r + 2]);
+              rc.oz = p.rp.rays_o[3 * r + 2];
+              rc.dz = p.rp.rays_d[3 * r + 2];
+              if (pi == 0) {
+                float z_reg[2], w_reg[2];
+                composite_ray<2>(lane, 64, ps.z + r * 64, ps.sigma + r * 64, ps.rgb + r * 192, nullptr, 0, p.fl.ndc,
+                                 p.fl.white_bkgd, rc, p.out[0], r, z_reg, w_reg);
+                if (p.has_fine) {
+                  // the slot's A buffer is dead until the next tile's first epilogue: use it as scratch
+                  float* scratch = reinterpret_cast<float*>(smem + kOffA + slot * kABytes) + wq * 1024;
+                  const float* u = p.rp.u_rand ? p.rp.u_rand + r * p.n_fine : p.rp.u_vals;
+                  resample_ray<2>(lane, 64, p.n_fine, z_reg, w_reg, u, p.rp.u_rand == nullptr, scratch,
+                                  p.pass[1].z + r * (64 + p.n_fine));
+                }
+              } else {
+                float z_reg[6], w_reg[6];
+                composite_ray<6>(lane, 192, ps.z + r * 192, ps.sigma + r * 192, ps.rgb + r * 576, nullptr, 0, p.fl.ndc,
+                                 p.fl.white_bkgd, rc, p.out[1], r, z_reg, w_reg);
+              }
+            }
+            group_sync(group);  // z_fine (global) visible before the group encodes fine tiles
+          }
+        }
+      }
+      tc_fence_before();
+    }
+  } else if (warp == 8) {
+    // =================================================================== weight producer
+    if (lane == 0) {
+      WorkList<kFused> work0(p, blockIdx.x * kSlots + 0, n_slots_total);
+      WorkList<kFused> work1(p, blockIdx.x * kSlots + (kSlots - 1), n_slots_total);
+      const int n_max = max(work0.n_items, kSlots > 1 ? work1.n_items : 0);
+      uint32_t q = 0;
+      for (int it = 0; it < n_max; ++it) {
+        for (int l = 0; l < kNumMatLayers; ++l) {
+          for (int s = 0; s < kSlots; ++s) {
+            const WorkList<kFused>& w = s == 0 ? work0 : work1;
+            if (it >= w.n_items) continue;
+            const uint8_t* src = p.pass[w.pass_of(it)].packed + kSmallBytes +
+                                 (size_t)tc_layer_chunk_offset(l) * kChunkBytes * (kSplit3 ? 2 : 1);
+            const int n_chunks = layer_chunks(l) * (kSplit3 ? 2 : 1);
+            for (int c = 0; c < n_chunks; ++c, ++q) {
+              const uint32_t stage = q % kStages;
+              mbar_wait(bar(kBarWEmpty + stage), ((q / kStages) & 1) ^ 1);
+              mbar_arrive_expect_tx(bar(kBarWFull + stage), kChunkBytes);
+              bulk_copy_g2s(smem_u32(smem + kOffW + stage * kChunkBytes), src + (size_t)c * kChunkBytes, kChunkBytes,
+                            bar(kBarWFull + stage));
+            }
+          }
+        }
+      }
+    }
+  } else {
+    // =================================================================== MMA issuer (warp 9)
+    WorkList<kFused> work0(p, blockIdx.x * kSlots + 0, n_slots_total);
+    WorkList<kFused> work1(p, blockIdx.x * kSlots + (kSlots - 1), n_slots_total);
+    const int n_max = max(work0.n_items, kSlots > 1 ? work1.n_items : 0);
+    uint32_t q = 0;
+    uint32_t a_parity[2] = {0, 0};
+    const uint32_t a_base = smem_u32(smem + kOffA), pe_base = smem_u32(smem + kOffPe), w_base = smem_u32(smem + kOffW);
+    for (int it = 0; it < n_max; ++it) {
+      for (int l = 0; l < kNumMatLayers; ++l) {
+        for (int s = 0; s < kSlots; ++s) {
+          const WorkList<kFused>& w = s == 0 ? work0 : work1;
+          if (it >= w.n_items) continue;
+          mbar_wait(bar(kBarAReady + s), a_parity[s]);
+          a_parity[s] ^= 1;
+          tc_fence_after();
+          const int n_kc = layer_k(l) / 64, n_nh = layer_n(l) / 128;
+          for (int kc = 0; kc < n_kc; ++kc) {
+            // A operand k-block: encoding buffer for M0 and for the first k-block of M5, else the A buffer
+            uint32_t a_hi, a_lo;
+            if (l == 0 || (l == 5 && kc == 0)) {
+              a_hi = pe_base + (kSplit3 ? 0 : s) * kKBlockBytes;
+              a_lo = pe_base + kKBlockBytes;
+            } else {
+              const int kb = l == 5 ? kc - 1 : kc;
+              a_hi = a_base + (kSplit3 ? 0 : s) * kABytes + kb * kKBlockBytes;
+              a_lo = a_base + kABytes + kb * kKBlockBytes;
+            }
+            for (int nh = 0; nh < n_nh; ++nh) {
+              const uint32_t d_tmem = tmem_base + (uint32_t)(s * 256 + nh * 128);
+              for (int part = 0; part < (kSplit3 ? 2 : 1); ++part, ++q) {
+                const uint32_t stage = q % kStages;
+                mbar_wait(bar(kBarWFull + stage), (q / kStages) & 1);
+                tc_fence_after();
+                if (lane == 0) {
+                  const uint32_t b_addr = w_base + stage * kChunkBytes;
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) {
+                    const uint64_t bd = make_desc(b_addr + k * 32);
+                    if (part == 0) {
+                      umma_bf16(d_tmem, make_desc(a_hi + k * 32), bd, (kc | k) != 0 ? 1u : 0u);
+                      if (kSplit3) umma_bf16(d_tmem, make_desc(a_lo + k * 32), bd, 1u);
+                    } else {
+                      umma_bf16(d_tmem, make_desc(a_hi + k * 32), bd, 1u);  // hi x W_lo
+                    }
+                  }
+                  umma_commit(bar(kBarWEmpty + stage));
+                }
+                __syncwarp();
+              }
+            }
+          }
+          if (lane == 0) umma_commit(bar(kBarDReady + s));
+          __syncwarp();
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host side
+std::mutex g_attr_mutex;
+int g_sm_count[64] = {0};
+bool g_attr_set[64][4] = {{false}};
+
+cudaError_t device_sm_count(int* out) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> lock(g_attr_mutex);
+  if (dev < 64 && g_sm_count[dev] > 0) { *out = g_sm_count[dev]; return cudaSuccess; }
+  int n = 0;
+  e = cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 64) g_sm_count[dev] = n;
+  *out = n;
+  return cudaSuccess;
+}
+
+template <bool kSplit3, bool kFused>
+cudaError_t launch(const TcParams& p, int64_t units_per_cta_slot_total, cudaStream_t s) {
+  int dev = 0, sms = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if ((e = device_sm_count(&sms)) != cudaSuccess) return e;
+  {
+    std::lock_guard<std::mutex> lock(g_attr_mutex);
+    const int variant = (kSplit3 ? 2 : 0) + (kFused ? 1 : 0);
+    if (dev >= 64 || !g_attr_set[dev][variant]) {
+      e = cudaFuncSetAttribute(k_render_tc<kSplit3, kFused>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+      if (e != cudaSuccess) return e;
+      if (dev < 64) g_attr_set[dev][variant] = true;
+    }
+  }
+  constexpr int kSlots = kSplit3 ? 1 : 2;
+  int64_t grid = (units_per_cta_slot_total + kSlots - 1) / kSlots;
+  if (grid > sms) grid = sms;
+  if (grid < 1) return cudaSuccess;
+  k_render_tc<kSplit3, kFused><<<(unsigned)grid, kNumThreads, kSmemBytes, s>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t launch_mlp_tc(int precision, const RayPtrs& rp, const RenderFlags& fl, int64_t n_rays, int S,
+                          const float* z, const void* packed, float* sigma, float* rgb, float* vis,
+                          cudaStream_t s) {
+  TcParams p{};
+  p.rp = rp;
+  p.fl = fl;
+  p.n_rays = n_rays;
+  p.pass[0].z = const_cast<float*>(z);
+  p.pass[0].packed = static_cast<const uint8_t*>(packed);
+  p.pass[0].sigma = sigma;
+  p.pass[0].rgb = rgb;
+  p.pass[0].vis = vis;
+  p.pass[0].n_points = n_rays * S;
+  p.pass[0].S = S;
+  p.pass[0].compute_z = 0;
+  p.pass[1] = p.pass[0];
+  p.n_units = (p.pass[0].n_points + kTile - 1) / kTile;
+  if (p.n_units == 0) return cudaSuccess;
+  if (precision == VIPNERF_PRECISION_BF16X3) return launch<true, false>(p, p.n_units, s);
+  return launch<false, false>(p, p.n_units, s);
+}
+
+cudaError_t launch_render_fused_tc(int precision, const FusedArgs& a, cudaStream_t s) {
+  if (a.n_rays == 0) return cudaSuccess;
+  TcParams p{};
+  p.rp = a.rp;
+  p.fl = a.fl;
+  p.n_rays = a.n_rays;
+  p.n_fine = a.n_fine;
+  p.has_fine = a.n_fine > 0;
+  const int Sf = a.n_coarse + a.n_fine;
+  for (int pi = 0; pi < 2; ++pi) {
+    const PassOutPtrs& o = pi ? a.out_fine : a.out_coarse;
+    PassDesc& d = p.pass[pi];
+    d.S = pi ? Sf : a.n_coarse;
+    d.n_points = a.n_rays * d.S;
+    d.packed = static_cast<const uint8_t*>(pi ? a.packed_fine : a.packed_coarse);
+    d.z = pi ? (o.z_vals ? o.z_vals : a.ws_z_fine) : (o.z_vals ? o.z_vals : a.ws_z_coarse);
+    d.sigma = o.raw_sigma ? o.raw_sigma : a.ws_sigma;  // workspace is shared by both passes
+    d.rgb = o.raw_rgb ? o.raw_rgb : a.ws_rgb;
+    d.vis = o.raw_visibility ? o.raw_visibility : a.ws_vis;
+    d.compute_z = pi == 0;
+    p.out[pi] = o;
+    p.out[pi].z_vals = nullptr;  // depths are produced in place
+  }
+  if (!p.has_fine) p.pass[1] = p.pass[0];
+  p.n_units = (a.n_rays + 1) / 2;
+  if (precision == VIPNERF_PRECISION_BF16X3) return launch<true, true>(p, p.n_units, s);
+  return launch<false, true>(p, p.n_units, s);
+}
+
+}  // namespace vipnerf
