@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""Benchmark of the ViP-NeRF volumetric render path (BASELINE.json metric: rays/sec, coarse+fine 64+128).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision bf16|bf16x3|fp32]
+
+A "step" is one pass of the hot path over one 4096-ray batch (the reference's `chunk`) of the workload
+BASELINE.json quotes the metric on: LLFF 'fern' camera (NDC), 64 coarse + 128 fine samples, visibility head
+on, eval forward (retraw=False, sec_views_vis=False).  Synthetic rays from the real fern intrinsics,
+random-init weights of the reference architecture.
+
+Prints ONE JSON line (rank 0).  `value` = whole-job rays/s with inputs resident in HBM (one fused kernel per
+step, CUDA events on the launching stream, L2 flushed between steps, max over ranks); `e2e` = the same metric
+through the reference-facing plugin (`model(batch)`) with pinned HOST inputs copied in and the rendered maps
+copied back inside the timed region (+ the single NCCL gather when N > 1); `roofline` = algorithmic FLOPs of
+the fused kernel / its measured duration against the measured dense-bf16 peak; `cpu_baseline` = the CPU oracle
+(port of the reference's PyTorch path) on this box's host cores on a bounded sample.
+
+--impl reference times the reference's own algorithm on the host CPU (the oracle port; the reference itself is
+pure Python and is not present on the GPU box), rank 0 only.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+RAYS_PER_STEP = 4096
+FLOP_PER_RAY = 303_890_432          # 256 MLP evaluations x 1,187,072 FLOP
+METRIC = 'rays/sec (coarse+fine, 64+128 samples) at 1/2/4/8 B200; PSNR vs ref'
+WORKLOAD = "LLFF 'fern' 3 input views, 64+128 coarse/fine, visibility head on, 4096-ray batches"
+
+
+def model_configs(precision):
+    mlp = dict(num_samples=64, netdepth=8, netwidth=256, points_positional_encoding_degree=10,
+               views_positional_encoding_degree=4, use_view_dirs=True, view_dependent_rgb=True, predict_visibility=True)
+    return {'data_loader': {'ndc': True},
+            'model': dict(name='VipNeRFFused01', coarse_mlp=dict(mlp), fine_mlp=dict(mlp, num_samples=128), chunk=4096,
+                          lindisp=False, netchunk=16384, perturb=True, raw_noise_std=1.0, white_bkgd=False,
+                          precision=precision)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.isfile(path):
+        with open(path) as f:
+            d = json.load(f)
+        return {'sustained': d['bf16_tflops_sustained'], 'burst': d['bf16_tflops'], 'source': 'measured'}
+    return {'sustained': 1400.0, 'burst': 1590.0, 'source': 'fallback'}   # B200_PROFILING.md fallback
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons of one GPU while the timed region runs."""
+    FIELDS = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+              'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(index), f'--query-gpu={self.FIELDS}',
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap')
+        for row in self.rows:
+            parts = [p.strip() for p in row.split(',')]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[2:6]):
+                if val.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+def cpu_oracle_rate(n_rays, reps, threads):
+    """rays/s of the CPU oracle (port of the reference's PyTorch path) on `n_rays` rays of the workload."""
+    import torch
+    from oracle import vipnerf_oracle as O
+    torch.set_num_threads(threads)
+    sd = O.synth_state_dict(0)
+    batch = O.make_rays('fern', n_rays, seed=2)
+    best = float('inf')
+    with torch.no_grad():
+        O.render(sd, O.make_rays('fern', min(256, n_rays), seed=2), ndc=True)   # warm-up
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            O.render(sd, batch, ndc=True)
+            best = min(best, time.perf_counter() - t0)
+    return n_rays / best
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's algorithm on the host CPU (oracle port), rank 0 only."""
+    if rank != 0:
+        return
+    import torch
+    from oracle import vipnerf_oracle as O
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    sd = O.synth_state_dict(0)
+    with torch.no_grad():
+        probe = O.make_rays('fern', 256, seed=2)
+        O.render(sd, probe, ndc=True)
+        t0 = time.perf_counter()
+        O.render(sd, probe, ndc=True)
+        rate = 256 / (time.perf_counter() - t0)
+        budget_s = 90.0
+        n = int(rate * budget_s / max(1, args.steps + args.warmup))
+        n = max(256, min(RAYS_PER_STEP, (n // 256) * 256))
+        batch = O.make_rays('fern', n, seed=2)
+        for _ in range(args.warmup):
+            O.render(sd, batch, ndc=True)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            O.render(sd, batch, ndc=True)
+        total = time.perf_counter() - t0
+    value = n * args.steps / total
+    sample = f'{n} rays of the 4096-ray batch per step, fp32 torch CPU'
+    line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'rays/s', 'n_gpus': args.gpus,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * total / args.steps,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': WORKLOAD, 'rays_per_step': n, 'samples': '64+128', 'host': 'cpu'},
+            'cpu_baseline': {'value': value, 'unit': 'rays/s', 'cores': threads, 'kind': 'port', 'sample': sample},
+            'e2e': {'value': value, 'unit': 'rays/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=50)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--precision', default='bf16', choices=['bf16', 'bf16x3', 'fp32'])
+    ap.add_argument('--rays-per-step', type=int, default=RAYS_PER_STEP)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if args.gpus > 1 and world == 1:
+        # not under torchrun: launch one process per GPU ourselves
+        port = 29500 + os.getpid() % 2000
+        cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', f'--nproc-per-node={args.gpus}',
+               '--master-addr', '127.0.0.1', '--master-port', str(port), os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+
+    if args.impl == 'reference':
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from oracle import vipnerf_oracle as O                      # only for synthetic weights / rays + cpu_baseline
+    from vipnerf_b200 import renderpath, sharding
+    from vipnerf_b200.ModelFactory import get_model
+
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py --impl ours needs a CUDA device (no CPU fallback)')
+    torch.cuda.set_device(local_rank)
+    device = torch.device('cuda', local_rank)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=device)
+
+    R = args.rays_per_step
+    precision = args.precision
+    model = get_model(model_configs(precision), None)
+    model.load_state_dict(O.synth_state_dict(0))
+    model = model.to(device).eval()
+    # weak scaling: every rank renders its own 4096-ray batch of the frame (different pixels per rank)
+    host_batch = {k: v.pin_memory() for k, v in O.make_rays('fern', R, seed=2 + rank).items()}
+    dev_batch = {k: v.to(device) for k, v in host_batch.items()}
+    packed_c = model._packed_weights('coarse', precision, device)
+    packed_f = model._packed_weights('fine', precision, device)
+    eval_keys = renderpath.pass_keys(True, False, 0)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)   # > 126 MB L2
+
+    def hot_path():
+        return renderpath.render_rays(dev_batch, packed_c, packed_f, ndc=True, precision=precision, keys=eval_keys)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ------------------------------------------------------------------ value: kernel path, inputs in HBM
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            hot_path()
+        barrier()
+        sampler = ClockSampler(local_rank)
+        starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+        ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+        for i in range(args.steps):
+            flush.zero_()                       # evict L2 between timed iterations (untimed)
+            starts[i].record()
+            hot_path()
+            ends[i].record()
+        barrier()
+        step_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
+        clocks = sampler.stop()
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = total_ms.item()
+    value = world * R * args.steps / (total_ms * 1e-3)
+
+    # ------------------------------------------------------------------ e2e: plugin call with host buffers
+    out_keys = ('rgb_fine', 'depth_fine', 'depth_var_fine', 'depth_ndc_fine', 'depth_var_ndc_fine')
+    host_out = {k: torch.empty((R, 3) if k == 'rgb_fine' else (R,), dtype=torch.float32).pin_memory() for k in out_keys}
+    h2d = sum(v.numel() * 4 for v in host_batch.values())
+    d2h = sum(v.numel() * 4 for v in host_out.values())
+
+    def e2e_step():
+        batch = {k: v.to(device, non_blocking=True) for k, v in host_batch.items()}
+        out = model(batch)
+        maps = {k: out[k] for k in out_keys}
+        if world > 1:   # the single collective of the path: gather the rendered pixels on rank 0
+            gathered = sharding.gather_outputs(maps, world * R, None, 0)
+            if rank == 0:
+                for k in out_keys:
+                    host_out[k].copy_(gathered[k][:R], non_blocking=True)
+        else:
+            for k in out_keys:
+                host_out[k].copy_(maps[k], non_blocking=True)
+
+    e2e_steps = args.steps
+    with torch.no_grad():
+        for _ in range(3):
+            e2e_step()
+        barrier()
+        e_total = 0.0
+        for _ in range(e2e_steps):
+            flush.zero_()
+            torch.cuda.synchronize()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            e2e_step()
+            e.record()
+            torch.cuda.synchronize()
+            e_total += s.elapsed_time(e)
+        barrier()
+    e_ms = torch.tensor([e_total], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(e_ms, op=dist.ReduceOp.MAX)
+    e2e_value = world * R * e2e_steps / (e_ms.item() * 1e-3)
+
+    if rank == 0:
+        peaks = measured_peaks()
+        kernel_ms = statistics.mean(step_ms)
+        achieved = R * FLOP_PER_RAY / (kernel_ms * 1e-3) / 1e12
+        traffic = None
+        tpath = os.path.join(ROOT, 'profiles', 'r01_traffic.json')
+        if os.path.isfile(tpath):
+            with open(tpath) as f:
+                traffic = json.load(f).get(precision)
+        line = {
+            'metric': METRIC, 'value': value, 'unit': 'rays/s', 'n_gpus': world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': total_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': {'bf16': 'bf16', 'bf16x3': 'bf16x3', 'fp32': 'f32'}[precision],
+            'data': 'synthetic',
+            'config': {'workload': WORKLOAD, 'rays_per_step_per_gpu': R, 'samples': '64+128', 'ndc': True,
+                       'precision': precision, 'kernel': 'k_render_tc (fused coarse+fine, 1 launch/step)'
+                       if precision != 'fp32' else 'staged fp32 kernels (5 launches/step)',
+                       'l2': 'flushed between timed iterations (256 MiB memset, untimed)',
+                       'weights': 'random-init reference architecture, density head rescaled (oracle.synth_state_dict)'},
+            'clocks': clocks,
+            'e2e': {'value': e2e_value, 'unit': 'rays/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                    'steps': e2e_steps, 'api': 'VipNeRFFused.forward(batch) via ModelFactory.get_model'},
+            'gpu_launches': args.steps * (1 if precision != 'fp32' else 5),
+            'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': peaks['sustained'], 'unit': 'TFLOP/s',
+                         'frac': achieved / peaks['sustained'], 'traffic': traffic,
+                         'peak_kind': f"dense bf16 sustained, {peaks['source']}", 'peak_burst': peaks['burst'],
+                         'frac_of_burst': achieved / peaks['burst'], 'flop_per_ray': FLOP_PER_RAY,
+                         'kernel_ms': kernel_ms},
+        }
+        if not args.no_cpu_baseline and world == 1:
+            threads = os.cpu_count() or 1
+            n_cpu = 1024
+            rate = cpu_oracle_rate(n_cpu, 3, threads)
+            line['cpu_baseline'] = {'value': rate, 'unit': 'rays/s', 'cores': threads, 'kind': 'port',
+                                    'sample': f'{n_cpu} rays of the same workload, best of 3, fp32 torch CPU oracle'}
+        else:
+            line['cpu_baseline'] = None
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -76,6 +76,17 @@ def test_composite_white_background(built_library):
     assert rel_err(got['rgb'], ref['rgb'])[0] <= STAGE_TOL
 
 
+def _check_fine_z(z, ref):
+    """Inverse-cdf samples that land in an almost empty bin are divided by denom ~ 1e-5 (VipNeRF01.py:257-259):
+    last-ulp differences of the cdf (summation order) are amplified to ~1e-4 of the depth range there - the
+    u = 1 sample of most rays is such a sample.  So: all but <= 4 of a ray's 192 depths within 1e-5, none off by
+    more than 1e-3 (a whole bin would be 1.6e-2), median at rounding level."""
+    d = (z - ref).abs() / ref.abs().max()
+    assert ((d > STAGE_TOL).sum(dim=1) <= 4).all(), (d > STAGE_TOL).sum(dim=1).max().item()
+    assert d.max().item() <= 1e-3, d.max().item()
+    assert d.median().item() <= 1e-6
+
+
 @pytest.mark.parametrize('scene', ['fern', 'dtu'])
 def test_fine_z_teacher_forced(scene, built_library):
     """get_z_vals_fine from the oracle's coarse sigma/rgb: sorted, same multiset of coarse depths, and equal to
@@ -88,10 +99,7 @@ def test_fine_z_teacher_forced(scene, built_library):
     z = got['z_vals_fine'].cpu()
     assert z.shape == (512, 192)
     assert (z[:, 1:] >= z[:, :-1]).all()
-    span = ref['z_vals_fine'].abs().max()
-    d = ((z - ref['z_vals_fine']).abs() / span).flatten()
-    assert torch.quantile(d, 0.999).item() <= STAGE_TOL
-    assert d.max().item() <= 2e-3
+    _check_fine_z(z, ref['z_vals_fine'])
 
 
 def test_sample_pdf_edge_cases(built_library):
@@ -107,9 +115,7 @@ def test_sample_pdf_edge_cases(built_library):
     comp = O.composite(sigma, rgb, z, batch['rays_d'], False)
     ref = O.fine_z_vals(z, comp['weights'], 128)
     got = renderpath.volume_rendering(to_cuda(batch), z.cuda(), sigma.cuda(), rgb.cuda(), ndc=False, n_fine=128)
-    d = ((got['z_vals_fine'].cpu() - ref).abs() / ref.abs().max()).flatten()
-    assert torch.quantile(d, 0.999).item() <= STAGE_TOL
-    assert d.max().item() <= 2e-3
+    _check_fine_z(got['z_vals_fine'].cpu(), ref)
 
 
 def test_fine_z_random_u(built_library):
@@ -122,8 +128,7 @@ def test_fine_z_random_u(built_library):
                                       ref['raw_rgb_coarse'].cuda(), ndc=ndc, n_fine=128, u_rand=u.cuda())
     z = got['z_vals_fine'].cpu()
     assert (z[:, 1:] >= z[:, :-1]).all()
-    d = ((z - want).abs() / want.abs().max()).flatten()
-    assert torch.quantile(d, 0.999).item() <= STAGE_TOL
+    _check_fine_z(z, want)
 
 
 def test_empty_and_ragged_batches(built_library):

@@ -165,6 +165,7 @@ size_t vipnerf_workspace_bytes(const vipnerf_cfg* cfg, int64_t n_rays) {
 
 int vipnerf_coarse_z(const vipnerf_cfg* cfg, const vipnerf_rays* rays, int64_t n_rays, float* z_vals, void* stream) {
   if (int rc = check_cfg(cfg)) return rc;
+  if (n_rays == 0) return VIPNERF_OK;  // empty batch: nothing to validate (empty tensors have NULL pointers)
   RayPtrs rp{};
   if (int rc = make_ray_ptrs(cfg, rays, &rp, true, false, false)) return rc;
   if (n_rays < 0 || z_vals == nullptr) return fail(VIPNERF_EINVAL, "n_rays < 0 or z_vals NULL");
@@ -179,6 +180,7 @@ int vipnerf_mlp_forward(const vipnerf_cfg* cfg, const vipnerf_rays* rays, int64_
                         size_t workspace_bytes, void* stream) {
   (void)workspace; (void)workspace_bytes;
   if (int rc = check_cfg(cfg)) return rc;
+  if (n_rays == 0) return VIPNERF_OK;
   RayPtrs rp{};
   if (int rc = make_ray_ptrs(cfg, rays, &rp, false, false)) return rc;
   if (n_rays < 0 || n_samples < 1 || n_samples > 256) return fail(VIPNERF_EINVAL, "n_rays=%lld n_samples=%d", (long long)n_rays, n_samples);
@@ -204,6 +206,7 @@ int vipnerf_composite(const vipnerf_cfg* cfg, const vipnerf_rays* rays, int64_t 
                       const float* z_vals, const float* sigma, const float* rgb, const float* vis2,
                       const vipnerf_pass_out* out, float* z_fine_out, void* stream) {
   if (int rc = check_cfg(cfg)) return rc;
+  if (n_rays == 0) return VIPNERF_OK;
   RayPtrs rp{};
   if (int rc = make_ray_ptrs(cfg, rays, &rp, false, z_fine_out != nullptr, false)) return rc;
   if (n_rays < 0 || n_samples < 3 || n_samples > 256) return fail(VIPNERF_EINVAL, "n_rays=%lld n_samples=%d", (long long)n_rays, n_samples);
@@ -219,6 +222,7 @@ int vipnerf_render_forward(const vipnerf_cfg* cfg, const vipnerf_rays* rays, int
                            const void* packed_fine, const vipnerf_out* out, void* workspace, size_t workspace_bytes,
                            void* stream) {
   if (int rc = check_cfg(cfg)) return rc;
+  if (n_rays == 0) return VIPNERF_OK;
   RayPtrs rp{};
   if (int rc = make_ray_ptrs(cfg, rays, &rp, true, true)) return rc;
   if (n_rays < 0) return fail(VIPNERF_EINVAL, "n_rays=%lld", (long long)n_rays);
