@@ -58,49 +58,51 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons of one GPU while the timed region runs."""
-    FIELDS = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
-              'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+    """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
 
-    def __init__(self, index):
-        self.rows, self.proc = [], None
+    def __init__(self, index, period_s=0.05):
+        self.sm, self.max_mhz, self.reasons, self.error = [], None, set(), None
+        self._stop = threading.Event()
         try:
-            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(index), f'--query-gpu={self.FIELDS}',
-                                          '--format=csv,noheader,nounits', '-lms', '100'],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
-        except Exception:
-            self.proc = None
+            import pynvml
+            self.nvml = pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get('CUDA_VISIBLE_DEVICES')
+            phys = int(visible.split(',')[index]) if visible and visible.split(',')[index].isdigit() else index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+        except Exception as e:   # noqa: BLE001
+            self.error = repr(e)
+            return
+        self.period = period_s
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append(line.strip())
+    def _run(self):
+        n = self.nvml
+        names = {'hw_slowdown': 'nvmlClocksThrottleReasonHwSlowdown',
+                 'hw_thermal_slowdown': 'nvmlClocksThrottleReasonHwThermalSlowdown',
+                 'sw_thermal_slowdown': 'nvmlClocksThrottleReasonSwThermalSlowdown',
+                 'sw_power_cap': 'nvmlClocksThrottleReasonSwPowerCap'}
+        while not self._stop.is_set():
+            try:
+                self.sm.append(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                mask = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                for key, attr in names.items():
+                    if mask & getattr(n, attr, 0):
+                        self.reasons.add(key)
+            except Exception as e:   # noqa: BLE001
+                self.error = repr(e)
+                return
+            time.sleep(self.period)
 
     def stop(self):
-        if self.proc is None:
-            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap')
-        for row in self.rows:
-            parts = [p.strip() for p in row.split(',')]
-            if len(parts) < 6:
-                continue
-            try:
-                sm.append(float(parts[0]))
-                mx.append(float(parts[1]))
-            except ValueError:
-                continue
-            for name, val in zip(names, parts[2:6]):
-                if val.lower().startswith('active'):
-                    reasons.add(name)
-        return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
-                'samples': len(sm), 'reasons': sorted(reasons)}
+        if self.error is not None and not self.sm:
+            return {'sm_mhz': None, 'sm_max_mhz': self.max_mhz, 'samples': 0, 'reasons': [f'nvml: {self.error}']}
+        self._stop.set()
+        self.thread.join(timeout=2)
+        return {'sm_mhz': statistics.median(self.sm) if self.sm else None, 'sm_max_mhz': self.max_mhz,
+                'samples': len(self.sm), 'reasons': sorted(self.reasons)}
 
 
 def cpu_oracle_rate(n_rays, reps, threads):
