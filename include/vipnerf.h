@@ -145,6 +145,11 @@ int vipnerf_composite(const vipnerf_cfg* cfg, const vipnerf_rays* rays, int64_t 
                       const float* z_vals, const float* sigma, const float* rgb, const float* vis2,
                       const vipnerf_pass_out* out, float* z_fine_out, void* stream);
 
+/* --- profiling aid (not part of the reference-facing path): a device buffer of 64 uint64 that CTA 0 of every
+ * subsequent tensor-core launch fills with cycle counters of its warp roles (see tools/tc_cycle_breakdown.py);
+ * NULL switches it off.  Process-global. */
+int vipnerf_debug_set_profile_buffer(void* dev_u64x64);
+
 #ifdef __cplusplus
 }
 #endif

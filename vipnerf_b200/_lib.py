@@ -60,6 +60,7 @@ EXPORTS = {
     'vipnerf_coarse_z': (c_int, [POINTER(Cfg), POINTER(Rays), c_int64, c_void_p, c_void_p]),
     'vipnerf_composite': (c_int, [POINTER(Cfg), POINTER(Rays), c_int64, c_int32, c_void_p, c_void_p, c_void_p,
                                   c_void_p, POINTER(PassOut), c_void_p, c_void_p]),
+    'vipnerf_debug_set_profile_buffer': (c_int, [c_void_p]),
 }
 
 _lock = threading.Lock()

@@ -138,6 +138,11 @@ const char* vipnerf_last_error(void) { return g_last_error.c_str(); }
 
 int vipnerf_check_config(const vipnerf_cfg* cfg) { return check_cfg(cfg); }
 
+int vipnerf_debug_set_profile_buffer(void* dev_u64x64) {
+  set_tc_profile_buffer(dev_u64x64);
+  return VIPNERF_OK;
+}
+
 size_t vipnerf_packed_weight_bytes(const vipnerf_cfg* cfg) {
   if (check_cfg(cfg) != VIPNERF_OK) return 0;
   switch (cfg->precision) {

@@ -60,5 +60,7 @@ struct FusedArgs {
   float* ws_vis;        // [R,Nc+Nf]
 };
 cudaError_t launch_render_fused_tc(int precision, const FusedArgs& a, cudaStream_t s);
+// debug: 64 x u64 device buffer that CTA 0 of the next tensor-core launches fills with cycle counters (null = off)
+void set_tc_profile_buffer(void* dev_ptr);
 
 }  // namespace vipnerf

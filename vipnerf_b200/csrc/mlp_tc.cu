@@ -167,6 +167,7 @@ struct TcParams {
   int64_t n_units;  // staged: tiles of pass 0;  fused: ray pairs
   int n_fine;
   int has_fine;
+  unsigned long long* prof;  // optional cycle counters of CTA 0 (vipnerf_debug_set_profile_buffer), else null
 };
 
 // Work of one tile slot (sg = global slot index over the whole grid): item i -> (pass, tile)
@@ -201,21 +202,38 @@ struct WorkList {
 };
 
 // ------------------------------------------------------------------------------------------ epilogue pieces
+// sin / cos of 2^k * x for k = 0..L-1 with ONE range reduction: t = x / (2 pi) is formed in double-float
+// (hi + lo, ~48 bits), scaling by 2^k is exact, and frac(2^k t) is exact, so every octave sees an argument in
+// [-0.5, 0.5] turns with ~1e-7 absolute error - independent of the frequency (the reference evaluates
+// sin(fl(x * 2^k)) with a full-precision libm).  kAccurate: sincospif (~1 ulp); otherwise the MUFU
+// approximations (abs. error ~5e-7, far below the bf16 rounding the value gets next).
+template <bool kAccurate>
+__device__ __forceinline__ void sincos_octave(float t_hi, float t_lo, int k, float& s, float& c) {
+  const float scale = (float)(1 << k);
+  const float a = t_hi * scale;
+  const float r = (a - rintf(a)) + t_lo * scale;   // turns, |r| <= 0.5 (+ tiny)
+  if (kAccurate) {
+    sincospif(2.f * r, &s, &c);
+  } else {
+    const float ang = r * 6.2831854820251465f;
+    s = __sinf(ang);
+    c = __cosf(ang);
+  }
+}
+
 // Row `row` of the slot's encoding buffer <- bf16(gamma(point)), 64 columns (63 + zero pad).
+// Column order of PositionalEncoder.encode (VipNeRF01.py:439-448): x(3), then per octave sin(3), cos(3).
 template <bool kSplit3>
 __device__ __forceinline__ void write_point_encoding(uint8_t* smem, int slot, int row, float x, float y, float z) {
   float v[64];
   v[0] = x; v[1] = y; v[2] = z;
   const float p[3] = {x, y, z};
 #pragma unroll
-  for (int k = 0; k < kLPts; ++k) {
+  for (int a = 0; a < 3; ++a) {
+    const float t_hi = p[a] * 0.15915493667125702f;
+    const float t_lo = fmaf(p[a], 6.4206382432985265e-09f, fmaf(p[a], 0.15915493667125702f, -t_hi));
 #pragma unroll
-    for (int a = 0; a < 3; ++a) {
-      float s, c;
-      sincosf(p[a] * (float)(1 << k), &s, &c);  // exact power-of-two scaling: same argument as the reference
-      v[3 + 6 * k + a] = s;
-      v[6 + 6 * k + a] = c;
-    }
+    for (int k = 0; k < kLPts; ++k) sincos_octave<kSplit3>(t_hi, t_lo, k, v[3 + 6 * k + a], v[6 + 6 * k + a]);
   }
   v[63] = 0.f;
   const uint32_t hi_base = smem_u32(smem + kOffPe + (kSplit3 ? 0 : slot) * kKBlockBytes) + row * 128;
@@ -238,16 +256,18 @@ __device__ __forceinline__ void write_point_encoding(uint8_t* smem, int slot, in
 
 // One trunk / feature layer epilogue for one row: accumulator (256 fp32 TMEM columns) -> +bias (-> ReLU) -> bf16
 // -> A buffer (in place).  kSigma additionally accumulates the density head on the fp32 activations.
+// The eight 32-column TMEM loads are software-pipelined: block cb+1 is in flight while block cb is processed
+// (tcgen05.wait::ld waits for everything outstanding, so the next load is issued right after the wait).
 template <bool kSplit3, bool kRelu, bool kSigma>
 __device__ __forceinline__ float layer_epilogue(uint8_t* smem, int slot, int row, uint32_t taddr,
                                                 const float* __restrict__ bias, const float* __restrict__ w_sigma) {
   float sigma_acc = 0.f;
   const uint32_t hi_base = smem_u32(smem + kOffA + (kSplit3 ? 0 : slot) * kABytes) + row * 128;
   const uint32_t lo_base = smem_u32(smem + kOffA + kABytes) + row * 128;
-#pragma unroll 1
+  uint32_t v[2][32];
+  tmem_ld32(taddr, v[0]);
+#pragma unroll
   for (int cb = 0; cb < 8; ++cb) {
-    uint32_t v[32];
-    tmem_ld32(taddr + cb * 32, v);
     float b[32];
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
@@ -255,10 +275,11 @@ __device__ __forceinline__ float layer_epilogue(uint8_t* smem, int slot, int row
       b[4 * q] = t.x; b[4 * q + 1] = t.y; b[4 * q + 2] = t.z; b[4 * q + 3] = t.w;
     }
     tmem_ld_wait();
+    if (cb + 1 < 8) tmem_ld32(taddr + (cb + 1) * 32, v[(cb + 1) & 1]);
     float h[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
-      h[j] = __uint_as_float(v[j]) + b[j];
+      h[j] = __uint_as_float(v[cb & 1][j]) + b[j];
       if (kRelu) h[j] = fmaxf(h[j], 0.f);
     }
     if (kSigma) {
@@ -295,10 +316,10 @@ __device__ __forceinline__ float layer_epilogue(uint8_t* smem, int slot, int row
 __device__ __forceinline__ void view_epilogue(uint32_t taddr, const float* vb_row, const float* __restrict__ w_out,
                                               float (&o)[4]) {
   o[0] = o[1] = o[2] = o[3] = 0.f;
-#pragma unroll 1
+  uint32_t v[2][32];
+  tmem_ld32(taddr, v[0]);
+#pragma unroll
   for (int cb = 0; cb < 4; ++cb) {
-    uint32_t v[32];
-    tmem_ld32(taddr + cb * 32, v);
     float b[32];
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
@@ -306,9 +327,10 @@ __device__ __forceinline__ void view_epilogue(uint32_t taddr, const float* vb_ro
       b[4 * q] = t.x; b[4 * q + 1] = t.y; b[4 * q + 2] = t.z; b[4 * q + 3] = t.w;
     }
     tmem_ld_wait();
+    if (cb + 1 < 4) tmem_ld32(taddr + (cb + 1) * 32, v[(cb + 1) & 1]);
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
-      const float h = fmaxf(__uint_as_float(v[j]) + b[j], 0.f);
+      const float h = fmaxf(__uint_as_float(v[cb & 1][j]) + b[j], 0.f);
       const float4 w = __ldg(reinterpret_cast<const float4*>(w_out) + cb * 32 + j);
       o[0] = fmaf(h, w.x, o[0]);
       o[1] = fmaf(h, w.y, o[1]);
@@ -359,18 +381,19 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const TcParams p) 
       const uint32_t taddr = tmem_base + (uint32_t)(slot * 256) + ((uint32_t)((warp & 3) * 32) << 16);
       float* vb = reinterpret_cast<float*>(smem + kOffVb) + slot * 256;
       float* pev = reinterpret_cast<float*>(smem + kOffPev) + slot * 64;
-      uint32_t d_parity = 0;
-      for (int it = 0; it < work.n_items; ++it) {
-        const int pi = work.pass_of(it);
-        const PassDesc& ps = p.pass[pi];
-        const int64_t tile = work.tile_of(it);
-        const int64_t pg = tile * kTile + row;
+      const bool prof_on = p.prof != nullptr && blockIdx.x == 0 && row == 0;
+      long long c_enc = 0, c_vb = 0, c_wait = 0, c_epi = 0, c_view = 0, c_hook = 0;
+      const long long c_begin = clock64();
+
+      // Sample position of this thread's row of item `it` and its encoding -> the slot's encoding buffer
+      // (VipNeRF01.py:105-107, :173-203, :439-448).
+      auto encode_item = [&](int it) {
+        const long long t0 = clock64();
+        const PassDesc& ps = p.pass[work.pass_of(it)];
+        const int64_t pg = work.tile_of(it) * kTile + row;
         const bool valid = pg < ps.n_points;
         const int64_t pc = valid ? pg : ps.n_points - 1;
         const int64_t ray = pc / ps.S;
-        const int64_t ray_first = min((tile * kTile) / ps.S, p.n_rays - 1);
-        const float* small = reinterpret_cast<const float*>(ps.packed);
-        // ---- sample position and its encoding (VipNeRF01.py:105-107, :173-203, :439-448)
         float zv;
         if (ps.compute_z) {
           const int s = (int)(pc - ray * ps.S);
@@ -384,10 +407,15 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const TcParams p) 
         const float py = fadd(p.rp.pts_o[3 * ray + 1], fmul(p.rp.pts_d[3 * ray + 1], zv));
         const float pz = fadd(p.rp.pts_o[3 * ray + 2], fmul(p.rp.pts_d[3 * ray + 2], zv));
         write_point_encoding<kSplit3>(smem, slot, row, px, py, pz);
-        fence_proxy_async();
-        tc_fence_before();  // orders the previous tile's tcgen05.ld before the MMA that overwrites the slot
-        mbar_arrive(bar(kBarAReady + slot));
-        // ---- view-direction part of M9 for the (at most two) rays of this tile, in fp32
+        c_enc += clock64() - t0;
+      };
+      // View-direction columns of views_linears.0 (+ bias) for the (at most two) rays of item `it`, fp32:
+      // vb[rs][c] = b[c] + sum_j W[c][256 + j] * gamma(view_dir[ray_first + rs])[j]   (VipNeRF01.py:576-579)
+      auto view_bias_item = [&](int it) {
+        const long long t0 = clock64();
+        const PassDesc& ps = p.pass[work.pass_of(it)];
+        const float* small = reinterpret_cast<const float*>(ps.packed);
+        const int64_t ray_first = min((work.tile_of(it) * kTile) / ps.S, p.n_rays - 1);
         if (row < 2 * kEncView) {
           const int rs = row / kEncView, j = row % kEncView;
           const int64_t r2 = min(ray_first + rs, p.n_rays - 1);
@@ -401,27 +429,51 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const TcParams p) 
           }
           pev[rs * 32 + j] = val;
         }
+        float w[kEncView];
+#pragma unroll
+        for (int j = 0; j < kEncView; ++j) w[j] = __ldg(small + kOffWViewDir + j * 128 + row);
+        float a0 = small[kOffBiasViews + row], a1 = a0;
         group_sync(group);
-        {
-          const float* wvd = small + kOffWViewDir;
-          float a0 = small[kOffBiasViews + row], a1 = a0;
-#pragma unroll 1
-          for (int j = 0; j < kEncView; ++j) {
-            const float w = __ldg(wvd + j * 128 + row);
-            a0 = fmaf(w, pev[j], a0);
-            a1 = fmaf(w, pev[32 + j], a1);
-          }
-          vb[row] = a0;
-          vb[128 + row] = a1;
+#pragma unroll
+        for (int j = 0; j < kEncView; ++j) {
+          a0 = fmaf(w[j], pev[j], a0);
+          a1 = fmaf(w[j], pev[32 + j], a1);
         }
+        vb[row] = a0;
+        vb[128 + row] = a1;
         group_sync(group);
+        c_vb += clock64() - t0;
+      };
+
+      uint32_t d_parity = 0;
+      if (work.n_items > 0) {
+        encode_item(0);
+        fence_proxy_async();
+        mbar_arrive(bar(kBarAReady + slot));
+      }
+      for (int it = 0; it < work.n_items; ++it) {
+        const int pi = work.pass_of(it);
+        const PassDesc& ps = p.pass[pi];
+        const int64_t tile = work.tile_of(it);
+        const int64_t pg = tile * kTile + row;
+        const bool valid = pg < ps.n_points;
+        const int64_t ray = (valid ? pg : ps.n_points - 1) / ps.S;
+        const int64_t ray_first = min((tile * kTile) / ps.S, p.n_rays - 1);
+        const float* small = reinterpret_cast<const float*>(ps.packed);
+        // the next item's depths exist unless it is the fine tile of the pair whose coarse tile is this item
+        const bool has_next = it + 1 < work.n_items;
+        const bool next_ready = has_next && (work.pass_of(it + 1) == 0 || (it + 1 - work.n_first_pass) / 3 < it);
+        bool next_encoded = false;
 
         float sigma_lin = 0.f;
 #pragma unroll 1
         for (int l = 0; l < 9; ++l) {
+          long long t0 = clock64();
           mbar_wait(bar(kBarDReady + slot), d_parity);
           d_parity ^= 1;
           tc_fence_after();
+          long long t1 = clock64();
+          c_wait += t1 - t0;
           const float* bias = small + kOffBias + l * 256;
           if (l == 7) sigma_lin = layer_epilogue<kSplit3, true, true>(smem, slot, row, taddr, bias, small + kOffWSigma);
           else if (l == 8) layer_epilogue<kSplit3, false, false>(smem, slot, row, taddr, bias, nullptr);
@@ -429,12 +481,23 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const TcParams p) 
           fence_proxy_async();
           tc_fence_before();
           mbar_arrive(bar(kBarAReady + slot));
+          c_epi += clock64() - t1;
+          if (l == 5) {
+            // M5 has retired: the encoding buffer is free, and so are vb/pev (the previous tile's M9 epilogue
+            // is long done).  Use the time this slot's M6 spends on the tensor pipe.
+            view_bias_item(it);
+            if (next_ready) { encode_item(it + 1); next_encoded = true; }
+          }
         }
+        long long t0 = clock64();
         mbar_wait(bar(kBarDReady + slot), d_parity);
         d_parity ^= 1;
         tc_fence_after();
+        long long t1 = clock64();
+        c_wait += t1 - t0;
         float o[4];
         view_epilogue(taddr, vb + (int)(ray - ray_first) * 128, small + kOffWOut, o);
+        tc_fence_before();  // orders this tile's last tcgen05.ld before the next tile's first MMA into the slot
         if (valid) {
           ps.sigma[pg] = fmaxf(sigma_lin + small[kOffBSigma], 0.f);  // :546-553 (eval: no noise)
           ps.rgb[3 * pg + 0] = sigmoidf(o[0] + small[kOffBOut + 0]);   // :585-594
@@ -442,10 +505,12 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const TcParams p) 
           ps.rgb[3 * pg + 2] = sigmoidf(o[2] + small[kOffBOut + 2]);
           ps.vis[pg] = sigmoidf(o[3] + small[kOffBOut + 3]);
         }
+        c_view += clock64() - t1;
         if (kFused) {
           // ---- per-ray stages on the two rays a pair of tiles completes (one warp per ray)
           const bool pair_done = pi == 0 || (tile % 3) == 2;
           if (pair_done) {
+            const long long th = clock64();
             group_sync(group);  // the rays' network outputs (global) are complete and visible to the group
             const int64_t pair = pi == 0 ? tile : tile / 3;
             const int wq = warp & 3;
@@ -473,10 +538,21 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const TcParams p) 
               }
             }
             group_sync(group);  // z_fine (global) visible before the group encodes fine tiles
+            c_hook += clock64() - th;
           }
+        }
+        if (has_next) {
+          if (!next_encoded) encode_item(it + 1);
+          fence_proxy_async();
+          mbar_arrive(bar(kBarAReady + slot));
         }
       }
       tc_fence_before();
+      if (prof_on) {
+        unsigned long long* q = p.prof + slot * 16;
+        q[0] = c_enc; q[1] = c_vb; q[2] = c_wait; q[3] = c_epi; q[4] = c_view; q[5] = c_hook;
+        q[6] = (unsigned long long)work.n_items; q[7] = (unsigned long long)(clock64() - c_begin);
+      }
     }
   } else if (warp == 8) {
     // =================================================================== weight producer
@@ -512,12 +588,18 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const TcParams p) 
     uint32_t q = 0;
     uint32_t a_parity[2] = {0, 0};
     const uint32_t a_base = smem_u32(smem + kOffA), pe_base = smem_u32(smem + kOffPe), w_base = smem_u32(smem + kOffW);
+    long long c_wait_a = 0, c_wait_w = 0;
+    const long long c_begin = clock64();
     for (int it = 0; it < n_max; ++it) {
       for (int l = 0; l < kNumMatLayers; ++l) {
         for (int s = 0; s < kSlots; ++s) {
           const WorkList<kFused>& w = s == 0 ? work0 : work1;
           if (it >= w.n_items) continue;
-          mbar_wait(bar(kBarAReady + s), a_parity[s]);
+          {
+            const long long t0 = clock64();
+            mbar_wait(bar(kBarAReady + s), a_parity[s]);
+            c_wait_a += clock64() - t0;
+          }
           a_parity[s] ^= 1;
           tc_fence_after();
           const int n_kc = layer_k(l) / 64, n_nh = layer_n(l) / 128;
@@ -536,7 +618,11 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const TcParams p) 
               const uint32_t d_tmem = tmem_base + (uint32_t)(s * 256 + nh * 128);
               for (int part = 0; part < (kSplit3 ? 2 : 1); ++part, ++q) {
                 const uint32_t stage = q % kStages;
-                mbar_wait(bar(kBarWFull + stage), (q / kStages) & 1);
+                {
+                  const long long t0 = clock64();
+                  mbar_wait(bar(kBarWFull + stage), (q / kStages) & 1);
+                  c_wait_w += clock64() - t0;
+                }
                 tc_fence_after();
                 if (lane == 0) {
                   const uint32_t b_addr = w_base + stage * kChunkBytes;
@@ -562,6 +648,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const TcParams p) 
       }
     }
     tc_fence_before();
+    if (p.prof != nullptr && blockIdx.x == 0 && lane == 0) {
+      p.prof[32] = c_wait_a; p.prof[33] = c_wait_w; p.prof[34] = (unsigned long long)(clock64() - c_begin);
+      p.prof[35] = q;
+    }
   }
   __syncthreads();
   if (warp == 9) {
@@ -572,6 +662,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const TcParams p) 
 
 // ------------------------------------------------------------------------------------------ host side
 std::mutex g_attr_mutex;
+unsigned long long* g_prof_buffer = nullptr;  // debug: set by vipnerf_debug_set_profile_buffer
 int g_sm_count[64] = {0};
 bool g_attr_set[64][4] = {{false}};
 
@@ -614,6 +705,11 @@ cudaError_t launch(const TcParams& p, int64_t units_per_cta_slot_total, cudaStre
 
 }  // namespace
 
+void set_tc_profile_buffer(void* dev_ptr) {
+  std::lock_guard<std::mutex> lock(g_attr_mutex);
+  g_prof_buffer = static_cast<unsigned long long*>(dev_ptr);
+}
+
 cudaError_t launch_mlp_tc(int precision, const RayPtrs& rp, const RenderFlags& fl, int64_t n_rays, int S,
                           const float* z, const void* packed, float* sigma, float* rgb, float* vis,
                           cudaStream_t s) {
@@ -631,6 +727,7 @@ cudaError_t launch_mlp_tc(int precision, const RayPtrs& rp, const RenderFlags& f
   p.pass[0].compute_z = 0;
   p.pass[1] = p.pass[0];
   p.n_units = (p.pass[0].n_points + kTile - 1) / kTile;
+  p.prof = g_prof_buffer;
   if (p.n_units == 0) return cudaSuccess;
   if (precision == VIPNERF_PRECISION_BF16X3) return launch<true, false>(p, p.n_units, s);
   return launch<false, false>(p, p.n_units, s);
@@ -661,6 +758,7 @@ cudaError_t launch_render_fused_tc(int precision, const FusedArgs& a, cudaStream
   }
   if (!p.has_fine) p.pass[1] = p.pass[0];
   p.n_units = (a.n_rays + 1) / 2;
+  p.prof = g_prof_buffer;
   if (precision == VIPNERF_PRECISION_BF16X3) return launch<true, true>(p, p.n_units, s);
   return launch<false, true>(p, p.n_units, s);
 }
