@@ -112,6 +112,61 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// One weight chunk (K = 64 = four K=16 steps) against one A k-block: four tcgen05.mma issued by ONE elected lane
+// from a single PTX block (descriptor start addresses advance by 32 B = 2 units per step), followed by the
+// commit that frees the weight stage.  `first_acc` = 0 makes the first MMA overwrite the accumulator.
+__device__ __forceinline__ void mma_chunk(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t first_acc,
+                                          uint32_t empty_bar) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p, t, e;\n"
+      ".reg .b64 a1, a2, a3, b1, b2, b3;\n"
+      "setp.ne.b32 p, %3, 0;\n"
+      "setp.eq.b32 t, 0, 0;\n"
+      "add.s64 a1, %1, 2;\n add.s64 a2, %1, 4;\n add.s64 a3, %1, 6;\n"
+      "add.s64 b1, %2, 2;\n add.s64 b2, %2, 4;\n add.s64 b3, %2, 6;\n"
+      "elect.sync _|e, 0xffffffff;\n"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %4, p;\n"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], a1, b1, %4, t;\n"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], a2, b2, %4, t;\n"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], a3, b3, %4, t;\n"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%5];\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(first_acc), "r"(kInstrDesc), "r"(empty_bar)
+      : "memory");
+}
+// BF16X3 "hi" weight chunk: (A_hi + A_lo) x W_hi = eight MMAs, then the commit.
+__device__ __forceinline__ void mma_chunk_split_hi(uint32_t d_tmem, uint64_t a_hi, uint64_t a_lo, uint64_t b_desc,
+                                                   uint32_t first_acc, uint32_t empty_bar) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p, t, e;\n"
+      ".reg .b64 a1, a2, a3, l1, l2, l3, b1, b2, b3;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "setp.eq.b32 t, 0, 0;\n"
+      "add.s64 a1, %1, 2;\n add.s64 a2, %1, 4;\n add.s64 a3, %1, 6;\n"
+      "add.s64 l1, %2, 2;\n add.s64 l2, %2, 4;\n add.s64 l3, %2, 6;\n"
+      "add.s64 b1, %3, 2;\n add.s64 b2, %3, 4;\n add.s64 b3, %3, 6;\n"
+      "elect.sync _|e, 0xffffffff;\n"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %3, %5, p;\n"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %2, %3, %5, t;\n"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], a1, b1, %5, t;\n"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], l1, b1, %5, t;\n"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], a2, b2, %5, t;\n"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], l2, b2, %5, t;\n"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], a3, b3, %5, t;\n"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], l3, b3, %5, t;\n"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%6];\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_hi), "l"(a_lo), "l"(b_desc), "r"(first_acc), "r"(kInstrDesc), "r"(empty_bar)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_elect(uint32_t bar) {
+  asm volatile(
+      "{\n.reg .pred e;\nelect.sync _|e, 0xffffffff;\n"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n}\n" ::"r"(bar)
+      : "memory");
+}
 // K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address >> 4 in
 // bits [0,14), LBO (ignored for swizzled K-major) = 1 in [16,30), SBO = 1024 B (8 rows x 128 B) in [32,46),
 // version 1 in [46,48), layout SWIZZLE_128B = 2 in [61,64).
@@ -145,6 +200,34 @@ __device__ __forceinline__ uint32_t pack_bf16_residual(float lo, float hi, uint3
   return pack_bf16(rlo, rhi);
 }
 __device__ __forceinline__ float sigmoidf(float x) { return 1.f / (1.f + expf(-x)); }
+// Packed fp32x2 arithmetic (Blackwell FADD2 / FFMA2) and fused ReLU + bf16x2 conversion (F2FP.RELU)
+__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack_f32x2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+template <bool kRelu>
+__device__ __forceinline__ uint32_t cvt_bf16x2(uint64_t v) {  // element 0 (low half of v) -> low 16 bits
+  float lo, hi;
+  unpack_f32x2(v, lo, hi);
+  uint32_t r;
+  if (kRelu) asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  else asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
 
 // ------------------------------------------------------------------------------------------ parameters
 struct PassDesc {
@@ -276,6 +359,23 @@ __device__ __forceinline__ float layer_epilogue(uint8_t* smem, int slot, int row
     }
     tmem_ld_wait();
     if (cb + 1 < 8) tmem_ld32(taddr + (cb + 1) * 32, v[(cb + 1) & 1]);
+    const uint32_t kb_off = (uint32_t)(cb >> 1) * kKBlockBytes;
+    if (!kSplit3 && !kSigma) {
+      // throughput path: FADD2 for the bias, ReLU fused into the bf16x2 conversion (1 instruction / element)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint32_t w[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int e = 8 * j + 2 * q;
+          const uint64_t acc = pack_f32x2(__uint_as_float(v[cb & 1][e]), __uint_as_float(v[cb & 1][e + 1]));
+          w[q] = cvt_bf16x2<kRelu>(fadd2(acc, pack_f32x2(b[e], b[e + 1])));
+        }
+        const int ch = (cb & 1) * 4 + j;
+        st_shared_v4(hi_base + kb_off + (uint32_t)((ch ^ (row & 7)) << 4), w[0], w[1], w[2], w[3]);
+      }
+      continue;
+    }
     float h[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
@@ -292,7 +392,6 @@ __device__ __forceinline__ float layer_epilogue(uint8_t* smem, int slot, int row
         sigma_acc = fmaf(h[4 * q + 3], t.w, sigma_acc);
       }
     }
-    const uint32_t kb_off = (uint32_t)(cb >> 1) * kKBlockBytes;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int ch = (cb & 1) * 4 + j;
@@ -315,7 +414,7 @@ __device__ __forceinline__ float layer_epilogue(uint8_t* smem, int slot, int row
 // M9 epilogue for one row: relu(acc + (bias + view-direction part)) . views_output_linear -> 4 logits
 __device__ __forceinline__ void view_epilogue(uint32_t taddr, const float* vb_row, const float* __restrict__ w_out,
                                               float (&o)[4]) {
-  o[0] = o[1] = o[2] = o[3] = 0.f;
+  uint64_t o01 = pack_f32x2(0.f, 0.f), o23 = o01;
   uint32_t v[2][32];
   tmem_ld32(taddr, v[0]);
 #pragma unroll
@@ -332,16 +431,17 @@ __device__ __forceinline__ void view_epilogue(uint32_t taddr, const float* vb_ro
     for (int j = 0; j < 32; ++j) {
       const float h = fmaxf(__uint_as_float(v[cb & 1][j]) + b[j], 0.f);
       const float4 w = __ldg(reinterpret_cast<const float4*>(w_out) + cb * 32 + j);
-      o[0] = fmaf(h, w.x, o[0]);
-      o[1] = fmaf(h, w.y, o[1]);
-      o[2] = fmaf(h, w.z, o[2]);
-      o[3] = fmaf(h, w.w, o[3]);
+      const uint64_t hh = pack_f32x2(h, h);
+      o01 = ffma2(hh, pack_f32x2(w.x, w.y), o01);
+      o23 = ffma2(hh, pack_f32x2(w.z, w.w), o23);
     }
   }
+  unpack_f32x2(o01, o[0], o[1]);
+  unpack_f32x2(o23, o[2], o[3]);
 }
 
 // ------------------------------------------------------------------------------------------ the kernel
-template <bool kSplit3, bool kFused>
+template <bool kSplit3, bool kFused, bool kProf>
 __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr int kSlots = kSplit3 ? 1 : 2;
@@ -381,14 +481,14 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const TcParams p) 
       const uint32_t taddr = tmem_base + (uint32_t)(slot * 256) + ((uint32_t)((warp & 3) * 32) << 16);
       float* vb = reinterpret_cast<float*>(smem + kOffVb) + slot * 256;
       float* pev = reinterpret_cast<float*>(smem + kOffPev) + slot * 64;
-      const bool prof_on = p.prof != nullptr && blockIdx.x == 0 && row == 0;
+      const bool prof_on = kProf && p.prof != nullptr && blockIdx.x == 0 && row == 0;
       long long c_enc = 0, c_vb = 0, c_wait = 0, c_epi = 0, c_view = 0, c_hook = 0;
-      const long long c_begin = clock64();
+      const long long c_begin = kProf ? clock64() : 0;
 
       // Sample position of this thread's row of item `it` and its encoding -> the slot's encoding buffer
       // (VipNeRF01.py:105-107, :173-203, :439-448).
       auto encode_item = [&](int it) {
-        const long long t0 = clock64();
+        const long long t0 = kProf ? clock64() : 0;
         const PassDesc& ps = p.pass[work.pass_of(it)];
         const int64_t pg = work.tile_of(it) * kTile + row;
         const bool valid = pg < ps.n_points;
@@ -407,12 +507,12 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const TcParams p) 
         const float py = fadd(p.rp.pts_o[3 * ray + 1], fmul(p.rp.pts_d[3 * ray + 1], zv));
         const float pz = fadd(p.rp.pts_o[3 * ray + 2], fmul(p.rp.pts_d[3 * ray + 2], zv));
         write_point_encoding<kSplit3>(smem, slot, row, px, py, pz);
-        c_enc += clock64() - t0;
+        if (kProf) c_enc += clock64() - t0;
       };
       // View-direction columns of views_linears.0 (+ bias) for the (at most two) rays of item `it`, fp32:
       // vb[rs][c] = b[c] + sum_j W[c][256 + j] * gamma(view_dir[ray_first + rs])[j]   (VipNeRF01.py:576-579)
       auto view_bias_item = [&](int it) {
-        const long long t0 = clock64();
+        const long long t0 = kProf ? clock64() : 0;
         const PassDesc& ps = p.pass[work.pass_of(it)];
         const float* small = reinterpret_cast<const float*>(ps.packed);
         const int64_t ray_first = min((work.tile_of(it) * kTile) / ps.S, p.n_rays - 1);
@@ -442,7 +542,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const TcParams p) 
         vb[row] = a0;
         vb[128 + row] = a1;
         group_sync(group);
-        c_vb += clock64() - t0;
+        if (kProf) c_vb += clock64() - t0;
       };
 
       uint32_t d_parity = 0;
@@ -468,11 +568,11 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const TcParams p) 
         float sigma_lin = 0.f;
 #pragma unroll 1
         for (int l = 0; l < 9; ++l) {
-          long long t0 = clock64();
+          const long long t0 = kProf ? clock64() : 0;
           mbar_wait(bar(kBarDReady + slot), d_parity);
           d_parity ^= 1;
           tc_fence_after();
-          long long t1 = clock64();
+          const long long t1 = kProf ? clock64() : 0;
           c_wait += t1 - t0;
           const float* bias = small + kOffBias + l * 256;
           if (l == 7) sigma_lin = layer_epilogue<kSplit3, true, true>(smem, slot, row, taddr, bias, small + kOffWSigma);
@@ -481,7 +581,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const TcParams p) 
           fence_proxy_async();
           tc_fence_before();
           mbar_arrive(bar(kBarAReady + slot));
-          c_epi += clock64() - t1;
+          if (kProf) c_epi += clock64() - t1;
           if (l == 5) {
             // M5 has retired: the encoding buffer is free, and so are vb/pev (the previous tile's M9 epilogue
             // is long done).  Use the time this slot's M6 spends on the tensor pipe.
@@ -489,11 +589,11 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const TcParams p) 
             if (next_ready) { encode_item(it + 1); next_encoded = true; }
           }
         }
-        long long t0 = clock64();
+        const long long t0 = kProf ? clock64() : 0;
         mbar_wait(bar(kBarDReady + slot), d_parity);
         d_parity ^= 1;
         tc_fence_after();
-        long long t1 = clock64();
+        const long long t1 = kProf ? clock64() : 0;
         c_wait += t1 - t0;
         float o[4];
         view_epilogue(taddr, vb + (int)(ray - ray_first) * 128, small + kOffWOut, o);
@@ -505,12 +605,12 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const TcParams p) 
           ps.rgb[3 * pg + 2] = sigmoidf(o[2] + small[kOffBOut + 2]);
           ps.vis[pg] = sigmoidf(o[3] + small[kOffBOut + 3]);
         }
-        c_view += clock64() - t1;
+        if (kProf) c_view += clock64() - t1;
         if (kFused) {
           // ---- per-ray stages on the two rays a pair of tiles completes (one warp per ray)
           const bool pair_done = pi == 0 || (tile % 3) == 2;
           if (pair_done) {
-            const long long th = clock64();
+            const long long th = kProf ? clock64() : 0;
             group_sync(group);  // the rays' network outputs (global) are complete and visible to the group
             const int64_t pair = pi == 0 ? tile : tile / 3;
             const int wq = warp & 3;
@@ -538,7 +638,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const TcParams p) 
               }
             }
             group_sync(group);  // z_fine (global) visible before the group encodes fine tiles
-            c_hook += clock64() - th;
+            if (kProf) c_hook += clock64() - th;
           }
         }
         if (has_next) {
@@ -582,73 +682,68 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const TcParams p) 
     }
   } else {
     // =================================================================== MMA issuer (warp 9)
+    // The whole warp runs the loop uniformly (so addresses and descriptors stay in uniform registers); one
+    // elected lane issues.  Per chunk: one barrier probe + one PTX block of 4 (BF16X3: 8 / 4) MMAs + commit.
     WorkList<kFused> work0(p, blockIdx.x * kSlots + 0, n_slots_total);
     WorkList<kFused> work1(p, blockIdx.x * kSlots + (kSlots - 1), n_slots_total);
     const int n_max = max(work0.n_items, kSlots > 1 ? work1.n_items : 0);
     uint32_t q = 0;
-    uint32_t a_parity[2] = {0, 0};
-    const uint32_t a_base = smem_u32(smem + kOffA), pe_base = smem_u32(smem + kOffPe), w_base = smem_u32(smem + kOffW);
+    uint32_t a_parity0 = 0, a_parity1 = 0;
+    const uint64_t a_desc0 = make_desc(smem_u32(smem + kOffA)), pe_desc0 = make_desc(smem_u32(smem + kOffPe));
+    const uint64_t w_desc0 = make_desc(smem_u32(smem + kOffW));
+    constexpr uint64_t kKBlockUnits = kKBlockBytes >> 4, kAUnits = kABytes >> 4, kChunkUnits = kChunkBytes >> 4;
     long long c_wait_a = 0, c_wait_w = 0;
-    const long long c_begin = clock64();
+    const long long c_begin = kProf ? clock64() : 0;
     for (int it = 0; it < n_max; ++it) {
       for (int l = 0; l < kNumMatLayers; ++l) {
+#pragma unroll
         for (int s = 0; s < kSlots; ++s) {
           const WorkList<kFused>& w = s == 0 ? work0 : work1;
           if (it >= w.n_items) continue;
           {
-            const long long t0 = clock64();
-            mbar_wait(bar(kBarAReady + s), a_parity[s]);
-            c_wait_a += clock64() - t0;
+            const long long t0 = kProf ? clock64() : 0;
+            mbar_wait(bar(kBarAReady + s), s == 0 ? a_parity0 : a_parity1);
+            if (kProf) c_wait_a += clock64() - t0;
           }
-          a_parity[s] ^= 1;
+          if (s == 0) a_parity0 ^= 1; else a_parity1 ^= 1;
           tc_fence_after();
           const int n_kc = layer_k(l) / 64, n_nh = layer_n(l) / 128;
+          const uint64_t slot_units = (kSplit3 ? 0 : s);
           for (int kc = 0; kc < n_kc; ++kc) {
             // A operand k-block: encoding buffer for M0 and for the first k-block of M5, else the A buffer
-            uint32_t a_hi, a_lo;
+            uint64_t a_hi, a_lo;
             if (l == 0 || (l == 5 && kc == 0)) {
-              a_hi = pe_base + (kSplit3 ? 0 : s) * kKBlockBytes;
-              a_lo = pe_base + kKBlockBytes;
+              a_hi = pe_desc0 + slot_units * kKBlockUnits;
+              a_lo = pe_desc0 + kKBlockUnits;
             } else {
               const int kb = l == 5 ? kc - 1 : kc;
-              a_hi = a_base + (kSplit3 ? 0 : s) * kABytes + kb * kKBlockBytes;
-              a_lo = a_base + kABytes + kb * kKBlockBytes;
+              a_hi = a_desc0 + slot_units * kAUnits + kb * kKBlockUnits;
+              a_lo = a_desc0 + kAUnits + kb * kKBlockUnits;
             }
             for (int nh = 0; nh < n_nh; ++nh) {
               const uint32_t d_tmem = tmem_base + (uint32_t)(s * 256 + nh * 128);
+#pragma unroll
               for (int part = 0; part < (kSplit3 ? 2 : 1); ++part, ++q) {
                 const uint32_t stage = q % kStages;
                 {
-                  const long long t0 = clock64();
+                  const long long t0 = kProf ? clock64() : 0;
                   mbar_wait(bar(kBarWFull + stage), (q / kStages) & 1);
-                  c_wait_w += clock64() - t0;
+                  if (kProf) c_wait_w += clock64() - t0;
                 }
                 tc_fence_after();
-                if (lane == 0) {
-                  const uint32_t b_addr = w_base + stage * kChunkBytes;
-#pragma unroll
-                  for (int k = 0; k < 4; ++k) {
-                    const uint64_t bd = make_desc(b_addr + k * 32);
-                    if (part == 0) {
-                      umma_bf16(d_tmem, make_desc(a_hi + k * 32), bd, (kc | k) != 0 ? 1u : 0u);
-                      if (kSplit3) umma_bf16(d_tmem, make_desc(a_lo + k * 32), bd, 1u);
-                    } else {
-                      umma_bf16(d_tmem, make_desc(a_hi + k * 32), bd, 1u);  // hi x W_lo
-                    }
-                  }
-                  umma_commit(bar(kBarWEmpty + stage));
-                }
-                __syncwarp();
+                const uint64_t b_desc = w_desc0 + stage * kChunkUnits;
+                if (!kSplit3) mma_chunk(d_tmem, a_hi, b_desc, kc != 0, bar(kBarWEmpty + stage));
+                else if (part == 0) mma_chunk_split_hi(d_tmem, a_hi, a_lo, b_desc, kc != 0, bar(kBarWEmpty + stage));
+                else mma_chunk(d_tmem, a_hi, b_desc, 1u, bar(kBarWEmpty + stage));  // hi x W_lo
               }
             }
           }
-          if (lane == 0) umma_commit(bar(kBarDReady + s));
-          __syncwarp();
+          umma_commit_elect(bar(kBarDReady + s));
         }
       }
     }
     tc_fence_before();
-    if (p.prof != nullptr && blockIdx.x == 0 && lane == 0) {
+    if (kProf && p.prof != nullptr && blockIdx.x == 0 && lane == 0) {
       p.prof[32] = c_wait_a; p.prof[33] = c_wait_w; p.prof[34] = (unsigned long long)(clock64() - c_begin);
       p.prof[35] = q;
     }
@@ -664,7 +759,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const TcParams p) 
 std::mutex g_attr_mutex;
 unsigned long long* g_prof_buffer = nullptr;  // debug: set by vipnerf_debug_set_profile_buffer
 int g_sm_count[64] = {0};
-bool g_attr_set[64][4] = {{false}};
+bool g_attr_set[64][8] = {{false}};
 
 cudaError_t device_sm_count(int* out) {
   int dev = 0;
@@ -680,27 +775,34 @@ cudaError_t device_sm_count(int* out) {
   return cudaSuccess;
 }
 
-template <bool kSplit3, bool kFused>
-cudaError_t launch(const TcParams& p, int64_t units_per_cta_slot_total, cudaStream_t s) {
+template <bool kSplit3, bool kFused, bool kProf>
+cudaError_t launch_variant(const TcParams& p, int64_t n_units, cudaStream_t s) {
   int dev = 0, sms = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
   if ((e = device_sm_count(&sms)) != cudaSuccess) return e;
   {
     std::lock_guard<std::mutex> lock(g_attr_mutex);
-    const int variant = (kSplit3 ? 2 : 0) + (kFused ? 1 : 0);
+    const int variant = (kSplit3 ? 2 : 0) + (kFused ? 1 : 0) + (kProf ? 4 : 0);
     if (dev >= 64 || !g_attr_set[dev][variant]) {
-      e = cudaFuncSetAttribute(k_render_tc<kSplit3, kFused>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+      e = cudaFuncSetAttribute(k_render_tc<kSplit3, kFused, kProf>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)kSmemBytes);
       if (e != cudaSuccess) return e;
       if (dev < 64) g_attr_set[dev][variant] = true;
     }
   }
   constexpr int kSlots = kSplit3 ? 1 : 2;
-  int64_t grid = (units_per_cta_slot_total + kSlots - 1) / kSlots;
+  int64_t grid = (n_units + kSlots - 1) / kSlots;
   if (grid > sms) grid = sms;
   if (grid < 1) return cudaSuccess;
-  k_render_tc<kSplit3, kFused><<<(unsigned)grid, kNumThreads, kSmemBytes, s>>>(p);
+  k_render_tc<kSplit3, kFused, kProf><<<(unsigned)grid, kNumThreads, kSmemBytes, s>>>(p);
   return cudaGetLastError();
+}
+
+template <bool kSplit3, bool kFused>
+cudaError_t launch(const TcParams& p, int64_t n_units, cudaStream_t s) {
+  if (p.prof != nullptr) return launch_variant<kSplit3, kFused, true>(p, n_units, s);
+  return launch_variant<kSplit3, kFused, false>(p, n_units, s);
 }
 
 }  // namespace
