@@ -135,6 +135,36 @@ __device__ __forceinline__ void mma_chunk(uint32_t d_tmem, uint64_t a_desc, uint
       "l"(a_desc), "l"(b_desc), "r"(first_acc), "r"(kInstrDesc), "r"(empty_bar)
       : "memory");
 }
+// Two weight chunks of the same k-block (output columns 0..127 and 128..255) against one A k-block: eight MMAs
+// and the two stage-release commits from one elected lane.
+__device__ __forceinline__ void mma_chunk_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b0_desc, uint64_t b1_desc,
+                                               uint32_t first_acc, uint32_t empty_bar0, uint32_t empty_bar1) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p, t, e;\n"
+      ".reg .b64 a1, a2, a3, b1, b2, b3, c1, c2, c3;\n"
+      ".reg .b32 d1;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "setp.eq.b32 t, 0, 0;\n"
+      "add.u32 d1, %0, 128;\n"
+      "add.s64 a1, %1, 2;\n add.s64 a2, %1, 4;\n add.s64 a3, %1, 6;\n"
+      "add.s64 b1, %2, 2;\n add.s64 b2, %2, 4;\n add.s64 b3, %2, 6;\n"
+      "add.s64 c1, %3, 2;\n add.s64 c2, %3, 4;\n add.s64 c3, %3, 6;\n"
+      "elect.sync _|e, 0xffffffff;\n"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %5, p;\n"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [d1], %1, %3, %5, p;\n"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], a1, b1, %5, t;\n"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [d1], a1, c1, %5, t;\n"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], a2, b2, %5, t;\n"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [d1], a2, c2, %5, t;\n"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], a3, b3, %5, t;\n"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [d1], a3, c3, %5, t;\n"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%6];\n"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%7];\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b0_desc), "l"(b1_desc), "r"(first_acc), "r"(kInstrDesc), "r"(empty_bar0), "r"(empty_bar1)
+      : "memory");
+}
 // BF16X3 "hi" weight chunk: (A_hi + A_lo) x W_hi = eight MMAs, then the commit.
 __device__ __forceinline__ void mma_chunk_split_hi(uint32_t d_tmem, uint64_t a_hi, uint64_t a_lo, uint64_t b_desc,
                                                    uint32_t first_acc, uint32_t empty_bar) {
@@ -445,7 +475,8 @@ template <bool kSplit3, bool kFused, bool kProf>
 __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr int kSlots = kSplit3 ? 1 : 2;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // the shuffle makes the warp index provably warp-uniform, so ptxas keeps the role loops in the uniform datapath
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const uint32_t bar0 = smem_u32(smem + kOffBar);
   auto bar = [&](int idx) { return bar0 + 8u * idx; };
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + kOffTmemPtr);
@@ -719,6 +750,21 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const TcParams p) 
               const int kb = l == 5 ? kc - 1 : kc;
               a_hi = a_desc0 + slot_units * kAUnits + kb * kKBlockUnits;
               a_lo = a_desc0 + kAUnits + kb * kKBlockUnits;
+            }
+            if (!kSplit3 && n_nh == 2) {
+              // both column halves of this k-block in one go: two ring stages, eight MMAs, one PTX block
+              const uint32_t st0 = q % kStages, st1 = (q + 1) % kStages;
+              {
+                const long long t0 = kProf ? clock64() : 0;
+                mbar_wait(bar(kBarWFull + st0), (q / kStages) & 1);
+                mbar_wait(bar(kBarWFull + st1), ((q + 1) / kStages) & 1);
+                if (kProf) c_wait_w += clock64() - t0;
+              }
+              tc_fence_after();
+              mma_chunk_pair(tmem_base + (uint32_t)(s * 256), a_hi, w_desc0 + st0 * kChunkUnits,
+                             w_desc0 + st1 * kChunkUnits, kc != 0, bar(kBarWEmpty + st0), bar(kBarWEmpty + st1));
+              q += 2;
+              continue;
             }
             for (int nh = 0; nh < n_nh; ++nh) {
               const uint32_t d_tmem = tmem_base + (uint32_t)(s * 256 + nh * 128);
