@@ -147,8 +147,8 @@ size_t vipnerf_packed_weight_bytes(const vipnerf_cfg* cfg) {
   if (check_cfg(cfg) != VIPNERF_OK) return 0;
   switch (cfg->precision) {
     case VIPNERF_PRECISION_FP32: return kSmallBytes + (size_t)kFp32BigFloats * sizeof(float);
-    case VIPNERF_PRECISION_BF16: return kSmallBytes + (size_t)kTcChunks * kChunkBytes;
-    default: return kSmallBytes + (size_t)2 * kTcChunks * kChunkBytes;
+    case VIPNERF_PRECISION_BF16: return kSmallBytes + (size_t)kTcBigBytes;
+    default: return kSmallBytes + (size_t)2 * kTcBigBytes;
   }
 }
 

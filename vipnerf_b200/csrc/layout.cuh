@@ -49,19 +49,29 @@ __host__ __device__ constexpr int fp32_layer_offset(int l) {
 }
 constexpr int kFp32BigFloats = fp32_layer_offset(kNumMatLayers);  // 589,824
 
-// ---- tensor-core big region: 16 KiB "chunk images".  One chunk = 128 output rows (n) x 64 k-columns
-// of bf16 in the canonical K-major SWIZZLE_128B shared-memory layout tcgen05.mma reads:
-//   byte(n, k) = n*128 + ((((k & 63) >> 3) ^ (n & 7)) << 4) + (k & 7)*2
-// Chunks are stored in the order the kernel consumes them: layer, k-chunk, n-half; in BF16X3 mode every
-// chunk is followed by its "lo" image (bf16(w - float(bf16(w)))).
-constexpr int kChunkBytes = 16384;
-__host__ __device__ constexpr int layer_chunks(int l) { return (layer_k(l) / 64) * (layer_n(l) / 128); }
-__host__ __device__ constexpr int tc_layer_chunk_offset(int l) {
+// ---- tensor-core big region: "chunk images".  One chunk = ALL output rows (n) of a layer x 32 k-columns of
+// bf16 in the canonical K-major SWIZZLE_64B shared-memory layout tcgen05.mma reads (64-byte rows, 8-row / 512-byte
+// swizzle atoms):
+//   byte(n, k) = n*64 + ((((k & 31) >> 3) ^ ((n >> 1) & 3)) << 4) + (k & 7)*2
+// so a chunk is 16 KiB for the 256-row layers (two N=256 MMAs of K=16) and 8 KiB for M9 (N=128).  Chunks are
+// stored in the order the kernel consumes them: layer, then k; in BF16X3 mode every chunk is followed by its
+// "lo" image (bf16(w - float(bf16(w)))).
+constexpr int kChunkK = 32;
+constexpr int kChunkBytes = 16384;   // ring stage size (largest chunk)
+__host__ __device__ constexpr int layer_chunks(int l) { return layer_k(l) / kChunkK; }
+__host__ __device__ constexpr int layer_chunk_bytes(int l) { return layer_n(l) * kChunkK * 2; }
+__host__ __device__ constexpr int tc_layer_chunk_offset(int l) {   // in chunks
   int off = 0;
   for (int i = 0; i < l; ++i) off += layer_chunks(i);
   return off;
 }
-constexpr int kTcChunks = tc_layer_chunk_offset(kNumMatLayers);  // 72
+__host__ __device__ constexpr int tc_layer_byte_offset(int l) {    // of the hi image set
+  int off = 0;
+  for (int i = 0; i < l; ++i) off += layer_chunks(i) * layer_chunk_bytes(i);
+  return off;
+}
+constexpr int kTcChunks = tc_layer_chunk_offset(kNumMatLayers);     // 76
+constexpr int kTcBigBytes = tc_layer_byte_offset(kNumMatLayers);    // 1,179,648
 
 // Maps A column k of matrix layer l to the source weight column (or -1 for a zero pad column).
 __host__ __device__ inline int source_col(int l, int k) {

@@ -8,7 +8,7 @@
 //   warps 0-3  epilogue group 0  (owns tile slot 0: TMEM columns [0,256),   A buffer 0, encoding buffer 0)
 //   warps 4-7  epilogue group 1  (owns tile slot 1: TMEM columns [256,512), A buffer 1, encoding buffer 1)
 //   warp  8    weight producer   (one lane: cp.async.bulk 16 KiB weight chunk images -> 4-stage smem ring)
-//   warp  9    MMA issuer        (one lane: tcgen05.mma M=128 N=128 K=16, bf16 x bf16 -> fp32 in TMEM)
+//   warp  9    MMA issuer        (one lane: tcgen05.mma M=128 N=256 K=16, bf16 x bf16 -> fp32 in TMEM)
 // A "tile" is 128 consecutive sample points (rows).  A row's activations live in shared memory as bf16 in the
 // canonical K-major SWIZZLE_128B layout (four 16 KiB k-blocks of 128 rows x 64 columns); the accumulator of a
 // layer lives in the slot's 256 TMEM columns.  Per layer: the MMA warp streams the layer's weight chunks
@@ -53,9 +53,11 @@ static_assert(kSmemBytes <= 232448, "exceeds the 227 KiB per-CTA shared memory l
 
 enum { kBarWFull = 0, kBarWEmpty = 4, kBarAReady = 8, kBarDReady = 10 };
 
-// tcgen05 instruction descriptor: D=F32, A=B=BF16, both K-major, N=128, M=128 (cute::UMMA::InstrDescriptor bits:
+// tcgen05 instruction descriptor: D=F32, A=B=BF16, both K-major, M=128, N=n (cute::UMMA::InstrDescriptor bits:
 // c_format[4,6)=1, a_format[7,10)=1, b_format[10,13)=1, n_dim[17,23)=N>>3, m_dim[24,29)=M>>4)
-constexpr uint32_t kInstrDesc = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+constexpr uint32_t instr_desc(uint32_t n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24);
+}
 
 constexpr long long kTimeoutCycles = 4000000000ll;  // ~2 s: a protocol bug traps instead of hanging the GPU
 
@@ -103,92 +105,54 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void group_sync(int group) {  // named barrier over one epilogue group (128 threads)
   asm volatile("bar.sync %0, 128;" ::"r"(group + 1) : "memory");
 }
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate) {
+// mbarrier.test_wait: non-blocking probe (try_wait may suspend the warp when the phase is not complete)
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
   asm volatile(
-      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(kInstrDesc), "r"(accumulate)
+      "{\n.reg .pred p;\nmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
       : "memory");
+  return ok != 0;
 }
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// One weight chunk (K = 64 = four K=16 steps) against one A k-block: four tcgen05.mma issued by ONE elected lane
-// from a single PTX block (descriptor start addresses advance by 32 B = 2 units per step), followed by the
-// commit that frees the weight stage.  `first_acc` = 0 makes the first MMA overwrite the accumulator.
+// One weight chunk (K = 32 = two K=16 steps) against the matching 64-byte half of an A k-block: two tcgen05.mma
+// issued by ONE elected lane from a single PTX block (descriptor start addresses advance by 32 B = 2 units per
+// step), followed by the commit that frees the weight stage.  `first_acc` = 0: the first MMA overwrites D.
 __device__ __forceinline__ void mma_chunk(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t first_acc,
-                                          uint32_t empty_bar) {
+                                          uint32_t idesc, uint32_t empty_bar) {
   asm volatile(
       "{\n"
       ".reg .pred p, t, e;\n"
-      ".reg .b64 a1, a2, a3, b1, b2, b3;\n"
+      ".reg .b64 a1, b1;\n"
       "setp.ne.b32 p, %3, 0;\n"
       "setp.eq.b32 t, 0, 0;\n"
-      "add.s64 a1, %1, 2;\n add.s64 a2, %1, 4;\n add.s64 a3, %1, 6;\n"
-      "add.s64 b1, %2, 2;\n add.s64 b2, %2, 4;\n add.s64 b3, %2, 6;\n"
+      "add.s64 a1, %1, 2;\n add.s64 b1, %2, 2;\n"
       "elect.sync _|e, 0xffffffff;\n"
       "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %4, p;\n"
       "@e tcgen05.mma.cta_group::1.kind::f16 [%0], a1, b1, %4, t;\n"
-      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], a2, b2, %4, t;\n"
-      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], a3, b3, %4, t;\n"
       "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%5];\n"
       "}\n" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(first_acc), "r"(kInstrDesc), "r"(empty_bar)
+      "l"(a_desc), "l"(b_desc), "r"(first_acc), "r"(idesc), "r"(empty_bar)
       : "memory");
 }
-// Two weight chunks of the same k-block (output columns 0..127 and 128..255) against one A k-block: eight MMAs
-// and the two stage-release commits from one elected lane.
-__device__ __forceinline__ void mma_chunk_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b0_desc, uint64_t b1_desc,
-                                               uint32_t first_acc, uint32_t empty_bar0, uint32_t empty_bar1) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p, t, e;\n"
-      ".reg .b64 a1, a2, a3, b1, b2, b3, c1, c2, c3;\n"
-      ".reg .b32 d1;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "setp.eq.b32 t, 0, 0;\n"
-      "add.u32 d1, %0, 128;\n"
-      "add.s64 a1, %1, 2;\n add.s64 a2, %1, 4;\n add.s64 a3, %1, 6;\n"
-      "add.s64 b1, %2, 2;\n add.s64 b2, %2, 4;\n add.s64 b3, %2, 6;\n"
-      "add.s64 c1, %3, 2;\n add.s64 c2, %3, 4;\n add.s64 c3, %3, 6;\n"
-      "elect.sync _|e, 0xffffffff;\n"
-      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %5, p;\n"
-      "@e tcgen05.mma.cta_group::1.kind::f16 [d1], %1, %3, %5, p;\n"
-      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], a1, b1, %5, t;\n"
-      "@e tcgen05.mma.cta_group::1.kind::f16 [d1], a1, c1, %5, t;\n"
-      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], a2, b2, %5, t;\n"
-      "@e tcgen05.mma.cta_group::1.kind::f16 [d1], a2, c2, %5, t;\n"
-      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], a3, b3, %5, t;\n"
-      "@e tcgen05.mma.cta_group::1.kind::f16 [d1], a3, c3, %5, t;\n"
-      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%6];\n"
-      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%7];\n"
-      "}\n" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b0_desc), "l"(b1_desc), "r"(first_acc), "r"(kInstrDesc), "r"(empty_bar0), "r"(empty_bar1)
-      : "memory");
-}
-// BF16X3 "hi" weight chunk: (A_hi + A_lo) x W_hi = eight MMAs, then the commit.
+// BF16X3 "hi" weight chunk: (A_hi + A_lo) x W_hi = four MMAs, then the commit.
 __device__ __forceinline__ void mma_chunk_split_hi(uint32_t d_tmem, uint64_t a_hi, uint64_t a_lo, uint64_t b_desc,
-                                                   uint32_t first_acc, uint32_t empty_bar) {
+                                                   uint32_t first_acc, uint32_t idesc, uint32_t empty_bar) {
   asm volatile(
       "{\n"
       ".reg .pred p, t, e;\n"
-      ".reg .b64 a1, a2, a3, l1, l2, l3, b1, b2, b3;\n"
+      ".reg .b64 a1, l1, b1;\n"
       "setp.ne.b32 p, %4, 0;\n"
       "setp.eq.b32 t, 0, 0;\n"
-      "add.s64 a1, %1, 2;\n add.s64 a2, %1, 4;\n add.s64 a3, %1, 6;\n"
-      "add.s64 l1, %2, 2;\n add.s64 l2, %2, 4;\n add.s64 l3, %2, 6;\n"
-      "add.s64 b1, %3, 2;\n add.s64 b2, %3, 4;\n add.s64 b3, %3, 6;\n"
+      "add.s64 a1, %1, 2;\n add.s64 l1, %2, 2;\n add.s64 b1, %3, 2;\n"
       "elect.sync _|e, 0xffffffff;\n"
       "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %3, %5, p;\n"
       "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %2, %3, %5, t;\n"
       "@e tcgen05.mma.cta_group::1.kind::f16 [%0], a1, b1, %5, t;\n"
       "@e tcgen05.mma.cta_group::1.kind::f16 [%0], l1, b1, %5, t;\n"
-      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], a2, b2, %5, t;\n"
-      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], l2, b2, %5, t;\n"
-      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], a3, b3, %5, t;\n"
-      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], l3, b3, %5, t;\n"
       "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%6];\n"
       "}\n" ::"r"(d_tmem),
-      "l"(a_hi), "l"(a_lo), "l"(b_desc), "r"(first_acc), "r"(kInstrDesc), "r"(empty_bar)
+      "l"(a_hi), "l"(a_lo), "l"(b_desc), "r"(first_acc), "r"(idesc), "r"(empty_bar)
       : "memory");
 }
 __device__ __forceinline__ void umma_commit_elect(uint32_t bar) {
@@ -203,6 +167,11 @@ __device__ __forceinline__ void umma_commit_elect(uint32_t bar) {
 __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
   return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
          (2ull << 61);
+}
+// K-major SWIZZLE_64B descriptor of a weight chunk: 64-byte rows, SBO = 512 B (8 rows), layout type 4.
+__device__ __forceinline__ uint64_t make_desc_sw64(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) |
+         (4ull << 61);
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
@@ -475,8 +444,7 @@ template <bool kSplit3, bool kFused, bool kProf>
 __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr int kSlots = kSplit3 ? 1 : 2;
-  // the shuffle makes the warp index provably warp-uniform, so ptxas keeps the role loops in the uniform datapath
-  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t bar0 = smem_u32(smem + kOffBar);
   auto bar = [&](int idx) { return bar0 + 8u * idx; };
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + kOffTmemPtr);
@@ -697,14 +665,15 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const TcParams p) 
           for (int s = 0; s < kSlots; ++s) {
             const WorkList<kFused>& w = s == 0 ? work0 : work1;
             if (it >= w.n_items) continue;
+            const uint32_t bytes = layer_chunk_bytes(l);
             const uint8_t* src = p.pass[w.pass_of(it)].packed + kSmallBytes +
-                                 (size_t)tc_layer_chunk_offset(l) * kChunkBytes * (kSplit3 ? 2 : 1);
+                                 (size_t)tc_layer_byte_offset(l) * (kSplit3 ? 2 : 1);
             const int n_chunks = layer_chunks(l) * (kSplit3 ? 2 : 1);
             for (int c = 0; c < n_chunks; ++c, ++q) {
               const uint32_t stage = q % kStages;
               mbar_wait(bar(kBarWEmpty + stage), ((q / kStages) & 1) ^ 1);
-              mbar_arrive_expect_tx(bar(kBarWFull + stage), kChunkBytes);
-              bulk_copy_g2s(smem_u32(smem + kOffW + stage * kChunkBytes), src + (size_t)c * kChunkBytes, kChunkBytes,
+              mbar_arrive_expect_tx(bar(kBarWFull + stage), bytes);
+              bulk_copy_g2s(smem_u32(smem + kOffW + stage * kChunkBytes), src + (size_t)c * bytes, bytes,
                             bar(kBarWFull + stage));
             }
           }
@@ -713,18 +682,20 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const TcParams p) 
     }
   } else {
     // =================================================================== MMA issuer (warp 9)
-    // The whole warp runs the loop uniformly (so addresses and descriptors stay in uniform registers); one
-    // elected lane issues.  Per chunk: one barrier probe + one PTX block of 4 (BF16X3: 8 / 4) MMAs + commit.
+    // The whole warp runs the loop; one elected lane issues.  Per 16 KiB weight chunk: the (already probed)
+    // full-barrier state, a non-blocking probe of the NEXT stage, then one PTX block of 2 MMAs (N=256, K=16
+    // each; BF16X3: 4 / 2) + the stage-release commit.
     WorkList<kFused> work0(p, blockIdx.x * kSlots + 0, n_slots_total);
     WorkList<kFused> work1(p, blockIdx.x * kSlots + (kSlots - 1), n_slots_total);
     const int n_max = max(work0.n_items, kSlots > 1 ? work1.n_items : 0);
     uint32_t q = 0;
     uint32_t a_parity0 = 0, a_parity1 = 0;
     const uint64_t a_desc0 = make_desc(smem_u32(smem + kOffA)), pe_desc0 = make_desc(smem_u32(smem + kOffPe));
-    const uint64_t w_desc0 = make_desc(smem_u32(smem + kOffW));
+    const uint64_t w_desc0 = make_desc_sw64(smem_u32(smem + kOffW));
     constexpr uint64_t kKBlockUnits = kKBlockBytes >> 4, kAUnits = kABytes >> 4, kChunkUnits = kChunkBytes >> 4;
     long long c_wait_a = 0, c_wait_w = 0;
     const long long c_begin = kProf ? clock64() : 0;
+    bool w_ready = false;  // state of the full barrier of chunk q (probed ahead)
     for (int it = 0; it < n_max; ++it) {
       for (int l = 0; l < kNumMatLayers; ++l) {
 #pragma unroll
@@ -738,10 +709,14 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const TcParams p) 
           }
           if (s == 0) a_parity0 ^= 1; else a_parity1 ^= 1;
           tc_fence_after();
-          const int n_kc = layer_k(l) / 64, n_nh = layer_n(l) / 128;
+          const int n_chunks = layer_chunks(l);
+          const uint32_t idesc = instr_desc(layer_n(l));
+          const uint32_t d_tmem = tmem_base + (uint32_t)(s * 256);
           const uint64_t slot_units = (kSplit3 ? 0 : s);
-          for (int kc = 0; kc < n_kc; ++kc) {
-            // A operand k-block: encoding buffer for M0 and for the first k-block of M5, else the A buffer
+          for (int c = 0; c < n_chunks; ++c) {
+            // A operand: 32 columns (64 B) of a k-block - the encoding buffer for M0 and the first two chunks of
+            // M5, else the A buffer.  kc = 64-column k-block, (c & 1) selects its 64-byte half.
+            const int kc = c >> 1;
             uint64_t a_hi, a_lo;
             if (l == 0 || (l == 5 && kc == 0)) {
               a_hi = pe_desc0 + slot_units * kKBlockUnits;
@@ -751,37 +726,22 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const TcParams p) 
               a_hi = a_desc0 + slot_units * kAUnits + kb * kKBlockUnits;
               a_lo = a_desc0 + kAUnits + kb * kKBlockUnits;
             }
-            if (!kSplit3 && n_nh == 2) {
-              // both column halves of this k-block in one go: two ring stages, eight MMAs, one PTX block
-              const uint32_t st0 = q % kStages, st1 = (q + 1) % kStages;
-              {
+            a_hi += (c & 1) * 4;  // + 64 B
+            a_lo += (c & 1) * 4;
+#pragma unroll
+            for (int part = 0; part < (kSplit3 ? 2 : 1); ++part, ++q) {
+              const uint32_t stage = q % kStages;
+              if (!w_ready) {
                 const long long t0 = kProf ? clock64() : 0;
-                mbar_wait(bar(kBarWFull + st0), (q / kStages) & 1);
-                mbar_wait(bar(kBarWFull + st1), ((q + 1) / kStages) & 1);
+                mbar_wait(bar(kBarWFull + stage), (q / kStages) & 1);
                 if (kProf) c_wait_w += clock64() - t0;
               }
               tc_fence_after();
-              mma_chunk_pair(tmem_base + (uint32_t)(s * 256), a_hi, w_desc0 + st0 * kChunkUnits,
-                             w_desc0 + st1 * kChunkUnits, kc != 0, bar(kBarWEmpty + st0), bar(kBarWEmpty + st1));
-              q += 2;
-              continue;
-            }
-            for (int nh = 0; nh < n_nh; ++nh) {
-              const uint32_t d_tmem = tmem_base + (uint32_t)(s * 256 + nh * 128);
-#pragma unroll
-              for (int part = 0; part < (kSplit3 ? 2 : 1); ++part, ++q) {
-                const uint32_t stage = q % kStages;
-                {
-                  const long long t0 = kProf ? clock64() : 0;
-                  mbar_wait(bar(kBarWFull + stage), (q / kStages) & 1);
-                  if (kProf) c_wait_w += clock64() - t0;
-                }
-                tc_fence_after();
-                const uint64_t b_desc = w_desc0 + stage * kChunkUnits;
-                if (!kSplit3) mma_chunk(d_tmem, a_hi, b_desc, kc != 0, bar(kBarWEmpty + stage));
-                else if (part == 0) mma_chunk_split_hi(d_tmem, a_hi, a_lo, b_desc, kc != 0, bar(kBarWEmpty + stage));
-                else mma_chunk(d_tmem, a_hi, b_desc, 1u, bar(kBarWEmpty + stage));  // hi x W_lo
-              }
+              w_ready = mbar_test_wait(bar(kBarWFull + (q + 1) % kStages), ((q + 1) / kStages) & 1);
+              const uint64_t b_desc = w_desc0 + stage * kChunkUnits;
+              if (!kSplit3) mma_chunk(d_tmem, a_hi, b_desc, c != 0, idesc, bar(kBarWEmpty + stage));
+              else if (part == 0) mma_chunk_split_hi(d_tmem, a_hi, a_lo, b_desc, c != 0, idesc, bar(kBarWEmpty + stage));
+              else mma_chunk(d_tmem, a_hi, b_desc, 1u, idesc, bar(kBarWEmpty + stage));  // hi x W_lo
             }
           }
           umma_commit_elect(bar(kBarDReady + s));

@@ -53,23 +53,24 @@ __global__ void k_pack_fp32(ParamPtrs pp, float* __restrict__ big) {
 template <bool kSplit3>
 __global__ void k_pack_tc(ParamPtrs pp, uint8_t* __restrict__ big) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;  // one bf16 element of the hi image set
-  if (i >= kTcChunks * (kChunkBytes / 2)) return;
-  const int chunk = i / (kChunkBytes / 2), e = i % (kChunkBytes / 2);
+  if (i >= kTcBigBytes / 2) return;
   int l = 0;
-  while (l < kNumMatLayers - 1 && chunk >= tc_layer_chunk_offset(l + 1)) ++l;
-  const int halves = layer_n(l) / 128;
-  const int cl = chunk - tc_layer_chunk_offset(l);
-  const int kc = cl / halves, nh = cl % halves;
-  const int n_local = e / 64, k_local = e % 64;
-  const float w = source_weight(pp, l, nh * 128 + n_local, kc * 64 + k_local);
-  const uint32_t byte = n_local * 128 + ((((k_local >> 3) ^ (n_local & 7))) << 4) + (k_local & 7) * 2;
+  while (l < kNumMatLayers - 1 && 2 * i >= tc_layer_byte_offset(l + 1)) ++l;
+  const int N = layer_n(l);
+  const int e = i - tc_layer_byte_offset(l) / 2;          // element index inside the layer
+  const int chunk = e / (N * kChunkK), r = e % (N * kChunkK);
+  const int n = r / kChunkK, k_local = r % kChunkK;
+  const float w = source_weight(pp, l, n, chunk * kChunkK + k_local);
+  const uint32_t byte = n * 64 + ((((k_local >> 3) ^ ((n >> 1) & 3))) << 4) + (k_local & 7) * 2;
+  const size_t chunk_bytes = (size_t)layer_chunk_bytes(l);
+  const size_t base = (size_t)tc_layer_byte_offset(l) * (kSplit3 ? 2 : 1);
   const __nv_bfloat16 hi = __float2bfloat16_rn(w);
   if (!kSplit3) {
-    *reinterpret_cast<__nv_bfloat16*>(big + (size_t)chunk * kChunkBytes + byte) = hi;
+    *reinterpret_cast<__nv_bfloat16*>(big + base + chunk * chunk_bytes + byte) = hi;
   } else {
     const __nv_bfloat16 lo = __float2bfloat16_rn(w - __bfloat162float(hi));
-    *reinterpret_cast<__nv_bfloat16*>(big + (size_t)(2 * chunk) * kChunkBytes + byte) = hi;
-    *reinterpret_cast<__nv_bfloat16*>(big + (size_t)(2 * chunk + 1) * kChunkBytes + byte) = lo;
+    *reinterpret_cast<__nv_bfloat16*>(big + base + (2 * chunk) * chunk_bytes + byte) = hi;
+    *reinterpret_cast<__nv_bfloat16*>(big + base + (2 * chunk + 1) * chunk_bytes + byte) = lo;
   }
 }
 
@@ -82,7 +83,7 @@ cudaError_t launch_pack_weights(int precision, const float* const params_dev[24]
   if (precision == VIPNERF_PRECISION_FP32) {
     k_pack_fp32<<<(kFp32BigFloats + 255) / 256, 256, 0, s>>>(pp, reinterpret_cast<float*>(big));
   } else {
-    const int n = kTcChunks * (kChunkBytes / 2);
+    const int n = kTcBigBytes / 2;
     if (precision == VIPNERF_PRECISION_BF16X3) k_pack_tc<true><<<(n + 255) / 256, 256, 0, s>>>(pp, big);
     else k_pack_tc<false><<<(n + 255) / 256, 256, 0, s>>>(pp, big);
   }
