@@ -155,34 +155,6 @@ __device__ __forceinline__ void mma_chunk_split_hi(uint32_t d_tmem, uint64_t a_h
       "l"(a_hi), "l"(a_lo), "l"(b_desc), "r"(first_acc), "r"(idesc), "r"(empty_bar)
       : "memory");
 }
-// The bias chunk: one accumulating MMA (BF16X3 hi image: two, A_hi and A_lo), then the stage-release commit.
-__device__ __forceinline__ void mma_bias(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                         uint32_t empty_bar) {
-  asm volatile(
-      "{\n"
-      ".reg .pred t, e;\n"
-      "setp.eq.b32 t, 0, 0;\n"
-      "elect.sync _|e, 0xffffffff;\n"
-      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, t;\n"
-      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%4];\n"
-      "}\n" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(empty_bar)
-      : "memory");
-}
-__device__ __forceinline__ void mma_bias_split_hi(uint32_t d_tmem, uint64_t a_hi, uint64_t a_lo, uint64_t b_desc,
-                                                  uint32_t idesc, uint32_t empty_bar) {
-  asm volatile(
-      "{\n"
-      ".reg .pred t, e;\n"
-      "setp.eq.b32 t, 0, 0;\n"
-      "elect.sync _|e, 0xffffffff;\n"
-      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %3, %4, t;\n"
-      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %2, %3, %4, t;\n"
-      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%5];\n"
-      "}\n" ::"r"(d_tmem),
-      "l"(a_hi), "l"(a_lo), "l"(b_desc), "r"(idesc), "r"(empty_bar)
-      : "memory");
-}
 __device__ __forceinline__ void umma_commit_elect(uint32_t bar) {
   asm volatile(
       "{\n.reg .pred e;\nelect.sync _|e, 0xffffffff;\n"
@@ -331,7 +303,7 @@ __device__ __forceinline__ void sincos_octave(float t_hi, float t_lo, int k, flo
   }
 }
 
-// Row `row` of the slot's encoding buffer <- bf16(gamma(point)), 64 columns (63 + the constant 1).
+// Row `row` of the slot's encoding buffer <- bf16(gamma(point)), 64 columns (63 + zero pad).
 // Column order of PositionalEncoder.encode (VipNeRF01.py:439-448): x(3), then per octave sin(3), cos(3).
 template <bool kSplit3>
 __device__ __forceinline__ void write_point_encoding(uint8_t* smem, int slot, int row, float x, float y, float z) {
@@ -345,7 +317,7 @@ __device__ __forceinline__ void write_point_encoding(uint8_t* smem, int slot, in
 #pragma unroll
     for (int k = 0; k < kLPts; ++k) sincos_octave<kSplit3>(t_hi, t_lo, k, v[3 + 6 * k + a], v[6 + 6 * k + a]);
   }
-  v[63] = 1.f;  // constant-one column: carries the layer biases through the tensor core (layout.cuh)
+  v[63] = 0.f;
   const uint32_t hi_base = smem_u32(smem + kOffPe + (kSplit3 ? 0 : slot) * kKBlockBytes) + row * 128;
   const uint32_t lo_base = smem_u32(smem + kOffPe + kKBlockBytes) + row * 128;
 #pragma unroll
@@ -364,13 +336,13 @@ __device__ __forceinline__ void write_point_encoding(uint8_t* smem, int slot, in
   }
 }
 
-// One trunk / feature layer epilogue for one row: accumulator (256 fp32 TMEM columns, bias already added by the
-// tensor core) (-> ReLU) -> bf16 -> A buffer (in place).  kSigma additionally accumulates the density head on the
-// fp32 activations.  The eight 32-column TMEM loads are software-pipelined: block cb+1 is in flight while block cb
-// is processed (tcgen05.wait::ld waits for everything outstanding, so the next load is issued right after it).
+// One trunk / feature layer epilogue for one row: accumulator (256 fp32 TMEM columns) -> +bias (-> ReLU) -> bf16
+// -> A buffer (in place).  kSigma additionally accumulates the density head on the fp32 activations.
+// The eight 32-column TMEM loads are software-pipelined: block cb+1 is in flight while block cb is processed
+// (tcgen05.wait::ld waits for everything outstanding, so the next load is issued right after the wait).
 template <bool kSplit3, bool kRelu, bool kSigma>
 __device__ __forceinline__ float layer_epilogue(uint8_t* smem, int slot, int row, uint32_t taddr,
-                                                const float* __restrict__ w_sigma) {
+                                                const float* __restrict__ bias, const float* __restrict__ w_sigma) {
   float sigma_acc = 0.f;
   const uint32_t hi_base = smem_u32(smem + kOffA + (kSplit3 ? 0 : slot) * kABytes) + row * 128;
   const uint32_t lo_base = smem_u32(smem + kOffA + kABytes) + row * 128;
@@ -378,26 +350,25 @@ __device__ __forceinline__ float layer_epilogue(uint8_t* smem, int slot, int row
   tmem_ld32(taddr, v[0]);
 #pragma unroll
   for (int cb = 0; cb < 8; ++cb) {
-    float ws[32];
-    if (kSigma) {
+    float b[32];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const float4 t = __ldg(reinterpret_cast<const float4*>(w_sigma + cb * 32) + q);
-        ws[4 * q] = t.x; ws[4 * q + 1] = t.y; ws[4 * q + 2] = t.z; ws[4 * q + 3] = t.w;
-      }
+    for (int q = 0; q < 8; ++q) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(bias + cb * 32) + q);
+      b[4 * q] = t.x; b[4 * q + 1] = t.y; b[4 * q + 2] = t.z; b[4 * q + 3] = t.w;
     }
     tmem_ld_wait();
     if (cb + 1 < 8) tmem_ld32(taddr + (cb + 1) * 32, v[(cb + 1) & 1]);
     const uint32_t kb_off = (uint32_t)(cb >> 1) * kKBlockBytes;
     if (!kSplit3 && !kSigma) {
-      // throughput path: ReLU fused into the bf16x2 conversion - one instruction per two elements
+      // throughput path: FADD2 for the bias, ReLU fused into the bf16x2 conversion (1 instruction / element)
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         uint32_t w[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int e = 8 * j + 2 * q;
-          w[q] = cvt_bf16x2<kRelu>(pack_f32x2(__uint_as_float(v[cb & 1][e]), __uint_as_float(v[cb & 1][e + 1])));
+          const uint64_t acc = pack_f32x2(__uint_as_float(v[cb & 1][e]), __uint_as_float(v[cb & 1][e + 1]));
+          w[q] = cvt_bf16x2<kRelu>(fadd2(acc, pack_f32x2(b[e], b[e + 1])));
         }
         const int ch = (cb & 1) * 4 + j;
         st_shared_v4(hi_base + kb_off + (uint32_t)((ch ^ (row & 7)) << 4), w[0], w[1], w[2], w[3]);
@@ -407,12 +378,18 @@ __device__ __forceinline__ float layer_epilogue(uint8_t* smem, int slot, int row
     float h[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
-      h[j] = __uint_as_float(v[cb & 1][j]);
+      h[j] = __uint_as_float(v[cb & 1][j]) + b[j];
       if (kRelu) h[j] = fmaxf(h[j], 0.f);
     }
     if (kSigma) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) sigma_acc = fmaf(h[j], ws[j], sigma_acc);
+      for (int q = 0; q < 8; ++q) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(w_sigma + cb * 32) + q);
+        sigma_acc = fmaf(h[4 * q], t.x, sigma_acc);
+        sigma_acc = fmaf(h[4 * q + 1], t.y, sigma_acc);
+        sigma_acc = fmaf(h[4 * q + 2], t.z, sigma_acc);
+        sigma_acc = fmaf(h[4 * q + 3], t.w, sigma_acc);
+      }
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -596,9 +573,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const TcParams p) 
           tc_fence_after();
           const long long t1 = kProf ? clock64() : 0;
           c_wait += t1 - t0;
-          if (l == 7) sigma_lin = layer_epilogue<kSplit3, true, true>(smem, slot, row, taddr, small + kOffWSigma);
-          else if (l == 8) layer_epilogue<kSplit3, false, false>(smem, slot, row, taddr, nullptr);
-          else layer_epilogue<kSplit3, true, false>(smem, slot, row, taddr, nullptr);
+          const float* bias = small + kOffBias + l * 256;
+          if (l == 7) sigma_lin = layer_epilogue<kSplit3, true, true>(smem, slot, row, taddr, bias, small + kOffWSigma);
+          else if (l == 8) layer_epilogue<kSplit3, false, false>(smem, slot, row, taddr, bias, nullptr);
+          else layer_epilogue<kSplit3, true, false>(smem, slot, row, taddr, bias, nullptr);
           fence_proxy_async();
           tc_fence_before();
           mbar_arrive(bar(kBarAReady + slot));
@@ -690,7 +668,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const TcParams p) 
             const uint32_t bytes = layer_chunk_bytes(l);
             const uint8_t* src = p.pass[w.pass_of(it)].packed + kSmallBytes +
                                  (size_t)tc_layer_byte_offset(l) * (kSplit3 ? 2 : 1);
-            const int n_chunks = layer_stream_chunks(l) * (kSplit3 ? 2 : 1);
+            const int n_chunks = layer_chunks(l) * (kSplit3 ? 2 : 1);
             for (int c = 0; c < n_chunks; ++c, ++q) {
               const uint32_t stage = q % kStages;
               mbar_wait(bar(kBarWEmpty + stage), ((q / kStages) & 1) ^ 1);
@@ -731,18 +709,16 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const TcParams p) 
           }
           if (s == 0) a_parity0 ^= 1; else a_parity1 ^= 1;
           tc_fence_after();
-          const int n_chunks = layer_stream_chunks(l);
-          const int n_weight_chunks = layer_chunks(l);
+          const int n_chunks = layer_chunks(l);
           const uint32_t idesc = instr_desc(layer_n(l));
           const uint32_t d_tmem = tmem_base + (uint32_t)(s * 256);
           const uint64_t slot_units = (kSplit3 ? 0 : s);
           for (int c = 0; c < n_chunks; ++c) {
-            // A operand: 32 columns (64 B) of a k-block - the encoding buffer for M0, the first two chunks of M5
-            // and every bias chunk, else the A buffer.  kc = 64-column k-block, (c & 1) selects its 64-byte half.
-            const bool bias_chunk = c == n_weight_chunks;
+            // A operand: 32 columns (64 B) of a k-block - the encoding buffer for M0 and the first two chunks of
+            // M5, else the A buffer.  kc = 64-column k-block, (c & 1) selects its 64-byte half.
             const int kc = c >> 1;
             uint64_t a_hi, a_lo;
-            if (l == 0 || (l == 5 && kc == 0) || bias_chunk) {
+            if (l == 0 || (l == 5 && kc == 0)) {
               a_hi = pe_desc0 + slot_units * kKBlockUnits;
               a_lo = pe_desc0 + kKBlockUnits;
             } else {
@@ -750,9 +726,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const TcParams p) 
               a_hi = a_desc0 + slot_units * kAUnits + kb * kKBlockUnits;
               a_lo = a_desc0 + kAUnits + kb * kKBlockUnits;
             }
-            const uint64_t half = bias_chunk ? 4 : (uint64_t)(c & 1) * 4;  // + 64 B: columns 32..63 of the k-block
-            a_hi += half;
-            a_lo += half;
+            a_hi += (c & 1) * 4;  // + 64 B
+            a_lo += (c & 1) * 4;
 #pragma unroll
             for (int part = 0; part < (kSplit3 ? 2 : 1); ++part, ++q) {
               const uint32_t stage = q % kStages;
@@ -764,17 +739,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const TcParams p) 
               tc_fence_after();
               w_ready = mbar_test_wait(bar(kBarWFull + (q + 1) % kStages), ((q + 1) / kStages) & 1);
               const uint64_t b_desc = w_desc0 + stage * kChunkUnits;
-              if (bias_chunk) {
-                // only the second K=16 step carries data (encoding columns 48..63 x chunk columns 16..31)
-                if (!kSplit3 || part == 1) mma_bias(d_tmem, a_hi + 2, b_desc + 2, idesc, bar(kBarWEmpty + stage));
-                else mma_bias_split_hi(d_tmem, a_hi + 2, a_lo + 2, b_desc + 2, idesc, bar(kBarWEmpty + stage));
-              } else if (!kSplit3) {
-                mma_chunk(d_tmem, a_hi, b_desc, c != 0, idesc, bar(kBarWEmpty + stage));
-              } else if (part == 0) {
-                mma_chunk_split_hi(d_tmem, a_hi, a_lo, b_desc, c != 0, idesc, bar(kBarWEmpty + stage));
-              } else {
-                mma_chunk(d_tmem, a_hi, b_desc, 1u, idesc, bar(kBarWEmpty + stage));  // hi x W_lo
-              }
+              if (!kSplit3) mma_chunk(d_tmem, a_hi, b_desc, c != 0, idesc, bar(kBarWEmpty + stage));
+              else if (part == 0) mma_chunk_split_hi(d_tmem, a_hi, a_lo, b_desc, c != 0, idesc, bar(kBarWEmpty + stage));
+              else mma_chunk(d_tmem, a_hi, b_desc, 1u, idesc, bar(kBarWEmpty + stage));  // hi x W_lo
             }
           }
           umma_commit_elect(bar(kBarDReady + s));
