@@ -155,6 +155,139 @@ __device__ __forceinline__ void mma_chunk_split_hi(uint32_t d_tmem, uint64_t a_h
       "l"(a_hi), "l"(a_lo), "l"(b_desc), "r"(first_acc), "r"(idesc), "r"(empty_bar)
       : "memory");
 }
+// The MMA issue loop of one run of `n_chunks` consecutive weight chunks, hand-written in PTX so that the per-chunk
+// cost is ~25 instructions (ptxas turns the equivalent C++ into ~135 with reconvergence barriers and R2UR moves,
+// which made the issuing warp - not the tensor pipe - the bottleneck).  Chunk c multiplies A columns
+// [32c, 32c+32) - k-block c>>1 (1024 descriptor units apart), 64-byte half c&1 (4 units) - with ring stage q&3
+// (1024 units apart), waits the stage's full barrier (parity (q>>2)&1), issues two N x K=16 MMAs from the elected
+// lane and commits the stage's empty barrier.  Returns the advanced chunk counter q.
+__device__ __forceinline__ uint32_t issue_chunks(uint32_t d_tmem, uint64_t a_desc, uint64_t w_desc0, uint32_t bar_full0,
+                                                 uint32_t bar_empty0, uint32_t q, uint32_t n_chunks, uint32_t first_acc,
+                                                 uint32_t idesc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p, pw, e, pacc, pt;\n"
+      ".reg .b32 c, stage, par, fb, eb, t, spins;\n"
+      ".reg .b64 a, b, a1, b1, t64;\n"
+      "mov.u32 c, 0;\n"
+      "setp.ne.b32 pacc, %7, 0;\n"
+      "setp.eq.b32 pt, 0, 0;\n"
+      "elect.sync _|e, 0xffffffff;\n"
+      "CHUNK_LOOP:\n"
+      "and.b32 stage, %0, 3;\n"
+      "shr.u32 par, %0, 2;\n"
+      "and.b32 par, par, 1;\n"
+      "shl.b32 t, stage, 3;\n"
+      "add.u32 fb, %4, t;\n"
+      "add.u32 eb, %5, t;\n"
+      "mov.u32 spins, 0;\n"
+      "CHUNK_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 pw, [fb], par;\n"
+      "@pw bra CHUNK_READY;\n"
+      "add.u32 spins, spins, 1;\n"
+      "setp.gt.u32 p, spins, 4000000;\n"
+      "@p trap;\n"
+      "bra CHUNK_WAIT;\n"
+      "CHUNK_READY:\n"
+      "tcgen05.fence::after_thread_sync;\n"
+      "mul.wide.u32 b, stage, 1024;\n"
+      "add.s64 b, b, %3;\n"
+      "shr.u32 t, c, 1;\n"
+      "mul.wide.u32 a, t, 1024;\n"
+      "and.b32 t, c, 1;\n"
+      "mul.wide.u32 t64, t, 4;\n"
+      "add.s64 a, a, t64;\n"
+      "add.s64 a, a, %2;\n"
+      "add.s64 a1, a, 2;\n"
+      "add.s64 b1, b, 2;\n"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%1], a, b, %8, pacc;\n"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%1], a1, b1, %8, pt;\n"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [eb];\n"
+      "setp.eq.b32 pacc, 0, 0;\n"
+      "add.u32 %0, %0, 1;\n"
+      "add.u32 c, c, 1;\n"
+      "setp.lt.u32 p, c, %6;\n"
+      "@p bra CHUNK_LOOP;\n"
+      "}\n"
+      : "+r"(q)
+      : "r"(d_tmem), "l"(a_desc), "l"(w_desc0), "r"(bar_full0), "r"(bar_empty0), "r"(n_chunks), "r"(first_acc),
+        "r"(idesc)
+      : "memory");
+  return q;
+}
+// BF16X3 variant: every weight chunk is two ring stages (hi image, lo image); per chunk
+// A_hi*W_hi + A_lo*W_hi (4 MMAs, commit) then A_hi*W_lo (2 MMAs, commit).
+__device__ __forceinline__ uint32_t issue_chunks_split(uint32_t d_tmem, uint64_t a_hi_desc, uint64_t a_lo_desc,
+                                                       uint64_t w_desc0, uint32_t bar_full0, uint32_t bar_empty0,
+                                                       uint32_t q, uint32_t n_chunks, uint32_t first_acc,
+                                                       uint32_t idesc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p, pw, e, pacc, pt;\n"
+      ".reg .b32 c, stage, par, fb, eb, t, spins, part;\n"
+      ".reg .b64 a, l, b, a1, l1, b1, t64, off;\n"
+      "mov.u32 c, 0;\n"
+      "setp.ne.b32 pacc, %8, 0;\n"
+      "setp.eq.b32 pt, 0, 0;\n"
+      "elect.sync _|e, 0xffffffff;\n"
+      "SCHUNK_LOOP:\n"
+      "mov.u32 part, 0;\n"
+      "shr.u32 t, c, 1;\n"
+      "mul.wide.u32 off, t, 1024;\n"
+      "and.b32 t, c, 1;\n"
+      "mul.wide.u32 t64, t, 4;\n"
+      "add.s64 off, off, t64;\n"
+      "add.s64 a, off, %2;\n"
+      "add.s64 l, off, %3;\n"
+      "add.s64 a1, a, 2;\n"
+      "add.s64 l1, l, 2;\n"
+      "SPART_LOOP:\n"
+      "and.b32 stage, %0, 3;\n"
+      "shr.u32 par, %0, 2;\n"
+      "and.b32 par, par, 1;\n"
+      "shl.b32 t, stage, 3;\n"
+      "add.u32 fb, %5, t;\n"
+      "add.u32 eb, %6, t;\n"
+      "mov.u32 spins, 0;\n"
+      "SCHUNK_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 pw, [fb], par;\n"
+      "@pw bra SCHUNK_READY;\n"
+      "add.u32 spins, spins, 1;\n"
+      "setp.gt.u32 p, spins, 4000000;\n"
+      "@p trap;\n"
+      "bra SCHUNK_WAIT;\n"
+      "SCHUNK_READY:\n"
+      "tcgen05.fence::after_thread_sync;\n"
+      "mul.wide.u32 b, stage, 1024;\n"
+      "add.s64 b, b, %4;\n"
+      "add.s64 b1, b, 2;\n"
+      "setp.eq.u32 p, part, 0;\n"
+      "@!p bra SLO_IMAGE;\n"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%1], a, b, %9, pacc;\n"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%1], l, b, %9, pt;\n"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%1], a1, b1, %9, pt;\n"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%1], l1, b1, %9, pt;\n"
+      "bra SPART_DONE;\n"
+      "SLO_IMAGE:\n"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%1], a, b, %9, pt;\n"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%1], a1, b1, %9, pt;\n"
+      "SPART_DONE:\n"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [eb];\n"
+      "setp.eq.b32 pacc, 0, 0;\n"
+      "add.u32 %0, %0, 1;\n"
+      "add.u32 part, part, 1;\n"
+      "setp.lt.u32 p, part, 2;\n"
+      "@p bra SPART_LOOP;\n"
+      "add.u32 c, c, 1;\n"
+      "setp.lt.u32 p, c, %7;\n"
+      "@p bra SCHUNK_LOOP;\n"
+      "}\n"
+      : "+r"(q)
+      : "r"(d_tmem), "l"(a_hi_desc), "l"(a_lo_desc), "l"(w_desc0), "r"(bar_full0), "r"(bar_empty0), "r"(n_chunks),
+        "r"(first_acc), "r"(idesc)
+      : "memory");
+  return q;
+}
 __device__ __forceinline__ void umma_commit_elect(uint32_t bar) {
   asm volatile(
       "{\n.reg .pred e;\nelect.sync _|e, 0xffffffff;\n"
@@ -682,9 +815,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const TcParams p) 
     }
   } else {
     // =================================================================== MMA issuer (warp 9)
-    // The whole warp runs the loop; one elected lane issues.  Per 16 KiB weight chunk: the (already probed)
-    // full-barrier state, a non-blocking probe of the NEXT stage, then one PTX block of 2 MMAs (N=256, K=16
-    // each; BF16X3: 4 / 2) + the stage-release commit.
+    // The whole warp runs the loop; one elected lane issues.  Per (tile, layer, slot) step: wait a_ready, run the
+    // PTX chunk loop(s) over the layer's A operand (encoding buffer for M0 and the first 64 columns of M5, the A
+    // buffer otherwise), commit d_ready.
     WorkList<kFused> work0(p, blockIdx.x * kSlots + 0, n_slots_total);
     WorkList<kFused> work1(p, blockIdx.x * kSlots + (kSlots - 1), n_slots_total);
     const int n_max = max(work0.n_items, kSlots > 1 ? work1.n_items : 0);
@@ -692,10 +825,11 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const TcParams p) 
     uint32_t a_parity0 = 0, a_parity1 = 0;
     const uint64_t a_desc0 = make_desc(smem_u32(smem + kOffA)), pe_desc0 = make_desc(smem_u32(smem + kOffPe));
     const uint64_t w_desc0 = make_desc_sw64(smem_u32(smem + kOffW));
-    constexpr uint64_t kKBlockUnits = kKBlockBytes >> 4, kAUnits = kABytes >> 4, kChunkUnits = kChunkBytes >> 4;
-    long long c_wait_a = 0, c_wait_w = 0;
+    constexpr uint64_t kKBlockUnits = kKBlockBytes >> 4, kAUnits = kABytes >> 4;
+    static_assert(kKBlockUnits == 1024 && (kChunkBytes >> 4) == 1024 && kStages == 4, "issue_chunks assumes these");
+    const uint32_t bar_full0 = bar(kBarWFull), bar_empty0 = bar(kBarWEmpty);
+    long long c_wait_a = 0;
     const long long c_begin = kProf ? clock64() : 0;
-    bool w_ready = false;  // state of the full barrier of chunk q (probed ahead)
     for (int it = 0; it < n_max; ++it) {
       for (int l = 0; l < kNumMatLayers; ++l) {
 #pragma unroll
@@ -709,39 +843,28 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const TcParams p) 
           }
           if (s == 0) a_parity0 ^= 1; else a_parity1 ^= 1;
           tc_fence_after();
-          const int n_chunks = layer_chunks(l);
           const uint32_t idesc = instr_desc(layer_n(l));
           const uint32_t d_tmem = tmem_base + (uint32_t)(s * 256);
           const uint64_t slot_units = (kSplit3 ? 0 : s);
-          for (int c = 0; c < n_chunks; ++c) {
-            // A operand: 32 columns (64 B) of a k-block - the encoding buffer for M0 and the first two chunks of
-            // M5, else the A buffer.  kc = 64-column k-block, (c & 1) selects its 64-byte half.
-            const int kc = c >> 1;
-            uint64_t a_hi, a_lo;
-            if (l == 0 || (l == 5 && kc == 0)) {
-              a_hi = pe_desc0 + slot_units * kKBlockUnits;
-              a_lo = pe_desc0 + kKBlockUnits;
+          const uint64_t pe_hi = pe_desc0 + slot_units * kKBlockUnits, pe_lo = pe_desc0 + kKBlockUnits;
+          const uint64_t a_hi = a_desc0 + slot_units * kAUnits, a_lo = a_desc0 + kAUnits;
+          if (!kSplit3) {
+            if (l == 0) {
+              q = issue_chunks(d_tmem, pe_hi, w_desc0, bar_full0, bar_empty0, q, 2, 0, idesc);
+            } else if (l == 5) {
+              q = issue_chunks(d_tmem, pe_hi, w_desc0, bar_full0, bar_empty0, q, 2, 0, idesc);
+              q = issue_chunks(d_tmem, a_hi, w_desc0, bar_full0, bar_empty0, q, 8, 1, idesc);
             } else {
-              const int kb = l == 5 ? kc - 1 : kc;
-              a_hi = a_desc0 + slot_units * kAUnits + kb * kKBlockUnits;
-              a_lo = a_desc0 + kAUnits + kb * kKBlockUnits;
+              q = issue_chunks(d_tmem, a_hi, w_desc0, bar_full0, bar_empty0, q, 8, 0, idesc);
             }
-            a_hi += (c & 1) * 4;  // + 64 B
-            a_lo += (c & 1) * 4;
-#pragma unroll
-            for (int part = 0; part < (kSplit3 ? 2 : 1); ++part, ++q) {
-              const uint32_t stage = q % kStages;
-              if (!w_ready) {
-                const long long t0 = kProf ? clock64() : 0;
-                mbar_wait(bar(kBarWFull + stage), (q / kStages) & 1);
-                if (kProf) c_wait_w += clock64() - t0;
-              }
-              tc_fence_after();
-              w_ready = mbar_test_wait(bar(kBarWFull + (q + 1) % kStages), ((q + 1) / kStages) & 1);
-              const uint64_t b_desc = w_desc0 + stage * kChunkUnits;
-              if (!kSplit3) mma_chunk(d_tmem, a_hi, b_desc, c != 0, idesc, bar(kBarWEmpty + stage));
-              else if (part == 0) mma_chunk_split_hi(d_tmem, a_hi, a_lo, b_desc, c != 0, idesc, bar(kBarWEmpty + stage));
-              else mma_chunk(d_tmem, a_hi, b_desc, 1u, idesc, bar(kBarWEmpty + stage));  // hi x W_lo
+          } else {
+            if (l == 0) {
+              q = issue_chunks_split(d_tmem, pe_hi, pe_lo, w_desc0, bar_full0, bar_empty0, q, 2, 0, idesc);
+            } else if (l == 5) {
+              q = issue_chunks_split(d_tmem, pe_hi, pe_lo, w_desc0, bar_full0, bar_empty0, q, 2, 0, idesc);
+              q = issue_chunks_split(d_tmem, a_hi, a_lo, w_desc0, bar_full0, bar_empty0, q, 8, 1, idesc);
+            } else {
+              q = issue_chunks_split(d_tmem, a_hi, a_lo, w_desc0, bar_full0, bar_empty0, q, 8, 0, idesc);
             }
           }
           umma_commit_elect(bar(kBarDReady + s));
@@ -750,7 +873,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const TcParams p) 
     }
     tc_fence_before();
     if (kProf && p.prof != nullptr && blockIdx.x == 0 && lane == 0) {
-      p.prof[32] = c_wait_a; p.prof[33] = c_wait_w; p.prof[34] = (unsigned long long)(clock64() - c_begin);
+      p.prof[32] = c_wait_a; p.prof[33] = 0; p.prof[34] = (unsigned long long)(clock64() - c_begin);
       p.prof[35] = q;
     }
   }
