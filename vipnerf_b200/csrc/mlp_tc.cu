@@ -27,6 +27,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <mutex>
 
 #include "kernels.h"
@@ -36,7 +37,7 @@ namespace vipnerf {
 namespace {
 
 constexpr int kTile = 128;
-constexpr int kStages = 4;
+constexpr int kMaxStages = 8;  // weight-ring stages: 4 x 16 KiB (one CTA per tile pair) or 8 x 8 KiB (CTA pairs)
 constexpr int kNumThreads = 320;
 constexpr uint32_t kABytes = 65536;
 constexpr uint32_t kKBlockBytes = 16384;
@@ -44,19 +45,19 @@ constexpr uint32_t kOffA = 0;                 // 2 x 64 KiB
 constexpr uint32_t kOffPe = 131072;           // 2 x 16 KiB
 constexpr uint32_t kOffW = 163840;            // 4 x 16 KiB
 constexpr uint32_t kOffTail = 229376;
-constexpr uint32_t kOffBar = kOffTail;        // 12 mbarriers
-constexpr uint32_t kOffTmemPtr = kOffTail + 128;
+constexpr uint32_t kOffBar = kOffTail;        // 28 mbarriers
+constexpr uint32_t kOffTmemPtr = kOffTail + 240;
 constexpr uint32_t kOffVb = kOffTail + 256;   // [2 slots][2 rays][128] fp32: view-direction part of M9 + bias
 constexpr uint32_t kOffPev = kOffVb + 2048;   // [2 slots][2 rays][32]  fp32: view-direction encodings
 constexpr uint32_t kSmemBytes = kOffPev + 512;
 static_assert(kSmemBytes <= 232448, "exceeds the 227 KiB per-CTA shared memory limit");
 
-enum { kBarWFull = 0, kBarWEmpty = 4, kBarAReady = 8, kBarDReady = 10 };
+enum { kBarWFull = 0, kBarWEmpty = 8, kBarAReady = 16, kBarDReady = 18, kBarLocalFull = 20 };
 
 // tcgen05 instruction descriptor: D=F32, A=B=BF16, both K-major, M=128, N=n (cute::UMMA::InstrDescriptor bits:
 // c_format[4,6)=1, a_format[7,10)=1, b_format[10,13)=1, n_dim[17,23)=N>>3, m_dim[24,29)=M>>4)
-constexpr uint32_t instr_desc(uint32_t n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24);
+constexpr uint32_t instr_desc(uint32_t n, uint32_t m = 128) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
 }
 
 constexpr long long kTimeoutCycles = 4000000000ll;  // ~2 s: a protocol bug traps instead of hanging the GPU
@@ -84,7 +85,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 }
 __device__ __noinline__ void mbar_timeout(uint32_t bar, uint32_t parity) {
   printf("vipnerf: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x,
-         (bar - kOffBar) / 8 % 16, parity);
+         (bar / 8) % 32, parity);
   __trap();
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
@@ -104,6 +105,23 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void group_sync(int group) {  // named barrier over one epilogue group (128 threads)
   asm volatile("bar.sync %0, 128;" ::"r"(group + 1) : "memory");
+}
+// ---- thread-block-cluster (CTA pair) helpers
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t rank) {  // shared::cta -> shared::cluster
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // mbarrier.test_wait: non-blocking probe (try_wait may suspend the warp when the phase is not complete)
 __device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
@@ -156,19 +174,24 @@ __device__ __forceinline__ void mma_chunk_split_hi(uint32_t d_tmem, uint64_t a_h
       : "memory");
 }
 // The MMA issue loop of one run of `n_chunks` consecutive weight chunks, hand-written in PTX so that the per-chunk
-// cost is ~25 instructions (ptxas turns the equivalent C++ into ~135 with reconvergence barriers and R2UR moves,
-// which made the issuing warp - not the tensor pipe - the bottleneck).  Chunk c multiplies A columns
-// [32c, 32c+32) - k-block c>>1 (1024 descriptor units apart), 64-byte half c&1 (4 units) - with ring stage q&3
-// (1024 units apart), waits the stage's full barrier (parity (q>>2)&1), issues two N x K=16 MMAs from the elected
-// lane and commits the stage's empty barrier.  Returns the advanced chunk counter q.
+// cost is ~25 instructions (ptxas turns the equivalent C++ into ~135 with reconvergence barriers and R2UR moves).
+// Chunk c multiplies A columns [32c, 32c+32) - k-block c>>1 (1024 descriptor units apart), 64-byte half c&1
+// (4 units) - with ring stage q mod kStages, waits the stage's full barrier, issues two N x K=16 MMAs from the
+// elected lane and commits the stage's empty barrier.  Returns the advanced chunk counter q.
+//   single CTA : 4 stages x 16 KiB (1024 units), tcgen05.mma.cta_group::1, M=128
+//   CTA pair   : 8 stages x  8 KiB ( 512 units: each CTA holds half of the chunk's rows), cta_group::2, M=256,
+//                commits multicast to both CTAs' barriers
+// The *_split variants are BF16X3: every weight chunk is two ring stages (hi image, lo image); per chunk
+// A_hi*W_hi + A_lo*W_hi (4 MMAs, commit) then A_hi*W_lo (2 MMAs, commit).
 __device__ __forceinline__ uint32_t issue_chunks(uint32_t d_tmem, uint64_t a_desc, uint64_t w_desc0, uint32_t bar_full0,
-                                                 uint32_t bar_empty0, uint32_t q, uint32_t n_chunks, uint32_t first_acc,
-                                                 uint32_t idesc) {
+        uint32_t bar_empty0, uint32_t q, uint32_t n_chunks, uint32_t first_acc, uint32_t idesc) {
   asm volatile(
       "{\n"
       ".reg .pred p, pw, e, pacc, pt;\n"
       ".reg .b32 c, stage, par, fb, eb, t, spins;\n"
       ".reg .b64 a, b, a1, b1, t64;\n"
+      ".reg .b16 mc;\n"
+      "mov.b16 mc, 3;\n"
       "mov.u32 c, 0;\n"
       "setp.ne.b32 pacc, %7, 0;\n"
       "setp.eq.b32 pt, 0, 0;\n"
@@ -215,17 +238,70 @@ __device__ __forceinline__ uint32_t issue_chunks(uint32_t d_tmem, uint64_t a_des
       : "memory");
   return q;
 }
-// BF16X3 variant: every weight chunk is two ring stages (hi image, lo image); per chunk
-// A_hi*W_hi + A_lo*W_hi (4 MMAs, commit) then A_hi*W_lo (2 MMAs, commit).
-__device__ __forceinline__ uint32_t issue_chunks_split(uint32_t d_tmem, uint64_t a_hi_desc, uint64_t a_lo_desc,
-                                                       uint64_t w_desc0, uint32_t bar_full0, uint32_t bar_empty0,
-                                                       uint32_t q, uint32_t n_chunks, uint32_t first_acc,
-                                                       uint32_t idesc) {
+__device__ __forceinline__ uint32_t issue_chunks_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t w_desc0, uint32_t bar_full0,
+        uint32_t bar_empty0, uint32_t q, uint32_t n_chunks, uint32_t first_acc, uint32_t idesc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p, pw, e, pacc, pt;\n"
+      ".reg .b32 c, stage, par, fb, eb, t, spins;\n"
+      ".reg .b64 a, b, a1, b1, t64;\n"
+      ".reg .b16 mc;\n"
+      "mov.b16 mc, 3;\n"
+      "mov.u32 c, 0;\n"
+      "setp.ne.b32 pacc, %7, 0;\n"
+      "setp.eq.b32 pt, 0, 0;\n"
+      "elect.sync _|e, 0xffffffff;\n"
+      "CHUNK_LOOP:\n"
+      "and.b32 stage, %0, 7;\n"
+      "shr.u32 par, %0, 3;\n"
+      "and.b32 par, par, 1;\n"
+      "shl.b32 t, stage, 3;\n"
+      "add.u32 fb, %4, t;\n"
+      "add.u32 eb, %5, t;\n"
+      "mov.u32 spins, 0;\n"
+      "CHUNK_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 pw, [fb], par;\n"
+      "@pw bra CHUNK_READY;\n"
+      "add.u32 spins, spins, 1;\n"
+      "setp.gt.u32 p, spins, 4000000;\n"
+      "@p trap;\n"
+      "bra CHUNK_WAIT;\n"
+      "CHUNK_READY:\n"
+      "tcgen05.fence::after_thread_sync;\n"
+      "mul.wide.u32 b, stage, 512;\n"
+      "add.s64 b, b, %3;\n"
+      "shr.u32 t, c, 1;\n"
+      "mul.wide.u32 a, t, 1024;\n"
+      "and.b32 t, c, 1;\n"
+      "mul.wide.u32 t64, t, 4;\n"
+      "add.s64 a, a, t64;\n"
+      "add.s64 a, a, %2;\n"
+      "add.s64 a1, a, 2;\n"
+      "add.s64 b1, b, 2;\n"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%1], a, b, %8, pacc;\n"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%1], a1, b1, %8, pt;\n"
+      "@e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [eb], mc;\n"
+      "setp.eq.b32 pacc, 0, 0;\n"
+      "add.u32 %0, %0, 1;\n"
+      "add.u32 c, c, 1;\n"
+      "setp.lt.u32 p, c, %6;\n"
+      "@p bra CHUNK_LOOP;\n"
+      "}\n"
+      : "+r"(q)
+      : "r"(d_tmem), "l"(a_desc), "l"(w_desc0), "r"(bar_full0), "r"(bar_empty0), "r"(n_chunks), "r"(first_acc),
+        "r"(idesc)
+      : "memory");
+  return q;
+}
+__device__ __forceinline__ uint32_t issue_chunks_split(uint32_t d_tmem, uint64_t a_hi_desc, uint64_t a_lo_desc, uint64_t w_desc0,
+        uint32_t bar_full0, uint32_t bar_empty0, uint32_t q, uint32_t n_chunks, uint32_t first_acc, uint32_t idesc) {
   asm volatile(
       "{\n"
       ".reg .pred p, pw, e, pacc, pt;\n"
       ".reg .b32 c, stage, par, fb, eb, t, spins, part;\n"
       ".reg .b64 a, l, b, a1, l1, b1, t64, off;\n"
+      ".reg .b16 mc;\n"
+      "mov.b16 mc, 3;\n"
       "mov.u32 c, 0;\n"
       "setp.ne.b32 pacc, %8, 0;\n"
       "setp.eq.b32 pt, 0, 0;\n"
@@ -288,10 +364,87 @@ __device__ __forceinline__ uint32_t issue_chunks_split(uint32_t d_tmem, uint64_t
       : "memory");
   return q;
 }
+__device__ __forceinline__ uint32_t issue_chunks_split_pair(uint32_t d_tmem, uint64_t a_hi_desc, uint64_t a_lo_desc, uint64_t w_desc0,
+        uint32_t bar_full0, uint32_t bar_empty0, uint32_t q, uint32_t n_chunks, uint32_t first_acc, uint32_t idesc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p, pw, e, pacc, pt;\n"
+      ".reg .b32 c, stage, par, fb, eb, t, spins, part;\n"
+      ".reg .b64 a, l, b, a1, l1, b1, t64, off;\n"
+      ".reg .b16 mc;\n"
+      "mov.b16 mc, 3;\n"
+      "mov.u32 c, 0;\n"
+      "setp.ne.b32 pacc, %8, 0;\n"
+      "setp.eq.b32 pt, 0, 0;\n"
+      "elect.sync _|e, 0xffffffff;\n"
+      "SCHUNK_LOOP:\n"
+      "mov.u32 part, 0;\n"
+      "shr.u32 t, c, 1;\n"
+      "mul.wide.u32 off, t, 1024;\n"
+      "and.b32 t, c, 1;\n"
+      "mul.wide.u32 t64, t, 4;\n"
+      "add.s64 off, off, t64;\n"
+      "add.s64 a, off, %2;\n"
+      "add.s64 l, off, %3;\n"
+      "add.s64 a1, a, 2;\n"
+      "add.s64 l1, l, 2;\n"
+      "SPART_LOOP:\n"
+      "and.b32 stage, %0, 7;\n"
+      "shr.u32 par, %0, 3;\n"
+      "and.b32 par, par, 1;\n"
+      "shl.b32 t, stage, 3;\n"
+      "add.u32 fb, %5, t;\n"
+      "add.u32 eb, %6, t;\n"
+      "mov.u32 spins, 0;\n"
+      "SCHUNK_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 pw, [fb], par;\n"
+      "@pw bra SCHUNK_READY;\n"
+      "add.u32 spins, spins, 1;\n"
+      "setp.gt.u32 p, spins, 4000000;\n"
+      "@p trap;\n"
+      "bra SCHUNK_WAIT;\n"
+      "SCHUNK_READY:\n"
+      "tcgen05.fence::after_thread_sync;\n"
+      "mul.wide.u32 b, stage, 512;\n"
+      "add.s64 b, b, %4;\n"
+      "add.s64 b1, b, 2;\n"
+      "setp.eq.u32 p, part, 0;\n"
+      "@!p bra SLO_IMAGE;\n"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%1], a, b, %9, pacc;\n"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%1], l, b, %9, pt;\n"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%1], a1, b1, %9, pt;\n"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%1], l1, b1, %9, pt;\n"
+      "bra SPART_DONE;\n"
+      "SLO_IMAGE:\n"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%1], a, b, %9, pt;\n"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%1], a1, b1, %9, pt;\n"
+      "SPART_DONE:\n"
+      "@e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [eb], mc;\n"
+      "setp.eq.b32 pacc, 0, 0;\n"
+      "add.u32 %0, %0, 1;\n"
+      "add.u32 part, part, 1;\n"
+      "setp.lt.u32 p, part, 2;\n"
+      "@p bra SPART_LOOP;\n"
+      "add.u32 c, c, 1;\n"
+      "setp.lt.u32 p, c, %7;\n"
+      "@p bra SCHUNK_LOOP;\n"
+      "}\n"
+      : "+r"(q)
+      : "r"(d_tmem), "l"(a_hi_desc), "l"(a_lo_desc), "l"(w_desc0), "r"(bar_full0), "r"(bar_empty0), "r"(n_chunks),
+        "r"(first_acc), "r"(idesc)
+      : "memory");
+  return q;
+}
 __device__ __forceinline__ void umma_commit_elect(uint32_t bar) {
   asm volatile(
       "{\n.reg .pred e;\nelect.sync _|e, 0xffffffff;\n"
       "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n}\n" ::"r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_elect_pair(uint32_t bar) {  // arrives on `bar` of BOTH CTAs of the pair
+  asm volatile(
+      "{\n.reg .pred e;\n.reg .b16 mc;\nmov.b16 mc, 3;\nelect.sync _|e, 0xffffffff;\n"
+      "@e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], mc;\n}\n" ::"r"(bar)
       : "memory");
 }
 // K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address >> 4 in
@@ -385,34 +538,46 @@ struct TcParams {
   unsigned long long* prof;  // optional cycle counters of CTA 0 (vipnerf_debug_set_profile_buffer), else null
 };
 
-// Work of one tile slot (sg = global slot index over the whole grid): item i -> (pass, tile)
-template <bool kFused>
+// Work of one tile slot: item i -> (pass, tile).  `unit` indexes the work units of the launch (fused: ray pairs,
+// staged: tiles); `cs` is the slot's index over the whole grid.  With CTA pairs the two CTAs of a cluster share a
+// slot index and split its units alternately (rank 0: even positions, rank 1: odd), and BOTH get the same number of
+// items - the tensor core works on both CTAs' tiles with every MMA - so a missing unit becomes a dummy item (tile
+// index past the end: every row invalid, nothing stored).
+template <bool kFused, bool kPair>
 struct WorkList {
-  int64_t first, stride;
-  int n_first_pass;  // fused: ray pairs of this slot;  staged: tiles
+  int64_t first, stride, end_unit, dummy;
+  int rank;
+  int n_first_pass;  // fused: coarse tiles (= ray pairs) of this CTA's slot;  staged: tiles
   int n_items;
-  __device__ WorkList(const TcParams& p, int sg, int n_slots) {
+  __device__ WorkList(const TcParams& p, int cs, int n_cs, int cta_rank) {
+    rank = cta_rank;
+    dummy = p.n_units;
+    int64_t cnt;
     if (kFused) {
-      const int64_t per = (p.n_units + n_slots - 1) / n_slots;
-      first = (int64_t)sg * per;
+      const int64_t per = (p.n_units + n_cs - 1) / n_cs;
+      first = (int64_t)cs * per;
       stride = 1;
-      int64_t cnt = p.n_units - first;
+      cnt = p.n_units - first;
       cnt = cnt < 0 ? 0 : (cnt > per ? per : cnt);
-      n_first_pass = (int)cnt;
-      n_items = (int)cnt * (p.has_fine ? 4 : 1);
     } else {
-      first = sg;
-      stride = n_slots;
-      n_first_pass = first < p.n_units ? (int)((p.n_units - first + stride - 1) / stride) : 0;
-      n_items = n_first_pass;
+      first = cs;
+      stride = n_cs;
+      cnt = first < p.n_units ? (p.n_units - first + stride - 1) / stride : 0;
     }
+    end_unit = first + cnt * stride;
+    n_first_pass = (int)(kPair ? (cnt + 1) / 2 : cnt);
+    n_items = n_first_pass * ((kFused && p.has_fine) ? 4 : 1);
   }
   __device__ __forceinline__ int pass_of(int i) const { return kFused && i >= n_first_pass ? 1 : 0; }
+  __device__ __forceinline__ int64_t unit_of(int i) const {  // i-th unit of this CTA's slot (or the dummy)
+    const int64_t u = first + (kPair ? 2 * (int64_t)i + rank : (int64_t)i) * stride;
+    return u < end_unit ? u : dummy;
+  }
   __device__ __forceinline__ int64_t tile_of(int i) const {
-    if (!kFused) return first + (int64_t)i * stride;
-    if (i < n_first_pass) return first + i;
+    if (!kFused) return unit_of(i);
+    if (i < n_first_pass) return unit_of(i);
     const int j = i - n_first_pass;
-    return 3 * (first + j / 3) + j % 3;
+    return 3 * unit_of(j / 3) + j % 3;
   }
 };
 
@@ -573,11 +738,14 @@ __device__ __forceinline__ void view_epilogue(uint32_t taddr, const float* vb_ro
 }
 
 // ------------------------------------------------------------------------------------------ the kernel
-template <bool kSplit3, bool kFused, bool kProf>
+template <bool kSplit3, bool kFused, bool kProf, bool kPair>
 __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr int kSlots = kSplit3 ? 1 : 2;
+  constexpr int kStages = kPair ? 8 : 4;
+  constexpr uint32_t kStageBytes = kPair ? 8192 : 16384;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t cta_rank = kPair ? cluster_ctarank() : 0;   // 0 = leader of the CTA pair (issues the MMAs)
   const uint32_t bar0 = smem_u32(smem + kOffBar);
   auto bar = [&](int idx) { return bar0 + 8u * idx; };
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + kOffTmemPtr);
@@ -587,21 +755,37 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const TcParams p) 
       printf("vipnerf: dynamic shared memory base is not 1024-byte aligned\n");
       __trap();
     }
-    for (int s = 0; s < kStages; ++s) { mbar_init(bar(kBarWFull + s), 1); mbar_init(bar(kBarWEmpty + s), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(bar(kBarAReady + s), 128); mbar_init(bar(kBarDReady + s), 1); }
+    // w_full: the local TMA's arrive.expect_tx (+ the peer's relayed arrival in pair mode); a_ready: one arrival per
+    // epilogue thread of every CTA feeding the MMA
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(bar(kBarWFull + s), kPair ? 2 : 1);
+      mbar_init(bar(kBarWEmpty + s), 1);
+      mbar_init(bar(kBarLocalFull + s), 1);
+    }
+    for (int s = 0; s < 2; ++s) { mbar_init(bar(kBarAReady + s), kPair ? 256 : 128); mbar_init(bar(kBarDReady + s), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 9) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem + kOffTmemPtr)),
-                 "r"(512)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (kPair) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem + kOffTmemPtr)),
+                   "r"(512)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem + kOffTmemPtr)),
+                   "r"(512)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (kPair) cluster_sync_all();   // the peer's barriers are initialised before anything arrives on them remotely
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
-  const int n_slots_total = gridDim.x * kSlots;
+  const int n_cta_groups = kPair ? gridDim.x / 2 : gridDim.x;       // clusters (pair mode) or CTAs
+  const int cta_group_idx = kPair ? blockIdx.x / 2 : blockIdx.x;
+  const int n_slots_total = n_cta_groups * kSlots;
 
   if (warp < 8) {
     // =================================================================== epilogue groups
@@ -609,7 +793,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const TcParams p) 
     if (group < kSlots) {
       const int slot = group;
       const int row = threadIdx.x & 127;
-      const WorkList<kFused> work(p, blockIdx.x * kSlots + slot, n_slots_total);
+      const WorkList<kFused, kPair> work(p, cta_group_idx * kSlots + slot, n_slots_total, (int)cta_rank);
+      // a_ready lives in the leader CTA: the peer's epilogue threads arrive on it through the cluster window
+      const uint32_t a_ready_bar = kPair ? map_to_cta(bar(kBarAReady + slot), 0) : bar(kBarAReady + slot);
+      auto arrive_a_ready = [&]() { if (kPair) mbar_arrive_cluster(a_ready_bar); else mbar_arrive(a_ready_bar); };
       const uint32_t taddr = tmem_base + (uint32_t)(slot * 256) + ((uint32_t)((warp & 3) * 32) << 16);
       float* vb = reinterpret_cast<float*>(smem + kOffVb) + slot * 256;
       float* pev = reinterpret_cast<float*>(smem + kOffPev) + slot * 64;
@@ -681,7 +868,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const TcParams p) 
       if (work.n_items > 0) {
         encode_item(0);
         fence_proxy_async();
-        mbar_arrive(bar(kBarAReady + slot));
+        arrive_a_ready();
       }
       for (int it = 0; it < work.n_items; ++it) {
         const int pi = work.pass_of(it);
@@ -712,7 +899,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const TcParams p) 
           else layer_epilogue<kSplit3, true, false>(smem, slot, row, taddr, bias, nullptr);
           fence_proxy_async();
           tc_fence_before();
-          mbar_arrive(bar(kBarAReady + slot));
+          arrive_a_ready();
           if (kProf) c_epi += clock64() - t1;
           if (l == 5) {
             // M5 has retired: the encoding buffer is free, and so are vb/pev (the previous tile's M9 epilogue
@@ -776,7 +963,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const TcParams p) 
         if (has_next) {
           if (!next_encoded) encode_item(it + 1);
           fence_proxy_async();
-          mbar_arrive(bar(kBarAReady + slot));
+          arrive_a_ready();
         }
       }
       tc_fence_before();
@@ -789,44 +976,49 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const TcParams p) 
   } else if (warp == 8) {
     // =================================================================== weight producer
     if (lane == 0) {
-      WorkList<kFused> work0(p, blockIdx.x * kSlots + 0, n_slots_total);
-      WorkList<kFused> work1(p, blockIdx.x * kSlots + (kSlots - 1), n_slots_total);
+      WorkList<kFused, kPair> work0(p, cta_group_idx * kSlots + 0, n_slots_total, (int)cta_rank);
+      WorkList<kFused, kPair> work1(p, cta_group_idx * kSlots + (kSlots - 1), n_slots_total, (int)cta_rank);
       const int n_max = max(work0.n_items, kSlots > 1 ? work1.n_items : 0);
+      // pair mode: this CTA streams its half of every chunk's rows; the leader's copies complete on w_full, the
+      // peer's on its local_full (relayed to the leader's w_full by the peer's warp 9)
+      const int full_base = (kPair && cta_rank == 1) ? kBarLocalFull : kBarWFull;
       uint32_t q = 0;
       for (int it = 0; it < n_max; ++it) {
         for (int l = 0; l < kNumMatLayers; ++l) {
           for (int s = 0; s < kSlots; ++s) {
-            const WorkList<kFused>& w = s == 0 ? work0 : work1;
+            const WorkList<kFused, kPair>& w = s == 0 ? work0 : work1;
             if (it >= w.n_items) continue;
-            const uint32_t bytes = layer_chunk_bytes(l);
+            const uint32_t chunk_bytes = layer_chunk_bytes(l);
+            const uint32_t bytes = kPair ? chunk_bytes / 2 : chunk_bytes;
             const uint8_t* src = p.pass[w.pass_of(it)].packed + kSmallBytes +
-                                 (size_t)tc_layer_byte_offset(l) * (kSplit3 ? 2 : 1);
+                                 (size_t)tc_layer_byte_offset(l) * (kSplit3 ? 2 : 1) + (kPair ? cta_rank * bytes : 0);
             const int n_chunks = layer_chunks(l) * (kSplit3 ? 2 : 1);
             for (int c = 0; c < n_chunks; ++c, ++q) {
               const uint32_t stage = q % kStages;
               mbar_wait(bar(kBarWEmpty + stage), ((q / kStages) & 1) ^ 1);
-              mbar_arrive_expect_tx(bar(kBarWFull + stage), bytes);
-              bulk_copy_g2s(smem_u32(smem + kOffW + stage * kChunkBytes), src + (size_t)c * bytes, bytes,
-                            bar(kBarWFull + stage));
+              mbar_arrive_expect_tx(bar(full_base + stage), bytes);
+              bulk_copy_g2s(smem_u32(smem + kOffW + stage * kStageBytes), src + (size_t)c * chunk_bytes, bytes,
+                            bar(full_base + stage));
             }
           }
         }
       }
     }
-  } else {
-    // =================================================================== MMA issuer (warp 9)
+  } else if (!kPair || cta_rank == 0) {
+    // =================================================================== MMA issuer (warp 9 of the leader CTA)
     // The whole warp runs the loop; one elected lane issues.  Per (tile, layer, slot) step: wait a_ready, run the
     // PTX chunk loop(s) over the layer's A operand (encoding buffer for M0 and the first 64 columns of M5, the A
-    // buffer otherwise), commit d_ready.
-    WorkList<kFused> work0(p, blockIdx.x * kSlots + 0, n_slots_total);
-    WorkList<kFused> work1(p, blockIdx.x * kSlots + (kSlots - 1), n_slots_total);
+    // buffer otherwise), commit d_ready.  In pair mode every MMA is M=256: rows 0-127 from this CTA's A buffer and
+    // TMEM, rows 128-255 from the peer's (same shared-memory / TMEM addresses), B rows split between the two.
+    WorkList<kFused, kPair> work0(p, cta_group_idx * kSlots + 0, n_slots_total, (int)cta_rank);
+    WorkList<kFused, kPair> work1(p, cta_group_idx * kSlots + (kSlots - 1), n_slots_total, (int)cta_rank);
     const int n_max = max(work0.n_items, kSlots > 1 ? work1.n_items : 0);
     uint32_t q = 0;
     uint32_t a_parity0 = 0, a_parity1 = 0;
     const uint64_t a_desc0 = make_desc(smem_u32(smem + kOffA)), pe_desc0 = make_desc(smem_u32(smem + kOffPe));
     const uint64_t w_desc0 = make_desc_sw64(smem_u32(smem + kOffW));
     constexpr uint64_t kKBlockUnits = kKBlockBytes >> 4, kAUnits = kABytes >> 4;
-    static_assert(kKBlockUnits == 1024 && (kChunkBytes >> 4) == 1024 && kStages == 4, "issue_chunks assumes these");
+    static_assert(kKBlockUnits == 1024 && (kStageBytes >> 4) == (kPair ? 512 : 1024), "issue_chunks* assume these");
     const uint32_t bar_full0 = bar(kBarWFull), bar_empty0 = bar(kBarWEmpty);
     long long c_wait_a = 0;
     const long long c_begin = kProf ? clock64() : 0;
@@ -834,7 +1026,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const TcParams p) 
       for (int l = 0; l < kNumMatLayers; ++l) {
 #pragma unroll
         for (int s = 0; s < kSlots; ++s) {
-          const WorkList<kFused>& w = s == 0 ? work0 : work1;
+          const WorkList<kFused, kPair>& w = s == 0 ? work0 : work1;
           if (it >= w.n_items) continue;
           {
             const long long t0 = kProf ? clock64() : 0;
@@ -843,31 +1035,26 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const TcParams p) 
           }
           if (s == 0) a_parity0 ^= 1; else a_parity1 ^= 1;
           tc_fence_after();
-          const uint32_t idesc = instr_desc(layer_n(l));
+          const uint32_t idesc = instr_desc(layer_n(l), kPair ? 256 : 128);
           const uint32_t d_tmem = tmem_base + (uint32_t)(s * 256);
           const uint64_t slot_units = (kSplit3 ? 0 : s);
           const uint64_t pe_hi = pe_desc0 + slot_units * kKBlockUnits, pe_lo = pe_desc0 + kKBlockUnits;
           const uint64_t a_hi = a_desc0 + slot_units * kAUnits, a_lo = a_desc0 + kAUnits;
-          if (!kSplit3) {
-            if (l == 0) {
-              q = issue_chunks(d_tmem, pe_hi, w_desc0, bar_full0, bar_empty0, q, 2, 0, idesc);
-            } else if (l == 5) {
-              q = issue_chunks(d_tmem, pe_hi, w_desc0, bar_full0, bar_empty0, q, 2, 0, idesc);
-              q = issue_chunks(d_tmem, a_hi, w_desc0, bar_full0, bar_empty0, q, 8, 1, idesc);
-            } else {
-              q = issue_chunks(d_tmem, a_hi, w_desc0, bar_full0, bar_empty0, q, 8, 0, idesc);
-            }
+          auto run = [&](uint64_t hi, uint64_t lo, uint32_t n, uint32_t acc) {
+            if (!kSplit3 && !kPair) q = issue_chunks(d_tmem, hi, w_desc0, bar_full0, bar_empty0, q, n, acc, idesc);
+            else if (!kSplit3) q = issue_chunks_pair(d_tmem, hi, w_desc0, bar_full0, bar_empty0, q, n, acc, idesc);
+            else if (!kPair) q = issue_chunks_split(d_tmem, hi, lo, w_desc0, bar_full0, bar_empty0, q, n, acc, idesc);
+            else q = issue_chunks_split_pair(d_tmem, hi, lo, w_desc0, bar_full0, bar_empty0, q, n, acc, idesc);
+          };
+          if (l == 0) {
+            run(pe_hi, pe_lo, 2, 0);
+          } else if (l == 5) {
+            run(pe_hi, pe_lo, 2, 0);
+            run(a_hi, a_lo, 8, 1);
           } else {
-            if (l == 0) {
-              q = issue_chunks_split(d_tmem, pe_hi, pe_lo, w_desc0, bar_full0, bar_empty0, q, 2, 0, idesc);
-            } else if (l == 5) {
-              q = issue_chunks_split(d_tmem, pe_hi, pe_lo, w_desc0, bar_full0, bar_empty0, q, 2, 0, idesc);
-              q = issue_chunks_split(d_tmem, a_hi, a_lo, w_desc0, bar_full0, bar_empty0, q, 8, 1, idesc);
-            } else {
-              q = issue_chunks_split(d_tmem, a_hi, a_lo, w_desc0, bar_full0, bar_empty0, q, 8, 0, idesc);
-            }
+            run(a_hi, a_lo, 8, 0);
           }
-          umma_commit_elect(bar(kBarDReady + s));
+          if (kPair) umma_commit_elect_pair(bar(kBarDReady + s)); else umma_commit_elect(bar(kBarDReady + s));
         }
       }
     }
@@ -876,11 +1063,36 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const TcParams p) 
       p.prof[32] = c_wait_a; p.prof[33] = 0; p.prof[34] = (unsigned long long)(clock64() - c_begin);
       p.prof[35] = q;
     }
+  } else {
+    // =================================================================== weight relay (warp 9 of the peer CTA)
+    // The peer's weight copies complete on its own local_full barriers; forward every completion to the leader's
+    // w_full (which counts the leader's own copy plus this arrival) so that the leader's MMAs see both halves.
+    WorkList<kFused, kPair> work0(p, cta_group_idx * kSlots + 0, n_slots_total, (int)cta_rank);
+    WorkList<kFused, kPair> work1(p, cta_group_idx * kSlots + (kSlots - 1), n_slots_total, (int)cta_rank);
+    const int n_max = max(work0.n_items, kSlots > 1 ? work1.n_items : 0);
+    uint32_t q = 0;
+    for (int it = 0; it < n_max; ++it) {
+      for (int l = 0; l < kNumMatLayers; ++l) {
+        for (int s = 0; s < kSlots; ++s) {
+          const WorkList<kFused, kPair>& w = s == 0 ? work0 : work1;
+          if (it >= w.n_items) continue;
+          const int n_chunks = layer_chunks(l) * (kSplit3 ? 2 : 1);
+          for (int c = 0; c < n_chunks; ++c, ++q) {
+            const uint32_t stage = q % kStages;
+            mbar_wait(bar(kBarLocalFull + stage), (q / kStages) & 1);
+            if (lane == 0) mbar_arrive_cluster(map_to_cta(bar(kBarWFull + stage), 0));
+            __syncwarp();
+          }
+        }
+      }
+    }
   }
   __syncthreads();
+  if (kPair) cluster_sync_all();   // the peer may still be reading this CTA's shared memory / signalling its barriers
   if (warp == 9) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    if (kPair) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
 }
 
@@ -888,7 +1100,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const TcParams p) 
 std::mutex g_attr_mutex;
 unsigned long long* g_prof_buffer = nullptr;  // debug: set by vipnerf_debug_set_profile_buffer
 int g_sm_count[64] = {0};
-bool g_attr_set[64][8] = {{false}};
+bool g_attr_set[64][16] = {{false}};
+// CTA-pair (cta_group::2) kernels unless VIPNERF_TC_CTA_PAIRS=0 (read once)
+const bool g_use_cta_pairs = []() { const char* e = getenv("VIPNERF_TC_CTA_PAIRS"); return e == nullptr || e[0] != '0'; }();
 
 cudaError_t device_sm_count(int* out) {
   int dev = 0;
@@ -904,34 +1118,52 @@ cudaError_t device_sm_count(int* out) {
   return cudaSuccess;
 }
 
-template <bool kSplit3, bool kFused, bool kProf>
+template <bool kSplit3, bool kFused, bool kProf, bool kPair>
 cudaError_t launch_variant(const TcParams& p, int64_t n_units, cudaStream_t s) {
   int dev = 0, sms = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
   if ((e = device_sm_count(&sms)) != cudaSuccess) return e;
+  auto kernel = k_render_tc<kSplit3, kFused, kProf, kPair>;
   {
     std::lock_guard<std::mutex> lock(g_attr_mutex);
-    const int variant = (kSplit3 ? 2 : 0) + (kFused ? 1 : 0) + (kProf ? 4 : 0);
+    const int variant = (kSplit3 ? 2 : 0) + (kFused ? 1 : 0) + (kProf ? 4 : 0) + (kPair ? 8 : 0);
     if (dev >= 64 || !g_attr_set[dev][variant]) {
-      e = cudaFuncSetAttribute(k_render_tc<kSplit3, kFused, kProf>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)kSmemBytes);
+      e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
       if (e != cudaSuccess) return e;
       if (dev < 64) g_attr_set[dev][variant] = true;
     }
   }
   constexpr int kSlots = kSplit3 ? 1 : 2;
-  int64_t grid = (n_units + kSlots - 1) / kSlots;
-  if (grid > sms) grid = sms;
-  if (grid < 1) return cudaSuccess;
-  k_render_tc<kSplit3, kFused, kProf><<<(unsigned)grid, kNumThreads, kSmemBytes, s>>>(p);
-  return cudaGetLastError();
+  constexpr int kCtasPerGroup = kPair ? 2 : 1;
+  // one slot (per CTA group) per work unit at most; a CTA pair serves two units per slot
+  int64_t groups = (n_units + kSlots * kCtasPerGroup - 1) / (kSlots * kCtasPerGroup);
+  if (groups > sms / kCtasPerGroup) groups = sms / kCtasPerGroup;
+  if (groups < 1) return cudaSuccess;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(groups * kCtasPerGroup));
+  cfg.blockDim = dim3(kNumThreads);
+  cfg.dynamicSmemBytes = kSmemBytes;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCtasPerGroup;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = kPair ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, p);
 }
 
 template <bool kSplit3, bool kFused>
 cudaError_t launch(const TcParams& p, int64_t n_units, cudaStream_t s) {
-  if (p.prof != nullptr) return launch_variant<kSplit3, kFused, true>(p, n_units, s);
-  return launch_variant<kSplit3, kFused, false>(p, n_units, s);
+  const bool pair = g_use_cta_pairs;
+  if (p.prof != nullptr) {
+    return pair ? launch_variant<kSplit3, kFused, true, true>(p, n_units, s)
+                : launch_variant<kSplit3, kFused, true, false>(p, n_units, s);
+  }
+  return pair ? launch_variant<kSplit3, kFused, false, true>(p, n_units, s)
+              : launch_variant<kSplit3, kFused, false, false>(p, n_units, s);
 }
 
 }  // namespace
