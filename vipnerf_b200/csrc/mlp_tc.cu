@@ -184,7 +184,8 @@ __device__ __forceinline__ void mma_chunk_split_hi(uint32_t d_tmem, uint64_t a_h
 // The *_split variants are BF16X3: every weight chunk is two ring stages (hi image, lo image); per chunk
 // A_hi*W_hi + A_lo*W_hi (4 MMAs, commit) then A_hi*W_lo (2 MMAs, commit).
 __device__ __forceinline__ uint32_t issue_chunks(uint32_t d_tmem, uint64_t a_desc, uint64_t w_desc0, uint32_t bar_full0,
-        uint32_t bar_empty0, uint32_t q, uint32_t n_chunks, uint32_t first_acc, uint32_t idesc) {
+        uint32_t bar_empty0, uint32_t q, uint32_t n_chunks, uint32_t first_acc, uint32_t idesc,
+        uint32_t& spin_total) {
   asm volatile(
       "{\n"
       ".reg .pred p, pw, e, pacc, pt;\n"
@@ -193,7 +194,7 @@ __device__ __forceinline__ uint32_t issue_chunks(uint32_t d_tmem, uint64_t a_des
       ".reg .b16 mc;\n"
       "mov.b16 mc, 3;\n"
       "mov.u32 c, 0;\n"
-      "setp.ne.b32 pacc, %7, 0;\n"
+      "setp.ne.b32 pacc, %8, 0;\n"
       "setp.eq.b32 pt, 0, 0;\n"
       "elect.sync _|e, 0xffffffff;\n"
       "CHUNK_LOOP:\n"
@@ -201,45 +202,47 @@ __device__ __forceinline__ uint32_t issue_chunks(uint32_t d_tmem, uint64_t a_des
       "shr.u32 par, %0, 2;\n"
       "and.b32 par, par, 1;\n"
       "shl.b32 t, stage, 3;\n"
-      "add.u32 fb, %4, t;\n"
-      "add.u32 eb, %5, t;\n"
+      "add.u32 fb, %5, t;\n"
+      "add.u32 eb, %6, t;\n"
       "mov.u32 spins, 0;\n"
       "CHUNK_WAIT:\n"
       "mbarrier.try_wait.parity.shared::cta.b64 pw, [fb], par;\n"
       "@pw bra CHUNK_READY;\n"
       "add.u32 spins, spins, 1;\n"
+      "add.u32 %1, %1, 1;\n"
       "setp.gt.u32 p, spins, 4000000;\n"
       "@p trap;\n"
       "bra CHUNK_WAIT;\n"
       "CHUNK_READY:\n"
       "tcgen05.fence::after_thread_sync;\n"
       "mul.wide.u32 b, stage, 1024;\n"
-      "add.s64 b, b, %3;\n"
+      "add.s64 b, b, %4;\n"
       "shr.u32 t, c, 1;\n"
       "mul.wide.u32 a, t, 1024;\n"
       "and.b32 t, c, 1;\n"
       "mul.wide.u32 t64, t, 4;\n"
       "add.s64 a, a, t64;\n"
-      "add.s64 a, a, %2;\n"
+      "add.s64 a, a, %3;\n"
       "add.s64 a1, a, 2;\n"
       "add.s64 b1, b, 2;\n"
-      "@e tcgen05.mma.cta_group::1.kind::f16 [%1], a, b, %8, pacc;\n"
-      "@e tcgen05.mma.cta_group::1.kind::f16 [%1], a1, b1, %8, pt;\n"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%2], a, b, %9, pacc;\n"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%2], a1, b1, %9, pt;\n"
       "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [eb];\n"
       "setp.eq.b32 pacc, 0, 0;\n"
       "add.u32 %0, %0, 1;\n"
       "add.u32 c, c, 1;\n"
-      "setp.lt.u32 p, c, %6;\n"
+      "setp.lt.u32 p, c, %7;\n"
       "@p bra CHUNK_LOOP;\n"
       "}\n"
-      : "+r"(q)
+      : "+r"(q), "+r"(spin_total)
       : "r"(d_tmem), "l"(a_desc), "l"(w_desc0), "r"(bar_full0), "r"(bar_empty0), "r"(n_chunks), "r"(first_acc),
         "r"(idesc)
       : "memory");
   return q;
 }
 __device__ __forceinline__ uint32_t issue_chunks_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t w_desc0, uint32_t bar_full0,
-        uint32_t bar_empty0, uint32_t q, uint32_t n_chunks, uint32_t first_acc, uint32_t idesc) {
+        uint32_t bar_empty0, uint32_t q, uint32_t n_chunks, uint32_t first_acc, uint32_t idesc,
+        uint32_t& spin_total) {
   asm volatile(
       "{\n"
       ".reg .pred p, pw, e, pacc, pt;\n"
@@ -248,7 +251,7 @@ __device__ __forceinline__ uint32_t issue_chunks_pair(uint32_t d_tmem, uint64_t 
       ".reg .b16 mc;\n"
       "mov.b16 mc, 3;\n"
       "mov.u32 c, 0;\n"
-      "setp.ne.b32 pacc, %7, 0;\n"
+      "setp.ne.b32 pacc, %8, 0;\n"
       "setp.eq.b32 pt, 0, 0;\n"
       "elect.sync _|e, 0xffffffff;\n"
       "CHUNK_LOOP:\n"
@@ -256,38 +259,39 @@ __device__ __forceinline__ uint32_t issue_chunks_pair(uint32_t d_tmem, uint64_t 
       "shr.u32 par, %0, 3;\n"
       "and.b32 par, par, 1;\n"
       "shl.b32 t, stage, 3;\n"
-      "add.u32 fb, %4, t;\n"
-      "add.u32 eb, %5, t;\n"
+      "add.u32 fb, %5, t;\n"
+      "add.u32 eb, %6, t;\n"
       "mov.u32 spins, 0;\n"
       "CHUNK_WAIT:\n"
       "mbarrier.try_wait.parity.shared::cta.b64 pw, [fb], par;\n"
       "@pw bra CHUNK_READY;\n"
       "add.u32 spins, spins, 1;\n"
+      "add.u32 %1, %1, 1;\n"
       "setp.gt.u32 p, spins, 4000000;\n"
       "@p trap;\n"
       "bra CHUNK_WAIT;\n"
       "CHUNK_READY:\n"
       "tcgen05.fence::after_thread_sync;\n"
       "mul.wide.u32 b, stage, 512;\n"
-      "add.s64 b, b, %3;\n"
+      "add.s64 b, b, %4;\n"
       "shr.u32 t, c, 1;\n"
       "mul.wide.u32 a, t, 1024;\n"
       "and.b32 t, c, 1;\n"
       "mul.wide.u32 t64, t, 4;\n"
       "add.s64 a, a, t64;\n"
-      "add.s64 a, a, %2;\n"
+      "add.s64 a, a, %3;\n"
       "add.s64 a1, a, 2;\n"
       "add.s64 b1, b, 2;\n"
-      "@e tcgen05.mma.cta_group::2.kind::f16 [%1], a, b, %8, pacc;\n"
-      "@e tcgen05.mma.cta_group::2.kind::f16 [%1], a1, b1, %8, pt;\n"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%2], a, b, %9, pacc;\n"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%2], a1, b1, %9, pt;\n"
       "@e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [eb], mc;\n"
       "setp.eq.b32 pacc, 0, 0;\n"
       "add.u32 %0, %0, 1;\n"
       "add.u32 c, c, 1;\n"
-      "setp.lt.u32 p, c, %6;\n"
+      "setp.lt.u32 p, c, %7;\n"
       "@p bra CHUNK_LOOP;\n"
       "}\n"
-      : "+r"(q)
+      : "+r"(q), "+r"(spin_total)
       : "r"(d_tmem), "l"(a_desc), "l"(w_desc0), "r"(bar_full0), "r"(bar_empty0), "r"(n_chunks), "r"(first_acc),
         "r"(idesc)
       : "memory");
@@ -1021,6 +1025,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const TcParams p) 
     static_assert(kKBlockUnits == 1024 && (kStageBytes >> 4) == (kPair ? 512 : 1024), "issue_chunks* assume these");
     const uint32_t bar_full0 = bar(kBarWFull), bar_empty0 = bar(kBarWEmpty);
     long long c_wait_a = 0;
+    uint32_t spins = 0;  // failed probes of the weight ring (prof builds report it)
     const long long c_begin = kProf ? clock64() : 0;
     for (int it = 0; it < n_max; ++it) {
       for (int l = 0; l < kNumMatLayers; ++l) {
@@ -1041,8 +1046,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const TcParams p) 
           const uint64_t pe_hi = pe_desc0 + slot_units * kKBlockUnits, pe_lo = pe_desc0 + kKBlockUnits;
           const uint64_t a_hi = a_desc0 + slot_units * kAUnits, a_lo = a_desc0 + kAUnits;
           auto run = [&](uint64_t hi, uint64_t lo, uint32_t n, uint32_t acc) {
-            if (!kSplit3 && !kPair) q = issue_chunks(d_tmem, hi, w_desc0, bar_full0, bar_empty0, q, n, acc, idesc);
-            else if (!kSplit3) q = issue_chunks_pair(d_tmem, hi, w_desc0, bar_full0, bar_empty0, q, n, acc, idesc);
+            if (!kSplit3 && !kPair) q = issue_chunks(d_tmem, hi, w_desc0, bar_full0, bar_empty0, q, n, acc, idesc, spins);
+            else if (!kSplit3) q = issue_chunks_pair(d_tmem, hi, w_desc0, bar_full0, bar_empty0, q, n, acc, idesc, spins);
             else if (!kPair) q = issue_chunks_split(d_tmem, hi, lo, w_desc0, bar_full0, bar_empty0, q, n, acc, idesc);
             else q = issue_chunks_split_pair(d_tmem, hi, lo, w_desc0, bar_full0, bar_empty0, q, n, acc, idesc);
           };
@@ -1060,7 +1065,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const TcParams p) 
     }
     tc_fence_before();
     if (kProf && p.prof != nullptr && blockIdx.x == 0 && lane == 0) {
-      p.prof[32] = c_wait_a; p.prof[33] = 0; p.prof[34] = (unsigned long long)(clock64() - c_begin);
+      p.prof[32] = c_wait_a; p.prof[33] = spins; p.prof[34] = (unsigned long long)(clock64() - c_begin);
       p.prof[35] = q;
     }
   } else {
