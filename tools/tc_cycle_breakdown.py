@@ -48,5 +48,5 @@ for slot in range(2):
         print(f'   {n:20s} {v:10d}  {100 * v / q[7]:5.1f}%   {v / q[6]:9.0f} / tile')
 m = b[32:36]
 print(f'MMA lane: total {m[2]} cycles, wait a_ready {m[0]} ({100 * m[0] / max(1, m[2]):.1f}%), chunks {m[3]}, '
-      f'failed weight-ring probes {m[1]} (each try_wait may suspend the warp), '
+      f'cycles waiting on the weight ring {m[1]} ({100 * m[1] / max(1, m[2]):.1f}%), '
       f'{(m[2] - m[0]) / max(1, m[3]):.0f} cycles per chunk outside a_ready waits (ideal 256)')

@@ -189,7 +189,7 @@ __device__ __forceinline__ uint32_t issue_chunks(uint32_t d_tmem, uint64_t a_des
   asm volatile(
       "{\n"
       ".reg .pred p, pw, e, pacc, pt;\n"
-      ".reg .b32 c, stage, par, fb, eb, t, spins;\n"
+      ".reg .b32 c, stage, par, fb, eb, t, spins, c0, c1;\n"
       ".reg .b64 a, b, a1, b1, t64;\n"
       ".reg .b16 mc;\n"
       "mov.b16 mc, 3;\n"
@@ -205,15 +205,18 @@ __device__ __forceinline__ uint32_t issue_chunks(uint32_t d_tmem, uint64_t a_des
       "add.u32 fb, %5, t;\n"
       "add.u32 eb, %6, t;\n"
       "mov.u32 spins, 0;\n"
+      "mov.u32 c0, %clock;\n"
       "CHUNK_WAIT:\n"
       "mbarrier.try_wait.parity.shared::cta.b64 pw, [fb], par;\n"
       "@pw bra CHUNK_READY;\n"
       "add.u32 spins, spins, 1;\n"
-      "add.u32 %1, %1, 1;\n"
-      "setp.gt.u32 p, spins, 4000000;\n"
+            "setp.gt.u32 p, spins, 4000000;\n"
       "@p trap;\n"
       "bra CHUNK_WAIT;\n"
       "CHUNK_READY:\n"
+      "mov.u32 c1, %clock;\n"
+      "sub.u32 c1, c1, c0;\n"
+      "add.u32 %1, %1, c1;\n"
       "tcgen05.fence::after_thread_sync;\n"
       "mul.wide.u32 b, stage, 1024;\n"
       "add.s64 b, b, %4;\n"
@@ -246,7 +249,7 @@ __device__ __forceinline__ uint32_t issue_chunks_pair(uint32_t d_tmem, uint64_t 
   asm volatile(
       "{\n"
       ".reg .pred p, pw, e, pacc, pt;\n"
-      ".reg .b32 c, stage, par, fb, eb, t, spins;\n"
+      ".reg .b32 c, stage, par, fb, eb, t, spins, c0, c1;\n"
       ".reg .b64 a, b, a1, b1, t64;\n"
       ".reg .b16 mc;\n"
       "mov.b16 mc, 3;\n"
@@ -262,15 +265,18 @@ __device__ __forceinline__ uint32_t issue_chunks_pair(uint32_t d_tmem, uint64_t 
       "add.u32 fb, %5, t;\n"
       "add.u32 eb, %6, t;\n"
       "mov.u32 spins, 0;\n"
+      "mov.u32 c0, %clock;\n"
       "CHUNK_WAIT:\n"
       "mbarrier.try_wait.parity.shared::cta.b64 pw, [fb], par;\n"
       "@pw bra CHUNK_READY;\n"
       "add.u32 spins, spins, 1;\n"
-      "add.u32 %1, %1, 1;\n"
-      "setp.gt.u32 p, spins, 4000000;\n"
+            "setp.gt.u32 p, spins, 4000000;\n"
       "@p trap;\n"
       "bra CHUNK_WAIT;\n"
       "CHUNK_READY:\n"
+      "mov.u32 c1, %clock;\n"
+      "sub.u32 c1, c1, c0;\n"
+      "add.u32 %1, %1, c1;\n"
       "tcgen05.fence::after_thread_sync;\n"
       "mul.wide.u32 b, stage, 512;\n"
       "add.s64 b, b, %4;\n"
