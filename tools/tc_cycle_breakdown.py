@@ -50,3 +50,9 @@ m = b[32:36]
 print(f'MMA lane: total {m[2]} cycles, wait a_ready {m[0]} ({100 * m[0] / max(1, m[2]):.1f}%), chunks {m[3]}, '
       f'cycles waiting on the weight ring {m[1]} ({100 * m[1] / max(1, m[2]):.1f}%), '
       f'{(m[2] - m[0]) / max(1, m[3]):.0f} cycles per chunk outside a_ready waits (ideal 256)')
+for r in range(2):
+    w, tot = b[40 + 4 * r], b[41 + 4 * r]
+    if tot:
+        print(f'weight producer CTA {r}: total {tot} cycles, waiting for free ring stages {w} ({100 * w / tot:.1f}%)')
+if b[49]:
+    print(f'weight relay (peer CTA): total {b[49]} cycles, waiting for its own copies {b[48]} ({100 * b[48] / b[49]:.1f}%)')

@@ -992,6 +992,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const TcParams p) 
       // pair mode: this CTA streams its half of every chunk's rows; the leader's copies complete on w_full, the
       // peer's on its local_full (relayed to the leader's w_full by the peer's warp 9)
       const int full_base = (kPair && cta_rank == 1) ? kBarLocalFull : kBarWFull;
+      long long c_prod_wait = 0;
+      const long long c_prod_begin = kProf ? clock64() : 0;
       uint32_t q = 0;
       for (int it = 0; it < n_max; ++it) {
         for (int l = 0; l < kNumMatLayers; ++l) {
@@ -1005,13 +1007,21 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const TcParams p) 
             const int n_chunks = layer_chunks(l) * (kSplit3 ? 2 : 1);
             for (int c = 0; c < n_chunks; ++c, ++q) {
               const uint32_t stage = q % kStages;
-              mbar_wait(bar(kBarWEmpty + stage), ((q / kStages) & 1) ^ 1);
+              {
+                const long long t0 = kProf ? clock64() : 0;
+                mbar_wait(bar(kBarWEmpty + stage), ((q / kStages) & 1) ^ 1);
+                if (kProf) c_prod_wait += clock64() - t0;
+              }
               mbar_arrive_expect_tx(bar(full_base + stage), bytes);
               bulk_copy_g2s(smem_u32(smem + kOffW + stage * kStageBytes), src + (size_t)c * chunk_bytes, bytes,
                             bar(full_base + stage));
             }
           }
         }
+      }
+      if (kProf && p.prof != nullptr && blockIdx.x < 2) {
+        p.prof[40 + 4 * blockIdx.x] = c_prod_wait;
+        p.prof[41 + 4 * blockIdx.x] = (unsigned long long)(clock64() - c_prod_begin);
       }
     }
   } else if (!kPair || cta_rank == 0) {
@@ -1082,6 +1092,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const TcParams p) 
     WorkList<kFused, kPair> work1(p, cta_group_idx * kSlots + (kSlots - 1), n_slots_total, (int)cta_rank);
     const int n_max = max(work0.n_items, kSlots > 1 ? work1.n_items : 0);
     uint32_t q = 0;
+    long long c_relay_wait = 0;
+    const long long c_relay_begin = kProf ? clock64() : 0;
     for (int it = 0; it < n_max; ++it) {
       for (int l = 0; l < kNumMatLayers; ++l) {
         for (int s = 0; s < kSlots; ++s) {
@@ -1090,12 +1102,20 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const TcParams p) 
           const int n_chunks = layer_chunks(l) * (kSplit3 ? 2 : 1);
           for (int c = 0; c < n_chunks; ++c, ++q) {
             const uint32_t stage = q % kStages;
-            mbar_wait(bar(kBarLocalFull + stage), (q / kStages) & 1);
+            {
+              const long long t0 = kProf ? clock64() : 0;
+              mbar_wait(bar(kBarLocalFull + stage), (q / kStages) & 1);
+              if (kProf) c_relay_wait += clock64() - t0;
+            }
             if (lane == 0) mbar_arrive_cluster(map_to_cta(bar(kBarWFull + stage), 0));
             __syncwarp();
           }
         }
       }
+    }
+    if (kProf && p.prof != nullptr && blockIdx.x == 1 && lane == 0) {
+      p.prof[48] = c_relay_wait;
+      p.prof[49] = (unsigned long long)(clock64() - c_relay_begin);
     }
   }
   __syncthreads();
