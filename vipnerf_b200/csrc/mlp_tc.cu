@@ -120,8 +120,14 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t rank
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
   return r;
 }
+// Arrive on an mbarrier of (possibly) another CTA of the cluster.  Default semantics (release at CTA scope), as
+// CUTLASS's ClusterBarrier::arrive does: a cluster-scope release costs ~1000 cycles per arrival (it fences and
+// invalidates L1), which throttled the CTA-pair weight relay to one chunk per microsecond.  CTA scope suffices
+// here: what the signal publishes (weight chunks, activation tiles) is consumed by the tensor core of the
+// signalling CTA itself through the async proxy (ordered by fence.proxy.async / the TMA's complete_tx), never by
+// threads of the other CTA.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // mbarrier.test_wait: non-blocking probe (try_wait may suspend the warp when the phase is not complete)
 __device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
