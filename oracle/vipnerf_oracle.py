@@ -198,7 +198,8 @@ def linear(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], mode: st
     if mode == 'fp32':
         return F.linear(x, w, b)
     if mode == 'bf16':
-        return F.linear(_round_bf16(x), _round_bf16(w), b)
+        # the kernel adds the bias on the tensor core too (as a bf16 weight column against a constant-one input)
+        return F.linear(_round_bf16(x), _round_bf16(w), _round_bf16(b) if b is not None else None)
     if mode == 'bf16x3':
         xh, wh = _round_bf16(x), _round_bf16(w)
         xl, wl = _round_bf16(x - xh), _round_bf16(w - wh)

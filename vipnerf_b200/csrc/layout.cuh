@@ -59,19 +59,21 @@ constexpr int kFp32BigFloats = fp32_layer_offset(kNumMatLayers);  // 589,824
 constexpr int kChunkK = 32;
 constexpr int kChunkBytes = 16384;   // ring stage size (largest chunk)
 __host__ __device__ constexpr int layer_chunks(int l) { return layer_k(l) / kChunkK; }
+// The bias is added by the tensor core as well: the encoding buffer's pad column (A column 63 of M0 and of the
+// first k-block of M5) holds the constant 1.0, so for M0 / M5 the bias is simply weight column 63; every other
+// 256-wide layer gets one extra "bias chunk" whose only non-zero column (31, facing encoding column 63) is the
+// bias, consumed by ONE K=16 MMA against the last 16 encoding columns.  M9's bias travels with the
+// view-direction term (fp32, per ray).  In bf16 mode the bias is therefore rounded to bf16; in BF16X3 mode the
+// lo image carries its residual.
+__host__ __device__ constexpr bool layer_has_bias_chunk(int l) { return l != 0 && l != 5 && l != 9; }
+__host__ __device__ constexpr int layer_stream_chunks(int l) { return layer_chunks(l) + (layer_has_bias_chunk(l) ? 1 : 0); }
 __host__ __device__ constexpr int layer_chunk_bytes(int l) { return layer_n(l) * kChunkK * 2; }
-__host__ __device__ constexpr int tc_layer_chunk_offset(int l) {   // in chunks
-  int off = 0;
-  for (int i = 0; i < l; ++i) off += layer_chunks(i);
-  return off;
-}
 __host__ __device__ constexpr int tc_layer_byte_offset(int l) {    // of the hi image set
   int off = 0;
-  for (int i = 0; i < l; ++i) off += layer_chunks(i) * layer_chunk_bytes(i);
+  for (int i = 0; i < l; ++i) off += layer_stream_chunks(i) * layer_chunk_bytes(i);
   return off;
 }
-constexpr int kTcChunks = tc_layer_chunk_offset(kNumMatLayers);     // 76
-constexpr int kTcBigBytes = tc_layer_byte_offset(kNumMatLayers);    // 1,179,648
+constexpr int kTcBigBytes = tc_layer_byte_offset(kNumMatLayers);    // 1,294,336 (76 weight + 7 bias chunks)
 
 // Maps A column k of matrix layer l to the source weight column (or -1 for a zero pad column).
 __host__ __device__ inline int source_col(int l, int k) {
@@ -79,6 +81,8 @@ __host__ __device__ inline int source_col(int l, int k) {
   if (l == 5) return k < kEncPts ? k : (k == 63 ? -1 : k - 1);  // 64 + j -> 63 + j
   return k;
 }
+// Index into params[24] of the bias of matrix layer l (M8 = feature_linear, M9 = views_linears.0).
+__host__ __device__ inline int bias_param(int l) { return l < 8 ? 2 * l + 1 : (l == 8 ? 21 : 17); }
 // Source tensor (index into params[24]) and its in-features of matrix layer l.
 __host__ __device__ inline int source_param(int l) { return l < 8 ? 2 * l : (l == 8 ? 20 : 16); }
 __host__ __device__ inline int source_in_features(int l) {

@@ -451,6 +451,86 @@ __device__ __forceinline__ uint32_t issue_chunks_split_pair(uint32_t d_tmem, uin
       : "memory");
   return q;
 }
+// The bias chunk of a layer: ONE accumulating MMA - A = the last 16 columns of the encoding k-block (column 63 is the
+// constant 1), B = the second K=16 step of the chunk (its column 31 holds the bias) - then the stage-release commit.
+__device__ __forceinline__ uint32_t issue_bias_chunk(uint32_t d_tmem, uint64_t a_desc, uint64_t w_desc0, uint32_t bar_full0,
+        uint32_t bar_empty0, uint32_t q, uint32_t idesc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p, pw, e, pt;\n"
+      ".reg .b32 stage, par, fb, eb, t, spins;\n"
+      ".reg .b64 b;\n"
+      ".reg .b16 mc;\n"
+      "mov.b16 mc, 3;\n"
+      "setp.eq.b32 pt, 0, 0;\n"
+      "elect.sync _|e, 0xffffffff;\n"
+      "and.b32 stage, %0, 3;\n"
+      "shr.u32 par, %0, 2;\n"
+      "and.b32 par, par, 1;\n"
+      "shl.b32 t, stage, 3;\n"
+      "add.u32 fb, %4, t;\n"
+      "add.u32 eb, %5, t;\n"
+      "mov.u32 spins, 0;\n"
+      "BIAS_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 pw, [fb], par;\n"
+      "@pw bra BIAS_READY;\n"
+      "add.u32 spins, spins, 1;\n"
+      "setp.gt.u32 p, spins, 4000000;\n"
+      "@p trap;\n"
+      "bra BIAS_WAIT;\n"
+      "BIAS_READY:\n"
+      "tcgen05.fence::after_thread_sync;\n"
+      "mul.wide.u32 b, stage, 1024;\n"
+      "add.s64 b, b, %3;\n"
+      "add.s64 b, b, 2;\n"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%1], %2, b, %6, pt;\n"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [eb];\n"
+      "add.u32 %0, %0, 1;\n"
+      "}\n"
+      : "+r"(q)
+      : "r"(d_tmem), "l"(a_desc), "l"(w_desc0), "r"(bar_full0), "r"(bar_empty0), "r"(idesc)
+      : "memory");
+  return q;
+}
+__device__ __forceinline__ uint32_t issue_bias_chunk_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t w_desc0, uint32_t bar_full0,
+        uint32_t bar_empty0, uint32_t q, uint32_t idesc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p, pw, e, pt;\n"
+      ".reg .b32 stage, par, fb, eb, t, spins;\n"
+      ".reg .b64 b;\n"
+      ".reg .b16 mc;\n"
+      "mov.b16 mc, 3;\n"
+      "setp.eq.b32 pt, 0, 0;\n"
+      "elect.sync _|e, 0xffffffff;\n"
+      "and.b32 stage, %0, 7;\n"
+      "shr.u32 par, %0, 3;\n"
+      "and.b32 par, par, 1;\n"
+      "shl.b32 t, stage, 3;\n"
+      "add.u32 fb, %4, t;\n"
+      "add.u32 eb, %5, t;\n"
+      "mov.u32 spins, 0;\n"
+      "BIAS_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 pw, [fb], par;\n"
+      "@pw bra BIAS_READY;\n"
+      "add.u32 spins, spins, 1;\n"
+      "setp.gt.u32 p, spins, 4000000;\n"
+      "@p trap;\n"
+      "bra BIAS_WAIT;\n"
+      "BIAS_READY:\n"
+      "tcgen05.fence::after_thread_sync;\n"
+      "mul.wide.u32 b, stage, 512;\n"
+      "add.s64 b, b, %3;\n"
+      "add.s64 b, b, 2;\n"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%1], %2, b, %6, pt;\n"
+      "@e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [eb], mc;\n"
+      "add.u32 %0, %0, 1;\n"
+      "}\n"
+      : "+r"(q)
+      : "r"(d_tmem), "l"(a_desc), "l"(w_desc0), "r"(bar_full0), "r"(bar_empty0), "r"(idesc)
+      : "memory");
+  return q;
+}
 __device__ __forceinline__ void umma_commit_elect(uint32_t bar) {
   asm volatile(
       "{\n.reg .pred e;\nelect.sync _|e, 0xffffffff;\n"
@@ -617,7 +697,7 @@ __device__ __forceinline__ void sincos_octave(float t_hi, float t_lo, int k, flo
   }
 }
 
-// Row `row` of the slot's encoding buffer <- bf16(gamma(point)), 64 columns (63 + zero pad).
+// Row `row` of the slot's encoding buffer <- bf16(gamma(point)), 64 columns (63 + the constant 1).
 // Column order of PositionalEncoder.encode (VipNeRF01.py:439-448): x(3), then per octave sin(3), cos(3).
 template <bool kSplit3>
 __device__ __forceinline__ void write_point_encoding(uint8_t* smem, int slot, int row, float x, float y, float z) {
@@ -631,7 +711,7 @@ __device__ __forceinline__ void write_point_encoding(uint8_t* smem, int slot, in
 #pragma unroll
     for (int k = 0; k < kLPts; ++k) sincos_octave<kSplit3>(t_hi, t_lo, k, v[3 + 6 * k + a], v[6 + 6 * k + a]);
   }
-  v[63] = 0.f;
+  v[63] = 1.f;  // constant-one column: carries the layer biases through the tensor core (layout.cuh)
   const uint32_t hi_base = smem_u32(smem + kOffPe + (kSplit3 ? 0 : slot) * kKBlockBytes) + row * 128;
   const uint32_t lo_base = smem_u32(smem + kOffPe + kKBlockBytes) + row * 128;
 #pragma unroll
@@ -650,13 +730,13 @@ __device__ __forceinline__ void write_point_encoding(uint8_t* smem, int slot, in
   }
 }
 
-// One trunk / feature layer epilogue for one row: accumulator (256 fp32 TMEM columns) -> +bias (-> ReLU) -> bf16
-// -> A buffer (in place).  kSigma additionally accumulates the density head on the fp32 activations.
-// The eight 32-column TMEM loads are software-pipelined: block cb+1 is in flight while block cb is processed
-// (tcgen05.wait::ld waits for everything outstanding, so the next load is issued right after the wait).
+// One trunk / feature layer epilogue for one row: accumulator (256 fp32 TMEM columns, bias already added by the
+// tensor core) (-> ReLU) -> bf16 -> A buffer (in place).  kSigma additionally accumulates the density head on the
+// fp32 activations.  The eight 32-column TMEM loads are software-pipelined: block cb+1 is in flight while block cb
+// is processed (tcgen05.wait::ld waits for everything outstanding, so the next load is issued right after it).
 template <bool kSplit3, bool kRelu, bool kSigma>
 __device__ __forceinline__ float layer_epilogue(uint8_t* smem, int slot, int row, uint32_t taddr,
-                                                const float* __restrict__ bias, const float* __restrict__ w_sigma) {
+                                                const float* __restrict__ w_sigma) {
   float sigma_acc = 0.f;
   const uint32_t hi_base = smem_u32(smem + kOffA + (kSplit3 ? 0 : slot) * kABytes) + row * 128;
   const uint32_t lo_base = smem_u32(smem + kOffA + kABytes) + row * 128;
@@ -664,25 +744,26 @@ __device__ __forceinline__ float layer_epilogue(uint8_t* smem, int slot, int row
   tmem_ld32(taddr, v[0]);
 #pragma unroll
   for (int cb = 0; cb < 8; ++cb) {
-    float b[32];
+    float ws[32];
+    if (kSigma) {
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const float4 t = __ldg(reinterpret_cast<const float4*>(bias + cb * 32) + q);
-      b[4 * q] = t.x; b[4 * q + 1] = t.y; b[4 * q + 2] = t.z; b[4 * q + 3] = t.w;
+      for (int q = 0; q < 8; ++q) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(w_sigma + cb * 32) + q);
+        ws[4 * q] = t.x; ws[4 * q + 1] = t.y; ws[4 * q + 2] = t.z; ws[4 * q + 3] = t.w;
+      }
     }
     tmem_ld_wait();
     if (cb + 1 < 8) tmem_ld32(taddr + (cb + 1) * 32, v[(cb + 1) & 1]);
     const uint32_t kb_off = (uint32_t)(cb >> 1) * kKBlockBytes;
     if (!kSplit3 && !kSigma) {
-      // throughput path: FADD2 for the bias, ReLU fused into the bf16x2 conversion (1 instruction / element)
+      // throughput path: ReLU fused into the bf16x2 conversion - one instruction per two elements
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         uint32_t w[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int e = 8 * j + 2 * q;
-          const uint64_t acc = pack_f32x2(__uint_as_float(v[cb & 1][e]), __uint_as_float(v[cb & 1][e + 1]));
-          w[q] = cvt_bf16x2<kRelu>(fadd2(acc, pack_f32x2(b[e], b[e + 1])));
+          w[q] = cvt_bf16x2<kRelu>(pack_f32x2(__uint_as_float(v[cb & 1][e]), __uint_as_float(v[cb & 1][e + 1])));
         }
         const int ch = (cb & 1) * 4 + j;
         st_shared_v4(hi_base + kb_off + (uint32_t)((ch ^ (row & 7)) << 4), w[0], w[1], w[2], w[3]);
@@ -692,18 +773,12 @@ __device__ __forceinline__ float layer_epilogue(uint8_t* smem, int slot, int row
     float h[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
-      h[j] = __uint_as_float(v[cb & 1][j]) + b[j];
+      h[j] = __uint_as_float(v[cb & 1][j]);
       if (kRelu) h[j] = fmaxf(h[j], 0.f);
     }
     if (kSigma) {
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const float4 t = __ldg(reinterpret_cast<const float4*>(w_sigma + cb * 32) + q);
-        sigma_acc = fmaf(h[4 * q], t.x, sigma_acc);
-        sigma_acc = fmaf(h[4 * q + 1], t.y, sigma_acc);
-        sigma_acc = fmaf(h[4 * q + 2], t.z, sigma_acc);
-        sigma_acc = fmaf(h[4 * q + 3], t.w, sigma_acc);
-      }
+      for (int j = 0; j < 32; ++j) sigma_acc = fmaf(h[j], ws[j], sigma_acc);
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -772,13 +847,13 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const TcParams p) 
       __trap();
     }
     // w_full: the local TMA's arrive.expect_tx (+ the peer's relayed arrival in pair mode); a_ready: one arrival per
-    // epilogue thread of every CTA feeding the MMA
+    // epilogue warp of every CTA feeding the MMA
     for (int s = 0; s < kStages; ++s) {
       mbar_init(bar(kBarWFull + s), kPair ? 2 : 1);
       mbar_init(bar(kBarWEmpty + s), 1);
       mbar_init(bar(kBarLocalFull + s), 1);
     }
-    for (int s = 0; s < 2; ++s) { mbar_init(bar(kBarAReady + s), kPair ? 256 : 128); mbar_init(bar(kBarDReady + s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(bar(kBarAReady + s), kPair ? 8 : 4); mbar_init(bar(kBarDReady + s), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 9) {
@@ -812,7 +887,11 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const TcParams p) 
       const WorkList<kFused, kPair> work(p, cta_group_idx * kSlots + slot, n_slots_total, (int)cta_rank);
       // a_ready lives in the leader CTA: the peer's epilogue threads arrive on it through the cluster window
       const uint32_t a_ready_bar = kPair ? map_to_cta(bar(kBarAReady + slot), 0) : bar(kBarAReady + slot);
-      auto arrive_a_ready = [&]() { if (kPair) mbar_arrive_cluster(a_ready_bar); else mbar_arrive(a_ready_bar); };
+      // one arrival per warp: every lane has fenced its writes to the async proxy, the warp converges, lane 0 signals
+      auto arrive_a_ready = [&]() {
+        __syncwarp();
+        if (lane == 0) { if (kPair) mbar_arrive_cluster(a_ready_bar); else mbar_arrive(a_ready_bar); }
+      };
       const uint32_t taddr = tmem_base + (uint32_t)(slot * 256) + ((uint32_t)((warp & 3) * 32) << 16);
       float* vb = reinterpret_cast<float*>(smem + kOffVb) + slot * 256;
       float* pev = reinterpret_cast<float*>(smem + kOffPev) + slot * 64;
@@ -909,10 +988,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const TcParams p) 
           tc_fence_after();
           const long long t1 = kProf ? clock64() : 0;
           c_wait += t1 - t0;
-          const float* bias = small + kOffBias + l * 256;
-          if (l == 7) sigma_lin = layer_epilogue<kSplit3, true, true>(smem, slot, row, taddr, bias, small + kOffWSigma);
-          else if (l == 8) layer_epilogue<kSplit3, false, false>(smem, slot, row, taddr, bias, nullptr);
-          else layer_epilogue<kSplit3, true, false>(smem, slot, row, taddr, bias, nullptr);
+          if (l == 7) sigma_lin = layer_epilogue<kSplit3, true, true>(smem, slot, row, taddr, small + kOffWSigma);
+          else if (l == 8) layer_epilogue<kSplit3, false, false>(smem, slot, row, taddr, nullptr);
+          else layer_epilogue<kSplit3, true, false>(smem, slot, row, taddr, nullptr);
           fence_proxy_async();
           tc_fence_before();
           arrive_a_ready();
@@ -1010,7 +1088,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const TcParams p) 
             const uint32_t bytes = kPair ? chunk_bytes / 2 : chunk_bytes;
             const uint8_t* src = p.pass[w.pass_of(it)].packed + kSmallBytes +
                                  (size_t)tc_layer_byte_offset(l) * (kSplit3 ? 2 : 1) + (kPair ? cta_rank * bytes : 0);
-            const int n_chunks = layer_chunks(l) * (kSplit3 ? 2 : 1);
+            const int n_chunks = layer_stream_chunks(l) * (kSplit3 ? 2 : 1);
             for (int c = 0; c < n_chunks; ++c, ++q) {
               const uint32_t stage = q % kStages;
               {
@@ -1081,6 +1159,14 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const TcParams p) 
           } else {
             run(a_hi, a_lo, 8, 0);
           }
+          if (layer_has_bias_chunk(l)) {
+            // encoding columns 48..63 (k-block offset 96 B = 6 units) x the bias chunk; BF16X3: hi and lo images
+            // (the lo part of the constant-one column is zero, so A_lo contributes nothing and is skipped)
+            for (int part = 0; part < (kSplit3 ? 2 : 1); ++part) {
+              q = kPair ? issue_bias_chunk_pair(d_tmem, pe_hi + 6, w_desc0, bar_full0, bar_empty0, q, idesc)
+                        : issue_bias_chunk(d_tmem, pe_hi + 6, w_desc0, bar_full0, bar_empty0, q, idesc);
+            }
+          }
           if (kPair) umma_commit_elect_pair(bar(kBarDReady + s)); else umma_commit_elect(bar(kBarDReady + s));
         }
       }
@@ -1105,7 +1191,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const TcParams p) 
         for (int s = 0; s < kSlots; ++s) {
           const WorkList<kFused, kPair>& w = s == 0 ? work0 : work1;
           if (it >= w.n_items) continue;
-          const int n_chunks = layer_chunks(l) * (kSplit3 ? 2 : 1);
+          const int n_chunks = layer_stream_chunks(l) * (kSplit3 ? 2 : 1);
           for (int c = 0; c < n_chunks; ++c, ++q) {
             const uint32_t stage = q % kStages;
             {

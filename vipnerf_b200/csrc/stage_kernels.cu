@@ -60,7 +60,14 @@ __global__ void k_pack_tc(ParamPtrs pp, uint8_t* __restrict__ big) {
   const int e = i - tc_layer_byte_offset(l) / 2;          // element index inside the layer
   const int chunk = e / (N * kChunkK), r = e % (N * kChunkK);
   const int n = r / kChunkK, k_local = r % kChunkK;
-  const float w = source_weight(pp, l, n, chunk * kChunkK + k_local);
+  float w;
+  if (chunk == layer_chunks(l)) {                         // the layer's bias chunk: column 31 <-> encoding column 63
+    w = k_local == kChunkK - 1 ? pp.p[bias_param(l)][n] : 0.f;
+  } else {
+    const int k = chunk * kChunkK + k_local;
+    const bool bias_col = (l == 0 || l == 5) && k == 63;  // the encoding block's constant-one column
+    w = bias_col ? pp.p[bias_param(l)][n] : source_weight(pp, l, n, k);
+  }
   const uint32_t byte = n * 64 + ((((k_local >> 3) ^ ((n >> 1) & 3))) << 4) + (k_local & 7) * 2;
   const size_t chunk_bytes = (size_t)layer_chunk_bytes(l);
   const size_t base = (size_t)tc_layer_byte_offset(l) * (kSplit3 ? 2 : 1);
