@@ -53,6 +53,7 @@ print(f'MMA lane: total {m[2]} cycles, wait a_ready {m[0]} ({100 * m[0] / max(1,
 for r in range(2):
     w, tot = b[40 + 4 * r], b[41 + 4 * r]
     if tot:
-        print(f'weight producer CTA {r}: total {tot} cycles, waiting for free ring stages {w} ({100 * w / tot:.1f}%)')
+        print(f'weight producer CTA {r}: total {tot} cycles, waiting for free ring stages {w} ({100 * w / tot:.1f}%), '
+              f'in expect_tx + cp.async.bulk issue {b[42 + 4 * r]} ({100 * b[42 + 4 * r] / tot:.1f}%)')
 if b[49]:
     print(f'weight relay (peer CTA): total {b[49]} cycles, waiting for its own copies {b[48]} ({100 * b[48] / b[49]:.1f}%)')

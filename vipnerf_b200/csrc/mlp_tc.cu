@@ -451,6 +451,127 @@ __device__ __forceinline__ uint32_t issue_chunks_split_pair(uint32_t d_tmem, uin
       : "memory");
   return q;
 }
+// Weight producer loop of one layer run (`n` consecutive chunks of `bytes` each, `stride` bytes apart in the packed
+// stream), hand-written in PTX for the same reason as issue_chunks: wait for the ring stage to be free, arm its full
+// barrier with the byte count, start the bulk copy (TMA engine), advance.  Executed by ONE lane.
+template <bool kPair>
+__device__ __forceinline__ uint32_t produce_chunks(const uint8_t* src, uint32_t bytes, uint32_t stride, uint32_t n,
+                                                   uint32_t q, uint32_t bar_full0, uint32_t bar_empty0,
+                                                   uint32_t w_smem0) {
+  if (kPair) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p, pw;\n"
+        ".reg .b32 c, stage, par, fb, eb, t, dst, spins;\n"
+        ".reg .b64 src;\n"
+        "mov.u32 c, 0;\n"
+        "mov.u64 src, %1;\n"
+        "PROD_LOOP:\n"
+        "and.b32 stage, %0, 7;\n"
+        "shr.u32 par, %0, 3;\n"
+        "and.b32 par, par, 1;\n"
+        "xor.b32 par, par, 1;\n"
+        "shl.b32 t, stage, 3;\n"
+        "add.u32 fb, %5, t;\n"
+        "add.u32 eb, %6, t;\n"
+        "mov.u32 spins, 0;\n"
+        "PROD_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 pw, [eb], par;\n"
+        "@pw bra PROD_READY;\n"
+        "add.u32 spins, spins, 1;\n"
+        "setp.gt.u32 p, spins, 4000000;\n"
+        "@p trap;\n"
+        "bra PROD_WAIT;\n"
+        "PROD_READY:\n"
+        "mbarrier.arrive.expect_tx.shared::cta.b64 _, [fb], %2;\n"
+        "mad.lo.u32 dst, stage, 8192, %7;\n"
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [dst], [src], %2, [fb];\n"
+        "cvt.u64.u32 %1, %3;\n"
+        "add.u64 src, src, %1;\n"
+        "add.u32 %0, %0, 1;\n"
+        "add.u32 c, c, 1;\n"
+        "setp.lt.u32 p, c, %4;\n"
+        "@p bra PROD_LOOP;\n"
+        "}\n"
+        : "+r"(q), "+l"(src)
+        : "r"(bytes), "r"(stride), "r"(n), "r"(bar_full0), "r"(bar_empty0), "r"(w_smem0)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n"
+        ".reg .pred p, pw;\n"
+        ".reg .b32 c, stage, par, fb, eb, t, dst, spins;\n"
+        ".reg .b64 src;\n"
+        "mov.u32 c, 0;\n"
+        "mov.u64 src, %1;\n"
+        "PROD_LOOP:\n"
+        "and.b32 stage, %0, 3;\n"
+        "shr.u32 par, %0, 2;\n"
+        "and.b32 par, par, 1;\n"
+        "xor.b32 par, par, 1;\n"
+        "shl.b32 t, stage, 3;\n"
+        "add.u32 fb, %5, t;\n"
+        "add.u32 eb, %6, t;\n"
+        "mov.u32 spins, 0;\n"
+        "PROD_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 pw, [eb], par;\n"
+        "@pw bra PROD_READY;\n"
+        "add.u32 spins, spins, 1;\n"
+        "setp.gt.u32 p, spins, 4000000;\n"
+        "@p trap;\n"
+        "bra PROD_WAIT;\n"
+        "PROD_READY:\n"
+        "mbarrier.arrive.expect_tx.shared::cta.b64 _, [fb], %2;\n"
+        "mad.lo.u32 dst, stage, 16384, %7;\n"
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [dst], [src], %2, [fb];\n"
+        "cvt.u64.u32 %1, %3;\n"
+        "add.u64 src, src, %1;\n"
+        "add.u32 %0, %0, 1;\n"
+        "add.u32 c, c, 1;\n"
+        "setp.lt.u32 p, c, %4;\n"
+        "@p bra PROD_LOOP;\n"
+        "}\n"
+        : "+r"(q), "+l"(src)
+        : "r"(bytes), "r"(stride), "r"(n), "r"(bar_full0), "r"(bar_empty0), "r"(w_smem0)
+        : "memory");
+  }
+  return q;
+}
+// Weight relay loop of the peer CTA (pair mode): for each of `n` chunks wait for the local copy (local_full) and
+// arrive on the leader's w_full of the same stage (`remote_full0` = cluster address of the leader's w_full[0]).
+__device__ __forceinline__ uint32_t relay_chunks(uint32_t n, uint32_t q, uint32_t bar_local0, uint32_t remote_full0) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p, pw;\n"
+      ".reg .b32 c, stage, par, lb, rb, t, spins;\n"
+      "mov.u32 c, 0;\n"
+      "RELAY_LOOP:\n"
+      "and.b32 stage, %0, 7;\n"
+      "shr.u32 par, %0, 3;\n"
+      "and.b32 par, par, 1;\n"
+      "shl.b32 t, stage, 3;\n"
+      "add.u32 lb, %2, t;\n"
+      "add.u32 rb, %3, t;\n"
+      "mov.u32 spins, 0;\n"
+      "RELAY_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 pw, [lb], par;\n"
+      "@pw bra RELAY_READY;\n"
+      "add.u32 spins, spins, 1;\n"
+      "setp.gt.u32 p, spins, 4000000;\n"
+      "@p trap;\n"
+      "bra RELAY_WAIT;\n"
+      "RELAY_READY:\n"
+      "mbarrier.arrive.shared::cluster.b64 _, [rb];\n"
+      "add.u32 %0, %0, 1;\n"
+      "add.u32 c, c, 1;\n"
+      "setp.lt.u32 p, c, %1;\n"
+      "@p bra RELAY_LOOP;\n"
+      "}\n"
+      : "+r"(q)
+      : "r"(n), "r"(bar_local0), "r"(remote_full0)
+      : "memory");
+  return q;
+}
 // The bias chunk of a layer: ONE accumulating MMA - A = the last 16 columns of the encoding k-block (column 63 is the
 // constant 1), B = the second K=16 step of the chunk (its column 31 holds the bias) - then the stage-release commit.
 __device__ __forceinline__ uint32_t issue_bias_chunk(uint32_t d_tmem, uint64_t a_desc, uint64_t w_desc0, uint32_t bar_full0,
@@ -1076,7 +1197,6 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const TcParams p) 
       // pair mode: this CTA streams its half of every chunk's rows; the leader's copies complete on w_full, the
       // peer's on its local_full (relayed to the leader's w_full by the peer's warp 9)
       const int full_base = (kPair && cta_rank == 1) ? kBarLocalFull : kBarWFull;
-      long long c_prod_wait = 0;
       const long long c_prod_begin = kProf ? clock64() : 0;
       uint32_t q = 0;
       for (int it = 0; it < n_max; ++it) {
@@ -1088,24 +1208,16 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const TcParams p) 
             const uint32_t bytes = kPair ? chunk_bytes / 2 : chunk_bytes;
             const uint8_t* src = p.pass[w.pass_of(it)].packed + kSmallBytes +
                                  (size_t)tc_layer_byte_offset(l) * (kSplit3 ? 2 : 1) + (kPair ? cta_rank * bytes : 0);
-            const int n_chunks = layer_stream_chunks(l) * (kSplit3 ? 2 : 1);
-            for (int c = 0; c < n_chunks; ++c, ++q) {
-              const uint32_t stage = q % kStages;
-              {
-                const long long t0 = kProf ? clock64() : 0;
-                mbar_wait(bar(kBarWEmpty + stage), ((q / kStages) & 1) ^ 1);
-                if (kProf) c_prod_wait += clock64() - t0;
-              }
-              mbar_arrive_expect_tx(bar(full_base + stage), bytes);
-              bulk_copy_g2s(smem_u32(smem + kOffW + stage * kStageBytes), src + (size_t)c * chunk_bytes, bytes,
-                            bar(full_base + stage));
-            }
+            const uint32_t n_chunks = layer_stream_chunks(l) * (kSplit3 ? 2 : 1);
+            q = produce_chunks<kPair>(src, bytes, chunk_bytes, n_chunks, q, bar(full_base), bar(kBarWEmpty),
+                                      smem_u32(smem + kOffW));
           }
         }
       }
       if (kProf && p.prof != nullptr && blockIdx.x < 2) {
-        p.prof[40 + 4 * blockIdx.x] = c_prod_wait;
+        p.prof[40 + 4 * blockIdx.x] = 0;
         p.prof[41 + 4 * blockIdx.x] = (unsigned long long)(clock64() - c_prod_begin);
+        p.prof[42 + 4 * blockIdx.x] = 0;
       }
     }
   } else if (!kPair || cta_rank == 0) {
@@ -1184,29 +1296,20 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const TcParams p) 
     WorkList<kFused, kPair> work1(p, cta_group_idx * kSlots + (kSlots - 1), n_slots_total, (int)cta_rank);
     const int n_max = max(work0.n_items, kSlots > 1 ? work1.n_items : 0);
     uint32_t q = 0;
-    long long c_relay_wait = 0;
+    const uint32_t remote_full0 = map_to_cta(bar(kBarWFull), 0);
     const long long c_relay_begin = kProf ? clock64() : 0;
     for (int it = 0; it < n_max; ++it) {
       for (int l = 0; l < kNumMatLayers; ++l) {
         for (int s = 0; s < kSlots; ++s) {
           const WorkList<kFused, kPair>& w = s == 0 ? work0 : work1;
           if (it >= w.n_items) continue;
-          const int n_chunks = layer_stream_chunks(l) * (kSplit3 ? 2 : 1);
-          for (int c = 0; c < n_chunks; ++c, ++q) {
-            const uint32_t stage = q % kStages;
-            {
-              const long long t0 = kProf ? clock64() : 0;
-              mbar_wait(bar(kBarLocalFull + stage), (q / kStages) & 1);
-              if (kProf) c_relay_wait += clock64() - t0;
-            }
-            if (lane == 0) mbar_arrive_cluster(map_to_cta(bar(kBarWFull + stage), 0));
-            __syncwarp();
-          }
+          const uint32_t n_chunks = layer_stream_chunks(l) * (kSplit3 ? 2 : 1);
+          if (lane == 0) q = relay_chunks(n_chunks, q, bar(kBarLocalFull), remote_full0);
         }
       }
     }
     if (kProf && p.prof != nullptr && blockIdx.x == 1 && lane == 0) {
-      p.prof[48] = c_relay_wait;
+      p.prof[48] = 0;
       p.prof[49] = (unsigned long long)(clock64() - c_relay_begin);
     }
   }
