@@ -457,12 +457,12 @@ __device__ __forceinline__ uint32_t issue_chunks_split_pair(uint32_t d_tmem, uin
 template <bool kPair>
 __device__ __forceinline__ uint32_t produce_chunks(const uint8_t* src, uint32_t bytes, uint32_t stride, uint32_t n,
                                                    uint32_t q, uint32_t bar_full0, uint32_t bar_empty0,
-                                                   uint32_t w_smem0) {
+                                                   uint32_t w_smem0, uint32_t& wait_cycles) {
   if (kPair) {
     asm volatile(
         "{\n"
         ".reg .pred p, pw;\n"
-        ".reg .b32 c, stage, par, fb, eb, t, dst, spins;\n"
+        ".reg .b32 c, stage, par, fb, eb, t, dst, spins, c0, c1;\n"
         ".reg .b64 src;\n"
         "mov.u32 c, 0;\n"
         "mov.u64 src, %1;\n"
@@ -472,9 +472,10 @@ __device__ __forceinline__ uint32_t produce_chunks(const uint8_t* src, uint32_t 
         "and.b32 par, par, 1;\n"
         "xor.b32 par, par, 1;\n"
         "shl.b32 t, stage, 3;\n"
-        "add.u32 fb, %5, t;\n"
-        "add.u32 eb, %6, t;\n"
+        "add.u32 fb, %6, t;\n"
+        "add.u32 eb, %7, t;\n"
         "mov.u32 spins, 0;\n"
+        "mov.u32 c0, %clock;\n"
         "PROD_WAIT:\n"
         "mbarrier.try_wait.parity.shared::cta.b64 pw, [eb], par;\n"
         "@pw bra PROD_READY;\n"
@@ -483,24 +484,27 @@ __device__ __forceinline__ uint32_t produce_chunks(const uint8_t* src, uint32_t 
         "@p trap;\n"
         "bra PROD_WAIT;\n"
         "PROD_READY:\n"
-        "mbarrier.arrive.expect_tx.shared::cta.b64 _, [fb], %2;\n"
-        "mad.lo.u32 dst, stage, 8192, %7;\n"
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [dst], [src], %2, [fb];\n"
-        "cvt.u64.u32 %1, %3;\n"
+        "mov.u32 c1, %clock;\n"
+        "sub.u32 c1, c1, c0;\n"
+        "add.u32 %2, %2, c1;\n"
+        "mbarrier.arrive.expect_tx.shared::cta.b64 _, [fb], %3;\n"
+        "mad.lo.u32 dst, stage, 8192, %8;\n"
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [dst], [src], %3, [fb];\n"
+        "cvt.u64.u32 %1, %4;\n"
         "add.u64 src, src, %1;\n"
         "add.u32 %0, %0, 1;\n"
         "add.u32 c, c, 1;\n"
-        "setp.lt.u32 p, c, %4;\n"
+        "setp.lt.u32 p, c, %5;\n"
         "@p bra PROD_LOOP;\n"
         "}\n"
-        : "+r"(q), "+l"(src)
+        : "+r"(q), "+l"(src), "+r"(wait_cycles)
         : "r"(bytes), "r"(stride), "r"(n), "r"(bar_full0), "r"(bar_empty0), "r"(w_smem0)
         : "memory");
   } else {
     asm volatile(
         "{\n"
         ".reg .pred p, pw;\n"
-        ".reg .b32 c, stage, par, fb, eb, t, dst, spins;\n"
+        ".reg .b32 c, stage, par, fb, eb, t, dst, spins, c0, c1;\n"
         ".reg .b64 src;\n"
         "mov.u32 c, 0;\n"
         "mov.u64 src, %1;\n"
@@ -510,9 +514,10 @@ __device__ __forceinline__ uint32_t produce_chunks(const uint8_t* src, uint32_t 
         "and.b32 par, par, 1;\n"
         "xor.b32 par, par, 1;\n"
         "shl.b32 t, stage, 3;\n"
-        "add.u32 fb, %5, t;\n"
-        "add.u32 eb, %6, t;\n"
+        "add.u32 fb, %6, t;\n"
+        "add.u32 eb, %7, t;\n"
         "mov.u32 spins, 0;\n"
+        "mov.u32 c0, %clock;\n"
         "PROD_WAIT:\n"
         "mbarrier.try_wait.parity.shared::cta.b64 pw, [eb], par;\n"
         "@pw bra PROD_READY;\n"
@@ -521,17 +526,20 @@ __device__ __forceinline__ uint32_t produce_chunks(const uint8_t* src, uint32_t 
         "@p trap;\n"
         "bra PROD_WAIT;\n"
         "PROD_READY:\n"
-        "mbarrier.arrive.expect_tx.shared::cta.b64 _, [fb], %2;\n"
-        "mad.lo.u32 dst, stage, 16384, %7;\n"
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [dst], [src], %2, [fb];\n"
-        "cvt.u64.u32 %1, %3;\n"
+        "mov.u32 c1, %clock;\n"
+        "sub.u32 c1, c1, c0;\n"
+        "add.u32 %2, %2, c1;\n"
+        "mbarrier.arrive.expect_tx.shared::cta.b64 _, [fb], %3;\n"
+        "mad.lo.u32 dst, stage, 16384, %8;\n"
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [dst], [src], %3, [fb];\n"
+        "cvt.u64.u32 %1, %4;\n"
         "add.u64 src, src, %1;\n"
         "add.u32 %0, %0, 1;\n"
         "add.u32 c, c, 1;\n"
-        "setp.lt.u32 p, c, %4;\n"
+        "setp.lt.u32 p, c, %5;\n"
         "@p bra PROD_LOOP;\n"
         "}\n"
-        : "+r"(q), "+l"(src)
+        : "+r"(q), "+l"(src), "+r"(wait_cycles)
         : "r"(bytes), "r"(stride), "r"(n), "r"(bar_full0), "r"(bar_empty0), "r"(w_smem0)
         : "memory");
   }
@@ -539,20 +547,22 @@ __device__ __forceinline__ uint32_t produce_chunks(const uint8_t* src, uint32_t 
 }
 // Weight relay loop of the peer CTA (pair mode): for each of `n` chunks wait for the local copy (local_full) and
 // arrive on the leader's w_full of the same stage (`remote_full0` = cluster address of the leader's w_full[0]).
-__device__ __forceinline__ uint32_t relay_chunks(uint32_t n, uint32_t q, uint32_t bar_local0, uint32_t remote_full0) {
+__device__ __forceinline__ uint32_t relay_chunks(uint32_t n, uint32_t q, uint32_t bar_local0, uint32_t remote_full0,
+                                                 uint32_t& wait_cycles) {
   asm volatile(
       "{\n"
       ".reg .pred p, pw;\n"
-      ".reg .b32 c, stage, par, lb, rb, t, spins;\n"
+      ".reg .b32 c, stage, par, lb, rb, t, spins, c0, c1;\n"
       "mov.u32 c, 0;\n"
       "RELAY_LOOP:\n"
       "and.b32 stage, %0, 7;\n"
       "shr.u32 par, %0, 3;\n"
       "and.b32 par, par, 1;\n"
       "shl.b32 t, stage, 3;\n"
-      "add.u32 lb, %2, t;\n"
-      "add.u32 rb, %3, t;\n"
+      "add.u32 lb, %3, t;\n"
+      "add.u32 rb, %4, t;\n"
       "mov.u32 spins, 0;\n"
+      "mov.u32 c0, %clock;\n"
       "RELAY_WAIT:\n"
       "mbarrier.try_wait.parity.shared::cta.b64 pw, [lb], par;\n"
       "@pw bra RELAY_READY;\n"
@@ -561,13 +571,16 @@ __device__ __forceinline__ uint32_t relay_chunks(uint32_t n, uint32_t q, uint32_
       "@p trap;\n"
       "bra RELAY_WAIT;\n"
       "RELAY_READY:\n"
+      "mov.u32 c1, %clock;\n"
+      "sub.u32 c1, c1, c0;\n"
+      "add.u32 %1, %1, c1;\n"
       "mbarrier.arrive.shared::cluster.b64 _, [rb];\n"
       "add.u32 %0, %0, 1;\n"
       "add.u32 c, c, 1;\n"
-      "setp.lt.u32 p, c, %1;\n"
+      "setp.lt.u32 p, c, %2;\n"
       "@p bra RELAY_LOOP;\n"
       "}\n"
-      : "+r"(q)
+      : "+r"(q), "+r"(wait_cycles)
       : "r"(n), "r"(bar_local0), "r"(remote_full0)
       : "memory");
   return q;
@@ -1198,7 +1211,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const TcParams p) 
       // peer's on its local_full (relayed to the leader's w_full by the peer's warp 9)
       const int full_base = (kPair && cta_rank == 1) ? kBarLocalFull : kBarWFull;
       const long long c_prod_begin = kProf ? clock64() : 0;
-      uint32_t q = 0;
+      uint32_t q = 0, prod_wait = 0;
       for (int it = 0; it < n_max; ++it) {
         for (int l = 0; l < kNumMatLayers; ++l) {
           for (int s = 0; s < kSlots; ++s) {
@@ -1210,12 +1223,12 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const TcParams p) 
                                  (size_t)tc_layer_byte_offset(l) * (kSplit3 ? 2 : 1) + (kPair ? cta_rank * bytes : 0);
             const uint32_t n_chunks = layer_stream_chunks(l) * (kSplit3 ? 2 : 1);
             q = produce_chunks<kPair>(src, bytes, chunk_bytes, n_chunks, q, bar(full_base), bar(kBarWEmpty),
-                                      smem_u32(smem + kOffW));
+                                      smem_u32(smem + kOffW), prod_wait);
           }
         }
       }
       if (kProf && p.prof != nullptr && blockIdx.x < 2) {
-        p.prof[40 + 4 * blockIdx.x] = 0;
+        p.prof[40 + 4 * blockIdx.x] = prod_wait;
         p.prof[41 + 4 * blockIdx.x] = (unsigned long long)(clock64() - c_prod_begin);
         p.prof[42 + 4 * blockIdx.x] = 0;
       }
@@ -1297,6 +1310,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const TcParams p) 
     const int n_max = max(work0.n_items, kSlots > 1 ? work1.n_items : 0);
     uint32_t q = 0;
     const uint32_t remote_full0 = map_to_cta(bar(kBarWFull), 0);
+    uint32_t relay_wait = 0;
     const long long c_relay_begin = kProf ? clock64() : 0;
     for (int it = 0; it < n_max; ++it) {
       for (int l = 0; l < kNumMatLayers; ++l) {
@@ -1304,12 +1318,12 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const TcParams p) 
           const WorkList<kFused, kPair>& w = s == 0 ? work0 : work1;
           if (it >= w.n_items) continue;
           const uint32_t n_chunks = layer_stream_chunks(l) * (kSplit3 ? 2 : 1);
-          if (lane == 0) q = relay_chunks(n_chunks, q, bar(kBarLocalFull), remote_full0);
+          if (lane == 0) q = relay_chunks(n_chunks, q, bar(kBarLocalFull), remote_full0, relay_wait);
         }
       }
     }
     if (kProf && p.prof != nullptr && blockIdx.x == 1 && lane == 0) {
-      p.prof[48] = 0;
+      p.prof[48] = relay_wait;
       p.prof[49] = (unsigned long long)(clock64() - c_relay_begin);
     }
   }
