@@ -43,7 +43,9 @@ cudaError_t launch_mlp_fp32(const RayPtrs& rp, const RenderFlags& fl, int64_t n_
 // mlp_tc.cu : tcgen05 evaluation (precision = BF16 or BF16X3)
 cudaError_t launch_mlp_tc(int precision, const RayPtrs& rp, const RenderFlags& fl, int64_t n_rays, int S,
                           const float* z, const void* packed, float* sigma, float* rgb, float* vis,
-                          cudaStream_t s);
+                          void* pe_scratch, cudaStream_t s);
+// bytes of scratch the tensor-core kernels need (encoding images parked per CTA and tile slot); device-dependent
+size_t tc_scratch_bytes();
 // mlp_tc.cu : the fused coarse+fine render of a ray batch in one launch
 struct FusedArgs {
   RayPtrs rp;
@@ -58,6 +60,7 @@ struct FusedArgs {
   float* ws_sigma;      // [R,Nc+Nf]   network outputs of the pass in flight (reused coarse -> fine)
   float* ws_rgb;        // [R,Nc+Nf,3]
   float* ws_vis;        // [R,Nc+Nf]
+  void* pe_scratch;     // tc_scratch_bytes()
 };
 cudaError_t launch_render_fused_tc(int precision, const FusedArgs& a, cudaStream_t s);
 // debug: 64 x u64 device buffer that CTA 0 of the next tensor-core launches fills with cycle counters (null = off)

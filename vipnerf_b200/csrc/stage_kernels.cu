@@ -61,12 +61,12 @@ __global__ void k_pack_tc(ParamPtrs pp, uint8_t* __restrict__ big) {
   const int chunk = e / (N * kChunkK), r = e % (N * kChunkK);
   const int n = r / kChunkK, k_local = r % kChunkK;
   float w;
-  if (chunk == layer_chunks(l)) {                         // the layer's bias chunk: column 31 <-> encoding column 63
+  if (chunk == layer_chunks(l)) {                         // the layer's bias chunk: only column 31 is non-zero
     w = k_local == kChunkK - 1 ? pp.p[bias_param(l)][n] : 0.f;
   } else {
-    const int k = chunk * kChunkK + k_local;
-    const bool bias_col = (l == 0 || l == 5) && k == 63;  // the encoding block's constant-one column
-    w = bias_col ? pp.p[bias_param(l)][n] : source_weight(pp, l, n, k);
+    const int sc = tc_source_col(l, chunk * kChunkK + k_local);
+    w = sc == -2 ? pp.p[bias_param(l)][n]
+                 : (sc < 0 ? 0.f : pp.p[source_param(l)][(int64_t)n * source_in_features(l) + sc]);
   }
   const uint32_t byte = n * 64 + ((((k_local >> 3) ^ ((n >> 1) & 3))) << 4) + (k_local & 7) * 2;
   const size_t chunk_bytes = (size_t)layer_chunk_bytes(l);
