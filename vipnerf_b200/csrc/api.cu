@@ -148,8 +148,8 @@ size_t vipnerf_packed_weight_bytes(const vipnerf_cfg* cfg) {
   if (check_cfg(cfg) != VIPNERF_OK) return 0;
   switch (cfg->precision) {
     case VIPNERF_PRECISION_FP32: return kSmallBytes + (size_t)kFp32BigFloats * sizeof(float);
-    case VIPNERF_PRECISION_BF16: return kSmallBytes + (size_t)kTcBigBytes;
-    default: return kSmallBytes + (size_t)2 * kTcBigBytes;
+    case VIPNERF_PRECISION_BF16: return kSmallBytes + (size_t)kTcBigBytes * tc_weight_replicas();
+    default: return kSmallBytes + (size_t)2 * kTcBigBytes * tc_weight_replicas();
   }
 }
 

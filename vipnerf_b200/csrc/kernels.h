@@ -29,6 +29,11 @@ struct RenderFlags {
   int n_sec_views;
 };
 
+// Number of copies of the tensor-core weight stream inside a packed buffer (env VIPNERF_TC_WEIGHT_REPLICAS,
+// default 8, read once): every SM re-reads the whole stream per tile, all SMs at nearly the same time, so a single
+// copy turns a handful of L2 slices into a hot spot; CTA (pair) i streams copy i mod n.
+int tc_weight_replicas();
+
 // stage_kernels.cu
 cudaError_t launch_pack_weights(int precision, const float* const params_dev[24], void* packed, cudaStream_t s);
 cudaError_t launch_coarse_z(const RayPtrs& rp, int64_t n_rays, int n_coarse, bool lindisp, float* z, cudaStream_t s);

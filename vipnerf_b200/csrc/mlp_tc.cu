@@ -771,6 +771,7 @@ struct TcParams {
   int has_fine;
   unsigned long long* prof;  // optional cycle counters of CTA 0 (vipnerf_debug_set_profile_buffer), else null
   uint8_t* pe_scratch;       // [grid][2 slots][2 (hi, lo)][16 KiB]: encoding k-block images parked for M5's second pass
+  int n_weight_replicas;     // copies of the weight stream in each packed buffer (kernels.h)
 };
 
 // Work of one tile slot: item i -> (pass, tile).  `unit` indexes the work units of the launch (fused: ray pairs,
@@ -1254,6 +1255,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const TcParams p) 
       const int full_base = (kPair && cta_rank == 1) ? kBarLocalFull : kBarWFull;
       const long long c_prod_begin = kProf ? clock64() : 0;
       RingState ring;
+      const size_t replica_offset =
+          (size_t)(cta_group_idx % p.n_weight_replicas) * ((size_t)kTcBigBytes * (kSplit3 ? 2 : 1));
       for (int it = 0; it < n_max; ++it) {
         for (int l = 0; l < kNumMatLayers; ++l) {
           for (int s = 0; s < kSlots; ++s) {
@@ -1261,7 +1264,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const TcParams p) 
             if (it >= w.n_items) continue;
             const uint32_t chunk_bytes = layer_chunk_bytes(l);
             const uint32_t bytes = kPair ? chunk_bytes / 2 : chunk_bytes;
-            const uint8_t* src = p.pass[w.pass_of(it)].packed + kSmallBytes +
+            const uint8_t* src = p.pass[w.pass_of(it)].packed + kSmallBytes + replica_offset +
                                  (size_t)tc_layer_byte_offset(l) * (kSplit3 ? 2 : 1) + (kPair ? cta_rank * bytes : 0);
             const uint32_t n_chunks = layer_stream_chunks(l) * (kSplit3 ? 2 : 1);
             produce_chunks<kPair>(ring, src, bytes, chunk_bytes, n_chunks, bar(full_base), bar(kBarWEmpty),
@@ -1485,6 +1488,7 @@ cudaError_t launch_mlp_tc(int precision, const RayPtrs& rp, const RenderFlags& f
   p.n_units = (p.pass[0].n_points + kTile - 1) / kTile;
   p.prof = g_prof_buffer;
   p.pe_scratch = static_cast<uint8_t*>(pe_scratch);
+  p.n_weight_replicas = tc_weight_replicas();
   if (p.n_units == 0) return cudaSuccess;
   if (precision == VIPNERF_PRECISION_BF16X3) return launch<true, false>(p, p.n_units, s);
   return launch<false, false>(p, p.n_units, s);
@@ -1517,6 +1521,7 @@ cudaError_t launch_render_fused_tc(int precision, const FusedArgs& a, cudaStream
   p.n_units = (a.n_rays + 1) / 2;
   p.prof = g_prof_buffer;
   p.pe_scratch = static_cast<uint8_t*>(a.pe_scratch);
+  p.n_weight_replicas = tc_weight_replicas();
   if (precision == VIPNERF_PRECISION_BF16X3) return launch<true, true>(p, p.n_units, s);
   return launch<false, true>(p, p.n_units, s);
 }

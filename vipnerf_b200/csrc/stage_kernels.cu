@@ -1,6 +1,8 @@
 // Weight packing, coarse sample placement and the stand-alone compositing / re-sampling kernel.
 #include <cuda_bf16.h>
 
+#include <cstdlib>
+
 #include "kernels.h"
 #include "layout.cuh"
 
@@ -81,6 +83,15 @@ __global__ void k_pack_tc(ParamPtrs pp, uint8_t* __restrict__ big) {
   }
 }
 
+int tc_weight_replicas() {
+  static const int n = []() {
+    const char* e = getenv("VIPNERF_TC_WEIGHT_REPLICAS");
+    int v = e ? atoi(e) : 8;
+    return v < 1 ? 1 : (v > 32 ? 32 : v);
+  }();
+  return n;
+}
+
 cudaError_t launch_pack_weights(int precision, const float* const params_dev[24], void* packed, cudaStream_t s) {
   ParamPtrs pp;
   for (int i = 0; i < 24; ++i) pp.p[i] = params_dev[i];
@@ -91,8 +102,11 @@ cudaError_t launch_pack_weights(int precision, const float* const params_dev[24]
     k_pack_fp32<<<(kFp32BigFloats + 255) / 256, 256, 0, s>>>(pp, reinterpret_cast<float*>(big));
   } else {
     const int n = kTcBigBytes / 2;
-    if (precision == VIPNERF_PRECISION_BF16X3) k_pack_tc<true><<<(n + 255) / 256, 256, 0, s>>>(pp, big);
-    else k_pack_tc<false><<<(n + 255) / 256, 256, 0, s>>>(pp, big);
+    const size_t copy_bytes = (size_t)kTcBigBytes * (precision == VIPNERF_PRECISION_BF16X3 ? 2 : 1);
+    for (int r = 0; r < tc_weight_replicas(); ++r) {
+      if (precision == VIPNERF_PRECISION_BF16X3) k_pack_tc<true><<<(n + 255) / 256, 256, 0, s>>>(pp, big + r * copy_bytes);
+      else k_pack_tc<false><<<(n + 255) / 256, 256, 0, s>>>(pp, big + r * copy_bytes);
+    }
   }
   return cudaGetLastError();
 }
