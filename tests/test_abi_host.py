@@ -44,10 +44,9 @@ def test_config_validation(built_library):
     lib = _lib.load()
     ok = _lib.make_cfg(precision='bf16')
     assert lib.vipnerf_check_config(ctypes.byref(ok)) == 0
-    reps = int(os.environ.get('VIPNERF_TC_WEIGHT_REPLICAS', '8'))   # copies of the weight stream (L2 hot-spot relief)
-    assert lib.vipnerf_packed_weight_bytes(ctypes.byref(ok)) == 27648 + reps * (72 + 7) * 16384   # 76 weight chunks (8 half-size) + 7 bias chunks
+    assert lib.vipnerf_packed_weight_bytes(ctypes.byref(ok)) == 27648 + (72 + 7) * 16384   # 76 weight chunks (8 of them half-size) + 7 bias chunks
     x3 = _lib.make_cfg(precision='bf16x3')
-    assert lib.vipnerf_packed_weight_bytes(ctypes.byref(x3)) == 27648 + reps * 2 * (72 + 7) * 16384
+    assert lib.vipnerf_packed_weight_bytes(ctypes.byref(x3)) == 27648 + 2 * (72 + 7) * 16384
     f32 = _lib.make_cfg(precision='fp32')
     assert lib.vipnerf_packed_weight_bytes(ctypes.byref(f32)) == 27648 + 589824 * 4
     assert lib.vipnerf_workspace_bytes(ctypes.byref(ok), 4096) > 4096 * (64 + 192 * 6) * 4

@@ -58,7 +58,7 @@ int check_cfg(const vipnerf_cfg* cfg) {
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct Workspace {
-  size_t off_z_coarse, off_z_fine, off_sigma, off_rgb, off_vis, off_vis2, off_tc_scratch, total;
+  size_t off_z_coarse, off_z_fine, off_sigma, off_rgb, off_vis, off_vis2, total;
 };
 
 Workspace carve(const vipnerf_cfg* cfg, int64_t n_rays) {
@@ -73,7 +73,6 @@ Workspace carve(const vipnerf_cfg* cfg, int64_t n_rays) {
   w.off_rgb = take(R * sf * 3);
   w.off_vis = take(R * sf);
   w.off_vis2 = take(R * sf * (size_t)cfg->n_sec_views);
-  w.off_tc_scratch = take(is_tc(cfg->precision) ? tc_scratch_bytes() / sizeof(float) : 0);
   w.total = off + 256;
   return w;
 }
@@ -148,8 +147,8 @@ size_t vipnerf_packed_weight_bytes(const vipnerf_cfg* cfg) {
   if (check_cfg(cfg) != VIPNERF_OK) return 0;
   switch (cfg->precision) {
     case VIPNERF_PRECISION_FP32: return kSmallBytes + (size_t)kFp32BigFloats * sizeof(float);
-    case VIPNERF_PRECISION_BF16: return kSmallBytes + (size_t)kTcBigBytes * tc_weight_replicas();
-    default: return kSmallBytes + (size_t)2 * kTcBigBytes * tc_weight_replicas();
+    case VIPNERF_PRECISION_BF16: return kSmallBytes + (size_t)kTcBigBytes;
+    default: return kSmallBytes + (size_t)2 * kTcBigBytes;
   }
 }
 
@@ -184,6 +183,7 @@ int vipnerf_coarse_z(const vipnerf_cfg* cfg, const vipnerf_rays* rays, int64_t n
 int vipnerf_mlp_forward(const vipnerf_cfg* cfg, const vipnerf_rays* rays, int64_t n_rays, int32_t n_samples,
                         const float* z_vals, const void* packed, const vipnerf_pass_out* out, void* workspace,
                         size_t workspace_bytes, void* stream) {
+  (void)workspace; (void)workspace_bytes;
   if (int rc = check_cfg(cfg)) return rc;
   if (n_rays == 0) return VIPNERF_OK;
   RayPtrs rp{};
@@ -200,12 +200,8 @@ int vipnerf_mlp_forward(const vipnerf_cfg* cfg, const vipnerf_rays* rays, int64_
                         out->raw_visibility2, s);
   } else {
     if (n_samples != 64 && n_samples != 192) return fail(VIPNERF_EUNSUPPORTED, "tensor-core MLP takes 64 or 192 samples per ray (got %d)", n_samples);
-    // the tensor-core kernel parks encoding images in the workspace (the same carving as vipnerf_render_forward)
-    const Workspace w = carve(cfg, n_rays);
-    if (!workspace || workspace_bytes < w.total) return fail(VIPNERF_EWORKSPACE, "workspace %zu bytes < required %zu (vipnerf_workspace_bytes)", workspace_bytes, w.total);
-    if (reinterpret_cast<uintptr_t>(workspace) & 255u) return fail(VIPNERF_EINVAL, "workspace must be 256-byte aligned");
     e = launch_mlp_tc(cfg->precision, rp, fl, n_rays, n_samples, z_vals, packed, out->raw_sigma, out->raw_rgb,
-                      out->raw_visibility, static_cast<uint8_t*>(workspace) + w.off_tc_scratch, s);
+                      out->raw_visibility, s);
   }
   if (e != cudaSuccess) return fail_cuda(e, "mlp_forward");
   return VIPNERF_OK;
@@ -258,7 +254,6 @@ int vipnerf_render_forward(const vipnerf_cfg* cfg, const vipnerf_rays* rays, int
     a.out_coarse = oc; a.out_fine = of;
     a.ws_z_coarse = at(w.off_z_coarse); a.ws_z_fine = at(w.off_z_fine);
     a.ws_sigma = at(w.off_sigma); a.ws_rgb = at(w.off_rgb); a.ws_vis = at(w.off_vis);
-    a.pe_scratch = at(w.off_tc_scratch);
     e = launch_render_fused_tc(cfg->precision, a, s);
     if (e != cudaSuccess) return fail_cuda(e, "render_fused_tc");
     return VIPNERF_OK;

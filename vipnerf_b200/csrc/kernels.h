@@ -29,11 +29,6 @@ struct RenderFlags {
   int n_sec_views;
 };
 
-// Number of copies of the tensor-core weight stream inside a packed buffer (env VIPNERF_TC_WEIGHT_REPLICAS,
-// default 8, read once): every SM re-reads the whole stream per tile, all SMs at nearly the same time, so a single
-// copy turns a handful of L2 slices into a hot spot; CTA (pair) i streams copy i mod n.
-int tc_weight_replicas();
-
 // stage_kernels.cu
 cudaError_t launch_pack_weights(int precision, const float* const params_dev[24], void* packed, cudaStream_t s);
 cudaError_t launch_coarse_z(const RayPtrs& rp, int64_t n_rays, int n_coarse, bool lindisp, float* z, cudaStream_t s);
@@ -48,9 +43,7 @@ cudaError_t launch_mlp_fp32(const RayPtrs& rp, const RenderFlags& fl, int64_t n_
 // mlp_tc.cu : tcgen05 evaluation (precision = BF16 or BF16X3)
 cudaError_t launch_mlp_tc(int precision, const RayPtrs& rp, const RenderFlags& fl, int64_t n_rays, int S,
                           const float* z, const void* packed, float* sigma, float* rgb, float* vis,
-                          void* pe_scratch, cudaStream_t s);
-// bytes of scratch the tensor-core kernels need (encoding images parked per CTA and tile slot); device-dependent
-size_t tc_scratch_bytes();
+                          cudaStream_t s);
 // mlp_tc.cu : the fused coarse+fine render of a ray batch in one launch
 struct FusedArgs {
   RayPtrs rp;
@@ -65,7 +58,6 @@ struct FusedArgs {
   float* ws_sigma;      // [R,Nc+Nf]   network outputs of the pass in flight (reused coarse -> fine)
   float* ws_rgb;        // [R,Nc+Nf,3]
   float* ws_vis;        // [R,Nc+Nf]
-  void* pe_scratch;     // tc_scratch_bytes()
 };
 cudaError_t launch_render_fused_tc(int precision, const FusedArgs& a, cudaStream_t s);
 // debug: 64 x u64 device buffer that CTA 0 of the next tensor-core launches fills with cycle counters (null = off)

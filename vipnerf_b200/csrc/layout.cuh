@@ -59,9 +59,10 @@ constexpr int kFp32BigFloats = fp32_layer_offset(kNumMatLayers);  // 589,824
 constexpr int kChunkK = 32;
 constexpr int kChunkBytes = 16384;   // ring stage size (largest chunk)
 __host__ __device__ constexpr int layer_chunks(int l) { return layer_k(l) / kChunkK; }
-// The bias is added by the tensor core as well: the encoding k-block's pad column (63) holds the constant 1.0, so
-// for M0 / M5 the bias is simply the weight column facing it; every other 256-wide layer gets one extra "bias
-// chunk" whose only non-zero column (31) is the bias, consumed by ONE K=16 MMA against an all-ones A block.  M9's bias travels with the
+// The bias is added by the tensor core as well: the encoding buffer's pad column (A column 63 of M0 and of the
+// first k-block of M5) holds the constant 1.0, so for M0 / M5 the bias is simply weight column 63; every other
+// 256-wide layer gets one extra "bias chunk" whose only non-zero column (31, facing encoding column 63) is the
+// bias, consumed by ONE K=16 MMA against the last 16 encoding columns.  M9's bias travels with the
 // view-direction term (fp32, per ray).  In bf16 mode the bias is therefore rounded to bf16; in BF16X3 mode the
 // lo image carries its residual.
 __host__ __device__ constexpr bool layer_has_bias_chunk(int l) { return l != 0 && l != 5 && l != 9; }
@@ -78,18 +79,6 @@ constexpr int kTcBigBytes = tc_layer_byte_offset(kNumMatLayers);    // 1,294,336
 __host__ __device__ inline int source_col(int l, int k) {
   if (l == 0) return k < kEncPts ? k : -1;
   if (l == 5) return k < kEncPts ? k : (k == 63 ? -1 : k - 1);  // 64 + j -> 63 + j
-  return k;
-}
-// Tensor-core path: A column k of matrix layer l -> source weight column; -1 = zero, -2 = the layer's bias (the
-// constant-one column 63 of the encoding k-block).  M5 is evaluated as two accumulation passes - the 256 hidden
-// columns first, the 64 encoding columns second - so its A columns are ordered [h4 | encoding].
-__host__ __device__ inline int tc_source_col(int l, int k) {
-  if (l == 0) return k < kEncPts ? k : -2;
-  if (l == 5) {
-    if (k < kWidth) return kEncPts + k;            // hidden part: reference columns 63 .. 318
-    const int j = k - kWidth;                       // encoding part
-    return j < kEncPts ? j : -2;
-  }
   return k;
 }
 // Index into params[24] of the bias of matrix layer l (M8 = feature_linear, M9 = views_linears.0).

@@ -37,23 +37,22 @@ namespace vipnerf {
 namespace {
 
 constexpr int kTile = 128;
+constexpr int kMaxStages = 8;  // weight-ring stages: 4 x 16 KiB (one CTA per tile pair) or 8 x 8 KiB (CTA pairs)
 constexpr int kNumThreads = 320;
 constexpr uint32_t kABytes = 65536;
 constexpr uint32_t kKBlockBytes = 16384;
 constexpr uint32_t kOffA = 0;                 // 2 x 64 KiB
-constexpr uint32_t kOffOnes = 131072;         // 4 KiB of bf16 1.0: the A operand of the bias chunks
-constexpr uint32_t kOffW = 135168;            // weight ring: 11 x 8 KiB (CTA pairs) or 5 x 16 KiB (single CTA)
-constexpr uint32_t kRingBytes = 90112;
-constexpr uint32_t kOffTail = kOffW + kRingBytes;
-constexpr uint32_t kOffBar = kOffTail;        // 37 mbarriers
-constexpr uint32_t kOffTmemPtr = kOffTail + 320;
-constexpr uint32_t kOffVb = kOffTail + 384;   // [2 slots][2 rays][128] fp32: view-direction part of M9 + bias
+constexpr uint32_t kOffPe = 131072;           // 2 x 16 KiB
+constexpr uint32_t kOffW = 163840;            // 4 x 16 KiB
+constexpr uint32_t kOffTail = 229376;
+constexpr uint32_t kOffBar = kOffTail;        // 28 mbarriers
+constexpr uint32_t kOffTmemPtr = kOffTail + 240;
+constexpr uint32_t kOffVb = kOffTail + 256;   // [2 slots][2 rays][128] fp32: view-direction part of M9 + bias
 constexpr uint32_t kOffPev = kOffVb + 2048;   // [2 slots][2 rays][32]  fp32: view-direction encodings
 constexpr uint32_t kSmemBytes = kOffPev + 512;
 static_assert(kSmemBytes <= 232448, "exceeds the 227 KiB per-CTA shared memory limit");
-constexpr uint32_t kPeScratchBytes = 16384;   // per tile slot: the encoding k-block image kept in global memory (L2)
 
-enum { kBarWFull = 0, kBarWEmpty = 11, kBarLocalFull = 22, kBarAReady = 33, kBarDReady = 35 };
+enum { kBarWFull = 0, kBarWEmpty = 8, kBarAReady = 16, kBarDReady = 18, kBarLocalFull = 20 };
 
 // tcgen05 instruction descriptor: D=F32, A=B=BF16, both K-major, M=128, N=n (cute::UMMA::InstrDescriptor bits:
 // c_format[4,6)=1, a_format[7,10)=1, b_format[10,13)=1, n_dim[17,23)=N>>3, m_dim[24,29)=M>>4)
@@ -180,150 +179,147 @@ __device__ __forceinline__ void mma_chunk_split_hi(uint32_t d_tmem, uint64_t a_h
       "l"(a_hi), "l"(a_lo), "l"(b_desc), "r"(first_acc), "r"(idesc), "r"(empty_bar)
       : "memory");
 }
-// Position in the weight ring (stage index and the phase parity of its barriers) plus a cycle counter the
-// profiling builds report; every role keeps its own copy and advances it chunk by chunk.
-struct RingState {
-  uint32_t stage = 0, phase = 0, wait_cycles = 0;
-};
-
 // The MMA issue loop of one run of `n_chunks` consecutive weight chunks, hand-written in PTX so that the per-chunk
 // cost is ~25 instructions (ptxas turns the equivalent C++ into ~135 with reconvergence barriers and R2UR moves).
 // Chunk c multiplies A columns [32c, 32c+32) - k-block c>>1 (1024 descriptor units apart), 64-byte half c&1
-// (4 units) - with the current ring stage: waits the stage's full barrier, issues two N x K=16 MMAs from the
-// elected lane, commits the stage's empty barrier and advances the ring.
-//   single CTA :  5 stages x 16 KiB (1024 units), tcgen05.mma.cta_group::1, M=128
-//   CTA pair   : 11 stages x  8 KiB ( 512 units: each CTA holds half of the chunk's rows), cta_group::2, M=256,
+// (4 units) - with ring stage q mod kStages, waits the stage's full barrier, issues two N x K=16 MMAs from the
+// elected lane and commits the stage's empty barrier.  Returns the advanced chunk counter q.
+//   single CTA : 4 stages x 16 KiB (1024 units), tcgen05.mma.cta_group::1, M=128
+//   CTA pair   : 8 stages x  8 KiB ( 512 units: each CTA holds half of the chunk's rows), cta_group::2, M=256,
 //                commits multicast to both CTAs' barriers
 // The *_split variants are BF16X3: every weight chunk is two ring stages (hi image, lo image); per chunk
 // A_hi*W_hi + A_lo*W_hi (4 MMAs, commit) then A_hi*W_lo (2 MMAs, commit).
-__device__ __forceinline__ void issue_chunks(RingState& rs, uint32_t d_tmem, uint64_t a_desc, uint64_t w_desc0,
-        uint32_t bar_full0, uint32_t bar_empty0, uint32_t n_chunks, uint32_t first_acc, uint32_t idesc) {
+__device__ __forceinline__ uint32_t issue_chunks(uint32_t d_tmem, uint64_t a_desc, uint64_t w_desc0, uint32_t bar_full0,
+        uint32_t bar_empty0, uint32_t q, uint32_t n_chunks, uint32_t first_acc, uint32_t idesc,
+        uint32_t& spin_total) {
   asm volatile(
       "{\n"
       ".reg .pred p, pw, e, pacc, pt;\n"
-      ".reg .b32 c, fb, eb, t, spins, c0, c1;\n"
+      ".reg .b32 c, stage, par, fb, eb, t, spins, c0, c1;\n"
       ".reg .b64 a, b, a1, b1, t64;\n"
       ".reg .b16 mc;\n"
       "mov.b16 mc, 3;\n"
       "mov.u32 c, 0;\n"
-      "setp.ne.b32 pacc, %9, 0;\n"
+      "setp.ne.b32 pacc, %8, 0;\n"
       "setp.eq.b32 pt, 0, 0;\n"
       "elect.sync _|e, 0xffffffff;\n"
       "CHUNK_LOOP:\n"
-      "shl.b32 t, %0, 3;\n"
-      "add.u32 fb, %6, t;\n"
-      "add.u32 eb, %7, t;\n"
+      "and.b32 stage, %0, 3;\n"
+      "shr.u32 par, %0, 2;\n"
+      "and.b32 par, par, 1;\n"
+      "shl.b32 t, stage, 3;\n"
+      "add.u32 fb, %5, t;\n"
+      "add.u32 eb, %6, t;\n"
       "mov.u32 spins, 0;\n"
       "mov.u32 c0, %clock;\n"
       "CHUNK_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 pw, [fb], %1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 pw, [fb], par;\n"
       "@pw bra CHUNK_READY;\n"
       "add.u32 spins, spins, 1;\n"
-      "setp.gt.u32 p, spins, 4000000;\n"
+            "setp.gt.u32 p, spins, 4000000;\n"
       "@p trap;\n"
       "bra CHUNK_WAIT;\n"
       "CHUNK_READY:\n"
       "mov.u32 c1, %clock;\n"
       "sub.u32 c1, c1, c0;\n"
-      "add.u32 %2, %2, c1;\n"
+      "add.u32 %1, %1, c1;\n"
       "tcgen05.fence::after_thread_sync;\n"
-      "mul.wide.u32 b, %0, 1024;\n"
-      "add.s64 b, b, %5;\n"
+      "mul.wide.u32 b, stage, 1024;\n"
+      "add.s64 b, b, %4;\n"
       "shr.u32 t, c, 1;\n"
       "mul.wide.u32 a, t, 1024;\n"
       "and.b32 t, c, 1;\n"
       "mul.wide.u32 t64, t, 4;\n"
       "add.s64 a, a, t64;\n"
-      "add.s64 a, a, %4;\n"
+      "add.s64 a, a, %3;\n"
       "add.s64 a1, a, 2;\n"
       "add.s64 b1, b, 2;\n"
-      "@e tcgen05.mma.cta_group::1.kind::f16 [%3], a, b, %10, pacc;\n"
-      "@e tcgen05.mma.cta_group::1.kind::f16 [%3], a1, b1, %10, pt;\n"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%2], a, b, %9, pacc;\n"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%2], a1, b1, %9, pt;\n"
       "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [eb];\n"
       "setp.eq.b32 pacc, 0, 0;\n"
       "add.u32 %0, %0, 1;\n"
-      "setp.eq.u32 p, %0, 5;\n"
-      "@p mov.u32 %0, 0;\n"
-      "@p xor.b32 %1, %1, 1;\n"
       "add.u32 c, c, 1;\n"
-      "setp.lt.u32 p, c, %8;\n"
+      "setp.lt.u32 p, c, %7;\n"
       "@p bra CHUNK_LOOP;\n"
       "}\n"
-      : "+r"(rs.stage), "+r"(rs.phase), "+r"(rs.wait_cycles)
+      : "+r"(q), "+r"(spin_total)
       : "r"(d_tmem), "l"(a_desc), "l"(w_desc0), "r"(bar_full0), "r"(bar_empty0), "r"(n_chunks), "r"(first_acc),
         "r"(idesc)
       : "memory");
+  return q;
 }
-__device__ __forceinline__ void issue_chunks_pair(RingState& rs, uint32_t d_tmem, uint64_t a_desc, uint64_t w_desc0,
-        uint32_t bar_full0, uint32_t bar_empty0, uint32_t n_chunks, uint32_t first_acc, uint32_t idesc) {
+__device__ __forceinline__ uint32_t issue_chunks_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t w_desc0, uint32_t bar_full0,
+        uint32_t bar_empty0, uint32_t q, uint32_t n_chunks, uint32_t first_acc, uint32_t idesc,
+        uint32_t& spin_total) {
   asm volatile(
       "{\n"
       ".reg .pred p, pw, e, pacc, pt;\n"
-      ".reg .b32 c, fb, eb, t, spins, c0, c1;\n"
+      ".reg .b32 c, stage, par, fb, eb, t, spins, c0, c1;\n"
       ".reg .b64 a, b, a1, b1, t64;\n"
       ".reg .b16 mc;\n"
       "mov.b16 mc, 3;\n"
       "mov.u32 c, 0;\n"
-      "setp.ne.b32 pacc, %9, 0;\n"
+      "setp.ne.b32 pacc, %8, 0;\n"
       "setp.eq.b32 pt, 0, 0;\n"
       "elect.sync _|e, 0xffffffff;\n"
       "CHUNK_LOOP:\n"
-      "shl.b32 t, %0, 3;\n"
-      "add.u32 fb, %6, t;\n"
-      "add.u32 eb, %7, t;\n"
+      "and.b32 stage, %0, 7;\n"
+      "shr.u32 par, %0, 3;\n"
+      "and.b32 par, par, 1;\n"
+      "shl.b32 t, stage, 3;\n"
+      "add.u32 fb, %5, t;\n"
+      "add.u32 eb, %6, t;\n"
       "mov.u32 spins, 0;\n"
       "mov.u32 c0, %clock;\n"
       "CHUNK_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 pw, [fb], %1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 pw, [fb], par;\n"
       "@pw bra CHUNK_READY;\n"
       "add.u32 spins, spins, 1;\n"
-      "setp.gt.u32 p, spins, 4000000;\n"
+            "setp.gt.u32 p, spins, 4000000;\n"
       "@p trap;\n"
       "bra CHUNK_WAIT;\n"
       "CHUNK_READY:\n"
       "mov.u32 c1, %clock;\n"
       "sub.u32 c1, c1, c0;\n"
-      "add.u32 %2, %2, c1;\n"
+      "add.u32 %1, %1, c1;\n"
       "tcgen05.fence::after_thread_sync;\n"
-      "mul.wide.u32 b, %0, 512;\n"
-      "add.s64 b, b, %5;\n"
+      "mul.wide.u32 b, stage, 512;\n"
+      "add.s64 b, b, %4;\n"
       "shr.u32 t, c, 1;\n"
       "mul.wide.u32 a, t, 1024;\n"
       "and.b32 t, c, 1;\n"
       "mul.wide.u32 t64, t, 4;\n"
       "add.s64 a, a, t64;\n"
-      "add.s64 a, a, %4;\n"
+      "add.s64 a, a, %3;\n"
       "add.s64 a1, a, 2;\n"
       "add.s64 b1, b, 2;\n"
-      "@e tcgen05.mma.cta_group::2.kind::f16 [%3], a, b, %10, pacc;\n"
-      "@e tcgen05.mma.cta_group::2.kind::f16 [%3], a1, b1, %10, pt;\n"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%2], a, b, %9, pacc;\n"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%2], a1, b1, %9, pt;\n"
       "@e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [eb], mc;\n"
       "setp.eq.b32 pacc, 0, 0;\n"
       "add.u32 %0, %0, 1;\n"
-      "setp.eq.u32 p, %0, 11;\n"
-      "@p mov.u32 %0, 0;\n"
-      "@p xor.b32 %1, %1, 1;\n"
       "add.u32 c, c, 1;\n"
-      "setp.lt.u32 p, c, %8;\n"
+      "setp.lt.u32 p, c, %7;\n"
       "@p bra CHUNK_LOOP;\n"
       "}\n"
-      : "+r"(rs.stage), "+r"(rs.phase), "+r"(rs.wait_cycles)
+      : "+r"(q), "+r"(spin_total)
       : "r"(d_tmem), "l"(a_desc), "l"(w_desc0), "r"(bar_full0), "r"(bar_empty0), "r"(n_chunks), "r"(first_acc),
         "r"(idesc)
       : "memory");
+  return q;
 }
-__device__ __forceinline__ void issue_chunks_split(RingState& rs, uint32_t d_tmem, uint64_t a_hi_desc, uint64_t a_lo_desc,
-        uint64_t w_desc0, uint32_t bar_full0, uint32_t bar_empty0, uint32_t n_chunks, uint32_t first_acc,
-        uint32_t idesc) {
+__device__ __forceinline__ uint32_t issue_chunks_split(uint32_t d_tmem, uint64_t a_hi_desc, uint64_t a_lo_desc, uint64_t w_desc0,
+        uint32_t bar_full0, uint32_t bar_empty0, uint32_t q, uint32_t n_chunks, uint32_t first_acc, uint32_t idesc) {
   asm volatile(
       "{\n"
       ".reg .pred p, pw, e, pacc, pt;\n"
-      ".reg .b32 c, fb, eb, t, spins, part;\n"
+      ".reg .b32 c, stage, par, fb, eb, t, spins, part;\n"
       ".reg .b64 a, l, b, a1, l1, b1, t64, off;\n"
       ".reg .b16 mc;\n"
       "mov.b16 mc, 3;\n"
       "mov.u32 c, 0;\n"
-      "setp.ne.b32 pacc, %9, 0;\n"
+      "setp.ne.b32 pacc, %8, 0;\n"
       "setp.eq.b32 pt, 0, 0;\n"
       "elect.sync _|e, 0xffffffff;\n"
       "SCHUNK_LOOP:\n"
@@ -333,17 +329,20 @@ __device__ __forceinline__ void issue_chunks_split(RingState& rs, uint32_t d_tme
       "and.b32 t, c, 1;\n"
       "mul.wide.u32 t64, t, 4;\n"
       "add.s64 off, off, t64;\n"
-      "add.s64 a, off, %3;\n"
-      "add.s64 l, off, %4;\n"
+      "add.s64 a, off, %2;\n"
+      "add.s64 l, off, %3;\n"
       "add.s64 a1, a, 2;\n"
       "add.s64 l1, l, 2;\n"
       "SPART_LOOP:\n"
-      "shl.b32 t, %0, 3;\n"
-      "add.u32 fb, %6, t;\n"
-      "add.u32 eb, %7, t;\n"
+      "and.b32 stage, %0, 3;\n"
+      "shr.u32 par, %0, 2;\n"
+      "and.b32 par, par, 1;\n"
+      "shl.b32 t, stage, 3;\n"
+      "add.u32 fb, %5, t;\n"
+      "add.u32 eb, %6, t;\n"
       "mov.u32 spins, 0;\n"
       "SCHUNK_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 pw, [fb], %1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 pw, [fb], par;\n"
       "@pw bra SCHUNK_READY;\n"
       "add.u32 spins, spins, 1;\n"
       "setp.gt.u32 p, spins, 4000000;\n"
@@ -351,50 +350,47 @@ __device__ __forceinline__ void issue_chunks_split(RingState& rs, uint32_t d_tme
       "bra SCHUNK_WAIT;\n"
       "SCHUNK_READY:\n"
       "tcgen05.fence::after_thread_sync;\n"
-      "mul.wide.u32 b, %0, 1024;\n"
-      "add.s64 b, b, %5;\n"
+      "mul.wide.u32 b, stage, 1024;\n"
+      "add.s64 b, b, %4;\n"
       "add.s64 b1, b, 2;\n"
       "setp.eq.u32 p, part, 0;\n"
       "@!p bra SLO_IMAGE;\n"
-      "@e tcgen05.mma.cta_group::1.kind::f16 [%2], a, b, %10, pacc;\n"
-      "@e tcgen05.mma.cta_group::1.kind::f16 [%2], l, b, %10, pt;\n"
-      "@e tcgen05.mma.cta_group::1.kind::f16 [%2], a1, b1, %10, pt;\n"
-      "@e tcgen05.mma.cta_group::1.kind::f16 [%2], l1, b1, %10, pt;\n"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%1], a, b, %9, pacc;\n"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%1], l, b, %9, pt;\n"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%1], a1, b1, %9, pt;\n"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%1], l1, b1, %9, pt;\n"
       "bra SPART_DONE;\n"
       "SLO_IMAGE:\n"
-      "@e tcgen05.mma.cta_group::1.kind::f16 [%2], a, b, %10, pt;\n"
-      "@e tcgen05.mma.cta_group::1.kind::f16 [%2], a1, b1, %10, pt;\n"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%1], a, b, %9, pt;\n"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%1], a1, b1, %9, pt;\n"
       "SPART_DONE:\n"
       "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [eb];\n"
       "setp.eq.b32 pacc, 0, 0;\n"
       "add.u32 %0, %0, 1;\n"
-      "setp.eq.u32 p, %0, 5;\n"
-      "@p mov.u32 %0, 0;\n"
-      "@p xor.b32 %1, %1, 1;\n"
       "add.u32 part, part, 1;\n"
       "setp.lt.u32 p, part, 2;\n"
       "@p bra SPART_LOOP;\n"
       "add.u32 c, c, 1;\n"
-      "setp.lt.u32 p, c, %8;\n"
+      "setp.lt.u32 p, c, %7;\n"
       "@p bra SCHUNK_LOOP;\n"
       "}\n"
-      : "+r"(rs.stage), "+r"(rs.phase)
+      : "+r"(q)
       : "r"(d_tmem), "l"(a_hi_desc), "l"(a_lo_desc), "l"(w_desc0), "r"(bar_full0), "r"(bar_empty0), "r"(n_chunks),
         "r"(first_acc), "r"(idesc)
       : "memory");
+  return q;
 }
-__device__ __forceinline__ void issue_chunks_split_pair(RingState& rs, uint32_t d_tmem, uint64_t a_hi_desc, uint64_t a_lo_desc,
-        uint64_t w_desc0, uint32_t bar_full0, uint32_t bar_empty0, uint32_t n_chunks, uint32_t first_acc,
-        uint32_t idesc) {
+__device__ __forceinline__ uint32_t issue_chunks_split_pair(uint32_t d_tmem, uint64_t a_hi_desc, uint64_t a_lo_desc, uint64_t w_desc0,
+        uint32_t bar_full0, uint32_t bar_empty0, uint32_t q, uint32_t n_chunks, uint32_t first_acc, uint32_t idesc) {
   asm volatile(
       "{\n"
       ".reg .pred p, pw, e, pacc, pt;\n"
-      ".reg .b32 c, fb, eb, t, spins, part;\n"
+      ".reg .b32 c, stage, par, fb, eb, t, spins, part;\n"
       ".reg .b64 a, l, b, a1, l1, b1, t64, off;\n"
       ".reg .b16 mc;\n"
       "mov.b16 mc, 3;\n"
       "mov.u32 c, 0;\n"
-      "setp.ne.b32 pacc, %9, 0;\n"
+      "setp.ne.b32 pacc, %8, 0;\n"
       "setp.eq.b32 pt, 0, 0;\n"
       "elect.sync _|e, 0xffffffff;\n"
       "SCHUNK_LOOP:\n"
@@ -404,17 +400,20 @@ __device__ __forceinline__ void issue_chunks_split_pair(RingState& rs, uint32_t 
       "and.b32 t, c, 1;\n"
       "mul.wide.u32 t64, t, 4;\n"
       "add.s64 off, off, t64;\n"
-      "add.s64 a, off, %3;\n"
-      "add.s64 l, off, %4;\n"
+      "add.s64 a, off, %2;\n"
+      "add.s64 l, off, %3;\n"
       "add.s64 a1, a, 2;\n"
       "add.s64 l1, l, 2;\n"
       "SPART_LOOP:\n"
-      "shl.b32 t, %0, 3;\n"
-      "add.u32 fb, %6, t;\n"
-      "add.u32 eb, %7, t;\n"
+      "and.b32 stage, %0, 7;\n"
+      "shr.u32 par, %0, 3;\n"
+      "and.b32 par, par, 1;\n"
+      "shl.b32 t, stage, 3;\n"
+      "add.u32 fb, %5, t;\n"
+      "add.u32 eb, %6, t;\n"
       "mov.u32 spins, 0;\n"
       "SCHUNK_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 pw, [fb], %1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 pw, [fb], par;\n"
       "@pw bra SCHUNK_READY;\n"
       "add.u32 spins, spins, 1;\n"
       "setp.gt.u32 p, spins, 4000000;\n"
@@ -422,58 +421,59 @@ __device__ __forceinline__ void issue_chunks_split_pair(RingState& rs, uint32_t 
       "bra SCHUNK_WAIT;\n"
       "SCHUNK_READY:\n"
       "tcgen05.fence::after_thread_sync;\n"
-      "mul.wide.u32 b, %0, 512;\n"
-      "add.s64 b, b, %5;\n"
+      "mul.wide.u32 b, stage, 512;\n"
+      "add.s64 b, b, %4;\n"
       "add.s64 b1, b, 2;\n"
       "setp.eq.u32 p, part, 0;\n"
       "@!p bra SLO_IMAGE;\n"
-      "@e tcgen05.mma.cta_group::2.kind::f16 [%2], a, b, %10, pacc;\n"
-      "@e tcgen05.mma.cta_group::2.kind::f16 [%2], l, b, %10, pt;\n"
-      "@e tcgen05.mma.cta_group::2.kind::f16 [%2], a1, b1, %10, pt;\n"
-      "@e tcgen05.mma.cta_group::2.kind::f16 [%2], l1, b1, %10, pt;\n"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%1], a, b, %9, pacc;\n"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%1], l, b, %9, pt;\n"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%1], a1, b1, %9, pt;\n"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%1], l1, b1, %9, pt;\n"
       "bra SPART_DONE;\n"
       "SLO_IMAGE:\n"
-      "@e tcgen05.mma.cta_group::2.kind::f16 [%2], a, b, %10, pt;\n"
-      "@e tcgen05.mma.cta_group::2.kind::f16 [%2], a1, b1, %10, pt;\n"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%1], a, b, %9, pt;\n"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%1], a1, b1, %9, pt;\n"
       "SPART_DONE:\n"
       "@e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [eb], mc;\n"
       "setp.eq.b32 pacc, 0, 0;\n"
       "add.u32 %0, %0, 1;\n"
-      "setp.eq.u32 p, %0, 11;\n"
-      "@p mov.u32 %0, 0;\n"
-      "@p xor.b32 %1, %1, 1;\n"
       "add.u32 part, part, 1;\n"
       "setp.lt.u32 p, part, 2;\n"
       "@p bra SPART_LOOP;\n"
       "add.u32 c, c, 1;\n"
-      "setp.lt.u32 p, c, %8;\n"
+      "setp.lt.u32 p, c, %7;\n"
       "@p bra SCHUNK_LOOP;\n"
       "}\n"
-      : "+r"(rs.stage), "+r"(rs.phase)
+      : "+r"(q)
       : "r"(d_tmem), "l"(a_hi_desc), "l"(a_lo_desc), "l"(w_desc0), "r"(bar_full0), "r"(bar_empty0), "r"(n_chunks),
         "r"(first_acc), "r"(idesc)
       : "memory");
+  return q;
 }
 // Weight producer loop of one layer run (`n` consecutive chunks of `bytes` each, `stride` bytes apart in the packed
-// stream): wait for the ring stage to be free, arm its full barrier with the byte count, start the bulk copy (TMA
-// engine), advance.  Executed by ONE lane.
+// stream), hand-written in PTX for the same reason as issue_chunks: wait for the ring stage to be free, arm its full
+// barrier with the byte count, start the bulk copy (TMA engine), advance.  Executed by ONE lane.
 template <bool kPair>
-__device__ __forceinline__ void produce_chunks(RingState& rs, const uint8_t* src, uint32_t bytes, uint32_t stride,
-                                               uint32_t n, uint32_t bar_full0, uint32_t bar_empty0, uint32_t w_smem0) {
+__device__ __forceinline__ uint32_t produce_chunks(const uint8_t* src, uint32_t bytes, uint32_t stride, uint32_t n,
+                                                   uint32_t q, uint32_t bar_full0, uint32_t bar_empty0,
+                                                   uint32_t w_smem0, uint32_t& wait_cycles) {
   if (kPair) {
-  asm volatile(
+    asm volatile(
         "{\n"
         ".reg .pred p, pw;\n"
-        ".reg .b32 c, fb, eb, t, dst, spins, par, c0, c1;\n"
-        ".reg .b64 src, st64;\n"
+        ".reg .b32 c, stage, par, fb, eb, t, dst, spins, c0, c1;\n"
+        ".reg .b64 src;\n"
         "mov.u32 c, 0;\n"
-        "mov.u64 src, %3;\n"
-        "cvt.u64.u32 st64, %5;\n"
+        "mov.u64 src, %1;\n"
         "PROD_LOOP:\n"
-        "xor.b32 par, %1, 1;\n"
-        "shl.b32 t, %0, 3;\n"
-        "add.u32 fb, %7, t;\n"
-        "add.u32 eb, %8, t;\n"
+        "and.b32 stage, %0, 7;\n"
+        "shr.u32 par, %0, 3;\n"
+        "and.b32 par, par, 1;\n"
+        "xor.b32 par, par, 1;\n"
+        "shl.b32 t, stage, 3;\n"
+        "add.u32 fb, %6, t;\n"
+        "add.u32 eb, %7, t;\n"
         "mov.u32 spins, 0;\n"
         "mov.u32 c0, %clock;\n"
         "PROD_WAIT:\n"
@@ -487,35 +487,35 @@ __device__ __forceinline__ void produce_chunks(RingState& rs, const uint8_t* src
         "mov.u32 c1, %clock;\n"
         "sub.u32 c1, c1, c0;\n"
         "add.u32 %2, %2, c1;\n"
-        "mbarrier.arrive.expect_tx.shared::cta.b64 _, [fb], %4;\n"
-        "mad.lo.u32 dst, %0, 8192, %9;\n"
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [dst], [src], %4, [fb];\n"
-        "add.u64 src, src, st64;\n"
+        "mbarrier.arrive.expect_tx.shared::cta.b64 _, [fb], %3;\n"
+        "mad.lo.u32 dst, stage, 8192, %8;\n"
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [dst], [src], %3, [fb];\n"
+        "cvt.u64.u32 %1, %4;\n"
+        "add.u64 src, src, %1;\n"
         "add.u32 %0, %0, 1;\n"
-        "setp.eq.u32 p, %0, 11;\n"
-        "@p mov.u32 %0, 0;\n"
-        "@p xor.b32 %1, %1, 1;\n"
         "add.u32 c, c, 1;\n"
-        "setp.lt.u32 p, c, %6;\n"
+        "setp.lt.u32 p, c, %5;\n"
         "@p bra PROD_LOOP;\n"
         "}\n"
-        : "+r"(rs.stage), "+r"(rs.phase), "+r"(rs.wait_cycles)
-        : "l"(src), "r"(bytes), "r"(stride), "r"(n), "r"(bar_full0), "r"(bar_empty0), "r"(w_smem0)
+        : "+r"(q), "+l"(src), "+r"(wait_cycles)
+        : "r"(bytes), "r"(stride), "r"(n), "r"(bar_full0), "r"(bar_empty0), "r"(w_smem0)
         : "memory");
   } else {
-  asm volatile(
+    asm volatile(
         "{\n"
         ".reg .pred p, pw;\n"
-        ".reg .b32 c, fb, eb, t, dst, spins, par, c0, c1;\n"
-        ".reg .b64 src, st64;\n"
+        ".reg .b32 c, stage, par, fb, eb, t, dst, spins, c0, c1;\n"
+        ".reg .b64 src;\n"
         "mov.u32 c, 0;\n"
-        "mov.u64 src, %3;\n"
-        "cvt.u64.u32 st64, %5;\n"
+        "mov.u64 src, %1;\n"
         "PROD_LOOP:\n"
-        "xor.b32 par, %1, 1;\n"
-        "shl.b32 t, %0, 3;\n"
-        "add.u32 fb, %7, t;\n"
-        "add.u32 eb, %8, t;\n"
+        "and.b32 stage, %0, 3;\n"
+        "shr.u32 par, %0, 2;\n"
+        "and.b32 par, par, 1;\n"
+        "xor.b32 par, par, 1;\n"
+        "shl.b32 t, stage, 3;\n"
+        "add.u32 fb, %6, t;\n"
+        "add.u32 eb, %7, t;\n"
         "mov.u32 spins, 0;\n"
         "mov.u32 c0, %clock;\n"
         "PROD_WAIT:\n"
@@ -529,39 +529,42 @@ __device__ __forceinline__ void produce_chunks(RingState& rs, const uint8_t* src
         "mov.u32 c1, %clock;\n"
         "sub.u32 c1, c1, c0;\n"
         "add.u32 %2, %2, c1;\n"
-        "mbarrier.arrive.expect_tx.shared::cta.b64 _, [fb], %4;\n"
-        "mad.lo.u32 dst, %0, 16384, %9;\n"
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [dst], [src], %4, [fb];\n"
-        "add.u64 src, src, st64;\n"
+        "mbarrier.arrive.expect_tx.shared::cta.b64 _, [fb], %3;\n"
+        "mad.lo.u32 dst, stage, 16384, %8;\n"
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [dst], [src], %3, [fb];\n"
+        "cvt.u64.u32 %1, %4;\n"
+        "add.u64 src, src, %1;\n"
         "add.u32 %0, %0, 1;\n"
-        "setp.eq.u32 p, %0, 5;\n"
-        "@p mov.u32 %0, 0;\n"
-        "@p xor.b32 %1, %1, 1;\n"
         "add.u32 c, c, 1;\n"
-        "setp.lt.u32 p, c, %6;\n"
+        "setp.lt.u32 p, c, %5;\n"
         "@p bra PROD_LOOP;\n"
         "}\n"
-        : "+r"(rs.stage), "+r"(rs.phase), "+r"(rs.wait_cycles)
-        : "l"(src), "r"(bytes), "r"(stride), "r"(n), "r"(bar_full0), "r"(bar_empty0), "r"(w_smem0)
+        : "+r"(q), "+l"(src), "+r"(wait_cycles)
+        : "r"(bytes), "r"(stride), "r"(n), "r"(bar_full0), "r"(bar_empty0), "r"(w_smem0)
         : "memory");
   }
+  return q;
 }
 // Weight relay loop of the peer CTA (pair mode): for each of `n` chunks wait for the local copy (local_full) and
 // arrive on the leader's w_full of the same stage (`remote_full0` = cluster address of the leader's w_full[0]).
-__device__ __forceinline__ void relay_chunks(RingState& rs, uint32_t n, uint32_t bar_local0, uint32_t remote_full0) {
+__device__ __forceinline__ uint32_t relay_chunks(uint32_t n, uint32_t q, uint32_t bar_local0, uint32_t remote_full0,
+                                                 uint32_t& wait_cycles) {
   asm volatile(
       "{\n"
       ".reg .pred p, pw;\n"
-      ".reg .b32 c, lb, rb, t, spins, c0, c1;\n"
+      ".reg .b32 c, stage, par, lb, rb, t, spins, c0, c1;\n"
       "mov.u32 c, 0;\n"
       "RELAY_LOOP:\n"
-      "shl.b32 t, %0, 3;\n"
-      "add.u32 lb, %4, t;\n"
-      "add.u32 rb, %5, t;\n"
+      "and.b32 stage, %0, 7;\n"
+      "shr.u32 par, %0, 3;\n"
+      "and.b32 par, par, 1;\n"
+      "shl.b32 t, stage, 3;\n"
+      "add.u32 lb, %3, t;\n"
+      "add.u32 rb, %4, t;\n"
       "mov.u32 spins, 0;\n"
       "mov.u32 c0, %clock;\n"
       "RELAY_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 pw, [lb], %1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 pw, [lb], par;\n"
       "@pw bra RELAY_READY;\n"
       "add.u32 spins, spins, 1;\n"
       "setp.gt.u32 p, spins, 4000000;\n"
@@ -570,39 +573,40 @@ __device__ __forceinline__ void relay_chunks(RingState& rs, uint32_t n, uint32_t
       "RELAY_READY:\n"
       "mov.u32 c1, %clock;\n"
       "sub.u32 c1, c1, c0;\n"
-      "add.u32 %2, %2, c1;\n"
+      "add.u32 %1, %1, c1;\n"
       "mbarrier.arrive.shared::cluster.b64 _, [rb];\n"
       "add.u32 %0, %0, 1;\n"
-      "setp.eq.u32 p, %0, 11;\n"
-      "@p mov.u32 %0, 0;\n"
-      "@p xor.b32 %1, %1, 1;\n"
       "add.u32 c, c, 1;\n"
-      "setp.lt.u32 p, c, %3;\n"
+      "setp.lt.u32 p, c, %2;\n"
       "@p bra RELAY_LOOP;\n"
       "}\n"
-      : "+r"(rs.stage), "+r"(rs.phase), "+r"(rs.wait_cycles)
+      : "+r"(q), "+r"(wait_cycles)
       : "r"(n), "r"(bar_local0), "r"(remote_full0)
       : "memory");
+  return q;
 }
-// The bias chunk of a layer: ONE accumulating MMA - A = the all-ones block, B = the second K=16 step of the chunk
-// (its column 31 holds the bias) - then the stage-release commit.
-__device__ __forceinline__ void issue_bias_chunk(RingState& rs, uint32_t d_tmem, uint64_t a_desc, uint64_t w_desc0,
-        uint32_t bar_full0, uint32_t bar_empty0, uint32_t idesc) {
+// The bias chunk of a layer: ONE accumulating MMA - A = the last 16 columns of the encoding k-block (column 63 is the
+// constant 1), B = the second K=16 step of the chunk (its column 31 holds the bias) - then the stage-release commit.
+__device__ __forceinline__ uint32_t issue_bias_chunk(uint32_t d_tmem, uint64_t a_desc, uint64_t w_desc0, uint32_t bar_full0,
+        uint32_t bar_empty0, uint32_t q, uint32_t idesc) {
   asm volatile(
       "{\n"
       ".reg .pred p, pw, e, pt;\n"
-      ".reg .b32 fb, eb, t, spins;\n"
+      ".reg .b32 stage, par, fb, eb, t, spins;\n"
       ".reg .b64 b;\n"
       ".reg .b16 mc;\n"
       "mov.b16 mc, 3;\n"
       "setp.eq.b32 pt, 0, 0;\n"
       "elect.sync _|e, 0xffffffff;\n"
-      "shl.b32 t, %0, 3;\n"
-      "add.u32 fb, %5, t;\n"
-      "add.u32 eb, %6, t;\n"
+      "and.b32 stage, %0, 3;\n"
+      "shr.u32 par, %0, 2;\n"
+      "and.b32 par, par, 1;\n"
+      "shl.b32 t, stage, 3;\n"
+      "add.u32 fb, %4, t;\n"
+      "add.u32 eb, %5, t;\n"
       "mov.u32 spins, 0;\n"
       "BIAS_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 pw, [fb], %1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 pw, [fb], par;\n"
       "@pw bra BIAS_READY;\n"
       "add.u32 spins, spins, 1;\n"
       "setp.gt.u32 p, spins, 4000000;\n"
@@ -610,37 +614,38 @@ __device__ __forceinline__ void issue_bias_chunk(RingState& rs, uint32_t d_tmem,
       "bra BIAS_WAIT;\n"
       "BIAS_READY:\n"
       "tcgen05.fence::after_thread_sync;\n"
-      "mul.wide.u32 b, %0, 1024;\n"
-      "add.s64 b, b, %4;\n"
+      "mul.wide.u32 b, stage, 1024;\n"
+      "add.s64 b, b, %3;\n"
       "add.s64 b, b, 2;\n"
-      "@e tcgen05.mma.cta_group::1.kind::f16 [%2], %3, b, %7, pt;\n"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%1], %2, b, %6, pt;\n"
       "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [eb];\n"
       "add.u32 %0, %0, 1;\n"
-      "setp.eq.u32 p, %0, 5;\n"
-      "@p mov.u32 %0, 0;\n"
-      "@p xor.b32 %1, %1, 1;\n"
       "}\n"
-      : "+r"(rs.stage), "+r"(rs.phase)
+      : "+r"(q)
       : "r"(d_tmem), "l"(a_desc), "l"(w_desc0), "r"(bar_full0), "r"(bar_empty0), "r"(idesc)
       : "memory");
+  return q;
 }
-__device__ __forceinline__ void issue_bias_chunk_pair(RingState& rs, uint32_t d_tmem, uint64_t a_desc, uint64_t w_desc0,
-        uint32_t bar_full0, uint32_t bar_empty0, uint32_t idesc) {
+__device__ __forceinline__ uint32_t issue_bias_chunk_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t w_desc0, uint32_t bar_full0,
+        uint32_t bar_empty0, uint32_t q, uint32_t idesc) {
   asm volatile(
       "{\n"
       ".reg .pred p, pw, e, pt;\n"
-      ".reg .b32 fb, eb, t, spins;\n"
+      ".reg .b32 stage, par, fb, eb, t, spins;\n"
       ".reg .b64 b;\n"
       ".reg .b16 mc;\n"
       "mov.b16 mc, 3;\n"
       "setp.eq.b32 pt, 0, 0;\n"
       "elect.sync _|e, 0xffffffff;\n"
-      "shl.b32 t, %0, 3;\n"
-      "add.u32 fb, %5, t;\n"
-      "add.u32 eb, %6, t;\n"
+      "and.b32 stage, %0, 7;\n"
+      "shr.u32 par, %0, 3;\n"
+      "and.b32 par, par, 1;\n"
+      "shl.b32 t, stage, 3;\n"
+      "add.u32 fb, %4, t;\n"
+      "add.u32 eb, %5, t;\n"
       "mov.u32 spins, 0;\n"
       "BIAS_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 pw, [fb], %1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 pw, [fb], par;\n"
       "@pw bra BIAS_READY;\n"
       "add.u32 spins, spins, 1;\n"
       "setp.gt.u32 p, spins, 4000000;\n"
@@ -648,19 +653,17 @@ __device__ __forceinline__ void issue_bias_chunk_pair(RingState& rs, uint32_t d_
       "bra BIAS_WAIT;\n"
       "BIAS_READY:\n"
       "tcgen05.fence::after_thread_sync;\n"
-      "mul.wide.u32 b, %0, 512;\n"
-      "add.s64 b, b, %4;\n"
+      "mul.wide.u32 b, stage, 512;\n"
+      "add.s64 b, b, %3;\n"
       "add.s64 b, b, 2;\n"
-      "@e tcgen05.mma.cta_group::2.kind::f16 [%2], %3, b, %7, pt;\n"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%1], %2, b, %6, pt;\n"
       "@e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [eb], mc;\n"
       "add.u32 %0, %0, 1;\n"
-      "setp.eq.u32 p, %0, 11;\n"
-      "@p mov.u32 %0, 0;\n"
-      "@p xor.b32 %1, %1, 1;\n"
       "}\n"
-      : "+r"(rs.stage), "+r"(rs.phase)
+      : "+r"(q)
       : "r"(d_tmem), "l"(a_desc), "l"(w_desc0), "r"(bar_full0), "r"(bar_empty0), "r"(idesc)
       : "memory");
+  return q;
 }
 __device__ __forceinline__ void umma_commit_elect(uint32_t bar) {
   asm volatile(
@@ -680,13 +683,6 @@ __device__ __forceinline__ void umma_commit_elect_pair(uint32_t bar) {  // arriv
 __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
   return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
          (2ull << 61);
-}
-// Descriptor of the 4 KiB all-ones block as a 128 x 16 K-major SWIZZLE_NONE operand (8x16-byte core matrices,
-// LBO = 128 B between the two K halves, SBO = 256 B between 8-row groups).  Every element is 1.0, so the exact
-// element order is immaterial.
-__device__ __forceinline__ uint64_t make_desc_ones(uint32_t smem_addr) {
-  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(256 >> 4) << 32) |
-         (1ull << 46);
 }
 // K-major SWIZZLE_64B descriptor of a weight chunk: 64-byte rows, SBO = 512 B (8 rows), layout type 4.
 __device__ __forceinline__ uint64_t make_desc_sw64(uint32_t smem_addr) {
@@ -770,8 +766,6 @@ struct TcParams {
   int n_fine;
   int has_fine;
   unsigned long long* prof;  // optional cycle counters of CTA 0 (vipnerf_debug_set_profile_buffer), else null
-  uint8_t* pe_scratch;       // [grid][2 slots][2 (hi, lo)][16 KiB]: encoding k-block images parked for M5's second pass
-  int n_weight_replicas;     // copies of the weight stream in each packed buffer (kernels.h)
 };
 
 // Work of one tile slot: item i -> (pass, tile).  `unit` indexes the work units of the launch (fused: ray pairs,
@@ -840,8 +834,7 @@ __device__ __forceinline__ void sincos_octave(float t_hi, float t_lo, int k, flo
 // Row `row` of the slot's encoding buffer <- bf16(gamma(point)), 64 columns (63 + the constant 1).
 // Column order of PositionalEncoder.encode (VipNeRF01.py:439-448): x(3), then per octave sin(3), cos(3).
 template <bool kSplit3>
-__device__ __forceinline__ void write_point_encoding(uint8_t* smem, int slot, int row, float x, float y, float z,
-                                                     uint8_t* scratch_hi, uint8_t* scratch_lo) {
+__device__ __forceinline__ void write_point_encoding(uint8_t* smem, int slot, int row, float x, float y, float z) {
   float v[64];
   v[0] = x; v[1] = y; v[2] = z;
   const float p[3] = {x, y, z};
@@ -852,11 +845,9 @@ __device__ __forceinline__ void write_point_encoding(uint8_t* smem, int slot, in
 #pragma unroll
     for (int k = 0; k < kLPts; ++k) sincos_octave<kSplit3>(t_hi, t_lo, k, v[3 + 6 * k + a], v[6 + 6 * k + a]);
   }
-  v[63] = 1.f;  // constant-one column: carries the biases of M0 / M5 through the tensor core (layout.cuh)
-  // The encoding lives in k-block 0 of the slot's A buffer while M0 runs; the same swizzled image is parked in global
-  // memory (L2) and copied back for the second accumulation pass of M5 (the skip connection).
-  const uint32_t hi_base = smem_u32(smem + kOffA + (kSplit3 ? 0 : slot) * kABytes) + row * 128;
-  const uint32_t lo_base = smem_u32(smem + kOffA + kABytes) + row * 128;
+  v[63] = 1.f;  // constant-one column: carries the layer biases through the tensor core (layout.cuh)
+  const uint32_t hi_base = smem_u32(smem + kOffPe + (kSplit3 ? 0 : slot) * kKBlockBytes) + row * 128;
+  const uint32_t lo_base = smem_u32(smem + kOffPe + kKBlockBytes) + row * 128;
 #pragma unroll
   for (int ch = 0; ch < 8; ++ch) {
     uint32_t w[4];
@@ -864,33 +855,12 @@ __device__ __forceinline__ void write_point_encoding(uint8_t* smem, int slot, in
     for (int q = 0; q < 4; ++q) w[q] = pack_bf16(v[8 * ch + 2 * q], v[8 * ch + 2 * q + 1]);
     const uint32_t off = (uint32_t)((ch ^ (row & 7)) << 4);
     st_shared_v4(hi_base + off, w[0], w[1], w[2], w[3]);
-    *reinterpret_cast<uint4*>(scratch_hi + row * 128 + off) = make_uint4(w[0], w[1], w[2], w[3]);
     if (kSplit3) {
       uint32_t r[4];
 #pragma unroll
       for (int q = 0; q < 4; ++q) r[q] = pack_bf16_residual(v[8 * ch + 2 * q], v[8 * ch + 2 * q + 1], w[q]);
       st_shared_v4(lo_base + off, r[0], r[1], r[2], r[3]);
-      *reinterpret_cast<uint4*>(scratch_lo + row * 128 + off) = make_uint4(r[0], r[1], r[2], r[3]);
     }
-  }
-}
-
-// Copies this row of the parked encoding image back into k-block 0 of the slot's A buffer (M5, second pass).
-template <bool kSplit3>
-__device__ __forceinline__ void restore_point_encoding(uint8_t* smem, int slot, int row, const uint8_t* scratch_hi,
-                                                       const uint8_t* scratch_lo) {
-  const uint32_t hi_base = smem_u32(smem + kOffA + (kSplit3 ? 0 : slot) * kABytes) + row * 128;
-  const uint32_t lo_base = smem_u32(smem + kOffA + kABytes) + row * 128;
-  uint4 h[8];
-#pragma unroll
-  for (int ch = 0; ch < 8; ++ch) h[ch] = *reinterpret_cast<const uint4*>(scratch_hi + row * 128 + ch * 16);
-#pragma unroll
-  for (int ch = 0; ch < 8; ++ch) st_shared_v4(hi_base + ch * 16, h[ch].x, h[ch].y, h[ch].z, h[ch].w);
-  if (kSplit3) {
-#pragma unroll
-    for (int ch = 0; ch < 8; ++ch) h[ch] = *reinterpret_cast<const uint4*>(scratch_lo + row * 128 + ch * 16);
-#pragma unroll
-    for (int ch = 0; ch < 8; ++ch) st_shared_v4(lo_base + ch * 16, h[ch].x, h[ch].y, h[ch].z, h[ch].w);
   }
 }
 
@@ -997,9 +967,8 @@ template <bool kSplit3, bool kFused, bool kProf, bool kPair>
 __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr int kSlots = kSplit3 ? 1 : 2;
-  constexpr int kStages = kPair ? 11 : 5;
+  constexpr int kStages = kPair ? 8 : 4;
   constexpr uint32_t kStageBytes = kPair ? 8192 : 16384;
-  static_assert(kStages * kStageBytes <= kRingBytes, "weight ring does not fit");
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t cta_rank = kPair ? cluster_ctarank() : 0;   // 0 = leader of the CTA pair (issues the MMAs)
   const uint32_t bar0 = smem_u32(smem + kOffBar);
@@ -1060,14 +1029,6 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const TcParams p) 
       const uint32_t taddr = tmem_base + (uint32_t)(slot * 256) + ((uint32_t)((warp & 3) * 32) << 16);
       float* vb = reinterpret_cast<float*>(smem + kOffVb) + slot * 256;
       float* pev = reinterpret_cast<float*>(smem + kOffPev) + slot * 64;
-      uint8_t* scratch_hi = p.pe_scratch + ((size_t)blockIdx.x * 2 + slot) * (2 * kPeScratchBytes);
-      uint8_t* scratch_lo = scratch_hi + kPeScratchBytes;
-      // the all-ones block (A operand of the bias chunks); the threads fence it to the async proxy together with
-      // their first encoding
-      {
-        uint32_t* ones = reinterpret_cast<uint32_t*>(smem + kOffOnes);
-        for (int i = row; i < 1024; i += 128) ones[i] = 0x3F803F80u;  // two bf16 1.0 (both groups write the same values)
-      }
       const bool prof_on = kProf && p.prof != nullptr && blockIdx.x == 0 && row == 0;
       long long c_enc = 0, c_vb = 0, c_wait = 0, c_epi = 0, c_view = 0, c_hook = 0;
       const long long c_begin = kProf ? clock64() : 0;
@@ -1093,7 +1054,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const TcParams p) 
         const float px = fadd(p.rp.pts_o[3 * ray + 0], fmul(p.rp.pts_d[3 * ray + 0], zv));
         const float py = fadd(p.rp.pts_o[3 * ray + 1], fmul(p.rp.pts_d[3 * ray + 1], zv));
         const float pz = fadd(p.rp.pts_o[3 * ray + 2], fmul(p.rp.pts_d[3 * ray + 2], zv));
-        write_point_encoding<kSplit3>(smem, slot, row, px, py, pz, scratch_hi, scratch_lo);
+        write_point_encoding<kSplit3>(smem, slot, row, px, py, pz);
         if (kProf) c_enc += clock64() - t0;
       };
       // View-direction columns of views_linears.0 (+ bias) for the (at most two) rays of item `it`, fp32:
@@ -1147,23 +1108,14 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const TcParams p) 
         const int64_t ray = (valid ? pg : ps.n_points - 1) / ps.S;
         const int64_t ray_first = min((tile * kTile) / ps.S, p.n_rays - 1);
         const float* small = reinterpret_cast<const float*>(ps.packed);
+        // the next item's depths exist unless it is the fine tile of the pair whose coarse tile is this item
         const bool has_next = it + 1 < work.n_items;
+        const bool next_ready = has_next && (work.pass_of(it + 1) == 0 || (it + 1 - work.n_first_pass) / 3 < it);
+        bool next_encoded = false;
 
         float sigma_lin = 0.f;
 #pragma unroll 1
         for (int l = 0; l < 9; ++l) {
-          if (l == 5) {
-            // M5 = skip layer, two accumulation passes: the first (K = 256 over h4, the whole A buffer) has been
-            // issued with a_ready(M5); once it retires, k-block 0 is free to take the encoding back for the second
-            // pass (K = 64, includes the bias through the constant-one column)
-            const long long t0 = kProf ? clock64() : 0;
-            mbar_wait(bar(kBarDReady + slot), d_parity);
-            d_parity ^= 1;
-            if (kProf) c_wait += clock64() - t0;
-            restore_point_encoding<kSplit3>(smem, slot, row, scratch_hi, scratch_lo);
-            fence_proxy_async();
-            arrive_a_ready();
-          }
           const long long t0 = kProf ? clock64() : 0;
           mbar_wait(bar(kBarDReady + slot), d_parity);
           d_parity ^= 1;
@@ -1177,7 +1129,12 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const TcParams p) 
           tc_fence_before();
           arrive_a_ready();
           if (kProf) c_epi += clock64() - t1;
-          if (l == 5) view_bias_item(it);  // vb / pev are free (the previous tile's M9 epilogue is long done)
+          if (l == 5) {
+            // M5 has retired: the encoding buffer is free, and so are vb/pev (the previous tile's M9 epilogue
+            // is long done).  Use the time this slot's M6 spends on the tensor pipe.
+            view_bias_item(it);
+            if (next_ready) { encode_item(it + 1); next_encoded = true; }
+          }
         }
         const long long t0 = kProf ? clock64() : 0;
         mbar_wait(bar(kBarDReady + slot), d_parity);
@@ -1232,7 +1189,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const TcParams p) 
           }
         }
         if (has_next) {
-          encode_item(it + 1);  // into k-block 0 of the (now idle) A buffer
+          if (!next_encoded) encode_item(it + 1);
           fence_proxy_async();
           arrive_a_ready();
         }
@@ -1254,9 +1211,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const TcParams p) 
       // peer's on its local_full (relayed to the leader's w_full by the peer's warp 9)
       const int full_base = (kPair && cta_rank == 1) ? kBarLocalFull : kBarWFull;
       const long long c_prod_begin = kProf ? clock64() : 0;
-      RingState ring;
-      const size_t replica_offset =
-          (size_t)(cta_group_idx % p.n_weight_replicas) * ((size_t)kTcBigBytes * (kSplit3 ? 2 : 1));
+      uint32_t q = 0, prod_wait = 0;
       for (int it = 0; it < n_max; ++it) {
         for (int l = 0; l < kNumMatLayers; ++l) {
           for (int s = 0; s < kSlots; ++s) {
@@ -1264,16 +1219,16 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const TcParams p) 
             if (it >= w.n_items) continue;
             const uint32_t chunk_bytes = layer_chunk_bytes(l);
             const uint32_t bytes = kPair ? chunk_bytes / 2 : chunk_bytes;
-            const uint8_t* src = p.pass[w.pass_of(it)].packed + kSmallBytes + replica_offset +
+            const uint8_t* src = p.pass[w.pass_of(it)].packed + kSmallBytes +
                                  (size_t)tc_layer_byte_offset(l) * (kSplit3 ? 2 : 1) + (kPair ? cta_rank * bytes : 0);
             const uint32_t n_chunks = layer_stream_chunks(l) * (kSplit3 ? 2 : 1);
-            produce_chunks<kPair>(ring, src, bytes, chunk_bytes, n_chunks, bar(full_base), bar(kBarWEmpty),
-                                  smem_u32(smem + kOffW));
+            q = produce_chunks<kPair>(src, bytes, chunk_bytes, n_chunks, q, bar(full_base), bar(kBarWEmpty),
+                                      smem_u32(smem + kOffW), prod_wait);
           }
         }
       }
       if (kProf && p.prof != nullptr && blockIdx.x < 2) {
-        p.prof[40 + 4 * blockIdx.x] = ring.wait_cycles;
+        p.prof[40 + 4 * blockIdx.x] = prod_wait;
         p.prof[41 + 4 * blockIdx.x] = (unsigned long long)(clock64() - c_prod_begin);
         p.prof[42 + 4 * blockIdx.x] = 0;
       }
@@ -1287,70 +1242,64 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const TcParams p) 
     WorkList<kFused, kPair> work0(p, cta_group_idx * kSlots + 0, n_slots_total, (int)cta_rank);
     WorkList<kFused, kPair> work1(p, cta_group_idx * kSlots + (kSlots - 1), n_slots_total, (int)cta_rank);
     const int n_max = max(work0.n_items, kSlots > 1 ? work1.n_items : 0);
-    RingState ring;
+    uint32_t q = 0;
     uint32_t a_parity0 = 0, a_parity1 = 0;
-    const uint64_t a_desc0 = make_desc(smem_u32(smem + kOffA));
+    const uint64_t a_desc0 = make_desc(smem_u32(smem + kOffA)), pe_desc0 = make_desc(smem_u32(smem + kOffPe));
     const uint64_t w_desc0 = make_desc_sw64(smem_u32(smem + kOffW));
-    const uint64_t ones_desc = make_desc_ones(smem_u32(smem + kOffOnes));
-    constexpr uint64_t kAUnits = kABytes >> 4;
-    static_assert((kKBlockBytes >> 4) == 1024 && (kStageBytes >> 4) == (kPair ? 512 : 1024), "issue_chunks* assume these");
+    constexpr uint64_t kKBlockUnits = kKBlockBytes >> 4, kAUnits = kABytes >> 4;
+    static_assert(kKBlockUnits == 1024 && (kStageBytes >> 4) == (kPair ? 512 : 1024), "issue_chunks* assume these");
     const uint32_t bar_full0 = bar(kBarWFull), bar_empty0 = bar(kBarWEmpty);
     long long c_wait_a = 0;
+    uint32_t spins = 0;  // failed probes of the weight ring (prof builds report it)
     const long long c_begin = kProf ? clock64() : 0;
-    uint32_t n_issued = 0;
     for (int it = 0; it < n_max; ++it) {
       for (int l = 0; l < kNumMatLayers; ++l) {
 #pragma unroll
         for (int s = 0; s < kSlots; ++s) {
           const WorkList<kFused, kPair>& w = s == 0 ? work0 : work1;
           if (it >= w.n_items) continue;
-          const uint32_t idesc = instr_desc(layer_n(l), kPair ? 256 : 128);
-          const uint32_t d_tmem = tmem_base + (uint32_t)(s * 256);
-          const uint64_t a_hi = a_desc0 + (kSplit3 ? 0 : s) * kAUnits, a_lo = a_desc0 + kAUnits;
-          auto wait_a_ready = [&]() {
+          {
             const long long t0 = kProf ? clock64() : 0;
             mbar_wait(bar(kBarAReady + s), s == 0 ? a_parity0 : a_parity1);
             if (kProf) c_wait_a += clock64() - t0;
-            if (s == 0) a_parity0 ^= 1; else a_parity1 ^= 1;
-            tc_fence_after();
+          }
+          if (s == 0) a_parity0 ^= 1; else a_parity1 ^= 1;
+          tc_fence_after();
+          const uint32_t idesc = instr_desc(layer_n(l), kPair ? 256 : 128);
+          const uint32_t d_tmem = tmem_base + (uint32_t)(s * 256);
+          const uint64_t slot_units = (kSplit3 ? 0 : s);
+          const uint64_t pe_hi = pe_desc0 + slot_units * kKBlockUnits, pe_lo = pe_desc0 + kKBlockUnits;
+          const uint64_t a_hi = a_desc0 + slot_units * kAUnits, a_lo = a_desc0 + kAUnits;
+          auto run = [&](uint64_t hi, uint64_t lo, uint32_t n, uint32_t acc) {
+            if (!kSplit3 && !kPair) q = issue_chunks(d_tmem, hi, w_desc0, bar_full0, bar_empty0, q, n, acc, idesc, spins);
+            else if (!kSplit3) q = issue_chunks_pair(d_tmem, hi, w_desc0, bar_full0, bar_empty0, q, n, acc, idesc, spins);
+            else if (!kPair) q = issue_chunks_split(d_tmem, hi, lo, w_desc0, bar_full0, bar_empty0, q, n, acc, idesc);
+            else q = issue_chunks_split_pair(d_tmem, hi, lo, w_desc0, bar_full0, bar_empty0, q, n, acc, idesc);
           };
-          auto commit_d_ready = [&]() {
-            if (kPair) umma_commit_elect_pair(bar(kBarDReady + s)); else umma_commit_elect(bar(kBarDReady + s));
-          };
-          auto run = [&](uint32_t n, uint32_t acc) {   // n chunks over the slot's A buffer, from k-block 0
-            if (!kSplit3 && !kPair) issue_chunks(ring, d_tmem, a_hi, w_desc0, bar_full0, bar_empty0, n, acc, idesc);
-            else if (!kSplit3) issue_chunks_pair(ring, d_tmem, a_hi, w_desc0, bar_full0, bar_empty0, n, acc, idesc);
-            else if (!kPair) issue_chunks_split(ring, d_tmem, a_hi, a_lo, w_desc0, bar_full0, bar_empty0, n, acc, idesc);
-            else issue_chunks_split_pair(ring, d_tmem, a_hi, a_lo, w_desc0, bar_full0, bar_empty0, n, acc, idesc);
-            n_issued += n;
-          };
-          wait_a_ready();
           if (l == 0) {
-            run(2, 0);                 // the encoding sits in k-block 0
+            run(pe_hi, pe_lo, 2, 0);
           } else if (l == 5) {
-            run(8, 0);                 // pass 1: h4
-            commit_d_ready();
-            wait_a_ready();            // the group has copied the encoding back into k-block 0
-            run(2, 1);                 // pass 2: encoding columns (+ bias via the constant-one column)
+            run(pe_hi, pe_lo, 2, 0);
+            run(a_hi, a_lo, 8, 1);
           } else {
-            run(8, 0);
+            run(a_hi, a_lo, 8, 0);
           }
           if (layer_has_bias_chunk(l)) {
-            // all-ones A block x the bias chunk (second K=16 step of the chunk); BF16X3: hi and lo images
+            // encoding columns 48..63 (k-block offset 96 B = 6 units) x the bias chunk; BF16X3: hi and lo images
+            // (the lo part of the constant-one column is zero, so A_lo contributes nothing and is skipped)
             for (int part = 0; part < (kSplit3 ? 2 : 1); ++part) {
-              if (kPair) issue_bias_chunk_pair(ring, d_tmem, ones_desc, w_desc0, bar_full0, bar_empty0, idesc);
-              else issue_bias_chunk(ring, d_tmem, ones_desc, w_desc0, bar_full0, bar_empty0, idesc);
+              q = kPair ? issue_bias_chunk_pair(d_tmem, pe_hi + 6, w_desc0, bar_full0, bar_empty0, q, idesc)
+                        : issue_bias_chunk(d_tmem, pe_hi + 6, w_desc0, bar_full0, bar_empty0, q, idesc);
             }
-            n_issued += 1;
           }
-          commit_d_ready();
+          if (kPair) umma_commit_elect_pair(bar(kBarDReady + s)); else umma_commit_elect(bar(kBarDReady + s));
         }
       }
     }
     tc_fence_before();
     if (kProf && p.prof != nullptr && blockIdx.x == 0 && lane == 0) {
-      p.prof[32] = c_wait_a; p.prof[33] = ring.wait_cycles; p.prof[34] = (unsigned long long)(clock64() - c_begin);
-      p.prof[35] = n_issued;
+      p.prof[32] = c_wait_a; p.prof[33] = spins; p.prof[34] = (unsigned long long)(clock64() - c_begin);
+      p.prof[35] = q;
     }
   } else {
     // =================================================================== weight relay (warp 9 of the peer CTA)
@@ -1359,8 +1308,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const TcParams p) 
     WorkList<kFused, kPair> work0(p, cta_group_idx * kSlots + 0, n_slots_total, (int)cta_rank);
     WorkList<kFused, kPair> work1(p, cta_group_idx * kSlots + (kSlots - 1), n_slots_total, (int)cta_rank);
     const int n_max = max(work0.n_items, kSlots > 1 ? work1.n_items : 0);
-    RingState ring;
+    uint32_t q = 0;
     const uint32_t remote_full0 = map_to_cta(bar(kBarWFull), 0);
+    uint32_t relay_wait = 0;
     const long long c_relay_begin = kProf ? clock64() : 0;
     for (int it = 0; it < n_max; ++it) {
       for (int l = 0; l < kNumMatLayers; ++l) {
@@ -1368,12 +1318,12 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const TcParams p) 
           const WorkList<kFused, kPair>& w = s == 0 ? work0 : work1;
           if (it >= w.n_items) continue;
           const uint32_t n_chunks = layer_stream_chunks(l) * (kSplit3 ? 2 : 1);
-          if (lane == 0) relay_chunks(ring, n_chunks, bar(kBarLocalFull), remote_full0);
+          if (lane == 0) q = relay_chunks(n_chunks, q, bar(kBarLocalFull), remote_full0, relay_wait);
         }
       }
     }
     if (kProf && p.prof != nullptr && blockIdx.x == 1 && lane == 0) {
-      p.prof[48] = ring.wait_cycles;
+      p.prof[48] = relay_wait;
       p.prof[49] = (unsigned long long)(clock64() - c_relay_begin);
     }
   }
@@ -1463,15 +1413,9 @@ void set_tc_profile_buffer(void* dev_ptr) {
   g_prof_buffer = static_cast<unsigned long long*>(dev_ptr);
 }
 
-size_t tc_scratch_bytes() {
-  int sms = 0;
-  if (device_sm_count(&sms) != cudaSuccess || sms <= 0) sms = 256;
-  return (size_t)sms * 2 * 2 * kPeScratchBytes;   // [CTA][slot][hi, lo]
-}
-
 cudaError_t launch_mlp_tc(int precision, const RayPtrs& rp, const RenderFlags& fl, int64_t n_rays, int S,
                           const float* z, const void* packed, float* sigma, float* rgb, float* vis,
-                          void* pe_scratch, cudaStream_t s) {
+                          cudaStream_t s) {
   TcParams p{};
   p.rp = rp;
   p.fl = fl;
@@ -1487,8 +1431,6 @@ cudaError_t launch_mlp_tc(int precision, const RayPtrs& rp, const RenderFlags& f
   p.pass[1] = p.pass[0];
   p.n_units = (p.pass[0].n_points + kTile - 1) / kTile;
   p.prof = g_prof_buffer;
-  p.pe_scratch = static_cast<uint8_t*>(pe_scratch);
-  p.n_weight_replicas = tc_weight_replicas();
   if (p.n_units == 0) return cudaSuccess;
   if (precision == VIPNERF_PRECISION_BF16X3) return launch<true, false>(p, p.n_units, s);
   return launch<false, false>(p, p.n_units, s);
@@ -1520,8 +1462,6 @@ cudaError_t launch_render_fused_tc(int precision, const FusedArgs& a, cudaStream
   if (!p.has_fine) p.pass[1] = p.pass[0];
   p.n_units = (a.n_rays + 1) / 2;
   p.prof = g_prof_buffer;
-  p.pe_scratch = static_cast<uint8_t*>(a.pe_scratch);
-  p.n_weight_replicas = tc_weight_replicas();
   if (precision == VIPNERF_PRECISION_BF16X3) return launch<true, true>(p, p.n_units, s);
   return launch<false, true>(p, p.n_units, s);
 }

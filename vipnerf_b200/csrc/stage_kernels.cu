@@ -1,8 +1,6 @@
 // Weight packing, coarse sample placement and the stand-alone compositing / re-sampling kernel.
 #include <cuda_bf16.h>
 
-#include <cstdlib>
-
 #include "kernels.h"
 #include "layout.cuh"
 
@@ -63,12 +61,12 @@ __global__ void k_pack_tc(ParamPtrs pp, uint8_t* __restrict__ big) {
   const int chunk = e / (N * kChunkK), r = e % (N * kChunkK);
   const int n = r / kChunkK, k_local = r % kChunkK;
   float w;
-  if (chunk == layer_chunks(l)) {                         // the layer's bias chunk: only column 31 is non-zero
+  if (chunk == layer_chunks(l)) {                         // the layer's bias chunk: column 31 <-> encoding column 63
     w = k_local == kChunkK - 1 ? pp.p[bias_param(l)][n] : 0.f;
   } else {
-    const int sc = tc_source_col(l, chunk * kChunkK + k_local);
-    w = sc == -2 ? pp.p[bias_param(l)][n]
-                 : (sc < 0 ? 0.f : pp.p[source_param(l)][(int64_t)n * source_in_features(l) + sc]);
+    const int k = chunk * kChunkK + k_local;
+    const bool bias_col = (l == 0 || l == 5) && k == 63;  // the encoding block's constant-one column
+    w = bias_col ? pp.p[bias_param(l)][n] : source_weight(pp, l, n, k);
   }
   const uint32_t byte = n * 64 + ((((k_local >> 3) ^ ((n >> 1) & 3))) << 4) + (k_local & 7) * 2;
   const size_t chunk_bytes = (size_t)layer_chunk_bytes(l);
@@ -83,15 +81,6 @@ __global__ void k_pack_tc(ParamPtrs pp, uint8_t* __restrict__ big) {
   }
 }
 
-int tc_weight_replicas() {
-  static const int n = []() {
-    const char* e = getenv("VIPNERF_TC_WEIGHT_REPLICAS");
-    int v = e ? atoi(e) : 8;
-    return v < 1 ? 1 : (v > 32 ? 32 : v);
-  }();
-  return n;
-}
-
 cudaError_t launch_pack_weights(int precision, const float* const params_dev[24], void* packed, cudaStream_t s) {
   ParamPtrs pp;
   for (int i = 0; i < 24; ++i) pp.p[i] = params_dev[i];
@@ -102,11 +91,8 @@ cudaError_t launch_pack_weights(int precision, const float* const params_dev[24]
     k_pack_fp32<<<(kFp32BigFloats + 255) / 256, 256, 0, s>>>(pp, reinterpret_cast<float*>(big));
   } else {
     const int n = kTcBigBytes / 2;
-    const size_t copy_bytes = (size_t)kTcBigBytes * (precision == VIPNERF_PRECISION_BF16X3 ? 2 : 1);
-    for (int r = 0; r < tc_weight_replicas(); ++r) {
-      if (precision == VIPNERF_PRECISION_BF16X3) k_pack_tc<true><<<(n + 255) / 256, 256, 0, s>>>(pp, big + r * copy_bytes);
-      else k_pack_tc<false><<<(n + 255) / 256, 256, 0, s>>>(pp, big + r * copy_bytes);
-    }
+    if (precision == VIPNERF_PRECISION_BF16X3) k_pack_tc<true><<<(n + 255) / 256, 256, 0, s>>>(pp, big);
+    else k_pack_tc<false><<<(n + 255) / 256, 256, 0, s>>>(pp, big);
   }
   return cudaGetLastError();
 }

@@ -206,11 +206,9 @@ def mlp_forward(batch: Dict[str, torch.Tensor], z_vals: torch.Tensor, packed: to
     keys = ['raw_sigma', 'raw_rgb', 'raw_visibility'] + (['raw_visibility2'] if n_sec_views else [])
     t = _alloc_pass(out, keys, R, S, n_sec_views, device)
     with torch.cuda.device(device):
-        ws_bytes = lib.vipnerf_workspace_bytes(ctypes.byref(cfg), R)
-        ws = _workspace(ws_bytes, device)
         _lib.check(lib.vipnerf_mlp_forward(ctypes.byref(cfg), ctypes.byref(rays), R, S, z_vals.data_ptr(),
-                                           packed.data_ptr(), ctypes.byref(out), ws.data_ptr(), ws_bytes,
-                                           _stream(device)), 'vipnerf_mlp_forward')
+                                           packed.data_ptr(), ctypes.byref(out), None, 0, _stream(device)),
+                   'vipnerf_mlp_forward')
     res = {'sigma': t['raw_sigma'], 'rgb': t['raw_rgb'], 'visibility': t['raw_visibility']}
     if n_sec_views:
         res['visibility2'] = t['raw_visibility2']
