@@ -23,6 +23,7 @@
 // BF16X3 mode (parity mode): every operand is split x = hi + lo (both bf16) and each product is evaluated as
 // hi*hi + lo*hi + hi*lo in the fp32 accumulator (3 MMAs).  Slot 1's buffers hold the lo parts, so only one
 // tile is in flight.
+#include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
@@ -52,7 +53,7 @@ constexpr uint32_t kOffPev = kOffVb + 2048;   // [2 slots][2 rays][32]  fp32: vi
 constexpr uint32_t kSmemBytes = kOffPev + 512;
 static_assert(kSmemBytes <= 232448, "exceeds the 227 KiB per-CTA shared memory limit");
 
-enum { kBarWFull = 0, kBarWEmpty = 8, kBarAReady = 16, kBarDReady = 18, kBarLocalFull = 20 };
+enum { kBarWFull = 0, kBarWEmpty = 8, kBarAReady = 16, kBarDReady = 18 };
 
 // tcgen05 instruction descriptor: D=F32, A=B=BF16, both K-major, M=128, N=n (cute::UMMA::InstrDescriptor bits:
 // c_format[4,6)=1, a_format[7,10)=1, b_format[10,13)=1, n_dim[17,23)=N>>3, m_dim[24,29)=M>>4)
@@ -453,135 +454,104 @@ __device__ __forceinline__ uint32_t issue_chunks_split_pair(uint32_t d_tmem, uin
 }
 // Weight producer loop of one layer run (`n` consecutive chunks of `bytes` each, `stride` bytes apart in the packed
 // stream), hand-written in PTX for the same reason as issue_chunks: wait for the ring stage to be free, arm its full
-// barrier with the byte count, start the bulk copy (TMA engine), advance.  Executed by ONE lane.
-template <bool kPair>
+// barrier with the byte count, start the bulk copy (TMA engine), advance.  Executed by ONE lane.  Single-CTA variant.
 __device__ __forceinline__ uint32_t produce_chunks(const uint8_t* src, uint32_t bytes, uint32_t stride, uint32_t n,
                                                    uint32_t q, uint32_t bar_full0, uint32_t bar_empty0,
                                                    uint32_t w_smem0, uint32_t& wait_cycles) {
-  if (kPair) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p, pw;\n"
-        ".reg .b32 c, stage, par, fb, eb, t, dst, spins, c0, c1;\n"
-        ".reg .b64 src;\n"
-        "mov.u32 c, 0;\n"
-        "mov.u64 src, %1;\n"
-        "PROD_LOOP:\n"
-        "and.b32 stage, %0, 7;\n"
-        "shr.u32 par, %0, 3;\n"
-        "and.b32 par, par, 1;\n"
-        "xor.b32 par, par, 1;\n"
-        "shl.b32 t, stage, 3;\n"
-        "add.u32 fb, %6, t;\n"
-        "add.u32 eb, %7, t;\n"
-        "mov.u32 spins, 0;\n"
-        "mov.u32 c0, %clock;\n"
-        "PROD_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 pw, [eb], par;\n"
-        "@pw bra PROD_READY;\n"
-        "add.u32 spins, spins, 1;\n"
-        "setp.gt.u32 p, spins, 4000000;\n"
-        "@p trap;\n"
-        "bra PROD_WAIT;\n"
-        "PROD_READY:\n"
-        "mov.u32 c1, %clock;\n"
-        "sub.u32 c1, c1, c0;\n"
-        "add.u32 %2, %2, c1;\n"
-        "mbarrier.arrive.expect_tx.shared::cta.b64 _, [fb], %3;\n"
-        "mad.lo.u32 dst, stage, 8192, %8;\n"
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [dst], [src], %3, [fb];\n"
-        "cvt.u64.u32 %1, %4;\n"
-        "add.u64 src, src, %1;\n"
-        "add.u32 %0, %0, 1;\n"
-        "add.u32 c, c, 1;\n"
-        "setp.lt.u32 p, c, %5;\n"
-        "@p bra PROD_LOOP;\n"
-        "}\n"
-        : "+r"(q), "+l"(src), "+r"(wait_cycles)
-        : "r"(bytes), "r"(stride), "r"(n), "r"(bar_full0), "r"(bar_empty0), "r"(w_smem0)
-        : "memory");
-  } else {
-    asm volatile(
-        "{\n"
-        ".reg .pred p, pw;\n"
-        ".reg .b32 c, stage, par, fb, eb, t, dst, spins, c0, c1;\n"
-        ".reg .b64 src;\n"
-        "mov.u32 c, 0;\n"
-        "mov.u64 src, %1;\n"
-        "PROD_LOOP:\n"
-        "and.b32 stage, %0, 3;\n"
-        "shr.u32 par, %0, 2;\n"
-        "and.b32 par, par, 1;\n"
-        "xor.b32 par, par, 1;\n"
-        "shl.b32 t, stage, 3;\n"
-        "add.u32 fb, %6, t;\n"
-        "add.u32 eb, %7, t;\n"
-        "mov.u32 spins, 0;\n"
-        "mov.u32 c0, %clock;\n"
-        "PROD_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 pw, [eb], par;\n"
-        "@pw bra PROD_READY;\n"
-        "add.u32 spins, spins, 1;\n"
-        "setp.gt.u32 p, spins, 4000000;\n"
-        "@p trap;\n"
-        "bra PROD_WAIT;\n"
-        "PROD_READY:\n"
-        "mov.u32 c1, %clock;\n"
-        "sub.u32 c1, c1, c0;\n"
-        "add.u32 %2, %2, c1;\n"
-        "mbarrier.arrive.expect_tx.shared::cta.b64 _, [fb], %3;\n"
-        "mad.lo.u32 dst, stage, 16384, %8;\n"
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [dst], [src], %3, [fb];\n"
-        "cvt.u64.u32 %1, %4;\n"
-        "add.u64 src, src, %1;\n"
-        "add.u32 %0, %0, 1;\n"
-        "add.u32 c, c, 1;\n"
-        "setp.lt.u32 p, c, %5;\n"
-        "@p bra PROD_LOOP;\n"
-        "}\n"
-        : "+r"(q), "+l"(src), "+r"(wait_cycles)
-        : "r"(bytes), "r"(stride), "r"(n), "r"(bar_full0), "r"(bar_empty0), "r"(w_smem0)
-        : "memory");
-  }
-  return q;
-}
-// Weight relay loop of the peer CTA (pair mode): for each of `n` chunks wait for the local copy (local_full) and
-// arrive on the leader's w_full of the same stage (`remote_full0` = cluster address of the leader's w_full[0]).
-__device__ __forceinline__ uint32_t relay_chunks(uint32_t n, uint32_t q, uint32_t bar_local0, uint32_t remote_full0,
-                                                 uint32_t& wait_cycles) {
   asm volatile(
       "{\n"
       ".reg .pred p, pw;\n"
-      ".reg .b32 c, stage, par, lb, rb, t, spins, c0, c1;\n"
+      ".reg .b32 c, stage, par, fb, eb, t, dst, spins, c0, c1;\n"
+      ".reg .b64 src;\n"
       "mov.u32 c, 0;\n"
-      "RELAY_LOOP:\n"
-      "and.b32 stage, %0, 7;\n"
-      "shr.u32 par, %0, 3;\n"
+      "mov.u64 src, %1;\n"
+      "PROD_LOOP:\n"
+      "and.b32 stage, %0, 3;\n"
+      "shr.u32 par, %0, 2;\n"
       "and.b32 par, par, 1;\n"
+      "xor.b32 par, par, 1;\n"
       "shl.b32 t, stage, 3;\n"
-      "add.u32 lb, %3, t;\n"
-      "add.u32 rb, %4, t;\n"
+      "add.u32 fb, %6, t;\n"
+      "add.u32 eb, %7, t;\n"
       "mov.u32 spins, 0;\n"
       "mov.u32 c0, %clock;\n"
-      "RELAY_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 pw, [lb], par;\n"
-      "@pw bra RELAY_READY;\n"
+      "PROD_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 pw, [eb], par;\n"
+      "@pw bra PROD_READY;\n"
       "add.u32 spins, spins, 1;\n"
       "setp.gt.u32 p, spins, 4000000;\n"
       "@p trap;\n"
-      "bra RELAY_WAIT;\n"
-      "RELAY_READY:\n"
+      "bra PROD_WAIT;\n"
+      "PROD_READY:\n"
+      "mov.u32 c1, %clock;\n"
+      "sub.u32 c1, c1, c0;\n"
+      "add.u32 %2, %2, c1;\n"
+      "mbarrier.arrive.expect_tx.shared::cta.b64 _, [fb], %3;\n"
+      "mad.lo.u32 dst, stage, 16384, %8;\n"
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [dst], [src], %3, [fb];\n"
+      "cvt.u64.u32 %1, %4;\n"
+      "add.u64 src, src, %1;\n"
+      "add.u32 %0, %0, 1;\n"
+      "add.u32 c, c, 1;\n"
+      "setp.lt.u32 p, c, %5;\n"
+      "@p bra PROD_LOOP;\n"
+      "}\n"
+      : "+r"(q), "+l"(src), "+r"(wait_cycles)
+      : "r"(bytes), "r"(stride), "r"(n), "r"(bar_full0), "r"(bar_empty0), "r"(w_smem0)
+      : "memory");
+  return q;
+}
+// CTA-pair variant.  The weight stream is addressed through a 2-D tensor map (rows of 64 bytes; the box is this CTA's
+// half of a chunk's rows) so that the copy can be a cp.async.bulk.tensor with .cta_group::2, whose complete_tx may
+// signal an mbarrier of the PEER CTA: both CTAs' copies complete directly on the LEADER's w_full (`bar_full_cl0` =
+// its shared::cluster address), which the leader arms with the byte count of both halves (`expect_bytes`; 0 in the
+// peer CTA, which only copies).  No relay hop between the peer's copy and the MMA-issuing lane.
+__device__ __forceinline__ uint32_t produce_chunks_pair(const void* tmap, uint32_t row0, uint32_t row_stride, uint32_t n,
+                                                        uint32_t q, uint32_t expect_bytes, uint32_t bar_full0,
+                                                        uint32_t bar_full_cl0, uint32_t bar_empty0, uint32_t w_smem0,
+                                                        uint32_t& wait_cycles) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p, pw, lead;\n"
+      ".reg .b32 c, stage, par, fb, fbc, eb, t, dst, spins, c0, c1, row, zero;\n"
+      "mov.u32 c, 0;\n"
+      "mov.u32 zero, 0;\n"
+      "mov.u32 row, %3;\n"
+      "setp.ne.u32 lead, %6, 0;\n"
+      "PRODP_LOOP:\n"
+      "and.b32 stage, %0, 7;\n"
+      "shr.u32 par, %0, 3;\n"
+      "and.b32 par, par, 1;\n"
+      "xor.b32 par, par, 1;\n"
+      "shl.b32 t, stage, 3;\n"
+      "add.u32 fb, %7, t;\n"
+      "add.u32 fbc, %8, t;\n"
+      "add.u32 eb, %9, t;\n"
+      "mov.u32 spins, 0;\n"
+      "mov.u32 c0, %clock;\n"
+      "PRODP_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 pw, [eb], par;\n"
+      "@pw bra PRODP_READY;\n"
+      "add.u32 spins, spins, 1;\n"
+      "setp.gt.u32 p, spins, 4000000;\n"
+      "@p trap;\n"
+      "bra PRODP_WAIT;\n"
+      "PRODP_READY:\n"
       "mov.u32 c1, %clock;\n"
       "sub.u32 c1, c1, c0;\n"
       "add.u32 %1, %1, c1;\n"
-      "mbarrier.arrive.shared::cluster.b64 _, [rb];\n"
+      "@lead mbarrier.arrive.expect_tx.shared::cta.b64 _, [fb], %6;\n"
+      "mad.lo.u32 dst, stage, 8192, %10;\n"
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [dst], [%2, {zero, row}], [fbc];\n"
+      "add.u32 row, row, %4;\n"
       "add.u32 %0, %0, 1;\n"
       "add.u32 c, c, 1;\n"
-      "setp.lt.u32 p, c, %2;\n"
-      "@p bra RELAY_LOOP;\n"
+      "setp.lt.u32 p, c, %5;\n"
+      "@p bra PRODP_LOOP;\n"
       "}\n"
       : "+r"(q), "+r"(wait_cycles)
-      : "r"(n), "r"(bar_local0), "r"(remote_full0)
+      : "l"(tmap), "r"(row0), "r"(row_stride), "r"(n), "r"(expect_bytes), "r"(bar_full0), "r"(bar_full_cl0),
+        "r"(bar_empty0), "r"(w_smem0)
       : "memory");
   return q;
 }
@@ -766,6 +736,10 @@ struct TcParams {
   int n_fine;
   int has_fine;
   unsigned long long* prof;  // optional cycle counters of CTA 0 (vipnerf_debug_set_profile_buffer), else null
+  // CTA-pair kernels: tensor maps over each pass's chunk-image stream seen as [rows][32] bf16 (64-byte rows, no
+  // swizzle - the images are stored pre-swizzled); [pass][0] box = 128 rows (half of a 256-row chunk), [pass][1] box =
+  // 64 rows (half of an M9 chunk)
+  alignas(64) CUtensorMap wmap[2][2];
 };
 
 // Work of one tile slot: item i -> (pass, tile).  `unit` indexes the work units of the launch (fused: ray pairs,
@@ -964,7 +938,7 @@ __device__ __forceinline__ void view_epilogue(uint32_t taddr, const float* vb_ro
 
 // ------------------------------------------------------------------------------------------ the kernel
 template <bool kSplit3, bool kFused, bool kProf, bool kPair>
-__global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const TcParams p) {
+__global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const __grid_constant__ TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr int kSlots = kSplit3 ? 1 : 2;
   constexpr int kStages = kPair ? 8 : 4;
@@ -980,12 +954,11 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const TcParams p) 
       printf("vipnerf: dynamic shared memory base is not 1024-byte aligned\n");
       __trap();
     }
-    // w_full: the local TMA's arrive.expect_tx (+ the peer's relayed arrival in pair mode); a_ready: one arrival per
-    // epilogue warp of every CTA feeding the MMA
+    // w_full: one arrival (the producer's arrive.expect_tx; in pair mode it covers both CTAs' copies, which complete
+    // on the leader's barrier); a_ready: one arrival per epilogue warp of every CTA feeding the MMA
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(bar(kBarWFull + s), kPair ? 2 : 1);
+      mbar_init(bar(kBarWFull + s), 1);
       mbar_init(bar(kBarWEmpty + s), 1);
-      mbar_init(bar(kBarLocalFull + s), 1);
     }
     for (int s = 0; s < 2; ++s) { mbar_init(bar(kBarAReady + s), kPair ? 8 : 4); mbar_init(bar(kBarDReady + s), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -1207,9 +1180,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const TcParams p) 
       WorkList<kFused, kPair> work0(p, cta_group_idx * kSlots + 0, n_slots_total, (int)cta_rank);
       WorkList<kFused, kPair> work1(p, cta_group_idx * kSlots + (kSlots - 1), n_slots_total, (int)cta_rank);
       const int n_max = max(work0.n_items, kSlots > 1 ? work1.n_items : 0);
-      // pair mode: this CTA streams its half of every chunk's rows; the leader's copies complete on w_full, the
-      // peer's on its local_full (relayed to the leader's w_full by the peer's warp 9)
-      const int full_base = (kPair && cta_rank == 1) ? kBarLocalFull : kBarWFull;
+      // pair mode: this CTA streams its half of every chunk's rows; both CTAs' copies complete on the leader's w_full
+      const uint32_t full_cluster0 = kPair ? map_to_cta(bar(kBarWFull), 0) : 0;
       const long long c_prod_begin = kProf ? clock64() : 0;
       uint32_t q = 0, prod_wait = 0;
       for (int it = 0; it < n_max; ++it) {
@@ -1222,8 +1194,17 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const TcParams p) 
             const uint8_t* src = p.pass[w.pass_of(it)].packed + kSmallBytes +
                                  (size_t)tc_layer_byte_offset(l) * (kSplit3 ? 2 : 1) + (kPair ? cta_rank * bytes : 0);
             const uint32_t n_chunks = layer_stream_chunks(l) * (kSplit3 ? 2 : 1);
-            q = produce_chunks<kPair>(src, bytes, chunk_bytes, n_chunks, q, bar(full_base), bar(kBarWEmpty),
+            if (kPair) {
+              // rows of 64 bytes: the chunk images of a layer are consecutive, this CTA takes rows [rank*n/2, +n/2)
+              const uint32_t rows = (uint32_t)layer_n(l);
+              const uint32_t row0 = (uint32_t)(tc_layer_byte_offset(l) * (kSplit3 ? 2 : 1)) / 64 + cta_rank * (rows / 2);
+              q = produce_chunks_pair(&p.wmap[w.pass_of(it)][l == 9 ? 1 : 0], row0, rows, n_chunks, q,
+                                      cta_rank == 0 ? chunk_bytes : 0, bar(kBarWFull), full_cluster0, bar(kBarWEmpty),
                                       smem_u32(smem + kOffW), prod_wait);
+            } else {
+              q = produce_chunks(src, bytes, chunk_bytes, n_chunks, q, bar(kBarWFull), bar(kBarWEmpty),
+                                 smem_u32(smem + kOffW), prod_wait);
+            }
           }
         }
       }
@@ -1301,31 +1282,6 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const TcParams p) 
       p.prof[32] = c_wait_a; p.prof[33] = spins; p.prof[34] = (unsigned long long)(clock64() - c_begin);
       p.prof[35] = q;
     }
-  } else {
-    // =================================================================== weight relay (warp 9 of the peer CTA)
-    // The peer's weight copies complete on its own local_full barriers; forward every completion to the leader's
-    // w_full (which counts the leader's own copy plus this arrival) so that the leader's MMAs see both halves.
-    WorkList<kFused, kPair> work0(p, cta_group_idx * kSlots + 0, n_slots_total, (int)cta_rank);
-    WorkList<kFused, kPair> work1(p, cta_group_idx * kSlots + (kSlots - 1), n_slots_total, (int)cta_rank);
-    const int n_max = max(work0.n_items, kSlots > 1 ? work1.n_items : 0);
-    uint32_t q = 0;
-    const uint32_t remote_full0 = map_to_cta(bar(kBarWFull), 0);
-    uint32_t relay_wait = 0;
-    const long long c_relay_begin = kProf ? clock64() : 0;
-    for (int it = 0; it < n_max; ++it) {
-      for (int l = 0; l < kNumMatLayers; ++l) {
-        for (int s = 0; s < kSlots; ++s) {
-          const WorkList<kFused, kPair>& w = s == 0 ? work0 : work1;
-          if (it >= w.n_items) continue;
-          const uint32_t n_chunks = layer_stream_chunks(l) * (kSplit3 ? 2 : 1);
-          if (lane == 0) q = relay_chunks(n_chunks, q, bar(kBarLocalFull), remote_full0, relay_wait);
-        }
-      }
-    }
-    if (kProf && p.prof != nullptr && blockIdx.x == 1 && lane == 0) {
-      p.prof[48] = relay_wait;
-      p.prof[49] = (unsigned long long)(clock64() - c_relay_begin);
-    }
   }
   __syncthreads();
   if (kPair) cluster_sync_all();   // the peer may still be reading this CTA's shared memory / signalling its barriers
@@ -1355,6 +1311,40 @@ cudaError_t device_sm_count(int* out) {
   if (e != cudaSuccess) return e;
   if (dev < 64) g_sm_count[dev] = n;
   *out = n;
+  return cudaSuccess;
+}
+
+// Tensor maps over a packed buffer's chunk-image stream (TcParams::wmap).  cuTensorMapEncodeTiled is a host-only
+// encoder (no device work); it is fetched from the driver through the runtime so that the library does not link
+// libcuda.
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode_tiled() {
+  static EncodeTiledFn fn = []() -> EncodeTiledFn {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      return nullptr;
+    return reinterpret_cast<EncodeTiledFn>(ptr);
+  }();
+  return fn;
+}
+cudaError_t encode_weight_maps(const uint8_t* packed, bool split3, CUtensorMap (&maps)[2]) {
+  EncodeTiledFn encode = get_encode_tiled();
+  if (encode == nullptr) return cudaErrorNotSupported;
+  const cuuint64_t dims[2] = {32, (cuuint64_t)kTcBigBytes * (split3 ? 2 : 1) / 64};
+  const cuuint64_t strides[1] = {64};
+  const cuuint32_t elem_strides[2] = {1, 1};
+  for (int i = 0; i < 2; ++i) {
+    const cuuint32_t box[2] = {32, i == 0 ? 128u : 64u};
+    const CUresult r = encode(&maps[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                              const_cast<uint8_t*>(packed) + kSmallBytes, dims, strides, box, elem_strides,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
+  }
   return cudaSuccess;
 }
 
@@ -1396,8 +1386,14 @@ cudaError_t launch_variant(const TcParams& p, int64_t n_units, cudaStream_t s) {
 }
 
 template <bool kSplit3, bool kFused>
-cudaError_t launch(const TcParams& p, int64_t n_units, cudaStream_t s) {
+cudaError_t launch(TcParams& p, int64_t n_units, cudaStream_t s) {
   const bool pair = g_use_cta_pairs;
+  if (pair) {
+    for (int pi = 0; pi < 2; ++pi) {
+      const cudaError_t e = encode_weight_maps(p.pass[pi].packed, kSplit3, p.wmap[pi]);
+      if (e != cudaSuccess) return e;
+    }
+  }
   if (p.prof != nullptr) {
     return pair ? launch_variant<kSplit3, kFused, true, true>(p, n_units, s)
                 : launch_variant<kSplit3, kFused, true, false>(p, n_units, s);
