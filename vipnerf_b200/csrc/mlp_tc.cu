@@ -9,6 +9,8 @@
 //   warps 4-7  epilogue group 1  (owns tile slot 1: TMEM columns [256,512), A buffer 1, encoding buffer 1)
 //   warp  8    weight producer   (one lane: cp.async.bulk 16 KiB weight chunk images -> 4-stage smem ring)
 //   warp  9    MMA issuer        (one lane: tcgen05.mma M=128 N=256 K=16, bf16 x bf16 -> fp32 in TMEM)
+//   warps 10-11 ray warps         (fused kernel: alpha compositing + hierarchical re-sampling of the rays a slot's
+//                                  tiles complete, asynchronously to the slot's next tiles)
 // A "tile" is 128 consecutive sample points (rows).  A row's activations live in shared memory as bf16 in the
 // canonical K-major SWIZZLE_128B layout (four 16 KiB k-blocks of 128 rows x 64 columns); the accumulator of a
 // layer lives in the slot's 256 TMEM columns.  Per layer: the MMA warp streams the layer's weight chunks
@@ -39,7 +41,7 @@ namespace {
 
 constexpr int kTile = 128;
 constexpr int kMaxStages = 8;  // weight-ring stages: 4 x 16 KiB (one CTA per tile pair) or 8 x 8 KiB (CTA pairs)
-constexpr int kNumThreads = 320;
+constexpr int kNumThreads = 384;   // 12 warps: a 10-warp CTA has the same per-thread register budget (3 warps per sub-partition)
 constexpr uint32_t kABytes = 65536;
 constexpr uint32_t kKBlockBytes = 16384;
 constexpr uint32_t kOffA = 0;                 // 2 x 64 KiB
@@ -47,13 +49,14 @@ constexpr uint32_t kOffPe = 131072;           // 2 x 16 KiB
 constexpr uint32_t kOffW = 163840;            // 4 x 16 KiB
 constexpr uint32_t kOffTail = 229376;
 constexpr uint32_t kOffBar = kOffTail;        // 28 mbarriers
+constexpr uint32_t kOffRayDone = kOffTail + 192; // [2 slots] u32: per-ray events the slot's ray warp has completed
 constexpr uint32_t kOffTmemPtr = kOffTail + 240;
 constexpr uint32_t kOffVb = kOffTail + 256;   // [2 slots][2 rays][128] fp32: view-direction part of M9 + bias
 constexpr uint32_t kOffPev = kOffVb + 2048;   // [2 slots][2 rays][32]  fp32: view-direction encodings
 constexpr uint32_t kSmemBytes = kOffPev + 512;
 static_assert(kSmemBytes <= 232448, "exceeds the 227 KiB per-CTA shared memory limit");
 
-enum { kBarWFull = 0, kBarWEmpty = 8, kBarAReady = 16, kBarDReady = 18 };
+enum { kBarWFull = 0, kBarWEmpty = 8, kBarAReady = 16, kBarDReady = 18, kBarRayFull = 20 };
 
 // tcgen05 instruction descriptor: D=F32, A=B=BF16, both K-major, M=128, N=n (cute::UMMA::InstrDescriptor bits:
 // c_format[4,6)=1, a_format[7,10)=1, b_format[10,13)=1, n_dim[17,23)=N>>3, m_dim[24,29)=M>>4)
@@ -61,6 +64,7 @@ constexpr uint32_t instr_desc(uint32_t n, uint32_t m = 128) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
 }
 
+constexpr int kRayScratchFloats = 512;   // >= resample_scratch_floats(64, 128) = 384
 constexpr long long kTimeoutCycles = 4000000000ll;  // ~2 s: a protocol bug traps instead of hanging the GPU
 
 // ------------------------------------------------------------------------------------------ PTX wrappers
@@ -252,27 +256,33 @@ __device__ __forceinline__ uint32_t issue_chunks(uint32_t d_tmem, uint64_t a_des
 }
 __device__ __forceinline__ uint32_t issue_chunks_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t w_desc0, uint32_t bar_full0,
         uint32_t bar_empty0, uint32_t q, uint32_t n_chunks, uint32_t first_acc, uint32_t idesc,
-        uint32_t& spin_total) {
+        uint32_t& spin_total, uint32_t skip_wait = 0, uint32_t ts_base = 0,
+        uint32_t* d2_total = nullptr) {
+  uint32_t d2 = 0;
   asm volatile(
       "{\n"
-      ".reg .pred p, pw, e, pacc, pt;\n"
+      ".reg .pred p, pw, e, pacc, pt, pskip, pts;\n"
+      ".reg .b32 tsa, tsv;\n"
       ".reg .b32 c, stage, par, fb, eb, t, spins, c0, c1;\n"
       ".reg .b64 a, b, a1, b1, t64;\n"
       ".reg .b16 mc;\n"
       "mov.b16 mc, 3;\n"
+      "setp.ne.b32 pts, %12, 0;\n"
       "mov.u32 c, 0;\n"
-      "setp.ne.b32 pacc, %8, 0;\n"
+      "setp.ne.b32 pacc, %9, 0;\n"
       "setp.eq.b32 pt, 0, 0;\n"
+      "setp.ne.b32 pskip, %11, 0;\n"
       "elect.sync _|e, 0xffffffff;\n"
       "CHUNK_LOOP:\n"
       "and.b32 stage, %0, 7;\n"
       "shr.u32 par, %0, 3;\n"
       "and.b32 par, par, 1;\n"
       "shl.b32 t, stage, 3;\n"
-      "add.u32 fb, %5, t;\n"
-      "add.u32 eb, %6, t;\n"
+      "add.u32 fb, %6, t;\n"
+      "add.u32 eb, %7, t;\n"
       "mov.u32 spins, 0;\n"
       "mov.u32 c0, %clock;\n"
+      "@pskip bra CHUNK_READY;\n"
       "CHUNK_WAIT:\n"
       "mbarrier.try_wait.parity.shared::cta.b64 pw, [fb], par;\n"
       "@pw bra CHUNK_READY;\n"
@@ -284,30 +294,34 @@ __device__ __forceinline__ uint32_t issue_chunks_pair(uint32_t d_tmem, uint64_t 
       "mov.u32 c1, %clock;\n"
       "sub.u32 c1, c1, c0;\n"
       "add.u32 %1, %1, c1;\n"
+      "shl.b32 tsa, stage, 2;\n"
+      "add.u32 tsa, tsa, %12;\n"
       "tcgen05.fence::after_thread_sync;\n"
       "mul.wide.u32 b, stage, 512;\n"
-      "add.s64 b, b, %4;\n"
+      "add.s64 b, b, %5;\n"
       "shr.u32 t, c, 1;\n"
       "mul.wide.u32 a, t, 1024;\n"
       "and.b32 t, c, 1;\n"
       "mul.wide.u32 t64, t, 4;\n"
       "add.s64 a, a, t64;\n"
-      "add.s64 a, a, %3;\n"
+      "add.s64 a, a, %4;\n"
       "add.s64 a1, a, 2;\n"
       "add.s64 b1, b, 2;\n"
-      "@e tcgen05.mma.cta_group::2.kind::f16 [%2], a, b, %9, pacc;\n"
-      "@e tcgen05.mma.cta_group::2.kind::f16 [%2], a1, b1, %9, pt;\n"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%3], a, b, %10, pacc;\n"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%3], a1, b1, %10, pt;\n"
       "@e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [eb], mc;\n"
+
       "setp.eq.b32 pacc, 0, 0;\n"
       "add.u32 %0, %0, 1;\n"
       "add.u32 c, c, 1;\n"
-      "setp.lt.u32 p, c, %7;\n"
+      "setp.lt.u32 p, c, %8;\n"
       "@p bra CHUNK_LOOP;\n"
       "}\n"
-      : "+r"(q), "+r"(spin_total)
+      : "+r"(q), "+r"(spin_total), "+r"(d2)
       : "r"(d_tmem), "l"(a_desc), "l"(w_desc0), "r"(bar_full0), "r"(bar_empty0), "r"(n_chunks), "r"(first_acc),
-        "r"(idesc)
+        "r"(idesc), "r"(skip_wait), "r"(ts_base)
       : "memory");
+  if (d2_total) *d2_total += d2;
   return q;
 }
 __device__ __forceinline__ uint32_t issue_chunks_split(uint32_t d_tmem, uint64_t a_hi_desc, uint64_t a_lo_desc, uint64_t w_desc0,
@@ -509,24 +523,27 @@ __device__ __forceinline__ uint32_t produce_chunks(const uint8_t* src, uint32_t 
 __device__ __forceinline__ uint32_t produce_chunks_pair(const void* tmap, uint32_t row0, uint32_t row_stride, uint32_t n,
                                                         uint32_t q, uint32_t expect_bytes, uint32_t bar_full0,
                                                         uint32_t bar_full_cl0, uint32_t bar_empty0, uint32_t w_smem0,
-                                                        uint32_t& wait_cycles) {
+                                                        uint32_t& wait_cycles, uint32_t ts_base = 0, uint32_t* d1_total = nullptr) {
+  uint32_t d1 = 0;
   asm volatile(
       "{\n"
-      ".reg .pred p, pw, lead;\n"
+      ".reg .pred p, pw, lead, pts;\n"
+      ".reg .b32 tsa, tsv;\n"
       ".reg .b32 c, stage, par, fb, fbc, eb, t, dst, spins, c0, c1, row, zero;\n"
       "mov.u32 c, 0;\n"
       "mov.u32 zero, 0;\n"
-      "mov.u32 row, %3;\n"
-      "setp.ne.u32 lead, %6, 0;\n"
+      "mov.u32 row, %4;\n"
+      "setp.ne.u32 lead, %7, 0;\n"
+      "setp.ne.b32 pts, %12, 0;\n"
       "PRODP_LOOP:\n"
       "and.b32 stage, %0, 7;\n"
       "shr.u32 par, %0, 3;\n"
       "and.b32 par, par, 1;\n"
       "xor.b32 par, par, 1;\n"
       "shl.b32 t, stage, 3;\n"
-      "add.u32 fb, %7, t;\n"
-      "add.u32 fbc, %8, t;\n"
-      "add.u32 eb, %9, t;\n"
+      "add.u32 fb, %8, t;\n"
+      "add.u32 fbc, %9, t;\n"
+      "add.u32 eb, %10, t;\n"
       "mov.u32 spins, 0;\n"
       "mov.u32 c0, %clock;\n"
       "PRODP_WAIT:\n"
@@ -540,19 +557,24 @@ __device__ __forceinline__ uint32_t produce_chunks_pair(const void* tmap, uint32
       "mov.u32 c1, %clock;\n"
       "sub.u32 c1, c1, c0;\n"
       "add.u32 %1, %1, c1;\n"
-      "@lead mbarrier.arrive.expect_tx.shared::cta.b64 _, [fb], %6;\n"
-      "mad.lo.u32 dst, stage, 8192, %10;\n"
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [dst], [%2, {zero, row}], [fbc];\n"
-      "add.u32 row, row, %4;\n"
+      "shl.b32 tsa, stage, 2;\n"
+      "add.u32 tsa, tsa, %12;\n"
+
+      "@lead mbarrier.arrive.expect_tx.shared::cta.b64 _, [fb], %7;\n"
+      "mad.lo.u32 dst, stage, 8192, %11;\n"
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [dst], [%3, {zero, row}], [fbc];\n"
+
+      "add.u32 row, row, %5;\n"
       "add.u32 %0, %0, 1;\n"
       "add.u32 c, c, 1;\n"
-      "setp.lt.u32 p, c, %5;\n"
+      "setp.lt.u32 p, c, %6;\n"
       "@p bra PRODP_LOOP;\n"
       "}\n"
-      : "+r"(q), "+r"(wait_cycles)
+      : "+r"(q), "+r"(wait_cycles), "+r"(d1)
       : "l"(tmap), "r"(row0), "r"(row_stride), "r"(n), "r"(expect_bytes), "r"(bar_full0), "r"(bar_full_cl0),
-        "r"(bar_empty0), "r"(w_smem0)
+        "r"(bar_empty0), "r"(w_smem0), "r"(ts_base)
       : "memory");
+  if (d1_total) *d1_total += d1;
   return q;
 }
 // The bias chunk of a layer: ONE accumulating MMA - A = the last 16 columns of the encoding k-block (column 63 is the
@@ -597,10 +619,10 @@ __device__ __forceinline__ uint32_t issue_bias_chunk(uint32_t d_tmem, uint64_t a
   return q;
 }
 __device__ __forceinline__ uint32_t issue_bias_chunk_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t w_desc0, uint32_t bar_full0,
-        uint32_t bar_empty0, uint32_t q, uint32_t idesc) {
+        uint32_t bar_empty0, uint32_t q, uint32_t idesc, uint32_t skip_wait = 0) {
   asm volatile(
       "{\n"
-      ".reg .pred p, pw, e, pt;\n"
+      ".reg .pred p, pw, e, pt, pskip;\n"
       ".reg .b32 stage, par, fb, eb, t, spins;\n"
       ".reg .b64 b;\n"
       ".reg .b16 mc;\n"
@@ -614,6 +636,8 @@ __device__ __forceinline__ uint32_t issue_bias_chunk_pair(uint32_t d_tmem, uint6
       "add.u32 fb, %4, t;\n"
       "add.u32 eb, %5, t;\n"
       "mov.u32 spins, 0;\n"
+      "setp.ne.b32 pskip, %7, 0;\n"
+      "@pskip bra BIAS_READY;\n"
       "BIAS_WAIT:\n"
       "mbarrier.try_wait.parity.shared::cta.b64 pw, [fb], par;\n"
       "@pw bra BIAS_READY;\n"
@@ -631,7 +655,7 @@ __device__ __forceinline__ uint32_t issue_bias_chunk_pair(uint32_t d_tmem, uint6
       "add.u32 %0, %0, 1;\n"
       "}\n"
       : "+r"(q)
-      : "r"(d_tmem), "l"(a_desc), "l"(w_desc0), "r"(bar_full0), "r"(bar_empty0), "r"(idesc)
+      : "r"(d_tmem), "l"(a_desc), "l"(w_desc0), "r"(bar_full0), "r"(bar_empty0), "r"(idesc), "r"(skip_wait)
       : "memory");
   return q;
 }
@@ -739,7 +763,9 @@ struct TcParams {
   // CTA-pair kernels: tensor maps over each pass's chunk-image stream seen as [rows][32] bf16 (64-byte rows, no
   // swizzle - the images are stored pre-swizzled); [pass][0] box = 128 rows (half of a 256-row chunk), [pass][1] box =
   // 64 rows (half of an M9 chunk)
+  float* ray_scratch;        // [grid][2 slots][kRayScratchFloats]: re-sampling scratch of the ray warps (fused kernel)
   alignas(64) CUtensorMap wmap[2][2];
+  int debug_noring;   // timing experiment (VIPNERF_TC_DEBUG_NORING=1): MMAs do not wait for weights - results are garbage
 };
 
 // Work of one tile slot: item i -> (pass, tile).  `unit` indexes the work units of the launch (fused: ray pairs,
@@ -960,7 +986,12 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const __grid_const
       mbar_init(bar(kBarWFull + s), 1);
       mbar_init(bar(kBarWEmpty + s), 1);
     }
-    for (int s = 0; s < 2; ++s) { mbar_init(bar(kBarAReady + s), kPair ? 8 : 4); mbar_init(bar(kBarDReady + s), 1); }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar(kBarAReady + s), kPair ? 8 : 4);
+      mbar_init(bar(kBarDReady + s), 1);
+      mbar_init(bar(kBarRayFull + s), 4);   // one arrival per warp of the slot's epilogue group
+      reinterpret_cast<volatile uint32_t*>(smem + kOffRayDone)[s] = 0;
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 9) {
@@ -1066,6 +1097,25 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const __grid_const
         if (kProf) c_vb += clock64() - t0;
       };
 
+      // Fine depths of the j-th ray pair of this slot exist once the ray warp has completed its j-th event (the coarse
+      // tiles are the slot's first events, one per pair).
+      uint32_t n_ray_events = 0;
+      auto ray_done_count = [&]() {
+        uint32_t v;
+        asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(smem + kOffRayDone) + 4u * slot) : "memory");
+        return v;
+      };
+      auto depths_ready = [&](int it2) {
+        if (!kFused || work.pass_of(it2) == 0 || (p.debug_noring & 4)) return true;
+        return ray_done_count() > (uint32_t)((it2 - work.n_first_pass) / 3);
+      };
+      auto wait_depths = [&](int it2) {
+        if (depths_ready(it2)) return;
+        const long long t0 = clock64();
+        while (!depths_ready(it2)) {
+          if (clock64() - t0 > kTimeoutCycles) { printf("vipnerf: ray warp timed out (block %d slot %d)\n", blockIdx.x, slot); __trap(); }
+        }
+      };
       uint32_t d_parity = 0;
       if (work.n_items > 0) {
         encode_item(0);
@@ -1083,7 +1133,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const __grid_const
         const float* small = reinterpret_cast<const float*>(ps.packed);
         // the next item's depths exist unless it is the fine tile of the pair whose coarse tile is this item
         const bool has_next = it + 1 < work.n_items;
-        const bool next_ready = has_next && (work.pass_of(it + 1) == 0 || (it + 1 - work.n_first_pass) / 3 < it);
+        // (checked again, without blocking, right before the prefetch)
         bool next_encoded = false;
 
         float sigma_lin = 0.f;
@@ -1106,7 +1156,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const __grid_const
             // M5 has retired: the encoding buffer is free, and so are vb/pev (the previous tile's M9 epilogue
             // is long done).  Use the time this slot's M6 spends on the tensor pipe.
             view_bias_item(it);
-            if (next_ready) { encode_item(it + 1); next_encoded = true; }
+            if (has_next && depths_ready(it + 1)) { encode_item(it + 1); next_encoded = true; }
           }
         }
         const long long t0 = kProf ? clock64() : 0;
@@ -1116,7 +1166,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const __grid_const
         const long long t1 = kProf ? clock64() : 0;
         c_wait += t1 - t0;
         float o[4];
-        view_epilogue(taddr, vb + (int)(ray - ray_first) * 128, small + kOffWOut, o);
+        if (!(p.debug_noring & 8)) view_epilogue(taddr, vb + (int)(ray - ray_first) * 128, small + kOffWOut, o);
+        else { o[0] = o[1] = o[2] = o[3] = 0.f; }
         tc_fence_before();  // orders this tile's last tcgen05.ld before the next tile's first MMA into the slot
         if (valid) {
           ps.sigma[pg] = fmaxf(sigma_lin + small[kOffBSigma], 0.f);  // :546-553 (eval: no noise)
@@ -1127,42 +1178,21 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const __grid_const
         }
         if (kProf) c_view += clock64() - t1;
         if (kFused) {
-          // ---- per-ray stages on the two rays a pair of tiles completes (one warp per ray)
+          // ---- per-ray stages on the two rays a pair of tiles completes: handed to the slot's ray warp.  Event k may
+          // only be signalled once the ray warp has consumed event k-1 (the mbarrier holds a single pending phase).
           const bool pair_done = pi == 0 || (tile % 3) == 2;
-          if (pair_done) {
+          if (pair_done && !(p.debug_noring & 4)) {
             const long long th = kProf ? clock64() : 0;
-            group_sync(group);  // the rays' network outputs (global) are complete and visible to the group
-            const int64_t pair = pi == 0 ? tile : tile / 3;
-            const int wq = warp & 3;
-            const int64_t r = 2 * pair + wq;
-            if (wq < 2 && r < p.n_rays) {
-              RayConsts rc;
-              rc.dnorm = vec3_norm(p.rp.pts_d[3 * r], p.rp.pts_d[3 * r + 1], p.rp.pts_d[3 * r + 2]);
-              rc.oz = p.rp.rays_o[3 * r + 2];
-              rc.dz = p.rp.rays_d[3 * r + 2];
-              if (pi == 0) {
-                float z_reg[2], w_reg[2];
-                composite_ray<2>(lane, 64, ps.z + r * 64, ps.sigma + r * 64, ps.rgb + r * 192, nullptr, 0, p.fl.ndc,
-                                 p.fl.white_bkgd, rc, p.out[0], r, z_reg, w_reg);
-                if (p.has_fine) {
-                  // the slot's A buffer is dead until the next tile's first epilogue: use it as scratch
-                  float* scratch = reinterpret_cast<float*>(smem + kOffA + slot * kABytes) + wq * 1024;
-                  const float* u = p.rp.u_rand ? p.rp.u_rand + r * p.n_fine : p.rp.u_vals;
-                  resample_ray<2>(lane, 64, p.n_fine, z_reg, w_reg, u, p.rp.u_rand == nullptr, scratch,
-                                  p.pass[1].z + r * (64 + p.n_fine));
-                }
-              } else {
-                float z_reg[6], w_reg[6];
-                composite_ray<6>(lane, 192, ps.z + r * 192, ps.sigma + r * 192, ps.rgb + r * 576, nullptr, 0, p.fl.ndc,
-                                 p.fl.white_bkgd, rc, p.out[1], r, z_reg, w_reg);
-              }
-            }
-            group_sync(group);  // z_fine (global) visible before the group encodes fine tiles
+            while (ray_done_count() < n_ray_events) {}
+            ++n_ray_events;
+            __threadfence_block();  // this thread's network outputs (global) before the signal
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar(kBarRayFull + slot));
             if (kProf) c_hook += clock64() - th;
           }
         }
         if (has_next) {
-          if (!next_encoded) encode_item(it + 1);
+          if (!next_encoded) { wait_depths(it + 1); encode_item(it + 1); }
           fence_proxy_async();
           arrive_a_ready();
         }
@@ -1176,14 +1206,14 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const __grid_const
     }
   } else if (warp == 8) {
     // =================================================================== weight producer
-    if (lane == 0) {
+    if (lane == 0 && p.debug_noring != 1) {
       WorkList<kFused, kPair> work0(p, cta_group_idx * kSlots + 0, n_slots_total, (int)cta_rank);
       WorkList<kFused, kPair> work1(p, cta_group_idx * kSlots + (kSlots - 1), n_slots_total, (int)cta_rank);
       const int n_max = max(work0.n_items, kSlots > 1 ? work1.n_items : 0);
       // pair mode: this CTA streams its half of every chunk's rows; both CTAs' copies complete on the leader's w_full
       const uint32_t full_cluster0 = kPair ? map_to_cta(bar(kBarWFull), 0) : 0;
       const long long c_prod_begin = kProf ? clock64() : 0;
-      uint32_t q = 0, prod_wait = 0;
+      uint32_t q = 0, prod_wait = 0, prod_d1 = 0;
       for (int it = 0; it < n_max; ++it) {
         for (int l = 0; l < kNumMatLayers; ++l) {
           for (int s = 0; s < kSlots; ++s) {
@@ -1199,8 +1229,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const __grid_const
               const uint32_t rows = (uint32_t)layer_n(l);
               const uint32_t row0 = (uint32_t)(tc_layer_byte_offset(l) * (kSplit3 ? 2 : 1)) / 64 + cta_rank * (rows / 2);
               q = produce_chunks_pair(&p.wmap[w.pass_of(it)][l == 9 ? 1 : 0], row0, rows, n_chunks, q,
-                                      cta_rank == 0 ? chunk_bytes : 0, bar(kBarWFull), full_cluster0, bar(kBarWEmpty),
-                                      smem_u32(smem + kOffW), prod_wait);
+                                      cta_rank == 0 ? (p.debug_noring == 3 ? chunk_bytes / 8 : chunk_bytes) : 0, bar(kBarWFull), full_cluster0, bar(kBarWEmpty),
+                                      smem_u32(smem + kOffW), prod_wait,
+                                      0, &prod_d1);
             } else {
               q = produce_chunks(src, bytes, chunk_bytes, n_chunks, q, bar(kBarWFull), bar(kBarWEmpty),
                                  smem_u32(smem + kOffW), prod_wait);
@@ -1211,10 +1242,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const __grid_const
       if (kProf && p.prof != nullptr && blockIdx.x < 2) {
         p.prof[40 + 4 * blockIdx.x] = prod_wait;
         p.prof[41 + 4 * blockIdx.x] = (unsigned long long)(clock64() - c_prod_begin);
-        p.prof[42 + 4 * blockIdx.x] = 0;
+        p.prof[42 + 4 * blockIdx.x] = prod_d1;
       }
     }
-  } else if (!kPair || cta_rank == 0) {
+  } else if (warp == 9 && (!kPair || cta_rank == 0)) {
     // =================================================================== MMA issuer (warp 9 of the leader CTA)
     // The whole warp runs the loop; one elected lane issues.  Per (tile, layer, slot) step: wait a_ready, run the
     // PTX chunk loop(s) over the layer's A operand (encoding buffer for M0 and the first 64 columns of M5, the A
@@ -1231,6 +1262,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const __grid_const
     static_assert(kKBlockUnits == 1024 && (kStageBytes >> 4) == (kPair ? 512 : 1024), "issue_chunks* assume these");
     const uint32_t bar_full0 = bar(kBarWFull), bar_empty0 = bar(kBarWEmpty);
     long long c_wait_a = 0;
+    uint32_t lane_d2 = 0;
     uint32_t spins = 0;  // failed probes of the weight ring (prof builds report it)
     const long long c_begin = kProf ? clock64() : 0;
     for (int it = 0; it < n_max; ++it) {
@@ -1253,7 +1285,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const __grid_const
           const uint64_t a_hi = a_desc0 + slot_units * kAUnits, a_lo = a_desc0 + kAUnits;
           auto run = [&](uint64_t hi, uint64_t lo, uint32_t n, uint32_t acc) {
             if (!kSplit3 && !kPair) q = issue_chunks(d_tmem, hi, w_desc0, bar_full0, bar_empty0, q, n, acc, idesc, spins);
-            else if (!kSplit3) q = issue_chunks_pair(d_tmem, hi, w_desc0, bar_full0, bar_empty0, q, n, acc, idesc, spins);
+            else if (!kSplit3) q = issue_chunks_pair(d_tmem, hi, w_desc0, bar_full0, bar_empty0, q, n, acc, idesc, spins, p.debug_noring == 1,
+                                                  0, &lane_d2);
             else if (!kPair) q = issue_chunks_split(d_tmem, hi, lo, w_desc0, bar_full0, bar_empty0, q, n, acc, idesc);
             else q = issue_chunks_split_pair(d_tmem, hi, lo, w_desc0, bar_full0, bar_empty0, q, n, acc, idesc);
           };
@@ -1269,7 +1302,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const __grid_const
             // encoding columns 48..63 (k-block offset 96 B = 6 units) x the bias chunk; BF16X3: hi and lo images
             // (the lo part of the constant-one column is zero, so A_lo contributes nothing and is skipped)
             for (int part = 0; part < (kSplit3 ? 2 : 1); ++part) {
-              q = kPair ? issue_bias_chunk_pair(d_tmem, pe_hi + 6, w_desc0, bar_full0, bar_empty0, q, idesc)
+              q = kPair ? issue_bias_chunk_pair(d_tmem, pe_hi + 6, w_desc0, bar_full0, bar_empty0, q, idesc, p.debug_noring == 1)
                         : issue_bias_chunk(d_tmem, pe_hi + 6, w_desc0, bar_full0, bar_empty0, q, idesc);
             }
           }
@@ -1281,6 +1314,53 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const __grid_const
     if (kProf && p.prof != nullptr && blockIdx.x == 0 && lane == 0) {
       p.prof[32] = c_wait_a; p.prof[33] = spins; p.prof[34] = (unsigned long long)(clock64() - c_begin);
       p.prof[35] = q;
+      p.prof[36] = lane_d2;
+    }
+  }
+  if (kFused && warp >= 10 && warp - 10 < kSlots && !(p.debug_noring & 4)) {
+    // =================================================================== ray warps (one per tile slot)
+    // Alpha compositing (volume_rendering, VipNeRF01.py:331-384) of the two rays a coarse tile / a fine tile triple
+    // completes and, after the coarse pass, their hierarchical re-sampling (get_z_vals_fine :205-216) - one warp,
+    // shuffle scans, asynchronous to the tiles the slot's epilogue group goes on with.
+    const int slot = warp - 10;
+    const WorkList<kFused, kPair> work(p, cta_group_idx * kSlots + slot, n_slots_total, (int)cta_rank);
+    float* scratch = p.ray_scratch + ((size_t)blockIdx.x * 2 + slot) * kRayScratchFloats;
+    uint32_t parity = 0, n_done = 0;
+    for (int it = 0; it < work.n_items; ++it) {
+      const int pi = work.pass_of(it);
+      const int64_t tile = work.tile_of(it);
+      if (!(pi == 0 || (tile % 3) == 2)) continue;
+      const PassDesc& ps = p.pass[pi];
+      mbar_wait(bar(kBarRayFull + slot), parity);
+      parity ^= 1;
+      const int64_t pair = pi == 0 ? tile : tile / 3;
+      for (int rr = 0; rr < 2; ++rr) {
+        const int64_t r = 2 * pair + rr;
+        if (r >= p.n_rays) continue;
+        RayConsts rc;
+        rc.dnorm = vec3_norm(p.rp.pts_d[3 * r], p.rp.pts_d[3 * r + 1], p.rp.pts_d[3 * r + 2]);
+        rc.oz = p.rp.rays_o[3 * r + 2];
+        rc.dz = p.rp.rays_d[3 * r + 2];
+        if (pi == 0) {
+          float z_reg[2], w_reg[2];
+          composite_ray<2>(lane, 64, ps.z + r * 64, ps.sigma + r * 64, ps.rgb + r * 192, nullptr, 0, p.fl.ndc,
+                           p.fl.white_bkgd, rc, p.out[0], r, z_reg, w_reg);
+          if (p.has_fine) {
+            const float* u = p.rp.u_rand ? p.rp.u_rand + r * p.n_fine : p.rp.u_vals;
+            resample_ray<2>(lane, 64, p.n_fine, z_reg, w_reg, u, p.rp.u_rand == nullptr, scratch,
+                            p.pass[1].z + r * (64 + p.n_fine));
+          }
+        } else {
+          float z_reg[6], w_reg[6];
+          composite_ray<6>(lane, 192, ps.z + r * 192, ps.sigma + r * 192, ps.rgb + r * 576, nullptr, 0, p.fl.ndc,
+                           p.fl.white_bkgd, rc, p.out[1], r, z_reg, w_reg);
+        }
+      }
+      ++n_done;
+      __threadfence_block();   // z_fine (global) before the count the epilogue group acquires
+      __syncwarp();
+      if (lane == 0)
+        asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(smem_u32(smem + kOffRayDone) + 4u * slot), "r"(n_done) : "memory");
     }
   }
   __syncthreads();
@@ -1331,14 +1411,14 @@ EncodeTiledFn get_encode_tiled() {
   }();
   return fn;
 }
-cudaError_t encode_weight_maps(const uint8_t* packed, bool split3, CUtensorMap (&maps)[2]) {
+cudaError_t encode_weight_maps(const uint8_t* packed, bool split3, CUtensorMap (&maps)[2], int box_div = 1) {
   EncodeTiledFn encode = get_encode_tiled();
   if (encode == nullptr) return cudaErrorNotSupported;
   const cuuint64_t dims[2] = {32, (cuuint64_t)kTcBigBytes * (split3 ? 2 : 1) / 64};
   const cuuint64_t strides[1] = {64};
   const cuuint32_t elem_strides[2] = {1, 1};
   for (int i = 0; i < 2; ++i) {
-    const cuuint32_t box[2] = {32, i == 0 ? 128u : 64u};
+    const cuuint32_t box[2] = {32, (i == 0 ? 128u : 64u) / box_div};
     const CUresult r = encode(&maps[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
                               const_cast<uint8_t*>(packed) + kSmallBytes, dims, strides, box, elem_strides,
                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
@@ -1388,9 +1468,10 @@ cudaError_t launch_variant(const TcParams& p, int64_t n_units, cudaStream_t s) {
 template <bool kSplit3, bool kFused>
 cudaError_t launch(TcParams& p, int64_t n_units, cudaStream_t s) {
   const bool pair = g_use_cta_pairs;
+  { const char* e = getenv("VIPNERF_TC_DEBUG_NORING"); p.debug_noring = (e != nullptr && pair && !kSplit3) ? atoi(e) : 0; }
   if (pair) {
     for (int pi = 0; pi < 2; ++pi) {
-      const cudaError_t e = encode_weight_maps(p.pass[pi].packed, kSplit3, p.wmap[pi]);
+      const cudaError_t e = encode_weight_maps(p.pass[pi].packed, kSplit3, p.wmap[pi], p.debug_noring == 3 ? 8 : 1);
       if (e != cudaSuccess) return e;
     }
   }
@@ -1408,6 +1489,8 @@ void set_tc_profile_buffer(void* dev_ptr) {
   std::lock_guard<std::mutex> lock(g_attr_mutex);
   g_prof_buffer = static_cast<unsigned long long*>(dev_ptr);
 }
+
+size_t tc_ray_scratch_floats() { return (size_t)512 * 2 * kRayScratchFloats; }   // up to 512 CTAs
 
 cudaError_t launch_mlp_tc(int precision, const RayPtrs& rp, const RenderFlags& fl, int64_t n_rays, int S,
                           const float* z, const void* packed, float* sigma, float* rgb, float* vis,
@@ -1448,15 +1531,17 @@ cudaError_t launch_render_fused_tc(int precision, const FusedArgs& a, cudaStream
     d.n_points = a.n_rays * d.S;
     d.packed = static_cast<const uint8_t*>(pi ? a.packed_fine : a.packed_coarse);
     d.z = pi ? (o.z_vals ? o.z_vals : a.ws_z_fine) : (o.z_vals ? o.z_vals : a.ws_z_coarse);
-    d.sigma = o.raw_sigma ? o.raw_sigma : a.ws_sigma;  // workspace is shared by both passes
-    d.rgb = o.raw_rgb ? o.raw_rgb : a.ws_rgb;
-    d.vis = o.raw_visibility ? o.raw_visibility : a.ws_vis;
+    // each pass has its own workspace region: the ray warps read a pass's outputs while the next tiles are written
+    d.sigma = o.raw_sigma ? o.raw_sigma : (pi ? a.ws_sigma : a.ws_sigma_c);
+    d.rgb = o.raw_rgb ? o.raw_rgb : (pi ? a.ws_rgb : a.ws_rgb_c);
+    d.vis = o.raw_visibility ? o.raw_visibility : (pi ? a.ws_vis : a.ws_vis_c);
     d.compute_z = pi == 0;
     p.out[pi] = o;
     p.out[pi].z_vals = nullptr;  // depths are produced in place
   }
   if (!p.has_fine) p.pass[1] = p.pass[0];
   p.n_units = (a.n_rays + 1) / 2;
+  p.ray_scratch = a.ws_ray_scratch;
   p.prof = g_prof_buffer;
   if (precision == VIPNERF_PRECISION_BF16X3) return launch<true, true>(p, p.n_units, s);
   return launch<false, true>(p, p.n_units, s);
