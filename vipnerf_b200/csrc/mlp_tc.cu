@@ -933,10 +933,14 @@ __device__ __forceinline__ float layer_epilogue(uint8_t* smem, int slot, int row
   return sigma_acc;
 }
 
-// M9 epilogue for one row: relu(acc + (bias + view-direction part)) . views_output_linear -> 4 logits
+// M9 epilogue for one row: relu(acc + (bias + view-direction part)) . views_output_linear -> 4 logits.
+// Four independent accumulator pairs (one per 32-column block, interleaved even/odd columns) keep the FFMA2
+// dependency chains short; they are summed at the end.
 __device__ __forceinline__ void view_epilogue(uint32_t taddr, const float* vb_row, const float* __restrict__ w_out,
                                               float (&o)[4]) {
-  uint64_t o01 = pack_f32x2(0.f, 0.f), o23 = o01;
+  uint64_t acc01[4], acc23[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) acc01[i] = acc23[i] = pack_f32x2(0.f, 0.f);
   uint32_t v[2][32];
   tmem_ld32(taddr, v[0]);
 #pragma unroll
@@ -954,10 +958,12 @@ __device__ __forceinline__ void view_epilogue(uint32_t taddr, const float* vb_ro
       const float h = fmaxf(__uint_as_float(v[cb & 1][j]) + b[j], 0.f);
       const float4 w = __ldg(reinterpret_cast<const float4*>(w_out) + cb * 32 + j);
       const uint64_t hh = pack_f32x2(h, h);
-      o01 = ffma2(hh, pack_f32x2(w.x, w.y), o01);
-      o23 = ffma2(hh, pack_f32x2(w.z, w.w), o23);
+      acc01[j & 3] = ffma2(hh, pack_f32x2(w.x, w.y), acc01[j & 3]);
+      acc23[j & 3] = ffma2(hh, pack_f32x2(w.z, w.w), acc23[j & 3]);
     }
   }
+  const uint64_t o01 = fadd2(fadd2(acc01[0], acc01[1]), fadd2(acc01[2], acc01[3]));
+  const uint64_t o23 = fadd2(fadd2(acc23[0], acc23[1]), fadd2(acc23[2], acc23[3]));
   unpack_f32x2(o01, o[0], o[1]);
   unpack_f32x2(o23, o[2], o[3]);
 }
