@@ -20,6 +20,8 @@ LIB_PATH = os.path.join(HERE, 'libvipnerf_b200.so')
 SOURCES = ['api.cu', 'stage_kernels.cu', 'mlp_fp32.cu', 'mlp_tc.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '-Xptxas', '-v', '--expt-relaxed-constexpr']
+# extra -D switches for experiments (e.g. VIPNERF_NVCC_DEFINES="VIPNERF_ONES_4K"), part of the build digest
+NVCC_FLAGS += ['-D' + d for d in os.environ.get('VIPNERF_NVCC_DEFINES', '').split() if d]
 
 
 def find_nvcc() -> str:

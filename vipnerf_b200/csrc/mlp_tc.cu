@@ -40,23 +40,46 @@ namespace vipnerf {
 namespace {
 
 constexpr int kTile = 128;
-constexpr int kMaxStages = 8;  // weight-ring stages: 4 x 16 KiB (one CTA per tile pair) or 8 x 8 KiB (CTA pairs)
 constexpr int kNumThreads = 384;   // 12 warps: a 10-warp CTA has the same per-thread register budget (3 warps per sub-partition)
 constexpr uint32_t kABytes = 65536;
 constexpr uint32_t kKBlockBytes = 16384;
+// Shared memory: two activation buffers (the point encoding of a tile lives in k-block 0 of its slot's buffer while
+// M0 / the encoding part of M5 run), then the weight ring, then barriers and small per-ray tables.
+// VIPNERF_ONES_4K (build-time fallback): a conventional 4 KiB all-ones operand instead of the 128-byte block read
+// through a zero-stride descriptor; costs one ring stage.
+#ifdef VIPNERF_ONES_4K
+#define VIPNERF_PAIR_STAGES 11
+#define VIPNERF_SINGLE_STAGES 5
+#else
+#define VIPNERF_PAIR_STAGES 12
+#define VIPNERF_SINGLE_STAGES 6
+#endif
+#define VIPNERF_STR2(x) #x
+#define VIPNERF_STR(x) VIPNERF_STR2(x)
+constexpr int kPairStages = VIPNERF_PAIR_STAGES;      // x 8 KiB (each CTA of a pair holds half of a chunk's rows)
+constexpr int kSingleStages = VIPNERF_SINGLE_STAGES;  // x 16 KiB
 constexpr uint32_t kOffA = 0;                 // 2 x 64 KiB
-constexpr uint32_t kOffPe = 131072;           // 2 x 16 KiB
-constexpr uint32_t kOffW = 163840;            // 4 x 16 KiB
-constexpr uint32_t kOffTail = 229376;
-constexpr uint32_t kOffBar = kOffTail;        // 28 mbarriers
-constexpr uint32_t kOffRayDone = kOffTail + 192; // [2 slots] u32: per-ray events the slot's ray warp has completed
-constexpr uint32_t kOffTmemPtr = kOffTail + 240;
-constexpr uint32_t kOffVb = kOffTail + 256;   // [2 slots][2 rays][128] fp32: view-direction part of M9 + bias
+constexpr uint32_t kOffW = 131072;            // weight ring, 96 KiB
+constexpr uint32_t kRingBytes = 98304;
+constexpr uint32_t kOffTail = kOffW + kRingBytes;
+constexpr uint32_t kOffBar = kOffTail;        // up to 32 mbarriers
+constexpr uint32_t kOffRayDone = kOffTail + 256;  // [2 slots] u32: per-ray events the slot's ray warp has completed
+constexpr uint32_t kOffTmemPtr = kOffTail + 264;
+constexpr uint32_t kOffVb = kOffTail + 272;   // [2 slots][2 rays][128] fp32: view-direction part of M9 + bias
 constexpr uint32_t kOffPev = kOffVb + 2048;   // [2 slots][2 rays][32]  fp32: view-direction encodings
+#ifdef VIPNERF_ONES_4K
+constexpr uint32_t kOffOnes = kOffW + 90112;  // 4 KiB of bf16 1.0 behind the (shorter) ring
+constexpr uint32_t kOnesBytes = 4096;
 constexpr uint32_t kSmemBytes = kOffPev + 512;
+#else
+constexpr uint32_t kOffOnes = kOffPev + 512;  // 128 B of bf16 1.0: the A operand of the bias chunks
+constexpr uint32_t kOnesBytes = 128;
+constexpr uint32_t kSmemBytes = kOffOnes + 128;
+#endif
 static_assert(kSmemBytes <= 232448, "exceeds the 227 KiB per-CTA shared memory limit");
+static_assert(kPairStages * 8192 <= kRingBytes && kSingleStages * 16384 <= kRingBytes, "weight ring does not fit");
 
-enum { kBarWFull = 0, kBarWEmpty = 8, kBarAReady = 16, kBarDReady = 18, kBarRayFull = 20 };
+enum { kBarWFull = 0, kBarWEmpty = 12, kBarAReady = 24, kBarDReady = 26, kBarRayFull = 28 };
 
 // tcgen05 instruction descriptor: D=F32, A=B=BF16, both K-major, M=128, N=n (cute::UMMA::InstrDescriptor bits:
 // c_format[4,6)=1, a_format[7,10)=1, b_format[10,13)=1, n_dim[17,23)=N>>3, m_dim[24,29)=M>>4)
@@ -184,120 +207,115 @@ __device__ __forceinline__ void mma_chunk_split_hi(uint32_t d_tmem, uint64_t a_h
       "l"(a_hi), "l"(a_lo), "l"(b_desc), "r"(first_acc), "r"(idesc), "r"(empty_bar)
       : "memory");
 }
+// Position in the weight ring (stage index and the phase parity of its barriers) plus a cycle counter the
+// profiling builds report; every role keeps its own copy and advances it chunk by chunk.
+struct RingState {
+  uint32_t stage = 0, phase = 0, wait_cycles = 0;
+};
+
 // The MMA issue loop of one run of `n_chunks` consecutive weight chunks, hand-written in PTX so that the per-chunk
 // cost is ~25 instructions (ptxas turns the equivalent C++ into ~135 with reconvergence barriers and R2UR moves).
 // Chunk c multiplies A columns [32c, 32c+32) - k-block c>>1 (1024 descriptor units apart), 64-byte half c&1
-// (4 units) - with ring stage q mod kStages, waits the stage's full barrier, issues two N x K=16 MMAs from the
-// elected lane and commits the stage's empty barrier.  Returns the advanced chunk counter q.
-//   single CTA : 4 stages x 16 KiB (1024 units), tcgen05.mma.cta_group::1, M=128
-//   CTA pair   : 8 stages x  8 KiB ( 512 units: each CTA holds half of the chunk's rows), cta_group::2, M=256,
+// (4 units) - with the current ring stage: waits the stage's full barrier, issues two N x K=16 MMAs from the
+// elected lane, commits the stage's empty barrier and advances the ring.
+//   single CTA :  6 stages x 16 KiB (1024 units), tcgen05.mma.cta_group::1, M=128
+//   CTA pair   : 12 stages x  8 KiB ( 512 units: each CTA holds half of the chunk's rows), cta_group::2, M=256,
 //                commits multicast to both CTAs' barriers
 // The *_split variants are BF16X3: every weight chunk is two ring stages (hi image, lo image); per chunk
 // A_hi*W_hi + A_lo*W_hi (4 MMAs, commit) then A_hi*W_lo (2 MMAs, commit).
-__device__ __forceinline__ uint32_t issue_chunks(uint32_t d_tmem, uint64_t a_desc, uint64_t w_desc0, uint32_t bar_full0,
-        uint32_t bar_empty0, uint32_t q, uint32_t n_chunks, uint32_t first_acc, uint32_t idesc,
-        uint32_t& spin_total) {
+__device__ __forceinline__ void issue_chunks(RingState& rs, uint32_t d_tmem, uint64_t a_desc, uint64_t w_desc0,
+        uint32_t bar_full0, uint32_t bar_empty0, uint32_t n_chunks, uint32_t first_acc, uint32_t idesc) {
   asm volatile(
       "{\n"
       ".reg .pred p, pw, e, pacc, pt;\n"
-      ".reg .b32 c, stage, par, fb, eb, t, spins, c0, c1;\n"
+      ".reg .b32 c, fb, eb, t, spins, c0, c1;\n"
       ".reg .b64 a, b, a1, b1, t64;\n"
       ".reg .b16 mc;\n"
       "mov.b16 mc, 3;\n"
       "mov.u32 c, 0;\n"
-      "setp.ne.b32 pacc, %8, 0;\n"
+      "setp.ne.b32 pacc, %9, 0;\n"
       "setp.eq.b32 pt, 0, 0;\n"
       "elect.sync _|e, 0xffffffff;\n"
       "CHUNK_LOOP:\n"
-      "and.b32 stage, %0, 3;\n"
-      "shr.u32 par, %0, 2;\n"
-      "and.b32 par, par, 1;\n"
-      "shl.b32 t, stage, 3;\n"
-      "add.u32 fb, %5, t;\n"
-      "add.u32 eb, %6, t;\n"
+      "shl.b32 t, %0, 3;\n"
+      "add.u32 fb, %6, t;\n"
+      "add.u32 eb, %7, t;\n"
       "mov.u32 spins, 0;\n"
       "mov.u32 c0, %clock;\n"
       "CHUNK_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 pw, [fb], par;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 pw, [fb], %1;\n"
       "@pw bra CHUNK_READY;\n"
       "add.u32 spins, spins, 1;\n"
-            "setp.gt.u32 p, spins, 4000000;\n"
+      "setp.gt.u32 p, spins, 4000000;\n"
       "@p trap;\n"
       "bra CHUNK_WAIT;\n"
       "CHUNK_READY:\n"
       "mov.u32 c1, %clock;\n"
       "sub.u32 c1, c1, c0;\n"
-      "add.u32 %1, %1, c1;\n"
+      "add.u32 %2, %2, c1;\n"
       "tcgen05.fence::after_thread_sync;\n"
-      "mul.wide.u32 b, stage, 1024;\n"
-      "add.s64 b, b, %4;\n"
+      "mul.wide.u32 b, %0, 1024;\n"
+      "add.s64 b, b, %5;\n"
       "shr.u32 t, c, 1;\n"
       "mul.wide.u32 a, t, 1024;\n"
       "and.b32 t, c, 1;\n"
       "mul.wide.u32 t64, t, 4;\n"
       "add.s64 a, a, t64;\n"
-      "add.s64 a, a, %3;\n"
+      "add.s64 a, a, %4;\n"
       "add.s64 a1, a, 2;\n"
       "add.s64 b1, b, 2;\n"
-      "@e tcgen05.mma.cta_group::1.kind::f16 [%2], a, b, %9, pacc;\n"
-      "@e tcgen05.mma.cta_group::1.kind::f16 [%2], a1, b1, %9, pt;\n"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%3], a, b, %10, pacc;\n"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%3], a1, b1, %10, pt;\n"
       "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [eb];\n"
       "setp.eq.b32 pacc, 0, 0;\n"
       "add.u32 %0, %0, 1;\n"
+      "setp.eq.u32 p, %0, " VIPNERF_STR(VIPNERF_SINGLE_STAGES) ";\n"
+      "@p mov.u32 %0, 0;\n"
+      "@p xor.b32 %1, %1, 1;\n"
       "add.u32 c, c, 1;\n"
-      "setp.lt.u32 p, c, %7;\n"
+      "setp.lt.u32 p, c, %8;\n"
       "@p bra CHUNK_LOOP;\n"
       "}\n"
-      : "+r"(q), "+r"(spin_total)
+      : "+r"(rs.stage), "+r"(rs.phase), "+r"(rs.wait_cycles)
       : "r"(d_tmem), "l"(a_desc), "l"(w_desc0), "r"(bar_full0), "r"(bar_empty0), "r"(n_chunks), "r"(first_acc),
         "r"(idesc)
       : "memory");
-  return q;
 }
-__device__ __forceinline__ uint32_t issue_chunks_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t w_desc0, uint32_t bar_full0,
-        uint32_t bar_empty0, uint32_t q, uint32_t n_chunks, uint32_t first_acc, uint32_t idesc,
-        uint32_t& spin_total, uint32_t skip_wait = 0, uint32_t ts_base = 0,
-        uint32_t* d2_total = nullptr) {
-  uint32_t d2 = 0;
+__device__ __forceinline__ void issue_chunks_pair(RingState& rs, uint32_t d_tmem, uint64_t a_desc, uint64_t w_desc0,
+        uint32_t bar_full0, uint32_t bar_empty0, uint32_t n_chunks, uint32_t first_acc, uint32_t idesc,
+        uint32_t skip_wait = 0) {
   asm volatile(
       "{\n"
-      ".reg .pred p, pw, e, pacc, pt, pskip, pts;\n"
-      ".reg .b32 tsa, tsv;\n"
-      ".reg .b32 c, stage, par, fb, eb, t, spins, c0, c1;\n"
+      ".reg .pred p, pw, e, pacc, pt, pskip;\n"
+      ".reg .b32 c, fb, eb, t, spins, c0, c1;\n"
       ".reg .b64 a, b, a1, b1, t64;\n"
       ".reg .b16 mc;\n"
       "mov.b16 mc, 3;\n"
-      "setp.ne.b32 pts, %12, 0;\n"
       "mov.u32 c, 0;\n"
       "setp.ne.b32 pacc, %9, 0;\n"
       "setp.eq.b32 pt, 0, 0;\n"
       "setp.ne.b32 pskip, %11, 0;\n"
       "elect.sync _|e, 0xffffffff;\n"
       "CHUNK_LOOP:\n"
-      "and.b32 stage, %0, 7;\n"
-      "shr.u32 par, %0, 3;\n"
-      "and.b32 par, par, 1;\n"
-      "shl.b32 t, stage, 3;\n"
+      "shl.b32 t, %0, 3;\n"
       "add.u32 fb, %6, t;\n"
       "add.u32 eb, %7, t;\n"
       "mov.u32 spins, 0;\n"
       "mov.u32 c0, %clock;\n"
       "@pskip bra CHUNK_READY;\n"
       "CHUNK_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 pw, [fb], par;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 pw, [fb], %1;\n"
       "@pw bra CHUNK_READY;\n"
       "add.u32 spins, spins, 1;\n"
-            "setp.gt.u32 p, spins, 4000000;\n"
+      "setp.gt.u32 p, spins, 4000000;\n"
       "@p trap;\n"
       "bra CHUNK_WAIT;\n"
       "CHUNK_READY:\n"
       "mov.u32 c1, %clock;\n"
       "sub.u32 c1, c1, c0;\n"
-      "add.u32 %1, %1, c1;\n"
-      "shl.b32 tsa, stage, 2;\n"
-      "add.u32 tsa, tsa, %12;\n"
+      "add.u32 %2, %2, c1;\n"
       "tcgen05.fence::after_thread_sync;\n"
-      "mul.wide.u32 b, stage, 512;\n"
+      "mul.wide.u32 b, %0, 512;\n"
       "add.s64 b, b, %5;\n"
       "shr.u32 t, c, 1;\n"
       "mul.wide.u32 a, t, 1024;\n"
@@ -310,31 +328,32 @@ __device__ __forceinline__ uint32_t issue_chunks_pair(uint32_t d_tmem, uint64_t 
       "@e tcgen05.mma.cta_group::2.kind::f16 [%3], a, b, %10, pacc;\n"
       "@e tcgen05.mma.cta_group::2.kind::f16 [%3], a1, b1, %10, pt;\n"
       "@e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [eb], mc;\n"
-
       "setp.eq.b32 pacc, 0, 0;\n"
       "add.u32 %0, %0, 1;\n"
+      "setp.eq.u32 p, %0, " VIPNERF_STR(VIPNERF_PAIR_STAGES) ";\n"
+      "@p mov.u32 %0, 0;\n"
+      "@p xor.b32 %1, %1, 1;\n"
       "add.u32 c, c, 1;\n"
       "setp.lt.u32 p, c, %8;\n"
       "@p bra CHUNK_LOOP;\n"
       "}\n"
-      : "+r"(q), "+r"(spin_total), "+r"(d2)
+      : "+r"(rs.stage), "+r"(rs.phase), "+r"(rs.wait_cycles)
       : "r"(d_tmem), "l"(a_desc), "l"(w_desc0), "r"(bar_full0), "r"(bar_empty0), "r"(n_chunks), "r"(first_acc),
-        "r"(idesc), "r"(skip_wait), "r"(ts_base)
+        "r"(idesc), "r"(skip_wait)
       : "memory");
-  if (d2_total) *d2_total += d2;
-  return q;
 }
-__device__ __forceinline__ uint32_t issue_chunks_split(uint32_t d_tmem, uint64_t a_hi_desc, uint64_t a_lo_desc, uint64_t w_desc0,
-        uint32_t bar_full0, uint32_t bar_empty0, uint32_t q, uint32_t n_chunks, uint32_t first_acc, uint32_t idesc) {
+__device__ __forceinline__ void issue_chunks_split(RingState& rs, uint32_t d_tmem, uint64_t a_hi_desc, uint64_t a_lo_desc,
+        uint64_t w_desc0, uint32_t bar_full0, uint32_t bar_empty0, uint32_t n_chunks, uint32_t first_acc,
+        uint32_t idesc) {
   asm volatile(
       "{\n"
       ".reg .pred p, pw, e, pacc, pt;\n"
-      ".reg .b32 c, stage, par, fb, eb, t, spins, part;\n"
+      ".reg .b32 c, fb, eb, t, spins, part;\n"
       ".reg .b64 a, l, b, a1, l1, b1, t64, off;\n"
       ".reg .b16 mc;\n"
       "mov.b16 mc, 3;\n"
       "mov.u32 c, 0;\n"
-      "setp.ne.b32 pacc, %8, 0;\n"
+      "setp.ne.b32 pacc, %9, 0;\n"
       "setp.eq.b32 pt, 0, 0;\n"
       "elect.sync _|e, 0xffffffff;\n"
       "SCHUNK_LOOP:\n"
@@ -344,20 +363,17 @@ __device__ __forceinline__ uint32_t issue_chunks_split(uint32_t d_tmem, uint64_t
       "and.b32 t, c, 1;\n"
       "mul.wide.u32 t64, t, 4;\n"
       "add.s64 off, off, t64;\n"
-      "add.s64 a, off, %2;\n"
-      "add.s64 l, off, %3;\n"
+      "add.s64 a, off, %3;\n"
+      "add.s64 l, off, %4;\n"
       "add.s64 a1, a, 2;\n"
       "add.s64 l1, l, 2;\n"
       "SPART_LOOP:\n"
-      "and.b32 stage, %0, 3;\n"
-      "shr.u32 par, %0, 2;\n"
-      "and.b32 par, par, 1;\n"
-      "shl.b32 t, stage, 3;\n"
-      "add.u32 fb, %5, t;\n"
-      "add.u32 eb, %6, t;\n"
+      "shl.b32 t, %0, 3;\n"
+      "add.u32 fb, %6, t;\n"
+      "add.u32 eb, %7, t;\n"
       "mov.u32 spins, 0;\n"
       "SCHUNK_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 pw, [fb], par;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 pw, [fb], %1;\n"
       "@pw bra SCHUNK_READY;\n"
       "add.u32 spins, spins, 1;\n"
       "setp.gt.u32 p, spins, 4000000;\n"
@@ -365,47 +381,50 @@ __device__ __forceinline__ uint32_t issue_chunks_split(uint32_t d_tmem, uint64_t
       "bra SCHUNK_WAIT;\n"
       "SCHUNK_READY:\n"
       "tcgen05.fence::after_thread_sync;\n"
-      "mul.wide.u32 b, stage, 1024;\n"
-      "add.s64 b, b, %4;\n"
+      "mul.wide.u32 b, %0, 1024;\n"
+      "add.s64 b, b, %5;\n"
       "add.s64 b1, b, 2;\n"
       "setp.eq.u32 p, part, 0;\n"
       "@!p bra SLO_IMAGE;\n"
-      "@e tcgen05.mma.cta_group::1.kind::f16 [%1], a, b, %9, pacc;\n"
-      "@e tcgen05.mma.cta_group::1.kind::f16 [%1], l, b, %9, pt;\n"
-      "@e tcgen05.mma.cta_group::1.kind::f16 [%1], a1, b1, %9, pt;\n"
-      "@e tcgen05.mma.cta_group::1.kind::f16 [%1], l1, b1, %9, pt;\n"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%2], a, b, %10, pacc;\n"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%2], l, b, %10, pt;\n"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%2], a1, b1, %10, pt;\n"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%2], l1, b1, %10, pt;\n"
       "bra SPART_DONE;\n"
       "SLO_IMAGE:\n"
-      "@e tcgen05.mma.cta_group::1.kind::f16 [%1], a, b, %9, pt;\n"
-      "@e tcgen05.mma.cta_group::1.kind::f16 [%1], a1, b1, %9, pt;\n"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%2], a, b, %10, pt;\n"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%2], a1, b1, %10, pt;\n"
       "SPART_DONE:\n"
       "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [eb];\n"
       "setp.eq.b32 pacc, 0, 0;\n"
       "add.u32 %0, %0, 1;\n"
+      "setp.eq.u32 p, %0, " VIPNERF_STR(VIPNERF_SINGLE_STAGES) ";\n"
+      "@p mov.u32 %0, 0;\n"
+      "@p xor.b32 %1, %1, 1;\n"
       "add.u32 part, part, 1;\n"
       "setp.lt.u32 p, part, 2;\n"
       "@p bra SPART_LOOP;\n"
       "add.u32 c, c, 1;\n"
-      "setp.lt.u32 p, c, %7;\n"
+      "setp.lt.u32 p, c, %8;\n"
       "@p bra SCHUNK_LOOP;\n"
       "}\n"
-      : "+r"(q)
+      : "+r"(rs.stage), "+r"(rs.phase)
       : "r"(d_tmem), "l"(a_hi_desc), "l"(a_lo_desc), "l"(w_desc0), "r"(bar_full0), "r"(bar_empty0), "r"(n_chunks),
         "r"(first_acc), "r"(idesc)
       : "memory");
-  return q;
 }
-__device__ __forceinline__ uint32_t issue_chunks_split_pair(uint32_t d_tmem, uint64_t a_hi_desc, uint64_t a_lo_desc, uint64_t w_desc0,
-        uint32_t bar_full0, uint32_t bar_empty0, uint32_t q, uint32_t n_chunks, uint32_t first_acc, uint32_t idesc) {
+__device__ __forceinline__ void issue_chunks_split_pair(RingState& rs, uint32_t d_tmem, uint64_t a_hi_desc, uint64_t a_lo_desc,
+        uint64_t w_desc0, uint32_t bar_full0, uint32_t bar_empty0, uint32_t n_chunks, uint32_t first_acc,
+        uint32_t idesc) {
   asm volatile(
       "{\n"
       ".reg .pred p, pw, e, pacc, pt;\n"
-      ".reg .b32 c, stage, par, fb, eb, t, spins, part;\n"
+      ".reg .b32 c, fb, eb, t, spins, part;\n"
       ".reg .b64 a, l, b, a1, l1, b1, t64, off;\n"
       ".reg .b16 mc;\n"
       "mov.b16 mc, 3;\n"
       "mov.u32 c, 0;\n"
-      "setp.ne.b32 pacc, %8, 0;\n"
+      "setp.ne.b32 pacc, %9, 0;\n"
       "setp.eq.b32 pt, 0, 0;\n"
       "elect.sync _|e, 0xffffffff;\n"
       "SCHUNK_LOOP:\n"
@@ -415,20 +434,17 @@ __device__ __forceinline__ uint32_t issue_chunks_split_pair(uint32_t d_tmem, uin
       "and.b32 t, c, 1;\n"
       "mul.wide.u32 t64, t, 4;\n"
       "add.s64 off, off, t64;\n"
-      "add.s64 a, off, %2;\n"
-      "add.s64 l, off, %3;\n"
+      "add.s64 a, off, %3;\n"
+      "add.s64 l, off, %4;\n"
       "add.s64 a1, a, 2;\n"
       "add.s64 l1, l, 2;\n"
       "SPART_LOOP:\n"
-      "and.b32 stage, %0, 7;\n"
-      "shr.u32 par, %0, 3;\n"
-      "and.b32 par, par, 1;\n"
-      "shl.b32 t, stage, 3;\n"
-      "add.u32 fb, %5, t;\n"
-      "add.u32 eb, %6, t;\n"
+      "shl.b32 t, %0, 3;\n"
+      "add.u32 fb, %6, t;\n"
+      "add.u32 eb, %7, t;\n"
       "mov.u32 spins, 0;\n"
       "SCHUNK_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 pw, [fb], par;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 pw, [fb], %1;\n"
       "@pw bra SCHUNK_READY;\n"
       "add.u32 spins, spins, 1;\n"
       "setp.gt.u32 p, spins, 4000000;\n"
@@ -436,57 +452,56 @@ __device__ __forceinline__ uint32_t issue_chunks_split_pair(uint32_t d_tmem, uin
       "bra SCHUNK_WAIT;\n"
       "SCHUNK_READY:\n"
       "tcgen05.fence::after_thread_sync;\n"
-      "mul.wide.u32 b, stage, 512;\n"
-      "add.s64 b, b, %4;\n"
+      "mul.wide.u32 b, %0, 512;\n"
+      "add.s64 b, b, %5;\n"
       "add.s64 b1, b, 2;\n"
       "setp.eq.u32 p, part, 0;\n"
       "@!p bra SLO_IMAGE;\n"
-      "@e tcgen05.mma.cta_group::2.kind::f16 [%1], a, b, %9, pacc;\n"
-      "@e tcgen05.mma.cta_group::2.kind::f16 [%1], l, b, %9, pt;\n"
-      "@e tcgen05.mma.cta_group::2.kind::f16 [%1], a1, b1, %9, pt;\n"
-      "@e tcgen05.mma.cta_group::2.kind::f16 [%1], l1, b1, %9, pt;\n"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%2], a, b, %10, pacc;\n"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%2], l, b, %10, pt;\n"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%2], a1, b1, %10, pt;\n"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%2], l1, b1, %10, pt;\n"
       "bra SPART_DONE;\n"
       "SLO_IMAGE:\n"
-      "@e tcgen05.mma.cta_group::2.kind::f16 [%1], a, b, %9, pt;\n"
-      "@e tcgen05.mma.cta_group::2.kind::f16 [%1], a1, b1, %9, pt;\n"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%2], a, b, %10, pt;\n"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%2], a1, b1, %10, pt;\n"
       "SPART_DONE:\n"
       "@e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [eb], mc;\n"
       "setp.eq.b32 pacc, 0, 0;\n"
       "add.u32 %0, %0, 1;\n"
+      "setp.eq.u32 p, %0, " VIPNERF_STR(VIPNERF_PAIR_STAGES) ";\n"
+      "@p mov.u32 %0, 0;\n"
+      "@p xor.b32 %1, %1, 1;\n"
       "add.u32 part, part, 1;\n"
       "setp.lt.u32 p, part, 2;\n"
       "@p bra SPART_LOOP;\n"
       "add.u32 c, c, 1;\n"
-      "setp.lt.u32 p, c, %7;\n"
+      "setp.lt.u32 p, c, %8;\n"
       "@p bra SCHUNK_LOOP;\n"
       "}\n"
-      : "+r"(q)
+      : "+r"(rs.stage), "+r"(rs.phase)
       : "r"(d_tmem), "l"(a_hi_desc), "l"(a_lo_desc), "l"(w_desc0), "r"(bar_full0), "r"(bar_empty0), "r"(n_chunks),
         "r"(first_acc), "r"(idesc)
       : "memory");
-  return q;
 }
-// Weight producer loop of one layer run (`n` consecutive chunks of `bytes` each, `stride` bytes apart in the packed
+// Weight producer loop of one run of `n` consecutive chunks (`bytes` each, `stride` bytes apart in the packed
 // stream), hand-written in PTX for the same reason as issue_chunks: wait for the ring stage to be free, arm its full
 // barrier with the byte count, start the bulk copy (TMA engine), advance.  Executed by ONE lane.  Single-CTA variant.
-__device__ __forceinline__ uint32_t produce_chunks(const uint8_t* src, uint32_t bytes, uint32_t stride, uint32_t n,
-                                                   uint32_t q, uint32_t bar_full0, uint32_t bar_empty0,
-                                                   uint32_t w_smem0, uint32_t& wait_cycles) {
+__device__ __forceinline__ void produce_chunks(RingState& rs, const uint8_t* src, uint32_t bytes, uint32_t stride,
+                                               uint32_t n, uint32_t bar_full0, uint32_t bar_empty0, uint32_t w_smem0) {
   asm volatile(
       "{\n"
       ".reg .pred p, pw;\n"
-      ".reg .b32 c, stage, par, fb, eb, t, dst, spins, c0, c1;\n"
-      ".reg .b64 src;\n"
+      ".reg .b32 c, fb, eb, t, dst, spins, par, c0, c1;\n"
+      ".reg .b64 src, st64;\n"
       "mov.u32 c, 0;\n"
-      "mov.u64 src, %1;\n"
+      "mov.u64 src, %3;\n"
+      "cvt.u64.u32 st64, %5;\n"
       "PROD_LOOP:\n"
-      "and.b32 stage, %0, 3;\n"
-      "shr.u32 par, %0, 2;\n"
-      "and.b32 par, par, 1;\n"
-      "xor.b32 par, par, 1;\n"
-      "shl.b32 t, stage, 3;\n"
-      "add.u32 fb, %6, t;\n"
-      "add.u32 eb, %7, t;\n"
+      "xor.b32 par, %1, 1;\n"
+      "shl.b32 t, %0, 3;\n"
+      "add.u32 fb, %7, t;\n"
+      "add.u32 eb, %8, t;\n"
       "mov.u32 spins, 0;\n"
       "mov.u32 c0, %clock;\n"
       "PROD_WAIT:\n"
@@ -500,47 +515,41 @@ __device__ __forceinline__ uint32_t produce_chunks(const uint8_t* src, uint32_t 
       "mov.u32 c1, %clock;\n"
       "sub.u32 c1, c1, c0;\n"
       "add.u32 %2, %2, c1;\n"
-      "mbarrier.arrive.expect_tx.shared::cta.b64 _, [fb], %3;\n"
-      "mad.lo.u32 dst, stage, 16384, %8;\n"
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [dst], [src], %3, [fb];\n"
-      "cvt.u64.u32 %1, %4;\n"
-      "add.u64 src, src, %1;\n"
+      "mbarrier.arrive.expect_tx.shared::cta.b64 _, [fb], %4;\n"
+      "mad.lo.u32 dst, %0, 16384, %9;\n"
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [dst], [src], %4, [fb];\n"
+      "add.u64 src, src, st64;\n"
       "add.u32 %0, %0, 1;\n"
+      "setp.eq.u32 p, %0, " VIPNERF_STR(VIPNERF_SINGLE_STAGES) ";\n"
+      "@p mov.u32 %0, 0;\n"
+      "@p xor.b32 %1, %1, 1;\n"
       "add.u32 c, c, 1;\n"
-      "setp.lt.u32 p, c, %5;\n"
+      "setp.lt.u32 p, c, %6;\n"
       "@p bra PROD_LOOP;\n"
       "}\n"
-      : "+r"(q), "+l"(src), "+r"(wait_cycles)
-      : "r"(bytes), "r"(stride), "r"(n), "r"(bar_full0), "r"(bar_empty0), "r"(w_smem0)
+      : "+r"(rs.stage), "+r"(rs.phase), "+r"(rs.wait_cycles)
+      : "l"(src), "r"(bytes), "r"(stride), "r"(n), "r"(bar_full0), "r"(bar_empty0), "r"(w_smem0)
       : "memory");
-  return q;
 }
 // CTA-pair variant.  The weight stream is addressed through a 2-D tensor map (rows of 64 bytes; the box is this CTA's
 // half of a chunk's rows) so that the copy can be a cp.async.bulk.tensor with .cta_group::2, whose complete_tx may
 // signal an mbarrier of the PEER CTA: both CTAs' copies complete directly on the LEADER's w_full (`bar_full_cl0` =
 // its shared::cluster address), which the leader arms with the byte count of both halves (`expect_bytes`; 0 in the
 // peer CTA, which only copies).  No relay hop between the peer's copy and the MMA-issuing lane.
-__device__ __forceinline__ uint32_t produce_chunks_pair(const void* tmap, uint32_t row0, uint32_t row_stride, uint32_t n,
-                                                        uint32_t q, uint32_t expect_bytes, uint32_t bar_full0,
-                                                        uint32_t bar_full_cl0, uint32_t bar_empty0, uint32_t w_smem0,
-                                                        uint32_t& wait_cycles, uint32_t ts_base = 0, uint32_t* d1_total = nullptr) {
-  uint32_t d1 = 0;
+__device__ __forceinline__ void produce_chunks_pair(RingState& rs, const void* tmap, uint32_t row0, uint32_t row_stride,
+                                                    uint32_t n, uint32_t expect_bytes, uint32_t bar_full0,
+                                                    uint32_t bar_full_cl0, uint32_t bar_empty0, uint32_t w_smem0) {
   asm volatile(
       "{\n"
-      ".reg .pred p, pw, lead, pts;\n"
-      ".reg .b32 tsa, tsv;\n"
-      ".reg .b32 c, stage, par, fb, fbc, eb, t, dst, spins, c0, c1, row, zero;\n"
+      ".reg .pred p, pw, lead;\n"
+      ".reg .b32 c, par, fb, fbc, eb, t, dst, spins, c0, c1, row, zero;\n"
       "mov.u32 c, 0;\n"
       "mov.u32 zero, 0;\n"
       "mov.u32 row, %4;\n"
       "setp.ne.u32 lead, %7, 0;\n"
-      "setp.ne.b32 pts, %12, 0;\n"
       "PRODP_LOOP:\n"
-      "and.b32 stage, %0, 7;\n"
-      "shr.u32 par, %0, 3;\n"
-      "and.b32 par, par, 1;\n"
-      "xor.b32 par, par, 1;\n"
-      "shl.b32 t, stage, 3;\n"
+      "xor.b32 par, %1, 1;\n"
+      "shl.b32 t, %0, 3;\n"
       "add.u32 fb, %8, t;\n"
       "add.u32 fbc, %9, t;\n"
       "add.u32 eb, %10, t;\n"
@@ -556,49 +565,43 @@ __device__ __forceinline__ uint32_t produce_chunks_pair(const void* tmap, uint32
       "PRODP_READY:\n"
       "mov.u32 c1, %clock;\n"
       "sub.u32 c1, c1, c0;\n"
-      "add.u32 %1, %1, c1;\n"
-      "shl.b32 tsa, stage, 2;\n"
-      "add.u32 tsa, tsa, %12;\n"
-
+      "add.u32 %2, %2, c1;\n"
       "@lead mbarrier.arrive.expect_tx.shared::cta.b64 _, [fb], %7;\n"
-      "mad.lo.u32 dst, stage, 8192, %11;\n"
+      "mad.lo.u32 dst, %0, 8192, %11;\n"
       "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [dst], [%3, {zero, row}], [fbc];\n"
-
       "add.u32 row, row, %5;\n"
       "add.u32 %0, %0, 1;\n"
+      "setp.eq.u32 p, %0, " VIPNERF_STR(VIPNERF_PAIR_STAGES) ";\n"
+      "@p mov.u32 %0, 0;\n"
+      "@p xor.b32 %1, %1, 1;\n"
       "add.u32 c, c, 1;\n"
       "setp.lt.u32 p, c, %6;\n"
       "@p bra PRODP_LOOP;\n"
       "}\n"
-      : "+r"(q), "+r"(wait_cycles), "+r"(d1)
+      : "+r"(rs.stage), "+r"(rs.phase), "+r"(rs.wait_cycles)
       : "l"(tmap), "r"(row0), "r"(row_stride), "r"(n), "r"(expect_bytes), "r"(bar_full0), "r"(bar_full_cl0),
-        "r"(bar_empty0), "r"(w_smem0), "r"(ts_base)
+        "r"(bar_empty0), "r"(w_smem0)
       : "memory");
-  if (d1_total) *d1_total += d1;
-  return q;
 }
-// The bias chunk of a layer: ONE accumulating MMA - A = the last 16 columns of the encoding k-block (column 63 is the
-// constant 1), B = the second K=16 step of the chunk (its column 31 holds the bias) - then the stage-release commit.
-__device__ __forceinline__ uint32_t issue_bias_chunk(uint32_t d_tmem, uint64_t a_desc, uint64_t w_desc0, uint32_t bar_full0,
-        uint32_t bar_empty0, uint32_t q, uint32_t idesc) {
+// The bias chunk of a layer: ONE accumulating MMA - A = the all-ones block, B = the second K=16 step of the chunk
+// (its column 31 holds the bias) - then the stage-release commit.
+__device__ __forceinline__ void issue_bias_chunk(RingState& rs, uint32_t d_tmem, uint64_t a_desc, uint64_t w_desc0,
+        uint32_t bar_full0, uint32_t bar_empty0, uint32_t idesc) {
   asm volatile(
       "{\n"
       ".reg .pred p, pw, e, pt;\n"
-      ".reg .b32 stage, par, fb, eb, t, spins;\n"
+      ".reg .b32 fb, eb, t, spins;\n"
       ".reg .b64 b;\n"
       ".reg .b16 mc;\n"
       "mov.b16 mc, 3;\n"
       "setp.eq.b32 pt, 0, 0;\n"
       "elect.sync _|e, 0xffffffff;\n"
-      "and.b32 stage, %0, 3;\n"
-      "shr.u32 par, %0, 2;\n"
-      "and.b32 par, par, 1;\n"
-      "shl.b32 t, stage, 3;\n"
-      "add.u32 fb, %4, t;\n"
-      "add.u32 eb, %5, t;\n"
+      "shl.b32 t, %0, 3;\n"
+      "add.u32 fb, %5, t;\n"
+      "add.u32 eb, %6, t;\n"
       "mov.u32 spins, 0;\n"
       "BIAS_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 pw, [fb], par;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 pw, [fb], %1;\n"
       "@pw bra BIAS_READY;\n"
       "add.u32 spins, spins, 1;\n"
       "setp.gt.u32 p, spins, 4000000;\n"
@@ -606,40 +609,39 @@ __device__ __forceinline__ uint32_t issue_bias_chunk(uint32_t d_tmem, uint64_t a
       "bra BIAS_WAIT;\n"
       "BIAS_READY:\n"
       "tcgen05.fence::after_thread_sync;\n"
-      "mul.wide.u32 b, stage, 1024;\n"
-      "add.s64 b, b, %3;\n"
+      "mul.wide.u32 b, %0, 1024;\n"
+      "add.s64 b, b, %4;\n"
       "add.s64 b, b, 2;\n"
-      "@e tcgen05.mma.cta_group::1.kind::f16 [%1], %2, b, %6, pt;\n"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%2], %3, b, %7, pt;\n"
       "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [eb];\n"
       "add.u32 %0, %0, 1;\n"
+      "setp.eq.u32 p, %0, " VIPNERF_STR(VIPNERF_SINGLE_STAGES) ";\n"
+      "@p mov.u32 %0, 0;\n"
+      "@p xor.b32 %1, %1, 1;\n"
       "}\n"
-      : "+r"(q)
+      : "+r"(rs.stage), "+r"(rs.phase)
       : "r"(d_tmem), "l"(a_desc), "l"(w_desc0), "r"(bar_full0), "r"(bar_empty0), "r"(idesc)
       : "memory");
-  return q;
 }
-__device__ __forceinline__ uint32_t issue_bias_chunk_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t w_desc0, uint32_t bar_full0,
-        uint32_t bar_empty0, uint32_t q, uint32_t idesc, uint32_t skip_wait = 0) {
+__device__ __forceinline__ void issue_bias_chunk_pair(RingState& rs, uint32_t d_tmem, uint64_t a_desc, uint64_t w_desc0,
+        uint32_t bar_full0, uint32_t bar_empty0, uint32_t idesc, uint32_t skip_wait = 0) {
   asm volatile(
       "{\n"
       ".reg .pred p, pw, e, pt, pskip;\n"
-      ".reg .b32 stage, par, fb, eb, t, spins;\n"
+      ".reg .b32 fb, eb, t, spins;\n"
       ".reg .b64 b;\n"
       ".reg .b16 mc;\n"
       "mov.b16 mc, 3;\n"
       "setp.eq.b32 pt, 0, 0;\n"
       "elect.sync _|e, 0xffffffff;\n"
-      "and.b32 stage, %0, 7;\n"
-      "shr.u32 par, %0, 3;\n"
-      "and.b32 par, par, 1;\n"
-      "shl.b32 t, stage, 3;\n"
-      "add.u32 fb, %4, t;\n"
-      "add.u32 eb, %5, t;\n"
+      "shl.b32 t, %0, 3;\n"
+      "add.u32 fb, %5, t;\n"
+      "add.u32 eb, %6, t;\n"
       "mov.u32 spins, 0;\n"
-      "setp.ne.b32 pskip, %7, 0;\n"
+      "setp.ne.b32 pskip, %8, 0;\n"
       "@pskip bra BIAS_READY;\n"
       "BIAS_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 pw, [fb], par;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 pw, [fb], %1;\n"
       "@pw bra BIAS_READY;\n"
       "add.u32 spins, spins, 1;\n"
       "setp.gt.u32 p, spins, 4000000;\n"
@@ -647,17 +649,19 @@ __device__ __forceinline__ uint32_t issue_bias_chunk_pair(uint32_t d_tmem, uint6
       "bra BIAS_WAIT;\n"
       "BIAS_READY:\n"
       "tcgen05.fence::after_thread_sync;\n"
-      "mul.wide.u32 b, stage, 512;\n"
-      "add.s64 b, b, %3;\n"
+      "mul.wide.u32 b, %0, 512;\n"
+      "add.s64 b, b, %4;\n"
       "add.s64 b, b, 2;\n"
-      "@e tcgen05.mma.cta_group::2.kind::f16 [%1], %2, b, %6, pt;\n"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%2], %3, b, %7, pt;\n"
       "@e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [eb], mc;\n"
       "add.u32 %0, %0, 1;\n"
+      "setp.eq.u32 p, %0, " VIPNERF_STR(VIPNERF_PAIR_STAGES) ";\n"
+      "@p mov.u32 %0, 0;\n"
+      "@p xor.b32 %1, %1, 1;\n"
       "}\n"
-      : "+r"(q)
+      : "+r"(rs.stage), "+r"(rs.phase)
       : "r"(d_tmem), "l"(a_desc), "l"(w_desc0), "r"(bar_full0), "r"(bar_empty0), "r"(idesc), "r"(skip_wait)
       : "memory");
-  return q;
 }
 __device__ __forceinline__ void umma_commit_elect(uint32_t bar) {
   asm volatile(
@@ -677,6 +681,16 @@ __device__ __forceinline__ void umma_commit_elect_pair(uint32_t bar) {  // arriv
 __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
   return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
          (2ull << 61);
+}
+// Descriptor of the all-ones A operand of the bias chunks (128 rows x K=16, SWIZZLE_NONE: 8-row x 16-byte core
+// matrices).  Every element is 1.0, so ONE 128-byte core matrix serves all of them through zero leading / stride
+// offsets; the VIPNERF_ONES_4K build lays the 16 x 2 core matrices out conventionally (LBO 128 B, SBO 256 B).
+__device__ __forceinline__ uint64_t make_desc_ones(uint32_t smem_addr) {
+#ifdef VIPNERF_ONES_4K
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(256 >> 4) << 32) | (1ull << 46);
+#else
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 46);
+#endif
 }
 // K-major SWIZZLE_64B descriptor of a weight chunk: 64-byte rows, SBO = 512 B (8 rows), layout type 4.
 __device__ __forceinline__ uint64_t make_desc_sw64(uint32_t smem_addr) {
@@ -831,10 +845,11 @@ __device__ __forceinline__ void sincos_octave(float t_hi, float t_lo, int k, flo
   }
 }
 
-// Row `row` of the slot's encoding buffer <- bf16(gamma(point)), 64 columns (63 + the constant 1).
-// Column order of PositionalEncoder.encode (VipNeRF01.py:439-448): x(3), then per octave sin(3), cos(3).
+// bf16(gamma(point)), 64 columns (63 + the constant 1), packed two per word: enc[0..31] (BF16X3: enc[32..63] = the
+// residuals).  Column order of PositionalEncoder.encode (VipNeRF01.py:439-448): x(3), then per octave sin(3), cos(3).
+// Column 63 is the constant 1 that carries the biases of M0 / M5 through the tensor core (layout.cuh).
 template <bool kSplit3>
-__device__ __forceinline__ void write_point_encoding(uint8_t* smem, int slot, int row, float x, float y, float z) {
+__device__ __forceinline__ void compute_point_encoding(float x, float y, float z, uint32_t* enc) {
   float v[64];
   v[0] = x; v[1] = y; v[2] = z;
   const float p[3] = {x, y, z};
@@ -845,22 +860,23 @@ __device__ __forceinline__ void write_point_encoding(uint8_t* smem, int slot, in
 #pragma unroll
     for (int k = 0; k < kLPts; ++k) sincos_octave<kSplit3>(t_hi, t_lo, k, v[3 + 6 * k + a], v[6 + 6 * k + a]);
   }
-  v[63] = 1.f;  // constant-one column: carries the layer biases through the tensor core (layout.cuh)
-  const uint32_t hi_base = smem_u32(smem + kOffPe + (kSplit3 ? 0 : slot) * kKBlockBytes) + row * 128;
-  const uint32_t lo_base = smem_u32(smem + kOffPe + kKBlockBytes) + row * 128;
+  v[63] = 1.f;
+#pragma unroll
+  for (int q = 0; q < 32; ++q) {
+    enc[q] = pack_bf16(v[2 * q], v[2 * q + 1]);
+    if (kSplit3) enc[32 + q] = pack_bf16_residual(v[2 * q], v[2 * q + 1], enc[q]);
+  }
+}
+// Row `row` of k-block 0 of the slot's activation buffer <- the packed encoding (K-major SWIZZLE_128B).
+template <bool kSplit3>
+__device__ __forceinline__ void store_point_encoding(uint8_t* smem, int slot, int row, const uint32_t* enc) {
+  const uint32_t hi_base = smem_u32(smem + kOffA + (kSplit3 ? 0 : slot) * kABytes) + row * 128;
+  const uint32_t lo_base = smem_u32(smem + kOffA + kABytes) + row * 128;
 #pragma unroll
   for (int ch = 0; ch < 8; ++ch) {
-    uint32_t w[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) w[q] = pack_bf16(v[8 * ch + 2 * q], v[8 * ch + 2 * q + 1]);
     const uint32_t off = (uint32_t)((ch ^ (row & 7)) << 4);
-    st_shared_v4(hi_base + off, w[0], w[1], w[2], w[3]);
-    if (kSplit3) {
-      uint32_t r[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) r[q] = pack_bf16_residual(v[8 * ch + 2 * q], v[8 * ch + 2 * q + 1], w[q]);
-      st_shared_v4(lo_base + off, r[0], r[1], r[2], r[3]);
-    }
+    st_shared_v4(hi_base + off, enc[4 * ch], enc[4 * ch + 1], enc[4 * ch + 2], enc[4 * ch + 3]);
+    if (kSplit3) st_shared_v4(lo_base + off, enc[32 + 4 * ch], enc[33 + 4 * ch], enc[34 + 4 * ch], enc[35 + 4 * ch]);
   }
 }
 
@@ -968,12 +984,32 @@ __device__ __forceinline__ void view_epilogue(uint32_t taddr, const float* vb_ro
   unpack_f32x2(o23, o[2], o[3]);
 }
 
+// The MMA steps of one tile, in issue order.  The skip layer M5 is two steps: its h4 part (K = 256 over the whole
+// activation buffer; weight chunks 2..9 of the layer) and, once that has retired and the epilogue group has put the
+// encoding back into k-block 0, its encoding part (K = 64, accumulating; chunks 0..1, carries the bias through the
+// constant-one column).  Every step ends with a d_ready commit and starts with an a_ready wait.
+constexpr int kNumSteps = 11;
+struct StepDesc {
+  int layer;            // matrix layer M0..M9 (layout.cuh)
+  uint32_t first_chunk; // first weight chunk of the layer's stream used by the step
+  uint32_t n_chunks;    // chunks multiplied against the activation buffer from k-block 0 on
+  uint32_t accumulate;  // 0: the first MMA overwrites the accumulator
+  bool bias_chunk;      // followed by the layer's bias chunk (all-ones A operand)
+};
+__device__ __forceinline__ StepDesc step_desc(int st) {
+  if (st == 0) return {0, 0, 2, 0, false};
+  if (st == 5) return {5, 2, 8, 0, false};
+  if (st == 6) return {5, 0, 2, 1, false};
+  const int l = st < 5 ? st : st - 1;
+  return {l, 0, 8, 0, layer_has_bias_chunk(l)};
+}
+
 // ------------------------------------------------------------------------------------------ the kernel
 template <bool kSplit3, bool kFused, bool kProf, bool kPair>
 __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const __grid_constant__ TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr int kSlots = kSplit3 ? 1 : 2;
-  constexpr int kStages = kPair ? 8 : 4;
+  constexpr int kStages = kPair ? kPairStages : kSingleStages;
   constexpr uint32_t kStageBytes = kPair ? 8192 : 16384;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t cta_rank = kPair ? cluster_ctarank() : 0;   // 0 = leader of the CTA pair (issues the MMAs)
@@ -1043,7 +1079,16 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const __grid_const
       long long c_enc = 0, c_vb = 0, c_wait = 0, c_epi = 0, c_view = 0, c_hook = 0;
       const long long c_begin = kProf ? clock64() : 0;
 
-      // Sample position of this thread's row of item `it` and its encoding -> the slot's encoding buffer
+      // the all-ones operand of the bias chunks; written (and fenced with the first encoding) by group 0, whose first
+      // a_ready precedes every MMA of the CTA pair
+      if (slot == 0) {
+        uint32_t* ones = reinterpret_cast<uint32_t*>(smem + kOffOnes);
+        for (int i = row; i < (int)(kOnesBytes / 4); i += 128) ones[i] = 0x3F803F80u;   // two bf16 1.0
+      }
+      // This row's packed point encoding: computed ahead of time (during M6 of the previous tile), stored into k-block 0
+      // at the tile boundary and once more for the encoding part of the skip layer M5.
+      uint32_t enc[kSplit3 ? 64 : 32];
+      // Sample position of this thread's row of item `it` and its encoding -> enc
       // (VipNeRF01.py:105-107, :173-203, :439-448).
       auto encode_item = [&](int it) {
         const long long t0 = kProf ? clock64() : 0;
@@ -1064,8 +1109,14 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const __grid_const
         const float px = fadd(p.rp.pts_o[3 * ray + 0], fmul(p.rp.pts_d[3 * ray + 0], zv));
         const float py = fadd(p.rp.pts_o[3 * ray + 1], fmul(p.rp.pts_d[3 * ray + 1], zv));
         const float pz = fadd(p.rp.pts_o[3 * ray + 2], fmul(p.rp.pts_d[3 * ray + 2], zv));
-        write_point_encoding<kSplit3>(smem, slot, row, px, py, pz);
+        compute_point_encoding<kSplit3>(px, py, pz, enc);
         if (kProf) c_enc += clock64() - t0;
+      };
+      // enc -> k-block 0 of the slot's (idle) activation buffer, visible to the tensor core, then a_ready
+      auto publish_encoding = [&]() {
+        store_point_encoding<kSplit3>(smem, slot, row, enc);
+        fence_proxy_async();
+        arrive_a_ready();
       };
       // View-direction columns of views_linears.0 (+ bias) for the (at most two) rays of item `it`, fp32:
       // vb[rs][c] = b[c] + sum_j W[c][256 + j] * gamma(view_dir[ray_first + rs])[j]   (VipNeRF01.py:576-579)
@@ -1125,8 +1176,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const __grid_const
       uint32_t d_parity = 0;
       if (work.n_items > 0) {
         encode_item(0);
-        fence_proxy_async();
-        arrive_a_ready();
+        publish_encoding();
       }
       for (int it = 0; it < work.n_items; ++it) {
         const int pi = work.pass_of(it);
@@ -1145,6 +1195,15 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const __grid_const
         float sigma_lin = 0.f;
 #pragma unroll 1
         for (int l = 0; l < 9; ++l) {
+          if (l == 5) {
+            // skip layer M5 = h4 part (K=256, issued on a_ready(M4's epilogue)) + encoding part (K=64, carries the bias):
+            // when the h4 part has retired, k-block 0 is free to take the encoding back
+            const long long tw = kProf ? clock64() : 0;
+            mbar_wait(bar(kBarDReady + slot), d_parity);
+            d_parity ^= 1;
+            if (kProf) c_wait += clock64() - tw;
+            publish_encoding();
+          }
           const long long t0 = kProf ? clock64() : 0;
           mbar_wait(bar(kBarDReady + slot), d_parity);
           d_parity ^= 1;
@@ -1159,8 +1218,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const __grid_const
           arrive_a_ready();
           if (kProf) c_epi += clock64() - t1;
           if (l == 5) {
-            // M5 has retired: the encoding buffer is free, and so are vb/pev (the previous tile's M9 epilogue
-            // is long done).  Use the time this slot's M6 spends on the tensor pipe.
+            // M5 has retired: enc is free for the next tile's encoding, and so are vb/pev (the previous tile's M9
+            // epilogue is long done).  Use the time this slot's M6 spends on the tensor pipe.
             view_bias_item(it);
             if (has_next && depths_ready(it + 1)) { encode_item(it + 1); next_encoded = true; }
           }
@@ -1199,8 +1258,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const __grid_const
         }
         if (has_next) {
           if (!next_encoded) { wait_depths(it + 1); encode_item(it + 1); }
-          fence_proxy_async();
-          arrive_a_ready();
+          publish_encoding();   // the activation buffer is idle: M9 has retired
         }
       }
       tc_fence_before();
@@ -1212,6 +1270,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const __grid_const
     }
   } else if (warp == 8) {
     // =================================================================== weight producer
+    // Streams the weight chunks of every (tile, step, slot) in the order the MMA issuer consumes them (StepDesc).
     if (lane == 0 && p.debug_noring != 1) {
       WorkList<kFused, kPair> work0(p, cta_group_idx * kSlots + 0, n_slots_total, (int)cta_rank);
       WorkList<kFused, kPair> work1(p, cta_group_idx * kSlots + (kSlots - 1), n_slots_total, (int)cta_rank);
@@ -1219,60 +1278,58 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const __grid_const
       // pair mode: this CTA streams its half of every chunk's rows; both CTAs' copies complete on the leader's w_full
       const uint32_t full_cluster0 = kPair ? map_to_cta(bar(kBarWFull), 0) : 0;
       const long long c_prod_begin = kProf ? clock64() : 0;
-      uint32_t q = 0, prod_wait = 0, prod_d1 = 0;
+      RingState ring;
+      constexpr uint32_t kImg = kSplit3 ? 2 : 1;   // ring items per chunk (BF16X3: hi image, lo image)
       for (int it = 0; it < n_max; ++it) {
-        for (int l = 0; l < kNumMatLayers; ++l) {
+        for (int st = 0; st < kNumSteps; ++st) {
           for (int s = 0; s < kSlots; ++s) {
             const WorkList<kFused, kPair>& w = s == 0 ? work0 : work1;
             if (it >= w.n_items) continue;
-            const uint32_t chunk_bytes = layer_chunk_bytes(l);
-            const uint32_t bytes = kPair ? chunk_bytes / 2 : chunk_bytes;
-            const uint8_t* src = p.pass[w.pass_of(it)].packed + kSmallBytes +
-                                 (size_t)tc_layer_byte_offset(l) * (kSplit3 ? 2 : 1) + (kPair ? cta_rank * bytes : 0);
-            const uint32_t n_chunks = layer_stream_chunks(l) * (kSplit3 ? 2 : 1);
+            const StepDesc sd = step_desc(st);
+            const uint32_t chunk_bytes = layer_chunk_bytes(sd.layer);
+            const uint32_t n_items = (sd.n_chunks + (sd.bias_chunk ? 1 : 0)) * kImg;
+            const uint32_t byte0 = (uint32_t)tc_layer_byte_offset(sd.layer) * kImg + sd.first_chunk * chunk_bytes * kImg;
             if (kPair) {
-              // rows of 64 bytes: the chunk images of a layer are consecutive, this CTA takes rows [rank*n/2, +n/2)
-              const uint32_t rows = (uint32_t)layer_n(l);
-              const uint32_t row0 = (uint32_t)(tc_layer_byte_offset(l) * (kSplit3 ? 2 : 1)) / 64 + cta_rank * (rows / 2);
-              q = produce_chunks_pair(&p.wmap[w.pass_of(it)][l == 9 ? 1 : 0], row0, rows, n_chunks, q,
-                                      cta_rank == 0 ? (p.debug_noring == 3 ? chunk_bytes / 8 : chunk_bytes) : 0, bar(kBarWFull), full_cluster0, bar(kBarWEmpty),
-                                      smem_u32(smem + kOffW), prod_wait,
-                                      0, &prod_d1);
+              // rows of 64 bytes: consecutive chunk images, this CTA takes rows [rank * n/2, +n/2) of each
+              const uint32_t rows = (uint32_t)layer_n(sd.layer);
+              produce_chunks_pair(ring, &p.wmap[w.pass_of(it)][sd.layer == 9 ? 1 : 0], byte0 / 64 + cta_rank * (rows / 2),
+                                  rows, n_items,
+                                  cta_rank == 0 ? (p.debug_noring == 3 ? chunk_bytes / 8 : chunk_bytes) : 0,
+                                  bar(kBarWFull), full_cluster0, bar(kBarWEmpty), smem_u32(smem + kOffW));
             } else {
-              q = produce_chunks(src, bytes, chunk_bytes, n_chunks, q, bar(kBarWFull), bar(kBarWEmpty),
-                                 smem_u32(smem + kOffW), prod_wait);
+              produce_chunks(ring, p.pass[w.pass_of(it)].packed + kSmallBytes + byte0, chunk_bytes, chunk_bytes, n_items,
+                             bar(kBarWFull), bar(kBarWEmpty), smem_u32(smem + kOffW));
             }
           }
         }
       }
       if (kProf && p.prof != nullptr && blockIdx.x < 2) {
-        p.prof[40 + 4 * blockIdx.x] = prod_wait;
+        p.prof[40 + 4 * blockIdx.x] = ring.wait_cycles;
         p.prof[41 + 4 * blockIdx.x] = (unsigned long long)(clock64() - c_prod_begin);
-        p.prof[42 + 4 * blockIdx.x] = prod_d1;
+        p.prof[42 + 4 * blockIdx.x] = 0;
       }
     }
   } else if (warp == 9 && (!kPair || cta_rank == 0)) {
     // =================================================================== MMA issuer (warp 9 of the leader CTA)
-    // The whole warp runs the loop; one elected lane issues.  Per (tile, layer, slot) step: wait a_ready, run the
-    // PTX chunk loop(s) over the layer's A operand (encoding buffer for M0 and the first 64 columns of M5, the A
-    // buffer otherwise), commit d_ready.  In pair mode every MMA is M=256: rows 0-127 from this CTA's A buffer and
-    // TMEM, rows 128-255 from the peer's (same shared-memory / TMEM addresses), B rows split between the two.
+    // The whole warp runs the loop; one elected lane issues.  Per (tile, step, slot): wait a_ready, run the PTX chunk
+    // loop over the slot's activation buffer from k-block 0 (the encoding sits there for M0 and for the encoding part
+    // of M5), add the bias chunk, commit d_ready.  In pair mode every MMA is M=256: rows 0-127 from this CTA's
+    // buffer and TMEM, rows 128-255 from the peer's (same shared-memory / TMEM addresses), B rows split between them.
     WorkList<kFused, kPair> work0(p, cta_group_idx * kSlots + 0, n_slots_total, (int)cta_rank);
     WorkList<kFused, kPair> work1(p, cta_group_idx * kSlots + (kSlots - 1), n_slots_total, (int)cta_rank);
     const int n_max = max(work0.n_items, kSlots > 1 ? work1.n_items : 0);
-    uint32_t q = 0;
-    uint32_t a_parity0 = 0, a_parity1 = 0;
-    const uint64_t a_desc0 = make_desc(smem_u32(smem + kOffA)), pe_desc0 = make_desc(smem_u32(smem + kOffPe));
+    RingState ring;
+    uint32_t a_parity0 = 0, a_parity1 = 0, n_issued = 0;
+    const uint64_t a_desc0 = make_desc(smem_u32(smem + kOffA));
     const uint64_t w_desc0 = make_desc_sw64(smem_u32(smem + kOffW));
-    constexpr uint64_t kKBlockUnits = kKBlockBytes >> 4, kAUnits = kABytes >> 4;
-    static_assert(kKBlockUnits == 1024 && (kStageBytes >> 4) == (kPair ? 512 : 1024), "issue_chunks* assume these");
+    const uint64_t ones_desc = make_desc_ones(smem_u32(smem + kOffOnes));
+    constexpr uint64_t kAUnits = kABytes >> 4;
+    static_assert((kKBlockBytes >> 4) == 1024 && (kStageBytes >> 4) == (kPair ? 512 : 1024), "issue_chunks* assume these");
     const uint32_t bar_full0 = bar(kBarWFull), bar_empty0 = bar(kBarWEmpty);
     long long c_wait_a = 0;
-    uint32_t lane_d2 = 0;
-    uint32_t spins = 0;  // failed probes of the weight ring (prof builds report it)
     const long long c_begin = kProf ? clock64() : 0;
     for (int it = 0; it < n_max; ++it) {
-      for (int l = 0; l < kNumMatLayers; ++l) {
+      for (int st = 0; st < kNumSteps; ++st) {
 #pragma unroll
         for (int s = 0; s < kSlots; ++s) {
           const WorkList<kFused, kPair>& w = s == 0 ? work0 : work1;
@@ -1284,33 +1341,22 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const __grid_const
           }
           if (s == 0) a_parity0 ^= 1; else a_parity1 ^= 1;
           tc_fence_after();
-          const uint32_t idesc = instr_desc(layer_n(l), kPair ? 256 : 128);
+          const StepDesc sd = step_desc(st);
+          const uint32_t idesc = instr_desc(layer_n(sd.layer), kPair ? 256 : 128);
           const uint32_t d_tmem = tmem_base + (uint32_t)(s * 256);
-          const uint64_t slot_units = (kSplit3 ? 0 : s);
-          const uint64_t pe_hi = pe_desc0 + slot_units * kKBlockUnits, pe_lo = pe_desc0 + kKBlockUnits;
-          const uint64_t a_hi = a_desc0 + slot_units * kAUnits, a_lo = a_desc0 + kAUnits;
-          auto run = [&](uint64_t hi, uint64_t lo, uint32_t n, uint32_t acc) {
-            if (!kSplit3 && !kPair) q = issue_chunks(d_tmem, hi, w_desc0, bar_full0, bar_empty0, q, n, acc, idesc, spins);
-            else if (!kSplit3) q = issue_chunks_pair(d_tmem, hi, w_desc0, bar_full0, bar_empty0, q, n, acc, idesc, spins, p.debug_noring == 1,
-                                                  0, &lane_d2);
-            else if (!kPair) q = issue_chunks_split(d_tmem, hi, lo, w_desc0, bar_full0, bar_empty0, q, n, acc, idesc);
-            else q = issue_chunks_split_pair(d_tmem, hi, lo, w_desc0, bar_full0, bar_empty0, q, n, acc, idesc);
-          };
-          if (l == 0) {
-            run(pe_hi, pe_lo, 2, 0);
-          } else if (l == 5) {
-            run(pe_hi, pe_lo, 2, 0);
-            run(a_hi, a_lo, 8, 1);
-          } else {
-            run(a_hi, a_lo, 8, 0);
-          }
-          if (layer_has_bias_chunk(l)) {
-            // encoding columns 48..63 (k-block offset 96 B = 6 units) x the bias chunk; BF16X3: hi and lo images
-            // (the lo part of the constant-one column is zero, so A_lo contributes nothing and is skipped)
+          const uint64_t a_hi = a_desc0 + (kSplit3 ? 0 : s) * kAUnits, a_lo = a_desc0 + kAUnits;
+          if (!kSplit3 && !kPair) issue_chunks(ring, d_tmem, a_hi, w_desc0, bar_full0, bar_empty0, sd.n_chunks, sd.accumulate, idesc);
+          else if (!kSplit3) issue_chunks_pair(ring, d_tmem, a_hi, w_desc0, bar_full0, bar_empty0, sd.n_chunks, sd.accumulate, idesc, p.debug_noring == 1);
+          else if (!kPair) issue_chunks_split(ring, d_tmem, a_hi, a_lo, w_desc0, bar_full0, bar_empty0, sd.n_chunks, sd.accumulate, idesc);
+          else issue_chunks_split_pair(ring, d_tmem, a_hi, a_lo, w_desc0, bar_full0, bar_empty0, sd.n_chunks, sd.accumulate, idesc);
+          n_issued += sd.n_chunks;
+          if (sd.bias_chunk) {
+            // all-ones A operand x the bias chunk (second K=16 step of the chunk); BF16X3: hi and lo images
             for (int part = 0; part < (kSplit3 ? 2 : 1); ++part) {
-              q = kPair ? issue_bias_chunk_pair(d_tmem, pe_hi + 6, w_desc0, bar_full0, bar_empty0, q, idesc, p.debug_noring == 1)
-                        : issue_bias_chunk(d_tmem, pe_hi + 6, w_desc0, bar_full0, bar_empty0, q, idesc);
+              if (kPair) issue_bias_chunk_pair(ring, d_tmem, ones_desc, w_desc0, bar_full0, bar_empty0, idesc, p.debug_noring == 1);
+              else issue_bias_chunk(ring, d_tmem, ones_desc, w_desc0, bar_full0, bar_empty0, idesc);
             }
+            n_issued += 1;
           }
           if (kPair) umma_commit_elect_pair(bar(kBarDReady + s)); else umma_commit_elect(bar(kBarDReady + s));
         }
@@ -1318,9 +1364,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const __grid_const
     }
     tc_fence_before();
     if (kProf && p.prof != nullptr && blockIdx.x == 0 && lane == 0) {
-      p.prof[32] = c_wait_a; p.prof[33] = spins; p.prof[34] = (unsigned long long)(clock64() - c_begin);
-      p.prof[35] = q;
-      p.prof[36] = lane_d2;
+      p.prof[32] = c_wait_a; p.prof[33] = ring.wait_cycles; p.prof[34] = (unsigned long long)(clock64() - c_begin);
+      p.prof[35] = n_issued;
     }
   }
   if (kFused && warp >= 10 && warp - 10 < kSlots && !(p.debug_noring & 4)) {
