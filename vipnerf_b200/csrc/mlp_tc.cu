@@ -211,6 +211,7 @@ __device__ __forceinline__ void mma_chunk_split_hi(uint32_t d_tmem, uint64_t a_h
 // profiling builds report; every role keeps its own copy and advances it chunk by chunk.
 struct RingState {
   uint32_t stage = 0, phase = 0, wait_cycles = 0;
+  uint32_t ready = 0;   // MMA issuer (probe-ahead loops): the current stage's full barrier was already seen complete
 };
 
 // The MMA issue loop of one run of `n_chunks` consecutive weight chunks, hand-written in PTX so that the per-chunk
@@ -281,63 +282,79 @@ __device__ __forceinline__ void issue_chunks(RingState& rs, uint32_t d_tmem, uin
         "r"(idesc)
       : "memory");
 }
+// Probe-ahead: an mbarrier probe has ~150-200 cycles of latency even when the phase is already complete, and the
+// loop is one dependent chain (probe -> branch -> MMAs -> commit -> next probe), which alone costs more than the 256
+// tensor cycles of a chunk.  So the probe of the NEXT stage (non-blocking test_wait) is issued before the current
+// chunk's MMAs and its result consumed one iteration later (carried across calls in rs.ready - the ring position is
+// continuous across layers and slots); only a stage found incomplete falls back to the blocking try_wait loop.
+// rs.wait_cycles counts only that real waiting.
 __device__ __forceinline__ void issue_chunks_pair(RingState& rs, uint32_t d_tmem, uint64_t a_desc, uint64_t w_desc0,
         uint32_t bar_full0, uint32_t bar_empty0, uint32_t n_chunks, uint32_t first_acc, uint32_t idesc,
         uint32_t skip_wait = 0) {
   asm volatile(
       "{\n"
       ".reg .pred p, pw, e, pacc, pt, pskip;\n"
-      ".reg .b32 c, fb, eb, t, spins, c0, c1;\n"
+      ".reg .b32 c, fb, eb, t, spins, c0, c1, ns, nph, nfb;\n"
       ".reg .b64 a, b, a1, b1, t64;\n"
       ".reg .b16 mc;\n"
       "mov.b16 mc, 3;\n"
       "mov.u32 c, 0;\n"
-      "setp.ne.b32 pacc, %9, 0;\n"
+      "setp.ne.b32 pacc, %10, 0;\n"
       "setp.eq.b32 pt, 0, 0;\n"
-      "setp.ne.b32 pskip, %11, 0;\n"
+      "setp.ne.b32 pskip, %12, 0;\n"
+      "setp.ne.b32 pw, %3, 0;\n"
       "elect.sync _|e, 0xffffffff;\n"
       "CHUNK_LOOP:\n"
       "shl.b32 t, %0, 3;\n"
-      "add.u32 fb, %6, t;\n"
-      "add.u32 eb, %7, t;\n"
+      "add.u32 fb, %7, t;\n"
+      "add.u32 eb, %8, t;\n"
+      "@pskip bra CHUNK_READY;\n"
+      "@pw bra CHUNK_READY;\n"
       "mov.u32 spins, 0;\n"
       "mov.u32 c0, %clock;\n"
-      "@pskip bra CHUNK_READY;\n"
       "CHUNK_WAIT:\n"
       "mbarrier.try_wait.parity.shared::cta.b64 pw, [fb], %1;\n"
-      "@pw bra CHUNK_READY;\n"
+      "@pw bra CHUNK_WAITED;\n"
       "add.u32 spins, spins, 1;\n"
       "setp.gt.u32 p, spins, 4000000;\n"
       "@p trap;\n"
       "bra CHUNK_WAIT;\n"
-      "CHUNK_READY:\n"
+      "CHUNK_WAITED:\n"
       "mov.u32 c1, %clock;\n"
       "sub.u32 c1, c1, c0;\n"
       "add.u32 %2, %2, c1;\n"
+      "CHUNK_READY:\n"
       "tcgen05.fence::after_thread_sync;\n"
       "mul.wide.u32 b, %0, 512;\n"
-      "add.s64 b, b, %5;\n"
+      "add.s64 b, b, %6;\n"
       "shr.u32 t, c, 1;\n"
       "mul.wide.u32 a, t, 1024;\n"
       "and.b32 t, c, 1;\n"
       "mul.wide.u32 t64, t, 4;\n"
       "add.s64 a, a, t64;\n"
-      "add.s64 a, a, %4;\n"
+      "add.s64 a, a, %5;\n"
       "add.s64 a1, a, 2;\n"
       "add.s64 b1, b, 2;\n"
-      "@e tcgen05.mma.cta_group::2.kind::f16 [%3], a, b, %10, pacc;\n"
-      "@e tcgen05.mma.cta_group::2.kind::f16 [%3], a1, b1, %10, pt;\n"
+      "add.u32 ns, %0, 1;\n"
+      "mov.u32 nph, %1;\n"
+      "setp.eq.u32 p, ns, " VIPNERF_STR(VIPNERF_PAIR_STAGES) ";\n"
+      "@p mov.u32 ns, 0;\n"
+      "@p xor.b32 nph, nph, 1;\n"
+      "shl.b32 t, ns, 3;\n"
+      "add.u32 nfb, %7, t;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 pw, [nfb], nph;\n"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%4], a, b, %11, pacc;\n"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%4], a1, b1, %11, pt;\n"
       "@e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [eb], mc;\n"
       "setp.eq.b32 pacc, 0, 0;\n"
-      "add.u32 %0, %0, 1;\n"
-      "setp.eq.u32 p, %0, " VIPNERF_STR(VIPNERF_PAIR_STAGES) ";\n"
-      "@p mov.u32 %0, 0;\n"
-      "@p xor.b32 %1, %1, 1;\n"
+      "mov.u32 %0, ns;\n"
+      "mov.u32 %1, nph;\n"
       "add.u32 c, c, 1;\n"
-      "setp.lt.u32 p, c, %8;\n"
+      "setp.lt.u32 p, c, %9;\n"
       "@p bra CHUNK_LOOP;\n"
+      "selp.u32 %3, 1, 0, pw;\n"
       "}\n"
-      : "+r"(rs.stage), "+r"(rs.phase), "+r"(rs.wait_cycles)
+      : "+r"(rs.stage), "+r"(rs.phase), "+r"(rs.wait_cycles), "+r"(rs.ready)
       : "r"(d_tmem), "l"(a_desc), "l"(w_desc0), "r"(bar_full0), "r"(bar_empty0), "r"(n_chunks), "r"(first_acc),
         "r"(idesc), "r"(skip_wait)
       : "memory");
@@ -539,46 +556,58 @@ __device__ __forceinline__ void produce_chunks(RingState& rs, const uint8_t* src
 __device__ __forceinline__ void produce_chunks_pair(RingState& rs, const void* tmap, uint32_t row0, uint32_t row_stride,
                                                     uint32_t n, uint32_t expect_bytes, uint32_t bar_full0,
                                                     uint32_t bar_full_cl0, uint32_t bar_empty0, uint32_t w_smem0) {
+  // probe-ahead like issue_chunks_pair: the next stage's empty barrier is probed before this stage's copy is issued
   asm volatile(
       "{\n"
       ".reg .pred p, pw, lead;\n"
-      ".reg .b32 c, par, fb, fbc, eb, t, dst, spins, c0, c1, row, zero;\n"
+      ".reg .b32 c, par, fb, fbc, eb, t, dst, spins, c0, c1, row, zero, ns, nph, neb;\n"
       "mov.u32 c, 0;\n"
       "mov.u32 zero, 0;\n"
-      "mov.u32 row, %4;\n"
-      "setp.ne.u32 lead, %7, 0;\n"
+      "mov.u32 row, %5;\n"
+      "setp.ne.u32 lead, %8, 0;\n"
+      "setp.ne.b32 pw, %3, 0;\n"
       "PRODP_LOOP:\n"
-      "xor.b32 par, %1, 1;\n"
       "shl.b32 t, %0, 3;\n"
-      "add.u32 fb, %8, t;\n"
-      "add.u32 fbc, %9, t;\n"
-      "add.u32 eb, %10, t;\n"
+      "add.u32 fb, %9, t;\n"
+      "add.u32 fbc, %10, t;\n"
+      "add.u32 eb, %11, t;\n"
+      "@pw bra PRODP_READY;\n"
+      "xor.b32 par, %1, 1;\n"
       "mov.u32 spins, 0;\n"
       "mov.u32 c0, %clock;\n"
       "PRODP_WAIT:\n"
       "mbarrier.try_wait.parity.shared::cta.b64 pw, [eb], par;\n"
-      "@pw bra PRODP_READY;\n"
+      "@pw bra PRODP_WAITED;\n"
       "add.u32 spins, spins, 1;\n"
       "setp.gt.u32 p, spins, 4000000;\n"
       "@p trap;\n"
       "bra PRODP_WAIT;\n"
-      "PRODP_READY:\n"
+      "PRODP_WAITED:\n"
       "mov.u32 c1, %clock;\n"
       "sub.u32 c1, c1, c0;\n"
       "add.u32 %2, %2, c1;\n"
-      "@lead mbarrier.arrive.expect_tx.shared::cta.b64 _, [fb], %7;\n"
-      "mad.lo.u32 dst, %0, 8192, %11;\n"
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [dst], [%3, {zero, row}], [fbc];\n"
-      "add.u32 row, row, %5;\n"
-      "add.u32 %0, %0, 1;\n"
-      "setp.eq.u32 p, %0, " VIPNERF_STR(VIPNERF_PAIR_STAGES) ";\n"
-      "@p mov.u32 %0, 0;\n"
-      "@p xor.b32 %1, %1, 1;\n"
+      "PRODP_READY:\n"
+      "add.u32 ns, %0, 1;\n"
+      "mov.u32 nph, %1;\n"
+      "setp.eq.u32 p, ns, " VIPNERF_STR(VIPNERF_PAIR_STAGES) ";\n"
+      "@p mov.u32 ns, 0;\n"
+      "@p xor.b32 nph, nph, 1;\n"
+      "shl.b32 t, ns, 3;\n"
+      "add.u32 neb, %11, t;\n"
+      "xor.b32 par, nph, 1;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 pw, [neb], par;\n"
+      "@lead mbarrier.arrive.expect_tx.shared::cta.b64 _, [fb], %8;\n"
+      "mad.lo.u32 dst, %0, 8192, %12;\n"
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [dst], [%4, {zero, row}], [fbc];\n"
+      "add.u32 row, row, %6;\n"
+      "mov.u32 %0, ns;\n"
+      "mov.u32 %1, nph;\n"
       "add.u32 c, c, 1;\n"
-      "setp.lt.u32 p, c, %6;\n"
+      "setp.lt.u32 p, c, %7;\n"
       "@p bra PRODP_LOOP;\n"
+      "selp.u32 %3, 1, 0, pw;\n"
       "}\n"
-      : "+r"(rs.stage), "+r"(rs.phase), "+r"(rs.wait_cycles)
+      : "+r"(rs.stage), "+r"(rs.phase), "+r"(rs.wait_cycles), "+r"(rs.ready)
       : "l"(tmap), "r"(row0), "r"(row_stride), "r"(n), "r"(expect_bytes), "r"(bar_full0), "r"(bar_full_cl0),
         "r"(bar_empty0), "r"(w_smem0)
       : "memory");
@@ -623,23 +652,27 @@ __device__ __forceinline__ void issue_bias_chunk(RingState& rs, uint32_t d_tmem,
       : "r"(d_tmem), "l"(a_desc), "l"(w_desc0), "r"(bar_full0), "r"(bar_empty0), "r"(idesc)
       : "memory");
 }
+template <bool kProbe>
 __device__ __forceinline__ void issue_bias_chunk_pair(RingState& rs, uint32_t d_tmem, uint64_t a_desc, uint64_t w_desc0,
         uint32_t bar_full0, uint32_t bar_empty0, uint32_t idesc, uint32_t skip_wait = 0) {
+  if (!kProbe) rs.ready = 0;
   asm volatile(
       "{\n"
       ".reg .pred p, pw, e, pt, pskip;\n"
-      ".reg .b32 fb, eb, t, spins;\n"
+      ".reg .b32 fb, eb, t, spins, ns, nph, nfb;\n"
       ".reg .b64 b;\n"
       ".reg .b16 mc;\n"
       "mov.b16 mc, 3;\n"
       "setp.eq.b32 pt, 0, 0;\n"
       "elect.sync _|e, 0xffffffff;\n"
       "shl.b32 t, %0, 3;\n"
-      "add.u32 fb, %5, t;\n"
-      "add.u32 eb, %6, t;\n"
+      "add.u32 fb, %6, t;\n"
+      "add.u32 eb, %7, t;\n"
       "mov.u32 spins, 0;\n"
-      "setp.ne.b32 pskip, %8, 0;\n"
+      "setp.ne.b32 pskip, %9, 0;\n"
+      "setp.ne.b32 pw, %2, 0;\n"
       "@pskip bra BIAS_READY;\n"
+      "@pw bra BIAS_READY;\n"
       "BIAS_WAIT:\n"
       "mbarrier.try_wait.parity.shared::cta.b64 pw, [fb], %1;\n"
       "@pw bra BIAS_READY;\n"
@@ -650,18 +683,26 @@ __device__ __forceinline__ void issue_bias_chunk_pair(RingState& rs, uint32_t d_
       "BIAS_READY:\n"
       "tcgen05.fence::after_thread_sync;\n"
       "mul.wide.u32 b, %0, 512;\n"
-      "add.s64 b, b, %4;\n"
+      "add.s64 b, b, %5;\n"
       "add.s64 b, b, 2;\n"
-      "@e tcgen05.mma.cta_group::2.kind::f16 [%2], %3, b, %7, pt;\n"
+      "add.u32 ns, %0, 1;\n"
+      "mov.u32 nph, %1;\n"
+      "setp.eq.u32 p, ns, " VIPNERF_STR(VIPNERF_PAIR_STAGES) ";\n"
+      "@p mov.u32 ns, 0;\n"
+      "@p xor.b32 nph, nph, 1;\n"
+      "shl.b32 t, ns, 3;\n"
+      "add.u32 nfb, %6, t;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 pw, [nfb], nph;\n"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%3], %4, b, %8, pt;\n"
       "@e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [eb], mc;\n"
-      "add.u32 %0, %0, 1;\n"
-      "setp.eq.u32 p, %0, " VIPNERF_STR(VIPNERF_PAIR_STAGES) ";\n"
-      "@p mov.u32 %0, 0;\n"
-      "@p xor.b32 %1, %1, 1;\n"
+      "mov.u32 %0, ns;\n"
+      "mov.u32 %1, nph;\n"
+      "selp.u32 %2, 1, 0, pw;\n"
       "}\n"
-      : "+r"(rs.stage), "+r"(rs.phase)
+      : "+r"(rs.stage), "+r"(rs.phase), "+r"(rs.ready)
       : "r"(d_tmem), "l"(a_desc), "l"(w_desc0), "r"(bar_full0), "r"(bar_empty0), "r"(idesc), "r"(skip_wait)
       : "memory");
+  if (!kProbe) rs.ready = 0;
 }
 __device__ __forceinline__ void umma_commit_elect(uint32_t bar) {
   asm volatile(
@@ -1353,7 +1394,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const __grid_const
           if (sd.bias_chunk) {
             // all-ones A operand x the bias chunk (second K=16 step of the chunk); BF16X3: hi and lo images
             for (int part = 0; part < (kSplit3 ? 2 : 1); ++part) {
-              if (kPair) issue_bias_chunk_pair(ring, d_tmem, ones_desc, w_desc0, bar_full0, bar_empty0, idesc, p.debug_noring == 1);
+              if (kPair) issue_bias_chunk_pair<!kSplit3>(ring, d_tmem, ones_desc, w_desc0, bar_full0, bar_empty0, idesc, p.debug_noring == 1);
               else issue_bias_chunk(ring, d_tmem, ones_desc, w_desc0, bar_full0, bar_empty0, idesc);
             }
             n_issued += 1;
