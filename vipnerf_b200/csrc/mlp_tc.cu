@@ -9,8 +9,9 @@
 //   warps 4-7  epilogue group 1  (owns tile slot 1: TMEM columns [256,512), A buffer 1, encoding buffer 1)
 //   warp  8    weight producer   (one lane: cp.async.bulk 16 KiB weight chunk images -> 4-stage smem ring)
 //   warp  9    MMA issuer        (one lane: tcgen05.mma M=128 N=256 K=16, bf16 x bf16 -> fp32 in TMEM)
-//   warps 10-11 ray warps         (fused kernel: alpha compositing + hierarchical re-sampling of the rays a slot's
-//                                  tiles complete, asynchronously to the slot's next tiles)
+//   warp  10   second weight producer (CTA pairs: warps 8 / 10 take the even / odd ring stages)
+//   warp  11   ray warp          (fused kernel: alpha compositing + hierarchical re-sampling of the rays the slots'
+//                                 tiles complete, asynchronously to the slots' next tiles)
 // A "tile" is 128 consecutive sample points (rows).  A row's activations live in shared memory as bf16 in the
 // canonical K-major SWIZZLE_128B layout (four 16 KiB k-blocks of 128 rows x 64 columns); the accumulator of a
 // layer lives in the slot's 256 TMEM columns.  Per layer: the MMA warp streams the layer's weight chunks
@@ -555,7 +556,8 @@ __device__ __forceinline__ void produce_chunks(RingState& rs, const uint8_t* src
 // peer CTA, which only copies).  No relay hop between the peer's copy and the MMA-issuing lane.
 __device__ __forceinline__ void produce_chunks_pair(RingState& rs, const void* tmap, uint32_t row0, uint32_t row_stride,
                                                     uint32_t n, uint32_t expect_bytes, uint32_t bar_full0,
-                                                    uint32_t bar_full_cl0, uint32_t bar_empty0, uint32_t w_smem0) {
+                                                    uint32_t bar_full_cl0, uint32_t bar_empty0, uint32_t w_smem0,
+                                                    uint32_t stage_step) {
   // probe-ahead like issue_chunks_pair: the next stage's empty barrier is probed before this stage's copy is issued
   asm volatile(
       "{\n"
@@ -587,10 +589,10 @@ __device__ __forceinline__ void produce_chunks_pair(RingState& rs, const void* t
       "sub.u32 c1, c1, c0;\n"
       "add.u32 %2, %2, c1;\n"
       "PRODP_READY:\n"
-      "add.u32 ns, %0, 1;\n"
+      "add.u32 ns, %0, %13;\n"
       "mov.u32 nph, %1;\n"
-      "setp.eq.u32 p, ns, " VIPNERF_STR(VIPNERF_PAIR_STAGES) ";\n"
-      "@p mov.u32 ns, 0;\n"
+      "setp.ge.u32 p, ns, " VIPNERF_STR(VIPNERF_PAIR_STAGES) ";\n"
+      "@p sub.u32 ns, ns, " VIPNERF_STR(VIPNERF_PAIR_STAGES) ";\n"
       "@p xor.b32 nph, nph, 1;\n"
       "shl.b32 t, ns, 3;\n"
       "add.u32 neb, %11, t;\n"
@@ -609,7 +611,7 @@ __device__ __forceinline__ void produce_chunks_pair(RingState& rs, const void* t
       "}\n"
       : "+r"(rs.stage), "+r"(rs.phase), "+r"(rs.wait_cycles), "+r"(rs.ready)
       : "l"(tmap), "r"(row0), "r"(row_stride), "r"(n), "r"(expect_bytes), "r"(bar_full0), "r"(bar_full_cl0),
-        "r"(bar_empty0), "r"(w_smem0)
+        "r"(bar_empty0), "r"(w_smem0), "r"(stage_step)
       : "memory");
 }
 // The bias chunk of a layer: ONE accumulating MMA - A = the all-ones block, B = the second K=16 step of the chunk
@@ -763,7 +765,12 @@ __device__ __forceinline__ uint32_t pack_bf16_residual(float lo, float hi, uint3
   const float rhi = hi - __uint_as_float(packed & 0xFFFF0000u);
   return pack_bf16(rlo, rhi);
 }
-__device__ __forceinline__ float sigmoidf(float x) { return 1.f / (1.f + expf(-x)); }
+// kAccurate (BF16X3): IEEE division and libm expf; otherwise the MUFU approximations (rel. error ~1e-6, far below the
+// bf16 noise of the logits)
+template <bool kAccurate>
+__device__ __forceinline__ float sigmoidf(float x) {
+  return kAccurate ? 1.f / (1.f + expf(-x)) : __fdividef(1.f, 1.f + __expf(-x));
+}
 // Packed fp32x2 arithmetic (Blackwell FADD2 / FFMA2) and fused ReLU + bf16x2 conversion (F2FP.RELU)
 __device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
   uint64_t r;
@@ -1277,10 +1284,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const __grid_const
         tc_fence_before();  // orders this tile's last tcgen05.ld before the next tile's first MMA into the slot
         if (valid) {
           ps.sigma[pg] = fmaxf(sigma_lin + small[kOffBSigma], 0.f);  // :546-553 (eval: no noise)
-          ps.rgb[3 * pg + 0] = sigmoidf(o[0] + small[kOffBOut + 0]);   // :585-594
-          ps.rgb[3 * pg + 1] = sigmoidf(o[1] + small[kOffBOut + 1]);
-          ps.rgb[3 * pg + 2] = sigmoidf(o[2] + small[kOffBOut + 2]);
-          ps.vis[pg] = sigmoidf(o[3] + small[kOffBOut + 3]);
+          ps.rgb[3 * pg + 0] = sigmoidf<kSplit3>(o[0] + small[kOffBOut + 0]);   // :585-594
+          ps.rgb[3 * pg + 1] = sigmoidf<kSplit3>(o[1] + small[kOffBOut + 1]);
+          ps.rgb[3 * pg + 2] = sigmoidf<kSplit3>(o[2] + small[kOffBOut + 2]);
+          ps.vis[pg] = sigmoidf<kSplit3>(o[3] + small[kOffBOut + 3]);
         }
         if (kProf) c_view += clock64() - t1;
         if (kFused) {
@@ -1309,10 +1316,14 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const __grid_const
         q[6] = (unsigned long long)work.n_items; q[7] = (unsigned long long)(clock64() - c_begin);
       }
     }
-  } else if (warp == 8) {
-    // =================================================================== weight producer
-    // Streams the weight chunks of every (tile, step, slot) in the order the MMA issuer consumes them (StepDesc).
+  } else if (warp == 8 || (kPair && warp == 10)) {
+    // =================================================================== weight producers
+    // Stream the weight chunks of every (tile, step, slot) in the order the MMA issuer consumes them (StepDesc).
+    // One lane can start a copy only every ~330 cycles (barrier probe + TMA issue latencies), more than the 256 tensor
+    // cycles of a chunk, so in pair mode TWO lanes share the ring: warp 8 takes the even ring items, warp 10 the odd.
     if (lane == 0 && p.debug_noring != 1) {
+      const uint32_t prod_par = warp == 8 ? 0u : 1u, prod_step = kPair ? 2u : 1u;
+      uint32_t g_item = 0;   // ring items issued so far (by both producers)
       WorkList<kFused, kPair> work0(p, cta_group_idx * kSlots + 0, n_slots_total, (int)cta_rank);
       WorkList<kFused, kPair> work1(p, cta_group_idx * kSlots + (kSlots - 1), n_slots_total, (int)cta_rank);
       const int n_max = max(work0.n_items, kSlots > 1 ? work1.n_items : 0);
@@ -1320,6 +1331,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const __grid_const
       const uint32_t full_cluster0 = kPair ? map_to_cta(bar(kBarWFull), 0) : 0;
       const long long c_prod_begin = kProf ? clock64() : 0;
       RingState ring;
+      ring.stage = kPair ? prod_par : 0;
       constexpr uint32_t kImg = kSplit3 ? 2 : 1;   // ring items per chunk (BF16X3: hi image, lo image)
       for (int it = 0; it < n_max; ++it) {
         for (int st = 0; st < kNumSteps; ++st) {
@@ -1333,10 +1345,13 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const __grid_const
             if (kPair) {
               // rows of 64 bytes: consecutive chunk images, this CTA takes rows [rank * n/2, +n/2) of each
               const uint32_t rows = (uint32_t)layer_n(sd.layer);
-              produce_chunks_pair(ring, &p.wmap[w.pass_of(it)][sd.layer == 9 ? 1 : 0], byte0 / 64 + cta_rank * (rows / 2),
-                                  rows, n_items,
-                                  cta_rank == 0 ? (p.debug_noring == 3 ? chunk_bytes / 8 : chunk_bytes) : 0,
-                                  bar(kBarWFull), full_cluster0, bar(kBarWEmpty), smem_u32(smem + kOffW));
+              const uint32_t i0 = ((g_item & 1u) == prod_par) ? 0u : 1u;   // this lane's first item of the run
+              if (n_items > i0)
+                produce_chunks_pair(ring, &p.wmap[w.pass_of(it)][sd.layer == 9 ? 1 : 0],
+                                    byte0 / 64 + cta_rank * (rows / 2) + i0 * rows, 2 * rows, (n_items - i0 + 1) / 2,
+                                    cta_rank == 0 ? (p.debug_noring == 3 ? chunk_bytes / 8 : chunk_bytes) : 0,
+                                    bar(kBarWFull), full_cluster0, bar(kBarWEmpty), smem_u32(smem + kOffW), prod_step);
+              g_item += n_items;
             } else {
               produce_chunks(ring, p.pass[w.pass_of(it)].packed + kSmallBytes + byte0, chunk_bytes, chunk_bytes, n_items,
                              bar(kBarWFull), bar(kBarWEmpty), smem_u32(smem + kOffW));
@@ -1344,7 +1359,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const __grid_const
           }
         }
       }
-      if (kProf && p.prof != nullptr && blockIdx.x < 2) {
+      if (kProf && p.prof != nullptr && blockIdx.x < 2 && warp == 8) {
         p.prof[40 + 4 * blockIdx.x] = ring.wait_cycles;
         p.prof[41 + 4 * blockIdx.x] = (unsigned long long)(clock64() - c_prod_begin);
         p.prof[42 + 4 * blockIdx.x] = 0;
@@ -1409,50 +1424,57 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const __grid_const
       p.prof[35] = n_issued;
     }
   }
-  if (kFused && warp >= 10 && warp - 10 < kSlots && !(p.debug_noring & 4)) {
-    // =================================================================== ray warps (one per tile slot)
+  if (kFused && warp == 11 && !(p.debug_noring & 4)) {
+    // =================================================================== ray warp
     // Alpha compositing (volume_rendering, VipNeRF01.py:331-384) of the two rays a coarse tile / a fine tile triple
     // completes and, after the coarse pass, their hierarchical re-sampling (get_z_vals_fine :205-216) - one warp,
-    // shuffle scans, asynchronous to the tiles the slot's epilogue group goes on with.
-    const int slot = warp - 10;
-    const WorkList<kFused, kPair> work(p, cta_group_idx * kSlots + slot, n_slots_total, (int)cta_rank);
-    float* scratch = p.ray_scratch + ((size_t)blockIdx.x * 2 + slot) * kRayScratchFloats;
-    uint32_t parity = 0, n_done = 0;
-    for (int it = 0; it < work.n_items; ++it) {
-      const int pi = work.pass_of(it);
-      const int64_t tile = work.tile_of(it);
-      if (!(pi == 0 || (tile % 3) == 2)) continue;
-      const PassDesc& ps = p.pass[pi];
-      mbar_wait(bar(kBarRayFull + slot), parity);
-      parity ^= 1;
-      const int64_t pair = pi == 0 ? tile : tile / 3;
-      for (int rr = 0; rr < 2; ++rr) {
-        const int64_t r = 2 * pair + rr;
-        if (r >= p.n_rays) continue;
-        RayConsts rc;
-        rc.dnorm = vec3_norm(p.rp.pts_d[3 * r], p.rp.pts_d[3 * r + 1], p.rp.pts_d[3 * r + 2]);
-        rc.oz = p.rp.rays_o[3 * r + 2];
-        rc.dz = p.rp.rays_d[3 * r + 2];
-        if (pi == 0) {
-          float z_reg[2], w_reg[2];
-          composite_ray<2>(lane, 64, ps.z + r * 64, ps.sigma + r * 64, ps.rgb + r * 192, nullptr, 0, p.fl.ndc,
-                           p.fl.white_bkgd, rc, p.out[0], r, z_reg, w_reg);
-          if (p.has_fine) {
-            const float* u = p.rp.u_rand ? p.rp.u_rand + r * p.n_fine : p.rp.u_vals;
-            resample_ray<2>(lane, 64, p.n_fine, z_reg, w_reg, u, p.rp.u_rand == nullptr, scratch,
-                            p.pass[1].z + r * (64 + p.n_fine));
+    // shuffle scans, asynchronous to the tiles the epilogue groups go on with.  Serves both tile slots, in the order
+    // their events become due.
+    const WorkList<kFused, kPair> work0(p, cta_group_idx * kSlots + 0, n_slots_total, (int)cta_rank);
+    const WorkList<kFused, kPair> work1(p, cta_group_idx * kSlots + (kSlots - 1), n_slots_total, (int)cta_rank);
+    const int n_max = max(work0.n_items, kSlots > 1 ? work1.n_items : 0);
+    float* scratch = p.ray_scratch + (size_t)blockIdx.x * 2 * kRayScratchFloats;
+    uint32_t parity[2] = {0, 0}, n_done[2] = {0, 0};
+    for (int it = 0; it < n_max; ++it) {
+#pragma unroll
+      for (int slot = 0; slot < kSlots; ++slot) {
+        const WorkList<kFused, kPair>& work = slot == 0 ? work0 : work1;
+        if (it >= work.n_items) continue;
+        const int pi = work.pass_of(it);
+        const int64_t tile = work.tile_of(it);
+        if (!(pi == 0 || (tile % 3) == 2)) continue;
+        const PassDesc& ps = p.pass[pi];
+        mbar_wait(bar(kBarRayFull + slot), parity[slot]);
+        parity[slot] ^= 1;
+        const int64_t pair = pi == 0 ? tile : tile / 3;
+        for (int rr = 0; rr < 2; ++rr) {
+          const int64_t r = 2 * pair + rr;
+          if (r >= p.n_rays) continue;
+          RayConsts rc;
+          rc.dnorm = vec3_norm(p.rp.pts_d[3 * r], p.rp.pts_d[3 * r + 1], p.rp.pts_d[3 * r + 2]);
+          rc.oz = p.rp.rays_o[3 * r + 2];
+          rc.dz = p.rp.rays_d[3 * r + 2];
+          if (pi == 0) {
+            float z_reg[2], w_reg[2];
+            composite_ray<2>(lane, 64, ps.z + r * 64, ps.sigma + r * 64, ps.rgb + r * 192, nullptr, 0, p.fl.ndc,
+                             p.fl.white_bkgd, rc, p.out[0], r, z_reg, w_reg);
+            if (p.has_fine) {
+              const float* u = p.rp.u_rand ? p.rp.u_rand + r * p.n_fine : p.rp.u_vals;
+              resample_ray<2>(lane, 64, p.n_fine, z_reg, w_reg, u, p.rp.u_rand == nullptr, scratch,
+                              p.pass[1].z + r * (64 + p.n_fine));
+            }
+          } else {
+            float z_reg[6], w_reg[6];
+            composite_ray<6>(lane, 192, ps.z + r * 192, ps.sigma + r * 192, ps.rgb + r * 576, nullptr, 0, p.fl.ndc,
+                             p.fl.white_bkgd, rc, p.out[1], r, z_reg, w_reg);
           }
-        } else {
-          float z_reg[6], w_reg[6];
-          composite_ray<6>(lane, 192, ps.z + r * 192, ps.sigma + r * 192, ps.rgb + r * 576, nullptr, 0, p.fl.ndc,
-                           p.fl.white_bkgd, rc, p.out[1], r, z_reg, w_reg);
         }
+        ++n_done[slot];
+        __threadfence_block();   // z_fine (global) before the count the epilogue group acquires
+        __syncwarp();
+        if (lane == 0)
+          asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(smem_u32(smem + kOffRayDone) + 4u * slot), "r"(n_done[slot]) : "memory");
       }
-      ++n_done;
-      __threadfence_block();   // z_fine (global) before the count the epilogue group acquires
-      __syncwarp();
-      if (lane == 0)
-        asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(smem_u32(smem + kOffRayDone) + 4u * slot), "r"(n_done) : "memory");
     }
   }
   __syncthreads();
