@@ -58,7 +58,7 @@ int check_cfg(const vipnerf_cfg* cfg) {
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct Workspace {
-  size_t off_z_coarse, off_z_fine, off_sigma, off_rgb, off_vis, off_vis2, off_sigma_c, off_rgb_c, off_vis_c, off_ray_scratch, total;
+  size_t off_z_coarse, off_z_fine, off_sigma, off_rgb, off_vis, off_vis2, off_sigma_c, off_rgb_c, off_vis_c, total;
 };
 
 Workspace carve(const vipnerf_cfg* cfg, int64_t n_rays) {
@@ -76,7 +76,6 @@ Workspace carve(const vipnerf_cfg* cfg, int64_t n_rays) {
   w.off_sigma_c = take(R * cfg->n_coarse);
   w.off_rgb_c = take(R * cfg->n_coarse * 3);
   w.off_vis_c = take(R * cfg->n_coarse);
-  w.off_ray_scratch = take(R > 0 ? tc_ray_scratch_floats() : 0);
   w.total = off + 256;
   return w;
 }
@@ -259,7 +258,6 @@ int vipnerf_render_forward(const vipnerf_cfg* cfg, const vipnerf_rays* rays, int
     a.ws_z_coarse = at(w.off_z_coarse); a.ws_z_fine = at(w.off_z_fine);
     a.ws_sigma = at(w.off_sigma); a.ws_rgb = at(w.off_rgb); a.ws_vis = at(w.off_vis);
     a.ws_sigma_c = at(w.off_sigma_c); a.ws_rgb_c = at(w.off_rgb_c); a.ws_vis_c = at(w.off_vis_c);
-    a.ws_ray_scratch = at(w.off_ray_scratch);
     e = launch_render_fused_tc(cfg->precision, a, s);
     if (e != cudaSuccess) return fail_cuda(e, "render_fused_tc");
     return VIPNERF_OK;

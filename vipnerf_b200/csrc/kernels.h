@@ -61,9 +61,8 @@ struct FusedArgs {
   float* ws_sigma_c;    // [R,Nc]      network outputs of the coarse pass (read by the ray warps while fine tiles run)
   float* ws_rgb_c;      // [R,Nc,3]
   float* ws_vis_c;      // [R,Nc]
-  float* ws_ray_scratch;  // tc_ray_scratch_floats() floats: re-sampling scratch of the ray warps
 };
-size_t tc_ray_scratch_floats();
+
 cudaError_t launch_render_fused_tc(int precision, const FusedArgs& a, cudaStream_t s);
 // debug: 64 x u64 device buffer that CTA 0 of the next tensor-core launches fills with cycle counters (null = off)
 void set_tc_profile_buffer(void* dev_ptr);

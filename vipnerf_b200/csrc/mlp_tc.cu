@@ -49,19 +49,20 @@ constexpr uint32_t kKBlockBytes = 16384;
 // VIPNERF_ONES_4K (build-time fallback): a conventional 4 KiB all-ones operand instead of the 128-byte block read
 // through a zero-stride descriptor; costs one ring stage.
 #ifdef VIPNERF_ONES_4K
-#define VIPNERF_PAIR_STAGES 11
+#define VIPNERF_PAIR_STAGES 10
 #define VIPNERF_SINGLE_STAGES 5
 #else
-#define VIPNERF_PAIR_STAGES 12
-#define VIPNERF_SINGLE_STAGES 6
+#define VIPNERF_PAIR_STAGES 11
+#define VIPNERF_SINGLE_STAGES 5
 #endif
 #define VIPNERF_STR2(x) #x
 #define VIPNERF_STR(x) VIPNERF_STR2(x)
 constexpr int kPairStages = VIPNERF_PAIR_STAGES;      // x 8 KiB (each CTA of a pair holds half of a chunk's rows)
 constexpr int kSingleStages = VIPNERF_SINGLE_STAGES;  // x 16 KiB
 constexpr uint32_t kOffA = 0;                 // 2 x 64 KiB
-constexpr uint32_t kOffW = 131072;            // weight ring, 96 KiB
+constexpr uint32_t kOffW = 131072;            // weight ring (88 KiB used) + the ray warp's re-sampling scratch
 constexpr uint32_t kRingBytes = 98304;
+constexpr uint32_t kOffRayScratch = kOffW + 90112;   // 2 KiB (resample_scratch_floats(64, 128) = 384 floats)
 constexpr uint32_t kOffTail = kOffW + kRingBytes;
 constexpr uint32_t kOffBar = kOffTail;        // up to 32 mbarriers
 constexpr uint32_t kOffRayDone = kOffTail + 256;  // [2 slots] u32: per-ray events the slot's ray warp has completed
@@ -69,7 +70,7 @@ constexpr uint32_t kOffTmemPtr = kOffTail + 264;
 constexpr uint32_t kOffVb = kOffTail + 272;   // [2 slots][2 rays][128] fp32: view-direction part of M9 + bias
 constexpr uint32_t kOffPev = kOffVb + 2048;   // [2 slots][2 rays][32]  fp32: view-direction encodings
 #ifdef VIPNERF_ONES_4K
-constexpr uint32_t kOffOnes = kOffW + 90112;  // 4 KiB of bf16 1.0 behind the (shorter) ring
+constexpr uint32_t kOffOnes = kOffW + 90112 + 2048;  // 4 KiB of bf16 1.0 behind the (shorter) ring
 constexpr uint32_t kOnesBytes = 4096;
 constexpr uint32_t kSmemBytes = kOffPev + 512;
 #else
@@ -78,7 +79,7 @@ constexpr uint32_t kOnesBytes = 128;
 constexpr uint32_t kSmemBytes = kOffOnes + 128;
 #endif
 static_assert(kSmemBytes <= 232448, "exceeds the 227 KiB per-CTA shared memory limit");
-static_assert(kPairStages * 8192 <= kRingBytes && kSingleStages * 16384 <= kRingBytes, "weight ring does not fit");
+static_assert(kPairStages * 8192 <= 90112 && kSingleStages * 16384 <= 90112, "weight ring does not fit");
 
 enum { kBarWFull = 0, kBarWEmpty = 12, kBarAReady = 24, kBarDReady = 26, kBarRayFull = 28 };
 
@@ -88,7 +89,7 @@ constexpr uint32_t instr_desc(uint32_t n, uint32_t m = 128) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
 }
 
-constexpr int kRayScratchFloats = 512;   // >= resample_scratch_floats(64, 128) = 384
+static_assert(resample_scratch_floats(64, 128) * 4 <= 2048, "ray scratch");
 constexpr long long kTimeoutCycles = 4000000000ll;  // ~2 s: a protocol bug traps instead of hanging the GPU
 
 // ------------------------------------------------------------------------------------------ PTX wrappers
@@ -220,8 +221,8 @@ struct RingState {
 // Chunk c multiplies A columns [32c, 32c+32) - k-block c>>1 (1024 descriptor units apart), 64-byte half c&1
 // (4 units) - with the current ring stage: waits the stage's full barrier, issues two N x K=16 MMAs from the
 // elected lane, commits the stage's empty barrier and advances the ring.
-//   single CTA :  6 stages x 16 KiB (1024 units), tcgen05.mma.cta_group::1, M=128
-//   CTA pair   : 12 stages x  8 KiB ( 512 units: each CTA holds half of the chunk's rows), cta_group::2, M=256,
+//   single CTA :  5 stages x 16 KiB (1024 units), tcgen05.mma.cta_group::1, M=128
+//   CTA pair   : 11 stages x  8 KiB ( 512 units: each CTA holds half of the chunk's rows), cta_group::2, M=256,
 //                commits multicast to both CTAs' barriers
 // The *_split variants are BF16X3: every weight chunk is two ring stages (hi image, lo image); per chunk
 // A_hi*W_hi + A_lo*W_hi (4 MMAs, commit) then A_hi*W_lo (2 MMAs, commit).
@@ -825,7 +826,6 @@ struct TcParams {
   // CTA-pair kernels: tensor maps over each pass's chunk-image stream seen as [rows][32] bf16 (64-byte rows, no
   // swizzle - the images are stored pre-swizzled); [pass][0] box = 128 rows (half of a 256-row chunk), [pass][1] box =
   // 64 rows (half of an M9 chunk)
-  float* ray_scratch;        // [grid][2 slots][kRayScratchFloats]: re-sampling scratch of the ray warps (fused kernel)
   alignas(64) CUtensorMap wmap[2][2];
   int debug_noring;   // timing experiment (VIPNERF_TC_DEBUG_NORING=1): MMAs do not wait for weights - results are garbage
 };
@@ -1433,7 +1433,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const __grid_const
     const WorkList<kFused, kPair> work0(p, cta_group_idx * kSlots + 0, n_slots_total, (int)cta_rank);
     const WorkList<kFused, kPair> work1(p, cta_group_idx * kSlots + (kSlots - 1), n_slots_total, (int)cta_rank);
     const int n_max = max(work0.n_items, kSlots > 1 ? work1.n_items : 0);
-    float* scratch = p.ray_scratch + (size_t)blockIdx.x * 2 * kRayScratchFloats;
+    float* scratch = reinterpret_cast<float*>(smem + kOffRayScratch);
     uint32_t parity[2] = {0, 0}, n_done[2] = {0, 0};
     for (int it = 0; it < n_max; ++it) {
 #pragma unroll
@@ -1604,8 +1604,6 @@ void set_tc_profile_buffer(void* dev_ptr) {
   g_prof_buffer = static_cast<unsigned long long*>(dev_ptr);
 }
 
-size_t tc_ray_scratch_floats() { return (size_t)512 * 2 * kRayScratchFloats; }   // up to 512 CTAs
-
 cudaError_t launch_mlp_tc(int precision, const RayPtrs& rp, const RenderFlags& fl, int64_t n_rays, int S,
                           const float* z, const void* packed, float* sigma, float* rgb, float* vis,
                           cudaStream_t s) {
@@ -1655,7 +1653,6 @@ cudaError_t launch_render_fused_tc(int precision, const FusedArgs& a, cudaStream
   }
   if (!p.has_fine) p.pass[1] = p.pass[0];
   p.n_units = (a.n_rays + 1) / 2;
-  p.ray_scratch = a.ws_ray_scratch;
   p.prof = g_prof_buffer;
   if (precision == VIPNERF_PRECISION_BF16X3) return launch<true, true>(p, p.n_units, s);
   return launch<false, true>(p, p.n_units, s);
