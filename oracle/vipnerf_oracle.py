@@ -219,8 +219,8 @@ def mlp_forward(params: Dict[str, torch.Tensor], pts: torch.Tensor, view_dirs: t
 
     In the tensor-core modes only the layers the CUDA kernel runs on tensor cores are emulated at reduced
     precision (the eight trunk layers, feature_linear and the feature columns of views_linears.0); the
-    density head, the view-direction columns of views_linears.0 and views_output_linear stay fp32, as in
-    the kernel."""
+    density head, the PRIMARY view-direction columns of views_linears.0 and views_output_linear stay fp32, as in
+    the kernel (the secondary views' direction columns are a tensor-core step there)."""
     enc = positional_encoding(pts, l_pts)
     h = enc
     for i in range(8):
@@ -238,9 +238,13 @@ def mlp_forward(params: Dict[str, torch.Tensor], pts: torch.Tensor, view_dirs: t
     n_feat = feature.shape[-1]
     feat_part = linear(feature, wv[:, :n_feat], None, mode) if mode != 'fp32' else None
 
-    def view_head(enc_view, feat, feat_pre):
+    def view_head(enc_view, feat, feat_pre, secondary=False):
         if mode == 'fp32':
             hv = F.relu(F.linear(torch.cat([feat, enc_view], dim=-1), wv, bv))
+        elif secondary:
+            # secondary views: the direction differs per sample, so the kernel runs these 27 columns (and the bias)
+            # on the tensor core as well
+            hv = F.relu(feat_pre + linear(enc_view, wv[:, n_feat:], bv, mode))
         else:
             hv = F.relu(feat_pre + F.linear(enc_view, wv[:, n_feat:], bv))
         return torch.sigmoid(F.linear(hv, wo, bo))
@@ -251,7 +255,7 @@ def mlp_forward(params: Dict[str, torch.Tensor], pts: torch.Tensor, view_dirs: t
         v = view_dirs2.shape[1]
         feat_v = feature[:, None, :].expand(-1, v, -1)
         feat_pre_v = feat_part[:, None, :].expand(-1, v, -1) if feat_part is not None else None
-        out2 = view_head(positional_encoding(view_dirs2, l_view), feat_v, feat_pre_v)
+        out2 = view_head(positional_encoding(view_dirs2, l_view), feat_v, feat_pre_v, secondary=True)
         result['visibility2'] = out2[..., 3:4]
     return result
 

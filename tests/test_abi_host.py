@@ -44,9 +44,9 @@ def test_config_validation(built_library):
     lib = _lib.load()
     ok = _lib.make_cfg(precision='bf16')
     assert lib.vipnerf_check_config(ctypes.byref(ok)) == 0
-    assert lib.vipnerf_packed_weight_bytes(ctypes.byref(ok)) == 27648 + (72 + 7) * 16384   # 76 weight chunks (8 of them half-size) + 7 bias chunks
+    assert lib.vipnerf_packed_weight_bytes(ctypes.byref(ok)) == 27648 + (72 + 7) * 16384 + 8192   # 76 weight chunks (8 half-size) + 7 bias chunks + the view-direction chunk
     x3 = _lib.make_cfg(precision='bf16x3')
-    assert lib.vipnerf_packed_weight_bytes(ctypes.byref(x3)) == 27648 + 2 * (72 + 7) * 16384
+    assert lib.vipnerf_packed_weight_bytes(ctypes.byref(x3)) == 27648 + 2 * ((72 + 7) * 16384 + 8192)
     f32 = _lib.make_cfg(precision='fp32')
     assert lib.vipnerf_packed_weight_bytes(ctypes.byref(f32)) == 27648 + 589824 * 4
     assert lib.vipnerf_workspace_bytes(ctypes.byref(ok), 4096) > 4096 * (64 + 192 * 6) * 4
@@ -58,7 +58,9 @@ def test_config_validation(built_library):
     bad_abi = _lib.make_cfg()
     bad_abi.abi = 99
     assert lib.vipnerf_check_config(ctypes.byref(bad_abi)) == -5
-    sec_tc = _lib.make_cfg(precision='bf16', n_sec_views=2)
+    sec_tc = _lib.make_cfg(precision='bf16', n_sec_views=2)     # secondary views run on the tensor path (<= 8 per tile)
+    assert lib.vipnerf_check_config(ctypes.byref(sec_tc)) == 0
+    sec_tc = _lib.make_cfg(precision='bf16', n_sec_views=9)
     assert lib.vipnerf_check_config(ctypes.byref(sec_tc)) == -2
     assert lib.vipnerf_check_config(None) == -1
     # NULL arguments are reported, never dereferenced

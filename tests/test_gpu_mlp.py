@@ -59,6 +59,24 @@ def test_mlp_tensor_core_matches_oracle(scene, S, precision, tol_max, tol_med, b
         assert med <= tol_med, (k, err, med)
 
 
+@pytest.mark.parametrize('precision,tol_max,tol_med', [('bf16x3', 1e-4, 5e-6), ('bf16', 3e-2, 2e-3)])
+@pytest.mark.parametrize('scene,S', [('fern', 192), ('dtu', 64)])
+def test_mlp_tensor_core_secondary_views(scene, S, precision, tol_max, tol_med, built_library):
+    """visibility2 on the tensor path (one K=32 MMA step per secondary view on the per-sample direction encodings)
+    vs the fp32 oracle, three secondary views (two share a k-block, the third starts the next)."""
+    from vipnerf_b200 import renderpath
+    ndc, batch, z = _points(scene, 90, S, 11, n_sec_views=3)
+    params = O.split_state_dict(O.synth_state_dict(0), 'fine_model')
+    ref = _oracle_mlp(params, ndc, batch, z, sec=True)
+    packed = renderpath.pack_mlp({k: v.cuda() for k, v in params.items()}, precision)
+    got = renderpath.mlp_forward(to_cuda(batch), z.cuda(), packed, ndc=ndc, precision=precision, n_sec_views=3)
+    for k in ('sigma', 'rgb', 'visibility', 'visibility2'):
+        assert got[k].shape == ref[k].shape, k
+        err, med = rel_err(got[k], ref[k])
+        assert err <= tol_max, (k, err, med)
+        assert med <= tol_med, (k, err, med)
+
+
 @pytest.mark.parametrize('precision', ['bf16', 'bf16x3'])
 def test_mlp_tensor_core_matches_emulation(precision, built_library):
     """Against the oracle run with the same operand rounding (bf16 operands / hi-lo split, fp32 accumulate) the

@@ -89,7 +89,7 @@ def test_fine_pass_teacher_forced_against_golden(scene, precision, tol, built_li
     ndc = O.SCENES[scene]['ndc']
     sd = {k: v.cuda() for k, v in O.synth_state_dict(0).items()}
     batch = to_cuda(inputs)
-    V = 2 if precision == 'fp32' else 0
+    V = 2
     packed = renderpath.pack_mlp(O.split_state_dict(sd, 'fine_model'), precision)
     z = golden['z_vals_fine'].cuda()
     raw = renderpath.mlp_forward(batch, z, packed, ndc=ndc, precision=precision, n_sec_views=V)
@@ -103,6 +103,28 @@ def test_fine_pass_teacher_forced_against_golden(scene, precision, tol, built_li
     for got, k in pairs:
         err = rel_err(got, golden[f'{k}_fine'])[0]
         assert err <= tol, (k, err)
+
+
+@pytest.mark.parametrize('scene', ['fern', 'dtu'])
+@pytest.mark.parametrize('precision', ['bf16x3', 'bf16'])
+def test_tensor_core_render_retraw_secondary_views(scene, precision, built_library):
+    """Fused tcgen05 kernel with retraw + sec_views_vis (2 secondary views): the reference's full key set; the
+    secondary-view visibilities (per sample and composited) against the golden - bf16x3 at the parity tolerance
+    on the coarse pass (no re-sampling discontinuity in the way), bf16 statistically."""
+    inputs, golden = split_io(load_npz(f'render_{scene}_retraw64.npz'))
+    ndc = O.SCENES[scene]['ndc']
+    with torch.no_grad():
+        out = _model(ndc, precision)(to_cuda(inputs), retraw=True, sec_views_vis=True)
+    assert set(golden) <= set(out)
+    for k in ('raw_visibility2_coarse', 'visibility2_coarse', 'visibility2_fine', 'raw_visibility_coarse',
+              'rgb_coarse'):
+        assert tuple(out[k].shape) == tuple(golden[k].shape), k
+        mx, p99, med = _percentiles(out[k], golden[k])
+        if precision == 'bf16x3':
+            tol = 1e-4 if k.endswith('_coarse') else 5e-3
+            assert mx <= tol, (k, mx, p99, med)
+        else:
+            assert med <= 2e-3 and mx <= 5e-2, (k, mx, p99, med)
 
 
 def _percentiles(a, b):

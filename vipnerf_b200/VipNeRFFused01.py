@@ -124,8 +124,9 @@ class VipNeRFFused(torch.nn.Module):
                 rays_o2 = torch.stack(others, dim=1)
             batch['rays_o2'] = rays_o2
             n_sec_views = rays_o2.shape[1]
-        # visibility2 is evaluated per sample and per secondary view by the fp32 kernels
-        precision = 'fp32' if n_sec_views > 0 else self.precision
+        # visibility2 runs on the tensor path too (one K=32 MMA step per secondary view); more than 8 views per
+        # tile only fit the fp32 kernels
+        precision = 'fp32' if n_sec_views > 8 else self.precision
         packed_c = self._packed_weights('coarse', precision, device)
         packed_f = self._packed_weights('fine', precision, device) if self.fine_mlp_needed else None
         if not self.fine_mlp_needed and not retraw:

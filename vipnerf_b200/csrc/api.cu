@@ -47,8 +47,8 @@ int check_cfg(const vipnerf_cfg* cfg) {
   if (cfg->precision != VIPNERF_PRECISION_FP32 && !is_tc(cfg->precision))
     return fail(VIPNERF_EUNSUPPORTED, "precision=%d unknown", cfg->precision);
   if (is_tc(cfg->precision)) {
-    if (cfg->n_sec_views != 0)
-      return fail(VIPNERF_EUNSUPPORTED, "secondary-view visibility (n_sec_views=%d) is only built for PRECISION_FP32", cfg->n_sec_views);
+    if (cfg->n_sec_views > 8)
+      return fail(VIPNERF_EUNSUPPORTED, "tensor-core path holds at most 8 secondary views per tile (n_sec_views=%d)", cfg->n_sec_views);
     if (cfg->n_coarse != 64 || (cfg->n_fine != 0 && cfg->n_fine != 128))
       return fail(VIPNERF_EUNSUPPORTED, "tensor-core path is built for 64 coarse + 128 fine samples (got %d + %d)", cfg->n_coarse, cfg->n_fine);
   }
@@ -58,7 +58,7 @@ int check_cfg(const vipnerf_cfg* cfg) {
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct Workspace {
-  size_t off_z_coarse, off_z_fine, off_sigma, off_rgb, off_vis, off_vis2, off_sigma_c, off_rgb_c, off_vis_c, total;
+  size_t off_z_coarse, off_z_fine, off_sigma, off_rgb, off_vis, off_vis2, off_sigma_c, off_rgb_c, off_vis_c, off_vis2_c, total;
 };
 
 Workspace carve(const vipnerf_cfg* cfg, int64_t n_rays) {
@@ -76,6 +76,7 @@ Workspace carve(const vipnerf_cfg* cfg, int64_t n_rays) {
   w.off_sigma_c = take(R * cfg->n_coarse);
   w.off_rgb_c = take(R * cfg->n_coarse * 3);
   w.off_vis_c = take(R * cfg->n_coarse);
+  w.off_vis2_c = take(R * cfg->n_coarse * (size_t)cfg->n_sec_views);
   w.total = off + 256;
   return w;
 }
@@ -204,7 +205,7 @@ int vipnerf_mlp_forward(const vipnerf_cfg* cfg, const vipnerf_rays* rays, int64_
   } else {
     if (n_samples != 64 && n_samples != 192) return fail(VIPNERF_EUNSUPPORTED, "tensor-core MLP takes 64 or 192 samples per ray (got %d)", n_samples);
     e = launch_mlp_tc(cfg->precision, rp, fl, n_rays, n_samples, z_vals, packed, out->raw_sigma, out->raw_rgb,
-                      out->raw_visibility, s);
+                      out->raw_visibility, out->raw_visibility2, s);
   }
   if (e != cudaSuccess) return fail_cuda(e, "mlp_forward");
   return VIPNERF_OK;
@@ -258,6 +259,7 @@ int vipnerf_render_forward(const vipnerf_cfg* cfg, const vipnerf_rays* rays, int
     a.ws_z_coarse = at(w.off_z_coarse); a.ws_z_fine = at(w.off_z_fine);
     a.ws_sigma = at(w.off_sigma); a.ws_rgb = at(w.off_rgb); a.ws_vis = at(w.off_vis);
     a.ws_sigma_c = at(w.off_sigma_c); a.ws_rgb_c = at(w.off_rgb_c); a.ws_vis_c = at(w.off_vis_c);
+    a.ws_vis2 = at(w.off_vis2); a.ws_vis2_c = at(w.off_vis2_c);
     e = launch_render_fused_tc(cfg->precision, a, s);
     if (e != cudaSuccess) return fail_cuda(e, "render_fused_tc");
     return VIPNERF_OK;

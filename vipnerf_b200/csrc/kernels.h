@@ -42,7 +42,7 @@ cudaError_t launch_mlp_fp32(const RayPtrs& rp, const RenderFlags& fl, int64_t n_
 
 // mlp_tc.cu : tcgen05 evaluation (precision = BF16 or BF16X3)
 cudaError_t launch_mlp_tc(int precision, const RayPtrs& rp, const RenderFlags& fl, int64_t n_rays, int S,
-                          const float* z, const void* packed, float* sigma, float* rgb, float* vis,
+                          const float* z, const void* packed, float* sigma, float* rgb, float* vis, float* vis2,
                           cudaStream_t s);
 // mlp_tc.cu : the fused coarse+fine render of a ray batch in one launch
 struct FusedArgs {
@@ -61,6 +61,8 @@ struct FusedArgs {
   float* ws_sigma_c;    // [R,Nc]      network outputs of the coarse pass (read by the ray warps while fine tiles run)
   float* ws_rgb_c;      // [R,Nc,3]
   float* ws_vis_c;      // [R,Nc]
+  float* ws_vis2;       // [R,Nc+Nf,V] secondary-view visibilities per sample (V > 0)
+  float* ws_vis2_c;     // [R,Nc,V]
 };
 
 cudaError_t launch_render_fused_tc(int precision, const FusedArgs& a, cudaStream_t s);

@@ -26,9 +26,15 @@ constexpr int kEncPts = 3 + 6 * kLPts;    // 63
 constexpr int kEncPtsPad = 64;
 constexpr int kEncView = 3 + 6 * kLView;  // 27
 constexpr int kNumMatLayers = 10;
+// Tensor-core builds carry one more chunk image behind M9, "layer" 10: the 27 view-direction columns of
+// views_linears.0 (+ its bias in column 31, facing a constant-one input column), K = 32, N = 128.  The fused kernel
+// multiplies it with the per-SAMPLE direction encodings of the secondary views (visibility2, VipNeRF01.py:527-530);
+// the primary view's direction is per ray and stays an fp32 CUDA-core term.
+constexpr int kViewChunkLayer = 10;
+constexpr int kNumTcLayers = 11;
 
-__host__ __device__ constexpr int layer_k(int l) { return l == 0 ? 64 : (l == 5 ? 320 : 256); }
-__host__ __device__ constexpr int layer_n(int l) { return l == 9 ? 128 : 256; }
+__host__ __device__ constexpr int layer_k(int l) { return l == 0 ? 64 : (l == 5 ? 320 : (l == 10 ? 32 : 256)); }
+__host__ __device__ constexpr int layer_n(int l) { return l >= 9 ? 128 : 256; }
 
 // ---- small fp32 parameters (first region of every packed buffer), offsets in floats
 constexpr int kOffBias = 0;                          // [9][256]: M0..M8 biases (M8 = feature_linear.bias)
@@ -65,7 +71,7 @@ __host__ __device__ constexpr int layer_chunks(int l) { return layer_k(l) / kChu
 // bias, consumed by ONE K=16 MMA against the last 16 encoding columns.  M9's bias travels with the
 // view-direction term (fp32, per ray).  In bf16 mode the bias is therefore rounded to bf16; in BF16X3 mode the
 // lo image carries its residual.
-__host__ __device__ constexpr bool layer_has_bias_chunk(int l) { return l != 0 && l != 5 && l != 9; }
+__host__ __device__ constexpr bool layer_has_bias_chunk(int l) { return l != 0 && l != 5 && l < 9; }
 __host__ __device__ constexpr int layer_stream_chunks(int l) { return layer_chunks(l) + (layer_has_bias_chunk(l) ? 1 : 0); }
 __host__ __device__ constexpr int layer_chunk_bytes(int l) { return layer_n(l) * kChunkK * 2; }
 __host__ __device__ constexpr int tc_layer_byte_offset(int l) {    // of the hi image set
@@ -73,7 +79,7 @@ __host__ __device__ constexpr int tc_layer_byte_offset(int l) {    // of the hi 
   for (int i = 0; i < l; ++i) off += layer_stream_chunks(i) * layer_chunk_bytes(i);
   return off;
 }
-constexpr int kTcBigBytes = tc_layer_byte_offset(kNumMatLayers);    // 1,294,336 (76 weight + 7 bias chunks)
+constexpr int kTcBigBytes = tc_layer_byte_offset(kNumTcLayers);    // 1,302,528 (76 weight + 7 bias chunks + the view-direction chunk)
 
 // Maps A column k of matrix layer l to the source weight column (or -1 for a zero pad column).
 __host__ __device__ inline int source_col(int l, int k) {

@@ -808,6 +808,7 @@ struct PassDesc {
   float* sigma;           // [R,S]   network outputs of the pass
   float* rgb;             // [R,S,3]
   float* vis;             // [R,S]
+  float* vis2;            // [R,S,V] visibility of every sample from the secondary views (null when V = 0)
   int64_t n_points;       // R*S
   int S;
   int compute_z;          // 1: z = get_z_vals_coarse(near, far) is generated here
@@ -1035,25 +1036,115 @@ __device__ __forceinline__ void view_epilogue(uint32_t taddr, const float* vb_ro
 // The MMA steps of one tile, in issue order.  The skip layer M5 is two steps: its h4 part (K = 256 over the whole
 // activation buffer; weight chunks 2..9 of the layer) and, once that has retired and the epilogue group has put the
 // encoding back into k-block 0, its encoding part (K = 64, accumulating; chunks 0..1, carries the bias through the
-// constant-one column).  Every step ends with a d_ready commit and starts with an a_ready wait.
-constexpr int kNumSteps = 11;
+// constant-one column).  With V secondary views, V more steps follow M9: E_v = direction encoding of view v (32
+// columns of k-block v/2, written by the epilogue group once M9 has retired) x the view-direction chunk, into TMEM
+// columns [128,256) of the slot - M9's accumulator (columns [0,128)) stays in place and is re-read for every view.
+// Every step ends with a d_ready commit and starts with an a_ready wait.
+constexpr int kNumBaseSteps = 11;
 struct StepDesc {
-  int layer;            // matrix layer M0..M9 (layout.cuh)
+  int layer;            // matrix layer M0..M9 / kViewChunkLayer (layout.cuh)
   uint32_t first_chunk; // first weight chunk of the layer's stream used by the step
-  uint32_t n_chunks;    // chunks multiplied against the activation buffer from k-block 0 on
+  uint32_t n_chunks;    // chunks multiplied against the activation buffer
   uint32_t accumulate;  // 0: the first MMA overwrites the accumulator
   bool bias_chunk;      // followed by the layer's bias chunk (all-ones A operand)
+  uint32_t a_units;     // A descriptor offset (16-byte units) of the step's first 32 columns
+  uint32_t d_col;       // TMEM column offset of the accumulator inside the slot
 };
 __device__ __forceinline__ StepDesc step_desc(int st) {
-  if (st == 0) return {0, 0, 2, 0, false};
-  if (st == 5) return {5, 2, 8, 0, false};
-  if (st == 6) return {5, 0, 2, 1, false};
+  if (st == 0) return {0, 0, 2, 0, false, 0, 0};
+  if (st == 5) return {5, 2, 8, 0, false, 0, 0};
+  if (st == 6) return {5, 0, 2, 1, false, 0, 0};
+  if (st >= kNumBaseSteps) {
+    const uint32_t v = (uint32_t)(st - kNumBaseSteps);
+    return {kViewChunkLayer, 0, 1, 0, false, (v >> 1) * (kKBlockBytes >> 4) + (v & 1) * 4, 128};
+  }
   const int l = st < 5 ? st : st - 1;
-  return {l, 0, 8, 0, layer_has_bias_chunk(l)};
+  return {l, 0, 8, 0, layer_has_bias_chunk(l), 0, 0};
+}
+
+// Visibility of this row's sample from each secondary view (VipNeRF01.py:218-226, :527-530): the same hidden layer
+// with the unit vector from that camera to the SAMPLE.  Called by every thread of an epilogue group once M9 has
+// retired, so the activation buffer is free: the V direction encodings (27 columns + zeros + a constant 1 facing the
+// bias column, 32 per view) go into its first k-blocks; then per view one K=32 MMA step into TMEM columns [128,256)
+// and an epilogue relu(M9 accumulator + E_v) . w_out[:, 3].  Kept out of line: the eval render without secondary
+// views must not pay registers for it.
+template <bool kSplit3, bool kPair>
+__device__ __noinline__ void secondary_views(uint8_t* smem, const TcParams& p, const PassDesc& ps, int slot, int row,
+                                             int lane, int64_t pg, bool valid, int64_t ray, uint32_t taddr,
+                                             uint32_t d_ready_bar, uint32_t a_ready_bar, uint32_t& d_parity) {
+  auto arrive_a_ready = [&]() {
+    __syncwarp();
+    if (lane == 0) { if (kPair) mbar_arrive_cluster(a_ready_bar); else mbar_arrive(a_ready_bar); }
+  };
+  const float* small = reinterpret_cast<const float*>(ps.packed);
+  const int V = p.fl.n_sec_views;
+  const int64_t pc = valid ? pg : ps.n_points - 1;
+  const float o3[3] = {p.rp.rays_o[3 * ray], p.rp.rays_o[3 * ray + 1], p.rp.rays_o[3 * ray + 2]};
+  const float d3[3] = {p.rp.rays_d[3 * ray], p.rp.rays_d[3 * ray + 1], p.rp.rays_d[3 * ray + 2]};
+  float zz = ps.z[pc];
+  if (p.fl.ndc) zz = depth_from_ndc_secondary(zz, o3[2], d3[2]);
+  for (int v = 0; v < V; ++v) {
+    const float* c2 = p.rp.rays_o2 + (ray * V + v) * 3;
+    const float o2[3] = {c2[0], c2[1], c2[2]};
+    float dd[3], pe[32];
+    secondary_view_dir(o3, d3, zz, o2, dd);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) pe[j] = 0.f;
+#pragma unroll
+    for (int ax = 0; ax < 3; ++ax) {
+      pe[ax] = dd[ax];
+#pragma unroll
+      for (int k = 0; k < kLView; ++k) {
+        const float ang = dd[ax] * (float)(1 << k);
+        if (kSplit3) { pe[3 + 6 * k + ax] = sinf(ang); pe[6 + 6 * k + ax] = cosf(ang); }
+        else { pe[3 + 6 * k + ax] = __sinf(ang); pe[6 + 6 * k + ax] = __cosf(ang); }
+      }
+    }
+    pe[31] = 1.f;
+    const uint32_t kb = (uint32_t)(v >> 1) * kKBlockBytes + row * 128;
+    const uint32_t hi_base = smem_u32(smem + kOffA + (kSplit3 ? 0 : slot) * kABytes) + kb;
+    const uint32_t lo_base = smem_u32(smem + kOffA + kABytes) + kb;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint32_t w[4], r[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        w[e] = pack_bf16(pe[8 * q + 2 * e], pe[8 * q + 2 * e + 1]);
+        r[e] = pack_bf16_residual(pe[8 * q + 2 * e], pe[8 * q + 2 * e + 1], w[e]);
+      }
+      const uint32_t off = (uint32_t)((((v & 1) * 4 + q) ^ (row & 7)) << 4);
+      st_shared_v4(hi_base + off, w[0], w[1], w[2], w[3]);
+      if (kSplit3) st_shared_v4(lo_base + off, r[0], r[1], r[2], r[3]);
+    }
+  }
+  fence_proxy_async();
+  arrive_a_ready();
+  const float b3 = small[kOffBOut + 3];
+  for (int v = 0; v < V; ++v) {
+    mbar_wait(d_ready_bar, d_parity);
+    d_parity ^= 1;
+    tc_fence_after();
+    float acc = 0.f;
+    uint32_t f[32], e[32];
+#pragma unroll
+    for (int cb = 0; cb < 4; ++cb) {
+      tmem_ld32(taddr + cb * 32, f);
+      tmem_ld32(taddr + 128 + cb * 32, e);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float h = fmaxf(__uint_as_float(f[j]) + __uint_as_float(e[j]), 0.f);
+        acc = fmaf(h, __ldg(small + kOffWOut + 4 * (cb * 32 + j) + 3), acc);
+      }
+    }
+    tc_fence_before();
+    if (v + 1 < V) arrive_a_ready();   // columns [128,256) are drained: the next view's step may overwrite them
+    if (valid) ps.vis2[pg * V + v] = sigmoidf<kSplit3>(acc + b3);
+  }
 }
 
 // ------------------------------------------------------------------------------------------ the kernel
-template <bool kSplit3, bool kFused, bool kProf, bool kPair>
+template <bool kSplit3, bool kFused, bool kProf, bool kPair, bool kSec>
 __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const __grid_constant__ TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr int kSlots = kSplit3 ? 1 : 2;
@@ -1289,6 +1380,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const __grid_const
           ps.rgb[3 * pg + 2] = sigmoidf<kSplit3>(o[2] + small[kOffBOut + 2]);
           ps.vis[pg] = sigmoidf<kSplit3>(o[3] + small[kOffBOut + 3]);
         }
+        if (kSec)   // compile-time: the eval render without secondary views pays nothing for this path
+          secondary_views<kSplit3, kPair>(smem, p, ps, slot, row, lane, pg, valid, ray, taddr, bar(kBarDReady + slot),
+                                          a_ready_bar, d_parity);
         if (kProf) c_view += clock64() - t1;
         if (kFused) {
           // ---- per-ray stages on the two rays a pair of tiles completes: handed to the slot's ray warp.  Event k may
@@ -1330,11 +1424,12 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const __grid_const
       // pair mode: this CTA streams its half of every chunk's rows; both CTAs' copies complete on the leader's w_full
       const uint32_t full_cluster0 = kPair ? map_to_cta(bar(kBarWFull), 0) : 0;
       const long long c_prod_begin = kProf ? clock64() : 0;
+      const int n_steps = kNumBaseSteps + (kSec ? p.fl.n_sec_views : 0);
       RingState ring;
       ring.stage = kPair ? prod_par : 0;
       constexpr uint32_t kImg = kSplit3 ? 2 : 1;   // ring items per chunk (BF16X3: hi image, lo image)
       for (int it = 0; it < n_max; ++it) {
-        for (int st = 0; st < kNumSteps; ++st) {
+        for (int st = 0; st < n_steps; ++st) {
           for (int s = 0; s < kSlots; ++s) {
             const WorkList<kFused, kPair>& w = s == 0 ? work0 : work1;
             if (it >= w.n_items) continue;
@@ -1347,7 +1442,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const __grid_const
               const uint32_t rows = (uint32_t)layer_n(sd.layer);
               const uint32_t i0 = ((g_item & 1u) == prod_par) ? 0u : 1u;   // this lane's first item of the run
               if (n_items > i0)
-                produce_chunks_pair(ring, &p.wmap[w.pass_of(it)][sd.layer == 9 ? 1 : 0],
+                produce_chunks_pair(ring, &p.wmap[w.pass_of(it)][sd.layer >= 9 ? 1 : 0],
                                     byte0 / 64 + cta_rank * (rows / 2) + i0 * rows, 2 * rows, (n_items - i0 + 1) / 2,
                                     cta_rank == 0 ? (p.debug_noring == 3 ? chunk_bytes / 8 : chunk_bytes) : 0,
                                     bar(kBarWFull), full_cluster0, bar(kBarWEmpty), smem_u32(smem + kOffW), prod_step);
@@ -1374,6 +1469,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const __grid_const
     WorkList<kFused, kPair> work0(p, cta_group_idx * kSlots + 0, n_slots_total, (int)cta_rank);
     WorkList<kFused, kPair> work1(p, cta_group_idx * kSlots + (kSlots - 1), n_slots_total, (int)cta_rank);
     const int n_max = max(work0.n_items, kSlots > 1 ? work1.n_items : 0);
+    const int n_steps = kNumBaseSteps + (kSec ? p.fl.n_sec_views : 0);
     RingState ring;
     uint32_t a_parity0 = 0, a_parity1 = 0, n_issued = 0;
     const uint64_t a_desc0 = make_desc(smem_u32(smem + kOffA));
@@ -1385,7 +1481,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const __grid_const
     long long c_wait_a = 0;
     const long long c_begin = kProf ? clock64() : 0;
     for (int it = 0; it < n_max; ++it) {
-      for (int st = 0; st < kNumSteps; ++st) {
+      for (int st = 0; st < n_steps; ++st) {
 #pragma unroll
         for (int s = 0; s < kSlots; ++s) {
           const WorkList<kFused, kPair>& w = s == 0 ? work0 : work1;
@@ -1399,8 +1495,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const __grid_const
           tc_fence_after();
           const StepDesc sd = step_desc(st);
           const uint32_t idesc = instr_desc(layer_n(sd.layer), kPair ? 256 : 128);
-          const uint32_t d_tmem = tmem_base + (uint32_t)(s * 256);
-          const uint64_t a_hi = a_desc0 + (kSplit3 ? 0 : s) * kAUnits, a_lo = a_desc0 + kAUnits;
+          const uint32_t d_tmem = tmem_base + (uint32_t)(s * 256) + sd.d_col;
+          const uint64_t a_hi = a_desc0 + (kSplit3 ? 0 : s) * kAUnits + sd.a_units, a_lo = a_desc0 + kAUnits + sd.a_units;
           if (!kSplit3 && !kPair) issue_chunks(ring, d_tmem, a_hi, w_desc0, bar_full0, bar_empty0, sd.n_chunks, sd.accumulate, idesc);
           else if (!kSplit3) issue_chunks_pair(ring, d_tmem, a_hi, w_desc0, bar_full0, bar_empty0, sd.n_chunks, sd.accumulate, idesc, p.debug_noring == 1);
           else if (!kPair) issue_chunks_split(ring, d_tmem, a_hi, a_lo, w_desc0, bar_full0, bar_empty0, sd.n_chunks, sd.accumulate, idesc);
@@ -1456,8 +1552,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const __grid_const
           rc.dz = p.rp.rays_d[3 * r + 2];
           if (pi == 0) {
             float z_reg[2], w_reg[2];
-            composite_ray<2>(lane, 64, ps.z + r * 64, ps.sigma + r * 64, ps.rgb + r * 192, nullptr, 0, p.fl.ndc,
-                             p.fl.white_bkgd, rc, p.out[0], r, z_reg, w_reg);
+            const int V = kSec ? p.fl.n_sec_views : 0;
+            composite_ray<2>(lane, 64, ps.z + r * 64, ps.sigma + r * 64, ps.rgb + r * 192,
+                             V > 0 ? ps.vis2 + r * 64 * V : nullptr, V, p.fl.ndc, p.fl.white_bkgd, rc, p.out[0], r, z_reg, w_reg);
             if (p.has_fine) {
               const float* u = p.rp.u_rand ? p.rp.u_rand + r * p.n_fine : p.rp.u_vals;
               resample_ray<2>(lane, 64, p.n_fine, z_reg, w_reg, u, p.rp.u_rand == nullptr, scratch,
@@ -1465,8 +1562,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const __grid_const
             }
           } else {
             float z_reg[6], w_reg[6];
-            composite_ray<6>(lane, 192, ps.z + r * 192, ps.sigma + r * 192, ps.rgb + r * 576, nullptr, 0, p.fl.ndc,
-                             p.fl.white_bkgd, rc, p.out[1], r, z_reg, w_reg);
+            const int V = kSec ? p.fl.n_sec_views : 0;
+            composite_ray<6>(lane, 192, ps.z + r * 192, ps.sigma + r * 192, ps.rgb + r * 576,
+                             V > 0 ? ps.vis2 + r * 192 * V : nullptr, V, p.fl.ndc, p.fl.white_bkgd, rc, p.out[1], r, z_reg, w_reg);
           }
         }
         ++n_done[slot];
@@ -1490,7 +1588,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const __grid_const
 std::mutex g_attr_mutex;
 unsigned long long* g_prof_buffer = nullptr;  // debug: set by vipnerf_debug_set_profile_buffer
 int g_sm_count[64] = {0};
-bool g_attr_set[64][16] = {{false}};
+bool g_attr_set[64][32] = {{false}};
 // CTA-pair (cta_group::2) kernels unless VIPNERF_TC_CTA_PAIRS=0 (read once)
 const bool g_use_cta_pairs = []() { const char* e = getenv("VIPNERF_TC_CTA_PAIRS"); return e == nullptr || e[0] != '0'; }();
 
@@ -1542,16 +1640,16 @@ cudaError_t encode_weight_maps(const uint8_t* packed, bool split3, CUtensorMap (
   return cudaSuccess;
 }
 
-template <bool kSplit3, bool kFused, bool kProf, bool kPair>
+template <bool kSplit3, bool kFused, bool kProf, bool kPair, bool kSec>
 cudaError_t launch_variant(const TcParams& p, int64_t n_units, cudaStream_t s) {
   int dev = 0, sms = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
   if ((e = device_sm_count(&sms)) != cudaSuccess) return e;
-  auto kernel = k_render_tc<kSplit3, kFused, kProf, kPair>;
+  auto kernel = k_render_tc<kSplit3, kFused, kProf, kPair, kSec>;
   {
     std::lock_guard<std::mutex> lock(g_attr_mutex);
-    const int variant = (kSplit3 ? 2 : 0) + (kFused ? 1 : 0) + (kProf ? 4 : 0) + (kPair ? 8 : 0);
+    const int variant = (kSplit3 ? 2 : 0) + (kFused ? 1 : 0) + (kProf ? 4 : 0) + (kPair ? 8 : 0) + (kSec ? 16 : 0);
     if (dev >= 64 || !g_attr_set[dev][variant]) {
       e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
       if (e != cudaSuccess) return e;
@@ -1589,12 +1687,16 @@ cudaError_t launch(TcParams& p, int64_t n_units, cudaStream_t s) {
       if (e != cudaSuccess) return e;
     }
   }
-  if (p.prof != nullptr) {
-    return pair ? launch_variant<kSplit3, kFused, true, true>(p, n_units, s)
-                : launch_variant<kSplit3, kFused, true, false>(p, n_units, s);
+  if (p.fl.n_sec_views > 0) {   // secondary views: separate instantiations (no profiling variant)
+    return pair ? launch_variant<kSplit3, kFused, false, true, true>(p, n_units, s)
+                : launch_variant<kSplit3, kFused, false, false, true>(p, n_units, s);
   }
-  return pair ? launch_variant<kSplit3, kFused, false, true>(p, n_units, s)
-              : launch_variant<kSplit3, kFused, false, false>(p, n_units, s);
+  if (p.prof != nullptr) {
+    return pair ? launch_variant<kSplit3, kFused, true, true, false>(p, n_units, s)
+                : launch_variant<kSplit3, kFused, true, false, false>(p, n_units, s);
+  }
+  return pair ? launch_variant<kSplit3, kFused, false, true, false>(p, n_units, s)
+              : launch_variant<kSplit3, kFused, false, false, false>(p, n_units, s);
 }
 
 }  // namespace
@@ -1605,7 +1707,7 @@ void set_tc_profile_buffer(void* dev_ptr) {
 }
 
 cudaError_t launch_mlp_tc(int precision, const RayPtrs& rp, const RenderFlags& fl, int64_t n_rays, int S,
-                          const float* z, const void* packed, float* sigma, float* rgb, float* vis,
+                          const float* z, const void* packed, float* sigma, float* rgb, float* vis, float* vis2,
                           cudaStream_t s) {
   TcParams p{};
   p.rp = rp;
@@ -1616,6 +1718,8 @@ cudaError_t launch_mlp_tc(int precision, const RayPtrs& rp, const RenderFlags& f
   p.pass[0].sigma = sigma;
   p.pass[0].rgb = rgb;
   p.pass[0].vis = vis;
+  p.pass[0].vis2 = vis2;
+  if (vis2 == nullptr) p.fl.n_sec_views = 0;
   p.pass[0].n_points = n_rays * S;
   p.pass[0].S = S;
   p.pass[0].compute_z = 0;
@@ -1647,6 +1751,7 @@ cudaError_t launch_render_fused_tc(int precision, const FusedArgs& a, cudaStream
     d.sigma = o.raw_sigma ? o.raw_sigma : (pi ? a.ws_sigma : a.ws_sigma_c);
     d.rgb = o.raw_rgb ? o.raw_rgb : (pi ? a.ws_rgb : a.ws_rgb_c);
     d.vis = o.raw_visibility ? o.raw_visibility : (pi ? a.ws_vis : a.ws_vis_c);
+    d.vis2 = a.fl.n_sec_views > 0 ? (o.raw_visibility2 ? o.raw_visibility2 : (pi ? a.ws_vis2 : a.ws_vis2_c)) : nullptr;
     d.compute_z = pi == 0;
     p.out[pi] = o;
     p.out[pi].z_vals = nullptr;  // depths are produced in place

@@ -55,13 +55,16 @@ __global__ void k_pack_tc(ParamPtrs pp, uint8_t* __restrict__ big) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;  // one bf16 element of the hi image set
   if (i >= kTcBigBytes / 2) return;
   int l = 0;
-  while (l < kNumMatLayers - 1 && 2 * i >= tc_layer_byte_offset(l + 1)) ++l;
+  while (l < kNumTcLayers - 1 && 2 * i >= tc_layer_byte_offset(l + 1)) ++l;
   const int N = layer_n(l);
   const int e = i - tc_layer_byte_offset(l) / 2;          // element index inside the layer
   const int chunk = e / (N * kChunkK), r = e % (N * kChunkK);
   const int n = r / kChunkK, k_local = r % kChunkK;
   float w;
-  if (chunk == layer_chunks(l)) {                         // the layer's bias chunk: column 31 <-> encoding column 63
+  if (l == kViewChunkLayer) {                             // view-direction columns of views_linears.0, bias in column 31
+    w = k_local < kEncView ? pp.p[16][n * (kWidth + kEncView) + kWidth + k_local]
+                           : (k_local == kChunkK - 1 ? pp.p[17][n] : 0.f);
+  } else if (chunk == layer_chunks(l)) {                         // the layer's bias chunk: column 31 <-> encoding column 63
     w = k_local == kChunkK - 1 ? pp.p[bias_param(l)][n] : 0.f;
   } else {
     const int k = chunk * kChunkK + k_local;
