@@ -145,6 +145,54 @@ int vipnerf_composite(const vipnerf_cfg* cfg, const vipnerf_rays* rays, int64_t 
                       const float* z_vals, const float* sigma, const float* rgb, const float* vis2,
                       const vipnerf_pass_out* out, float* z_fine_out, void* stream);
 
+/* --- the steps either side of the path, on the device -----------------------------
+ *
+ * vipnerf_generate_rays replaces the per-pixel part of DataPreprocessor.create_test_data
+ * (src/data_preprocessors/DataPreprocessor01.py:776-864): get_rays :335-352 (pinhole direction K^-1 [x, y, 1],
+ * y/z flipped, rotated by the camera-to-world pose), get_view_dirs :376-378, get_ndc_rays :355-373, the near/far
+ * fills and the broadcast of the secondary camera centres (rays_o2, :851-854) for pixels
+ * [first_pixel, first_pixel + n_rays) of the frame in row-major order.  The 4x4 pose algebra
+ * (preprocess_poses :906-945) stays on the host: `pose` is the processed 3x4 camera-to-world matrix. */
+typedef struct vipnerf_camera {
+  int32_t height, width;
+  int32_t ndc;             /* also fill rays_o_ndc / rays_d_ndc / near_ndc / far_ndc                    */
+  int32_t n_sec_views;     /* V <= 8 secondary camera centres                                           */
+  int32_t has_view_pose;   /* view_dirs from view_kinv / view_pose instead of the render camera (:801-814) */
+  float kinv[9];           /* numpy.linalg.inv(intrinsic), row-major, fp32 (:345)                        */
+  float pose[12];          /* processed pose[:3, :4], row-major                                          */
+  float view_kinv[9];
+  float view_pose[12];
+  float near, far;         /* model_configs['near'], ['far']                                             */
+  float near_ndc, far_ndc; /* model_configs['near_ndc'], ['far_ndc']                                     */
+  float sx, sy;            /* -1 / (w / (2 fx)),  -1 / (h / (2 fy))   (:364-369)                         */
+  float sec_origins[24];   /* [V][3] processed secondary poses' translation column                       */
+} vipnerf_camera;
+
+/* Device buffers vipnerf_generate_rays fills (same keys as vipnerf_rays; NULL = not wanted). */
+typedef struct vipnerf_ray_buffers {
+  float* rays_o;      /* [R,3] */
+  float* rays_d;      /* [R,3] */
+  float* view_dirs;   /* [R,3] */
+  float* near;        /* [R,1] */
+  float* far;         /* [R,1] */
+  float* rays_o_ndc;  /* [R,3] */
+  float* rays_d_ndc;  /* [R,3] */
+  float* near_ndc;    /* [R,1] */
+  float* far_ndc;     /* [R,1] */
+  float* rays_o2;     /* [R,V,3] */
+} vipnerf_ray_buffers;
+
+int vipnerf_generate_rays(const vipnerf_camera* camera, int64_t first_pixel, int64_t n_rays,
+                          const vipnerf_ray_buffers* out, void* stream);
+
+/* vipnerf_postprocess_frame replaces DataPreprocessor.retrieve_inference_outputs' per-pixel work
+ * (DataPreprocessor01.py:866-894): post_process_image :1074-1078 (clip to [0,1], round(x * 255) half-to-even,
+ * uint8), post_process_depth :1080-1083 (clip to [0, inf)) for up to 4 depth-like maps, and the
+ * (h*w, V) -> (V, h*w) transpose of visibility2 (:887-890).  Any pointer may be NULL (skipped). */
+int vipnerf_postprocess_frame(int64_t n_rays, int32_t n_sec_views, const float* rgb, uint8_t* image_u8,
+                              int32_t n_depth_maps, const float* const* depth_in, float* const* depth_out,
+                              const float* visibility2, float* visibility2_out, void* stream);
+
 /* --- profiling aid (not part of the reference-facing path): a device buffer of 64 uint64 that CTA 0 of every
  * subsequent tensor-core launch fills with cycle counters of its warp roles (see tools/tc_cycle_breakdown.py);
  * NULL switches it off.  Process-global. */

@@ -15,6 +15,12 @@ def load_npz(name):
         return {k: torch.from_numpy(f[k]) for k in f.files}
 
 
+def load_npz_raw(name):
+    """numpy arrays (no torch conversion): frame fixtures hold uint8 / 0-d arrays"""
+    with numpy.load(os.path.join(GOLDEN, name)) as f:
+        return {k: f[k] for k in f.files}
+
+
 def split_io(arrays):
     inputs = {k[3:]: v for k, v in arrays.items() if k.startswith('in.')}
     outputs = {k[4:]: v for k, v in arrays.items() if k.startswith('out.')}

@@ -8,7 +8,7 @@ from __future__ import annotations
 import ctypes
 import os
 import threading
-from ctypes import POINTER, Structure, c_char_p, c_int, c_int32, c_int64, c_size_t, c_uint32, c_void_p
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_uint32, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'libvipnerf_b200.so')
@@ -45,6 +45,20 @@ class Out(Structure):
     _fields_ = [('coarse', PassOut), ('fine', PassOut)]
 
 
+class Camera(Structure):   # vipnerf_camera
+    _fields_ = [('height', c_int32), ('width', c_int32), ('ndc', c_int32), ('n_sec_views', c_int32),
+                ('has_view_pose', c_int32), ('kinv', c_float * 9), ('pose', c_float * 12), ('view_kinv', c_float * 9),
+                ('view_pose', c_float * 12), ('near', c_float), ('far', c_float), ('near_ndc', c_float),
+                ('far_ndc', c_float), ('sx', c_float), ('sy', c_float), ('sec_origins', c_float * 24)]
+
+
+RAY_BUFFER_FIELDS = RAY_FIELDS[:10]
+
+
+class RayBuffers(Structure):   # vipnerf_ray_buffers
+    _fields_ = [(name, c_float_p) for name in RAY_BUFFER_FIELDS]
+
+
 EXPORTS = {
     # name: (restype, argtypes)  -- must list every symbol include/vipnerf.h declares
     'vipnerf_abi_version': (c_int, []),
@@ -60,6 +74,9 @@ EXPORTS = {
     'vipnerf_coarse_z': (c_int, [POINTER(Cfg), POINTER(Rays), c_int64, c_void_p, c_void_p]),
     'vipnerf_composite': (c_int, [POINTER(Cfg), POINTER(Rays), c_int64, c_int32, c_void_p, c_void_p, c_void_p,
                                   c_void_p, POINTER(PassOut), c_void_p, c_void_p]),
+    'vipnerf_generate_rays': (c_int, [POINTER(Camera), c_int64, c_int64, POINTER(RayBuffers), c_void_p]),
+    'vipnerf_postprocess_frame': (c_int, [c_int64, c_int32, c_void_p, c_void_p, c_int32, POINTER(c_void_p),
+                                          POINTER(c_void_p), c_void_p, c_void_p, c_void_p]),
     'vipnerf_debug_set_profile_buffer': (c_int, [c_void_p]),
 }
 

@@ -142,6 +142,36 @@ const char* vipnerf_last_error(void) { return g_last_error.c_str(); }
 
 int vipnerf_check_config(const vipnerf_cfg* cfg) { return check_cfg(cfg); }
 
+int vipnerf_generate_rays(const vipnerf_camera* camera, int64_t first_pixel, int64_t n_rays,
+                          const vipnerf_ray_buffers* out, void* stream) {
+  if (camera == nullptr || out == nullptr) return fail(VIPNERF_EINVAL, "camera / out is NULL");
+  if (camera->height < 1 || camera->width < 1) return fail(VIPNERF_EINVAL, "resolution %d x %d", camera->height, camera->width);
+  if (camera->n_sec_views < 0 || camera->n_sec_views > 8) return fail(VIPNERF_EUNSUPPORTED, "n_sec_views=%d outside [0,8]", camera->n_sec_views);
+  if (n_rays < 0 || first_pixel < 0 || first_pixel + n_rays > (int64_t)camera->height * camera->width)
+    return fail(VIPNERF_EINVAL, "pixels [%lld, %lld) outside the %d x %d frame", (long long)first_pixel,
+                (long long)(first_pixel + n_rays), camera->height, camera->width);
+  if (n_rays == 0) return VIPNERF_OK;
+  if (camera->n_sec_views > 0 && out->rays_o2 == nullptr) return fail(VIPNERF_EINVAL, "n_sec_views=%d but rays_o2 is NULL", camera->n_sec_views);
+  cudaError_t e = launch_generate_rays(*camera, first_pixel, n_rays, *out, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return fail_cuda(e, "generate_rays");
+  return VIPNERF_OK;
+}
+
+int vipnerf_postprocess_frame(int64_t n_rays, int32_t n_sec_views, const float* rgb, uint8_t* image_u8,
+                              int32_t n_depth_maps, const float* const* depth_in, float* const* depth_out,
+                              const float* visibility2, float* visibility2_out, void* stream) {
+  if (n_rays < 0 || n_depth_maps < 0 || n_depth_maps > 4 || n_sec_views < 0)
+    return fail(VIPNERF_EINVAL, "n_rays=%lld n_depth_maps=%d n_sec_views=%d", (long long)n_rays, n_depth_maps, n_sec_views);
+  if (n_depth_maps > 0 && (depth_in == nullptr || depth_out == nullptr)) return fail(VIPNERF_EINVAL, "depth map lists are NULL");
+  for (int i = 0; i < n_depth_maps; ++i)
+    if (depth_in[i] == nullptr || depth_out[i] == nullptr) return fail(VIPNERF_EINVAL, "depth map %d is NULL", i);
+  if (n_rays == 0) return VIPNERF_OK;
+  cudaError_t e = launch_postprocess_frame(n_rays, n_sec_views, rgb, image_u8, n_depth_maps, depth_in, depth_out,
+                                           visibility2, visibility2_out, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return fail_cuda(e, "postprocess_frame");
+  return VIPNERF_OK;
+}
+
 int vipnerf_debug_set_profile_buffer(void* dev_u64x64) {
   set_tc_profile_buffer(dev_u64x64);
   return VIPNERF_OK;

@@ -66,6 +66,12 @@ struct FusedArgs {
 };
 
 cudaError_t launch_render_fused_tc(int precision, const FusedArgs& a, cudaStream_t s);
+// frame_kernels.cu : per-pixel ray generation and frame post-processing
+cudaError_t launch_generate_rays(const vipnerf_camera& camera, int64_t first_pixel, int64_t n_rays,
+                                 const vipnerf_ray_buffers& out, cudaStream_t s);
+cudaError_t launch_postprocess_frame(int64_t n_rays, int n_sec_views, const float* rgb, uint8_t* image, int n_depth,
+                                     const float* const* depth_in, float* const* depth_out, const float* vis2,
+                                     float* vis2_out, cudaStream_t s);
 // debug: 64 x u64 device buffer that CTA 0 of the next tensor-core launches fills with cycle counters (null = off)
 void set_tc_profile_buffer(void* dev_ptr);
 
