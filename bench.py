@@ -159,6 +159,97 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def run_frame(args, rank, world, local_rank):
+    """--workload frame: BASELINE config 5 - the LLFF 504x378 full-frame render (190,512 rays per step) STRONGLY
+    scaled over the ranks: every rank generates its pixel range on the device (vipnerf_generate_rays), renders it
+    with the fused kernel, ONE NCCL gather brings the per-ray maps to rank 0, which post-processes on the device and
+    copies the finished frame (uint8 image + depth maps) to the host.  All of that is inside the timed region; the
+    only per-step host input is the camera pose.  Prints one JSON line (informational: the default workload is the
+    4096-ray batch BASELINE.json quotes the metric on)."""
+    import numpy
+    import torch
+    import torch.distributed as dist
+    from oracle import vipnerf_oracle as O
+    from vipnerf_b200 import sharding
+    from vipnerf_b200.DataPreprocessorFactory import get_data_preprocessor
+    from vipnerf_b200.ModelFactory import get_model
+
+    torch.cuda.set_device(local_rank)
+    device = torch.device('cuda', local_rank)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=device)
+    sc = O.SCENES['fern_half']
+    h, w, f = sc['h'], sc['w'], sc['f']
+    R = h * w
+    cfg = model_configs(args.precision)
+    cfg['data_loader']['data_preprocessor_name'] = 'DataPreprocessorFused01'
+    cfg['device'] = [local_rank]
+    mc = {'resolution': [h, w], 'intrinsic': [[f, 0.0, w / 2], [0.0, f, h / 2], [0.0, 0.0, 1.0]],
+          'average_pose': numpy.eye(4).tolist(), 'translation_scale': 1, 'near': sc['near'], 'far': sc['far'],
+          'near_ndc': 0.0, 'far_ndc': 1.0}
+    dp = get_data_preprocessor(cfg, 'test', model_configs=mc)
+    model = get_model(cfg, mc)
+    model.load_state_dict(O.synth_state_dict(0))
+    model = model.to(device).eval()
+    poses = [numpy.concatenate([O._pose_from_seed(100 + i), [[0, 0, 0, 1]]], 0).astype(numpy.float32) for i in range(8)]
+    lo, hi = sharding.shard_range(R, rank, world)
+    keys = ('rgb_fine', 'depth_fine', 'depth_var_fine', 'depth_ndc_fine', 'depth_var_ndc_fine')
+
+    def step(i):
+        batch = dp.create_test_data(poses[i % len(poses)], preprocess_pose=False, first_pixel=lo, n_rays=hi - lo)
+        out = model(batch)
+        maps = {k: out[k] for k in keys}
+        if world > 1:
+            maps = sharding.gather_outputs(maps, R, None, 0)
+        if rank == 0:
+            return dp.postprocess(maps, '_fine')     # device post-processing + the single D2H copy (synchronises)
+        return None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.no_grad():
+        for i in range(args.warmup):
+            step(i)
+        barrier()
+        sampler = ClockSampler(local_rank)
+        t_ms = 0.0
+        frame = None
+        for i in range(args.steps):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            frame = step(i)
+            e.record()
+            torch.cuda.synchronize()
+            t_ms += s.elapsed_time(e)
+        barrier()
+        clocks = sampler.stop()
+    total = torch.tensor([t_ms], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(total, op=dist.ReduceOp.MAX)
+    total_ms = total.item()
+    if rank == 0:
+        value = R * args.steps / (total_ms * 1e-3)
+        line = {'metric': METRIC, 'value': value, 'unit': 'rays/s', 'n_gpus': world, 'steps': args.steps,
+                'warmup': args.warmup, 'ms_per_step': total_ms / args.steps, 'higher_is_better': True,
+                'scaling': 'strong', 'vs_baseline': None, 'dtype': args.precision, 'data': 'synthetic',
+                'config': {'workload': 'LLFF 504x378 full-frame render (190,512 rays per step), rays sharded over the GPUs, '
+                                       'on-device ray generation, one NCCL gather, device post-processing, finished frame to host',
+                           'rays_per_step': R, 'samples': '64+128', 'ndc': True, 'precision': args.precision,
+                           'frames_per_s': args.steps / (total_ms * 1e-3)},
+                'clocks': clocks,
+                'e2e': {'value': value, 'unit': 'rays/s', 'h2d_bytes_per_step': 0,
+                        'd2h_bytes_per_step': int(frame['image'].nbytes + sum(frame[k].nbytes for k in frame if k != 'image')),
+                        'note': 'the timed region IS end to end: pose in (kernel argument), finished frame out'},
+                'gpu_launches': args.steps * 3}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -168,6 +259,7 @@ def main():
     ap.add_argument('--precision', default='bf16', choices=['bf16', 'bf16x3', 'fp32'])
     ap.add_argument('--rays-per-step', type=int, default=RAYS_PER_STEP)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--workload', default='batch', choices=['batch', 'frame'])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
 
@@ -183,6 +275,9 @@ def main():
 
     if args.impl == 'reference':
         run_reference(args, rank, world)
+        return
+    if args.workload == 'frame':
+        run_frame(args, rank, world, local_rank)
         return
 
     import torch

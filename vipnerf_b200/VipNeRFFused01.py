@@ -77,18 +77,23 @@ class VipNeRFFused(torch.nn.Module):
                     raise NotImplementedError(f'{name} shape {shape}: kernels are built for (8, 256, 10, 4)')
         self._pack_lock = threading.Lock()
         self._packed: Dict[tuple, tuple] = {}
+        self._param_lists: Dict[str, list] = {}
 
     # ------------------------------------------------------------------ packed-weight cache
     def _packed_weights(self, which: str, precision: str, device) -> torch.Tensor:
         mlp = self.coarse_model if which == 'coarse' else self.fine_model
-        tensors = mlp.named_tensors()
-        version = tuple((t.data_ptr(), t._version) for t in tensors.values())
-        key = (which, precision, str(device))
+        # (storage address, in-place version) of every parameter: cheap to read, changes whenever an optimizer step,
+        # load_state_dict or .to() touches a weight
+        params = self._param_lists.get(which)
+        if params is None:   # nn.Parameter objects keep their identity through .to() / load_state_dict
+            params = self._param_lists[which] = list(mlp.parameters())
+        version = tuple([(t.data_ptr(), t._version) for t in params])
+        key = (which, precision, device.index)
         with self._pack_lock:
             hit = self._packed.get(key)
             if hit is not None and hit[0] == version:
                 return hit[1]
-            packed = renderpath.pack_mlp({k: v.detach() for k, v in tensors.items()}, precision)
+            packed = renderpath.pack_mlp({k: v.detach() for k, v in mlp.named_tensors().items()}, precision)
             self._packed[key] = (version, packed)
             return packed
 
