@@ -62,6 +62,8 @@ def test_generate_rays_pixel_ranges_tile_the_frame(scene, built_library):
              for lo, hi in zip(cuts[:-1], cuts[1:])]
     for k in whole:
         assert torch.equal(torch.cat([p[k] for p in parts], dim=0), whole[k]), k
+    for part in parts:      # every tensor must be usable as a render input: 16-byte aligned whatever the ray count
+        assert all(t.data_ptr() % 16 == 0 for t in part.values())
     with pytest.raises(Exception):
         dp.create_test_data(g['pose.render'], first_pixel=R - 3, n_rays=8)
 

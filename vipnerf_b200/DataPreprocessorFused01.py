@@ -133,16 +133,17 @@ class DataPreprocessorFused:
         if cam.ndc:
             widths.update({'rays_o_ndc': 3, 'rays_d_ndc': 3, 'near_ndc': 1, 'far_ndc': 1})
         # one allocation, one launch: every key is a contiguous slice of the same buffer
-        total = sum(widths.values()) + 3 * V
-        flat = torch.empty(max(R, 1) * total, dtype=torch.float32, device=self.device)
+        # (every slice starts on a 16-byte boundary, which the render entry points require)
+        if V > 0:
+            widths['rays_o2'] = 3 * V
+        pad4 = lambda n: (n + 3) // 4 * 4
+        flat = torch.empty(max(sum(pad4(R * wd) for wd in widths.values()), 4), dtype=torch.float32, device=self.device)
         batch, bufs, off = {}, _lib.RayBuffers(), 0
         for name, wd in widths.items():
-            batch[name] = flat[off:off + R * wd].view(R, wd)
+            t = flat[off:off + R * wd]
+            batch[name] = t.view(R, V, 3) if name == 'rays_o2' else t.view(R, wd)
             setattr(bufs, name, batch[name].data_ptr())
-            off += R * wd
-        if V > 0:
-            batch['rays_o2'] = flat[off:off + R * V * 3].view(R, V, 3)
-            bufs.rays_o2 = batch['rays_o2'].data_ptr()
+            off += pad4(R * wd)
         with torch.cuda.device(self.device):
             stream = torch.cuda.current_stream(self.device).cuda_stream
             _lib.check(lib.vipnerf_generate_rays(ctypes.byref(cam), first_pixel, R, ctypes.byref(bufs), stream),
