@@ -193,6 +193,20 @@ int vipnerf_postprocess_frame(int64_t n_rays, int32_t n_sec_views, const float* 
                               int32_t n_depth_maps, const float* const* depth_in, float* const* depth_out,
                               const float* visibility2, float* visibility2_out, void* stream);
 
+/* --- the visibility prior generator -----------------------------------------------
+ * Replaces VisibilityWeightsComputer.compute_weights
+ * (src/prior_generators/visibility/VisibilityMask02_NeRF_LLFF.py:27-35 = create_psv :41-47,
+ * compute_transformed_coordinates :49-82, bilinear_interpolation :84-162) for one ordered frame pair:
+ * weights[y, x] = exp(-min_d mean_c |warp_d(frame2)[y, x, c] - frame1[y, x, c]| / temperature) over the given depth
+ * planes, fp64 like the reference; mask = weights > 0.5 (start_generation :276-277; may be NULL).
+ * frame1 / frame2: DEVICE uint8 [h, w, 3]; k1inv = inv(intrinsic1), t = extrinsic2 @ inv(extrinsic1), k2 = intrinsic2
+ * and depth_planes_host[n_planes <= 256] are small HOST arrays (row-major fp64, made with the reference's own numpy
+ * expressions); weights: DEVICE fp64 [h, w]; mask: DEVICE uint8 [h, w]. */
+int vipnerf_visibility_prior(int32_t height, int32_t width, const uint8_t* frame1, const uint8_t* frame2,
+                             const double* k1inv_host, const double* t_host, const double* k2_host,
+                             const double* depth_planes_host, int32_t n_planes, double temperature,
+                             double* weights, uint8_t* mask, void* stream);
+
 /* --- profiling aid (not part of the reference-facing path): a device buffer of 64 uint64 that CTA 0 of every
  * subsequent tensor-core launch fills with cycle counters of its warp roles (see tools/tc_cycle_breakdown.py);
  * NULL switches it off.  Process-global. */

@@ -8,7 +8,7 @@ from __future__ import annotations
 import ctypes
 import os
 import threading
-from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_uint32, c_void_p
+from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_size_t, c_uint32, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'libvipnerf_b200.so')
@@ -77,6 +77,9 @@ EXPORTS = {
     'vipnerf_generate_rays': (c_int, [POINTER(Camera), c_int64, c_int64, POINTER(RayBuffers), c_void_p]),
     'vipnerf_postprocess_frame': (c_int, [c_int64, c_int32, c_void_p, c_void_p, c_int32, POINTER(c_void_p),
                                           POINTER(c_void_p), c_void_p, c_void_p, c_void_p]),
+    'vipnerf_visibility_prior': (c_int, [c_int32, c_int32, c_void_p, c_void_p, POINTER(c_double), POINTER(c_double),
+                                         POINTER(c_double), POINTER(c_double), c_int32, c_double, c_void_p, c_void_p,
+                                         c_void_p]),
     'vipnerf_debug_set_profile_buffer': (c_int, [c_void_p]),
 }
 

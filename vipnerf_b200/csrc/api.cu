@@ -172,6 +172,22 @@ int vipnerf_postprocess_frame(int64_t n_rays, int32_t n_sec_views, const float* 
   return VIPNERF_OK;
 }
 
+int vipnerf_visibility_prior(int32_t height, int32_t width, const uint8_t* frame1, const uint8_t* frame2,
+                             const double* k1inv_host, const double* t_host, const double* k2_host,
+                             const double* depth_planes_host, int32_t n_planes, double temperature,
+                             double* weights, uint8_t* mask, void* stream) {
+  if (height < 1 || width < 1) return fail(VIPNERF_EINVAL, "resolution %d x %d", height, width);
+  if (n_planes < 1 || n_planes > 256) return fail(VIPNERF_EUNSUPPORTED, "n_planes=%d outside [1,256]", n_planes);
+  if (!frame1 || !frame2 || !k1inv_host || !t_host || !k2_host || !depth_planes_host || !weights)
+    return fail(VIPNERF_EINVAL, "frame / matrix / planes / weights pointer is NULL");
+  if (!(temperature > 0.0)) return fail(VIPNERF_EINVAL, "temperature must be positive");
+  cudaError_t e = launch_visibility_weights(height, width, frame1, frame2, k1inv_host, t_host, k2_host,
+                                            depth_planes_host, n_planes, temperature, weights, mask,
+                                            static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return fail_cuda(e, "visibility_prior");
+  return VIPNERF_OK;
+}
+
 int vipnerf_debug_set_profile_buffer(void* dev_u64x64) {
   set_tc_profile_buffer(dev_u64x64);
   return VIPNERF_OK;

@@ -72,6 +72,10 @@ cudaError_t launch_generate_rays(const vipnerf_camera& camera, int64_t first_pix
 cudaError_t launch_postprocess_frame(int64_t n_rays, int n_sec_views, const float* rgb, uint8_t* image, int n_depth,
                                      const float* const* depth_in, float* const* depth_out, const float* vis2,
                                      float* vis2_out, cudaStream_t s);
+// prior_kernels.cu : plane-sweep-volume visibility weights (the visibility prior generator)
+cudaError_t launch_visibility_weights(int h, int w, const uint8_t* frame1, const uint8_t* frame2, const double k1inv[9],
+                                      const double t[16], const double k2[9], const double* planes_host, int n_planes,
+                                      double temperature, double* weights, uint8_t* mask, cudaStream_t s);
 // debug: 64 x u64 device buffer that CTA 0 of the next tensor-core launches fills with cycle counters (null = off)
 void set_tc_profile_buffer(void* dev_ptr);
 
