@@ -39,10 +39,10 @@ METRIC = 'rays/sec (coarse+fine, 64+128 samples) at 1/2/4/8 B200; PSNR vs ref'
 WORKLOAD = "LLFF 'fern' 3 input views, 64+128 coarse/fine, visibility head on, 4096-ray batches"
 
 
-def model_configs(precision):
+def model_configs(precision, ndc=True):
     mlp = dict(num_samples=64, netdepth=8, netwidth=256, points_positional_encoding_degree=10,
                views_positional_encoding_degree=4, use_view_dirs=True, view_dependent_rgb=True, predict_visibility=True)
-    return {'data_loader': {'ndc': True},
+    return {'data_loader': {'ndc': ndc},
             'model': dict(name='VipNeRFFused01', coarse_mlp=dict(mlp), fine_mlp=dict(mlp, num_samples=128), chunk=4096,
                           lindisp=False, netchunk=16384, perturb=True, raw_noise_std=1.0, white_bkgd=False,
                           precision=precision)}
@@ -179,10 +179,10 @@ def run_frame(args, rank, world, local_rank):
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl', device_id=device)
-    sc = O.SCENES['fern_half']
-    h, w, f = sc['h'], sc['w'], sc['f']
+    sc = O.SCENES['fern_half' if args.scene == 'fern' else 'dtu']   # BASELINE config 5 (LLFF 504x378) / 4 (DTU 400x300)
+    h, w, f, ndc = sc['h'], sc['w'], sc['f'], sc['ndc']
     R = h * w
-    cfg = model_configs(args.precision)
+    cfg = model_configs(args.precision, ndc)
     cfg['data_loader']['data_preprocessor_name'] = 'DataPreprocessorFused01'
     cfg['device'] = [local_rank]
     mc = {'resolution': [h, w], 'intrinsic': [[f, 0.0, w / 2], [0.0, f, h / 2], [0.0, 0.0, 1.0]],
@@ -194,7 +194,7 @@ def run_frame(args, rank, world, local_rank):
     model = model.to(device).eval()
     poses = [numpy.concatenate([O._pose_from_seed(100 + i), [[0, 0, 0, 1]]], 0).astype(numpy.float32) for i in range(8)]
     lo, hi = sharding.shard_range(R, rank, world)
-    keys = ('rgb_fine', 'depth_fine', 'depth_var_fine', 'depth_ndc_fine', 'depth_var_ndc_fine')
+    keys = ('rgb_fine', 'depth_fine', 'depth_var_fine') + (('depth_ndc_fine', 'depth_var_ndc_fine') if ndc else ())
 
     def step(i):
         batch = dp.create_test_data(poses[i % len(poses)], preprocess_pose=False, first_pixel=lo, n_rays=hi - lo)
@@ -236,9 +236,10 @@ def run_frame(args, rank, world, local_rank):
         line = {'metric': METRIC, 'value': value, 'unit': 'rays/s', 'n_gpus': world, 'steps': args.steps,
                 'warmup': args.warmup, 'ms_per_step': total_ms / args.steps, 'higher_is_better': True,
                 'scaling': 'strong', 'vs_baseline': None, 'dtype': args.precision, 'data': 'synthetic',
-                'config': {'workload': 'LLFF 504x378 full-frame render (190,512 rays per step), rays sharded over the GPUs, '
+                'config': {'workload': ('LLFF 504x378' if args.scene == 'fern' else 'DTU 400x300') +
+                                       f' full-frame render ({R:,} rays per step), rays sharded over the GPUs, '
                                        'on-device ray generation, one NCCL gather, device post-processing, finished frame to host',
-                           'rays_per_step': R, 'samples': '64+128', 'ndc': True, 'precision': args.precision,
+                           'rays_per_step': R, 'samples': '64+128', 'ndc': ndc, 'precision': args.precision,
                            'frames_per_s': args.steps / (total_ms * 1e-3)},
                 'clocks': clocks,
                 'e2e': {'value': value, 'unit': 'rays/s', 'h2d_bytes_per_step': 0,
@@ -260,6 +261,7 @@ def main():
     ap.add_argument('--rays-per-step', type=int, default=RAYS_PER_STEP)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--workload', default='batch', choices=['batch', 'frame'])
+    ap.add_argument('--scene', default='fern', choices=['fern', 'dtu'], help='camera of the frame workload')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
 
