@@ -4,24 +4,26 @@
 // Reference being replaced: VipNeRF.render_rays (src/models/VipNeRF01.py:74-171) = get_z_vals_coarse :173,
 // PositionalEncoder :416, MLP.forward :509-596, volume_rendering :331, get_z_vals_fine/sample_pdf :205-262.
 //
-// One persistent CTA per SM, 320 threads:
-//   warps 0-3  epilogue group 0  (owns tile slot 0: TMEM columns [0,256),   A buffer 0, encoding buffer 0)
-//   warps 4-7  epilogue group 1  (owns tile slot 1: TMEM columns [256,512), A buffer 1, encoding buffer 1)
-//   warp  8    weight producer   (one lane: cp.async.bulk 16 KiB weight chunk images -> 4-stage smem ring)
-//   warp  9    MMA issuer        (one lane: tcgen05.mma M=128 N=256 K=16, bf16 x bf16 -> fp32 in TMEM)
-//   warp  10   second weight producer (CTA pairs: warps 8 / 10 take the even / odd ring stages)
+// One persistent CTA per SM (clusters of two CTAs working on one tcgen05.mma.cta_group::2), 384 threads:
+//   warps 0-3  epilogue group 0  (owns tile slot 0: TMEM columns [0,256),   activation buffer 0)
+//   warps 4-7  epilogue group 1  (owns tile slot 1: TMEM columns [256,512), activation buffer 1)
+//   warp  8    weight producer   (one lane: tensor-map TMA copies of this CTA's half of the weight chunk images into
+//                                 the even stages of the shared-memory ring; all stages in the single-CTA variant)
+//   warp  9    MMA issuer        (leader CTA; one lane: tcgen05.mma M=256 N=256 K=16, bf16 x bf16 -> fp32 in TMEM)
+//   warp  10   second weight producer (CTA pairs: the odd ring stages)
 //   warp  11   ray warp          (fused kernel: alpha compositing + hierarchical re-sampling of the rays the slots'
 //                                 tiles complete, asynchronously to the slots' next tiles)
 // A "tile" is 128 consecutive sample points (rows).  A row's activations live in shared memory as bf16 in the
-// canonical K-major SWIZZLE_128B layout (four 16 KiB k-blocks of 128 rows x 64 columns); the accumulator of a
-// layer lives in the slot's 256 TMEM columns.  Per layer: the MMA warp streams the layer's weight chunks
-// against the slot's A buffer; when the last MMA retires (tcgen05.commit -> d_ready) the slot's epilogue group
-// pulls the accumulator with tcgen05.ld, adds bias, applies ReLU, rounds to bf16 and overwrites the A buffer in
-// place (the MMAs that read it have completed), then signals a_ready.  Two slots ping-pong so the tensor pipe
-// works on one tile while the other tile's epilogue runs on the CUDA cores.
-// The sample points, their sinusoidal encodings, the density / colour / visibility heads, and (fused kernel)
-// alpha compositing and hierarchical re-sampling are all done by the epilogue groups, so no per-sample
-// intermediate other than the 5 network outputs per sample leaves the SM.
+// canonical K-major SWIZZLE_128B layout (four 16 KiB k-blocks of 128 rows x 64 columns; the tile's point encoding
+// sits in k-block 0 while M0 and the encoding part of the skip layer run); the accumulator of a layer lives in the
+// slot's 256 TMEM columns.  Per step (step_desc): the MMA warp streams the step's weight chunks against the slot's
+// activation buffer; when the last MMA retires (tcgen05.commit -> d_ready) the slot's epilogue group pulls the
+// accumulator with tcgen05.ld (the bias was added by the tensor core), applies ReLU, rounds to bf16 and overwrites
+// the buffer in place (the MMAs that read it have completed), then signals a_ready.  Two slots ping-pong so the
+// tensor pipe works on one tile while the other tile's epilogue runs on the CUDA cores.
+// The sample points, their sinusoidal encodings and the density / colour / visibility heads are done by the epilogue
+// groups, alpha compositing and hierarchical re-sampling by the ray warp, so no per-sample intermediate other than
+// the 5 (+V) network outputs per sample leaves the SM.
 //
 // BF16X3 mode (parity mode): every operand is split x = hi + lo (both bf16) and each product is evaluated as
 // hi*hi + lo*hi + hi*lo in the fp32 accumulator (3 MMAs).  Slot 1's buffers hold the lo parts, so only one
@@ -101,9 +103,6 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -124,11 +123,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > kTimeoutCycles) mbar_timeout(bar, parity);
   }
-}
-__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-               "l"(src), "r"(bytes), "r"(bar)
-               : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -158,56 +152,6 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t rank
 // threads of the other CTA.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-// mbarrier.test_wait: non-blocking probe (try_wait may suspend the warp when the phase is not complete)
-__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n.reg .pred p;\nmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// One weight chunk (K = 32 = two K=16 steps) against the matching 64-byte half of an A k-block: two tcgen05.mma
-// issued by ONE elected lane from a single PTX block (descriptor start addresses advance by 32 B = 2 units per
-// step), followed by the commit that frees the weight stage.  `first_acc` = 0: the first MMA overwrites D.
-__device__ __forceinline__ void mma_chunk(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t first_acc,
-                                          uint32_t idesc, uint32_t empty_bar) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p, t, e;\n"
-      ".reg .b64 a1, b1;\n"
-      "setp.ne.b32 p, %3, 0;\n"
-      "setp.eq.b32 t, 0, 0;\n"
-      "add.s64 a1, %1, 2;\n add.s64 b1, %2, 2;\n"
-      "elect.sync _|e, 0xffffffff;\n"
-      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %4, p;\n"
-      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], a1, b1, %4, t;\n"
-      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%5];\n"
-      "}\n" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(first_acc), "r"(idesc), "r"(empty_bar)
-      : "memory");
-}
-// BF16X3 "hi" weight chunk: (A_hi + A_lo) x W_hi = four MMAs, then the commit.
-__device__ __forceinline__ void mma_chunk_split_hi(uint32_t d_tmem, uint64_t a_hi, uint64_t a_lo, uint64_t b_desc,
-                                                   uint32_t first_acc, uint32_t idesc, uint32_t empty_bar) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p, t, e;\n"
-      ".reg .b64 a1, l1, b1;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "setp.eq.b32 t, 0, 0;\n"
-      "add.s64 a1, %1, 2;\n add.s64 l1, %2, 2;\n add.s64 b1, %3, 2;\n"
-      "elect.sync _|e, 0xffffffff;\n"
-      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %3, %5, p;\n"
-      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %2, %3, %5, t;\n"
-      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], a1, b1, %5, t;\n"
-      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], l1, b1, %5, t;\n"
-      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%6];\n"
-      "}\n" ::"r"(d_tmem),
-      "l"(a_hi), "l"(a_lo), "l"(b_desc), "r"(first_acc), "r"(idesc), "r"(empty_bar)
-      : "memory");
 }
 // Position in the weight ring (stage index and the phase parity of its barriers) plus a cycle counter the
 // profiling builds report; every role keeps its own copy and advances it chunk by chunk.
