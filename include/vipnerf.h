@@ -207,6 +207,43 @@ int vipnerf_visibility_prior(int32_t height, int32_t width, const uint8_t* frame
                              const double* depth_planes_host, int32_t n_planes, double temperature,
                              double* weights, uint8_t* mask, void* stream);
 
+/* --- training: forward with saved activations + backward --------------------------
+ * Replaces what torch.autograd does for the reference's training step (src/Trainer01.py:93-102:
+ * `model(batch)` in train mode -> LossComputer.compute_losses -> `TotalLoss.backward()`): the forward of
+ * VipNeRF.render_rays with perturb / raw_noise_std active (VipNeRF01.py:194-202, :242, :549-552; retraw and
+ * sec_views_vis are forced on, :40) and the gradient of every parameter given the gradients of the outputs.
+ * The losses themselves stay the caller's (loss_functions/*.py operate on the returned tensors).
+ * Arithmetic: fp32 CUDA-core kernels (cfg->precision must be VIPNERF_PRECISION_FP32), like the reference's
+ * training arithmetic.  Random numbers are the caller's: rays->t_rand [R,Nc], rays->u_rand [R,Nf] (torch.rand) and
+ * sigma_noise_* = raw_noise_std * torch.randn, drawn exactly where the reference draws them; NULL = that source off.
+ *
+ * `saved` (vipnerf_train_saved_bytes, about 11 KB per sample point) receives the activations of both MLPs; the caller
+ * keeps it, together with the forward outputs z_vals / raw_sigma / raw_rgb / raw_visibility (/ raw_visibility2) of
+ * both sample sets, until vipnerf_train_backward.  `grad_out` has the layout of vipnerf_out and holds the upstream
+ * gradient of each output (NULL = zero; z_vals carries no gradient: sample positions are detached, :213).
+ * param_grads_*[24] = one fp32 device buffer per parameter tensor, same order and shapes as vipnerf_pack_weights'
+ * params; every element is overwritten.  packed_* must be VIPNERF_PRECISION_FP32 packs of the current weights. */
+size_t vipnerf_train_saved_bytes(const vipnerf_cfg* cfg, int64_t n_rays);
+size_t vipnerf_train_workspace_bytes(const vipnerf_cfg* cfg, int64_t n_rays);
+int vipnerf_train_forward(const vipnerf_cfg* cfg, const vipnerf_rays* rays, int64_t n_rays,
+                          const float* sigma_noise_coarse, const float* sigma_noise_fine, const void* packed_coarse,
+                          const void* packed_fine, const vipnerf_out* out, void* saved, size_t saved_bytes,
+                          void* workspace, size_t workspace_bytes, void* stream);
+int vipnerf_train_backward(const vipnerf_cfg* cfg, const vipnerf_rays* rays, int64_t n_rays, const void* packed_coarse,
+                           const void* packed_fine, const vipnerf_out* fwd_out, const vipnerf_out* grad_out,
+                           const void* saved, size_t saved_bytes, float* const param_grads_coarse[24],
+                           float* const param_grads_fine[24], void* workspace, size_t workspace_bytes, void* stream);
+
+/* Backward of volume_rendering alone (stage entry point of the parity tests; VipNeRF01.py:331-384 differentiated):
+ * given the network outputs of one sample set (sigma [R,S] after its ReLU, rgb [R,S,3] / vis [R,S] / vis2 [R,S,V] after
+ * their sigmoids) and the upstream gradients `grad_out` of the outputs, writes d_sigma_logit [R,S] (gradient w.r.t. the
+ * density logit, i.e. through the ReLU) and d_head_logits [R,S,1+V,4] (gradient w.r.t. the views_output_linear logits
+ * of the primary view [rgb, visibility] and of each secondary view [0, 0, 0, visibility2]). */
+int vipnerf_composite_backward(const vipnerf_cfg* cfg, const vipnerf_rays* rays, int64_t n_rays, int32_t n_samples,
+                               const float* z_vals, const float* sigma, const float* rgb, const float* vis,
+                               const float* vis2, const vipnerf_pass_out* grad_out, float* d_sigma_logit,
+                               float* d_head_logits, void* stream);
+
 /* --- profiling aid (not part of the reference-facing path): a device buffer of 64 uint64 that CTA 0 of every
  * subsequent tensor-core launch fills with cycle counters of its warp roles (see tools/tc_cycle_breakdown.py);
  * NULL switches it off.  Process-global. */

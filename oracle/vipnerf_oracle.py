@@ -171,6 +171,23 @@ def make_rays(scene: str, n_rays: int, seed: int = 1, n_sec_views: int = 0, firs
     return batch
 
 
+def make_supervision(scene: str, n_rays: int, n_sec: int, iter_num: int = 40000) -> dict:
+    """Synthetic supervision with the keys the reference's losses read (MSE01.py:30-31, SparseDepthMSE01.py:33-37,
+    VisibilityPriorLoss01.py:33-36): two thirds of the rays carry colour targets, the rest sparse depths."""
+    sc = SCENES[scene]
+    u = _splitmix_uniform(n_rays * 8, 4242).reshape(n_rays, 8)
+    mask_nerf = numpy.arange(n_rays) < (2 * n_rays) // 3
+    return {
+        'target_rgb': torch.from_numpy(u[:, :3].copy()),
+        'indices_mask_nerf': torch.from_numpy(mask_nerf),
+        'indices_mask_sparse_depth': torch.from_numpy(~mask_nerf),
+        'sparse_depth_values': torch.from_numpy((sc['near'] + u[:, 3:4] * (min(sc['far'], 8.0) - sc['near'])).astype('float32')),
+        'visibility_prior_masks': torch.from_numpy((u[:, 4:4 + n_sec] > 0.3).astype('float32')),
+        'iter_num': iter_num,
+        'num_frames': n_sec + 1,
+    }
+
+
 # --------------------------------------------------------------------------------------
 # Stage functions
 # --------------------------------------------------------------------------------------
@@ -306,7 +323,7 @@ def fine_z_vals(z_coarse: torch.Tensor, weights_coarse: torch.Tensor, n_fine: in
     """[R,Nc] -> [R,Nc+n_fine] sorted.  Reference: get_z_vals_fine :205-216 (mid-points as bins, the first
     and last coarse weight dropped, sort of the concatenation)."""
     mids = .5 * (z_coarse[..., 1:] + z_coarse[..., :-1])
-    samples = sample_pdf(mids, weights_coarse[..., 1:-1], n_fine, u)
+    samples = sample_pdf(mids, weights_coarse[..., 1:-1], n_fine, u).detach()   # :213
     z, _ = torch.sort(torch.cat([z_coarse, samples], -1), -1)
     return z
 
@@ -372,40 +389,79 @@ def composite(sigma: torch.Tensor, rgb: torch.Tensor, z_vals: torch.Tensor, ray_
 # Whole path
 # --------------------------------------------------------------------------------------
 
+def draw_training_randoms(n_rays: int, n_coarse: int = 64, n_fine: int = 128, chunk: int = 4096,
+                          netchunk: int = 16384, perturb: bool = True, raw_noise_std: float = 1.0,
+                          has_fine: bool = True) -> Dict[str, torch.Tensor]:
+    """Consumes torch's global CPU generator in exactly the order the reference's train-mode forward does and
+    returns the draws as whole-batch tensors: per `chunk` of rays (batchify_rays :54) first torch.rand [r,Nc]
+    (get_z_vals_coarse :200), then one torch.randn [n,1] per `netchunk` slice of the flattened coarse points
+    (batchify :305 -> get_view_independent_outputs :551), then torch.rand [r,Nf] (sample_pdf :242) and the
+    fine network's randn slices.  Keys: t_rand [R,Nc], u_rand [R,Nf], sigma_noise_coarse [R,Nc],
+    sigma_noise_fine [R,Nc+Nf] (already multiplied by raw_noise_std); a key is absent when its source is off."""
+    parts = {'t_rand': [], 'u_rand': [], 'sigma_noise_coarse': [], 'sigma_noise_fine': []}
+
+    def noise(n_points, r, s):
+        pieces = [torch.randn(min(netchunk, n_points - i), 1) * raw_noise_std for i in range(0, n_points, netchunk)]
+        return torch.cat(pieces, 0).reshape(r, s)
+
+    for i in range(0, n_rays, chunk):
+        r = min(chunk, n_rays - i)
+        if perturb:
+            parts['t_rand'].append(torch.rand(r, n_coarse))
+        if raw_noise_std > 0:
+            parts['sigma_noise_coarse'].append(noise(r * n_coarse, r, n_coarse))
+        if has_fine:
+            if perturb:
+                parts['u_rand'].append(torch.rand(r, n_fine))
+            if raw_noise_std > 0:
+                parts['sigma_noise_fine'].append(noise(r * (n_coarse + n_fine), r, n_coarse + n_fine))
+    return {k: torch.cat(v, 0) for k, v in parts.items() if v}
+
+
 def render(state_dict: Dict[str, torch.Tensor], batch: Dict[str, torch.Tensor], *, ndc: bool,
            n_coarse: int = 64, n_fine: int = 128, retraw: bool = False, sec_views_vis: bool = False,
            white_bkgd: bool = False, lindisp: bool = False, mode: str = 'fp32', has_fine: bool = True,
            chunk: int = 4096, netchunk: int = 16384,
-           forced_z_fine: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
-    """The eval-mode render of a ray batch: same output keys/shapes as `VipNeRF.forward`.
+           forced_z_fine: Optional[torch.Tensor] = None,
+           train_randoms: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
+    """The render of a ray batch: same output keys/shapes as `VipNeRF.forward`.
     Reference: forward :34-41, batchify_rays :47-72, render_rays :74-171, run_network :264-293,
-    batchify :295-329.  `forced_z_fine` (teacher forcing) replaces the fine sample positions."""
+    batchify :295-329.  `forced_z_fine` (teacher forcing) replaces the fine sample positions.
+    `train_randoms` (see draw_training_randoms) = train mode: stratified jitter, random cdf positions and density
+    noise from the given draws; retraw and sec_views_vis are then forced on like `forward` :40 does.  The result is
+    differentiable w.r.t. `state_dict` tensors that require grad (torch autograd = the gradient oracle)."""
     n = batch['rays_o'].shape[0]
+    if train_randoms is not None:
+        retraw, sec_views_vis = True, True
     outs = []
     for i in range(0, n, chunk):
         sub = {k: (v[i:i + chunk] if isinstance(v, torch.Tensor) and v.shape[0] == n else v)
                for k, v in batch.items()}
         fz = forced_z_fine[i:i + chunk] if forced_z_fine is not None else None
+        tr = {k: v[i:i + chunk] for k, v in train_randoms.items()} if train_randoms is not None else {}
         outs.append(_render_chunk(state_dict, sub, ndc, n_coarse, n_fine, retraw, sec_views_vis, white_bkgd,
-                                  lindisp, mode, has_fine, netchunk, fz))
+                                  lindisp, mode, has_fine, netchunk, fz, tr))
     return {k: torch.cat([o[k] for o in outs], dim=0) for k in outs[0]}
 
 
-def _run_mlp(params, pts, view_dirs, view_dirs2, mode, netchunk):
+def _run_mlp(params, pts, view_dirs, view_dirs2, mode, netchunk, sigma_noise=None):
     r, s = pts.shape[:2]
     pts_flat = pts.reshape(-1, 3)
     vd_flat = view_dirs[:, None, :].expand(r, s, 3).reshape(-1, 3)
     vd2_flat = view_dirs2.reshape(r * s, view_dirs2.shape[2], 3) if view_dirs2 is not None else None
+    noise_flat = sigma_noise.reshape(-1, 1) if sigma_noise is not None else None
     chunks = []
     for i in range(0, pts_flat.shape[0], netchunk):
         chunks.append(mlp_forward(params, pts_flat[i:i + netchunk], vd_flat[i:i + netchunk],
-                                  vd2_flat[i:i + netchunk] if vd2_flat is not None else None, mode=mode))
+                                  vd2_flat[i:i + netchunk] if vd2_flat is not None else None, mode=mode,
+                                  sigma_noise=noise_flat[i:i + netchunk] if noise_flat is not None else None))
     merged = {k: torch.cat([c[k] for c in chunks], dim=0) for k in chunks[0]}
     return {k: v.reshape(r, s, *v.shape[1:]) for k, v in merged.items()}
 
 
 def _render_chunk(sd, b, ndc, n_coarse, n_fine, retraw, sec_views_vis, white_bkgd, lindisp, mode, has_fine,
-                  netchunk, forced_z_fine):
+                  netchunk, forced_z_fine, train=None):
+    train = train or {}
     rays_o, rays_d, view_dirs = b['rays_o'], b['rays_d'], b['view_dirs']
     if ndc:
         p_o, p_d, near, far = b['rays_o_ndc'], b['rays_d_ndc'], b['near_ndc'], b['far_ndc']
@@ -417,7 +473,7 @@ def _render_chunk(sd, b, ndc, n_coarse, n_fine, retraw, sec_views_vis, white_bkg
     def one_pass(tag, params, z):
         pts = p_o[..., None, :] + p_d[..., None, :] * z[..., :, None]
         vd2 = other_view_dirs(z, rays_o, rays_d, rays_o2, ndc) if rays_o2 is not None else None
-        raw = _run_mlp(params, pts, view_dirs, vd2, mode, netchunk)
+        raw = _run_mlp(params, pts, view_dirs, vd2, mode, netchunk, train.get(f'sigma_noise_{tag}'))
         comp = composite(raw['sigma'][..., 0], raw['rgb'], z, p_d, ndc, rays_o, rays_d, white_bkgd,
                          raw['visibility2'][..., 0] if 'visibility2' in raw else None)
         ret[f'z_vals_{tag}'] = z
@@ -432,10 +488,10 @@ def _render_chunk(sd, b, ndc, n_coarse, n_fine, retraw, sec_views_vis, white_bkg
             ret[f'raw_rgb_{tag}'] = raw['rgb']
         return comp['weights']
 
-    z_c = coarse_z_vals(near, far, n_coarse, lindisp)
+    z_c = coarse_z_vals(near, far, n_coarse, lindisp, train.get('t_rand'))
     w_c = one_pass('coarse', split_state_dict(sd, 'coarse_model'), z_c)
     if has_fine:
-        z_f = forced_z_fine if forced_z_fine is not None else fine_z_vals(z_c, w_c, n_fine)
+        z_f = forced_z_fine if forced_z_fine is not None else fine_z_vals(z_c, w_c, n_fine, train.get('u_rand'))
         one_pass('fine', split_state_dict(sd, 'fine_model'), z_f)
     if not retraw:
         for tag in ('coarse', 'fine') if has_fine else ('coarse',):

@@ -48,7 +48,16 @@ def test_config_validation(built_library):
     x3 = _lib.make_cfg(precision='bf16x3')
     assert lib.vipnerf_packed_weight_bytes(ctypes.byref(x3)) == 27648 + 2 * ((72 + 7) * 16384 + 8192)
     f32 = _lib.make_cfg(precision='fp32')
-    assert lib.vipnerf_packed_weight_bytes(ctypes.byref(f32)) == 27648 + 589824 * 4
+    assert lib.vipnerf_packed_weight_bytes(ctypes.byref(f32)) == 27648 + (589824 + 557056) * 4   # forward + backward-data images
+    # training buffers: fp32 only; about 11 KB of saved activations per sample point
+    assert lib.vipnerf_train_saved_bytes(ctypes.byref(ok), 4096) == 0
+    f32v = _lib.make_cfg(precision='fp32', n_sec_views=1)
+    per_point = lib.vipnerf_train_saved_bytes(ctypes.byref(f32v), 4096) / (4096 * 256)
+    assert 10500 < per_point < 11500
+    assert lib.vipnerf_train_workspace_bytes(ctypes.byref(f32v), 4096) > 4096 * 192 * 9 * 1024
+    assert lib.vipnerf_train_forward(ctypes.byref(ok), None, 16, None, None, None, None, None, None, 0, None, 0, None) == -2
+    assert lib.vipnerf_train_forward(ctypes.byref(f32), None, 16, None, None, None, None, None, None, 0, None, 0, None) == -1
+    assert lib.vipnerf_train_backward(ctypes.byref(f32), None, 16, None, None, None, None, None, 0, None, None, None, 0, None) == -1
     assert lib.vipnerf_workspace_bytes(ctypes.byref(ok), 4096) > 4096 * (64 + 192 * 6) * 4
     bad = _lib.make_cfg(width=128)
     assert lib.vipnerf_check_config(ctypes.byref(bad)) == -2
@@ -92,16 +101,16 @@ def test_plugin_factory_and_state_dict():
         get_model({'data_loader': {'ndc': True}, 'model': {'name': 'NoSuchModel01'}}, None)
 
 
-def test_plugin_rejects_cpu_and_training():
+def test_plugin_rejects_cpu_tensors_and_unsupported_shapes():
     from oracle import vipnerf_oracle as O
     from vipnerf_b200.ModelFactory import get_model
     model = get_model(_configs(ndc=False), None).eval()
     batch = O.make_rays('dtu', 8)
     with pytest.raises(RuntimeError, match='no CPU fallback'):
         model(batch)
-    model.train()
-    with pytest.raises(NotImplementedError):
-        model(batch)
+    model.train()   # training mode has no CPU path either
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        model(O.make_rays('dtu', 8, n_sec_views=2))
     with pytest.raises(NotImplementedError):
         get_model(_configs(coarse_mlp=dict(_configs()['model']['coarse_mlp'], netwidth=128)), None)
 

@@ -8,9 +8,12 @@ as `VipNeRF.forward` (src/models/VipNeRF01.py:34-41, :128-133, :161-170, :366-38
 (`coarse_model.pts_linears.0.weight`, ... ) so reference checkpoints load unchanged
 (src/Tester01.py:45-49), usable under torch.nn.DataParallel (src/Tester01.py:42).
 
-Scope of this round: inference (`model.eval()` / `torch.no_grad()`).  Training forward+backward is the
-"next" row f1 of SURVEY.md section 8 and raises NotImplementedError.  There is no CPU fallback: inputs must be
-CUDA tensors and the shared library must be built.
+`model.eval()`: the fused tensor-core render (configs['model']['precision'], default bf16).  `model.train()`: the
+training step of SURVEY.md section 8 row f1 - train-mode forward (stratified jitter, random cdf samples, density noise
+drawn from torch's CPU generator in the reference's order; retraw and sec_views_vis forced on, VipNeRF01.py:40) and its
+backward through vipnerf_b200.training, in fp32 like the reference's training arithmetic, so that
+`loss.backward()` fills `.grad` of the same parameters the reference's optimizer steps (Trainer01.py:93-102, :519).
+There is no CPU fallback: inputs must be CUDA tensors and the shared library must be built.
 """
 from __future__ import annotations
 
@@ -19,7 +22,7 @@ from typing import Dict, Optional
 
 import torch
 
-from . import renderpath
+from . import renderpath, training
 
 
 class RadianceMLPParams(torch.nn.Module):
@@ -104,18 +107,14 @@ class VipNeRFFused(torch.nn.Module):
                 if isinstance(input_batch['common_data'][key], torch.Tensor):
                     input_batch['common_data'][key] = input_batch['common_data'][key][0]
         if self.training:
-            raise NotImplementedError(
-                'VipNeRFFused: training-mode forward (stratified jitter, density noise, autograd) is not part of '
-                'this build; call model.eval() for validation / test renders')
+            return self.render_train(input_batch)
         return self.render(input_batch, retraw=retraw, sec_views_vis=sec_views_vis)
 
-    def render(self, input_dict: dict, retraw: bool, sec_views_vis: bool):
+    def _ray_batch(self, input_dict: dict, sec_views_vis: bool):
         rays_o = input_dict['rays_o']
         if not isinstance(rays_o, torch.Tensor) or not rays_o.is_cuda:
             raise RuntimeError('VipNeRFFused needs CUDA tensors (move the batch with CommonUtils.move_to_device); '
                                'there is no CPU fallback')
-        device = rays_o.device
-        model_cfg = self.configs['model']
         batch = {k: input_dict[k] for k in ('rays_o', 'rays_d', 'view_dirs', 'near', 'far', 'rays_o_ndc',
                                             'rays_d_ndc', 'near_ndc', 'far_ndc') if k in input_dict}
         n_sec_views = 0
@@ -129,6 +128,29 @@ class VipNeRFFused(torch.nn.Module):
                 rays_o2 = torch.stack(others, dim=1)
             batch['rays_o2'] = rays_o2
             n_sec_views = rays_o2.shape[1]
+        return batch, n_sec_views
+
+    def render_train(self, input_dict: dict):
+        """Train-mode forward (VipNeRF01.py:40: retraw and sec_views_vis forced on), differentiable w.r.t. the
+        parameters; random numbers are drawn here, from torch's CPU generator, where the reference draws them."""
+        model_cfg = self.configs['model']
+        batch, n_sec_views = self._ray_batch(input_dict, True)
+        device = batch['rays_o'].device
+        n_coarse = model_cfg['coarse_mlp']['num_samples']
+        n_fine = model_cfg['fine_mlp']['num_samples'] if self.fine_mlp_needed else 0
+        draws = training.draw_training_randoms(
+            batch['rays_o'].shape[0], n_coarse, n_fine, model_cfg['chunk'], model_cfg['netchunk'],
+            model_cfg['perturb'] > 0, float(model_cfg['raw_noise_std']), self.fine_mlp_needed)
+        batch.update({k: v.to(device) for k, v in draws.items()})
+        return training.render_rays_train(
+            batch, self.coarse_model.named_tensors(), self.fine_model.named_tensors() if self.fine_mlp_needed else None,
+            ndc=self.ndc, n_coarse=n_coarse, n_fine=n_fine, n_sec_views=n_sec_views,
+            white_bkgd=model_cfg['white_bkgd'], lindisp=model_cfg['lindisp'])
+
+    def render(self, input_dict: dict, retraw: bool, sec_views_vis: bool):
+        batch, n_sec_views = self._ray_batch(input_dict, sec_views_vis)
+        device = batch['rays_o'].device
+        model_cfg = self.configs['model']
         # visibility2 runs on the tensor path too (one K=32 MMA step per secondary view); more than 8 views per
         # tile only fit the fp32 kernels
         precision = 'fp32' if n_sec_views > 8 else self.precision

@@ -80,6 +80,15 @@ EXPORTS = {
     'vipnerf_visibility_prior': (c_int, [c_int32, c_int32, c_void_p, c_void_p, POINTER(c_double), POINTER(c_double),
                                          POINTER(c_double), POINTER(c_double), c_int32, c_double, c_void_p, c_void_p,
                                          c_void_p]),
+    'vipnerf_train_saved_bytes': (c_size_t, [POINTER(Cfg), c_int64]),
+    'vipnerf_train_workspace_bytes': (c_size_t, [POINTER(Cfg), c_int64]),
+    'vipnerf_train_forward': (c_int, [POINTER(Cfg), POINTER(Rays), c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
+                                      POINTER(Out), c_void_p, c_size_t, c_void_p, c_size_t, c_void_p]),
+    'vipnerf_train_backward': (c_int, [POINTER(Cfg), POINTER(Rays), c_int64, c_void_p, c_void_p, POINTER(Out),
+                                       POINTER(Out), c_void_p, c_size_t, POINTER(c_void_p), POINTER(c_void_p),
+                                       c_void_p, c_size_t, c_void_p]),
+    'vipnerf_composite_backward': (c_int, [POINTER(Cfg), POINTER(Rays), c_int64, c_int32, c_void_p, c_void_p, c_void_p,
+                                           c_void_p, c_void_p, POINTER(PassOut), c_void_p, c_void_p, c_void_p]),
     'vipnerf_debug_set_profile_buffer': (c_int, [c_void_p]),
 }
 

@@ -132,6 +132,59 @@ PassOutPtrs to_dev(const vipnerf_pass_out* o) {
   return p;
 }
 
+PassGradPtrs to_grads(const vipnerf_pass_out* o) {
+  PassGradPtrs g{};
+  if (o == nullptr) return g;
+  g.rgb = o->rgb; g.acc = o->acc; g.depth = o->depth; g.depth_var = o->depth_var; g.depth_ndc = o->depth_ndc;
+  g.depth_var_ndc = o->depth_var_ndc; g.visibility2 = o->visibility2; g.alpha = o->alpha; g.visibility = o->visibility;
+  g.weights = o->weights; g.raw_sigma = o->raw_sigma; g.raw_rgb = o->raw_rgb; g.raw_visibility = o->raw_visibility;
+  g.raw_visibility2 = o->raw_visibility2;
+  return g;
+}
+
+// Activations the training forward keeps per sample set (floats; P points, nv = 1 + V views): kernels.h MlpSave
+struct SavedPass { size_t enc, h, feat, hv, pev, end; };
+struct SavedLayout { SavedPass coarse, fine; size_t total; };
+
+SavedLayout carve_saved(const vipnerf_cfg* cfg, int64_t n_rays) {
+  SavedLayout L{};
+  const size_t R = (size_t)(n_rays > 0 ? n_rays : 0), nv = 1 + (size_t)cfg->n_sec_views;
+  size_t off = 0;
+  auto take = [&](size_t floats) { size_t o = off; off = align_up(off + floats * sizeof(float), 256); return o; };
+  auto pass = [&](size_t P) {
+    SavedPass s{};
+    s.enc = take(P * 64); s.h = take(P * 256 * 8); s.feat = take(P * 256); s.hv = take(P * nv * 128); s.pev = take(P * nv * 32);
+    s.end = off;
+    return s;
+  };
+  L.coarse = pass(R * cfg->n_coarse);
+  if (cfg->n_fine > 0) L.fine = pass(R * ((size_t)cfg->n_coarse + cfg->n_fine));
+  L.total = off + 256;
+  return L;
+}
+
+// Scratch of the backward: sized for the larger sample set, reused by both
+struct BwdLayout { size_t dsig, dlogit, dpre, dfeat, dacc9, dhv, partial, total; };
+
+BwdLayout carve_bwd(const vipnerf_cfg* cfg, int64_t n_rays) {
+  BwdLayout L{};
+  const size_t R = (size_t)(n_rays > 0 ? n_rays : 0), nv = 1 + (size_t)cfg->n_sec_views;
+  const size_t P = R * ((size_t)cfg->n_coarse + cfg->n_fine);
+  size_t off = 0;
+  auto take = [&](size_t floats) { size_t o = off; off = align_up(off + floats * sizeof(float), 256); return o; };
+  L.dsig = take(P); L.dlogit = take(P * nv * 4); L.dpre = take(P * 256 * 8); L.dfeat = take(P * 256);
+  L.dacc9 = take(P * 128); L.dhv = take(P * nv * 128); L.partial = take(gemm_tn_partial_floats());
+  L.total = off + 256;
+  return L;
+}
+
+int check_train_cfg(const vipnerf_cfg* cfg) {
+  if (int rc = check_cfg(cfg)) return rc;
+  if (cfg->precision != VIPNERF_PRECISION_FP32)
+    return fail(VIPNERF_EUNSUPPORTED, "the training path computes in fp32 (cfg.precision=%d)", cfg->precision);
+  return VIPNERF_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -196,7 +249,7 @@ int vipnerf_debug_set_profile_buffer(void* dev_u64x64) {
 size_t vipnerf_packed_weight_bytes(const vipnerf_cfg* cfg) {
   if (check_cfg(cfg) != VIPNERF_OK) return 0;
   switch (cfg->precision) {
-    case VIPNERF_PRECISION_FP32: return kSmallBytes + (size_t)kFp32BigFloats * sizeof(float);
+    case VIPNERF_PRECISION_FP32: return kSmallBytes + (size_t)(kFp32BigFloats + kFp32BwdFloats) * sizeof(float);
     case VIPNERF_PRECISION_BF16: return kSmallBytes + (size_t)kTcBigBytes;
     default: return kSmallBytes + (size_t)2 * kTcBigBytes;
   }
@@ -330,6 +383,184 @@ int vipnerf_render_forward(const vipnerf_cfg* cfg, const vipnerf_rays* rays, int
     e = launch_composite(rp, fl, n_rays, S, z, sig, rgb, vis2, oo, cfg->n_fine, (pass == 0 && has_fine) ? z_f : nullptr, s);
     if (e != cudaSuccess) return fail_cuda(e, "composite");
   }
+  return VIPNERF_OK;
+}
+
+size_t vipnerf_train_saved_bytes(const vipnerf_cfg* cfg, int64_t n_rays) {
+  if (check_train_cfg(cfg) != VIPNERF_OK || n_rays < 0) return 0;
+  return carve_saved(cfg, n_rays).total;
+}
+
+size_t vipnerf_train_workspace_bytes(const vipnerf_cfg* cfg, int64_t n_rays) {
+  if (check_train_cfg(cfg) != VIPNERF_OK || n_rays < 0) return 0;
+  const size_t fwd = carve(cfg, n_rays).total, bwd = carve_bwd(cfg, n_rays).total;
+  return fwd > bwd ? fwd : bwd;
+}
+
+int vipnerf_train_forward(const vipnerf_cfg* cfg, const vipnerf_rays* rays, int64_t n_rays,
+                          const float* sigma_noise_coarse, const float* sigma_noise_fine, const void* packed_coarse,
+                          const void* packed_fine, const vipnerf_out* out, void* saved, size_t saved_bytes,
+                          void* workspace, size_t workspace_bytes, void* stream) {
+  if (int rc = check_train_cfg(cfg)) return rc;
+  if (n_rays == 0) return VIPNERF_OK;
+  RayPtrs rp{};
+  if (int rc = make_ray_ptrs(cfg, rays, &rp, true, true)) return rc;
+  if (n_rays < 0) return fail(VIPNERF_EINVAL, "n_rays=%lld", (long long)n_rays);
+  if (!packed_coarse || !out || !saved) return fail(VIPNERF_EINVAL, "packed_coarse / out / saved is NULL");
+  const bool has_fine = cfg->n_fine > 0;
+  if (has_fine && !packed_fine) return fail(VIPNERF_EINVAL, "n_fine=%d but packed_fine is NULL", cfg->n_fine);
+  if (misaligned(sigma_noise_coarse) || misaligned(sigma_noise_fine)) return fail(VIPNERF_EINVAL, "sigma_noise pointers must be 16-byte aligned");
+  const Workspace w = carve(cfg, n_rays);
+  const SavedLayout L = carve_saved(cfg, n_rays);
+  if (!workspace || workspace_bytes < w.total) return fail(VIPNERF_EWORKSPACE, "workspace %zu bytes < required %zu", workspace_bytes, w.total);
+  if (saved_bytes < L.total) return fail(VIPNERF_EWORKSPACE, "saved buffer %zu bytes < required %zu", saved_bytes, L.total);
+  if ((reinterpret_cast<uintptr_t>(workspace) & 255u) || (reinterpret_cast<uintptr_t>(saved) & 255u))
+    return fail(VIPNERF_EINVAL, "workspace / saved must be 256-byte aligned");
+  const PassOutPtrs oc = to_dev(&out->coarse), of = to_dev(&out->fine);
+  for (int pass = 0; pass < (has_fine ? 2 : 1); ++pass) {
+    const PassOutPtrs& o = pass ? of : oc;
+    if (!o.z_vals || !o.raw_sigma || !o.raw_rgb || !o.raw_visibility || (cfg->n_sec_views > 0 && !o.raw_visibility2))
+      return fail(VIPNERF_EINVAL, "training forward needs the z_vals / raw_sigma / raw_rgb / raw_visibility (/ raw_visibility2) outputs of both sample sets (the backward reads them)");
+  }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  uint8_t* sv = static_cast<uint8_t*>(saved);
+  const RenderFlags fl = make_flags(cfg);
+  const int Nc = cfg->n_coarse, Sf = cfg->n_coarse + cfg->n_fine;
+  cudaError_t e;
+  if ((e = launch_coarse_z(rp, n_rays, Nc, fl.lindisp, oc.z_vals, s)) != cudaSuccess) return fail_cuda(e, "coarse_z");
+  for (int pass = 0; pass < (has_fine ? 2 : 1); ++pass) {
+    const PassOutPtrs& o = pass ? of : oc;
+    const SavedPass& sp = pass ? L.fine : L.coarse;
+    const int S = pass ? Sf : Nc;
+    MlpSave ms{};
+    ms.noise = pass ? sigma_noise_fine : sigma_noise_coarse;
+    ms.enc = reinterpret_cast<float*>(sv + sp.enc); ms.h = reinterpret_cast<float*>(sv + sp.h);
+    ms.feat = reinterpret_cast<float*>(sv + sp.feat); ms.hv = reinterpret_cast<float*>(sv + sp.hv);
+    ms.pev = reinterpret_cast<float*>(sv + sp.pev);
+    float* vis2 = fl.n_sec_views ? o.raw_visibility2 : nullptr;
+    e = launch_mlp_fp32(rp, fl, n_rays, S, o.z_vals, pass ? packed_fine : packed_coarse, o.raw_sigma, o.raw_rgb,
+                        o.raw_visibility, vis2, s, &ms);
+    if (e != cudaSuccess) return fail_cuda(e, "mlp_fp32 (training)");
+    PassOutPtrs oo = o;
+    oo.z_vals = nullptr;
+    e = launch_composite(rp, fl, n_rays, S, o.z_vals, o.raw_sigma, o.raw_rgb, vis2, oo, cfg->n_fine,
+                         (pass == 0 && has_fine) ? of.z_vals : nullptr, s);
+    if (e != cudaSuccess) return fail_cuda(e, "composite");
+  }
+  return VIPNERF_OK;
+}
+
+int vipnerf_train_backward(const vipnerf_cfg* cfg, const vipnerf_rays* rays, int64_t n_rays, const void* packed_coarse,
+                           const void* packed_fine, const vipnerf_out* fwd_out, const vipnerf_out* grad_out,
+                           const void* saved, size_t saved_bytes, float* const param_grads_coarse[24],
+                           float* const param_grads_fine[24], void* workspace, size_t workspace_bytes, void* stream) {
+  if (int rc = check_train_cfg(cfg)) return rc;
+  RayPtrs rp{};
+  if (n_rays > 0)
+    if (int rc = make_ray_ptrs(cfg, rays, &rp, false, false)) return rc;
+  if (n_rays < 0) return fail(VIPNERF_EINVAL, "n_rays=%lld", (long long)n_rays);
+  const bool has_fine = cfg->n_fine > 0;
+  if (!packed_coarse || !fwd_out || !grad_out || !param_grads_coarse) return fail(VIPNERF_EINVAL, "packed_coarse / fwd_out / grad_out / param_grads_coarse is NULL");
+  if (has_fine && (!packed_fine || !param_grads_fine)) return fail(VIPNERF_EINVAL, "n_fine=%d but packed_fine / param_grads_fine is NULL", cfg->n_fine);
+  for (int i = 0; i < 24; ++i)
+    if (!param_grads_coarse[i] || (has_fine && !param_grads_fine[i])) return fail(VIPNERF_EINVAL, "param_grads[%d] is NULL", i);
+  const SavedLayout L = carve_saved(cfg, n_rays);
+  const BwdLayout B = carve_bwd(cfg, n_rays);
+  if (n_rays > 0 && (!saved || saved_bytes < L.total)) return fail(VIPNERF_EWORKSPACE, "saved buffer %zu bytes < required %zu", saved_bytes, L.total);
+  if (!workspace || workspace_bytes < B.total) return fail(VIPNERF_EWORKSPACE, "workspace %zu bytes < required %zu", workspace_bytes, B.total);
+  if ((reinterpret_cast<uintptr_t>(workspace) & 255u) || (reinterpret_cast<uintptr_t>(saved) & 255u))
+    return fail(VIPNERF_EINVAL, "workspace / saved must be 256-byte aligned");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const uint8_t* sv = static_cast<const uint8_t*>(saved);
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  auto wf = [&](size_t off) { return reinterpret_cast<float*>(ws + off); };
+  const RenderFlags fl = make_flags(cfg);
+  const int nv = 1 + cfg->n_sec_views;
+  const int Nc = cfg->n_coarse, Sf = cfg->n_coarse + cfg->n_fine;
+  cudaError_t e;
+  // shapes of the 24 parameter tensors (vipnerf_pack_weights order), for the empty-batch zero fill
+  static const int kParamFloats[24] = {256 * 63, 256, 65536, 256, 65536, 256, 65536, 256, 65536, 256, 256 * 319, 256,
+                                       65536, 256, 65536, 256, 128 * 283, 128, 256, 1, 65536, 256, 512, 4};
+  for (int pass = 0; pass < (has_fine ? 2 : 1); ++pass) {
+    float* const* pg = pass ? param_grads_fine : param_grads_coarse;
+    if (n_rays == 0) {  // no rays: every gradient is zero
+      for (int i = 0; i < 24; ++i)
+        if ((e = cudaMemsetAsync(pg[i], 0, kParamFloats[i] * sizeof(float), s)) != cudaSuccess) return fail_cuda(e, "memset");
+      continue;
+    }
+    const vipnerf_pass_out& fo = pass ? fwd_out->fine : fwd_out->coarse;
+    const SavedPass& sp = pass ? L.fine : L.coarse;
+    const int S = pass ? Sf : Nc;
+    const int64_t P = n_rays * S;
+    if (!fo.z_vals || !fo.raw_sigma || !fo.raw_rgb || !fo.raw_visibility || (cfg->n_sec_views > 0 && !fo.raw_visibility2))
+      return fail(VIPNERF_EINVAL, "fwd_out must hold z_vals / raw_sigma / raw_rgb / raw_visibility (/ raw_visibility2) of both sample sets");
+    const float* enc = reinterpret_cast<const float*>(sv + sp.enc);
+    const float* h = reinterpret_cast<const float*>(sv + sp.h);
+    const float* feat = reinterpret_cast<const float*>(sv + sp.feat);
+    const float* hv = reinterpret_cast<const float*>(sv + sp.hv);
+    const float* pev = reinterpret_cast<const float*>(sv + sp.pev);
+    float* dsig = wf(B.dsig); float* dlogit = wf(B.dlogit); float* dpre = wf(B.dpre); float* dfeat = wf(B.dfeat);
+    float* dacc9 = wf(B.dacc9); float* dhv = wf(B.dhv); float* partial = wf(B.partial);
+
+    // 1. volume_rendering backwards -> logit gradients per sample
+    e = launch_composite_bwd(rp, fl, n_rays, S, fo.z_vals, fo.raw_sigma, fo.raw_rgb, fo.raw_visibility,
+                             cfg->n_sec_views ? fo.raw_visibility2 : nullptr,
+                             to_grads(pass ? &grad_out->fine : &grad_out->coarse), dsig, dlogit, s);
+    if (e != cudaSuccess) return fail_cuda(e, "composite_bwd");
+    // 2. backward-data chain through the MLP
+    MlpBwdArgs a{};
+    a.n_points = P; a.nviews = nv; a.dsig = dsig; a.dlogit = dlogit; a.h = h; a.hv = hv;
+    a.dpre = dpre; a.dfeat = dfeat; a.dacc9 = dacc9; a.dhv = dhv;
+    if ((e = launch_mlp_bwd_fp32(a, pass ? packed_fine : packed_coarse, s)) != cudaSuccess) return fail_cuda(e, "mlp_bwd_fp32");
+    // 3. parameter gradients: dW = dY^T X over all points, db = column sums of dY
+    const size_t PL = (size_t)P * 256;
+    for (int l = 0; l < 8 && e == cudaSuccess; ++l) {
+      const float* dy = dpre + l * PL;
+      float* dw = pg[2 * l];
+      float* db = pg[2 * l + 1];
+      if (l == 0) {
+        e = launch_gemm_tn(dy, 256, 256, enc, 64, 64, P, dw, kEncPts, kEncPts, db, partial, s);
+      } else if (l == 5) {   // input = cat([encoding, h4]) (:543-544)
+        e = launch_gemm_tn(dy, 256, 256, enc, 64, 64, P, dw, kWidth + kEncPts, kEncPts, db, partial, s);
+        if (e == cudaSuccess)
+          e = launch_gemm_tn(dy, 256, 256, h + 4 * PL, 256, 256, P, dw + kEncPts, kWidth + kEncPts, 256, nullptr, partial, s);
+      } else {
+        e = launch_gemm_tn(dy, 256, 256, h + (l - 1) * PL, 256, 256, P, dw, 256, 256, db, partial, s);
+      }
+    }
+    if (e != cudaSuccess) return fail_cuda(e, "gemm_tn (pts_linears)");
+    // feature_linear (input h7 = output of pts_linears.7)
+    if ((e = launch_gemm_tn(dfeat, 256, 256, h + 7 * PL, 256, 256, P, pg[20], 256, 256, pg[21], partial, s)) != cudaSuccess)
+      return fail_cuda(e, "gemm_tn (feature_linear)");
+    // views_linears.0: feature columns over points, direction columns and bias over (point, view) rows
+    if ((e = launch_gemm_tn(dacc9, 128, 128, feat, 256, 256, P, pg[16], kWidth + kEncView, 256, nullptr, partial, s)) != cudaSuccess)
+      return fail_cuda(e, "gemm_tn (views_linears feature columns)");
+    if ((e = launch_gemm_tn(dhv, 128, 128, pev, 32, 32, P * nv, pg[16] + kWidth, kWidth + kEncView, kEncView, pg[17], partial, s)) != cudaSuccess)
+      return fail_cuda(e, "gemm_tn (views_linears direction columns)");
+    // views_output_linear [4][128] and pts_output_linear [1][256]
+    if ((e = launch_small_tn(dlogit, 4, hv, 128, P * nv, pg[22], pg[23], partial, s)) != cudaSuccess)
+      return fail_cuda(e, "small_tn (views_output_linear)");
+    if ((e = launch_small_tn(dsig, 1, h + 7 * PL, 256, P, pg[18], pg[19], partial, s)) != cudaSuccess)
+      return fail_cuda(e, "small_tn (pts_output_linear)");
+  }
+  return VIPNERF_OK;
+}
+
+int vipnerf_composite_backward(const vipnerf_cfg* cfg, const vipnerf_rays* rays, int64_t n_rays, int32_t n_samples,
+                               const float* z_vals, const float* sigma, const float* rgb, const float* vis,
+                               const float* vis2, const vipnerf_pass_out* grad_out, float* d_sigma_logit,
+                               float* d_head_logits, void* stream) {
+  if (int rc = check_cfg(cfg)) return rc;
+  if (n_rays == 0) return VIPNERF_OK;
+  RayPtrs rp{};
+  if (int rc = make_ray_ptrs(cfg, rays, &rp, false, false, false)) return rc;
+  if (n_rays < 0 || n_samples < 3 || n_samples > 256) return fail(VIPNERF_EINVAL, "n_rays=%lld n_samples=%d", (long long)n_rays, n_samples);
+  if (!z_vals || !sigma || !rgb || !vis || !grad_out || !d_sigma_logit || !d_head_logits)
+    return fail(VIPNERF_EINVAL, "z_vals / sigma / rgb / vis / grad_out / outputs is NULL");
+  if (cfg->n_sec_views > 0 && !vis2) return fail(VIPNERF_EINVAL, "n_sec_views=%d but vis2 is NULL", cfg->n_sec_views);
+  cudaError_t e = launch_composite_bwd(rp, make_flags(cfg), n_rays, n_samples, z_vals, sigma, rgb, vis, vis2,
+                                       to_grads(grad_out), d_sigma_logit, d_head_logits, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return fail_cuda(e, "composite_bwd");
   return VIPNERF_OK;
 }
 

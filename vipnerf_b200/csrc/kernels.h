@@ -36,9 +36,53 @@ cudaError_t launch_composite(const RayPtrs& rp, const RenderFlags& fl, int64_t n
                              const float* sigma, const float* rgb, const float* vis2, const PassOutPtrs& out,
                              int n_fine, float* z_fine_out, cudaStream_t s);
 
-// mlp_fp32.cu : CUDA-core evaluation of the MLP on R*S sample points (pts = pts_o + pts_d * z)
+// Training: what the forward of one sample set keeps for its backward (point-major fp32, P = R*S points,
+// nviews = 1 + V view directions per point).
+struct MlpSave {
+  const float* noise;  // [P] raw_noise_std * randn added to the density logit (VipNeRF01.py:549-552), or null
+  float* enc;          // [P][64]   positional encoding (column 63 = 0)
+  float* h;            // [8][P][256] outputs of pts_linears.0..7 (post-ReLU)
+  float* feat;         // [P][256]  feature_linear output
+  float* hv;           // [P][nviews][128] views_linears.0 output (post-ReLU) per view
+  float* pev;          // [P][nviews][32]  view-direction encodings (27 used)
+};
+struct MlpBwdArgs {
+  int64_t n_points;
+  int nviews;
+  const float* dsig;    // [P]            gradient w.r.t. the density logit (after the ReLU mask)
+  const float* dlogit;  // [P][nviews][4] gradient w.r.t. the views_output_linear logits
+  const float* h;       // saved activations
+  const float* hv;
+  float* dpre;          // [8][P][256] pre-activation gradients of pts_linears.0..7
+  float* dfeat;         // [P][256]    gradient w.r.t. the feature vector
+  float* dacc9;         // [P][128]    pre-activation gradient of views_linears.0 summed over views
+  float* dhv;           // [P][nviews][128] the same per view
+};
+
+// mlp_fp32.cu : CUDA-core evaluation of the MLP on R*S sample points (pts = pts_o + pts_d * z); `save` != null =
+// training forward.  launch_mlp_bwd_fp32 = the backward-data chain of the same points.
 cudaError_t launch_mlp_fp32(const RayPtrs& rp, const RenderFlags& fl, int64_t n_rays, int S, const float* z,
-                            const void* packed, float* sigma, float* rgb, float* vis, float* vis2, cudaStream_t s);
+                            const void* packed, float* sigma, float* rgb, float* vis, float* vis2, cudaStream_t s,
+                            const MlpSave* save = nullptr);
+cudaError_t launch_mlp_bwd_fp32(const MlpBwdArgs& a, const void* packed, cudaStream_t s);
+
+// train_kernels.cu : backward of volume_rendering and the parameter-gradient reductions
+struct PassGradPtrs {  // upstream gradients of one sample set's outputs (null = zero)
+  const float *rgb, *acc, *depth, *depth_var, *depth_ndc, *depth_var_ndc, *visibility2;
+  const float *alpha, *visibility, *weights, *raw_sigma, *raw_rgb, *raw_visibility, *raw_visibility2;
+};
+cudaError_t launch_composite_bwd(const RayPtrs& rp, const RenderFlags& fl, int64_t n_rays, int S, const float* z,
+                                 const float* sigma, const float* rgb, const float* vis, const float* vis2,
+                                 const PassGradPtrs& g, float* dsig, float* dlogit, cudaStream_t s);
+// C[m][n] = sum_p A[p][m] * B[p][n] over n_rows rows (A: lda floats per row, M in {128, 256}; B: ldb floats per row,
+// N in {32, 64, 128, 256}), written to dst[m * ldc + n] for n < n_valid; bias_dst[m] = sum_p A[p][m] when non-null.
+// `partial` must hold gemm_tn_partial_floats() floats.
+size_t gemm_tn_partial_floats();
+cudaError_t launch_gemm_tn(const float* A, int lda, int M, const float* B, int ldb, int N, int64_t n_rows, float* dst,
+                           int ldc, int n_valid, float* bias_dst, float* partial, cudaStream_t s);
+// out[m][n] = sum_p G[p][m] * H[p][n] for M <= 4 (G: M floats per row), N <= 256; gsum_dst[m] = sum_p G[p][m].
+cudaError_t launch_small_tn(const float* G, int M, const float* H, int N, int64_t n_rows, float* dst, float* gsum_dst,
+                            float* partial, cudaStream_t s);
 
 // mlp_tc.cu : tcgen05 evaluation (precision = BF16 or BF16X3)
 cudaError_t launch_mlp_tc(int precision, const RayPtrs& rp, const RenderFlags& fl, int64_t n_rays, int S,

@@ -54,6 +54,14 @@ __host__ __device__ constexpr int fp32_layer_offset(int l) {
   return off;
 }
 constexpr int kFp32BigFloats = fp32_layer_offset(kNumMatLayers);  // 589,824
+// ---- fp32 backward region (training, behind the forward region): the matrices of the backward-data chain
+// dX = dY . W, i.e. the nn.Linear weights in their original [out][in] orientation restricted to the 256 hidden /
+// feature input columns, in the order the chain consumes them: views_linears.0[:, :256] (128 rows),
+// feature_linear, pts_linears.7 .. pts_linears.1 (pts_linears.5: columns 63..318).
+constexpr int kBwdOffViews = 0;
+constexpr int kBwdOffFeature = kBwdOffViews + 128 * 256;
+constexpr int kBwdOffTrunk = kBwdOffFeature + 256 * 256;
+constexpr int kFp32BwdFloats = kBwdOffTrunk + 7 * 256 * 256;      // 557,056
 
 // ---- tensor-core big region: "chunk images".  One chunk = ALL output rows (n) of a layer x 32 k-columns of
 // bf16 in the canonical K-major SWIZZLE_64B shared-memory layout tcgen05.mma reads (64-byte rows, 8-row / 512-byte

@@ -50,6 +50,24 @@ __global__ void k_pack_fp32(ParamPtrs pp, float* __restrict__ big) {
   big[i] = source_weight(pp, l, n, k);
 }
 
+// backward-data images of the training path (layout.cuh): original [out][in] rows, hidden input columns only
+__global__ void k_pack_fp32_bwd(ParamPtrs pp, float* __restrict__ bwd) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= kFp32BwdFloats) return;
+  float v;
+  if (i < kBwdOffFeature) {
+    const int o = i / 256, c = i % 256;
+    v = pp.p[16][o * (kWidth + kEncView) + c];
+  } else if (i < kBwdOffTrunk) {
+    v = pp.p[20][i - kBwdOffFeature];
+  } else {
+    const int e = i - kBwdOffTrunk;
+    const int l = 7 - e / 65536, o = (e % 65536) / 256, c = e % 256;
+    v = l == 5 ? pp.p[10][o * (kWidth + kEncPts) + kEncPts + c] : pp.p[2 * l][o * 256 + c];
+  }
+  bwd[i] = v;
+}
+
 template <bool kSplit3>
 __global__ void k_pack_tc(ParamPtrs pp, uint8_t* __restrict__ big) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;  // one bf16 element of the hi image set
@@ -92,6 +110,7 @@ cudaError_t launch_pack_weights(int precision, const float* const params_dev[24]
   k_pack_small<<<(kSmallFloats + 255) / 256, 256, 0, s>>>(pp, small);
   if (precision == VIPNERF_PRECISION_FP32) {
     k_pack_fp32<<<(kFp32BigFloats + 255) / 256, 256, 0, s>>>(pp, reinterpret_cast<float*>(big));
+    k_pack_fp32_bwd<<<(kFp32BwdFloats + 255) / 256, 256, 0, s>>>(pp, reinterpret_cast<float*>(big) + kFp32BigFloats);
   } else {
     const int n = kTcBigBytes / 2;
     if (precision == VIPNERF_PRECISION_BF16X3) k_pack_tc<true><<<(n + 255) / 256, 256, 0, s>>>(pp, big);

@@ -1,0 +1,429 @@
+// Training backward of the render path: the gradient of volume_rendering and the
+// parameter-gradient reductions.  The reference gets these from torch.autograd over its op graph
+// (Trainer01.py:93-102: model(batch) -> LossComputer -> loss.backward()); here each is one explicit kernel.
+//
+//  k_composite_bwd  one warp per ray, the mirror image of composite_ray (stages.cuh): re-computes alpha /
+//                   transmittance / weights from (z, sigma), turns the upstream gradients of every output of
+//                   volume_rendering (VipNeRF01.py:331-384) into gradients of the per-sample network outputs with
+//                   warp-shuffle scans (the cumprod's backward is an exclusive SUFFIX sum along the ray), and folds in
+//                   the ReLU / sigmoid derivatives of the heads, so that what leaves the kernel are logit gradients.
+//  k_gemm_tn        dW = dY^T X: C[m][n] = sum_p A[p][m] B[p][n], the reduction running over ALL sample points
+//                   (about 10^6 per batch).  fp32 FFMA with 128 x BN tiles; the point range is split over the grid,
+//                   partial tiles go to a scratch buffer and k_reduce_partials adds them in a fixed order, so
+//                   gradients are bit-reproducible run to run (no atomics).  Bias gradients (column sums of dY) ride
+//                   along in the threads that already hold the dY values.
+//  k_small_tn       the same for the 1- and 4-row heads (pts_output_linear, views_output_linear): HBM-bound streaming.
+#include <cuda_runtime.h>
+
+#include "kernels.h"
+#include "layout.cuh"
+
+namespace vipnerf {
+namespace {
+
+// ---------------------------------------------------------------------------------------------------------------
+template <int SPL>
+__global__ void __launch_bounds__(128)
+k_composite_bwd(RayPtrs rp, RenderFlags fl, int64_t n_rays, int S, const float* __restrict__ z,
+                const float* __restrict__ sigma, const float* __restrict__ rgb, const float* __restrict__ vis,
+                const float* __restrict__ vis2, PassGradPtrs G, float* __restrict__ dsig, float* __restrict__ dlogit) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t ray = (int64_t)blockIdx.x * 4 + warp;
+  if (ray >= n_rays) return;
+  const int V = fl.n_sec_views, nviews = 1 + V;
+  const bool ndc = fl.ndc;
+  const float dnorm = vec3_norm(rp.pts_d[3 * ray], rp.pts_d[3 * ray + 1], rp.pts_d[3 * ray + 2]);
+  const float oz = rp.rays_o[3 * ray + 2], dz = rp.rays_d[3 * ray + 2];
+  const int base = lane * SPL;
+  const float* zr = z + ray * S;
+  const float* sr = sigma + ray * S;
+
+  // ---- forward quantities, exactly as composite_ray computes them
+  float zz[SPL], al[SPL], om[SPL], ex[SPL], dl[SPL], tr[SPL], w[SPL], sg[SPL];
+#pragma unroll
+  for (int j = 0; j < SPL; ++j) {
+    const int i = base + j;
+    const bool valid = i < S;
+    zz[j] = valid ? zr[i] : 0.f;
+    const float z_next = (i + 1 < S) ? zr[i + 1] : (ndc ? 1.f : 1e10f);
+    dl[j] = fmul(fsub(z_next, zz[j]), dnorm);
+    sg[j] = valid ? sr[i] : 0.f;
+    ex[j] = expf(fmul(-sg[j], dl[j]));
+    al[j] = valid ? fsub(1.f, ex[j]) : 0.f;
+    om[j] = fadd(fsub(1.f, al[j]), 1e-10f);
+  }
+  float incl = 1.f;
+#pragma unroll
+  for (int j = 0; j < SPL; ++j) incl *= om[j];
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const float t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl *= t;
+  }
+  float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+  if (lane == 0) excl = 1.f;
+  tr[0] = excl;
+#pragma unroll
+  for (int j = 1; j < SPL; ++j) tr[j] = tr[j - 1] * om[j - 1];
+  float acc = 0.f, wz = 0.f;
+#pragma unroll
+  for (int j = 0; j < SPL; ++j) {
+    w[j] = base + j < S ? fmul(al[j], tr[j]) : 0.f;
+    acc += w[j];
+    wz += w[j] * zz[j];
+  }
+  acc = warp_sum(acc);
+  wz = warp_sum(wz);
+  const float denom = fadd(acc, 1e-6f);
+  const float inv = 1.f / denom;
+  const float d_nat = wz * inv;            // depth in the sampling space (NDC z in NDC mode)
+  float zw[SPL], d_wld = 0.f, e_nat = 0.f, e_wld = 0.f;
+  {
+    float s1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < SPL; ++j) {
+      zw[j] = ndc ? depth_from_ndc(zz[j], oz, dz) : zz[j];
+      s1 += w[j] * zw[j];
+    }
+    d_wld = warp_sum(s1) * inv;
+#pragma unroll
+    for (int j = 0; j < SPL; ++j) {
+      e_nat += w[j] * (zz[j] - d_nat);
+      e_wld += w[j] * (zw[j] - d_wld);
+    }
+    e_nat = warp_sum(e_nat);
+    e_wld = warp_sum(e_wld);
+  }
+
+  // ---- upstream gradients of the per-ray maps
+  float g_rgb[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) g_rgb[k] = G.rgb ? G.rgb[3 * ray + k] : 0.f;
+  float g_acc = G.acc ? G.acc[ray] : 0.f;
+  if (fl.white_bkgd) g_acc -= g_rgb[0] + g_rgb[1] + g_rgb[2];            // rgb += 1 - acc, :363-364
+  // depth / depth_var are the world-space statistics; in NDC mode depth_ndc / depth_var_ndc are the native ones (:356-361)
+  const float gd_w = G.depth ? G.depth[ray] : 0.f;
+  const float gv_w = G.depth_var ? G.depth_var[ray] : 0.f;
+  const float gd_n = (ndc && G.depth_ndc) ? G.depth_ndc[ray] : 0.f;
+  const float gv_n = (ndc && G.depth_var_ndc) ? G.depth_var_ndc[ray] : 0.f;
+
+  // ---- dL/dw_i
+  float gw[SPL];
+#pragma unroll
+  for (int j = 0; j < SPL; ++j) {
+    const int i = base + j;
+    float t = 0.f;
+    if (i < S) {
+      const float* c = rgb + (ray * S + i) * 3;
+      t = g_rgb[0] * c[0] + g_rgb[1] * c[1] + g_rgb[2] * c[2] + g_acc;
+      const float aw = zw[j] - d_wld;
+      t += gd_w * aw * inv + gv_w * (aw * aw - 2.f * aw * inv * e_wld);
+      const float an = zz[j] - d_nat;
+      t += gd_n * an * inv + gv_n * (an * an - 2.f * an * inv * e_nat);
+      if (G.weights) t += G.weights[ray * S + i];
+    }
+    gw[j] = t;
+  }
+  const bool has_v2 = V > 0 && vis2 != nullptr;
+  if (has_v2 && G.visibility2 != nullptr) {
+    for (int v = 0; v < V; ++v) {
+      const float g2 = G.visibility2[ray * V + v];
+      float m = 0.f;
+#pragma unroll
+      for (int j = 0; j < SPL; ++j)
+        if (base + j < S) m += w[j] * vis2[(ray * S + base + j) * V + v];
+      const float vis2_map = warp_sum(m) * inv;
+#pragma unroll
+      for (int j = 0; j < SPL; ++j)
+        if (base + j < S) gw[j] += g2 * (vis2[(ray * S + base + j) * V + v] - vis2_map) * inv;
+    }
+  }
+
+  // ---- w = alpha * T;  T = exclusive cumprod of om;  om = 1 - alpha + 1e-10
+  float ga[SPL], x[SPL];
+  float loc = 0.f;
+#pragma unroll
+  for (int j = 0; j < SPL; ++j) {
+    const int i = base + j;
+    const bool valid = i < S;
+    ga[j] = gw[j] * tr[j] + ((valid && G.alpha) ? G.alpha[ray * S + i] : 0.f);
+    const float gt = gw[j] * al[j] + ((valid && G.visibility) ? G.visibility[ray * S + i] : 0.f);
+    x[j] = valid ? gt * tr[j] : 0.f;
+    loc += x[j];
+  }
+  float sfx_incl = loc;   // inclusive suffix sum over lanes
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const float t = __shfl_down_sync(0xffffffffu, sfx_incl, o);
+    if (lane + o < 32) sfx_incl += t;
+  }
+  float sfx = __shfl_down_sync(0xffffffffu, sfx_incl, 1);  // sum over the samples of all later lanes
+  if (lane == 31) sfx = 0.f;
+#pragma unroll
+  for (int j = SPL - 1; j >= 0; --j) {
+    const int i = base + j;
+    // sfx = sum_{i' > i} gT_i' T_i'  ->  dL/d om_i = sfx / om_i  ->  alpha_i receives the negative of it
+    const float g_alpha = ga[j] - sfx / om[j];
+    sfx += x[j];
+    if (i < S) {
+      float gs = g_alpha * dl[j] * ex[j];                              // alpha = 1 - exp(-sigma * delta)
+      if (G.raw_sigma) gs += G.raw_sigma[ray * S + i];
+      dsig[ray * S + i] = sg[j] > 0.f ? gs : 0.f;                      // sigma = relu(logit (+ noise))
+    }
+  }
+
+  // ---- head logits: rgb / visibility (primary view), visibility2 (secondary views); sigmoid' = y (1 - y)
+#pragma unroll
+  for (int j = 0; j < SPL; ++j) {
+    const int i = base + j;
+    if (i >= S) continue;
+    const int64_t p = ray * S + i;
+    float4 o;
+    float* of = reinterpret_cast<float*>(&o);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const float c = rgb[p * 3 + k];
+      float gc = w[j] * g_rgb[k];
+      if (G.raw_rgb) gc += G.raw_rgb[p * 3 + k];
+      of[k] = gc * c * (1.f - c);
+    }
+    const float sv = vis[p];
+    of[3] = G.raw_visibility ? G.raw_visibility[p] * sv * (1.f - sv) : 0.f;
+    *reinterpret_cast<float4*>(dlogit + p * nviews * 4) = o;
+    for (int v = 0; v < V; ++v) {
+      float gl = 0.f;
+      if (has_v2) {
+        const float s2 = vis2[p * V + v];
+        float gv = G.visibility2 ? w[j] * G.visibility2[ray * V + v] * inv : 0.f;
+        if (G.raw_visibility2) gv += G.raw_visibility2[p * V + v];
+        gl = gv * s2 * (1.f - s2);
+      }
+      *reinterpret_cast<float4*>(dlogit + (p * nviews + 1 + v) * 4) = make_float4(0.f, 0.f, 0.f, gl);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kGemmBM = 128;
+constexpr int kGemmBK = 16;
+constexpr int kGemmTargetCtas = 296;        // two CTAs per SM
+constexpr int kGemmMaxMainFloats = 80 * 65536;
+constexpr int kGemmMaxBiasFloats = kGemmTargetCtas * 256;
+
+template <int BN>
+__global__ void __launch_bounds__(256)
+k_gemm_tn(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb, int64_t n_rows,
+          int64_t rows_per_split, int M, int N, float* __restrict__ partial, float* __restrict__ bias_partial) {
+  constexpr int TN = BN / 16;
+  __shared__ __align__(16) float As[2][kGemmBK][kGemmBM];
+  __shared__ __align__(16) float Bs[2][kGemmBK][BN];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.x * kGemmBM, n0 = blockIdx.y * BN;
+  const int64_t r_begin = (int64_t)blockIdx.z * rows_per_split;
+  const int64_t r_end = min(n_rows, r_begin + rows_per_split);
+  const int n_steps = r_end > r_begin ? (int)((r_end - r_begin + kGemmBK - 1) / kGemmBK) : 0;
+  const bool do_bias = bias_partial != nullptr && blockIdx.y == 0 && tx == 0;
+
+  float acc[8][TN];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+  float bsum[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) bsum[i] = 0.f;
+
+  // loader mapping: A tile = 16 rows x 32 float4 (two per thread); B tile = 16 rows x BN/4 float4
+  constexpr int kBVec = kGemmBK * BN / 4;           // 512 / 256 / 128
+  constexpr int kBPer = (kBVec + 255) / 256;        // 2 / 1 / 1
+  float4 ra[2], rb[kBPer];
+  auto load_tile = [&](int step) {
+    const int64_t r0 = r_begin + (int64_t)step * kGemmBK;
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      const int idx = tid + t * 256, row = idx >> 5, c4 = idx & 31;
+      const int64_t r = r0 + row;
+      ra[t] = r < r_end ? *reinterpret_cast<const float4*>(A + r * lda + m0 + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int t = 0; t < kBPer; ++t) {
+      const int idx = tid + t * 256;
+      if (idx < kBVec) {
+        const int row = idx / (BN / 4), c4 = idx % (BN / 4);
+        const int64_t r = r0 + row;
+        rb[t] = r < r_end ? *reinterpret_cast<const float4*>(B + r * ldb + n0 + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+  };
+  auto store_tile = [&](int buf) {
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      const int idx = tid + t * 256, row = idx >> 5, c4 = idx & 31;
+      *reinterpret_cast<float4*>(&As[buf][row][c4 * 4]) = ra[t];
+    }
+#pragma unroll
+    for (int t = 0; t < kBPer; ++t) {
+      const int idx = tid + t * 256;
+      if (idx < kBVec) {
+        const int row = idx / (BN / 4), c4 = idx % (BN / 4);
+        *reinterpret_cast<float4*>(&Bs[buf][row][c4 * 4]) = rb[t];
+      }
+    }
+  };
+
+  if (n_steps > 0) {
+    load_tile(0);
+    store_tile(0);
+  }
+  __syncthreads();
+  for (int step = 0; step < n_steps; ++step) {
+    const int cur = step & 1;
+    if (step + 1 < n_steps) load_tile(step + 1);
+#pragma unroll
+    for (int k = 0; k < kGemmBK; ++k) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[cur][k][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[cur][k][64 + ty * 4]);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      float b[TN];
+      if constexpr (TN == 8) {
+        const float4 b0 = *reinterpret_cast<const float4*>(&Bs[cur][k][tx * 4]);
+        const float4 b1 = *reinterpret_cast<const float4*>(&Bs[cur][k][BN / 2 + tx * 4]);
+        b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w;
+        b[TN - 4] = b1.x; b[TN - 3] = b1.y; b[TN - 2] = b1.z; b[TN - 1] = b1.w;
+      } else if constexpr (TN == 4) {
+        const float4 b0 = *reinterpret_cast<const float4*>(&Bs[cur][k][tx * 4]);
+        b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w;
+      } else {
+        const float2 b0 = *reinterpret_cast<const float2*>(&Bs[cur][k][tx * 2]);
+        b[0] = b0.x; b[1] = b0.y;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+      if (do_bias) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) bsum[i] += a[i];
+      }
+    }
+    if (step + 1 < n_steps) store_tile(cur ^ 1);
+    __syncthreads();
+  }
+
+  // partial[z][m][n]
+  float* out = partial + (size_t)blockIdx.z * M * N;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+    float* row = out + (size_t)m * N + n0;
+    if constexpr (TN == 8) {
+      *reinterpret_cast<float4*>(row + tx * 4) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+      *reinterpret_cast<float4*>(row + BN / 2 + tx * 4) = make_float4(acc[i][TN - 4], acc[i][TN - 3], acc[i][TN - 2], acc[i][TN - 1]);
+    } else if constexpr (TN == 4) {
+      *reinterpret_cast<float4*>(row + tx * 4) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+    } else {
+      *reinterpret_cast<float2*>(row + tx * 2) = make_float2(acc[i][0], acc[i][1]);
+    }
+    if (do_bias) bias_partial[(size_t)blockIdx.z * M + m] = bsum[i];
+  }
+}
+
+// dst[m * ldc + n] = sum_s partial[s][m][n], n < n_valid  (fixed summation order)
+__global__ void k_reduce_partials(const float* __restrict__ partial, int n_split, int M, int N, float* __restrict__ dst,
+                                  int ldc, int n_valid) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M * n_valid) return;
+  const int m = i / n_valid, n = i % n_valid;
+  float s = 0.f;
+  for (int k = 0; k < n_split; ++k) s += partial[((size_t)k * M + m) * N + n];
+  dst[(size_t)m * ldc + n] = s;
+}
+
+template <int M>
+__global__ void __launch_bounds__(256)
+k_small_tn(const float* __restrict__ G, const float* __restrict__ H, int N, int64_t n_rows, int64_t rows_per_split,
+           float* __restrict__ partial, float* __restrict__ gsum_partial) {
+  const int n = threadIdx.x;
+  const int64_t r_begin = (int64_t)blockIdx.x * rows_per_split;
+  const int64_t r_end = min(n_rows, r_begin + rows_per_split);
+  float acc[M];
+#pragma unroll
+  for (int m = 0; m < M; ++m) acc[m] = 0.f;
+  float gs = 0.f;
+  if (n < N) {
+#pragma unroll 4
+    for (int64_t r = r_begin; r < r_end; ++r) {
+      const float hval = H[r * N + n];
+#pragma unroll
+      for (int m = 0; m < M; ++m) acc[m] = fmaf(G[r * M + m], hval, acc[m]);
+      if (n < M) gs += G[r * M + n];
+    }
+#pragma unroll
+    for (int m = 0; m < M; ++m) partial[((size_t)blockIdx.x * M + m) * N + n] = acc[m];
+    if (n < M) gsum_partial[(size_t)blockIdx.x * M + n] = gs;
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_composite_bwd(const RayPtrs& rp, const RenderFlags& fl, int64_t n_rays, int S, const float* z,
+                                 const float* sigma, const float* rgb, const float* vis, const float* vis2,
+                                 const PassGradPtrs& g, float* dsig, float* dlogit, cudaStream_t s) {
+  if (n_rays == 0) return cudaSuccess;
+  const unsigned grid = (unsigned)((n_rays + 3) / 4);
+  const int spl = (S + 31) / 32;
+#define VIPNERF_LAUNCH_CBWD(SPL) \
+  k_composite_bwd<SPL><<<grid, 128, 0, s>>>(rp, fl, n_rays, S, z, sigma, rgb, vis, vis2, g, dsig, dlogit)
+  if (spl <= 2) VIPNERF_LAUNCH_CBWD(2);
+  else if (spl <= 6) VIPNERF_LAUNCH_CBWD(6);
+  else VIPNERF_LAUNCH_CBWD(8);
+#undef VIPNERF_LAUNCH_CBWD
+  return cudaGetLastError();
+}
+
+size_t gemm_tn_partial_floats() { return (size_t)kGemmMaxMainFloats + kGemmMaxBiasFloats; }
+
+cudaError_t launch_gemm_tn(const float* A, int lda, int M, const float* B, int ldb, int N, int64_t n_rows, float* dst,
+                           int ldc, int n_valid, float* bias_dst, float* partial, cudaStream_t s) {
+  if ((M != 128 && M != 256) || (N != 32 && N != 64 && N != 128 && N != 256)) return cudaErrorInvalidValue;
+  const int BN = N >= 128 ? 128 : N;
+  const int tiles = (M / kGemmBM) * (N / BN);
+  int64_t n_split = kGemmTargetCtas / tiles;
+  const int64_t max_by_rows = (n_rows + 255) / 256;
+  if (n_split > max_by_rows) n_split = max_by_rows;
+  if (n_split < 1) n_split = 1;
+  while (n_split * M * N > kGemmMaxMainFloats) --n_split;
+  int64_t rows_per_split = (n_rows + n_split - 1) / n_split;
+  rows_per_split = (rows_per_split + kGemmBK - 1) / kGemmBK * kGemmBK;
+  if (rows_per_split < kGemmBK) rows_per_split = kGemmBK;
+  float* bias_partial = bias_dst ? partial + kGemmMaxMainFloats : nullptr;
+  const dim3 grid(M / kGemmBM, N / BN, (unsigned)n_split);
+  if (BN == 128) k_gemm_tn<128><<<grid, 256, 0, s>>>(A, lda, B, ldb, n_rows, rows_per_split, M, N, partial, bias_partial);
+  else if (BN == 64) k_gemm_tn<64><<<grid, 256, 0, s>>>(A, lda, B, ldb, n_rows, rows_per_split, M, N, partial, bias_partial);
+  else k_gemm_tn<32><<<grid, 256, 0, s>>>(A, lda, B, ldb, n_rows, rows_per_split, M, N, partial, bias_partial);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  k_reduce_partials<<<(M * n_valid + 255) / 256, 256, 0, s>>>(partial, (int)n_split, M, N, dst, ldc, n_valid);
+  if (bias_dst) k_reduce_partials<<<(M + 255) / 256, 256, 0, s>>>(bias_partial, (int)n_split, M, 1, bias_dst, 1, 1);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_small_tn(const float* G, int M, const float* H, int N, int64_t n_rows, float* dst, float* gsum_dst,
+                            float* partial, cudaStream_t s) {
+  if ((M != 1 && M != 4) || N < 4 || N > 256) return cudaErrorInvalidValue;
+  int64_t n_split = 4 * 148;
+  const int64_t max_by_rows = (n_rows + 63) / 64;
+  if (n_split > max_by_rows) n_split = max_by_rows;
+  if (n_split < 1) n_split = 1;
+  const int64_t rows_per_split = (n_rows + n_split - 1) / n_split;
+  float* gsum_partial = partial + kGemmMaxMainFloats;
+  if (M == 1) k_small_tn<1><<<(unsigned)n_split, 256, 0, s>>>(G, H, N, n_rows, rows_per_split, partial, gsum_partial);
+  else k_small_tn<4><<<(unsigned)n_split, 256, 0, s>>>(G, H, N, n_rows, rows_per_split, partial, gsum_partial);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  k_reduce_partials<<<(M * N + 255) / 256, 256, 0, s>>>(partial, (int)n_split, M, N, dst, N, N);
+  if (gsum_dst) k_reduce_partials<<<1, 256, 0, s>>>(gsum_partial, (int)n_split, M, 1, gsum_dst, 1, 1);
+  return cudaGetLastError();
+}
+
+}  // namespace vipnerf
