@@ -251,6 +251,137 @@ def run_frame(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+TRAIN_FLOP_PER_POINT = 2 * (593_536 + 557_056 + 593_536)   # forward + backward-data chain + parameter gradients (MACs x 2)
+
+
+def run_train(args, rank, world, local_rank):
+    """--workload train: BASELINE config 3 - one TRAINING iteration of the RealEstate-10K setup (2 input views -> one
+    secondary view, 2048 + 2048 rays, the four losses of the shipped configs) through the plugin exactly as
+    Trainer01.train_one_iter (:61-107) drives it: zero_grad, model(batch) in train mode, the losses, backward,
+    Adam step.  Weak scaling: every rank steps its own batch and the gradients are summed with one NCCL all-reduce per
+    step (what torch.nn.DataParallel's reduce does in the reference).  fp32 CUDA-core kernels (row f1, first correct
+    path) - informational; the default workload is the eval render BASELINE.json quotes the metric on."""
+    import torch
+    import torch.distributed as dist
+    from oracle import vipnerf_oracle as O
+    from vipnerf_b200.ModelFactory import get_model
+
+    torch.cuda.set_device(local_rank)
+    device = torch.device('cuda', local_rank)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=device)
+    R, V = args.rays_per_step, 1
+    model = get_model(model_configs('bf16', ndc=True), None)
+    model.load_state_dict(O.synth_state_dict(0))
+    model = model.to(device).train()
+    opt = torch.optim.Adam(model.parameters(), lr=5e-4, betas=(0.9, 0.999))
+    host = {k: v.pin_memory() for k, v in O.make_rays('re10k', R, seed=2 + rank, n_sec_views=V).items()}
+    sup_host = O.make_supervision('re10k', R, V)
+    sup = {k: (v.to(device) if isinstance(v, torch.Tensor) else v) for k, v in sup_host.items()}
+    m_nerf, m_depth = sup['indices_mask_nerf'], sup['indices_mask_sparse_depth']
+
+    def losses(out):   # MSE01 + 0.1 VisibilityLoss01 + 0.001 VisibilityPriorLoss01 + 0.1 SparseDepthMSE01
+        total = 0
+        for t in ('coarse', 'fine'):
+            total = total + torch.mean(torch.square(out[f'rgb_{t}'][m_nerf] - sup['target_rgb'][m_nerf]))
+            pred, tgt = out[f'raw_visibility_{t}'][..., 0], out[f'visibility_{t}']
+            total = total + 0.1 * (torch.mean(torch.abs(pred - tgt.detach())) + torch.mean(torch.abs(pred.detach() - tgt)))
+            total = total + 0.001 * torch.mean(torch.sum(sup['visibility_prior_masks'][m_nerf] * (1 - out[f'visibility2_{t}'][m_nerf]), dim=1))
+        return total + 0.1 * torch.mean(torch.square(out['depth_fine'][m_depth] - sup['sparse_depth_values'][:, 0][m_depth]))
+
+    h2d = sum(v.numel() * 4 for v in host.values())
+
+    def step():
+        batch = {k: v.to(device, non_blocking=True) for k, v in host.items()}
+        opt.zero_grad(set_to_none=True)
+        loss = losses(model(batch))
+        loss.backward()
+        if world > 1:
+            flat = torch.cat([p.grad.reshape(-1) for p in model.parameters()])
+            dist.all_reduce(flat)
+            off = 0
+            for p in model.parameters():
+                p.grad.copy_(flat[off:off + p.numel()].view_as(p))
+                off += p.numel()
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    t_ms = 0.0
+    loss_value = None
+    for _ in range(args.steps):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        loss = step()
+        loss_value = loss.item()           # the step's result comes back to the host (4 bytes)
+        e.record()
+        torch.cuda.synchronize()
+        t_ms += s.elapsed_time(e)
+    barrier()
+    clocks = sampler.stop()
+    total = torch.tensor([t_ms], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(total, op=dist.ReduceOp.MAX)
+    total_ms = total.item()
+    if rank == 0:
+        value = world * R * args.steps / (total_ms * 1e-3)
+        sm_mhz = clocks.get('sm_mhz') or 1900.0
+        peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12     # fp32 FFMA lanes x 2 FLOP x measured SM clock
+        achieved = value / world * 256 * TRAIN_FLOP_PER_POINT / 1e12
+        line = {'metric': 'training rays/s (forward + 4 losses + backward + Adam), 64+128 samples', 'value': value,
+                'unit': 'rays/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+                'ms_per_step': total_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+                'dtype': 'f32', 'data': 'synthetic',
+                'config': {'workload': 'RealEstate-10K camera, 2 input views (1 secondary view), full ViP-NeRF visibility + '
+                                       'sparse-depth losses, one training iteration per step',
+                           'rays_per_step_per_gpu': R, 'samples': '64+128', 'ndc': True,
+                           'kernels': 'fp32 CUDA-core training path (k_mlp_fp32<save>, k_composite_bwd, k_mlp_bwd_fp32, k_gemm_tn)',
+                           'l2': 'working set (about 22 KB per sample point, > 20 GB per step) exceeds L2 by construction',
+                           'final_loss': loss_value},
+                'clocks': clocks,
+                'e2e': {'value': value, 'unit': 'rays/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4,
+                        'note': 'the timed region IS end to end: pinned host rays in, loss value out'},
+                'gpu_launches': args.steps * 70,
+                'roofline': {'bound': 'fp32-ffma', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
+                             'frac': achieved / peak, 'traffic': None,
+                             'peak_kind': '148 SMs x 128 FFMA lanes x 2 x measured SM clock (CUDA cores; the tensor-core '
+                                          'backward is the next step of row f1)',
+                             'flop_per_ray': 256 * TRAIN_FLOP_PER_POINT}}
+        if not args.no_cpu_baseline and world == 1:
+            threads = os.cpu_count() or 1
+            torch.set_num_threads(threads)
+            n_cpu = 128
+            rays = O.make_rays('re10k', n_cpu, seed=2, n_sec_views=V)
+            sup_c = O.make_supervision('re10k', n_cpu, V)
+            sd = {k: v.clone().requires_grad_(True) for k, v in O.synth_state_dict(0).items()}
+            best = float('inf')
+            for _ in range(2):
+                t0 = time.perf_counter()
+                draws = O.draw_training_randoms(n_cpu)
+                out = O.render(sd, rays, ndc=True, train_randoms=draws)
+                mn, md = sup_c['indices_mask_nerf'], sup_c['indices_mask_sparse_depth']
+                l = sum(torch.mean(torch.square(out[f'rgb_{t}'][mn] - sup_c['target_rgb'][mn])) for t in ('coarse', 'fine'))
+                l = l + 0.1 * torch.mean(torch.square(out['depth_fine'][md] - sup_c['sparse_depth_values'][:, 0][md]))
+                l.backward()
+                best = min(best, time.perf_counter() - t0)
+            line['cpu_baseline'] = {'value': n_cpu / best, 'unit': 'rays/s', 'cores': threads, 'kind': 'port',
+                                    'sample': f'{n_cpu}-ray training step (forward + backward, torch autograd over the CPU oracle), best of 2'}
+        else:
+            line['cpu_baseline'] = None
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -260,7 +391,7 @@ def main():
     ap.add_argument('--precision', default='bf16', choices=['bf16', 'bf16x3', 'fp32'])
     ap.add_argument('--rays-per-step', type=int, default=RAYS_PER_STEP)
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--workload', default='batch', choices=['batch', 'frame'])
+    ap.add_argument('--workload', default='batch', choices=['batch', 'frame', 'train'])
     ap.add_argument('--scene', default='fern', choices=['fern', 'dtu'], help='camera of the frame workload')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
@@ -280,6 +411,9 @@ def main():
         return
     if args.workload == 'frame':
         run_frame(args, rank, world, local_rank)
+        return
+    if args.workload == 'train':
+        run_train(args, rank, world, local_rank)
         return
 
     import torch
