@@ -60,7 +60,7 @@ def measured_peaks():
 class ClockSampler:
     """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
 
-    def __init__(self, index, period_s=0.05):
+    def __init__(self, index, period_s=0.01):
         self.sm, self.max_mhz, self.reasons, self.error = [], None, set(), None
         self._stop = threading.Event()
         try:
@@ -264,6 +264,7 @@ def run_train(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
     from oracle import vipnerf_oracle as O
+    from vipnerf_b200 import sharding
     from vipnerf_b200.ModelFactory import get_model
 
     torch.cuda.set_device(local_rank)
@@ -298,12 +299,7 @@ def run_train(args, rank, world, local_rank):
         loss = losses(model(batch))
         loss.backward()
         if world > 1:
-            flat = torch.cat([p.grad.reshape(-1) for p in model.parameters()])
-            dist.all_reduce(flat)
-            off = 0
-            for p in model.parameters():
-                p.grad.copy_(flat[off:off + p.numel()].view_as(p))
-                off += p.numel()
+            sharding.allreduce_gradients(model, average=True)
         opt.step()
         return loss
 

@@ -65,3 +65,44 @@ def test_sharded_render_equals_unsharded_gloo(n_rays):
         p.join(timeout=120)
         assert p.exitcode == 0
     assert q.get(timeout=10) is True
+
+
+def _grad_worker(rank, world, port, result_queue):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        torch.manual_seed(0)
+        net = torch.nn.Sequential(torch.nn.Linear(6, 16), torch.nn.ReLU(), torch.nn.Linear(16, 3))
+        g = torch.Generator().manual_seed(1)
+        x, y = torch.randn(10, 6, generator=g), torch.randn(10, 3, generator=g)
+        lo, hi = sharding.shard_range(10, rank, world)
+        # global-mean loss: every rank contributes its shard's share, gradients are summed
+        loss = torch.sum(torch.square(net(x[lo:hi]) - y[lo:hi])) / x.shape[0]
+        loss.backward()
+        sharding.allreduce_gradients(net)
+        if rank == 0:
+            ref = torch.nn.Sequential(torch.nn.Linear(6, 16), torch.nn.ReLU(), torch.nn.Linear(16, 3))
+            ref.load_state_dict(net.state_dict())
+            torch.sum(torch.square(ref(x) - y) / x.shape[0]).backward()
+            ok = all(torch.allclose(a.grad, b.grad, rtol=1e-5, atol=1e-7) for a, b in zip(net.parameters(), ref.parameters()))
+            result_queue.put(bool(ok))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_allreduce_gradients_equals_full_batch_gloo():
+    """Data-parallel training step: shard the rays, backward per rank, one all-reduce of the flat gradient buffer ==
+    the gradients of the un-sharded batch."""
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_grad_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert q.get(timeout=10) is True

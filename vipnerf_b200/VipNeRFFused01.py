@@ -138,10 +138,24 @@ class VipNeRFFused(torch.nn.Module):
         device = batch['rays_o'].device
         n_coarse = model_cfg['coarse_mlp']['num_samples']
         n_fine = model_cfg['fine_mlp']['num_samples'] if self.fine_mlp_needed else 0
-        draws = training.draw_training_randoms(
-            batch['rays_o'].shape[0], n_coarse, n_fine, model_cfg['chunk'], model_cfg['netchunk'],
-            model_cfg['perturb'] > 0, float(model_cfg['raw_noise_std']), self.fine_mlp_needed)
-        batch.update({k: v.to(device) for k, v in draws.items()})
+        n_rays = batch['rays_o'].shape[0]
+        perturb, noise_std = model_cfg['perturb'] > 0, float(model_cfg['raw_noise_std'])
+        if model_cfg.get('rng', 'reference') == 'device':
+            # configs['model']['rng'] = 'device': the same distributions drawn by the device generator - no host work
+            # and no upload, but not the reference's random stream (a seeded run differs from the reference's)
+            draws = {}
+            if perturb:
+                draws['t_rand'] = torch.rand(n_rays, n_coarse, device=device)
+                if self.fine_mlp_needed:
+                    draws['u_rand'] = torch.rand(n_rays, n_fine, device=device)
+            if noise_std > 0:
+                draws['sigma_noise_coarse'] = torch.randn(n_rays, n_coarse, device=device) * noise_std
+                if self.fine_mlp_needed:
+                    draws['sigma_noise_fine'] = torch.randn(n_rays, n_coarse + n_fine, device=device) * noise_std
+        else:
+            draws = training.draw_training_randoms(n_rays, n_coarse, n_fine, model_cfg['chunk'], model_cfg['netchunk'],
+                                                   perturb, noise_std, self.fine_mlp_needed)
+        batch.update({k: v.to(device, non_blocking=True) for k, v in draws.items()})
         return training.render_rays_train(
             batch, self.coarse_model.named_tensors(), self.fine_model.named_tensors() if self.fine_mlp_needed else None,
             ndc=self.ndc, n_coarse=n_coarse, n_fine=n_fine, n_sec_views=n_sec_views,

@@ -5,7 +5,9 @@ rank 0.  This replaces the reference's single-process torch.nn.DataParallel scat
 torch.distributed (NCCL on GPUs; the same code runs over gloo for the CPU tests).
 
 Partition: rank r of G gets rays [r*ceil(N/G), min(N, (r+1)*ceil(N/G))) - what DataParallel.scatter does along
-dim 0.  No other collective exists on the path.
+dim 0.  No other collective exists on the render path.  Training (row f1) has one exchange step of its own: the
+parameter gradients of the ranks' ray shards are summed (`allreduce_gradients`), which is what DataParallel's
+backward does when it reduces the replicas' gradients onto the master copy (src/Trainer01.py:517).
 """
 from __future__ import annotations
 
@@ -83,3 +85,22 @@ def render_sharded(render_fn: Callable[[Dict[str, object]], Dict[str, torch.Tens
     local = render_fn(shard_batch(batch, rank, world))
     local = {k: v for k, v in local.items() if isinstance(v, torch.Tensor)}
     return gather_outputs(local, n, group, dst)
+
+
+def allreduce_gradients(module: torch.nn.Module, group: Optional[dist.ProcessGroup] = None, average: bool = False) -> None:
+    """The one collective of a data-parallel training step: sums (or averages) `.grad` of every parameter over the
+    ranks with ONE all-reduce of a flat buffer (2.4 MB of fp32 per MLP pair), then scatters the result back into the
+    gradient tensors.  Call between `loss.backward()` and `optimizer.step()`.  A loss that is a mean over the GLOBAL
+    batch must be scaled by the local share before backward (sum semantics), or use average=True for per-rank means."""
+    params = [p for p in module.parameters() if p.grad is not None]
+    if not params:
+        return
+    flat = torch.cat([p.grad.reshape(-1) for p in params])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    if average:
+        flat /= dist.get_world_size(group)
+    off = 0
+    for p in params:
+        n = p.numel()
+        p.grad.copy_(flat[off:off + n].view_as(p.grad))
+        off += n
