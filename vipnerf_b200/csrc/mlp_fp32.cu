@@ -9,7 +9,7 @@
 //
 // One block = 64 consecutive sample points, 128 threads.  Activations live in shared memory k-major
 // (act[k][point]) so that a thread's 8 points are two 128-bit loads; the transposed weights stream through a
-// double-buffered 32-row shared window with cp.async; each thread owns an 8-point x 16-column register tile.
+// three-stage ring of 8-row shared windows with cp.async; each thread owns an 8-point x 16-column register tile.
 //
 // Training (reference Trainer01.py:93-102 = model(batch) + loss.backward()):
 //  * k_mlp_fp32<true> is the same forward with the density noise of VipNeRF01.py:549-552 added and every
@@ -29,10 +29,11 @@ namespace {
 
 constexpr int kPts = 64;
 constexpr int kThreads = 128;
-constexpr int kKC = 32;  // weight rows per shared window
+constexpr int kKC = 8;   // weight rows per shared window: 16 KiB for both buffers, so that TWO blocks fit an SM (2 warps per scheduler hide each other's barriers and load latencies)
 
 constexpr int kActFloats = 320 * kPts;
-constexpr int kWbufFloats = 2 * kKC * 256;
+constexpr int kStages = 3;  // weight ring depth (prefetch distance 2 chunks)
+constexpr int kWbufFloats = kStages * kKC * 256;
 constexpr int kPevFloats = kEncView * kPts;
 constexpr int kDirFloats = 3 * kPts;
 constexpr size_t kSmemBytes = (kActFloats + kWbufFloats + kPevFloats + kDirFloats) * sizeof(float);
@@ -59,7 +60,7 @@ __device__ __forceinline__ void matmul_layer(const float* __restrict__ wt, int K
   const int n_chunks = K / kKC;
   auto prefetch = [&](int c) {
     const float* src = wt + (size_t)c * kKC * N;
-    float* dst = wbuf + (c & 1) * (kKC * 256);
+    float* dst = wbuf + (c % kStages) * (kKC * 256);
 #pragma unroll
     for (int v = 0; v < kVecPerThread; ++v) {
       const int e = (v * kThreads + tid) * 4;
@@ -68,10 +69,13 @@ __device__ __forceinline__ void matmul_layer(const float* __restrict__ wt, int K
     cp_async_commit();
   };
   prefetch(0);
+  if (n_chunks > 1) prefetch(1);
   for (int c = 0; c < n_chunks; ++c) {
-    if (c + 1 < n_chunks) { prefetch(c + 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+    if (c + 2 < n_chunks) { prefetch(c + 2); cp_async_wait<2>(); }
+    else if (c + 1 < n_chunks) { cp_async_wait<1>(); }
+    else { cp_async_wait<0>(); }
     __syncthreads();
-    const float* wb = wbuf + (c & 1) * (kKC * 256);
+    const float* wb = wbuf + (c % kStages) * (kKC * 256);
     const float* ar = act_rows + (size_t)c * kKC * kPts + tp * 8;
 #pragma unroll 4
     for (int kk = 0; kk < kKC; ++kk) {
@@ -90,7 +94,7 @@ __device__ __forceinline__ void matmul_layer(const float* __restrict__ wt, int K
         }
       }
     }
-    __syncthreads();  // window (c&1) is free for chunk c+2; on the last chunk: all reads of act are done
+    __syncthreads();  // stage c % kStages is free for chunk c+3; on the last chunk: all reads of act are done
   }
 }
 
@@ -179,13 +183,13 @@ __device__ __forceinline__ void save_view_encoding(const float* pev_s, float* __
 }
 
 template <bool kSave>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, 2)
 k_mlp_fp32(RayPtrs rp, RenderFlags fl, int64_t n_points, int S, const float* __restrict__ z,
            const float* __restrict__ small, const float* __restrict__ big, float* __restrict__ out_sigma,
            float* __restrict__ out_rgb, float* __restrict__ out_vis, float* __restrict__ out_vis2, MlpSave sv) {
   extern __shared__ __align__(16) float smem[];
   float* act = smem;                    // [320][64]: rows 0..63 encoding (row 63 = 0), rows 64..319 hidden
-  float* wbuf = act + kActFloats;       // [2][32][256]
+  float* wbuf = act + kActFloats;       // [kStages][kKC][256]
   float* pev = wbuf + kWbufFloats;      // [27][64] view-direction encoding per point
   float* dir2 = pev + kPevFloats;       // [3][64]
   const int tid = threadIdx.x;
@@ -335,7 +339,7 @@ k_mlp_fp32(RayPtrs rp, RenderFlags fl, int64_t n_points, int S, const float* __r
 
 // ------------------------------------------------------------------------------------------------
 // Backward-data chain of one 64-point tile (training).  g = shared [256][64] gradient rows, k-major like `act`.
-constexpr int kMaxViews = 17;  // primary + up to 16 secondary views
+constexpr int kMaxViews = 17;  // primary + up to 16 secondary views (17 KiB of logit gradients per tile)
 constexpr size_t kBwdSmemBytes = (256 * kPts + kWbufFloats + kPts * kMaxViews * 4 + kPts) * sizeof(float);
 
 // Epilogue of one backward product: acc = gradient w.r.t. the OUTPUT of the layer below (its post-ReLU h, or the
@@ -377,11 +381,11 @@ __device__ __forceinline__ void bwd_epilogue(float (&acc)[8][16], float* g, int 
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, 2)
 k_mlp_bwd_fp32(MlpBwdArgs a, const float* __restrict__ small, const float* __restrict__ wb) {
   extern __shared__ __align__(16) float smem[];
   float* g = smem;                         // [256][64]
-  float* wbuf = g + 256 * kPts;            // [2][32][256]
+  float* wbuf = g + 256 * kPts;            // [kStages][kKC][256]
   float* dl_s = wbuf + kWbufFloats;        // [64][nviews][4] head-logit gradients
   float* dsig_s = dl_s + kPts * kMaxViews * 4;  // [64]
   const int tid = threadIdx.x;
@@ -405,17 +409,27 @@ k_mlp_bwd_fp32(MlpBwdArgs a, const float* __restrict__ small, const float* __res
     float accp[kPts];
 #pragma unroll
     for (int p = 0; p < kPts; ++p) accp[p] = 0.f;
+    const int n_valid = (int)min((int64_t)kPts, P - p0);
     for (int v = 0; v < nv; ++v) {
+      // all 64 loads of a view are issued before the first use (clamped address instead of a branch per point):
+      // one DRAM latency per view instead of one per point
+      float hvv[kPts];
+#pragma unroll
+      for (int p = 0; p < kPts; ++p) hvv[p] = a.hv[((p0 + min(p, n_valid - 1)) * nv + v) * 128 + n];
 #pragma unroll
       for (int p = 0; p < kPts; ++p) {
-        const int64_t pg = p0 + p;
-        const bool valid = pg < P;
-        const float hvv = valid ? a.hv[(pg * nv + v) * 128 + n] : 0.f;
-        const float4 d4 = *reinterpret_cast<const float4*>(dl_s + (p * nv + v) * 4);
+        const float4 d4 = *reinterpret_cast<const float4*>(dl_s + (p * nv + v) * 4);   // zero for rows past the end
         const float gsum = fmaf(d4.x, wo.x, fmaf(d4.y, wo.y, fmaf(d4.z, wo.z, d4.w * wo.w)));
-        const float gp = hvv > 0.f ? gsum : 0.f;
-        if (valid) a.dhv[(pg * nv + v) * 128 + n] = gp;
-        accp[p] += gp;
+        hvv[p] = hvv[p] > 0.f ? gsum : 0.f;
+        accp[p] += hvv[p];
+      }
+      if (n_valid == kPts) {
+#pragma unroll
+        for (int p = 0; p < kPts; ++p) a.dhv[((p0 + p) * nv + v) * 128 + n] = hvv[p];
+      } else {
+#pragma unroll
+        for (int p = 0; p < kPts; ++p)
+          if (p < n_valid) a.dhv[((p0 + p) * nv + v) * 128 + n] = hvv[p];
       }
     }
 #pragma unroll
