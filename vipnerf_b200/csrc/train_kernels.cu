@@ -8,7 +8,8 @@
 //                   warp-shuffle scans (the cumprod's backward is an exclusive SUFFIX sum along the ray), and folds in
 //                   the ReLU / sigmoid derivatives of the heads, so that what leaves the kernel are logit gradients.
 //  k_gemm_tn        dW = dY^T X: C[m][n] = sum_p A[p][m] B[p][n], the reduction running over ALL sample points
-//                   (about 10^6 per batch).  fp32 FFMA with 128 x BN tiles; the point range is split over the grid,
+//                   (about 10^6 per batch).  fp32 FFMA with 128 x BN tiles fed by a 4-stage cp.async ring; the point
+//                   range is split over the grid,
 //                   partial tiles go to a scratch buffer and k_reduce_partials adds them in a fixed order, so
 //                   gradients are bit-reproducible run to run (no atomics).  Bias gradients (column sums of dY) ride
 //                   along in the threads that already hold the dY values.
@@ -210,13 +211,23 @@ constexpr int kGemmTargetCtas = 296;        // two CTAs per SM
 constexpr int kGemmMaxMainFloats = 80 * 65536;
 constexpr int kGemmMaxBiasFloats = kGemmTargetCtas * 256;
 
+constexpr int kGemmStages = 4;   // cp.async ring depth: loads run three k-steps ahead of the FMAs
+template <int BN> constexpr size_t gemm_smem_bytes() { return (size_t)kGemmStages * kGemmBK * (kGemmBM + BN) * sizeof(float); }
+
+__device__ __forceinline__ void cp_async16_zfill(void* smem, const void* gmem, bool valid) {
+  const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+  const int bytes = valid ? 16 : 0;   // src-size 0: the 16 destination bytes are zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(bytes));
+}
+
 template <int BN>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 k_gemm_tn(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb, int64_t n_rows,
           int64_t rows_per_split, int M, int N, float* __restrict__ partial, float* __restrict__ bias_partial) {
   constexpr int TN = BN / 16;
-  __shared__ __align__(16) float As[2][kGemmBK][kGemmBM];
-  __shared__ __align__(16) float Bs[2][kGemmBK][BN];
+  extern __shared__ __align__(16) float gemm_smem[];
+  float* As = gemm_smem;                                        // [stage][16][128]
+  float* Bs = gemm_smem + kGemmStages * kGemmBK * kGemmBM;      // [stage][16][BN]
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int m0 = blockIdx.x * kGemmBM, n0 = blockIdx.y * BN;
   const int64_t r_begin = (int64_t)blockIdx.z * rows_per_split;
@@ -233,68 +244,75 @@ k_gemm_tn(const float* __restrict__ A, int lda, const float* __restrict__ B, int
 #pragma unroll
   for (int i = 0; i < 8; ++i) bsum[i] = 0.f;
 
-  // loader mapping: A tile = 16 rows x 32 float4 (two per thread); B tile = 16 rows x BN/4 float4
+  // loader mapping: A tile = 16 rows x 32 float4 (two per thread); B tile = 16 rows x BN/4 float4.  Rows past the
+  // end of this CTA's point range are zero-filled (clamped source address, src-size 0).
   constexpr int kBVec = kGemmBK * BN / 4;           // 512 / 256 / 128
   constexpr int kBPer = (kBVec + 255) / 256;        // 2 / 1 / 1
-  float4 ra[2], rb[kBPer];
-  auto load_tile = [&](int step) {
-    const int64_t r0 = r_begin + (int64_t)step * kGemmBK;
+  const int rows_total = (int)max((int64_t)0, r_end - r_begin);
+  const float* a_src[2];
+  const float* b_src[kBPer];
+  int a_row[2], b_row[kBPer], a_dst[2], b_dst[kBPer];
 #pragma unroll
-    for (int t = 0; t < 2; ++t) {
-      const int idx = tid + t * 256, row = idx >> 5, c4 = idx & 31;
-      const int64_t r = r0 + row;
-      ra[t] = r < r_end ? *reinterpret_cast<const float4*>(A + r * lda + m0 + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
+  for (int t = 0; t < 2; ++t) {
+    const int idx = tid + t * 256, c4 = idx & 31;
+    a_row[t] = idx >> 5;
+    a_dst[t] = a_row[t] * kGemmBM + c4 * 4;
+    a_src[t] = A + (r_begin + a_row[t]) * lda + m0 + c4 * 4;
+  }
 #pragma unroll
-    for (int t = 0; t < kBPer; ++t) {
-      const int idx = tid + t * 256;
-      if (idx < kBVec) {
-        const int row = idx / (BN / 4), c4 = idx % (BN / 4);
-        const int64_t r = r0 + row;
-        rb[t] = r < r_end ? *reinterpret_cast<const float4*>(B + r * ldb + n0 + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int t = 0; t < kBPer; ++t) {
+    const int idx = tid + t * 256, c4 = idx % (BN / 4);
+    b_row[t] = idx / (BN / 4);
+    b_dst[t] = b_row[t] * BN + c4 * 4;
+    b_src[t] = B + (r_begin + b_row[t]) * ldb + n0 + c4 * 4;
+  }
+  auto issue_tile = [&](int step) {
+    if (step < n_steps) {
+      const int left = rows_total - step * kGemmBK;     // rows of this CTA's range at or after the tile's first row
+      float* as = As + (step % kGemmStages) * kGemmBK * kGemmBM;
+      float* bs = Bs + (step % kGemmStages) * kGemmBK * BN;
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const bool valid = a_row[t] < left;
+        cp_async16_zfill(as + a_dst[t], valid ? a_src[t] : A, valid);
+        a_src[t] += (size_t)kGemmBK * lda;
+      }
+#pragma unroll
+      for (int t = 0; t < kBPer; ++t) {
+        if (kBVec >= 256 * (t + 1) || tid + t * 256 < kBVec) {
+          const bool valid = b_row[t] < left;
+          cp_async16_zfill(bs + b_dst[t], valid ? b_src[t] : B, valid);
+          b_src[t] += (size_t)kGemmBK * ldb;
+        }
       }
     }
-  };
-  auto store_tile = [&](int buf) {
-#pragma unroll
-    for (int t = 0; t < 2; ++t) {
-      const int idx = tid + t * 256, row = idx >> 5, c4 = idx & 31;
-      *reinterpret_cast<float4*>(&As[buf][row][c4 * 4]) = ra[t];
-    }
-#pragma unroll
-    for (int t = 0; t < kBPer; ++t) {
-      const int idx = tid + t * 256;
-      if (idx < kBVec) {
-        const int row = idx / (BN / 4), c4 = idx % (BN / 4);
-        *reinterpret_cast<float4*>(&Bs[buf][row][c4 * 4]) = rb[t];
-      }
-    }
+    asm volatile("cp.async.commit_group;\n" ::);   // one group per step, empty ones included, keeps the count uniform
   };
 
-  if (n_steps > 0) {
-    load_tile(0);
-    store_tile(0);
-  }
-  __syncthreads();
+#pragma unroll
+  for (int st = 0; st < kGemmStages - 1; ++st) issue_tile(st);
   for (int step = 0; step < n_steps; ++step) {
-    const int cur = step & 1;
-    if (step + 1 < n_steps) load_tile(step + 1);
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(kGemmStages - 2));   // this step's tile has landed
+    __syncthreads();                                                     // ... for every thread; step-1's buffer is free
+    issue_tile(step + kGemmStages - 1);
+    const float* as = As + (step % kGemmStages) * kGemmBK * kGemmBM;
+    const float* bs = Bs + (step % kGemmStages) * kGemmBK * BN;
 #pragma unroll
     for (int k = 0; k < kGemmBK; ++k) {
-      const float4 a0 = *reinterpret_cast<const float4*>(&As[cur][k][ty * 4]);
-      const float4 a1 = *reinterpret_cast<const float4*>(&As[cur][k][64 + ty * 4]);
+      const float4 a0 = *reinterpret_cast<const float4*>(as + k * kGemmBM + ty * 4);
+      const float4 a1 = *reinterpret_cast<const float4*>(as + k * kGemmBM + 64 + ty * 4);
       const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
       float b[TN];
       if constexpr (TN == 8) {
-        const float4 b0 = *reinterpret_cast<const float4*>(&Bs[cur][k][tx * 4]);
-        const float4 b1 = *reinterpret_cast<const float4*>(&Bs[cur][k][BN / 2 + tx * 4]);
+        const float4 b0 = *reinterpret_cast<const float4*>(bs + k * BN + tx * 4);
+        const float4 b1 = *reinterpret_cast<const float4*>(bs + k * BN + BN / 2 + tx * 4);
         b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w;
         b[TN - 4] = b1.x; b[TN - 3] = b1.y; b[TN - 2] = b1.z; b[TN - 1] = b1.w;
       } else if constexpr (TN == 4) {
-        const float4 b0 = *reinterpret_cast<const float4*>(&Bs[cur][k][tx * 4]);
+        const float4 b0 = *reinterpret_cast<const float4*>(bs + k * BN + tx * 4);
         b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w;
       } else {
-        const float2 b0 = *reinterpret_cast<const float2*>(&Bs[cur][k][tx * 2]);
+        const float2 b0 = *reinterpret_cast<const float2*>(bs + k * BN + tx * 2);
         b[0] = b0.x; b[1] = b0.y;
       }
 #pragma unroll
@@ -306,9 +324,8 @@ k_gemm_tn(const float* __restrict__ A, int lda, const float* __restrict__ B, int
         for (int i = 0; i < 8; ++i) bsum[i] += a[i];
       }
     }
-    if (step + 1 < n_steps) store_tile(cur ^ 1);
-    __syncthreads();
   }
+  asm volatile("cp.async.wait_group 0;\n" ::);
 
   // partial[z][m][n]
   float* out = partial + (size_t)blockIdx.z * M * N;
@@ -398,10 +415,19 @@ cudaError_t launch_gemm_tn(const float* A, int lda, int M, const float* B, int l
   if (rows_per_split < kGemmBK) rows_per_split = kGemmBK;
   float* bias_partial = bias_dst ? partial + kGemmMaxMainFloats : nullptr;
   const dim3 grid(M / kGemmBM, N / BN, (unsigned)n_split);
-  if (BN == 128) k_gemm_tn<128><<<grid, 256, 0, s>>>(A, lda, B, ldb, n_rows, rows_per_split, M, N, partial, bias_partial);
-  else if (BN == 64) k_gemm_tn<64><<<grid, 256, 0, s>>>(A, lda, B, ldb, n_rows, rows_per_split, M, N, partial, bias_partial);
-  else k_gemm_tn<32><<<grid, 256, 0, s>>>(A, lda, B, ldb, n_rows, rows_per_split, M, N, partial, bias_partial);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e;
+#define VIPNERF_LAUNCH_GEMM(BNV)                                                                                     \
+  do {                                                                                                               \
+    e = cudaFuncSetAttribute(k_gemm_tn<BNV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes<BNV>()); \
+    if (e != cudaSuccess) return e;                                                                                  \
+    k_gemm_tn<BNV><<<grid, 256, gemm_smem_bytes<BNV>(), s>>>(A, lda, B, ldb, n_rows, rows_per_split, M, N, partial,  \
+                                                             bias_partial);                                          \
+  } while (0)
+  if (BN == 128) VIPNERF_LAUNCH_GEMM(128);
+  else if (BN == 64) VIPNERF_LAUNCH_GEMM(64);
+  else VIPNERF_LAUNCH_GEMM(32);
+#undef VIPNERF_LAUNCH_GEMM
+  e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   k_reduce_partials<<<(M * n_valid + 255) / 256, 256, 0, s>>>(partial, (int)n_split, M, N, dst, ldc, n_valid);
   if (bias_dst) k_reduce_partials<<<(M + 255) / 256, 256, 0, s>>>(bias_partial, (int)n_split, M, 1, bias_dst, 1, 1);
