@@ -467,12 +467,15 @@ cudaError_t launch_mlp_fp32(const RayPtrs& rp, const RenderFlags& fl, int64_t n_
   if (vis2 == nullptr) f.n_sec_views = 0;
   const unsigned grid = (unsigned)((n_points + kPts - 1) / kPts);
   cudaError_t e;
+  // two blocks per SM need the maximum shared-memory carve-out (2 x 112.5 KiB)
   if (save == nullptr) {
     e = cudaFuncSetAttribute(k_mlp_fp32<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_mlp_fp32<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
     k_mlp_fp32<false><<<grid, kThreads, kSmemBytes, s>>>(rp, f, n_points, S, z, small, big, sigma, rgb, vis, vis2, MlpSave{});
   } else {
     e = cudaFuncSetAttribute(k_mlp_fp32<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_mlp_fp32<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
     k_mlp_fp32<true><<<grid, kThreads, kSmemBytes, s>>>(rp, f, n_points, S, z, small, big, sigma, rgb, vis, vis2, *save);
   }
@@ -483,6 +486,7 @@ cudaError_t launch_mlp_bwd_fp32(const MlpBwdArgs& a, const void* packed, cudaStr
   if (a.n_points == 0) return cudaSuccess;
   if (a.nviews < 1 || a.nviews > kMaxViews) return cudaErrorInvalidValue;
   cudaError_t e = cudaFuncSetAttribute(k_mlp_bwd_fp32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmemBytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_mlp_bwd_fp32, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   if (e != cudaSuccess) return e;
   const float* small = reinterpret_cast<const float*>(packed);
   const float* wb = reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(packed) + kSmallBytes) + kFp32BigFloats;
