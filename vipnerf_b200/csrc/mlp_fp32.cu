@@ -130,7 +130,7 @@ __device__ __forceinline__ void view_head(const float (&acc9)[8][8], const float
       pre[i][2] = acc9[i][4 * j + 2] + b4.z;
       pre[i][3] = acc9[i][4 * j + 3] + b4.w;
     }
-#pragma unroll 1
+#pragma unroll 3
     for (int e = 0; e < kEncView; ++e) {
       const float4 w = *reinterpret_cast<const float4*>(wvd + e * 128 + n0);
       const float4 p0 = *reinterpret_cast<const float4*>(pev + e * kPts + tp * 8);
@@ -229,12 +229,16 @@ k_mlp_fp32(RayPtrs rp, RenderFlags fl, int64_t n_points, int S, const float* __r
 #pragma unroll
         for (int i = 0; i < 8; ++i) sigma_partial[i] = 0.f;
       }
+      float4 bias4[4];   // all 16 bias values of this thread's columns in one round trip
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bias4[j] = *reinterpret_cast<const float4*>(bias + j * 64 + tn * 4);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
+        const float bq[4] = {bias4[j].x, bias4[j].y, bias4[j].z, bias4[j].w};
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int n = j * 64 + tn * 4 + q;
-          const float b = bias[n];
+          const float b = bq[q];
           float h[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -342,6 +346,15 @@ k_mlp_fp32(RayPtrs rp, RenderFlags fl, int64_t n_points, int S, const float* __r
 constexpr int kMaxViews = 17;  // primary + up to 16 secondary views (17 KiB of logit gradients per tile)
 constexpr size_t kBwdSmemBytes = (256 * kPts + kWbufFloats + kPts * kMaxViews * 4 + kPts) * sizeof(float);
 
+// Pulls the 64 x 256 fp32 rows a later epilogue will read (ReLU masks) from HBM into L2 while the product before it
+// runs: 512 lines of 128 B per tile, four prefetches per thread.
+__device__ __forceinline__ void prefetch_rows_l2(const float* __restrict__ base, int64_t p0, int64_t n_points) {
+  for (int t = threadIdx.x; t < kPts * 8; t += kThreads) {
+    const int64_t pg = p0 + (t >> 3);
+    if (pg < n_points) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + pg * 256 + (t & 7) * 32));
+  }
+}
+
 // Epilogue of one backward product: acc = gradient w.r.t. the OUTPUT of the layer below (its post-ReLU h, or the
 // feature vector).  Adds the density head's contribution, applies the ReLU mask from the saved activations,
 // stores the result point-major (it is that layer's pre-activation gradient) and k-major into `g` for the next product.
@@ -445,10 +458,12 @@ k_mlp_bwd_fp32(MlpBwdArgs a, const float* __restrict__ small, const float* __res
   matmul_layer<4>(wb + kBwdOffViews, 128, g, wbuf, tp, tn, acc);
   bwd_epilogue(acc, g, tp, tn, p0, P, nullptr, a.dfeat, nullptr, nullptr);
   // feature_linear and the density head meet at h8: g_h8 = g_feature . W_f + g_sigma_pre * w_sigma, masked by h8 > 0
+  prefetch_rows_l2(a.h + (size_t)7 * P * 256, p0, P);
   matmul_layer<4>(wb + kBwdOffFeature, 256, g, wbuf, tp, tn, acc);
   bwd_epilogue(acc, g, tp, tn, p0, P, a.h + (size_t)7 * P * 256, a.dpre + (size_t)7 * P * 256, dsig_s, small + kOffWSigma);
   // pts_linears.7 .. 1: g_h_l = g_pre_l . W_l (hidden columns), masked by h_l > 0 -> g_pre_{l-1}
   for (int l = 7; l >= 1; --l) {
+    prefetch_rows_l2(a.h + (size_t)(l - 1) * P * 256, p0, P);
     matmul_layer<4>(wb + kBwdOffTrunk + (size_t)(7 - l) * 65536, 256, g, wbuf, tp, tn, acc);
     bwd_epilogue(acc, g, tp, tn, p0, P, a.h + (size_t)(l - 1) * P * 256, a.dpre + (size_t)(l - 1) * P * 256, nullptr, nullptr);
   }
