@@ -147,7 +147,7 @@ def _compare_full_grads(model, ref_grads):
     return worst
 
 
-@pytest.mark.parametrize('scene,n_rays,n_sec', [('fern', 333, 1), ('dtu', 200, 3)])
+@pytest.mark.parametrize('scene,n_rays,n_sec', [('fern', 333, 1), ('dtu', 200, 3), ('re10k', 128, 1)])   # re10k = BASELINE config 3
 def test_training_gradients_vs_oracle_autograd(scene, n_rays, n_sec, built_library):
     """Full gradient tensors against torch autograd over the oracle, with the draws of the plugin's own generator
     mirror, a ray count that is not a multiple of anything, and a different number of secondary views."""
