@@ -42,6 +42,9 @@ typedef enum vipnerf_status {
 #define VIPNERF_FLAG_NDC         (1u << 0) /* configs['data_loader']['ndc']   (VipNeRF01.py:16)          */
 #define VIPNERF_FLAG_WHITE_BKGD  (1u << 1) /* configs['model']['white_bkgd']  (VipNeRF01.py:363-364)     */
 #define VIPNERF_FLAG_LINDISP     (1u << 2) /* configs['model']['lindisp']     (VipNeRF01.py:183-190)     */
+#define VIPNERF_FLAG_TRAIN_TF32  (1u << 3) /* vipnerf_train_backward: the 256-wide parameter-gradient products
+                                              dW = dY^T X run on the tensor cores (tcgen05 kind::tf32, operands rounded
+                                              to tf32, fp32 accumulate) instead of fp32 CUDA cores                 */
 
 /* cfg.precision: arithmetic of the 256-wide matmuls (trunk layers, feature_linear, feature columns of
  * views_linears.0).  Everything else (encodings, heads, compositing, sampling) is always fp32. */
@@ -243,6 +246,17 @@ int vipnerf_composite_backward(const vipnerf_cfg* cfg, const vipnerf_rays* rays,
                                const float* z_vals, const float* sigma, const float* rgb, const float* vis,
                                const float* vis2, const vipnerf_pass_out* grad_out, float* d_sigma_logit,
                                float* d_head_logits, void* stream);
+
+/* The parameter-gradient product of the training backward alone (stage entry point of the parity tests):
+ * dw[m * ld_dw + n] = sum_p dy[p * ld_dy + m] * x[p * ld_x + n] for n < n_valid (what autograd computes for
+ * nn.Linear.weight: grad_output^T @ input), db[m] = sum_p dy[p * ld_dy + m] (NULL = skip).
+ * m in {128, 256}; n in {32, 64, 128, 256}.  mode 0 = fp32 CUDA-core kernel (k_gemm_tn; what vipnerf_train_backward
+ * uses by default), mode 1 = tcgen05 kind::tf32 kernel (k_gemm_tn_tf32; n must be 256; operands rounded to tf32 by the
+ * TMA copy; what VIPNERF_FLAG_TRAIN_TF32 selects).  workspace: vipnerf_param_gradient_gemm_workspace_bytes() bytes, 256-byte aligned. */
+size_t vipnerf_param_gradient_gemm_workspace_bytes(void);
+int vipnerf_param_gradient_gemm(const float* dy, int32_t ld_dy, int32_t m, const float* x, int32_t ld_x, int32_t n,
+                                int64_t n_rows, float* dw, int32_t ld_dw, int32_t n_valid, float* db, int32_t mode,
+                                void* workspace, size_t workspace_bytes, void* stream);
 
 /* --- profiling aid (not part of the reference-facing path): a device buffer of 64 uint64 that CTA 0 of every
  * subsequent tensor-core launch fills with cycle counters of its warp roles (see tools/tc_cycle_breakdown.py);

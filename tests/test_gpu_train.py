@@ -22,12 +22,13 @@ GRAD_MAX_TOL = 1e-2
 GRAD_NORM_TOL = 2e-3
 
 
-def _configs(ndc, chunk=4096, netchunk=16384, perturb=True, raw_noise_std=1.0, fine=True, white_bkgd=False):
+def _configs(ndc, chunk=4096, netchunk=16384, perturb=True, raw_noise_std=1.0, fine=True, white_bkgd=False,
+             train_precision='fp32'):
     mlp = dict(num_samples=64, netdepth=8, netwidth=256, points_positional_encoding_degree=10,
                views_positional_encoding_degree=4, use_view_dirs=True, view_dependent_rgb=True, predict_visibility=True)
     model = dict(name='VipNeRFFused01', coarse_mlp=dict(mlp), fine_mlp=dict(mlp, num_samples=128), chunk=chunk,
                  lindisp=False, netchunk=netchunk, perturb=perturb, raw_noise_std=raw_noise_std, white_bkgd=white_bkgd,
-                 precision='bf16')
+                 precision='bf16', train_precision=train_precision)
     if not fine:
         del model['fine_mlp']
     return {'data_loader': {'ndc': ndc}, 'model': model}
@@ -147,14 +148,39 @@ def _compare_full_grads(model, ref_grads):
     return worst
 
 
-@pytest.mark.parametrize('scene,n_rays,n_sec', [('fern', 333, 1), ('dtu', 200, 3), ('re10k', 128, 1)])   # re10k = BASELINE config 3
-def test_training_gradients_vs_oracle_autograd(scene, n_rays, n_sec, built_library):
+@pytest.mark.parametrize('mode', [0, 1])
+@pytest.mark.parametrize('P,M,N', [(4096, 256, 256), (10007, 128, 256), (96, 256, 256), (777, 256, 64), (5000, 128, 32)])
+def test_param_gradient_gemm(P, M, N, mode, built_library):
+    """dW = dY^T X and db = column sums, fp32 CUDA-core kernel (mode 0) and tcgen05 tf32 kernel (mode 1, N = 256),
+    against an fp64 product; ragged row counts exercise the zero-filled tails of both kernels."""
+    from vipnerf_b200 import training
+    if mode == 1 and N != 256:
+        with pytest.raises(NotImplementedError):
+            training.param_gradient_gemm(torch.zeros(P, M, device='cuda'), torch.zeros(P, N, device='cuda'), mode=1)
+        return
+    g = torch.Generator().manual_seed(P + M + N)
+    dy = (torch.randn(P, M, generator=g) * torch.rand(P, 1, generator=g)).cuda()
+    x = torch.relu(torch.randn(P, N, generator=g)).cuda()
+    dw, db = training.param_gradient_gemm(dy, x, mode=mode)
+    ref = dy.double().t() @ x.double()
+    err = ((dw.double() - ref).abs().max() / ref.abs().max()).item()
+    assert err <= (1e-3 if mode == 1 else 2e-6), err          # tf32: 2^-11 per operand; fp32: summation order
+    ref_b = dy.double().sum(0)
+    assert ((db.double() - ref_b).abs().max() / ref_b.abs().max()).item() <= 2e-6
+    again, _ = training.param_gradient_gemm(dy, x, mode=mode)
+    assert torch.equal(dw, again)                             # fixed-order split reduction
+
+
+@pytest.mark.parametrize('scene,n_rays,n_sec,train_precision', [
+    ('fern', 333, 1, 'fp32'), ('dtu', 200, 3, 'fp32'), ('re10k', 128, 1, 'fp32'),   # re10k = BASELINE config 3
+    ('fern', 333, 1, 'tf32'), ('re10k', 128, 1, 'tf32')])
+def test_training_gradients_vs_oracle_autograd(scene, n_rays, n_sec, train_precision, built_library):
     """Full gradient tensors against torch autograd over the oracle, with the draws of the plugin's own generator
     mirror, a ray count that is not a multiple of anything, and a different number of secondary views."""
     ndc = O.SCENES[scene]['ndc']
     rays = O.make_rays(scene, n_rays, seed=21, n_sec_views=n_sec)
     sup = O.make_supervision(scene, n_rays, n_sec)
-    cfg = _configs(ndc, chunk=128, netchunk=5000)
+    cfg = _configs(ndc, chunk=128, netchunk=5000, train_precision=train_precision)
     model = _train_model(cfg)
     torch.manual_seed(5)
     out = model(dict(H.to_cuda(rays)))
@@ -168,7 +194,7 @@ def test_training_gradients_vs_oracle_autograd(scene, n_rays, n_sec, built_libra
         mx, _ = H.rel_err(out[k], ref_out[k])
         assert mx <= 1e-4, (k, mx)
     worst = _compare_full_grads(model, ref_grads)
-    print(f'{scene}: worst gradient error {worst[0]:.2e} ({worst[1]})')
+    print(f'{scene} {train_precision}: worst gradient error {worst[0]:.2e} ({worst[1]})')
 
 
 def test_training_without_random_sources_and_coarse_only(built_library):

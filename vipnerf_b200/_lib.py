@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'libvipnerf_b200.so')
 
 ABI_VERSION = 1
-FLAG_NDC, FLAG_WHITE_BKGD, FLAG_LINDISP = 1, 2, 4
+FLAG_NDC, FLAG_WHITE_BKGD, FLAG_LINDISP, FLAG_TRAIN_TF32 = 1, 2, 4, 8
 PRECISION = {'fp32': 0, 'bf16': 1, 'bf16x3': 2}
 STATUS_NAMES = {0: 'OK', -1: 'EINVAL', -2: 'EUNSUPPORTED', -3: 'ECUDA', -4: 'EWORKSPACE', -5: 'EABI'}
 
@@ -89,6 +89,9 @@ EXPORTS = {
                                        c_void_p, c_size_t, c_void_p]),
     'vipnerf_composite_backward': (c_int, [POINTER(Cfg), POINTER(Rays), c_int64, c_int32, c_void_p, c_void_p, c_void_p,
                                            c_void_p, c_void_p, POINTER(PassOut), c_void_p, c_void_p, c_void_p]),
+    'vipnerf_param_gradient_gemm_workspace_bytes': (c_size_t, []),
+    'vipnerf_param_gradient_gemm': (c_int, [c_void_p, c_int32, c_int32, c_void_p, c_int32, c_int32, c_int64, c_void_p,
+                                            c_int32, c_int32, c_void_p, c_int32, c_void_p, c_size_t, c_void_p]),
     'vipnerf_debug_set_profile_buffer': (c_int, [c_void_p]),
 }
 
@@ -134,7 +137,8 @@ def check(status: int, what: str) -> None:
 
 
 def make_cfg(n_coarse=64, n_fine=128, n_sec_views=0, ndc=False, white_bkgd=False, lindisp=False, precision='bf16',
-             l_pts=10, l_view=4, depth=8, width=256, skip=4) -> Cfg:
-    flags = (FLAG_NDC if ndc else 0) | (FLAG_WHITE_BKGD if white_bkgd else 0) | (FLAG_LINDISP if lindisp else 0)
+             l_pts=10, l_view=4, depth=8, width=256, skip=4, train_tf32=False) -> Cfg:
+    flags = ((FLAG_NDC if ndc else 0) | (FLAG_WHITE_BKGD if white_bkgd else 0) | (FLAG_LINDISP if lindisp else 0)
+             | (FLAG_TRAIN_TF32 if train_tf32 else 0))
     return Cfg(ABI_VERSION, n_coarse, n_fine, l_pts, l_view, depth, width, skip, n_sec_views, flags,
                PRECISION[precision], 0)

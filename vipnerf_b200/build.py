@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 OBJ_DIR = os.path.join(HERE, 'build')
 LIB_PATH = os.path.join(HERE, 'libvipnerf_b200.so')
-SOURCES = ['api.cu', 'stage_kernels.cu', 'frame_kernels.cu', 'prior_kernels.cu', 'mlp_fp32.cu', 'train_kernels.cu', 'mlp_tc.cu']
+SOURCES = ['api.cu', 'stage_kernels.cu', 'frame_kernels.cu', 'prior_kernels.cu', 'mlp_fp32.cu', 'train_kernels.cu', 'gemm_tc.cu', 'mlp_tc.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '-Xptxas', '-v', '--expt-relaxed-constexpr']
 # extra -D switches for experiments (e.g. VIPNERF_NVCC_DEFINES="VIPNERF_ONES_4K"), part of the build digest

@@ -163,6 +163,14 @@ SavedLayout carve_saved(const vipnerf_cfg* cfg, int64_t n_rays) {
   return L;
 }
 
+// Split-reduction scratch of the parameter-gradient products: the larger of the FFMA and the tensor-core kernels' partial
+// tiles (the latter: one 256 x 256 tile per SM, up to 160 SMs), followed by the column-sum partials.
+constexpr size_t kColsumPartialFloats = 4 * 148 * 256;
+size_t gemm_partial_floats() {
+  const size_t a = gemm_tn_partial_floats(), b = gemm_tn_tc_partial_floats(160);
+  return a > b ? a : b;
+}
+
 // Scratch of the backward: sized for the larger sample set, reused by both
 struct BwdLayout { size_t dsig, dlogit, dpre, dfeat, dacc9, dhv, partial, total; };
 
@@ -173,7 +181,7 @@ BwdLayout carve_bwd(const vipnerf_cfg* cfg, int64_t n_rays) {
   size_t off = 0;
   auto take = [&](size_t floats) { size_t o = off; off = align_up(off + floats * sizeof(float), 256); return o; };
   L.dsig = take(P); L.dlogit = take(P * nv * 4); L.dpre = take(P * 256 * 8); L.dfeat = take(P * 256);
-  L.dacc9 = take(P * 128); L.dhv = take(P * nv * 128); L.partial = take(gemm_tn_partial_floats());
+  L.dacc9 = take(P * 128); L.dhv = take(P * nv * 128); L.partial = take(gemm_partial_floats() + kColsumPartialFloats);
   L.total = off + 256;
   return L;
 }
@@ -514,6 +522,14 @@ int vipnerf_train_backward(const vipnerf_cfg* cfg, const vipnerf_rays* rays, int
     if ((e = launch_mlp_bwd_fp32(a, pass ? packed_fine : packed_coarse, s)) != cudaSuccess) return fail_cuda(e, "mlp_bwd_fp32");
     // 3. parameter gradients: dW = dY^T X over all points, db = column sums of dY
     const size_t PL = (size_t)P * 256;
+    const bool tf32 = (cfg->flags & VIPNERF_FLAG_TRAIN_TF32) != 0;
+    // one 256-wide product: fp32 CUDA cores, or the tensor cores (+ a column-sum pass for the bias gradient)
+    auto wide_gemm = [&](const float* dy, int M, const float* x, float* dw, int ldc, float* db) -> cudaError_t {
+      if (!tf32) return launch_gemm_tn(dy, M, M, x, 256, 256, P, dw, ldc, 256, db, partial, s);
+      cudaError_t r = launch_gemm_tn_tc(dy, M, M, x, 256, P, dw, ldc, 256, partial, s);
+      if (r == cudaSuccess && db != nullptr) r = launch_colsum(dy, M, M, P, db, partial + gemm_partial_floats(), s);
+      return r;
+    };
     for (int l = 0; l < 8 && e == cudaSuccess; ++l) {
       const float* dy = dpre + l * PL;
       float* dw = pg[2 * l];
@@ -523,17 +539,17 @@ int vipnerf_train_backward(const vipnerf_cfg* cfg, const vipnerf_rays* rays, int
       } else if (l == 5) {   // input = cat([encoding, h4]) (:543-544)
         e = launch_gemm_tn(dy, 256, 256, enc, 64, 64, P, dw, kWidth + kEncPts, kEncPts, db, partial, s);
         if (e == cudaSuccess)
-          e = launch_gemm_tn(dy, 256, 256, h + 4 * PL, 256, 256, P, dw + kEncPts, kWidth + kEncPts, 256, nullptr, partial, s);
+          e = wide_gemm(dy, 256, h + 4 * PL, dw + kEncPts, kWidth + kEncPts, nullptr);
       } else {
-        e = launch_gemm_tn(dy, 256, 256, h + (l - 1) * PL, 256, 256, P, dw, 256, 256, db, partial, s);
+        e = wide_gemm(dy, 256, h + (l - 1) * PL, dw, 256, db);
       }
     }
     if (e != cudaSuccess) return fail_cuda(e, "gemm_tn (pts_linears)");
     // feature_linear (input h7 = output of pts_linears.7)
-    if ((e = launch_gemm_tn(dfeat, 256, 256, h + 7 * PL, 256, 256, P, pg[20], 256, 256, pg[21], partial, s)) != cudaSuccess)
+    if ((e = wide_gemm(dfeat, 256, h + 7 * PL, pg[20], 256, pg[21])) != cudaSuccess)
       return fail_cuda(e, "gemm_tn (feature_linear)");
     // views_linears.0: feature columns over points, direction columns and bias over (point, view) rows
-    if ((e = launch_gemm_tn(dacc9, 128, 128, feat, 256, 256, P, pg[16], kWidth + kEncView, 256, nullptr, partial, s)) != cudaSuccess)
+    if ((e = wide_gemm(dacc9, 128, feat, pg[16], kWidth + kEncView, nullptr)) != cudaSuccess)
       return fail_cuda(e, "gemm_tn (views_linears feature columns)");
     if ((e = launch_gemm_tn(dhv, 128, 128, pev, 32, 32, P * nv, pg[16] + kWidth, kWidth + kEncView, kEncView, pg[17], partial, s)) != cudaSuccess)
       return fail_cuda(e, "gemm_tn (views_linears direction columns)");
@@ -561,6 +577,35 @@ int vipnerf_composite_backward(const vipnerf_cfg* cfg, const vipnerf_rays* rays,
   cudaError_t e = launch_composite_bwd(rp, make_flags(cfg), n_rays, n_samples, z_vals, sigma, rgb, vis, vis2,
                                        to_grads(grad_out), d_sigma_logit, d_head_logits, static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return fail_cuda(e, "composite_bwd");
+  return VIPNERF_OK;
+}
+
+size_t vipnerf_param_gradient_gemm_workspace_bytes(void) { return (gemm_partial_floats() + kColsumPartialFloats) * sizeof(float) + 256; }
+
+int vipnerf_param_gradient_gemm(const float* dy, int32_t ld_dy, int32_t m, const float* x, int32_t ld_x, int32_t n,
+                                int64_t n_rows, float* dw, int32_t ld_dw, int32_t n_valid, float* db, int32_t mode,
+                                void* workspace, size_t workspace_bytes, void* stream) {
+  if (!dy || !x || !dw || !workspace) return fail(VIPNERF_EINVAL, "dy / x / dw / workspace is NULL");
+  if ((m != 128 && m != 256) || (n != 32 && n != 64 && n != 128 && n != 256))
+    return fail(VIPNERF_EUNSUPPORTED, "m=%d n=%d: m in {128, 256}, n in {32, 64, 128, 256}", m, n);
+  if (n_rows < 1 || ld_dy < m || ld_x < n || n_valid < 1 || n_valid > n || ld_dw < n_valid)
+    return fail(VIPNERF_EINVAL, "n_rows=%lld ld_dy=%d ld_x=%d n_valid=%d ld_dw=%d", (long long)n_rows, ld_dy, ld_x, n_valid, ld_dw);
+  if (misaligned(dy) || misaligned(x) || (ld_dy & 3) || (ld_x & 3)) return fail(VIPNERF_EINVAL, "dy / x must be 16-byte aligned with row strides that are multiples of 4 floats");
+  if (workspace_bytes < vipnerf_param_gradient_gemm_workspace_bytes() || (reinterpret_cast<uintptr_t>(workspace) & 255u))
+    return fail(VIPNERF_EWORKSPACE, "workspace %zu bytes (need %zu, 256-byte aligned)", workspace_bytes, vipnerf_param_gradient_gemm_workspace_bytes());
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  float* partial = static_cast<float*>(workspace);
+  cudaError_t e;
+  if (mode != 0 && mode != 1) return fail(VIPNERF_EINVAL, "mode=%d", mode);
+  if (mode == 1) {
+    if (n != 256) return fail(VIPNERF_EUNSUPPORTED, "the tensor-core product is built for n = 256 (got %d)", n);
+    e = launch_gemm_tn_tc(dy, ld_dy, m, x, ld_x, n_rows, dw, ld_dw, n_valid, partial, s);
+    if (e == cudaSuccess && db != nullptr)
+      e = launch_colsum(dy, ld_dy, m, n_rows, db, partial + gemm_partial_floats(), s);
+  } else {
+    e = launch_gemm_tn(dy, ld_dy, m, x, ld_x, n, n_rows, dw, ld_dw, n_valid, db, partial, s);
+  }
+  if (e != cudaSuccess) return fail_cuda(e, "param_gradient_gemm");
   return VIPNERF_OK;
 }
 

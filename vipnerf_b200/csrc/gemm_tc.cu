@@ -1,0 +1,276 @@
+// Parameter-gradient GEMM on the tensor cores:  C[m][n] = sum_p A[p][m] * B[p][n]  (dW = dY^T X, training row f1).
+//
+// Both operands are the fp32 point-major arrays the chain kernels already write (A = pre-activation gradients
+// [P][M], B = layer inputs [P][256]); the reduction index p is the OUTER index of both, i.e. both are "MN-major"
+// operands for the MMA.  tcgen05.mma kind::tf32 reads fp32 words from shared memory directly, so no conversion or
+// transposition pass exists: the TMA engine drops [32 points] x [32 columns] fp32 boxes (128-byte rows, 128-byte
+// swizzle with 32-byte atoms - the only layout tcgen05 reads MN-major 32-bit operands from) into a 3-stage ring, one elected thread issues M=128, N=256, K=8 MMAs (one per 8 points and 128-row half of the
+// output) that accumulate the CTA's whole 256 x 256 (or 128 x 256) fp32 tile in TMEM (all 512 columns), and after
+// the CTA's point range is exhausted four warps drain TMEM into a partial tile that k_reduce_partials (train_kernels.cu)
+// sums over the CTAs in a fixed order.  One CTA per SM, 148 point ranges.
+//
+//   warp 0      TMA producer (one lane)
+//   warp 1      TMEM allocation, MMA issue (one lane), commits that free ring stages
+//   warps 2..5  epilogue: TMEM -> registers -> global partial tile (warp w owns TMEM lanes 32*(w%4)..)
+//
+// Roofline: HBM.  Each CTA reads every A and B row of its point range once: (M + 256) * 4 bytes per point and layer,
+// i.e. 2 KiB/point for the 256 x 256 layers -> 2.1 GB per layer at 10^6 points, 0.33 ms at 6.4 TB/s; the tf32 tensor
+// time of the same layer is 0.2 ms.  The FFMA kernel it replaces needs 2.4 ms.
+//
+// Numerics: operands are rounded to tf32 (10-bit mantissa) by the TMA copy (CU_TENSOR_MAP_DATA_TYPE_TFLOAT32),
+// products accumulate in fp32.  Gradients therefore carry ~2^-11 relative rounding noise per product; it is opt-in
+// (configs['model']['train_precision'] = 'tf32'), the default training path stays fp32 FFMA.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdio>
+
+#include "kernels.h"
+
+namespace vipnerf {
+namespace {
+
+constexpr int kTcStages = 3;
+constexpr int kTcRows = 32;                        // points per ring stage
+constexpr int kBoxBytes = kTcRows * 128;           // one [32 points][32 fp32] box
+constexpr int kTcThreads = 192;
+constexpr long long kTcTimeoutCycles = 4000000000ll;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {   // a protocol bug traps instead of hanging
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > kTcTimeoutCycles) {
+      printf("vipnerf gemm_tc: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+
+// MN-major shared-memory matrix descriptor for 32-bit operands (cute::UMMA::SmemDescriptor).  tf32 operands whose
+// reduction index is the outer one can only be read in the SWIZZLE_128B_BASE32B layout (layout type 1): atoms of
+// [4 k] x [32 fp32 = 128 B] whose 32-byte chunks are XOR-ed with (k % 4) - what the TMA writes in the
+// CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B mode.  An MMA of K = 8 reads two atoms along K (512 B apart = the stride-dimension
+// byte offset); consecutive atoms along M / N are one TMA box (4 KiB) apart = the leading-dimension byte offset.
+// start >> 4 in [0,14), LBO >> 4 in [16,30), SBO >> 4 in [32,46), version 1 in [46,48), layout type in [61,64).
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(kBoxBytes >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) |
+         (1ull << 46) | (1ull << 61);
+}
+// Instruction descriptor: D = F32 (c_format 1 at [4,6)), A = B = TF32 (format 2 at [7,10) / [10,13)), both operands
+// MN-major (a_major bit 15, b_major bit 16), N >> 3 at [17,23), M >> 4 at [24,29).
+constexpr uint32_t instr_desc_tf32_mn(uint32_t n, uint32_t m) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((n >> 3) << 17) | ((m >> 4) << 24);
+}
+
+struct GemmTcParams {
+  CUtensorMap map_a, map_b;
+  int M;                    // 128 or 256
+  int64_t n_rows, rows_per_split;
+  float* partial;           // [gridDim.x][M][256]
+};
+
+__global__ void __launch_bounds__(kTcThreads, 1) k_gemm_tn_tf32(const __grid_constant__ GemmTcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];   // ring stages, then the mbarriers and the TMEM base slot
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int halves = p.M / 128;
+  const int a_boxes = p.M / 32;
+  const uint32_t stage_bytes = (uint32_t)(a_boxes + 8) * kBoxBytes;
+  uint8_t* tail = smem + kTcStages * stage_bytes;
+  uint32_t* tmem_ptr_slot = reinterpret_cast<uint32_t*>(tail + 8 * (2 * kTcStages + 1));
+  const uint32_t bar0 = smem_u32(tail);
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (kTcStages + s); };
+  const uint32_t done_bar = bar0 + 8u * (2 * kTcStages);
+
+  const int64_t r_begin = (int64_t)blockIdx.x * p.rows_per_split;
+  const int64_t r_end = min(p.n_rows, r_begin + p.rows_per_split);
+  const int n_steps = r_end > r_begin ? (int)((r_end - r_begin + kTcRows - 1) / kTcRows) : 0;
+
+  if (threadIdx.x == 0) {
+    if ((smem_u32(smem) & 1023u) != 0) { printf("vipnerf gemm_tc: shared memory base not 1 KiB aligned\n"); __trap(); }
+    for (int s = 0; s < kTcStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(done_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_ptr_slot);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int s = 0; s < n_steps; ++s) {
+        const int st = s % kTcStages;
+        if (s >= kTcStages) mbar_wait(empty_bar(st), ((s / kTcStages) - 1) & 1);
+        mbar_expect_tx(full_bar(st), stage_bytes);
+        const uint32_t dst = smem_u32(smem) + (uint32_t)st * stage_bytes;
+        const int row = (int)(r_begin + (int64_t)s * kTcRows);   // rows past the end of the arrays are zero-filled by the TMA
+        for (int j = 0; j < a_boxes; ++j) tma_load_2d(dst + j * kBoxBytes, &p.map_a, j * 32, row, full_bar(st));
+        for (int j = 0; j < 8; ++j) tma_load_2d(dst + (a_boxes + j) * kBoxBytes, &p.map_b, j * 32, row, full_bar(st));
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = instr_desc_tf32_mn(256, 128);
+      for (int s = 0; s < n_steps; ++s) {
+        const int st = s % kTcStages;
+        mbar_wait(full_bar(st), (s / kTcStages) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a0 = smem_u32(smem) + (uint32_t)st * stage_bytes;
+        const uint32_t b0 = a0 + (uint32_t)a_boxes * kBoxBytes;
+#pragma unroll
+        for (int k = 0; k < kTcRows / 8; ++k) {               // K = 8 points per MMA = one 1 KiB atom row of every box
+          const uint64_t b_desc = make_desc_mn(b0 + k * 1024);
+          for (int h = 0; h < halves; ++h) {
+            const uint64_t a_desc = make_desc_mn(a0 + h * 4 * kBoxBytes + k * 1024);
+            umma_tf32(tmem_base + h * 256, a_desc, b_desc, idesc, (s > 0 || k > 0) ? 1u : 0u);
+          }
+        }
+        umma_commit(empty_bar(st));     // frees the stage when its MMAs have retired
+      }
+      umma_commit(done_bar);            // all MMAs of this CTA retired -> TMEM holds the tile
+    }
+  } else {
+    // epilogue warps: warp w may touch TMEM lanes [32 * (w % 4), +32)
+    float* out = p.partial + (size_t)blockIdx.x * p.M * 256;
+    const int quarter = warp & 3;
+    if (n_steps > 0) {
+      mbar_wait(done_bar, 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+    for (int h = 0; h < halves; ++h) {
+      const int m = h * 128 + quarter * 32 + lane;
+      for (int c = 0; c < 8; ++c) {
+        uint32_t v[32];
+        if (n_steps > 0) {
+          tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + h * 256 + c * 32, v);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = 0u;
+        }
+        float4* dst = reinterpret_cast<float4*>(out + (size_t)m * 256 + c * 32);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          dst[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
+                               __uint_as_float(v[4 * i + 3]));
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode_tiled() {
+  static EncodeTiledFn fn = []() -> EncodeTiledFn {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      return nullptr;
+    return reinterpret_cast<EncodeTiledFn>(ptr);
+  }();
+  return fn;
+}
+
+// [n_rows][ld] fp32 row-major, first `cols` columns used; box = 32 columns x 32 rows, 128-byte swizzle with 32-byte atoms, tf32 rounding
+cudaError_t encode_rows_map(CUtensorMap* map, const float* base, int ld, int cols, int64_t n_rows) {
+  EncodeTiledFn encode = get_encode_tiled();
+  if (encode == nullptr) return cudaErrorNotSupported;
+  const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)n_rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+  const cuuint32_t box[2] = {32, (cuuint32_t)kTcRows};
+  const cuuint32_t elem_strides[2] = {1, 1};
+  const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 2,
+                            const_cast<float*>(base), dims, strides, box, elem_strides, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
+}  // namespace
+
+size_t gemm_tn_tc_partial_floats(int sms) { return (size_t)sms * 256 * 256; }
+
+cudaError_t launch_gemm_tn_tc(const float* A, int lda, int M, const float* B, int ldb, int64_t n_rows, float* dst,
+                              int ldc, int n_valid, float* partial, cudaStream_t s) {
+  if ((M != 128 && M != 256) || n_rows < 1) return cudaErrorInvalidValue;
+  if ((reinterpret_cast<uintptr_t>(A) & 15u) || (reinterpret_cast<uintptr_t>(B) & 15u) || (lda & 3) || (ldb & 3))
+    return cudaErrorInvalidValue;
+  int dev = 0, sms = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+  int64_t n_split = sms;
+  const int64_t max_by_rows = (n_rows + 4 * kTcRows - 1) / (4 * kTcRows);
+  if (n_split > max_by_rows) n_split = max_by_rows;
+  int64_t rows_per_split = (n_rows + n_split - 1) / n_split;
+  rows_per_split = (rows_per_split + kTcRows - 1) / kTcRows * kTcRows;
+  n_split = (n_rows + rows_per_split - 1) / rows_per_split;
+
+  GemmTcParams p{};
+  if ((e = encode_rows_map(&p.map_a, A, lda, M, n_rows)) != cudaSuccess) return e;
+  if ((e = encode_rows_map(&p.map_b, B, ldb, 256, n_rows)) != cudaSuccess) return e;
+  p.M = M; p.n_rows = n_rows; p.rows_per_split = rows_per_split; p.partial = partial;
+  const size_t smem = (size_t)kTcStages * (M / 32 + 8) * kBoxBytes + 128;
+  if ((e = cudaFuncSetAttribute(k_gemm_tn_tf32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+  k_gemm_tn_tf32<<<(unsigned)n_split, kTcThreads, smem, s>>>(p);
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  return launch_reduce_partials(partial, (int)n_split, M, 256, dst, ldc, n_valid, s);
+}
+
+}  // namespace vipnerf

@@ -80,6 +80,14 @@ cudaError_t launch_composite_bwd(const RayPtrs& rp, const RenderFlags& fl, int64
 size_t gemm_tn_partial_floats();
 cudaError_t launch_gemm_tn(const float* A, int lda, int M, const float* B, int ldb, int N, int64_t n_rows, float* dst,
                            int ldc, int n_valid, float* bias_dst, float* partial, cudaStream_t s);
+cudaError_t launch_reduce_partials(const float* partial, int n_split, int M, int N, float* dst, int ldc, int n_valid,
+                                   cudaStream_t s);
+cudaError_t launch_colsum(const float* A, int lda, int M, int64_t n_rows, float* dst, float* partial, cudaStream_t s);
+// gemm_tc.cu : the same product on the tensor cores (tcgen05 kind::tf32 reading the fp32 arrays through TMA), N = 256,
+// M in {128, 256}; no bias output (launch_colsum).  `partial`: gemm_tn_tc_partial_floats(#SMs) floats.
+size_t gemm_tn_tc_partial_floats(int sms);
+cudaError_t launch_gemm_tn_tc(const float* A, int lda, int M, const float* B, int ldb, int64_t n_rows, float* dst,
+                              int ldc, int n_valid, float* partial, cudaStream_t s);
 // out[m][n] = sum_p G[p][m] * H[p][n] for M <= 4 (G: M floats per row), N <= 256; gsum_dst[m] = sum_p G[p][m].
 cudaError_t launch_small_tn(const float* G, int M, const float* H, int N, int64_t n_rows, float* dst, float* gsum_dst,
                             float* partial, cudaStream_t s);

@@ -434,6 +434,40 @@ cudaError_t launch_gemm_tn(const float* A, int lda, int M, const float* B, int l
   return cudaGetLastError();
 }
 
+cudaError_t launch_reduce_partials(const float* partial, int n_split, int M, int N, float* dst, int ldc, int n_valid,
+                                   cudaStream_t s) {
+  k_reduce_partials<<<(M * n_valid + 255) / 256, 256, 0, s>>>(partial, n_split, M, N, dst, ldc, n_valid);
+  return cudaGetLastError();
+}
+
+// bias_dst[m] = sum_p A[p][m] alone (the tensor-core GEMM does not produce the column sums): A viewed as G with M
+// columns against a one-column H of ones is what k_small_tn's gsum path computes - here a dedicated streaming kernel.
+__global__ void __launch_bounds__(256) k_colsum(const float* __restrict__ A, int lda, int M, int64_t n_rows,
+                                                int64_t rows_per_split, float* __restrict__ partial) {
+  const int m = threadIdx.x;
+  const int64_t r_begin = (int64_t)blockIdx.x * rows_per_split;
+  const int64_t r_end = min(n_rows, r_begin + rows_per_split);
+  float acc = 0.f;
+  if (m < M) {
+#pragma unroll 8
+    for (int64_t r = r_begin; r < r_end; ++r) acc += A[r * lda + m];
+    partial[(size_t)blockIdx.x * M + m] = acc;
+  }
+}
+
+cudaError_t launch_colsum(const float* A, int lda, int M, int64_t n_rows, float* dst, float* partial, cudaStream_t s) {
+  if (M < 1 || M > 256) return cudaErrorInvalidValue;
+  int64_t n_split = 4 * 148;
+  const int64_t max_by_rows = (n_rows + 63) / 64;
+  if (n_split > max_by_rows) n_split = max_by_rows;
+  if (n_split < 1) n_split = 1;
+  const int64_t rows_per_split = (n_rows + n_split - 1) / n_split;
+  k_colsum<<<(unsigned)n_split, 256, 0, s>>>(A, lda, M, n_rows, rows_per_split, partial);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  return launch_reduce_partials(partial, (int)n_split, M, 1, dst, 1, 1, s);
+}
+
 cudaError_t launch_small_tn(const float* G, int M, const float* H, int N, int64_t n_rows, float* dst, float* gsum_dst,
                             float* partial, cudaStream_t s) {
   if ((M != 1 && M != 4) || N < 4 || N > 256) return cudaErrorInvalidValue;

@@ -117,7 +117,8 @@ class _RenderTrain(torch.autograd.Function):
         n_coarse, n_fine, V = spec['n_coarse'], spec['n_fine'] if has_fine else 0, spec['n_sec_views']
         R = outputs[0].shape[0]
         cfg = _lib.make_cfg(n_coarse=n_coarse, n_fine=n_fine, n_sec_views=V, ndc=spec['ndc'],
-                            white_bkgd=spec['white_bkgd'], lindisp=spec['lindisp'], precision='fp32')
+                            white_bkgd=spec['white_bkgd'], lindisp=spec['lindisp'], precision='fp32',
+                            train_tf32=spec['tf32_gradients'])
         keep: list = []
         rays = renderpath._make_rays(spec['batch'], spec['ndc'], n_coarse, n_fine, V, keep)
         fwd, gout = _lib.Out(), _lib.Out()
@@ -145,18 +146,19 @@ class _RenderTrain(torch.autograd.Function):
 def render_rays_train(batch: Dict[str, torch.Tensor], params_coarse: Dict[str, torch.Tensor],
                       params_fine: Optional[Dict[str, torch.Tensor]], *, ndc: bool, n_coarse: int = 64,
                       n_fine: int = 128, n_sec_views: int = 0, white_bkgd: bool = False,
-                      lindisp: bool = False) -> Dict[str, torch.Tensor]:
+                      lindisp: bool = False, tf32_gradients: bool = False) -> Dict[str, torch.Tensor]:
     """Train-mode VipNeRF.render_rays (VipNeRF01.py:74-171 with self.training: retraw and sec_views_vis on, :40),
     differentiable w.r.t. the MLP parameters.  `batch` holds the ray tensors plus the random draws (`t_rand`, `u_rand`,
     `sigma_noise_coarse`, `sigma_noise_fine`; see draw_training_randoms) - a missing draw switches that source off.
-    `params_*`: the reference's state_dict names of one MLP -> parameter tensors (CUDA, fp32)."""
+    `params_*`: the reference's state_dict names of one MLP -> parameter tensors (CUDA, fp32).
+    `tf32_gradients`: the 256-wide parameter-gradient products of the backward run on the tensor cores (tcgen05 tf32)."""
     renderpath._require_cuda(batch['rays_o'], 'rays_o')
     has_fine = params_fine is not None and n_fine > 0
     names = renderpath.MLP_PARAM_ORDER
     keys = renderpath.pass_keys(ndc, True, n_sec_views)
     out_names = [f'{k}_coarse' for k in keys] + ([f'{k}_fine' for k in keys] if has_fine else [])
     spec = dict(batch=batch, ndc=ndc, n_coarse=n_coarse, n_fine=n_fine, n_sec_views=n_sec_views, white_bkgd=white_bkgd,
-                lindisp=lindisp, has_fine=has_fine, out_names=out_names)
+                lindisp=lindisp, has_fine=has_fine, out_names=out_names, tf32_gradients=bool(tf32_gradients))
     params = [params_coarse[k] for k in names] + ([params_fine[k] for k in names] if has_fine else [])
     outputs = _RenderTrain.apply(spec, *params)
     result = dict(zip(out_names, outputs))
@@ -198,3 +200,22 @@ def volume_rendering_backward(batch: Dict[str, torch.Tensor], z_vals: torch.Tens
             visibility.data_ptr(), renderpath._ptr(visibility2), ctypes.byref(gout), d_sigma.data_ptr(),
             d_logits.data_ptr(), renderpath._stream(device)), 'vipnerf_composite_backward')
     return d_sigma, d_logits
+
+
+def param_gradient_gemm(dy: torch.Tensor, x: torch.Tensor, *, mode: int = 0, with_bias: bool = True):
+    """dW = dy^T x and db = column sums of dy over all rows (vipnerf_param_gradient_gemm).  dy [P,M], x [P,N] fp32 CUDA;
+    mode 0 = fp32 CUDA cores, 1 = tcgen05 tf32 (N = 256)."""
+    lib = _lib.load()
+    dy, x = renderpath._f32c(dy, 'dy'), renderpath._f32c(x, 'x')
+    P, M = dy.shape
+    N = x.shape[1]
+    device = dy.device
+    dw = torch.empty((M, N), dtype=torch.float32, device=device)
+    db = torch.empty((M,), dtype=torch.float32, device=device) if with_bias else None
+    with torch.cuda.device(device):
+        ws_bytes = lib.vipnerf_param_gradient_gemm_workspace_bytes()
+        ws = renderpath._workspace(ws_bytes, device)
+        _lib.check(lib.vipnerf_param_gradient_gemm(dy.data_ptr(), M, M, x.data_ptr(), N, N, P, dw.data_ptr(), N, N,
+                                                   renderpath._ptr(db), mode, ws.data_ptr(), ws_bytes,
+                                                   renderpath._stream(device)), 'vipnerf_param_gradient_gemm')
+    return dw, db
