@@ -133,8 +133,8 @@ def _oracle_step(sd_cpu, rays, sup, draws, ndc, **kw):
     return out, total.detach(), {k: v.grad for k, v in sd.items()}
 
 
-def _compare_full_grads(model, ref_grads):
-    worst = (0.0, '')
+def _compare_full_grads(model, ref_grads, max_tol=GRAD_MAX_TOL, norm_tol=5 * GRAD_NORM_TOL):
+    worst, worst_norm = (0.0, ''), 0.0
     for name, p in model.named_parameters():
         ref = ref_grads[name]
         g = p.grad.detach().cpu()
@@ -142,10 +142,11 @@ def _compare_full_grads(model, ref_grads):
         scale = ref.abs().max().clamp_min(1e-30)
         e_max = ((g - ref).abs().max() / scale).item()
         e_norm = ((g - ref).norm() / ref.norm().clamp_min(1e-30)).item()
-        assert e_max <= GRAD_MAX_TOL, (name, e_max)
-        assert e_norm <= 5 * GRAD_NORM_TOL, (name, e_norm)
+        assert e_max <= max_tol, (name, e_max)
+        assert e_norm <= norm_tol, (name, e_norm)
         worst = max(worst, (e_max, name))
-    return worst
+        worst_norm = max(worst_norm, e_norm)
+    return worst[0], worst[1], worst_norm
 
 
 @pytest.mark.parametrize('mode', [0, 1])
@@ -189,12 +190,20 @@ def test_training_gradients_vs_oracle_autograd(scene, n_rays, n_sec, train_preci
     torch.manual_seed(5)
     draws = O.draw_training_randoms(n_rays, 64, 128, 128, 5000, True, 1.0)
     ref_out, ref_total, ref_grads = _oracle_step(O.synth_state_dict(0), rays, sup, draws, ndc, chunk=128, netchunk=5000)
-    assert abs(total.item() - ref_total.item()) <= 2e-4 * abs(ref_total.item())
-    for k in ('rgb_coarse', 'rgb_fine', 'visibility2_coarse', 'visibility2_fine', 'depth_coarse'):
-        mx, _ = H.rel_err(out[k], ref_out[k])
-        assert mx <= 1e-4, (k, mx)
-    worst = _compare_full_grads(model, ref_grads)
-    print(f'{scene} {train_precision}: worst gradient error {worst[0]:.2e} ({worst[1]})')
+    # tf32 mode: every product of the step sees operands rounded to 10 mantissa bits (PyTorch's allow_tf32 arithmetic);
+    # the forward moves by ~1e-3 and ReLU decisions of near-zero units flip, so the gates are statistical there
+    tf32 = train_precision == 'tf32'
+    assert abs(total.item() - ref_total.item()) <= (2e-2 if tf32 else 2e-4) * abs(ref_total.item())
+    for k in ('rgb_coarse', 'rgb_fine', 'visibility2_coarse', 'visibility2_fine', 'depth_coarse', 'raw_sigma_coarse',
+              'raw_rgb_coarse', 'raw_visibility_coarse'):
+        mx, med = H.rel_err(out[k], ref_out[k])
+        print(f'{scene} {train_precision} {k}: max {mx:.2e} median {med:.2e}')
+        if tf32:
+            assert med <= 2e-3 and mx <= 0.2, (k, mx, med)
+        else:
+            assert mx <= 1e-4, (k, mx)
+    worst = _compare_full_grads(model, ref_grads, max_tol=0.5 if tf32 else GRAD_MAX_TOL, norm_tol=0.2 if tf32 else 5 * GRAD_NORM_TOL)
+    print(f'{scene} {train_precision}: worst gradient error {worst[0]:.2e} ({worst[1]}), worst L2 error {worst[2]:.2e}')
 
 
 def test_training_without_random_sources_and_coarse_only(built_library):

@@ -186,6 +186,75 @@ BwdLayout carve_bwd(const vipnerf_cfg* cfg, int64_t n_rays) {
   return L;
 }
 
+// ---- tensor-core training chains (VIPNERF_FLAG_TRAIN_TF32): every 256-wide product is one k_linear_tf32 launch
+const float* packed_small(const void* packed) { return reinterpret_cast<const float*>(packed); }
+const float* packed_big(const void* packed) {   // forward images Wt[in][out] (layout.cuh)
+  return reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(packed) + kSmallBytes);
+}
+const float* packed_out_in(const void* packed) { return packed_big(packed) + kFp32BigFloats; }   // [out][in] images
+
+LinearTcArgs linear_args(const float* x, int ldx, int k, const float* w, int ldw, int N, int64_t P, float* out, int ld_out) {
+  LinearTcArgs a{};
+  a.x[0] = x; a.ldx[0] = ldx; a.k[0] = k; a.w[0] = w; a.ldw[0] = ldw;
+  a.N = N; a.n_rows = P; a.out = out; a.ld_out = ld_out;
+  return a;
+}
+
+// MLP.forward of one sample set on the tensor cores: encodings -> ten products -> heads; fills the saved activations
+cudaError_t mlp_forward_tc(const RayPtrs& rp, const RenderFlags& fl, int64_t n_rays, int S, const float* z,
+                           const void* packed, const MlpSave& sv, float* acc9, float* sigma, float* rgb, float* vis,
+                           float* vis2, cudaStream_t s) {
+  const int64_t P = n_rays * S;
+  const size_t PL = (size_t)P * 256;
+  const float* small = packed_small(packed);
+  const float* woi = packed_out_in(packed);
+  cudaError_t e;
+  if ((e = launch_encode_points(rp, fl, n_rays, S, z, sv.enc, sv.pev, s)) != cudaSuccess) return e;
+  for (int l = 0; l < 8; ++l) {
+    LinearTcArgs a;
+    if (l == 0) {
+      a = linear_args(sv.enc, 64, 64, woi + kBwdOffEnc0, 64, 256, P, sv.h, 256);
+    } else {
+      a = linear_args(sv.h + (l - 1) * PL, 256, 256, woi + kBwdOffTrunk + (size_t)(7 - l) * 65536, 256, 256, P, sv.h + l * PL, 256);
+      if (l == 5) {   // cat([encoding, h4]) (:543-544): a second operand pair accumulates into the same tile
+        a.x[1] = sv.enc; a.ldx[1] = 64; a.k[1] = 64; a.w[1] = woi + kBwdOffEnc5; a.ldw[1] = 64;
+      }
+    }
+    a.bias = small + kOffBias + l * 256;
+    a.relu = true;
+    if ((e = launch_linear_tc(a, s)) != cudaSuccess) return e;
+  }
+  LinearTcArgs f = linear_args(sv.h + 7 * PL, 256, 256, woi + kBwdOffFeature, 256, 256, P, sv.feat, 256);
+  f.bias = small + kOffBias + 8 * 256;
+  if ((e = launch_linear_tc(f, s)) != cudaSuccess) return e;
+  LinearTcArgs v = linear_args(sv.feat, 256, 256, woi + kBwdOffViews, 256, 128, P, acc9, 128);
+  if ((e = launch_linear_tc(v, s)) != cudaSuccess) return e;
+  return launch_heads_fwd(P, 1 + fl.n_sec_views, packed, sv.h + 7 * PL, acc9, sv.pev, sv.noise, sigma, rgb, vis, vis2, sv.hv, s);
+}
+
+// backward-data chain of one sample set on the tensor cores (same outputs as launch_mlp_bwd_fp32)
+cudaError_t mlp_backward_tc(const MlpBwdArgs& a, const void* packed, cudaStream_t s) {
+  const int64_t P = a.n_points;
+  const size_t PL = (size_t)P * 256;
+  const float* small = packed_small(packed);
+  const float* wio = packed_big(packed);
+  cudaError_t e;
+  if ((e = launch_heads_bwd(P, a.nviews, packed, a.dlogit, a.hv, a.dhv, a.dacc9, s)) != cudaSuccess) return e;
+  LinearTcArgs g = linear_args(a.dacc9, 128, 128, wio + fp32_layer_offset(9), 128, 256, P, a.dfeat, 256);
+  if ((e = launch_linear_tc(g, s)) != cudaSuccess) return e;
+  g = linear_args(a.dfeat, 256, 256, wio + fp32_layer_offset(8), 256, 256, P, a.dpre + 7 * PL, 256);
+  g.rank1_row = a.dsig; g.rank1_col = small + kOffWSigma;
+  g.mask = a.h + 7 * PL; g.ld_mask = 256;
+  if ((e = launch_linear_tc(g, s)) != cudaSuccess) return e;
+  for (int l = 7; l >= 1; --l) {
+    g = linear_args(a.dpre + l * PL, 256, 256, wio + fp32_layer_offset(l) + (l == 5 ? 64 * 256 : 0), 256, 256, P,
+                    a.dpre + (l - 1) * PL, 256);
+    g.mask = a.h + (l - 1) * PL; g.ld_mask = 256;
+    if ((e = launch_linear_tc(g, s)) != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
+
 int check_train_cfg(const vipnerf_cfg* cfg) {
   if (int rc = check_cfg(cfg)) return rc;
   if (cfg->precision != VIPNERF_PRECISION_FP32)
@@ -418,9 +487,9 @@ int vipnerf_train_forward(const vipnerf_cfg* cfg, const vipnerf_rays* rays, int6
   const bool has_fine = cfg->n_fine > 0;
   if (has_fine && !packed_fine) return fail(VIPNERF_EINVAL, "n_fine=%d but packed_fine is NULL", cfg->n_fine);
   if (misaligned(sigma_noise_coarse) || misaligned(sigma_noise_fine)) return fail(VIPNERF_EINVAL, "sigma_noise pointers must be 16-byte aligned");
-  const Workspace w = carve(cfg, n_rays);
+  const size_t ws_need = vipnerf_train_workspace_bytes(cfg, n_rays);
   const SavedLayout L = carve_saved(cfg, n_rays);
-  if (!workspace || workspace_bytes < w.total) return fail(VIPNERF_EWORKSPACE, "workspace %zu bytes < required %zu", workspace_bytes, w.total);
+  if (!workspace || workspace_bytes < ws_need) return fail(VIPNERF_EWORKSPACE, "workspace %zu bytes < required %zu", workspace_bytes, ws_need);
   if (saved_bytes < L.total) return fail(VIPNERF_EWORKSPACE, "saved buffer %zu bytes < required %zu", saved_bytes, L.total);
   if ((reinterpret_cast<uintptr_t>(workspace) & 255u) || (reinterpret_cast<uintptr_t>(saved) & 255u))
     return fail(VIPNERF_EINVAL, "workspace / saved must be 256-byte aligned");
@@ -446,9 +515,16 @@ int vipnerf_train_forward(const vipnerf_cfg* cfg, const vipnerf_rays* rays, int6
     ms.feat = reinterpret_cast<float*>(sv + sp.feat); ms.hv = reinterpret_cast<float*>(sv + sp.hv);
     ms.pev = reinterpret_cast<float*>(sv + sp.pev);
     float* vis2 = fl.n_sec_views ? o.raw_visibility2 : nullptr;
-    e = launch_mlp_fp32(rp, fl, n_rays, S, o.z_vals, pass ? packed_fine : packed_coarse, o.raw_sigma, o.raw_rgb,
-                        o.raw_visibility, vis2, s, &ms);
-    if (e != cudaSuccess) return fail_cuda(e, "mlp_fp32 (training)");
+    if (cfg->flags & VIPNERF_FLAG_TRAIN_TF32) {
+      // the feature product of the views layer lives in the backward's (idle) scratch until the heads have consumed it
+      float* acc9 = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + carve_bwd(cfg, n_rays).dacc9);
+      e = mlp_forward_tc(rp, fl, n_rays, S, o.z_vals, pass ? packed_fine : packed_coarse, ms, acc9, o.raw_sigma, o.raw_rgb,
+                         o.raw_visibility, vis2, s);
+    } else {
+      e = launch_mlp_fp32(rp, fl, n_rays, S, o.z_vals, pass ? packed_fine : packed_coarse, o.raw_sigma, o.raw_rgb,
+                          o.raw_visibility, vis2, s, &ms);
+    }
+    if (e != cudaSuccess) return fail_cuda(e, "mlp forward (training)");
     PassOutPtrs oo = o;
     oo.z_vals = nullptr;
     e = launch_composite(rp, fl, n_rays, S, o.z_vals, o.raw_sigma, o.raw_rgb, vis2, oo, cfg->n_fine,
@@ -519,7 +595,9 @@ int vipnerf_train_backward(const vipnerf_cfg* cfg, const vipnerf_rays* rays, int
     MlpBwdArgs a{};
     a.n_points = P; a.nviews = nv; a.dsig = dsig; a.dlogit = dlogit; a.h = h; a.hv = hv;
     a.dpre = dpre; a.dfeat = dfeat; a.dacc9 = dacc9; a.dhv = dhv;
-    if ((e = launch_mlp_bwd_fp32(a, pass ? packed_fine : packed_coarse, s)) != cudaSuccess) return fail_cuda(e, "mlp_bwd_fp32");
+    e = (cfg->flags & VIPNERF_FLAG_TRAIN_TF32) ? mlp_backward_tc(a, pass ? packed_fine : packed_coarse, s)
+                                               : launch_mlp_bwd_fp32(a, pass ? packed_fine : packed_coarse, s);
+    if (e != cudaSuccess) return fail_cuda(e, "mlp backward-data chain");
     // 3. parameter gradients: dW = dY^T X over all points, db = column sums of dY
     const size_t PL = (size_t)P * 256;
     const bool tf32 = (cfg->flags & VIPNERF_FLAG_TRAIN_TF32) != 0;

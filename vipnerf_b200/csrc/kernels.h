@@ -88,6 +88,32 @@ cudaError_t launch_colsum(const float* A, int lda, int M, int64_t n_rows, float*
 size_t gemm_tn_tc_partial_floats(int sms);
 cudaError_t launch_gemm_tn_tc(const float* A, int lda, int M, const float* B, int ldb, int64_t n_rows, float* dst,
                               int ldc, int n_valid, float* partial, cudaStream_t s);
+// train_kernels.cu : the non-product pieces of the tensor-core training path (encodings, heads forward / backward)
+cudaError_t launch_encode_points(const RayPtrs& rp, const RenderFlags& fl, int64_t n_rays, int S, const float* z,
+                                 float* enc, float* pev, cudaStream_t s);
+cudaError_t launch_heads_fwd(int64_t n_points, int nviews, const void* packed, const float* h7, const float* acc9,
+                             const float* pev, const float* noise, float* sigma, float* rgb, float* vis, float* vis2,
+                             float* hv, cudaStream_t s);
+cudaError_t launch_heads_bwd(int64_t n_points, int nviews, const void* packed, const float* dlogit, const float* hv,
+                             float* dhv, float* dacc9, cudaStream_t s);
+// gemm_tc.cu : one linear layer of the training chains on the tensor cores (tcgen05 kind::tf32, K-major operands):
+// out[p][n] = epilogue(sum_k x0[p][k] w0[n][k] (+ sum_k x1[p][k] w1[n][k])), epilogue = + bias[n], + rank1_row[p] *
+// rank1_col[n], ReLU, ReLU-mask (mask[p][n] > 0), each optional.  k[i] = reduction length of pair i (multiple of 32; k[1]
+// may be 0), N in {128, 256}; rows are points.
+struct LinearTcArgs {
+  const float* x[2]; int ldx[2];
+  const float* w[2]; int ldw[2];
+  int k[2];
+  int N;
+  int64_t n_rows;
+  const float* bias;
+  const float* rank1_row;
+  const float* rank1_col;
+  const float* mask; int ld_mask;
+  bool relu;
+  float* out; int ld_out;
+};
+cudaError_t launch_linear_tc(const LinearTcArgs& a, cudaStream_t s);
 // out[m][n] = sum_p G[p][m] * H[p][n] for M <= 4 (G: M floats per row), N <= 256; gsum_dst[m] = sum_p G[p][m].
 cudaError_t launch_small_tn(const float* G, int M, const float* H, int N, int64_t n_rows, float* dst, float* gsum_dst,
                             float* partial, cudaStream_t s);

@@ -61,7 +61,10 @@ constexpr int kFp32BigFloats = fp32_layer_offset(kNumMatLayers);  // 589,824
 constexpr int kBwdOffViews = 0;
 constexpr int kBwdOffFeature = kBwdOffViews + 128 * 256;
 constexpr int kBwdOffTrunk = kBwdOffFeature + 256 * 256;
-constexpr int kFp32BwdFloats = kBwdOffTrunk + 7 * 256 * 256;      // 557,056
+constexpr int kBwdOffEnc0 = kBwdOffTrunk + 7 * 256 * 256;         // pts_linears.0 padded to [256][64] (column 63 = 0)
+constexpr int kBwdOffEnc5 = kBwdOffEnc0 + 256 * 64;               // pts_linears.5[:, :63] padded to [256][64]
+constexpr int kFp32BwdFloats = kBwdOffEnc5 + 256 * 64;            // 589,824; the two encoding blocks serve the
+                                                                  // tensor-core forward, whose B operands are [out][in]
 
 // ---- tensor-core big region: "chunk images".  One chunk = ALL output rows (n) of a layer x 32 k-columns of
 // bf16 in the canonical K-major SWIZZLE_64B shared-memory layout tcgen05.mma reads (64-byte rows, 8-row / 512-byte

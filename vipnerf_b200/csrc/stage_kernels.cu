@@ -60,10 +60,16 @@ __global__ void k_pack_fp32_bwd(ParamPtrs pp, float* __restrict__ bwd) {
     v = pp.p[16][o * (kWidth + kEncView) + c];
   } else if (i < kBwdOffTrunk) {
     v = pp.p[20][i - kBwdOffFeature];
-  } else {
+  } else if (i < kBwdOffEnc0) {
     const int e = i - kBwdOffTrunk;
     const int l = 7 - e / 65536, o = (e % 65536) / 256, c = e % 256;
     v = l == 5 ? pp.p[10][o * (kWidth + kEncPts) + kEncPts + c] : pp.p[2 * l][o * 256 + c];
+  } else if (i < kBwdOffEnc5) {
+    const int o = (i - kBwdOffEnc0) / 64, c = (i - kBwdOffEnc0) % 64;
+    v = c < kEncPts ? pp.p[0][o * kEncPts + c] : 0.f;
+  } else {
+    const int o = (i - kBwdOffEnc5) / 64, c = (i - kBwdOffEnc5) % 64;
+    v = c < kEncPts ? pp.p[10][o * (kWidth + kEncPts) + c] : 0.f;
   }
   bwd[i] = v;
 }

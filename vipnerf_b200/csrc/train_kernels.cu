@@ -381,7 +381,181 @@ k_small_tn(const float* __restrict__ G, const float* __restrict__ H, int N, int6
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Tensor-core training path (VIPNERF_FLAG_TRAIN_TF32): the pieces of the MLP that are not matrix products.
+//
+// k_encode_points: sample points o + d z and their 63-d encoding (column 63 = 0), plus the 27-d view-direction encoding
+// of the primary view and of every secondary view (compute_other_view_dirs, VipNeRF01.py:218-226).  One thread per point.
+__global__ void __launch_bounds__(128)
+k_encode_points(RayPtrs rp, RenderFlags fl, int64_t n_points, int S, const float* __restrict__ z,
+                float* __restrict__ enc, float* __restrict__ pev) {
+  const int64_t pg = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pg >= n_points) return;
+  const int64_t ray = pg / S;
+  const int nviews = 1 + fl.n_sec_views;
+  const float zz = z[pg];
+  float* e = enc + pg * 64;
+#pragma unroll
+  for (int axis = 0; axis < 3; ++axis) {
+    const float x = fadd(rp.pts_o[3 * ray + axis], fmul(rp.pts_d[3 * ray + axis], zz));   // :105-107
+    encode_axis<kLPts>(x, axis, [&](int col, float v) { e[col] = v; });
+  }
+  e[63] = 0.f;
+  for (int v = 0; v < nviews; ++v) {
+    float dir[3];
+    if (v == 0) {
+      dir[0] = rp.view_dirs[3 * ray]; dir[1] = rp.view_dirs[3 * ray + 1]; dir[2] = rp.view_dirs[3 * ray + 2];
+    } else {
+      const float o3[3] = {rp.rays_o[3 * ray], rp.rays_o[3 * ray + 1], rp.rays_o[3 * ray + 2]};
+      const float d3[3] = {rp.rays_d[3 * ray], rp.rays_d[3 * ray + 1], rp.rays_d[3 * ray + 2]};
+      const float* c2 = rp.rays_o2 + (ray * fl.n_sec_views + (v - 1)) * 3;
+      const float o2[3] = {c2[0], c2[1], c2[2]};
+      const float zw = fl.ndc ? depth_from_ndc_secondary(zz, o3[2], d3[2]) : zz;
+      secondary_view_dir(o3, d3, zw, o2, dir);
+    }
+    float* pe = pev + (pg * nviews + v) * 32;
+#pragma unroll
+    for (int axis = 0; axis < 3; ++axis) encode_axis<kLView>(dir[axis], axis, [&](int col, float val) { pe[col] = val; });
+#pragma unroll
+    for (int c = kEncView; c < 32; ++c) pe[c] = 0.f;
+  }
+}
+
+// k_heads_fwd: everything behind the products - density head (+ noise, ReLU; VipNeRF01.py:546-553) from h7 and, per
+// view, views_linears.0's direction columns + bias on top of the feature product (acc9), ReLU, views_output_linear and
+// the sigmoids (:576-594).  One thread per point; the 16 KiB of head weights sit in shared memory (every lane reads the
+// same word: broadcasts).  Stores the views layer's output per view for the backward.
+__global__ void __launch_bounds__(128)
+k_heads_fwd(int64_t n_points, int nviews, const float* __restrict__ small, const float* __restrict__ h7,
+            const float* __restrict__ acc9, const float* __restrict__ pev, const float* __restrict__ noise,
+            float* __restrict__ out_sigma, float* __restrict__ out_rgb, float* __restrict__ out_vis,
+            float* __restrict__ out_vis2, float* __restrict__ hv) {
+  __shared__ __align__(16) float s_wvd[kEncView * 128];
+  __shared__ __align__(16) float s_wout[128 * 4];
+  __shared__ float s_bv[128];
+  __shared__ float s_ws[256];
+  for (int i = threadIdx.x; i < kEncView * 128; i += blockDim.x) s_wvd[i] = small[kOffWViewDir + i];
+  for (int i = threadIdx.x; i < 512; i += blockDim.x) s_wout[i] = small[kOffWOut + i];
+  for (int i = threadIdx.x; i < 128; i += blockDim.x) s_bv[i] = small[kOffBiasViews + i];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_ws[i] = small[kOffWSigma + i];
+  __syncthreads();
+  const int64_t pg = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pg >= n_points) return;
+  {
+    const float4* h = reinterpret_cast<const float4*>(h7 + pg * 256);
+    float s = 0.f;
+#pragma unroll 8
+    for (int i = 0; i < 64; ++i) {
+      const float4 a = h[i];
+      s = fmaf(a.x, s_ws[4 * i], s); s = fmaf(a.y, s_ws[4 * i + 1], s); s = fmaf(a.z, s_ws[4 * i + 2], s); s = fmaf(a.w, s_ws[4 * i + 3], s);
+    }
+    float pre = s + small[kOffBSigma];
+    if (noise != nullptr) pre = pre + noise[pg];
+    out_sigma[pg] = fmaxf(pre, 0.f);
+  }
+  const float4* a9 = reinterpret_cast<const float4*>(acc9 + pg * 128);
+  const float bo[4] = {small[kOffBOut], small[kOffBOut + 1], small[kOffBOut + 2], small[kOffBOut + 3]};
+  for (int v = 0; v < nviews; ++v) {
+    float pe[kEncView];
+    const float* pp = pev + (pg * nviews + v) * 32;
+#pragma unroll
+    for (int e = 0; e < kEncView; ++e) pe[e] = pp[e];
+    float o[4] = {0.f, 0.f, 0.f, 0.f};
+    float4* hv_row = reinterpret_cast<float4*>(hv + (pg * nviews + v) * 128);
+    for (int n4 = 0; n4 < 32; ++n4) {
+      const float4 a = a9[n4];
+      float pre[4] = {a.x + s_bv[4 * n4], a.y + s_bv[4 * n4 + 1], a.z + s_bv[4 * n4 + 2], a.w + s_bv[4 * n4 + 3]};
+#pragma unroll
+      for (int e = 0; e < kEncView; ++e) {
+        const float4 w = *reinterpret_cast<const float4*>(s_wvd + e * 128 + 4 * n4);
+        pre[0] = fmaf(pe[e], w.x, pre[0]); pre[1] = fmaf(pe[e], w.y, pre[1]);
+        pre[2] = fmaf(pe[e], w.z, pre[2]); pre[3] = fmaf(pe[e], w.w, pre[3]);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        pre[q] = fmaxf(pre[q], 0.f);
+        const float4 wo = *reinterpret_cast<const float4*>(s_wout + (4 * n4 + q) * 4);
+        o[0] = fmaf(pre[q], wo.x, o[0]); o[1] = fmaf(pre[q], wo.y, o[1]);
+        o[2] = fmaf(pre[q], wo.z, o[2]); o[3] = fmaf(pre[q], wo.w, o[3]);
+      }
+      hv_row[n4] = make_float4(pre[0], pre[1], pre[2], pre[3]);
+    }
+    if (v == 0) {
+      out_rgb[3 * pg + 0] = 1.f / (1.f + expf(-(o[0] + bo[0])));
+      out_rgb[3 * pg + 1] = 1.f / (1.f + expf(-(o[1] + bo[1])));
+      out_rgb[3 * pg + 2] = 1.f / (1.f + expf(-(o[2] + bo[2])));
+      out_vis[pg] = 1.f / (1.f + expf(-(o[3] + bo[3])));
+    } else {
+      out_vis2[pg * (nviews - 1) + (v - 1)] = 1.f / (1.f + expf(-(o[3] + bo[3])));
+    }
+  }
+}
+
+// k_heads_bwd: the head part of the backward (the first phase of k_mlp_bwd_fp32 as a kernel of its own): per view
+// g_pre[p][view][n] = relu'(hv) * sum_k dlogit[p][view][k] * W_out[k][n]; their sum over views is the gradient of the
+// feature product.  64 points per block, thread = hidden unit n.
+__global__ void __launch_bounds__(128)
+k_heads_bwd(int64_t n_points, int nviews, const float* __restrict__ small, const float* __restrict__ dlogit,
+            const float* __restrict__ hv, float* __restrict__ dhv, float* __restrict__ dacc9) {
+  extern __shared__ __align__(16) float dl_s[];   // [64][nviews][4]
+  const int64_t p0 = (int64_t)blockIdx.x * 64;
+  const int n = threadIdx.x;
+  for (int t = threadIdx.x; t < 64 * nviews * 4; t += blockDim.x) {
+    const int64_t e = p0 * nviews * 4 + t;
+    dl_s[t] = e < n_points * nviews * 4 ? dlogit[e] : 0.f;
+  }
+  __syncthreads();
+  const float4 wo = *reinterpret_cast<const float4*>(small + kOffWOut + n * 4);
+  const int n_valid = (int)min((int64_t)64, n_points - p0);
+  float accp[64];
+#pragma unroll
+  for (int p = 0; p < 64; ++p) accp[p] = 0.f;
+  for (int v = 0; v < nviews; ++v) {
+    float hvv[64];
+#pragma unroll
+    for (int p = 0; p < 64; ++p) hvv[p] = hv[((p0 + min(p, n_valid - 1)) * nviews + v) * 128 + n];
+#pragma unroll
+    for (int p = 0; p < 64; ++p) {
+      const float4 d4 = *reinterpret_cast<const float4*>(dl_s + (p * nviews + v) * 4);
+      const float gsum = fmaf(d4.x, wo.x, fmaf(d4.y, wo.y, fmaf(d4.z, wo.z, d4.w * wo.w)));
+      hvv[p] = hvv[p] > 0.f ? gsum : 0.f;
+      accp[p] += hvv[p];
+    }
+#pragma unroll
+    for (int p = 0; p < 64; ++p)
+      if (p < n_valid) dhv[((p0 + p) * nviews + v) * 128 + n] = hvv[p];
+  }
+#pragma unroll
+  for (int p = 0; p < 64; ++p)
+    if (p < n_valid) dacc9[(p0 + p) * 128 + n] = accp[p];
+}
+
 }  // namespace
+
+cudaError_t launch_encode_points(const RayPtrs& rp, const RenderFlags& fl, int64_t n_rays, int S, const float* z,
+                                 float* enc, float* pev, cudaStream_t s) {
+  const int64_t P = n_rays * S;
+  if (P == 0) return cudaSuccess;
+  k_encode_points<<<(unsigned)((P + 127) / 128), 128, 0, s>>>(rp, fl, P, S, z, enc, pev);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_heads_fwd(int64_t n_points, int nviews, const void* packed, const float* h7, const float* acc9,
+                             const float* pev, const float* noise, float* sigma, float* rgb, float* vis, float* vis2,
+                             float* hv, cudaStream_t s) {
+  if (n_points == 0) return cudaSuccess;
+  k_heads_fwd<<<(unsigned)((n_points + 127) / 128), 128, 0, s>>>(n_points, nviews, reinterpret_cast<const float*>(packed), h7,
+                                                                 acc9, pev, noise, sigma, rgb, vis, vis2, hv);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_heads_bwd(int64_t n_points, int nviews, const void* packed, const float* dlogit, const float* hv,
+                             float* dhv, float* dacc9, cudaStream_t s) {
+  if (n_points == 0) return cudaSuccess;
+  k_heads_bwd<<<(unsigned)((n_points + 63) / 64), 128, 64 * nviews * 4 * sizeof(float), s>>>(
+      n_points, nviews, reinterpret_cast<const float*>(packed), dlogit, hv, dhv, dacc9);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_composite_bwd(const RayPtrs& rp, const RenderFlags& fl, int64_t n_rays, int S, const float* z,
                                  const float* sigma, const float* rgb, const float* vis, const float* vis2,

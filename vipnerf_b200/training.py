@@ -66,7 +66,8 @@ class _RenderTrain(torch.autograd.Function):
         has_fine = spec['has_fine']
         n_coarse, n_fine, V = spec['n_coarse'], spec['n_fine'] if has_fine else 0, spec['n_sec_views']
         cfg = _lib.make_cfg(n_coarse=n_coarse, n_fine=n_fine, n_sec_views=V, ndc=spec['ndc'],
-                            white_bkgd=spec['white_bkgd'], lindisp=spec['lindisp'], precision='fp32')
+                            white_bkgd=spec['white_bkgd'], lindisp=spec['lindisp'], precision='fp32',
+                            train_tf32=spec['tf32'])
         names = renderpath.MLP_PARAM_ORDER
         packed_c = renderpath.pack_mlp(dict(zip(names, [p.detach() for p in params[:24]])), 'fp32')
         packed_f = renderpath.pack_mlp(dict(zip(names, [p.detach() for p in params[24:48]])), 'fp32') if has_fine else None
@@ -118,7 +119,7 @@ class _RenderTrain(torch.autograd.Function):
         R = outputs[0].shape[0]
         cfg = _lib.make_cfg(n_coarse=n_coarse, n_fine=n_fine, n_sec_views=V, ndc=spec['ndc'],
                             white_bkgd=spec['white_bkgd'], lindisp=spec['lindisp'], precision='fp32',
-                            train_tf32=spec['tf32_gradients'])
+                            train_tf32=spec['tf32'])
         keep: list = []
         rays = renderpath._make_rays(spec['batch'], spec['ndc'], n_coarse, n_fine, V, keep)
         fwd, gout = _lib.Out(), _lib.Out()
@@ -146,19 +147,20 @@ class _RenderTrain(torch.autograd.Function):
 def render_rays_train(batch: Dict[str, torch.Tensor], params_coarse: Dict[str, torch.Tensor],
                       params_fine: Optional[Dict[str, torch.Tensor]], *, ndc: bool, n_coarse: int = 64,
                       n_fine: int = 128, n_sec_views: int = 0, white_bkgd: bool = False,
-                      lindisp: bool = False, tf32_gradients: bool = False) -> Dict[str, torch.Tensor]:
+                      lindisp: bool = False, tf32: bool = False) -> Dict[str, torch.Tensor]:
     """Train-mode VipNeRF.render_rays (VipNeRF01.py:74-171 with self.training: retraw and sec_views_vis on, :40),
     differentiable w.r.t. the MLP parameters.  `batch` holds the ray tensors plus the random draws (`t_rand`, `u_rand`,
     `sigma_noise_coarse`, `sigma_noise_fine`; see draw_training_randoms) - a missing draw switches that source off.
     `params_*`: the reference's state_dict names of one MLP -> parameter tensors (CUDA, fp32).
-    `tf32_gradients`: the 256-wide parameter-gradient products of the backward run on the tensor cores (tcgen05 tf32)."""
+    `tf32`: every 256-wide product of the step (forward chain, backward-data chain, parameter gradients) runs on the
+    tensor cores (tcgen05 kind::tf32: operands rounded to tf32, fp32 accumulation) instead of fp32 CUDA cores."""
     renderpath._require_cuda(batch['rays_o'], 'rays_o')
     has_fine = params_fine is not None and n_fine > 0
     names = renderpath.MLP_PARAM_ORDER
     keys = renderpath.pass_keys(ndc, True, n_sec_views)
     out_names = [f'{k}_coarse' for k in keys] + ([f'{k}_fine' for k in keys] if has_fine else [])
     spec = dict(batch=batch, ndc=ndc, n_coarse=n_coarse, n_fine=n_fine, n_sec_views=n_sec_views, white_bkgd=white_bkgd,
-                lindisp=lindisp, has_fine=has_fine, out_names=out_names, tf32_gradients=bool(tf32_gradients))
+                lindisp=lindisp, has_fine=has_fine, out_names=out_names, tf32=bool(tf32))
     params = [params_coarse[k] for k in names] + ([params_fine[k] for k in names] if has_fine else [])
     outputs = _RenderTrain.apply(spec, *params)
     result = dict(zip(out_names, outputs))
