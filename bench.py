@@ -345,7 +345,7 @@ def run_train(args, rank, world, local_rank):
         line = {'metric': 'training rays/s (forward + 4 losses + backward + Adam), 64+128 samples', 'value': value,
                 'unit': 'rays/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
                 'ms_per_step': total_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-                'dtype': 'f32' if args.train_precision == 'fp32' else 'f32 (tf32 parameter-gradient products)', 'data': 'synthetic',
+                'dtype': 'f32' if args.train_precision == 'fp32' else 'tf32', 'data': 'synthetic',
                 'config': {'workload': 'RealEstate-10K camera, 2 input views (1 secondary view), full ViP-NeRF visibility + '
                                        'sparse-depth losses, one training iteration per step',
                            'rays_per_step_per_gpu': R, 'samples': '64+128', 'ndc': True,
@@ -353,7 +353,9 @@ def run_train(args, rank, world, local_rank):
                                               if args.rng == 'reference' else ' (torch CUDA generator, same distributions)'),
                            'train_precision': args.train_precision,
                            'kernels': 'fp32 CUDA-core training path (k_mlp_fp32<save>, k_composite_bwd, k_mlp_bwd_fp32, k_gemm_tn)'
-                                      + ('; 256-wide parameter-gradient products on tcgen05 (k_gemm_tn_tf32)' if args.train_precision == 'tf32' else ''),
+                                      if args.train_precision == 'fp32' else
+                                      'tensor-core training path: k_linear_tf32 (forward and backward-data chains) + k_gemm_tn_tf32 '
+                                      '(parameter gradients) on tcgen05 kind::tf32; encodings, heads, compositing and its backward fp32',
                            'l2': 'working set (about 22 KB per sample point, > 20 GB per step) exceeds L2 by construction',
                            'final_loss': loss_value},
                 'clocks': clocks,
@@ -402,7 +404,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--workload', default='batch', choices=['batch', 'frame', 'train'])
     ap.add_argument('--train-precision', default='fp32', choices=['fp32', 'tf32'],
-                    help='train workload: tf32 = parameter-gradient products on the tensor cores (tcgen05)')
+                    help='train workload: tf32 = every 256-wide product of the step on the tensor cores (tcgen05 kind::tf32)')
     ap.add_argument('--rng', default='reference', choices=['reference', 'device'],
                     help='train workload: where the stratified jitter / cdf samples / density noise are drawn')
     ap.add_argument('--scene', default='fern', choices=['fern', 'dtu'], help='camera of the frame workload')

@@ -190,19 +190,20 @@ def test_training_gradients_vs_oracle_autograd(scene, n_rays, n_sec, train_preci
     torch.manual_seed(5)
     draws = O.draw_training_randoms(n_rays, 64, 128, 128, 5000, True, 1.0)
     ref_out, ref_total, ref_grads = _oracle_step(O.synth_state_dict(0), rays, sup, draws, ndc, chunk=128, netchunk=5000)
-    # tf32 mode: every product of the step sees operands rounded to 10 mantissa bits (PyTorch's allow_tf32 arithmetic);
-    # the forward moves by ~1e-3 and ReLU decisions of near-zero units flip, so the gates are statistical there
+    # tf32 mode: every 256-wide product of the step sees operands rounded to 10 mantissa bits (PyTorch's allow_tf32
+    # arithmetic), fp32 accumulation; heads, compositing and sampling stay fp32
     tf32 = train_precision == 'tf32'
-    assert abs(total.item() - ref_total.item()) <= (2e-2 if tf32 else 2e-4) * abs(ref_total.item())
+    assert abs(total.item() - ref_total.item()) <= (2e-3 if tf32 else 2e-4) * abs(ref_total.item())
     for k in ('rgb_coarse', 'rgb_fine', 'visibility2_coarse', 'visibility2_fine', 'depth_coarse', 'raw_sigma_coarse',
               'raw_rgb_coarse', 'raw_visibility_coarse'):
         mx, med = H.rel_err(out[k], ref_out[k])
         print(f'{scene} {train_precision} {k}: max {mx:.2e} median {med:.2e}')
-        if tf32:
-            assert med <= 2e-3 and mx <= 0.2, (k, mx, med)
+        if tf32:   # measured: composited maps 1e-5, density logits 7e-4 (max), everything else 7e-6
+            assert mx <= (5e-3 if k.startswith('raw_sigma') else 5e-4) and med <= 5e-4, (k, mx, med)
         else:
             assert mx <= 1e-4, (k, mx)
-    worst = _compare_full_grads(model, ref_grads, max_tol=0.5 if tf32 else GRAD_MAX_TOL, norm_tol=0.2 if tf32 else 5 * GRAD_NORM_TOL)
+    # measured in tf32 mode: worst entry 3e-3 .. 6e-3 of the tensor's max, L2 error 5e-3 .. 6e-3
+    worst = _compare_full_grads(model, ref_grads, max_tol=3e-2 if tf32 else GRAD_MAX_TOL, norm_tol=3e-2 if tf32 else 5 * GRAD_NORM_TOL)
     print(f'{scene} {train_precision}: worst gradient error {worst[0]:.2e} ({worst[1]}), worst L2 error {worst[2]:.2e}')
 
 
