@@ -19,10 +19,12 @@ ap = argparse.ArgumentParser()
 ap.add_argument('--rays', type=int, default=4096)
 ap.add_argument('--steps', type=int, default=4)
 ap.add_argument('--rng', default='reference')
+ap.add_argument('--train-precision', default='fp32')
 args = ap.parse_args()
 
 cfg = bench.model_configs('bf16', ndc=True)
 cfg['model']['rng'] = args.rng
+cfg['model']['train_precision'] = args.train_precision
 model = get_model(cfg, None)
 model.load_state_dict(O.synth_state_dict(0))
 model = model.cuda().train()

@@ -250,10 +250,11 @@ cudaError_t encode_rows_map(CUtensorMap* map, const float* base, int ld, int col
 // ring, one thread issues four K=8 MMAs per box pair (M=128 points, N columns, accumulators in N TMEM columns), and
 // four epilogue warps drain TMEM row by row: + bias, + a rank-1 term (the density head's contribution to dL/dh8),
 // ReLU, ReLU-mask from a saved activation, 128-byte stores.  Up to two (X, W) pairs accumulate into the same tile
-// (the skip layer's cat([encoding, h4]) input).  One 128-point tile per CTA, two CTAs per SM (96 KiB of shared
-// memory and 256 TMEM columns each), so one CTA's epilogue overlaps the other's MMAs.
+// (the skip layer's cat([encoding, h4]) input).  Persistent, one CTA per SM: a 4-stage ring (192 KiB) keeps loads in
+// flight across tile boundaries and the two 256-column TMEM accumulators alternate, so the epilogue of one 128-point
+// tile overlaps the loads and MMAs of the next.
 // Roofline: HBM - K*4 bytes read and N*4 written (+ N*4 for a mask) per point; the weights come from L2.
-constexpr int kLinStages = 2;
+constexpr int kLinStages = 4;
 constexpr int kLinRows = 128;
 
 struct LinearTcParams {
@@ -279,28 +280,33 @@ constexpr uint32_t instr_desc_tf32_k(uint32_t n, uint32_t m) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
 }
 
-__global__ void __launch_bounds__(kTcThreads, 2) k_linear_tf32(const __grid_constant__ LinearTcParams p) {
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1) k_linear_tf32(const __grid_constant__ LinearTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t a_bytes = kLinRows * 128, b_bytes = (uint32_t)p.N * 128;
   const uint32_t stage_bytes = a_bytes + b_bytes;
   uint8_t* tail = smem + kLinStages * stage_bytes;
-  uint32_t* tmem_ptr_slot = reinterpret_cast<uint32_t*>(tail + 8 * (2 * kLinStages + 1));
+  uint32_t* tmem_ptr_slot = reinterpret_cast<uint32_t*>(tail + 8 * (2 * kLinStages + 4));
   const uint32_t bar0 = smem_u32(tail);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (kLinStages + s); };
-  const uint32_t done_bar = bar0 + 8u * (2 * kLinStages);
-  const int n_steps = p.chunks[0] + p.chunks[1];
-  const int row0 = (int)((int64_t)blockIdx.x * kLinRows);
+  auto acc_full = [&](int b) { return bar0 + 8u * (2 * kLinStages + b); };
+  auto acc_empty = [&](int b) { return bar0 + 8u * (2 * kLinStages + 2 + b); };
+  const int n_chunks = p.chunks[0] + p.chunks[1];
+  const int n_tiles = (int)((p.n_rows + kLinRows - 1) / kLinRows);
 
   if (threadIdx.x == 0) {
     if ((smem_u32(smem) & 1023u) != 0) { printf("vipnerf linear_tc: shared memory base not 1 KiB aligned\n"); __trap(); }
     for (int s = 0; s < kLinStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    mbar_init(done_bar, 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(acc_full(b), 1); mbar_init(acc_empty(b), 4); }   // one arrival per epilogue warp
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_slot)), "r"(p.N) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_slot)), "r"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -308,75 +314,97 @@ __global__ void __launch_bounds__(kTcThreads, 2) k_linear_tf32(const __grid_cons
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_ptr_slot);
 
+  // Persistent: CTA b owns tiles b, b + gridDim.x, ...  The ring runs continuously across tiles (step counter g); the
+  // two TMEM accumulators alternate, so the epilogue of tile i overlaps the loads and MMAs of tile i + 1.
   if (warp == 0) {
     if (lane == 0) {
-      for (int s = 0; s < n_steps; ++s) {
-        const int st = s % kLinStages;
-        if (s >= kLinStages) mbar_wait(empty_bar(st), ((s / kLinStages) - 1) & 1);
-        mbar_expect_tx(full_bar(st), stage_bytes);
-        const uint32_t dst = smem_u32(smem) + (uint32_t)st * stage_bytes;
-        const int pair = s < p.chunks[0] ? 0 : 1;
-        const int kc = (pair ? s - p.chunks[0] : s) * 32;
-        tma_load_2d(dst, &p.map_a[pair], kc, row0, full_bar(st));           // rows past the end are zero-filled
-        tma_load_2d(dst + a_bytes, &p.map_b[pair], kc, 0, full_bar(st));
+      int g = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int row0 = tile * kLinRows;
+        for (int c = 0; c < n_chunks; ++c, ++g) {
+          const int st = g % kLinStages;
+          if (g >= kLinStages) mbar_wait(empty_bar(st), ((g / kLinStages) - 1) & 1);
+          mbar_expect_tx(full_bar(st), stage_bytes);
+          const uint32_t dst = smem_u32(smem) + (uint32_t)st * stage_bytes;
+          const int pair = c < p.chunks[0] ? 0 : 1;
+          const int kc = (pair ? c - p.chunks[0] : c) * 32;
+          tma_load_2d(dst, &p.map_a[pair], kc, row0, full_bar(st));           // rows past the end are zero-filled
+          tma_load_2d(dst + a_bytes, &p.map_b[pair], kc, 0, full_bar(st));
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc = instr_desc_tf32_k((uint32_t)p.N, 128);
-      for (int s = 0; s < n_steps; ++s) {
-        const int st = s % kLinStages;
-        mbar_wait(full_bar(st), (s / kLinStages) & 1);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t a0 = smem_u32(smem) + (uint32_t)st * stage_bytes;
-        const uint32_t b0 = a0 + a_bytes;
+      int g = 0, i = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++i) {
+        const int buf = i & 1;
+        if (i >= 2) {   // the epilogue has drained this accumulator's previous tile
+          mbar_wait(acc_empty(buf), ((i >> 1) - 1) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
+        for (int c = 0; c < n_chunks; ++c, ++g) {
+          const int st = g % kLinStages;
+          mbar_wait(full_bar(st), (g / kLinStages) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t a0 = smem_u32(smem) + (uint32_t)st * stage_bytes;
+          const uint32_t b0 = a0 + a_bytes;
 #pragma unroll
-        for (int k = 0; k < 4; ++k)   // K = 8 fp32 = 32 bytes along the 128-byte swizzled rows
-          umma_tf32(tmem_base, make_desc_k(a0 + k * 32), make_desc_k(b0 + k * 32), idesc, (s > 0 || k > 0) ? 1u : 0u);
-        umma_commit(empty_bar(st));
+          for (int k = 0; k < 4; ++k)   // K = 8 fp32 = 32 bytes along the 128-byte swizzled rows
+            umma_tf32(tmem_base + buf * 256, make_desc_k(a0 + k * 32), make_desc_k(b0 + k * 32), idesc, (c > 0 || k > 0) ? 1u : 0u);
+          umma_commit(empty_bar(st));
+        }
+        umma_commit(acc_full(buf));
       }
-      umma_commit(done_bar);
     }
   } else {
     const int quarter = warp & 3;
-    const int64_t pg = (int64_t)row0 + quarter * 32 + lane;
-    const bool valid = pg < p.n_rows;
-    mbar_wait(done_bar, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const float r1 = (p.rank1_row != nullptr && valid) ? p.rank1_row[pg] : 0.f;
-    for (int c = 0; c < p.N / 32; ++c) {
-      uint32_t v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + c * 32, v);
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (!valid) continue;
-      float4* dst = reinterpret_cast<float4*>(p.out + pg * p.ld_out + c * 32);
-      const float4* msk = p.mask ? reinterpret_cast<const float4*>(p.mask + pg * p.ld_mask + c * 32) : nullptr;
+    int i = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++i) {
+      const int buf = i & 1;
+      const int64_t pg = (int64_t)tile * kLinRows + quarter * 32 + lane;
+      const bool valid = pg < p.n_rows;
+      mbar_wait(acc_full(buf), (i >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const float r1 = (p.rank1_row != nullptr && valid) ? p.rank1_row[pg] : 0.f;
+      for (int c = 0; c < p.N / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * 256 + c * 32, v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (!valid) continue;
+        float4* dst = reinterpret_cast<float4*>(p.out + pg * p.ld_out + c * 32);
+        const float4* msk = p.mask ? reinterpret_cast<const float4*>(p.mask + pg * p.ld_mask + c * 32) : nullptr;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float4 o = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
-                               __uint_as_float(v[4 * i + 3]));
-        if (p.bias != nullptr) {
-          const float4 b = *reinterpret_cast<const float4*>(p.bias + c * 32 + 4 * i);
-          o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+        for (int q = 0; q < 8; ++q) {
+          float4 o = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
+                                 __uint_as_float(v[4 * q + 3]));
+          if (p.bias != nullptr) {
+            const float4 b = *reinterpret_cast<const float4*>(p.bias + c * 32 + 4 * q);
+            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+          }
+          if (p.rank1_row != nullptr) {
+            const float4 u = *reinterpret_cast<const float4*>(p.rank1_col + c * 32 + 4 * q);
+            o.x = fmaf(r1, u.x, o.x); o.y = fmaf(r1, u.y, o.y); o.z = fmaf(r1, u.z, o.z); o.w = fmaf(r1, u.w, o.w);
+          }
+          if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+          if (msk != nullptr) {
+            const float4 m = msk[q];
+            o.x = m.x > 0.f ? o.x : 0.f; o.y = m.y > 0.f ? o.y : 0.f; o.z = m.z > 0.f ? o.z : 0.f; o.w = m.w > 0.f ? o.w : 0.f;
+          }
+          dst[q] = o;
         }
-        if (p.rank1_row != nullptr) {
-          const float4 u = *reinterpret_cast<const float4*>(p.rank1_col + c * 32 + 4 * i);
-          o.x = fmaf(r1, u.x, o.x); o.y = fmaf(r1, u.y, o.y); o.z = fmaf(r1, u.z, o.z); o.w = fmaf(r1, u.w, o.w);
-        }
-        if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-        if (msk != nullptr) {
-          const float4 m = msk[i];
-          o.x = m.x > 0.f ? o.x : 0.f; o.y = m.y > 0.f ? o.y : 0.f; o.z = m.z > 0.f ? o.z : 0.f; o.w = m.w > 0.f ? o.w : 0.f;
-        }
-        dst[i] = o;
       }
+      // this warp's TMEM reads of the accumulator are complete: hand it back to the MMA warp
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty(buf));
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.N) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
 }
 
@@ -414,8 +442,11 @@ cudaError_t launch_linear_tc(const LinearTcArgs& a, cudaStream_t s) {
   p.mask = a.mask; p.ld_mask = a.ld_mask; p.relu = a.relu ? 1 : 0; p.out = a.out; p.ld_out = a.ld_out;
   const size_t smem = (size_t)kLinStages * (kLinRows * 128 + a.N * 128) + 128;
   if ((e = cudaFuncSetAttribute(k_linear_tf32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(k_linear_tf32, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)) != cudaSuccess) return e;
-  k_linear_tf32<<<(unsigned)((a.n_rows + kLinRows - 1) / kLinRows), kTcThreads, smem, s>>>(p);
+  int dev = 0, sms = 0;
+  if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+  if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+  const int64_t n_tiles = (a.n_rows + kLinRows - 1) / kLinRows;
+  k_linear_tf32<<<(unsigned)(n_tiles < sms ? n_tiles : sms), kTcThreads, smem, s>>>(p);
   return cudaGetLastError();
 }
 

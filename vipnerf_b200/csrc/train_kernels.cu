@@ -352,7 +352,17 @@ __global__ void k_reduce_partials(const float* __restrict__ partial, int n_split
   if (i >= M * n_valid) return;
   const int m = i / n_valid, n = i % n_valid;
   float s = 0.f;
-  for (int k = 0; k < n_split; ++k) s += partial[((size_t)k * M + m) * N + n];
+  const size_t stride = (size_t)M * N;
+  const float* src = partial + (size_t)m * N + n;
+  int k = 0;
+  for (; k + 8 <= n_split; k += 8) {   // eight independent loads in flight, summed in index order
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = src[(size_t)(k + u) * stride];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) s += v[u];
+  }
+  for (; k < n_split; ++k) s += src[(size_t)k * stride];
   dst[(size_t)m * ldc + n] = s;
 }
 
