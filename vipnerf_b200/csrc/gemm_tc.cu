@@ -248,8 +248,8 @@ cudaError_t encode_rows_map(CUtensorMap* map, const float* base, int ld, int col
 // weight matrix (nn.Linear's own orientation for the forward, the transposed image for the backward-data chain).
 // The TMA engine loads [128 points x 32 k] and [N x 32 k] boxes (plain 128-byte swizzle, tf32 rounding) into a 2-stage
 // ring, one thread issues four K=8 MMAs per box pair (M=128 points, N columns, accumulators in N TMEM columns), and
-// four epilogue warps drain TMEM, transpose 32 x 32 chunks through shared memory and apply + bias, + a rank-1 term
-// (the density head's contribution to dL/dh8), ReLU, ReLU-mask from a saved activation on fully coalesced rows.  Up to two (X, W) pairs accumulate into the same tile
+// four epilogue warps drain TMEM row by row: + bias, + a rank-1 term (the density head's contribution to dL/dh8),
+// ReLU, ReLU-mask from a saved activation, 128-byte stores.  Up to two (X, W) pairs accumulate into the same tile
 // (the skip layer's cat([encoding, h4]) input).  Persistent, one CTA per SM: a 4-stage ring (192 KiB) keeps loads in
 // flight across tile boundaries and the two 256-column TMEM accumulators alternate, so the epilogue of one 128-point
 // tile overlaps the loads and MMAs of the next.
@@ -362,48 +362,37 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_linear_tf32(const __grid_cons
     int i = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++i) {
       const int buf = i & 1;
+      const int64_t pg = (int64_t)tile * kLinRows + quarter * 32 + lane;
+      const bool valid = pg < p.n_rows;
       mbar_wait(acc_full(buf), (i >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      // Each lane owns one accumulator row, but a row-per-lane store would touch 32 different 128-byte lines per
-      // instruction; the 32 x 32 chunk is transposed through a 4 KiB shared buffer (XOR-swizzled 16-byte columns, no
-      // bank conflicts) so that every global instruction of the warp covers four full 128-byte lines.
-      float* stage = reinterpret_cast<float*>(tail + 128) + (warp - 2) * 1024;
-      const int cq = lane & 7, rsub = lane >> 3;
-      const int64_t row_base = (int64_t)tile * kLinRows + quarter * 32;
+      const float r1 = (p.rank1_row != nullptr && valid) ? p.rank1_row[pg] : 0.f;
       for (int c = 0; c < p.N / 32; ++c) {
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * 256 + c * 32, v);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (!valid) continue;
+        float4* dst = reinterpret_cast<float4*>(p.out + pg * p.ld_out + c * 32);
+        const float4* msk = p.mask ? reinterpret_cast<const float4*>(p.mask + pg * p.ld_mask + c * 32) : nullptr;
 #pragma unroll
-        for (int q = 0; q < 8; ++q)
-          *reinterpret_cast<float4*>(stage + lane * 32 + 4 * (q ^ (lane & 7))) =
-              make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
-                          __uint_as_float(v[4 * q + 3]));
-        __syncwarp();
-        const int col = c * 32 + 4 * cq;
-        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f), u4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p.bias != nullptr) bias4 = *reinterpret_cast<const float4*>(p.bias + col);
-        if (p.rank1_row != nullptr) u4 = *reinterpret_cast<const float4*>(p.rank1_col + col);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int r = j * 4 + rsub;
-          const int64_t row = row_base + r;
-          if (row < p.n_rows) {
-            float4 o = *reinterpret_cast<const float4*>(stage + r * 32 + 4 * (cq ^ (r & 7)));
-            o.x += bias4.x; o.y += bias4.y; o.z += bias4.z; o.w += bias4.w;
-            if (p.rank1_row != nullptr) {
-              const float r1 = p.rank1_row[row];
-              o.x = fmaf(r1, u4.x, o.x); o.y = fmaf(r1, u4.y, o.y); o.z = fmaf(r1, u4.z, o.z); o.w = fmaf(r1, u4.w, o.w);
-            }
-            if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-            if (p.mask != nullptr) {
-              const float4 m = *reinterpret_cast<const float4*>(p.mask + row * p.ld_mask + col);
-              o.x = m.x > 0.f ? o.x : 0.f; o.y = m.y > 0.f ? o.y : 0.f; o.z = m.z > 0.f ? o.z : 0.f; o.w = m.w > 0.f ? o.w : 0.f;
-            }
-            *reinterpret_cast<float4*>(p.out + row * p.ld_out + col) = o;
+        for (int q = 0; q < 8; ++q) {
+          float4 o = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
+                                 __uint_as_float(v[4 * q + 3]));
+          if (p.bias != nullptr) {
+            const float4 b = *reinterpret_cast<const float4*>(p.bias + c * 32 + 4 * q);
+            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
           }
+          if (p.rank1_row != nullptr) {
+            const float4 u = *reinterpret_cast<const float4*>(p.rank1_col + c * 32 + 4 * q);
+            o.x = fmaf(r1, u.x, o.x); o.y = fmaf(r1, u.y, o.y); o.z = fmaf(r1, u.z, o.z); o.w = fmaf(r1, u.w, o.w);
+          }
+          if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+          if (msk != nullptr) {
+            const float4 m = msk[q];
+            o.x = m.x > 0.f ? o.x : 0.f; o.y = m.y > 0.f ? o.y : 0.f; o.z = m.z > 0.f ? o.z : 0.f; o.w = m.w > 0.f ? o.w : 0.f;
+          }
+          dst[q] = o;
         }
-        __syncwarp();   // the buffer is rewritten by the next chunk
       }
       // this warp's TMEM reads of the accumulator are complete: hand it back to the MMA warp
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -451,7 +440,7 @@ cudaError_t launch_linear_tc(const LinearTcArgs& a, cudaStream_t s) {
   if (a.k[1] == 0) { p.map_a[1] = p.map_a[0]; p.map_b[1] = p.map_b[0]; }
   p.N = a.N; p.n_rows = a.n_rows; p.bias = a.bias; p.rank1_row = a.rank1_row; p.rank1_col = a.rank1_col;
   p.mask = a.mask; p.ld_mask = a.ld_mask; p.relu = a.relu ? 1 : 0; p.out = a.out; p.ld_out = a.ld_out;
-  const size_t smem = (size_t)kLinStages * (kLinRows * 128 + a.N * 128) + 128 + 4 * 4096;   // ring, barriers, transpose buffers
+  const size_t smem = (size_t)kLinStages * (kLinRows * 128 + a.N * 128) + 128;
   if ((e = cudaFuncSetAttribute(k_linear_tf32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
   int dev = 0, sms = 0;
   if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
