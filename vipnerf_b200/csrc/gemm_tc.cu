@@ -364,6 +364,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_linear_tf32(const __grid_cons
       const int buf = i & 1;
       const int64_t pg = (int64_t)tile * kLinRows + quarter * 32 + lane;
       const bool valid = pg < p.n_rows;
+      if (p.mask != nullptr && valid) {   // this row's ReLU mask (1 KiB from HBM) travels to L2 while the MMAs of the tile run
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          if (c * 32 < p.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.mask + pg * p.ld_mask + c * 32));
+      }
       mbar_wait(acc_full(buf), (i >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const float r1 = (p.rank1_row != nullptr && valid) ? p.rank1_row[pg] : 0.f;
