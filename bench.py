@@ -252,6 +252,13 @@ def run_frame(args, rank, world, local_rank):
 
 
 TRAIN_FLOP_PER_POINT = 2 * (593_536 + 557_056 + 593_536)   # forward + backward-data chain + parameter gradients (MACs x 2)
+# Algorithmic HBM bytes per sample point of the tensor-core training step at one secondary view (two view directions per
+# point); every fp32 activation / gradient array is written once and read once per consumer, weights stay in L2
+# (derivation: DESIGN.md section 4.6):
+#   forward 22,852 (encodings 512, ten layer products 19,456, heads 2,844, compositing 40)
+#   + compositing backward and heads backward 2,672 + backward-data chain 26,116
+#   + parameter gradients 31,012 (nine tensor-core products 17,920, three FFMA products 3,840, heads 2,084, column sums 7,168)
+TRAIN_TC_BYTES_PER_POINT = 22_852 + 2_672 + 26_116 + 31_012   # 82,652
 
 
 def run_train(args, rank, world, local_rank):
@@ -342,6 +349,26 @@ def run_train(args, rank, world, local_rank):
         sm_mhz = clocks.get('sm_mhz') or 1900.0
         peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12     # fp32 FFMA lanes x 2 FLOP x measured SM clock
         achieved = value / world * 256 * TRAIN_FLOP_PER_POINT / 1e12
+        if args.train_precision == 'tf32':
+            # the tensor-core step is HBM-bound: activations and gradients make one round trip per consumer
+            hbm_peak = 6464.3
+            ppath = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+            if os.path.isfile(ppath):
+                with open(ppath) as f:
+                    hbm_peak = json.load(f).get('hbm_gbs', hbm_peak)
+            gbs = value / world * 256 * TRAIN_TC_BYTES_PER_POINT / 1e9
+            roofline = {'bound': 'hbm', 'achieved': gbs, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': gbs / hbm_peak,
+                        'traffic': None,
+                        'peak_kind': 'measured HBM copy bandwidth (MEASURED_PEAKS.json), whole step',
+                        'bytes_per_ray': 256 * TRAIN_TC_BYTES_PER_POINT,
+                        'note': 'algorithmic bytes of all kernels of the step / step time; k_gemm_tn_tf32 alone: 1.61 GB in '
+                                '256 us under ncu = 0.97 of the peak (profiles/r01_train_ncu_summary.md)',
+                        'tensor_tflops_algorithmic': achieved}
+        else:
+            roofline = {'bound': 'fp32-ffma', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
+                        'frac': achieved / peak, 'traffic': None,
+                        'peak_kind': '148 SMs x 128 FFMA lanes x 2 x measured SM clock (CUDA cores)',
+                        'flop_per_ray': 256 * TRAIN_FLOP_PER_POINT}
         line = {'metric': 'training rays/s (forward + 4 losses + backward + Adam), 64+128 samples', 'value': value,
                 'unit': 'rays/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
                 'ms_per_step': total_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
@@ -361,12 +388,8 @@ def run_train(args, rank, world, local_rank):
                 'clocks': clocks,
                 'e2e': {'value': value, 'unit': 'rays/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4,
                         'note': 'the timed region IS end to end: pinned host rays in, loss value out'},
-                'gpu_launches': args.steps * 70,
-                'roofline': {'bound': 'fp32-ffma', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
-                             'frac': achieved / peak, 'traffic': None,
-                             'peak_kind': '148 SMs x 128 FFMA lanes x 2 x measured SM clock (CUDA cores; the tensor-core '
-                                          'backward is the next step of row f1)',
-                             'flop_per_ray': 256 * TRAIN_FLOP_PER_POINT}}
+                'gpu_launches': args.steps * (149 if args.train_precision == 'tf32' else 95),   # counted in the ncu launch lists (profiles/)
+                'roofline': roofline}
         if not args.no_cpu_baseline and world == 1:
             threads = os.cpu_count() or 1
             torch.set_num_threads(threads)
