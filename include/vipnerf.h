@@ -42,9 +42,10 @@ typedef enum vipnerf_status {
 #define VIPNERF_FLAG_NDC         (1u << 0) /* configs['data_loader']['ndc']   (VipNeRF01.py:16)          */
 #define VIPNERF_FLAG_WHITE_BKGD  (1u << 1) /* configs['model']['white_bkgd']  (VipNeRF01.py:363-364)     */
 #define VIPNERF_FLAG_LINDISP     (1u << 2) /* configs['model']['lindisp']     (VipNeRF01.py:183-190)     */
-#define VIPNERF_FLAG_TRAIN_TF32  (1u << 3) /* vipnerf_train_backward: the 256-wide parameter-gradient products
-                                              dW = dY^T X run on the tensor cores (tcgen05 kind::tf32, operands rounded
-                                              to tf32, fp32 accumulate) instead of fp32 CUDA cores                 */
+#define VIPNERF_FLAG_TRAIN_TF32  (1u << 3) /* vipnerf_train_forward / _backward: every 256-wide product of the step
+                                              (forward chain, backward-data chain, parameter gradients dW = dY^T X) runs
+                                              on the tensor cores (tcgen05 kind::tf32: operands rounded to tf32, fp32
+                                              accumulate) instead of fp32 CUDA cores                               */
 
 /* cfg.precision: arithmetic of the 256-wide matmuls (trunk layers, feature_linear, feature columns of
  * views_linears.0).  Everything else (encodings, heads, compositing, sampling) is always fp32. */
@@ -216,8 +217,8 @@ int vipnerf_visibility_prior(int32_t height, int32_t width, const uint8_t* frame
  * VipNeRF.render_rays with perturb / raw_noise_std active (VipNeRF01.py:194-202, :242, :549-552; retraw and
  * sec_views_vis are forced on, :40) and the gradient of every parameter given the gradients of the outputs.
  * The losses themselves stay the caller's (loss_functions/*.py operate on the returned tensors).
- * Arithmetic: fp32 CUDA-core kernels (cfg->precision must be VIPNERF_PRECISION_FP32), like the reference's
- * training arithmetic.  Random numbers are the caller's: rays->t_rand [R,Nc], rays->u_rand [R,Nf] (torch.rand) and
+ * Arithmetic: cfg->precision must be VIPNERF_PRECISION_FP32 (fp32 packed weights); fp32 CUDA-core kernels like the
+ * reference's training arithmetic by default, tensor cores with VIPNERF_FLAG_TRAIN_TF32.  Random numbers are the caller's: rays->t_rand [R,Nc], rays->u_rand [R,Nf] (torch.rand) and
  * sigma_noise_* = raw_noise_std * torch.randn, drawn exactly where the reference draws them; NULL = that source off.
  *
  * `saved` (vipnerf_train_saved_bytes, about 11 KB per sample point) receives the activations of both MLPs; the caller

@@ -11,8 +11,9 @@ as `VipNeRF.forward` (src/models/VipNeRF01.py:34-41, :128-133, :161-170, :366-38
 `model.eval()`: the fused tensor-core render (configs['model']['precision'], default bf16).  `model.train()`: the
 training step of SURVEY.md section 8 row f1 - train-mode forward (stratified jitter, random cdf samples, density noise
 drawn from torch's CPU generator in the reference's order; retraw and sec_views_vis forced on, VipNeRF01.py:40) and its
-backward through vipnerf_b200.training, in fp32 like the reference's training arithmetic, so that
-`loss.backward()` fills `.grad` of the same parameters the reference's optimizer steps (Trainer01.py:93-102, :519).
+backward through vipnerf_b200.training, so that `loss.backward()` fills `.grad` of the same parameters the reference's
+optimizer steps (Trainer01.py:93-102, :519) - in fp32 like the reference's training arithmetic by default, or with every
+256-wide product on the tensor cores (configs['model']['train_precision'] = 'tf32').
 There is no CPU fallback: inputs must be CUDA tensors and the shared library must be built.
 """
 from __future__ import annotations

@@ -18,8 +18,9 @@
 // time of the same layer is 0.2 ms.  The FFMA kernel it replaces needs 2.4 ms.
 //
 // Numerics: operands are rounded to tf32 (10-bit mantissa) by the TMA copy (CU_TENSOR_MAP_DATA_TYPE_TFLOAT32),
-// products accumulate in fp32.  Gradients therefore carry ~2^-11 relative rounding noise per product; it is opt-in
-// (configs['model']['train_precision'] = 'tf32'), the default training path stays fp32 FFMA.
+// products accumulate in fp32.  The tensor-core training mode is opt-in (configs['model']['train_precision'] = 'tf32',
+// VIPNERF_FLAG_TRAIN_TF32); the default training path stays fp32 FFMA.  The second kernel of this file, k_linear_tf32
+// (below), runs the forward and backward-data chains of that mode.
 #include <cuda.h>
 #include <cuda_runtime.h>
 
