@@ -39,3 +39,23 @@ def test_oracle_training_step_matches_reference(scene):
     for name, fp in grads.items():
         H.check_grad_fingerprint(name, sd[name].grad, fp, 1e-5, report)   # measured 3e-7
     assert len(report) == 48
+
+
+@pytest.mark.parametrize('n_rays,chunk,netchunk,perturb,noise,has_fine', [
+    (48, 32, 1000, True, 1.0, True), (100, 4096, 16384, True, 1.0, True), (70, 64, None, False, 0.5, True),
+    (33, 16, 500, True, 0.0, False)])
+def test_plugin_draw_order_matches_oracle(n_rays, chunk, netchunk, perturb, noise, has_fine):
+    """The product's own generator mirror (vipnerf_b200.training.draw_training_randoms, what the plugin calls in train
+    mode) consumes torch's CPU generator exactly like the oracle's, which the golden training step pins to the
+    reference: same keys, bit-identical tensors, same generator state afterwards."""
+    from vipnerf_b200 import training
+    torch.manual_seed(123)
+    a = training.draw_training_randoms(n_rays, 64, 128, chunk, netchunk, perturb, noise, has_fine)
+    tail_a = torch.rand(4)
+    torch.manual_seed(123)
+    b = O.draw_training_randoms(n_rays, 64, 128, chunk, netchunk if netchunk else 10 ** 9, perturb, noise, has_fine)
+    tail_b = torch.rand(4)
+    assert set(a) == set(b)
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
+    assert torch.equal(tail_a, tail_b)
