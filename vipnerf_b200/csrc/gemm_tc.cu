@@ -372,6 +372,55 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_linear_tf32(const __grid_cons
       }
       mbar_wait(acc_full(buf), (i >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#ifdef VIPNERF_LINEAR_EPILOGUE_V2
+      // EXPERIMENT (not in the default build; enable with VIPNERF_NVCC_DEFINES=VIPNERF_LINEAR_EPILOGUE_V2): each 32 x 32
+      // chunk goes through a 4 KiB shared buffer (XOR-swizzled 16-byte columns) so that every global instruction of a
+      // warp covers four full 128-byte lines instead of 32 partial ones.  A first version of this measured 2x SLOWER
+      // than the row-per-lane epilogue below because its mask loads sat behind per-row branches and were issued one
+      // DRAM latency at a time; here all eight are predicated and issued before the first use.  Unmeasured.
+      {
+        float* stage = reinterpret_cast<float*>(tail + 128) + (warp - 2) * 1024;
+        const int cq = lane & 7, rsub = lane >> 3;
+        const int64_t row_base = (int64_t)tile * kLinRows + quarter * 32;
+        for (int c = 0; c < p.N / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * 256 + c * 32, v);
+          const int col = c * 32 + 4 * cq;
+          float4 m[8];
+          float r1[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {   // independent of the accumulator: in flight while tcgen05.ld completes
+            const int64_t row = row_base + j * 4 + rsub;
+            const bool ok = row < p.n_rows;
+            m[j] = (p.mask != nullptr && ok) ? *reinterpret_cast<const float4*>(p.mask + row * p.ld_mask + col)
+                                             : make_float4(1.f, 1.f, 1.f, 1.f);
+            r1[j] = (p.rank1_row != nullptr && ok) ? p.rank1_row[row] : 0.f;
+          }
+          float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f), u4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.bias != nullptr) bias4 = *reinterpret_cast<const float4*>(p.bias + col);
+          if (p.rank1_row != nullptr) u4 = *reinterpret_cast<const float4*>(p.rank1_col + col);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<float4*>(stage + lane * 32 + 4 * (q ^ (lane & 7))) =
+                make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
+                            __uint_as_float(v[4 * q + 3]));
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int r = j * 4 + rsub;
+            float4 o = *reinterpret_cast<const float4*>(stage + r * 32 + 4 * (cq ^ (r & 7)));
+            o.x = fmaf(r1[j], u4.x, o.x + bias4.x); o.y = fmaf(r1[j], u4.y, o.y + bias4.y);
+            o.z = fmaf(r1[j], u4.z, o.z + bias4.z); o.w = fmaf(r1[j], u4.w, o.w + bias4.w);
+            if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+            o.x = m[j].x > 0.f ? o.x : 0.f; o.y = m[j].y > 0.f ? o.y : 0.f; o.z = m[j].z > 0.f ? o.z : 0.f; o.w = m[j].w > 0.f ? o.w : 0.f;
+            if (row_base + r < p.n_rows) *reinterpret_cast<float4*>(p.out + (row_base + r) * p.ld_out + col) = o;
+          }
+          __syncwarp();   // the buffer is rewritten by the next chunk
+        }
+      }
+      (void)valid;
+#else
       const float r1 = (p.rank1_row != nullptr && valid) ? p.rank1_row[pg] : 0.f;
       for (int c = 0; c < p.N / 32; ++c) {
         uint32_t v[32];
@@ -400,6 +449,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_linear_tf32(const __grid_cons
           dst[q] = o;
         }
       }
+#endif
       // this warp's TMEM reads of the accumulator are complete: hand it back to the MMA warp
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
@@ -446,7 +496,11 @@ cudaError_t launch_linear_tc(const LinearTcArgs& a, cudaStream_t s) {
   if (a.k[1] == 0) { p.map_a[1] = p.map_a[0]; p.map_b[1] = p.map_b[0]; }
   p.N = a.N; p.n_rows = a.n_rows; p.bias = a.bias; p.rank1_row = a.rank1_row; p.rank1_col = a.rank1_col;
   p.mask = a.mask; p.ld_mask = a.ld_mask; p.relu = a.relu ? 1 : 0; p.out = a.out; p.ld_out = a.ld_out;
+#ifdef VIPNERF_LINEAR_EPILOGUE_V2
+  const size_t smem = (size_t)kLinStages * (kLinRows * 128 + a.N * 128) + 128 + 4 * 4096;   // + the transpose buffers
+#else
   const size_t smem = (size_t)kLinStages * (kLinRows * 128 + a.N * 128) + 128;
+#endif
   if ((e = cudaFuncSetAttribute(k_linear_tf32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
   int dev = 0, sms = 0;
   if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
