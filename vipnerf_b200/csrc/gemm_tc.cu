@@ -15,7 +15,8 @@
 //
 // Roofline: HBM.  Each CTA reads every A and B row of its point range once: (M + 256) * 4 bytes per point and layer,
 // i.e. 2 KiB/point for the 256 x 256 layers -> 2.1 GB per layer at 10^6 points, 0.33 ms at 6.4 TB/s; the tf32 tensor
-// time of the same layer is 0.2 ms.  The FFMA kernel it replaces needs 2.4 ms.
+// time of the same layer is 0.2 ms.  Measured: 256 us for 786,432 points (0.97 of the HBM peak); the FFMA kernel it
+// replaces needs 1.7 ms.
 //
 // Numerics: operands are rounded to tf32 (10-bit mantissa) by the TMA copy (CU_TENSOR_MAP_DATA_TYPE_TFLOAT32),
 // products accumulate in fp32.  The tensor-core training mode is opt-in (configs['model']['train_precision'] = 'tf32',
