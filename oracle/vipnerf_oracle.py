@@ -208,6 +208,15 @@ def _round_bf16(t: torch.Tensor) -> torch.Tensor:
     return t.to(torch.bfloat16).to(torch.float32)
 
 
+def _round_fp16(t: torch.Tensor) -> torch.Tensor:
+    return t.clamp(-65504.0, 65504.0).to(torch.float16).to(torch.float32)
+
+
+def _round_tf32(t: torch.Tensor) -> torch.Tensor:
+    bits = t.contiguous().view(torch.int32)
+    return ((bits + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
 def linear(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], mode: str = 'fp32') -> torch.Tensor:
     """y = x W^T + b.  `mode` emulates the arithmetic of the CUDA kernels' tensor-core layers:
     'fp32' (the reference), 'bf16' (both operands rounded to bf16, fp32 accumulate) and
@@ -221,6 +230,17 @@ def linear(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], mode: st
         xh, wh = _round_bf16(x), _round_bf16(w)
         xl, wl = _round_bf16(x - xh), _round_bf16(w - wh)
         return F.linear(xh, wh, b) + (F.linear(xl, wh) + F.linear(xh, wl))
+    # modes below exist for tools/precision_study.py (error of candidate tensor-core arithmetics, measured on the CPU)
+    if mode == 'fp16':      # kind::f16 with fp16 operands: 11-bit significands at the bf16 MMA rate, fp32 accumulate
+        return F.linear(_round_fp16(x), _round_fp16(w), _round_fp16(b) if b is not None else None)
+    if mode == 'fp16_a2':   # 2 MMAs: activations split hi + lo (fp16), weights rounded once
+        xh, wh = _round_fp16(x), _round_fp16(w)
+        return F.linear(xh, wh, _round_fp16(b) if b is not None else None) + F.linear(_round_fp16(x - xh), wh)
+    if mode == 'bf16_a2':   # 2 MMAs: activations split hi + lo (bf16), weights rounded once
+        xh, wh = _round_bf16(x), _round_bf16(w)
+        return F.linear(xh, wh, _round_bf16(b) if b is not None else None) + F.linear(_round_bf16(x - xh), wh)
+    if mode == 'tf32':      # kind::tf32: 11-bit significands at half the bf16 rate
+        return F.linear(_round_tf32(x), _round_tf32(w), b)
     raise ValueError(mode)
 
 

@@ -53,7 +53,17 @@ class RadianceMLPParams(torch.nn.Module):
         raise RuntimeError('RadianceMLPParams holds parameters only; call VipNeRFFused.forward')
 
     def named_tensors(self) -> Dict[str, torch.Tensor]:
-        return {k: v for k, v in self.state_dict(keep_vars=True).items()}
+        """The 24 tensors under the reference's state_dict names, read BY ATTRIBUTE: inside an nn.DataParallel replica
+        (Tester01.py:42, Trainer01.py:517 with a device list) `_parameters` is empty - `parameters()` and `state_dict()`
+        return nothing there - while `linear.weight` is the replica's broadcast copy (a non-leaf tensor that carries the
+        autograd edge back to the master parameter)."""
+        out: Dict[str, torch.Tensor] = {}
+        for i, layer in enumerate(self.pts_linears):
+            out[f'pts_linears.{i}.weight'], out[f'pts_linears.{i}.bias'] = layer.weight, layer.bias
+        for name, layer in (('views_linears.0', self.views_linears[0]), ('pts_output_linear', self.pts_output_linear),
+                            ('feature_linear', self.feature_linear), ('views_output_linear', self.views_output_linear)):
+            out[f'{name}.weight'], out[f'{name}.bias'] = layer.weight, layer.bias
+        return out
 
 
 class VipNeRFFused(torch.nn.Module):
@@ -82,26 +92,41 @@ class VipNeRFFused(torch.nn.Module):
                          m['views_positional_encoding_degree'])
                 if shape != (8, 256, 10, 4):
                     raise NotImplementedError(f'{name} shape {shape}: kernels are built for (8, 256, 10, 4)')
+        # Shared BY REFERENCE between nn.DataParallel replicas (replicate() copies __dict__ shallowly): entries are keyed
+        # per device and validated against the tensors the calling replica actually holds, so sharing is harmless.
         self._pack_lock = threading.Lock()
         self._packed: Dict[tuple, tuple] = {}
-        self._param_lists: Dict[str, list] = {}
 
     # ------------------------------------------------------------------ packed-weight cache
+    def invalidate_packed(self) -> None:
+        """Drops the packed weight images.  Needed only after writes that bypass autograd's version counter
+        (`p.data.copy_()`, `p.data.mul_()` ...); optimizer steps, load_state_dict and .to() are detected."""
+        with self._pack_lock:
+            self._packed.clear()
+
     def _packed_weights(self, which: str, precision: str, device) -> torch.Tensor:
         mlp = self.coarse_model if which == 'coarse' else self.fine_model
-        # (storage address, in-place version) of every parameter: cheap to read, changes whenever an optimizer step,
-        # load_state_dict or .to() touches a weight
-        params = self._param_lists.get(which)
-        if params is None:   # nn.Parameter objects keep their identity through .to() / load_state_dict
-            params = self._param_lists[which] = list(mlp.parameters())
-        version = tuple([(t.data_ptr(), t._version) for t in params])
+        tensors = mlp.named_tensors()
+        # (storage address, in-place version) of every tensor: cheap to read, changes whenever an optimizer step,
+        # load_state_dict or .to() touches a weight - and on every forward of a DataParallel replica, whose weights are
+        # fresh broadcast copies
+        version = tuple([(t.data_ptr(), t._version) for t in tensors.values()])
         key = (which, precision, device.index)
+        stream = torch.cuda.current_stream(device)
+        if getattr(mlp, '_is_replica', False):
+            # a replica's tensors live for one forward only; a later broadcast may reuse their addresses with other
+            # values, so (address, version) identifies nothing there: pack per call (2.6 MB, one small kernel)
+            return renderpath.pack_mlp({k: v.detach() for k, v in tensors.items()}, precision)
         with self._pack_lock:
             hit = self._packed.get(key)
             if hit is not None and hit[0] == version:
+                if hit[2] != stream.cuda_stream:     # packed on another stream: order this stream after the pack kernel
+                    stream.wait_event(hit[3])
                 return hit[1]
-            packed = renderpath.pack_mlp({k: v.detach() for k, v in mlp.named_tensors().items()}, precision)
-            self._packed[key] = (version, packed)
+            packed = renderpath.pack_mlp({k: v.detach() for k, v in tensors.items()}, precision)
+            done = torch.cuda.Event()
+            done.record(stream)
+            self._packed[key] = (version, packed, stream.cuda_stream, done)
             return packed
 
     # ------------------------------------------------------------------ the reference's forward contract

@@ -33,7 +33,12 @@ def _f32c(t: torch.Tensor, name: str) -> torch.Tensor:
     _require_cuda(t, name)
     if t.dtype != torch.float32:
         t = t.float()
-    return t.contiguous()
+    t = t.contiguous()
+    if t.data_ptr() % 16 != 0:
+        # a ray-dimension slice (batch[k][lo:hi] of sharding.shard_batch, Trainer01.py:83-87 sub-batches) is contiguous
+        # but starts at 12*lo / 4*lo bytes; the library reads rays with 16-byte vector loads
+        t = t.clone(memory_format=torch.contiguous_format)
+    return t
 
 
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
