@@ -61,7 +61,7 @@ class ClockSampler:
     """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
 
     def __init__(self, index, period_s=0.01):
-        self.sm, self.max_mhz, self.reasons, self.error = [], None, set(), None
+        self.sm, self.max_mhz, self.reasons, self.error, self.power = [], None, set(), None, []
         self._stop = threading.Event()
         try:
             import pynvml
@@ -87,6 +87,10 @@ class ClockSampler:
         while not self._stop.is_set():
             try:
                 self.sm.append(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                try:
+                    self.power.append(n.nvmlDeviceGetPowerUsage(self.handle) / 1000.0)
+                except Exception:   # noqa: BLE001
+                    pass
                 mask = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
                 for key, attr in names.items():
                     if mask & getattr(n, attr, 0):
@@ -102,6 +106,7 @@ class ClockSampler:
         self._stop.set()
         self.thread.join(timeout=2)
         return {'sm_mhz': statistics.median(self.sm) if self.sm else None, 'sm_max_mhz': self.max_mhz,
+                'sm_mhz_min': min(self.sm) if self.sm else None, 'power_w_max': max(self.power) if self.power else None,
                 'samples': len(self.sm), 'reasons': sorted(self.reasons)}
 
 
@@ -122,38 +127,115 @@ def cpu_oracle_rate(n_rays, reps, threads):
     return n_rays / best
 
 
+def bench_config(rays_per_step):
+    """The workload description BOTH arms print (identical dict, so the driver's same_config holds); everything that
+    is specific to one arm (precision, kernel, the CPU arm's bounded sample) goes into `details`."""
+    return {'workload': WORKLOAD, 'rays_per_step': rays_per_step, 'samples': '64+128', 'ndc': True,
+            'l2': 'GPU arm: flushed between timed iterations (256 MiB memset, untimed); CPU arm: n/a'}
+
+
+# parity_check gates per arithmetic: key family -> (median, p99, max) of |out - ref| / max|ref|
+# (tests/test_gpu_bench_shapes.py holds the same numbers and their derivation)
+_GATES = {
+    'bf16': {'map': (1e-4, 2e-3, 1e-2), 'depth': (3e-3, 3e-2, 1e-1)},
+    'fp16': {'map': (2e-5, 4e-4, 2e-3), 'depth': (6e-4, 6e-3, 1e-1)},
+    'bf16x3': {'map': (1e-5, 1e-4, 1e-4), 'depth': (1e-5, 1e-3, 1e-2)},
+    'fp32': {'map': (1e-5, 1e-4, 1e-4), 'depth': (1e-5, 1e-3, 1e-2)},
+}
+PARITY_KEYS = ('rgb_fine', 'acc_fine', 'depth_fine', 'depth_ndc_fine', 'rgb_coarse', 'acc_coarse', 'depth_coarse')
+
+
+def parity_check(out, host_batch, precision, n_sub=512):
+    """Compares the maps of a launch (the LAST TIMED one) with the CPU oracle on a strided `n_sub`-ray subset of the
+    same batch (rays are independent).  Untimed.  Returns {'ok', 'against', per key {'median','p99','max'}}."""
+    import torch
+    from oracle import vipnerf_oracle as O
+    R = host_batch['rays_o'].shape[0]
+    idx = torch.arange(0, R, max(1, R // n_sub))[:n_sub]
+    sub = {k: v[idx] for k, v in host_batch.items()}
+    with torch.no_grad():
+        ref = O.render(O.synth_state_dict(0), sub, ndc=True)
+    res, ok = {}, True
+    for k in PARITY_KEYS:
+        got = out[k].detach()[idx.to(out[k].device)].cpu().double()
+        d = ((got - ref[k].double()).abs() / ref[k].abs().max().clamp_min(1e-30)).flatten()
+        med, p99, mx = d.median().item(), torch.quantile(d, 0.99).item(), d.max().item()
+        g = _GATES[precision]['depth' if k.startswith('depth') else 'map']
+        good = bool(torch.isfinite(d).all()) and med <= g[0] and p99 <= g[1] and mx <= g[2]
+        ok = ok and good
+        res[k] = {'median': med, 'p99': p99, 'max': mx, 'ok': good}
+    return {'ok': ok, 'against': f'CPU oracle (pinned to the unmodified reference) on {len(idx)} strided rays of the timed batch',
+            'norm': '|out - ref| / max|ref| per key', 'precision': precision, 'keys': res}
+
+
+def time_launches(fn, steps, flush, pre=None):
+    """CUDA-event windows around `steps` calls of fn on the current stream, L2 flushed (untimed) before each."""
+    import torch
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    last = None
+    for i in range(steps):
+        if flush is not None:
+            flush.zero_()
+        starts[i].record()
+        last = fn()
+        ends[i].record()
+    return starts, ends, last
+
+
 def run_reference(args, rank, world):
-    """--impl reference: the reference's algorithm on the host CPU (oracle port), rank 0 only."""
+    """--impl reference: the reference's own CPU implementation of the path on this box's host cores, rank 0 only.
+    Drives the UNMODIFIED reference model staged under oracle/_ref (oracle/build_ref.py; `kind: reference`) when it is
+    present, else the oracle port (`kind: port`); same weights, same ray batch, same config as the GPU arm."""
     if rank != 0:
         return
     import torch
+    from oracle import build_ref
     from oracle import vipnerf_oracle as O
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
     sd = O.synth_state_dict(0)
+    if build_ref.ref_available():
+        kind = 'reference'
+        cfg = model_configs('bf16')
+        cfg['model']['name'] = 'VipNeRF01'
+        del cfg['model']['precision']
+        model = build_ref.load_ref_get_model()(cfg, None)
+        model.load_state_dict(sd)
+        model.eval()
+
+        def render(b):
+            return model(dict(b))
+    else:
+        kind = 'port'
+
+        def render(b):
+            return O.render(sd, b, ndc=True)
     with torch.no_grad():
         probe = O.make_rays('fern', 256, seed=2)
-        O.render(sd, probe, ndc=True)
+        render(probe)
         t0 = time.perf_counter()
-        O.render(sd, probe, ndc=True)
+        render(probe)
         rate = 256 / (time.perf_counter() - t0)
         budget_s = 90.0
         n = int(rate * budget_s / max(1, args.steps + args.warmup))
-        n = max(256, min(RAYS_PER_STEP, (n // 256) * 256))
+        n = max(256, min(args.rays_per_step, (n // 256) * 256))
         batch = O.make_rays('fern', n, seed=2)
         for _ in range(args.warmup):
-            O.render(sd, batch, ndc=True)
+            render(batch)
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            O.render(sd, batch, ndc=True)
+            render(batch)
         total = time.perf_counter() - t0
     value = n * args.steps / total
-    sample = f'{n} rays of the 4096-ray batch per step, fp32 torch CPU'
+    sample = (f'{n} rays of the {args.rays_per_step}-ray batch per step, fp32 torch CPU, '
+              + ('unmodified reference VipNeRF01 (oracle/_ref)' if kind == 'reference' else 'oracle port'))
     line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'rays/s', 'n_gpus': args.gpus,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * total / args.steps,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': WORKLOAD, 'rays_per_step': n, 'samples': '64+128', 'host': 'cpu'},
-            'cpu_baseline': {'value': value, 'unit': 'rays/s', 'cores': threads, 'kind': 'port', 'sample': sample},
+            'config': bench_config(args.rays_per_step),
+            'details': {'host': 'cpu', 'threads': threads, 'rays_timed_per_step': n, 'kind': kind},
+            'cpu_baseline': {'value': value, 'unit': 'rays/s', 'cores': threads, 'kind': kind, 'sample': sample},
             'e2e': {'value': value, 'unit': 'rays/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
     print(json.dumps(line), flush=True)
@@ -261,33 +343,23 @@ TRAIN_FLOP_PER_POINT = 2 * (593_536 + 557_056 + 593_536)   # forward + backward-
 TRAIN_TC_BYTES_PER_POINT = 22_852 + 2_672 + 26_116 + 31_012   # 82,652
 
 
-def run_train(args, rank, world, local_rank):
-    """--workload train: BASELINE config 3 - one TRAINING iteration of the RealEstate-10K setup (2 input views -> one
-    secondary view, 2048 + 2048 rays, the four losses of the shipped configs) through the plugin exactly as
-    Trainer01.train_one_iter (:61-107) drives it: zero_grad, model(batch) in train mode, the losses, backward,
-    Adam step.  Weak scaling: every rank steps its own batch and the gradients are summed with one NCCL all-reduce per
-    step (what torch.nn.DataParallel's reduce does in the reference).  fp32 CUDA-core kernels (row f1, first correct
-    path) - informational; the default workload is the eval render BASELINE.json quotes the metric on."""
+def make_train_step(device, R, rng, train_precision, seed, world=1):
+    """One training iteration of BASELINE config 3 through the plugin exactly as Trainer01.train_one_iter (:61-107)
+    drives it: pinned host rays in, zero_grad, model(batch) in train mode, the four losses, backward, Adam step.
+    Returns (step_fn, model, h2d_bytes)."""
     import torch
-    import torch.distributed as dist
     from oracle import vipnerf_oracle as O
     from vipnerf_b200 import sharding
     from vipnerf_b200.ModelFactory import get_model
-
-    torch.cuda.set_device(local_rank)
-    device = torch.device('cuda', local_rank)
-    if world > 1:
-        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        dist.init_process_group('nccl', device_id=device)
-    R, V = args.rays_per_step, 1
+    V = 1
     cfg = model_configs('bf16', ndc=True)
-    cfg['model']['rng'] = args.rng
-    cfg['model']['train_precision'] = args.train_precision
+    cfg['model']['rng'] = rng
+    cfg['model']['train_precision'] = train_precision
     model = get_model(cfg, None)
     model.load_state_dict(O.synth_state_dict(0))
     model = model.to(device).train()
     opt = torch.optim.Adam(model.parameters(), lr=5e-4, betas=(0.9, 0.999))
-    host = {k: v.pin_memory() for k, v in O.make_rays('re10k', R, seed=2 + rank, n_sec_views=V).items()}
+    host = {k: v.pin_memory() for k, v in O.make_rays('re10k', R, seed=seed, n_sec_views=V).items()}
     sup_host = O.make_supervision('re10k', R, V)
     sup = {k: (v.to(device) if isinstance(v, torch.Tensor) else v) for k, v in sup_host.items()}
     # the reference's losses index with boolean masks (a device sync + a sort per use); the masks are fixed for the
@@ -307,8 +379,6 @@ def run_train(args, rank, world, local_rank):
             total = total + 0.001 * torch.mean(torch.sum(prior_nerf * (1 - out[f'visibility2_{t}'].index_select(0, m_nerf)), dim=1))
         return total + 0.1 * torch.mean(torch.square(out['depth_fine'].index_select(0, m_depth) - depth_gt))
 
-    h2d = sum(v.numel() * 4 for v in host.values())
-
     def step():
         batch = {k: v.to(device, non_blocking=True) for k, v in host.items()}
         opt.zero_grad(set_to_none=True)
@@ -318,6 +388,58 @@ def run_train(args, rank, world, local_rank):
             sharding.allreduce_gradients(model, average=True)
         opt.step()
         return loss
+
+    return step, model, sum(v.numel() * 4 for v in host.values())
+
+
+def train_record(device, steps=5, warmup=3, R=4096):
+    """`train` sub-record of the default bench line: the 4096-ray training iteration in tensor-core mode (device-side
+    random draws), ms per step and the fraction of the TENSOR roofline (3.66 TFLOP per iteration)."""
+    import torch
+    step, _, h2d = make_train_step(device, R, 'device', 'tf32', seed=2)
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    t_ms, loss_value = 0.0, None
+    for _ in range(steps):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        loss_value = step().item()
+        e.record()
+        torch.cuda.synchronize()
+        t_ms += s.elapsed_time(e)
+    ms = t_ms / steps
+    peaks = measured_peaks()
+    tflops = R * 256 * TRAIN_FLOP_PER_POINT / (ms * 1e-3) / 1e12
+    return {'workload': 'RealEstate-10K camera, 1 secondary view, 4096-ray training iteration: pinned host rays in, train-mode '
+                        'forward, the four ViP-NeRF losses, backward, Adam, loss value out',
+            'train_precision': 'tf32 (tcgen05 kind::tf32 chains + parameter gradients)', 'rng': 'device',
+            'ms_per_step': ms, 'value': R / (ms * 1e-3), 'unit': 'rays/s', 'steps': steps,
+            'flop_per_step': R * 256 * TRAIN_FLOP_PER_POINT, 'achieved_tflops': tflops,
+            'roofline': {'bound': 'tensor', 'achieved': tflops, 'peak': peaks['sustained'] / 2, 'unit': 'TFLOP/s',
+                         'frac': tflops / (peaks['sustained'] / 2),
+                         'peak_kind': 'dense tf32 = half the measured sustained bf16 rate'},
+            'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4, 'final_loss': loss_value}
+
+
+def run_train(args, rank, world, local_rank):
+    """--workload train: BASELINE config 3 - one TRAINING iteration of the RealEstate-10K setup (2 input views -> one
+    secondary view, 2048 + 2048 rays, the four losses of the shipped configs) through the plugin exactly as
+    Trainer01.train_one_iter (:61-107) drives it: zero_grad, model(batch) in train mode, the losses, backward,
+    Adam step.  Weak scaling: every rank steps its own batch and the gradients are summed with one NCCL all-reduce per
+    step (what torch.nn.DataParallel's reduce does in the reference).  Informational; the default workload is the eval
+    render BASELINE.json quotes the metric on (its line carries a `train` sub-record)."""
+    import torch
+    import torch.distributed as dist
+    from oracle import vipnerf_oracle as O
+
+    torch.cuda.set_device(local_rank)
+    device = torch.device('cuda', local_rank)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=device)
+    R, V = args.rays_per_step, 1
+    step, model, h2d = make_train_step(device, R, args.rng, args.train_precision, seed=2 + rank, world=world)
 
     def barrier():
         if world > 1:
@@ -422,7 +544,7 @@ def main():
     ap.add_argument('--steps', type=int, default=50)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--precision', default='bf16', choices=['bf16', 'bf16x3', 'fp32'])
+    ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp16', 'bf16x3', 'fp32'])
     ap.add_argument('--rays-per-step', type=int, default=RAYS_PER_STEP)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--workload', default='batch', choices=['batch', 'frame', 'train'])
@@ -431,6 +553,8 @@ def main():
     ap.add_argument('--rng', default='reference', choices=['reference', 'device'],
                     help='train workload: where the stratified jitter / cdf samples / density noise are drawn')
     ap.add_argument('--scene', default='fern', choices=['fern', 'dtu'], help='camera of the frame workload')
+    ap.add_argument('--quick', action='store_true', help='batch workload: skip the sustained / precision_modes / train sub-records')
+    ap.add_argument('--no-train', action='store_true', help='batch workload: skip the train sub-record')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
 
@@ -454,10 +578,35 @@ def main():
         run_train(args, rank, world, local_rank)
         return
 
+    run_batch(args, rank, world, local_rank)
+
+
+def _measure_kernel(model, precision, dev_batch, steps, warmup, flush, barrier):
+    """Device-timed launches of the hot path with inputs resident in HBM.  Returns (per-step ms, last output)."""
+    import torch
+    from vipnerf_b200 import renderpath
+    device = dev_batch['rays_o'].device
+    packed_c = model._packed_weights('coarse', precision, device)
+    packed_f = model._packed_weights('fine', precision, device)
+    eval_keys = renderpath.pass_keys(True, False, 0)
+
+    def hot_path():
+        return renderpath.render_rays(dev_batch, packed_c, packed_f, ndc=True, precision=precision, keys=eval_keys)
+
+    with torch.no_grad():
+        for _ in range(warmup):
+            hot_path()
+        barrier()
+        starts, ends, last = time_launches(hot_path, steps, flush)
+        barrier()
+    return [s.elapsed_time(e) for s, e in zip(starts, ends)], last
+
+
+def run_batch(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
-    from oracle import vipnerf_oracle as O                      # only for synthetic weights / rays + cpu_baseline
-    from vipnerf_b200 import renderpath, sharding
+    from oracle import vipnerf_oracle as O                      # only for synthetic weights / rays, parity_check and cpu_baseline
+    from vipnerf_b200 import sharding
     from vipnerf_b200.ModelFactory import get_model
 
     if not torch.cuda.is_available():
@@ -470,50 +619,45 @@ def main():
 
     R = args.rays_per_step
     precision = args.precision
-    model = get_model(model_configs(precision), None)
-    model.load_state_dict(O.synth_state_dict(0))
-    model = model.to(device).eval()
+    sd = O.synth_state_dict(0)
+
+    def make_model(prec):
+        m = get_model(model_configs(prec), None)
+        m.load_state_dict(sd)
+        return m.to(device).eval()
+
+    model = make_model(precision)
     # weak scaling: every rank renders its own 4096-ray batch of the frame (different pixels per rank)
     host_batch = {k: v.pin_memory() for k, v in O.make_rays('fern', R, seed=2 + rank).items()}
     dev_batch = {k: v.to(device) for k, v in host_batch.items()}
-    packed_c = model._packed_weights('coarse', precision, device)
-    packed_f = model._packed_weights('fine', precision, device)
-    eval_keys = renderpath.pass_keys(True, False, 0)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)   # > 126 MB L2
-
-    def hot_path():
-        return renderpath.render_rays(dev_batch, packed_c, packed_f, ndc=True, precision=precision, keys=eval_keys)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
     # ------------------------------------------------------------------ value: kernel path, inputs in HBM
-    with torch.no_grad():
-        for _ in range(args.warmup):
-            hot_path()
-        barrier()
-        sampler = ClockSampler(local_rank)
-        starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-        ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-        for i in range(args.steps):
-            flush.zero_()                       # evict L2 between timed iterations (untimed)
-            starts[i].record()
-            hot_path()
-            ends[i].record()
-        barrier()
-        step_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
-        clocks = sampler.stop()
-    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=device)
-    if world > 1:
-        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
-    total_ms = total_ms.item()
+    sampler = ClockSampler(local_rank)
+    step_ms, last_out = _measure_kernel(model, precision, dev_batch, args.steps, args.warmup, flush, barrier)
+    clocks = sampler.stop()
+    total_ms = max_over_ranks(sum(step_ms))
     value = world * R * args.steps / (total_ms * 1e-3)
+    # parity of the LAST TIMED launch (untimed): every rank checks its own batch, any failure fails the run
+    check = parity_check(last_out, host_batch, precision)
+    all_ok = max_over_ranks(0.0 if check['ok'] else 1.0) == 0.0
 
     # ------------------------------------------------------------------ e2e: plugin call with host buffers
     out_keys = ('rgb_fine', 'depth_fine', 'depth_var_fine', 'depth_ndc_fine', 'depth_var_ndc_fine')
-    host_out = {k: torch.empty((R, 3) if k == 'rgb_fine' else (R,), dtype=torch.float32).pin_memory() for k in out_keys}
+    n_host_rays = world * R if (world > 1 and rank == 0) else R
+    host_out = {k: torch.empty((n_host_rays, 3) if k == 'rgb_fine' else (n_host_rays,), dtype=torch.float32).pin_memory()
+                for k in out_keys}
     h2d = sum(v.numel() * 4 for v in host_batch.values())
     d2h = sum(v.numel() * 4 for v in host_out.values())
 
@@ -522,66 +666,131 @@ def main():
         out = model(batch)
         maps = {k: out[k] for k in out_keys}
         if world > 1:   # the single collective of the path: gather the rendered pixels on rank 0
-            gathered = sharding.gather_outputs(maps, world * R, None, 0)
-            if rank == 0:
-                for k in out_keys:
-                    host_out[k].copy_(gathered[k][:R], non_blocking=True)
-        else:
-            for k in out_keys:
+            maps = sharding.gather_outputs(maps, world * R, None, 0)
+        if maps is not None:
+            for k in out_keys:   # rank 0 brings the WHOLE gathered result to the host
                 host_out[k].copy_(maps[k], non_blocking=True)
+        return maps
 
     e2e_steps = args.steps
     with torch.no_grad():
         for _ in range(3):
             e2e_step()
         barrier()
-        # Steps are enqueued back to back like a serving loop (no host sync per step): every step's window - its H2D
-        # copies, the render, its D2H copies (+ the gather) - is timed with its own event pair on the stream; the L2
-        # flush between steps is outside the windows, as for `value`.
-        e_starts = [torch.cuda.Event(enable_timing=True) for _ in range(e2e_steps)]
-        e_ends = [torch.cuda.Event(enable_timing=True) for _ in range(e2e_steps)]
-        for i in range(e2e_steps):
-            flush.zero_()
-            e_starts[i].record()
-            e2e_step()
-            e_ends[i].record()
+        # (a) pipelined: steps enqueued back to back like a serving loop (no host sync per step); every step's window -
+        # its H2D copies, the render, (the gather), its D2H copies - is timed with its own event pair on the stream
+        starts, ends, _ = time_launches(e2e_step, e2e_steps, flush)
         barrier()
-        e_total = sum(s.elapsed_time(e) for s, e in zip(e_starts, e_ends))
-    e_ms = torch.tensor([e_total], dtype=torch.float64, device=device)
+        e_total = max_over_ranks(sum(s.elapsed_time(e) for s, e in zip(starts, ends)))
+        # (b) synchronous: the host waits for every step's result before it issues the next one (wall clock per step,
+        # flush outside the window)
+        t_sync = 0.0
+        for _ in range(e2e_steps):
+            flush.zero_()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            e2e_step()
+            torch.cuda.synchronize()
+            t_sync += time.perf_counter() - t0
+        barrier()
+        t_sync = max_over_ranks(t_sync)
+    e2e_value = world * R * e2e_steps / (e_total * 1e-3)
+    e2e_synced = world * R * e2e_steps / t_sync
+
+    # sharded == unsharded (N > 1): rank 0 re-renders every rank's batch alone and compares with what the gather
+    # delivered - bit for bit (untimed)
+    sharded_ok = None
     if world > 1:
-        dist.all_reduce(e_ms, op=dist.ReduceOp.MAX)
-    e2e_value = world * R * e2e_steps / (e_ms.item() * 1e-3)
+        with torch.no_grad():
+            gathered = e2e_step()
+            barrier()
+            if rank == 0:
+                sharded_ok = True
+                for r in range(world):
+                    b = {k: v.to(device) for k, v in O.make_rays('fern', R, seed=2 + r).items()}
+                    alone = model(b)
+                    for k in out_keys:
+                        sharded_ok = sharded_ok and bool(torch.equal(alone[k], gathered[k][r * R:(r + 1) * R]))
+                        sharded_ok = sharded_ok and bool(torch.equal(host_out[k][r * R:(r + 1) * R], alone[k].cpu()))
+
+    # ------------------------------------------------------------------ sub-records (rank 0 of a 1-GPU run only)
+    extras = {}
+    if world == 1 and not args.quick:
+        peaks = measured_peaks()
+        # sustained: 65,536-ray launches back to back for ~0.5 s, against the SUSTAINED dense-bf16 peak
+        big = {k: v.to(device) for k, v in O.make_rays('fern', 65536, seed=2).items()}
+        s_sampler = ClockSampler(local_rank)
+        s_ms, _ = _measure_kernel(model, precision, big, 30, 3, None, barrier)
+        s_clocks = s_sampler.stop()
+        s_rate = 65536 * len(s_ms) / (sum(s_ms) * 1e-3)
+        extras['sustained'] = {'rays_per_launch': 65536, 'launches': len(s_ms), 'value': s_rate, 'unit': 'rays/s',
+                               'achieved': s_rate * FLOP_PER_RAY / 1e12, 'peak': peaks['sustained'],
+                               'frac': s_rate * FLOP_PER_RAY / 1e12 / peaks['sustained'],
+                               'peak_kind': f"dense bf16 sustained, {peaks['source']}", 'clocks': s_clocks,
+                               'ms_per_launch_first_last': [round(x, 3) for x in (s_ms[:3] + s_ms[-3:])],
+                               'l2': 'not flushed: launches back to back'}
+        del big
+        # the other arithmetics of the same kernel on the same batch: throughput and parity of their last timed launch
+        modes = {}
+        for prec in ('fp16', 'bf16x3', 'bf16'):
+            if prec == precision:
+                continue
+            m = make_model(prec)
+            ms, out_m = _measure_kernel(m, prec, dev_batch, max(5, args.steps // 2), 3, flush, barrier)
+            modes[prec] = {'value': R * len(ms) / (sum(ms) * 1e-3), 'unit': 'rays/s', 'ms_per_step': statistics.mean(ms),
+                           'parity_check': parity_check(out_m, host_batch, prec)}
+            all_ok = all_ok and modes[prec]['parity_check']['ok']
+        extras['precision_modes'] = modes
+        if not args.no_train:
+            extras['train'] = train_record(device, steps=5, warmup=3)
 
     if rank == 0:
         peaks = measured_peaks()
         kernel_ms = statistics.mean(step_ms)
         achieved = R * FLOP_PER_RAY / (kernel_ms * 1e-3) / 1e12
-        traffic = None
-        tpath = os.path.join(ROOT, 'profiles', 'r01_traffic.json')
-        if os.path.isfile(tpath):
-            with open(tpath) as f:
-                traffic = json.load(f).get(precision)
+        prof = {}
+        ppath = os.path.join(ROOT, 'profiles', 'r02_traffic.json')
+        if not os.path.isfile(ppath):
+            ppath = os.path.join(ROOT, 'profiles', 'r01_traffic.json')
+        if os.path.isfile(ppath):
+            with open(ppath) as f:
+                prof = json.load(f)
+        traffic = prof.get(precision)
         line = {
             'metric': METRIC, 'value': value, 'unit': 'rays/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': total_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
-            'vs_baseline': None, 'dtype': {'bf16': 'bf16', 'bf16x3': 'bf16x3', 'fp32': 'f32'}[precision],
+            'vs_baseline': None, 'dtype': {'bf16': 'bf16', 'bf16x3': 'bf16x3', 'fp32': 'f32', 'fp16': 'f16'}[precision],
             'data': 'synthetic',
-            'config': {'workload': WORKLOAD, 'rays_per_step_per_gpu': R, 'samples': '64+128', 'ndc': True,
-                       'precision': precision, 'kernel': 'k_render_tc (fused coarse+fine, 1 launch/step)'
-                       if precision != 'fp32' else 'staged fp32 kernels (5 launches/step)',
-                       'l2': 'flushed between timed iterations (256 MiB memset, untimed)',
-                       'weights': 'random-init reference architecture, density head rescaled (oracle.synth_state_dict)'},
+            'config': bench_config(R),
+            'details': {'precision': precision, 'rays_per_step_per_gpu': R,
+                        'kernel': 'k_render_tc (fused coarse+fine, 1 launch/step)' if precision != 'fp32'
+                        else 'staged fp32 kernels (5 launches/step)',
+                        'weights': 'random-init reference architecture, density head rescaled (oracle.synth_state_dict)'},
             'clocks': clocks,
             'e2e': {'value': e2e_value, 'unit': 'rays/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                     'steps': e2e_steps, 'api': 'VipNeRFFused.forward(batch) via ModelFactory.get_model',
-                    'timing': 'per-step CUDA-event windows (H2D copies + render + D2H copies), steps enqueued back to back'},
+                    'timing': 'per-step CUDA-event windows (H2D copies + render (+ gather) + D2H copies of the whole result), '
+                              'steps enqueued back to back',
+                    'value_host_sync_per_step': e2e_synced,
+                    'timing_host_sync': 'wall clock per step with torch.cuda.synchronize() on both sides'},
             'gpu_launches': args.steps * (1 if precision != 'fp32' else 5),
-            'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': peaks['sustained'], 'unit': 'TFLOP/s',
-                         'frac': achieved / peaks['sustained'], 'traffic': traffic,
-                         'peak_kind': f"dense bf16 sustained, {peaks['source']}", 'peak_burst': peaks['burst'],
-                         'frac_of_burst': achieved / peaks['burst'], 'flop_per_ray': FLOP_PER_RAY,
-                         'kernel_ms': kernel_ms},
+            'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': peaks['burst'], 'unit': 'TFLOP/s',
+                         'frac': achieved / peaks['burst'], 'traffic': traffic,
+                         'peak_kind': f"dense bf16 BURST (cuBLAS best of 10), {peaks['source']}: the kernel is timed alone, "
+                                      '~0.9 ms launches with an L2 flush in between',
+                         'peak_sustained': peaks['sustained'], 'frac_of_sustained': achieved / peaks['sustained'],
+                         'flop_per_ray': FLOP_PER_RAY, 'kernel_ms': kernel_ms,
+                         'tensor_pipe_active_ncu': prof.get('tensor_pipe_active'),
+                         'sustained': extras.get('sustained')},
+            'parity_check': check,
         }
+        if sharded_ok is not None:
+            line['sharded_equals_unsharded'] = sharded_ok
+            all_ok = all_ok and sharded_ok
+        if 'precision_modes' in extras:
+            line['precision_modes'] = extras['precision_modes']
+        if 'train' in extras:
+            line['train'] = extras['train']
         if not args.no_cpu_baseline and world == 1:
             threads = os.cpu_count() or 1
             n_cpu = 1024
@@ -593,6 +802,8 @@ def main():
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+    if not all_ok:
+        raise SystemExit('bench.py: parity_check FAILED - the timed launch does not match the oracle (see the JSON line)')
 
 
 if __name__ == '__main__':

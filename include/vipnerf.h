@@ -52,6 +52,8 @@ typedef enum vipnerf_status {
 #define VIPNERF_PRECISION_FP32    0 /* CUDA-core FFMA, staged kernels; the bit-for-bit-closest path      */
 #define VIPNERF_PRECISION_BF16    1 /* tcgen05.mma kind::f16, bf16 operands, fp32 accumulate in TMEM     */
 #define VIPNERF_PRECISION_BF16X3  2 /* tcgen05.mma, hi/lo bf16 split of both operands (3 MMAs / product) */
+#define VIPNERF_PRECISION_FP16    3 /* tcgen05.mma kind::f16, fp16 operands (11-bit significand, saturating
+                                       at +-65504), fp32 accumulate: the bf16 rate at ~8x smaller rounding   */
 
 typedef struct vipnerf_cfg {
   int32_t abi;          /* VIPNERF_ABI_VERSION */

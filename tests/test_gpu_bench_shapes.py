@@ -43,6 +43,9 @@ BF16_GATES = {
     'visibility2_coarse': _MAP, 'visibility2_fine': _MAP,
     'depth_coarse': _DEPTH, 'depth_fine': _DEPTH, 'depth_ndc_coarse': _DEPTH, 'depth_ndc_fine': _DEPTH,
 }
+# fp16 operands (same MMA rate as bf16, 11-bit significands): gates from tools/precision_study.py with margin
+_MAP16, _DEPTH16 = (2e-5, 4e-4, 2e-3), (6e-4, 6e-3, 1e-1)   # depth max: one ray on a discontinuity, as in bf16
+FP16_GATES = {k: (_MAP16 if v is _MAP else _DEPTH16) for k, v in BF16_GATES.items()}
 X3_KEYS = ('rgb_coarse', 'rgb_fine', 'acc_coarse', 'acc_fine', 'depth_coarse', 'depth_fine', 'visibility2_coarse',
            'visibility2_fine', 'depth_ndc_coarse', 'depth_ndc_fine')
 REPORT = {}
@@ -82,7 +85,7 @@ def _gate(out, ref, precision, tag, keys=None):
             else:
                 assert med <= 1e-5 and p99 <= 1e-3 and mx <= 1e-2, (tag, k, med, p99, mx)
         else:
-            g = BF16_GATES[k]
+            g = (FP16_GATES if precision == 'fp16' else BF16_GATES)[k]
             assert med <= g[0] and p99 <= g[1] and mx <= g[2], (tag, k, med, p99, mx, g)
 
 
@@ -114,7 +117,7 @@ def oracle_4096():
     return batch, ref, full
 
 
-@pytest.mark.parametrize('precision', ['bf16', 'bf16x3', 'fp32'])
+@pytest.mark.parametrize('precision', ['bf16', 'fp16', 'bf16x3', 'fp32'])
 def test_benchmarked_4096_ray_batch_vs_oracle(precision, oracle_4096, built_library):
     """The exact launch bench.py times (fern NDC, 4096 rays, eval keys) against the CPU oracle on all 4096 rays."""
     batch, ref, _ = oracle_4096
@@ -122,13 +125,13 @@ def test_benchmarked_4096_ray_batch_vs_oracle(precision, oracle_4096, built_libr
         out = _model(True, precision)(to_cuda(batch))
     assert set(out) == set(ref)
     _gate(out, ref, precision, 'fern4096')
-    if precision != 'bf16':
+    if precision not in ('bf16', 'fp16'):
         assert O.psnr_u8(out['rgb_fine'], ref['rgb_fine']) >= 55.0
     # alpha maps (kept by the reference in eval mode, VipNeRF01.py:168-170): coarse is free of the re-sampling
     # discontinuity
     med, p99, mx = _stats(out['alpha_coarse'], ref['alpha_coarse'])
     REPORT[f'fern4096/{precision}/alpha_coarse'] = {'median': med, 'p99': p99, 'max': mx}
-    assert p99 <= (5e-2 if precision == 'bf16' else 1e-4), (med, p99, mx)
+    assert p99 <= {'bf16': 5e-2, 'fp16': 5e-3}.get(precision, 1e-4), (med, p99, mx)
 
 
 @pytest.mark.parametrize('precision', ['bf16x3', 'fp32'])
@@ -151,7 +154,7 @@ def test_fine_pass_teacher_forced_4096_rays(precision, oracle_4096, built_librar
         assert mx <= 1e-4, (k, med, p99, mx)
 
 
-@pytest.mark.parametrize('precision', ['bf16', 'bf16x3'])
+@pytest.mark.parametrize('precision', ['bf16', 'fp16', 'bf16x3'])
 @pytest.mark.parametrize('n_rays', [4096, 65536])
 def test_rows_do_not_depend_on_batch_size(precision, n_rays, built_library):
     """Many ray pairs per CTA slot (4096 rays: 7, 65536 rays: 111) vs one: a strided 296-ray subset rendered alone
@@ -168,7 +171,7 @@ def test_rows_do_not_depend_on_batch_size(precision, n_rays, built_library):
         assert torch.equal(full[k], again[k]), k
 
 
-@pytest.mark.parametrize('precision', ['bf16', 'bf16x3'])
+@pytest.mark.parametrize('precision', ['bf16', 'fp16', 'bf16x3'])
 def test_validation_chunk_65536_rays_retraw_secondary_views(precision, built_library):
     """Trainer01.run_validation's call: model(batch, retraw=True, sec_views_vis=True) on a 65,536-ray chunk with two
     secondary views; a strided 1024-ray subset against the CPU oracle, every key of the reference's output."""
@@ -188,12 +191,15 @@ def test_validation_chunk_65536_rays_retraw_secondary_views(precision, built_lib
         REPORT[f'fern65536rs/{precision}/{k}'] = {'median': med, 'p99': p99, 'max': mx}
         if precision == 'bf16x3':
             assert mx <= 1e-4, (k, med, p99, mx)
+        elif precision == 'fp16':
+            assert med <= 3e-4 and mx <= 2e-2, (k, med, p99, mx)
         else:
             assert med <= 2e-3 and mx <= 1e-1, (k, med, p99, mx)
     assert torch.equal(out_sel['z_vals_coarse'].cpu(), ref['z_vals_coarse'])
 
 
-@pytest.mark.parametrize('scene,precision', [('fern_half', 'bf16'), ('fern_half', 'bf16x3'), ('dtu', 'bf16')])
+@pytest.mark.parametrize('scene,precision', [('fern_half', 'bf16'), ('fern_half', 'fp16'), ('fern_half', 'bf16x3'), ('dtu', 'bf16'),
+                                             ('dtu', 'fp16')])
 def test_full_frame_render_vs_oracle_subset(scene, precision, built_library):
     """BASELINE configs 4 / 5: a whole frame (LLFF 504x378 = 190,512 rays; DTU 400x300 = 120,000 rays) generated on
     the device and rendered in one call; a strided 2048-ray subset against the CPU oracle fed the same ray tensors,
@@ -221,7 +227,7 @@ def test_full_frame_render_vs_oracle_subset(scene, precision, built_library):
         ref = O.render(O.synth_state_dict(0), {k: v.cpu() for k, v in sub_batch.items()}, ndc=ndc)
     _assert_rows_bit_identical(out, sub, idx, f'{scene}/{precision}')
     _gate(sub, ref, precision, f'frame_{scene}')
-    if precision == 'bf16':    # "PSNR within 0.05 dB of reference" on the frame's pixels, against a common pseudo-GT
+    if precision in ('bf16', 'fp16'):    # "PSNR within 0.05 dB of reference" on the frame's pixels, against a common pseudo-GT
         g = torch.Generator().manual_seed(0)
         gt = (ref['rgb_fine'] + 0.1 * torch.randn(ref['rgb_fine'].shape, generator=g)).clamp(0, 1)
         assert abs(O.psnr_u8(sub['rgb_fine'].cpu(), gt) - O.psnr_u8(ref['rgb_fine'], gt)) <= 0.05

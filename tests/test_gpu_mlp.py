@@ -41,7 +41,7 @@ def test_mlp_fp32_matches_oracle(scene, S, built_library):
         assert med <= 2e-6, (k, err, med)
 
 
-@pytest.mark.parametrize('precision,tol_max,tol_med', [('bf16x3', 1e-4, 5e-6), ('bf16', 3e-2, 2e-3)])
+@pytest.mark.parametrize('precision,tol_max,tol_med', [('bf16x3', 1e-4, 5e-6), ('bf16', 3e-2, 2e-3), ('fp16', 4e-3, 3e-4)])
 @pytest.mark.parametrize('scene,S', [('fern', 64), ('dtu', 192)])
 def test_mlp_tensor_core_matches_oracle(scene, S, precision, tol_max, tol_med, built_library):
     """tcgen05 MLP vs the fp32 oracle.  bf16x3 (hi/lo split, 3 MMAs) is the parity mode: <= 1e-4 relative.
@@ -59,7 +59,7 @@ def test_mlp_tensor_core_matches_oracle(scene, S, precision, tol_max, tol_med, b
         assert med <= tol_med, (k, err, med)
 
 
-@pytest.mark.parametrize('precision,tol_max,tol_med', [('bf16x3', 1e-4, 5e-6), ('bf16', 3e-2, 2e-3)])
+@pytest.mark.parametrize('precision,tol_max,tol_med', [('bf16x3', 1e-4, 5e-6), ('bf16', 3e-2, 2e-3), ('fp16', 4e-3, 3e-4)])
 @pytest.mark.parametrize('scene,S', [('fern', 192), ('dtu', 64)])
 def test_mlp_tensor_core_secondary_views(scene, S, precision, tol_max, tol_med, built_library):
     """visibility2 on the tensor path (one K=32 MMA step per secondary view on the per-sample direction encodings)
@@ -77,7 +77,7 @@ def test_mlp_tensor_core_secondary_views(scene, S, precision, tol_max, tol_med, 
         assert med <= tol_med, (k, err, med)
 
 
-@pytest.mark.parametrize('precision', ['bf16', 'bf16x3'])
+@pytest.mark.parametrize('precision', ['bf16', 'fp16', 'bf16x3'])
 def test_mlp_tensor_core_matches_emulation(precision, built_library):
     """Against the oracle run with the same operand rounding (bf16 operands / hi-lo split, fp32 accumulate) the
     kernel must agree much more tightly than against fp32: what is left is accumulation order."""

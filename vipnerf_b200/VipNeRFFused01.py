@@ -77,8 +77,8 @@ class VipNeRFFused(torch.nn.Module):
         self.fine_mlp_needed = 'fine_mlp' in model_cfg
         if not self.coarse_mlp_needed:
             raise NotImplementedError('a coarse MLP is required')
-        self.precision = model_cfg.get('precision', 'bf16')   # 'fp32' | 'bf16' | 'bf16x3'
-        if self.precision not in ('fp32', 'bf16', 'bf16x3'):
+        self.precision = model_cfg.get('precision', 'bf16')   # 'fp32' | 'bf16' | 'fp16' | 'bf16x3'
+        if self.precision not in ('fp32', 'bf16', 'fp16', 'bf16x3'):
             raise ValueError(f"configs['model']['precision'] = {self.precision!r}")
         # training arithmetic: 'fp32' (like the reference) or 'tf32' = the 256-wide products of the step on the tensor cores
         if model_cfg.get('train_precision', 'fp32') not in ('fp32', 'tf32'):

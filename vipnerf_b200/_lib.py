@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(HERE, 'libvipnerf_b200.so')
 
 ABI_VERSION = 1
 FLAG_NDC, FLAG_WHITE_BKGD, FLAG_LINDISP, FLAG_TRAIN_TF32 = 1, 2, 4, 8
-PRECISION = {'fp32': 0, 'bf16': 1, 'bf16x3': 2}
+PRECISION = {'fp32': 0, 'bf16': 1, 'bf16x3': 2, 'fp16': 3}
 STATUS_NAMES = {0: 'OK', -1: 'EINVAL', -2: 'EUNSUPPORTED', -3: 'ECUDA', -4: 'EWORKSPACE', -5: 'EABI'}
 
 c_float_p = c_void_p  # device pointers travel as integers

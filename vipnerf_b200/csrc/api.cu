@@ -31,7 +31,9 @@ int fail_cuda(cudaError_t e, const char* what) {
   return fail(VIPNERF_ECUDA, "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
 }
 
-bool is_tc(int precision) { return precision == VIPNERF_PRECISION_BF16 || precision == VIPNERF_PRECISION_BF16X3; }
+bool is_tc(int precision) {
+  return precision == VIPNERF_PRECISION_BF16 || precision == VIPNERF_PRECISION_BF16X3 || precision == VIPNERF_PRECISION_FP16;
+}
 
 int check_cfg(const vipnerf_cfg* cfg) {
   if (cfg == nullptr) return fail(VIPNERF_EINVAL, "cfg is NULL");
@@ -327,7 +329,8 @@ size_t vipnerf_packed_weight_bytes(const vipnerf_cfg* cfg) {
   if (check_cfg(cfg) != VIPNERF_OK) return 0;
   switch (cfg->precision) {
     case VIPNERF_PRECISION_FP32: return kSmallBytes + (size_t)(kFp32BigFloats + kFp32BwdFloats) * sizeof(float);
-    case VIPNERF_PRECISION_BF16: return kSmallBytes + (size_t)kTcBigBytes;
+    case VIPNERF_PRECISION_BF16:
+    case VIPNERF_PRECISION_FP16: return kSmallBytes + (size_t)kTcBigBytes;
     default: return kSmallBytes + (size_t)2 * kTcBigBytes;
   }
 }

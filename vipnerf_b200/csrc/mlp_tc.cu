@@ -87,8 +87,10 @@ enum { kBarWFull = 0, kBarWEmpty = 12, kBarAReady = 24, kBarDReady = 26, kBarRay
 
 // tcgen05 instruction descriptor: D=F32, A=B=BF16, both K-major, M=128, N=n (cute::UMMA::InstrDescriptor bits:
 // c_format[4,6)=1, a_format[7,10)=1, b_format[10,13)=1, n_dim[17,23)=N>>3, m_dim[24,29)=M>>4)
-constexpr uint32_t instr_desc(uint32_t n, uint32_t m = 128) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
+// `half`: A = B = F16 (format 0) instead of BF16 (format 1) - the same kind::f16 instruction at the same rate with an
+// 11-bit instead of an 8-bit significand (VIPNERF_PRECISION_FP16).
+constexpr uint32_t instr_desc(uint32_t n, uint32_t m = 128, bool half = false) {
+  return (1u << 4) | ((half ? 0u : 1u) << 7) | ((half ? 0u : 1u) << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
 }
 
 static_assert(resample_scratch_floats(64, 128) * 4 <= 2048, "ray scratch");
@@ -704,6 +706,14 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&p);
 }
+// two fp32 -> packed 16-bit operands of the tensor core: bf16, or (kHalf) fp16 saturating to +-65504 instead of inf
+template <bool kHalf>
+__device__ __forceinline__ uint32_t pack_op(float lo, float hi) {
+  if (!kHalf) return pack_bf16(lo, hi);
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
 // residual of a packed bf16 pair: (lo, hi) - float(bf16(lo, hi)), packed to bf16 again
 __device__ __forceinline__ uint32_t pack_bf16_residual(float lo, float hi, uint32_t packed) {
   const float rlo = lo - __uint_as_float(packed << 16);
@@ -735,13 +745,18 @@ __device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
   return d;
 }
-template <bool kRelu>
-__device__ __forceinline__ uint32_t cvt_bf16x2(uint64_t v) {  // element 0 (low half of v) -> low 16 bits
+template <bool kRelu, bool kHalf>
+__device__ __forceinline__ uint32_t cvt_op_x2(uint64_t v) {  // element 0 (low half of v) -> low 16 bits
   float lo, hi;
   unpack_f32x2(v, lo, hi);
   uint32_t r;
-  if (kRelu) asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-  else asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  if (kHalf) {
+    if (kRelu) asm("cvt.rn.satfinite.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    else asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  } else {
+    if (kRelu) asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    else asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  }
   return r;
 }
 
@@ -841,7 +856,7 @@ __device__ __forceinline__ void sincos_octave(float t_hi, float t_lo, int k, flo
 // bf16(gamma(point)), 64 columns (63 + the constant 1), packed two per word: enc[0..31] (BF16X3: enc[32..63] = the
 // residuals).  Column order of PositionalEncoder.encode (VipNeRF01.py:439-448): x(3), then per octave sin(3), cos(3).
 // Column 63 is the constant 1 that carries the biases of M0 / M5 through the tensor core (layout.cuh).
-template <bool kSplit3>
+template <bool kSplit3, bool kHalf>
 __device__ __forceinline__ void compute_point_encoding(float x, float y, float z, uint32_t* enc) {
   float v[64];
   v[0] = x; v[1] = y; v[2] = z;
@@ -856,7 +871,7 @@ __device__ __forceinline__ void compute_point_encoding(float x, float y, float z
   v[63] = 1.f;
 #pragma unroll
   for (int q = 0; q < 32; ++q) {
-    enc[q] = pack_bf16(v[2 * q], v[2 * q + 1]);
+    enc[q] = pack_op<kHalf>(v[2 * q], v[2 * q + 1]);
     if (kSplit3) enc[32 + q] = pack_bf16_residual(v[2 * q], v[2 * q + 1], enc[q]);
   }
 }
@@ -877,7 +892,7 @@ __device__ __forceinline__ void store_point_encoding(uint8_t* smem, int slot, in
 // tensor core) (-> ReLU) -> bf16 -> A buffer (in place).  kSigma additionally accumulates the density head on the
 // fp32 activations.  The eight 32-column TMEM loads are software-pipelined: block cb+1 is in flight while block cb
 // is processed (tcgen05.wait::ld waits for everything outstanding, so the next load is issued right after it).
-template <bool kSplit3, bool kRelu, bool kSigma>
+template <bool kSplit3, bool kRelu, bool kSigma, bool kHalf>
 __device__ __forceinline__ float layer_epilogue(uint8_t* smem, int slot, int row, uint32_t taddr,
                                                 const float* __restrict__ w_sigma) {
   float sigma_acc = 0.f;
@@ -906,7 +921,7 @@ __device__ __forceinline__ float layer_epilogue(uint8_t* smem, int slot, int row
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int e = 8 * j + 2 * q;
-          w[q] = cvt_bf16x2<kRelu>(pack_f32x2(__uint_as_float(v[cb & 1][e]), __uint_as_float(v[cb & 1][e + 1])));
+          w[q] = cvt_op_x2<kRelu, kHalf>(pack_f32x2(__uint_as_float(v[cb & 1][e]), __uint_as_float(v[cb & 1][e + 1])));
         }
         const int ch = (cb & 1) * 4 + j;
         st_shared_v4(hi_base + kb_off + (uint32_t)((ch ^ (row & 7)) << 4), w[0], w[1], w[2], w[3]);
@@ -928,7 +943,7 @@ __device__ __forceinline__ float layer_epilogue(uint8_t* smem, int slot, int row
       const int ch = (cb & 1) * 4 + j;
       uint32_t w[4];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) w[q] = pack_bf16(h[8 * j + 2 * q], h[8 * j + 2 * q + 1]);
+      for (int q = 0; q < 4; ++q) w[q] = pack_op<kHalf>(h[8 * j + 2 * q], h[8 * j + 2 * q + 1]);
       const uint32_t off = kb_off + (uint32_t)((ch ^ (row & 7)) << 4);
       st_shared_v4(hi_base + off, w[0], w[1], w[2], w[3]);
       if (kSplit3) {
@@ -1012,7 +1027,7 @@ __device__ __forceinline__ StepDesc step_desc(int st) {
 // bias column, 32 per view) go into its first k-blocks; then per view one K=32 MMA step into TMEM columns [128,256)
 // and an epilogue relu(M9 accumulator + E_v) . w_out[:, 3].  Kept out of line: the eval render without secondary
 // views must not pay registers for it.
-template <bool kSplit3, bool kPair>
+template <bool kSplit3, bool kPair, bool kHalf>
 __device__ __noinline__ void secondary_views(uint8_t* smem, const TcParams& p, const PassDesc& ps, int slot, int row,
                                              int lane, int64_t pg, bool valid, int64_t ray, uint32_t taddr,
                                              uint32_t d_ready_bar, uint32_t a_ready_bar, uint32_t& d_parity) {
@@ -1053,8 +1068,8 @@ __device__ __noinline__ void secondary_views(uint8_t* smem, const TcParams& p, c
       uint32_t w[4], r[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        w[e] = pack_bf16(pe[8 * q + 2 * e], pe[8 * q + 2 * e + 1]);
-        r[e] = pack_bf16_residual(pe[8 * q + 2 * e], pe[8 * q + 2 * e + 1], w[e]);
+        w[e] = pack_op<kHalf>(pe[8 * q + 2 * e], pe[8 * q + 2 * e + 1]);
+        r[e] = kSplit3 ? pack_bf16_residual(pe[8 * q + 2 * e], pe[8 * q + 2 * e + 1], w[e]) : 0u;
       }
       const uint32_t off = (uint32_t)((((v & 1) * 4 + q) ^ (row & 7)) << 4);
       st_shared_v4(hi_base + off, w[0], w[1], w[2], w[3]);
@@ -1088,8 +1103,9 @@ __device__ __noinline__ void secondary_views(uint8_t* smem, const TcParams& p, c
 }
 
 // ------------------------------------------------------------------------------------------ the kernel
-template <bool kSplit3, bool kFused, bool kProf, bool kPair, bool kSec>
+template <bool kSplit3, bool kFused, bool kProf, bool kPair, bool kSec, bool kHalf>
 __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const __grid_constant__ TcParams p) {
+  static_assert(!(kSplit3 && kHalf), "the hi/lo split is a bf16 mode");
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr int kSlots = kSplit3 ? 1 : 2;
   constexpr int kStages = kPair ? kPairStages : kSingleStages;
@@ -1166,7 +1182,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const __grid_const
       // a_ready precedes every MMA of the CTA pair
       if (slot == 0) {
         uint32_t* ones = reinterpret_cast<uint32_t*>(smem + kOffOnes);
-        for (int i = row; i < (int)(kOnesBytes / 4); i += 128) ones[i] = 0x3F803F80u;   // two bf16 1.0
+        for (int i = row; i < (int)(kOnesBytes / 4); i += 128) ones[i] = kHalf ? 0x3C003C00u : 0x3F803F80u;   // two bf16 (fp16) 1.0
       }
       // This row's packed point encoding: computed ahead of time (during M6 of the previous tile), stored into k-block 0
       // at the tile boundary and once more for the encoding part of the skip layer M5.
@@ -1192,7 +1208,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const __grid_const
         const float px = fadd(p.rp.pts_o[3 * ray + 0], fmul(p.rp.pts_d[3 * ray + 0], zv));
         const float py = fadd(p.rp.pts_o[3 * ray + 1], fmul(p.rp.pts_d[3 * ray + 1], zv));
         const float pz = fadd(p.rp.pts_o[3 * ray + 2], fmul(p.rp.pts_d[3 * ray + 2], zv));
-        compute_point_encoding<kSplit3>(px, py, pz, enc);
+        compute_point_encoding<kSplit3, kHalf>(px, py, pz, enc);
         if (kProf) c_enc += clock64() - t0;
       };
       // enc -> k-block 0 of the slot's (idle) activation buffer, visible to the tensor core, then a_ready
@@ -1293,9 +1309,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const __grid_const
           tc_fence_after();
           const long long t1 = kProf ? clock64() : 0;
           c_wait += t1 - t0;
-          if (l == 7) sigma_lin = layer_epilogue<kSplit3, true, true>(smem, slot, row, taddr, small + kOffWSigma);
-          else if (l == 8) layer_epilogue<kSplit3, false, false>(smem, slot, row, taddr, nullptr);
-          else layer_epilogue<kSplit3, true, false>(smem, slot, row, taddr, nullptr);
+          if (l == 7) sigma_lin = layer_epilogue<kSplit3, true, true, kHalf>(smem, slot, row, taddr, small + kOffWSigma);
+          else if (l == 8) layer_epilogue<kSplit3, false, false, kHalf>(smem, slot, row, taddr, nullptr);
+          else layer_epilogue<kSplit3, true, false, kHalf>(smem, slot, row, taddr, nullptr);
           fence_proxy_async();
           tc_fence_before();
           arrive_a_ready();
@@ -1325,7 +1341,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const __grid_const
           ps.vis[pg] = sigmoidf<kSplit3>(o[3] + small[kOffBOut + 3]);
         }
         if (kSec)   // compile-time: the eval render without secondary views pays nothing for this path
-          secondary_views<kSplit3, kPair>(smem, p, ps, slot, row, lane, pg, valid, ray, taddr, bar(kBarDReady + slot),
+          secondary_views<kSplit3, kPair, kHalf>(smem, p, ps, slot, row, lane, pg, valid, ray, taddr, bar(kBarDReady + slot),
                                           a_ready_bar, d_parity);
         if (kProf) c_view += clock64() - t1;
         if (kFused) {
@@ -1438,7 +1454,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const __grid_const
           if (s == 0) a_parity0 ^= 1; else a_parity1 ^= 1;
           tc_fence_after();
           const StepDesc sd = step_desc(st);
-          const uint32_t idesc = instr_desc(layer_n(sd.layer), kPair ? 256 : 128);
+          const uint32_t idesc = instr_desc(layer_n(sd.layer), kPair ? 256 : 128, kHalf);
           const uint32_t d_tmem = tmem_base + (uint32_t)(s * 256) + sd.d_col;
           const uint64_t a_hi = a_desc0 + (kSplit3 ? 0 : s) * kAUnits + sd.a_units, a_lo = a_desc0 + kAUnits + sd.a_units;
           if (!kSplit3 && !kPair) issue_chunks(ring, d_tmem, a_hi, w_desc0, bar_full0, bar_empty0, sd.n_chunks, sd.accumulate, idesc);
@@ -1532,7 +1548,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const __grid_const
 std::mutex g_attr_mutex;
 unsigned long long* g_prof_buffer = nullptr;  // debug: set by vipnerf_debug_set_profile_buffer
 int g_sm_count[64] = {0};
-bool g_attr_set[64][32] = {{false}};
+bool g_attr_set[64][64] = {{false}};
 // CTA-pair (cta_group::2) kernels unless VIPNERF_TC_CTA_PAIRS=0 (read once)
 const bool g_use_cta_pairs = []() { const char* e = getenv("VIPNERF_TC_CTA_PAIRS"); return e == nullptr || e[0] != '0'; }();
 
@@ -1584,16 +1600,16 @@ cudaError_t encode_weight_maps(const uint8_t* packed, bool split3, CUtensorMap (
   return cudaSuccess;
 }
 
-template <bool kSplit3, bool kFused, bool kProf, bool kPair, bool kSec>
+template <bool kSplit3, bool kFused, bool kProf, bool kPair, bool kSec, bool kHalf = false>
 cudaError_t launch_variant(const TcParams& p, int64_t n_units, cudaStream_t s) {
   int dev = 0, sms = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
   if ((e = device_sm_count(&sms)) != cudaSuccess) return e;
-  auto kernel = k_render_tc<kSplit3, kFused, kProf, kPair, kSec>;
+  auto kernel = k_render_tc<kSplit3, kFused, kProf, kPair, kSec, kHalf>;
   {
     std::lock_guard<std::mutex> lock(g_attr_mutex);
-    const int variant = (kSplit3 ? 2 : 0) + (kFused ? 1 : 0) + (kProf ? 4 : 0) + (kPair ? 8 : 0) + (kSec ? 16 : 0);
+    const int variant = (kSplit3 ? 2 : 0) + (kFused ? 1 : 0) + (kProf ? 4 : 0) + (kPair ? 8 : 0) + (kSec ? 16 : 0) + (kHalf ? 32 : 0);
     if (dev >= 64 || !g_attr_set[dev][variant]) {
       e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
       if (e != cudaSuccess) return e;
@@ -1621,15 +1637,19 @@ cudaError_t launch_variant(const TcParams& p, int64_t n_units, cudaStream_t s) {
   return cudaLaunchKernelEx(&cfg, kernel, p);
 }
 
-template <bool kSplit3, bool kFused>
+template <bool kSplit3, bool kFused, bool kHalf = false>
 cudaError_t launch(TcParams& p, int64_t n_units, cudaStream_t s) {
-  const bool pair = g_use_cta_pairs;
+  const bool pair = g_use_cta_pairs || kHalf;   // fp16 operands: CTA-pair kernels only
   { const char* e = getenv("VIPNERF_TC_DEBUG_NORING"); p.debug_noring = (e != nullptr && pair && !kSplit3) ? atoi(e) : 0; }
   if (pair) {
     for (int pi = 0; pi < 2; ++pi) {
       const cudaError_t e = encode_weight_maps(p.pass[pi].packed, kSplit3, p.wmap[pi], p.debug_noring == 3 ? 8 : 1);
       if (e != cudaSuccess) return e;
     }
+  }
+  if (kHalf) {   // fp16 operands: CTA pairs, no profiling variant
+    return p.fl.n_sec_views > 0 ? launch_variant<false, kFused, false, true, true, true>(p, n_units, s)
+                                : launch_variant<false, kFused, false, true, false, true>(p, n_units, s);
   }
   if (p.fl.n_sec_views > 0) {   // secondary views: separate instantiations (no profiling variant)
     return pair ? launch_variant<kSplit3, kFused, false, true, true>(p, n_units, s)
@@ -1672,6 +1692,7 @@ cudaError_t launch_mlp_tc(int precision, const RayPtrs& rp, const RenderFlags& f
   p.prof = g_prof_buffer;
   if (p.n_units == 0) return cudaSuccess;
   if (precision == VIPNERF_PRECISION_BF16X3) return launch<true, false>(p, p.n_units, s);
+  if (precision == VIPNERF_PRECISION_FP16) return launch<false, false, true>(p, p.n_units, s);
   return launch<false, false>(p, p.n_units, s);
 }
 
@@ -1704,6 +1725,7 @@ cudaError_t launch_render_fused_tc(int precision, const FusedArgs& a, cudaStream
   p.n_units = (a.n_rays + 1) / 2;
   p.prof = g_prof_buffer;
   if (precision == VIPNERF_PRECISION_BF16X3) return launch<true, true>(p, p.n_units, s);
+  if (precision == VIPNERF_PRECISION_FP16) return launch<false, true, true>(p, p.n_units, s);
   return launch<false, true>(p, p.n_units, s);
 }
 

@@ -1,5 +1,6 @@
 // Weight packing, coarse sample placement and the stand-alone compositing / re-sampling kernel.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "kernels.h"
 #include "layout.cuh"
@@ -74,7 +75,7 @@ __global__ void k_pack_fp32_bwd(ParamPtrs pp, float* __restrict__ bwd) {
   bwd[i] = v;
 }
 
-template <bool kSplit3>
+template <bool kSplit3, bool kHalf = false>
 __global__ void k_pack_tc(ParamPtrs pp, uint8_t* __restrict__ big) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;  // one bf16 element of the hi image set
   if (i >= kTcBigBytes / 2) return;
@@ -98,6 +99,10 @@ __global__ void k_pack_tc(ParamPtrs pp, uint8_t* __restrict__ big) {
   const uint32_t byte = n * 64 + ((((k_local >> 3) ^ ((n >> 1) & 3))) << 4) + (k_local & 7) * 2;
   const size_t chunk_bytes = (size_t)layer_chunk_bytes(l);
   const size_t base = (size_t)tc_layer_byte_offset(l) * (kSplit3 ? 2 : 1);
+  if (kHalf) {   // fp16 image (VIPNERF_PRECISION_FP16): saturate instead of overflowing to inf
+    *reinterpret_cast<__half*>(big + base + chunk * chunk_bytes + byte) = __float2half_rn(fminf(fmaxf(w, -65504.f), 65504.f));
+    return;
+  }
   const __nv_bfloat16 hi = __float2bfloat16_rn(w);
   if (!kSplit3) {
     *reinterpret_cast<__nv_bfloat16*>(big + base + chunk * chunk_bytes + byte) = hi;
@@ -120,6 +125,7 @@ cudaError_t launch_pack_weights(int precision, const float* const params_dev[24]
   } else {
     const int n = kTcBigBytes / 2;
     if (precision == VIPNERF_PRECISION_BF16X3) k_pack_tc<true><<<(n + 255) / 256, 256, 0, s>>>(pp, big);
+    else if (precision == VIPNERF_PRECISION_FP16) k_pack_tc<false, true><<<(n + 255) / 256, 256, 0, s>>>(pp, big);
     else k_pack_tc<false><<<(n + 255) / 256, 256, 0, s>>>(pp, big);
   }
   return cudaGetLastError();
