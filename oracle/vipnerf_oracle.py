@@ -268,12 +268,20 @@ def mlp_forward(params: Dict[str, torch.Tensor], pts: torch.Tensor, view_dirs: t
     if sigma_noise is not None:
         sigma_raw = sigma_raw + sigma_noise
     sigma = F.relu(sigma_raw)
-    feature = linear(h, params['feature_linear.weight'], params['feature_linear.bias'], mode)
-
     wv, bv = params['views_linears.0.weight'], params['views_linears.0.bias']
     wo, bo = params['views_output_linear.weight'], params['views_output_linear.bias']
-    n_feat = feature.shape[-1]
-    feat_part = linear(feature, wv[:, :n_feat], None, mode) if mode != 'fp32' else None
+    n_feat = params['feature_linear.weight'].shape[0]
+    if mode == 'fp32':
+        feature = F.linear(h, params['feature_linear.weight'], params['feature_linear.bias'])
+        feat_part = None
+    else:
+        # the tensor-core kernels fold feature_linear (no activation, :564) into the feature columns of views_linears.0:
+        # Wv_f (W8 h + b8) = (Wv_f W8) h + Wv_f b8, the product matrix formed in double precision at pack time
+        # (vipnerf_b200/csrc/layout.cuh); `feature` itself is not an output (:533-534)
+        wf = (wv[:, :n_feat].double() @ params['feature_linear.weight'].double()).float()
+        bv = (bv.double() + wv[:, :n_feat].double() @ params['feature_linear.bias'].double()).float()
+        feature = None
+        feat_part = linear(h, wf, None, mode)
 
     def view_head(enc_view, feat, feat_pre, secondary=False):
         if mode == 'fp32':
@@ -290,7 +298,7 @@ def mlp_forward(params: Dict[str, torch.Tensor], pts: torch.Tensor, view_dirs: t
     result = {'sigma': sigma, 'rgb': out[..., :3], 'visibility': out[..., 3:4]}
     if view_dirs2 is not None:
         v = view_dirs2.shape[1]
-        feat_v = feature[:, None, :].expand(-1, v, -1)
+        feat_v = feature[:, None, :].expand(-1, v, -1) if feature is not None else None
         feat_pre_v = feat_part[:, None, :].expand(-1, v, -1) if feat_part is not None else None
         out2 = view_head(positional_encoding(view_dirs2, l_view), feat_v, feat_pre_v, secondary=True)
         result['visibility2'] = out2[..., 3:4]

@@ -44,9 +44,10 @@ def test_config_validation(built_library):
     lib = _lib.load()
     ok = _lib.make_cfg(precision='bf16')
     assert lib.vipnerf_check_config(ctypes.byref(ok)) == 0
-    assert lib.vipnerf_packed_weight_bytes(ctypes.byref(ok)) == 27648 + (72 + 7) * 16384 + 8192   # 76 weight chunks (8 half-size) + 7 bias chunks + the view-direction chunk
+    assert lib.vipnerf_packed_weight_bytes(ctypes.byref(ok)) == 27648 + (64 + 6) * 16384 + 8192   # 68 weight chunks (8 half-size; feature_linear is folded into M9) + 6 bias chunks + the view-direction chunk
+    assert lib.vipnerf_packed_weight_bytes(ctypes.byref(_lib.make_cfg(precision='fp16'))) == 27648 + (64 + 6) * 16384 + 8192
     x3 = _lib.make_cfg(precision='bf16x3')
-    assert lib.vipnerf_packed_weight_bytes(ctypes.byref(x3)) == 27648 + 2 * ((72 + 7) * 16384 + 8192)
+    assert lib.vipnerf_packed_weight_bytes(ctypes.byref(x3)) == 27648 + 2 * ((64 + 6) * 16384 + 8192)
     f32 = _lib.make_cfg(precision='fp32')
     assert lib.vipnerf_packed_weight_bytes(ctypes.byref(f32)) == 27648 + (589824 + 589824) * 4   # forward images + [out][in] images (backward-data chain, tensor-core forward)
     # training buffers: fp32 only; about 11 KB of saved activations per sample point

@@ -44,7 +44,10 @@ constexpr int kOffBSigma = kOffWSigma + 256;         // [4]    pts_output_linear
 constexpr int kOffWViewDir = kOffBSigma + 4;         // [27][128] views_linears.0.weight[:, 256+j] transposed
 constexpr int kOffWOut = kOffWViewDir + 27 * 128;    // [128][4]  views_output_linear.weight transposed
 constexpr int kOffBOut = kOffWOut + 128 * 4;         // [4]    views_output_linear.bias
-constexpr int kSmallFloats = kOffBOut + 4;
+// tensor-core kernels (feature_linear folded into views_linears.0, see below): views_linears.0.bias +
+// views_linears.0.weight[:, :256] . feature_linear.bias
+constexpr int kOffBiasViewsFused = kOffBOut + 4;     // [128]
+constexpr int kSmallFloats = kOffBiasViewsFused + 128;
 constexpr int kSmallBytes = ((kSmallFloats * 4 + 1023) / 1024) * 1024;  // keep the big region 1 KiB aligned
 
 // ---- fp32 big region: per matrix layer the transposed weight Wt[k][n] (k = A column), floats
@@ -82,15 +85,24 @@ __host__ __device__ constexpr int layer_chunks(int l) { return layer_k(l) / kChu
 // bias, consumed by ONE K=16 MMA against the last 16 encoding columns.  M9's bias travels with the
 // view-direction term (fp32, per ray).  In bf16 mode the bias is therefore rounded to bf16; in BF16X3 mode the
 // lo image carries its residual.
-__host__ __device__ constexpr bool layer_has_bias_chunk(int l) { return l != 0 && l != 5 && l < 9; }
-__host__ __device__ constexpr int layer_stream_chunks(int l) { return layer_chunks(l) + (layer_has_bias_chunk(l) ? 1 : 0); }
+//
+// feature_linear (M8) has NO activation (VipNeRF01.py:564) and its output feeds only views_linears.0 (:576-579; the
+// `feature` tensor itself is dropped, :533-534), so on the tensor path the two are ONE layer:
+//   views_linears.0[:, :256] . (W8 h7 + b8) = (Wv_f W8) h7 + Wv_f b8
+// The packer forms Wv_f W8 [128 x 256] in double precision and stores it as "M9"; Wv_f b8 joins the views bias
+// (kOffBiasViewsFused).  The tensor-core stream therefore has no M8 chunks: 2,112 of 18,432 tensor cycles per tile and
+// one epilogue pass less.  (The fp32 kernels and the training path keep the two layers apart.)
+__host__ __device__ constexpr bool layer_has_bias_chunk(int l) { return l != 0 && l != 5 && l < 8; }
+__host__ __device__ constexpr int layer_stream_chunks(int l) {
+  return l == 8 ? 0 : layer_chunks(l) + (layer_has_bias_chunk(l) ? 1 : 0);
+}
 __host__ __device__ constexpr int layer_chunk_bytes(int l) { return layer_n(l) * kChunkK * 2; }
 __host__ __device__ constexpr int tc_layer_byte_offset(int l) {    // of the hi image set
   int off = 0;
   for (int i = 0; i < l; ++i) off += layer_stream_chunks(i) * layer_chunk_bytes(i);
   return off;
 }
-constexpr int kTcBigBytes = tc_layer_byte_offset(kNumTcLayers);    // 1,302,528 (76 weight + 7 bias chunks + the view-direction chunk)
+constexpr int kTcBigBytes = tc_layer_byte_offset(kNumTcLayers);    // 1,155,072 (68 weight + 6 bias chunks + the view-direction chunk)
 
 // Maps A column k of matrix layer l to the source weight column (or -1 for a zero pad column).
 __host__ __device__ inline int source_col(int l, int k) {

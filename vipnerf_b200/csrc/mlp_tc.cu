@@ -999,7 +999,7 @@ __device__ __forceinline__ void view_epilogue(uint32_t taddr, const float* vb_ro
 // columns of k-block v/2, written by the epilogue group once M9 has retired) x the view-direction chunk, into TMEM
 // columns [128,256) of the slot - M9's accumulator (columns [0,128)) stays in place and is re-read for every view.
 // Every step ends with a d_ready commit and starts with an a_ready wait.
-constexpr int kNumBaseSteps = 11;
+constexpr int kNumBaseSteps = 10;
 struct StepDesc {
   int layer;            // matrix layer M0..M9 / kViewChunkLayer (layout.cuh)
   uint32_t first_chunk; // first weight chunk of the layer's stream used by the step
@@ -1017,7 +1017,7 @@ __device__ __forceinline__ StepDesc step_desc(int st) {
     const uint32_t v = (uint32_t)(st - kNumBaseSteps);
     return {kViewChunkLayer, 0, 1, 0, false, (v >> 1) * (kKBlockBytes >> 4) + (v & 1) * 4, 128};
   }
-  const int l = st < 5 ? st : st - 1;
+  const int l = st < 5 ? st : (st == 9 ? 9 : st - 1);   // 7 -> M6, 8 -> M7, 9 -> M9 (feature_linear folded in, layout.cuh)
   return {l, 0, 8, 0, layer_has_bias_chunk(l), 0, 0};
 }
 
@@ -1240,7 +1240,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const __grid_const
         float w[kEncView];
 #pragma unroll
         for (int j = 0; j < kEncView; ++j) w[j] = __ldg(small + kOffWViewDir + j * 128 + row);
-        float a0 = small[kOffBiasViews + row], a1 = a0;
+        float a0 = small[kOffBiasViewsFused + row], a1 = a0;
         group_sync(group);
 #pragma unroll
         for (int j = 0; j < kEncView; ++j) {
@@ -1293,7 +1293,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const __grid_const
 
         float sigma_lin = 0.f;
 #pragma unroll 1
-        for (int l = 0; l < 9; ++l) {
+        for (int l = 0; l < 8; ++l) {
           if (l == 5) {
             // skip layer M5 = h4 part (K=256, issued on a_ready(M4's epilogue)) + encoding part (K=64, carries the bias):
             // when the h4 part has retired, k-block 0 is free to take the encoding back
@@ -1310,7 +1310,6 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const __grid_const
           const long long t1 = kProf ? clock64() : 0;
           c_wait += t1 - t0;
           if (l == 7) sigma_lin = layer_epilogue<kSplit3, true, true, kHalf>(smem, slot, row, taddr, small + kOffWSigma);
-          else if (l == 8) layer_epilogue<kSplit3, false, false, kHalf>(smem, slot, row, taddr, nullptr);
           else layer_epilogue<kSplit3, true, false, kHalf>(smem, slot, row, taddr, nullptr);
           fence_proxy_async();
           tc_fence_before();

@@ -11,6 +11,20 @@ struct ParamPtrs { const float* p[24]; };
 
 // ---------------------------------------------------------------------------------------------------
 // pack: reference nn.Linear tensors (VipNeRF01.py:472-491, [out,in] row-major fp32) -> kernel layout
+// feature_linear folded into views_linears.0 (layout.cuh): bias and weight of the fused 256 -> 128 layer, formed in
+// double precision from the fp32 masters (p[16] = views_linears.0.weight [128][283], p[17] its bias,
+// p[20] = feature_linear.weight [256][256], p[21] its bias)
+__device__ __forceinline__ float fused_views_bias(const ParamPtrs& pp, int n) {
+  double acc = (double)pp.p[17][n];
+  for (int j = 0; j < kWidth; ++j) acc += (double)pp.p[16][n * (kWidth + kEncView) + j] * (double)pp.p[21][j];
+  return (float)acc;
+}
+__device__ __forceinline__ float fused_views_weight(const ParamPtrs& pp, int n, int k) {
+  double acc = 0.0;
+  for (int j = 0; j < kWidth; ++j) acc += (double)pp.p[16][n * (kWidth + kEncView) + j] * (double)pp.p[20][j * kWidth + k];
+  return (float)acc;
+}
+
 __global__ void k_pack_small(ParamPtrs pp, float* __restrict__ small) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= kSmallFloats) return;
@@ -30,8 +44,10 @@ __global__ void k_pack_small(ParamPtrs pp, float* __restrict__ small) {
   } else if (i < kOffBOut) {
     const int c = (i - kOffWOut) / 4, k = (i - kOffWOut) % 4;
     v = pp.p[22][k * 128 + c];
-  } else {
+  } else if (i < kOffBiasViewsFused) {
     v = pp.p[23][i - kOffBOut];
+  } else {
+    v = fused_views_bias(pp, i - kOffBiasViewsFused);
   }
   small[i] = v;
 }
@@ -88,13 +104,13 @@ __global__ void k_pack_tc(ParamPtrs pp, uint8_t* __restrict__ big) {
   float w;
   if (l == kViewChunkLayer) {                             // view-direction columns of views_linears.0, bias in column 31
     w = k_local < kEncView ? pp.p[16][n * (kWidth + kEncView) + kWidth + k_local]
-                           : (k_local == kChunkK - 1 ? pp.p[17][n] : 0.f);
+                           : (k_local == kChunkK - 1 ? fused_views_bias(pp, n) : 0.f);
   } else if (chunk == layer_chunks(l)) {                         // the layer's bias chunk: column 31 <-> encoding column 63
     w = k_local == kChunkK - 1 ? pp.p[bias_param(l)][n] : 0.f;
   } else {
     const int k = chunk * kChunkK + k_local;
     const bool bias_col = (l == 0 || l == 5) && k == 63;  // the encoding block's constant-one column
-    w = bias_col ? pp.p[bias_param(l)][n] : source_weight(pp, l, n, k);
+    w = bias_col ? pp.p[bias_param(l)][n] : (l == 9 ? fused_views_weight(pp, n, k) : source_weight(pp, l, n, k));
   }
   const uint32_t byte = n * 64 + ((((k_local >> 3) ^ ((n >> 1) & 3))) << 4) + (k_local & 7) * 2;
   const size_t chunk_bytes = (size_t)layer_chunk_bytes(l);
