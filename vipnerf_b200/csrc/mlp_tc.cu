@@ -65,6 +65,11 @@ constexpr uint32_t kOffA = 0;                 // 2 x 64 KiB
 constexpr uint32_t kOffW = 131072;            // weight ring (88 KiB used) + the ray warp's re-sampling scratch
 constexpr uint32_t kRingBytes = 98304;
 constexpr uint32_t kOffRayScratch = kOffW + 90112;   // 2 KiB (resample_scratch_floats(64, 128) = 384 floats)
+// Small fp32 head parameters of BOTH passes' MLPs, staged once per CTA (they were __ldg loads from a ~28 KiB L1 that
+// the per-tile global traffic keeps evicting: every miss is an L2 round trip inside the view epilogue's dependency
+// chain): per pass views_output_linear.weight^T [128][4] (2 KiB) and pts_output_linear.weight [256] (1 KiB).
+constexpr uint32_t kOffHead = kOffW + 92160;         // 2 x 3 KiB
+constexpr uint32_t kHeadFloats = 768;                // per pass: [0,512) W_out^T, [512,768) w_sigma
 constexpr uint32_t kOffTail = kOffW + kRingBytes;
 constexpr uint32_t kOffBar = kOffTail;        // up to 32 mbarriers
 constexpr uint32_t kOffRayDone = kOffTail + 256;  // [2 slots] u32: per-ray events the slot's ray warp has completed
@@ -72,16 +77,16 @@ constexpr uint32_t kOffTmemPtr = kOffTail + 264;
 constexpr uint32_t kOffVb = kOffTail + 272;   // [2 slots][2 rays][128] fp32: view-direction part of M9 + bias
 constexpr uint32_t kOffPev = kOffVb + 2048;   // [2 slots][2 rays][32]  fp32: view-direction encodings
 #ifdef VIPNERF_ONES_4K
-constexpr uint32_t kOffOnes = kOffW + 90112 + 2048;  // 4 KiB of bf16 1.0 behind the (shorter) ring
-constexpr uint32_t kOnesBytes = 4096;
-constexpr uint32_t kSmemBytes = kOffPev + 512;
+#error "VIPNERF_ONES_4K is no longer supported (its 4 KiB now hold the staged head parameters)"
 #else
 constexpr uint32_t kOffOnes = kOffPev + 512;  // 128 B of bf16 1.0: the A operand of the bias chunks
 constexpr uint32_t kOnesBytes = 128;
-constexpr uint32_t kSmemBytes = kOffOnes + 128;
+constexpr uint32_t kOffHeadBias = kOffOnes + 128;   // [2 passes][8] fp32: views_output_linear.bias (4), pts_output_linear.bias
+constexpr uint32_t kSmemBytes = kOffHeadBias + 64;
 #endif
 static_assert(kSmemBytes <= 232448, "exceeds the 227 KiB per-CTA shared memory limit");
 static_assert(kPairStages * 8192 <= 90112 && kSingleStages * 16384 <= 90112, "weight ring does not fit");
+static_assert(kOffHead + 2 * kHeadFloats * 4 <= kOffTail, "head parameters do not fit");
 
 enum { kBarWFull = 0, kBarWEmpty = 12, kBarAReady = 24, kBarDReady = 26, kBarRayFull = 28 };
 
@@ -894,7 +899,7 @@ __device__ __forceinline__ void store_point_encoding(uint8_t* smem, int slot, in
 // is processed (tcgen05.wait::ld waits for everything outstanding, so the next load is issued right after it).
 template <bool kSplit3, bool kRelu, bool kSigma, bool kHalf>
 __device__ __forceinline__ float layer_epilogue(uint8_t* smem, int slot, int row, uint32_t taddr,
-                                                const float* __restrict__ w_sigma) {
+                                                const float* w_sigma /* shared */) {
   float sigma_acc = 0.f;
   const uint32_t hi_base = smem_u32(smem + kOffA + (kSplit3 ? 0 : slot) * kABytes) + row * 128;
   const uint32_t lo_base = smem_u32(smem + kOffA + kABytes) + row * 128;
@@ -906,7 +911,7 @@ __device__ __forceinline__ float layer_epilogue(uint8_t* smem, int slot, int row
     if (kSigma) {
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
-        const float4 t = __ldg(reinterpret_cast<const float4*>(w_sigma + cb * 32) + q);
+        const float4 t = *(reinterpret_cast<const float4*>(w_sigma + cb * 32) + q);   // shared memory (kOffHead)
         ws[4 * q] = t.x; ws[4 * q + 1] = t.y; ws[4 * q + 2] = t.z; ws[4 * q + 3] = t.w;
       }
     }
@@ -960,7 +965,7 @@ __device__ __forceinline__ float layer_epilogue(uint8_t* smem, int slot, int row
 // M9 epilogue for one row: relu(acc + (bias + view-direction part)) . views_output_linear -> 4 logits.
 // Four independent accumulator pairs (one per 32-column block, interleaved even/odd columns) keep the FFMA2
 // dependency chains short; they are summed at the end.
-__device__ __forceinline__ void view_epilogue(uint32_t taddr, const float* vb_row, const float* __restrict__ w_out,
+__device__ __forceinline__ void view_epilogue(uint32_t taddr, const float* vb_row, const float* w_out /* shared */,
                                               float (&o)[4]) {
   uint64_t acc01[4], acc23[4];
 #pragma unroll
@@ -980,7 +985,7 @@ __device__ __forceinline__ void view_epilogue(uint32_t taddr, const float* vb_ro
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
       const float h = fmaxf(__uint_as_float(v[cb & 1][j]) + b[j], 0.f);
-      const float4 w = __ldg(reinterpret_cast<const float4*>(w_out) + cb * 32 + j);
+      const float4 w = *(reinterpret_cast<const float4*>(w_out) + cb * 32 + j);
       const uint64_t hh = pack_f32x2(h, h);
       acc01[j & 3] = ffma2(hh, pack_f32x2(w.x, w.y), acc01[j & 3]);
       acc23[j & 3] = ffma2(hh, pack_f32x2(w.z, w.w), acc23[j & 3]);
@@ -1019,6 +1024,22 @@ __device__ __forceinline__ StepDesc step_desc(int st) {
   }
   const int l = st < 5 ? st : (st == 9 ? 9 : st - 1);   // 7 -> M6, 8 -> M7, 9 -> M9 (feature_linear folded in, layout.cuh)
   return {l, 0, 8, 0, layer_has_bias_chunk(l), 0, 0};
+}
+
+// tc_layer_byte_offset for a run-time layer index without the run-time loop (the producer lanes evaluated it per step)
+__device__ __forceinline__ uint32_t tc_layer_offset_rt(int l) {
+  switch (l) {
+    case 0: return tc_layer_byte_offset(0);
+    case 1: return tc_layer_byte_offset(1);
+    case 2: return tc_layer_byte_offset(2);
+    case 3: return tc_layer_byte_offset(3);
+    case 4: return tc_layer_byte_offset(4);
+    case 5: return tc_layer_byte_offset(5);
+    case 6: return tc_layer_byte_offset(6);
+    case 7: return tc_layer_byte_offset(7);
+    case 9: return tc_layer_byte_offset(9);
+    default: return tc_layer_byte_offset(kViewChunkLayer);
+  }
 }
 
 // Visibility of this row's sample from each secondary view (VipNeRF01.py:218-226, :527-530): the same hidden layer
@@ -1078,7 +1099,8 @@ __device__ __noinline__ void secondary_views(uint8_t* smem, const TcParams& p, c
   }
   fence_proxy_async();
   arrive_a_ready();
-  const float b3 = small[kOffBOut + 3];
+  const float* head = reinterpret_cast<const float*>(smem + kOffHead) + (&ps == &p.pass[1] ? kHeadFloats : 0);
+  const float b3 = reinterpret_cast<const float*>(smem + kOffHeadBias)[(&ps == &p.pass[1] ? 8 : 0) + 3];
   for (int v = 0; v < V; ++v) {
     mbar_wait(d_ready_bar, d_parity);
     d_parity ^= 1;
@@ -1093,7 +1115,7 @@ __device__ __noinline__ void secondary_views(uint8_t* smem, const TcParams& p, c
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         const float h = fmaxf(__uint_as_float(f[j]) + __uint_as_float(e[j]), 0.f);
-        acc = fmaf(h, __ldg(small + kOffWOut + 4 * (cb * 32 + j) + 3), acc);
+        acc = fmaf(h, head[4 * (cb * 32 + j) + 3], acc);
       }
     }
     tc_fence_before();
@@ -1134,6 +1156,19 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const __grid_const
       reinterpret_cast<volatile uint32_t*>(smem + kOffRayDone)[s] = 0;
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  {
+    float* head = reinterpret_cast<float*>(smem + kOffHead);
+    for (int i = threadIdx.x; i < 2 * (int)kHeadFloats; i += kNumThreads) {
+      const float* small = reinterpret_cast<const float*>(p.pass[i / kHeadFloats].packed);
+      const int j = i % kHeadFloats;
+      head[i] = j < 512 ? small[kOffWOut + j] : small[kOffWSigma + j - 512];
+    }
+    if (threadIdx.x < 16) {
+      const float* small = reinterpret_cast<const float*>(p.pass[threadIdx.x >> 3].packed);
+      const int j = threadIdx.x & 7;
+      reinterpret_cast<float*>(smem + kOffHeadBias)[threadIdx.x] = j < 4 ? small[kOffBOut + j] : (j == 4 ? small[kOffBSigma] : 0.f);
+    }
   }
   if (warp == 9) {
     if (kPair) {
@@ -1285,7 +1320,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const __grid_const
         const bool valid = pg < ps.n_points;
         const int64_t ray = (valid ? pg : ps.n_points - 1) / ps.S;
         const int64_t ray_first = min((tile * kTile) / ps.S, p.n_rays - 1);
-        const float* small = reinterpret_cast<const float*>(ps.packed);
+        const float* head = reinterpret_cast<const float*>(smem + kOffHead) + pi * kHeadFloats;
+        const float* head_bias = reinterpret_cast<const float*>(smem + kOffHeadBias) + pi * 8;
         // the next item's depths exist unless it is the fine tile of the pair whose coarse tile is this item
         const bool has_next = it + 1 < work.n_items;
         // (checked again, without blocking, right before the prefetch)
@@ -1297,6 +1333,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const __grid_const
           if (l == 5) {
             // skip layer M5 = h4 part (K=256, issued on a_ready(M4's epilogue)) + encoding part (K=64, carries the bias):
             // when the h4 part has retired, k-block 0 is free to take the encoding back
+            // The per-ray view-direction term of this tile's M9 is computed HERE, in the shadow of M5's 2048 tensor
+            // cycles the thread would otherwise spend waiting (vb / pev are free: the previous tile's M9 epilogue is done).
+            view_bias_item(it);
             const long long tw = kProf ? clock64() : 0;
             mbar_wait(bar(kBarDReady + slot), d_parity);
             d_parity ^= 1;
@@ -1309,16 +1348,14 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const __grid_const
           tc_fence_after();
           const long long t1 = kProf ? clock64() : 0;
           c_wait += t1 - t0;
-          if (l == 7) sigma_lin = layer_epilogue<kSplit3, true, true, kHalf>(smem, slot, row, taddr, small + kOffWSigma);
+          if (l == 7) sigma_lin = layer_epilogue<kSplit3, true, true, kHalf>(smem, slot, row, taddr, head + 512);
           else layer_epilogue<kSplit3, true, false, kHalf>(smem, slot, row, taddr, nullptr);
           fence_proxy_async();
           tc_fence_before();
           arrive_a_ready();
           if (kProf) c_epi += clock64() - t1;
           if (l == 5) {
-            // M5 has retired: enc is free for the next tile's encoding, and so are vb/pev (the previous tile's M9
-            // epilogue is long done).  Use the time this slot's M6 spends on the tensor pipe.
-            view_bias_item(it);
+            // M5 has retired: enc is free for the next tile's encoding.  Use the time this slot's M6 spends on the tensor pipe.
             if (has_next && depths_ready(it + 1)) { encode_item(it + 1); next_encoded = true; }
           }
         }
@@ -1329,15 +1366,15 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const __grid_const
         const long long t1 = kProf ? clock64() : 0;
         c_wait += t1 - t0;
         float o[4];
-        if (!(p.debug_noring & 8)) view_epilogue(taddr, vb + (int)(ray - ray_first) * 128, small + kOffWOut, o);
+        if (!(p.debug_noring & 8)) view_epilogue(taddr, vb + (int)(ray - ray_first) * 128, head, o);
         else { o[0] = o[1] = o[2] = o[3] = 0.f; }
         tc_fence_before();  // orders this tile's last tcgen05.ld before the next tile's first MMA into the slot
         if (valid) {
-          ps.sigma[pg] = fmaxf(sigma_lin + small[kOffBSigma], 0.f);  // :546-553 (eval: no noise)
-          ps.rgb[3 * pg + 0] = sigmoidf<kSplit3>(o[0] + small[kOffBOut + 0]);   // :585-594
-          ps.rgb[3 * pg + 1] = sigmoidf<kSplit3>(o[1] + small[kOffBOut + 1]);
-          ps.rgb[3 * pg + 2] = sigmoidf<kSplit3>(o[2] + small[kOffBOut + 2]);
-          ps.vis[pg] = sigmoidf<kSplit3>(o[3] + small[kOffBOut + 3]);
+          ps.sigma[pg] = fmaxf(sigma_lin + head_bias[4], 0.f);  // :546-553 (eval: no noise)
+          ps.rgb[3 * pg + 0] = sigmoidf<kSplit3>(o[0] + head_bias[0]);   // :585-594
+          ps.rgb[3 * pg + 1] = sigmoidf<kSplit3>(o[1] + head_bias[1]);
+          ps.rgb[3 * pg + 2] = sigmoidf<kSplit3>(o[2] + head_bias[2]);
+          ps.vis[pg] = sigmoidf<kSplit3>(o[3] + head_bias[3]);
         }
         if (kSec)   // compile-time: the eval render without secondary views pays nothing for this path
           secondary_views<kSplit3, kPair, kHalf>(smem, p, ps, slot, row, lane, pg, valid, ray, taddr, bar(kBarDReady + slot),
@@ -1395,7 +1432,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const __grid_const
             const StepDesc sd = step_desc(st);
             const uint32_t chunk_bytes = layer_chunk_bytes(sd.layer);
             const uint32_t n_items = (sd.n_chunks + (sd.bias_chunk ? 1 : 0)) * kImg;
-            const uint32_t byte0 = (uint32_t)tc_layer_byte_offset(sd.layer) * kImg + sd.first_chunk * chunk_bytes * kImg;
+            const uint32_t byte0 = tc_layer_offset_rt(sd.layer) * kImg + sd.first_chunk * chunk_bytes * kImg;
             if (kPair) {
               // rows of 64 bytes: consecutive chunk images, this CTA takes rows [rank * n/2, +n/2) of each
               const uint32_t rows = (uint32_t)layer_n(sd.layer);
