@@ -900,7 +900,11 @@ __device__ __forceinline__ void store_point_encoding(uint8_t* smem, int slot, in
 template <bool kSplit3, bool kRelu, bool kSigma, bool kHalf>
 __device__ __forceinline__ float layer_epilogue(uint8_t* smem, int slot, int row, uint32_t taddr,
                                                 const float* w_sigma /* shared */) {
-  float sigma_acc = 0.f;
+  // density head: four independent partial sums (packed pairs on the throughput path) keep the FMA chain short
+  float sigma_acc[4] = {0.f, 0.f, 0.f, 0.f};
+  uint64_t sigma_acc2[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) sigma_acc2[i] = pack_f32x2(0.f, 0.f);
   const uint32_t hi_base = smem_u32(smem + kOffA + (kSplit3 ? 0 : slot) * kABytes) + row * 128;
   const uint32_t lo_base = smem_u32(smem + kOffA + kABytes) + row * 128;
   uint32_t v[2][32];
@@ -918,7 +922,7 @@ __device__ __forceinline__ float layer_epilogue(uint8_t* smem, int slot, int row
     tmem_ld_wait();
     if (cb + 1 < 8) tmem_ld32(taddr + (cb + 1) * 32, v[(cb + 1) & 1]);
     const uint32_t kb_off = (uint32_t)(cb >> 1) * kKBlockBytes;
-    if (!kSplit3 && !kSigma) {
+    if (!kSplit3) {
       // throughput path: ReLU fused into the bf16x2 conversion - one instruction per two elements
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -927,6 +931,9 @@ __device__ __forceinline__ float layer_epilogue(uint8_t* smem, int slot, int row
         for (int q = 0; q < 4; ++q) {
           const int e = 8 * j + 2 * q;
           w[q] = cvt_op_x2<kRelu, kHalf>(pack_f32x2(__uint_as_float(v[cb & 1][e]), __uint_as_float(v[cb & 1][e + 1])));
+          if (kSigma)   // sigma += relu(h) . w_sigma on the fp32 accumulator values (VipNeRF01.py:546-553)
+            sigma_acc2[q] = ffma2(pack_f32x2(fmaxf(__uint_as_float(v[cb & 1][e]), 0.f), fmaxf(__uint_as_float(v[cb & 1][e + 1]), 0.f)),
+                                  pack_f32x2(ws[e], ws[e + 1]), sigma_acc2[q]);
         }
         const int ch = (cb & 1) * 4 + j;
         st_shared_v4(hi_base + kb_off + (uint32_t)((ch ^ (row & 7)) << 4), w[0], w[1], w[2], w[3]);
@@ -941,7 +948,7 @@ __device__ __forceinline__ float layer_epilogue(uint8_t* smem, int slot, int row
     }
     if (kSigma) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) sigma_acc = fmaf(h[j], ws[j], sigma_acc);
+      for (int j = 0; j < 32; ++j) sigma_acc[j & 3] = fmaf(h[j], ws[j], sigma_acc[j & 3]);
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -959,7 +966,12 @@ __device__ __forceinline__ float layer_epilogue(uint8_t* smem, int slot, int row
       }
     }
   }
-  return sigma_acc;
+  if (!kSplit3) {
+    float lo, hi;
+    unpack_f32x2(fadd2(fadd2(sigma_acc2[0], sigma_acc2[1]), fadd2(sigma_acc2[2], sigma_acc2[3])), lo, hi);
+    return lo + hi;
+  }
+  return (sigma_acc[0] + sigma_acc[1]) + (sigma_acc[2] + sigma_acc[3]);
 }
 
 // M9 epilogue for one row: relu(acc + (bias + view-direction part)) . views_output_linear -> 4 logits.
@@ -1524,51 +1536,61 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_render_tc(const __grid_const
     // their events become due.
     const WorkList<kFused, kPair> work0(p, cta_group_idx * kSlots + 0, n_slots_total, (int)cta_rank);
     const WorkList<kFused, kPair> work1(p, cta_group_idx * kSlots + (kSlots - 1), n_slots_total, (int)cta_rank);
-    const int n_max = max(work0.n_items, kSlots > 1 ? work1.n_items : 0);
     float* scratch = reinterpret_cast<float*>(smem + kOffRayScratch);
+    // Events of a slot, in order: one per coarse tile (= ray pair), then one per completed fine tile triple.  The two
+    // slots' events are served in the order they BECOME DUE (non-blocking probes of both barriers): a slot must not
+    // wait for its sibling's tile to finish before its own pair is composited.
     uint32_t parity[2] = {0, 0}, n_done[2] = {0, 0};
-    for (int it = 0; it < n_max; ++it) {
-#pragma unroll
-      for (int slot = 0; slot < kSlots; ++slot) {
-        const WorkList<kFused, kPair>& work = slot == 0 ? work0 : work1;
-        if (it >= work.n_items) continue;
-        const int pi = work.pass_of(it);
-        const int64_t tile = work.tile_of(it);
-        if (!(pi == 0 || (tile % 3) == 2)) continue;
-        const PassDesc& ps = p.pass[pi];
-        mbar_wait(bar(kBarRayFull + slot), parity[slot]);
-        parity[slot] ^= 1;
-        const int64_t pair = pi == 0 ? tile : tile / 3;
-        for (int rr = 0; rr < 2; ++rr) {
-          const int64_t r = 2 * pair + rr;
-          if (r >= p.n_rays) continue;
-          RayConsts rc;
-          rc.dnorm = vec3_norm(p.rp.pts_d[3 * r], p.rp.pts_d[3 * r + 1], p.rp.pts_d[3 * r + 2]);
-          rc.oz = p.rp.rays_o[3 * r + 2];
-          rc.dz = p.rp.rays_d[3 * r + 2];
-          if (pi == 0) {
-            float z_reg[2], w_reg[2];
-            const int V = kSec ? p.fl.n_sec_views : 0;
-            composite_ray<2>(lane, 64, ps.z + r * 64, ps.sigma + r * 64, ps.rgb + r * 192,
-                             V > 0 ? ps.vis2 + r * 64 * V : nullptr, V, p.fl.ndc, p.fl.white_bkgd, rc, p.out[0], r, z_reg, w_reg);
-            if (p.has_fine) {
-              const float* u = p.rp.u_rand ? p.rp.u_rand + r * p.n_fine : p.rp.u_vals;
-              resample_ray<2>(lane, 64, p.n_fine, z_reg, w_reg, u, p.rp.u_rand == nullptr, scratch,
-                              p.pass[1].z + r * (64 + p.n_fine));
-            }
-          } else {
-            float z_reg[6], w_reg[6];
-            const int V = kSec ? p.fl.n_sec_views : 0;
-            composite_ray<6>(lane, 192, ps.z + r * 192, ps.sigma + r * 192, ps.rgb + r * 576,
-                             V > 0 ? ps.vis2 + r * 192 * V : nullptr, V, p.fl.ndc, p.fl.white_bkgd, rc, p.out[1], r, z_reg, w_reg);
-          }
-        }
-        ++n_done[slot];
-        __threadfence_block();   // z_fine (global) before the count the epilogue group acquires
-        __syncwarp();
-        if (lane == 0)
-          asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(smem_u32(smem + kOffRayDone) + 4u * slot), "r"(n_done[slot]) : "memory");
+    const uint32_t n_events[2] = {(uint32_t)(work0.n_first_pass * (p.has_fine ? 2 : 1)),
+                                  kSlots > 1 ? (uint32_t)(work1.n_first_pass * (p.has_fine ? 2 : 1)) : 0u};
+    const long long t_start = clock64();
+    int slot = 0;
+    while (n_done[0] < n_events[0] || n_done[1] < n_events[1]) {
+      slot ^= (kSlots > 1 ? 1 : 0);
+      if (n_done[slot] >= n_events[slot]) continue;
+      // warp-uniform probe: lane 0 decides, then every lane acquires the (already completed) phase itself
+      uint32_t due = lane == 0 ? (uint32_t)mbar_try_wait(bar(kBarRayFull + slot), parity[slot]) : 0u;
+      due = __shfl_sync(0xffffffffu, due, 0);
+      if (!due) {
+        if (clock64() - t_start > 8 * kTimeoutCycles) mbar_timeout(bar(kBarRayFull + slot), parity[slot]);
+        continue;
       }
+      mbar_wait(bar(kBarRayFull + slot), parity[slot]);
+      parity[slot] ^= 1;
+      const WorkList<kFused, kPair>& work = slot == 0 ? work0 : work1;
+      const int ev = (int)n_done[slot];
+      const int pi = ev < work.n_first_pass ? 0 : 1;
+      const int64_t pair = work.unit_of(pi == 0 ? ev : ev - work.n_first_pass);
+      const PassDesc& ps = p.pass[pi];
+      for (int rr = 0; rr < 2; ++rr) {
+        const int64_t r = 2 * pair + rr;
+        if (r >= p.n_rays) continue;
+        RayConsts rc;
+        rc.dnorm = vec3_norm(p.rp.pts_d[3 * r], p.rp.pts_d[3 * r + 1], p.rp.pts_d[3 * r + 2]);
+        rc.oz = p.rp.rays_o[3 * r + 2];
+        rc.dz = p.rp.rays_d[3 * r + 2];
+        if (pi == 0) {
+          float z_reg[2], w_reg[2];
+          const int V = kSec ? p.fl.n_sec_views : 0;
+          composite_ray<2>(lane, 64, ps.z + r * 64, ps.sigma + r * 64, ps.rgb + r * 192,
+                           V > 0 ? ps.vis2 + r * 64 * V : nullptr, V, p.fl.ndc, p.fl.white_bkgd, rc, p.out[0], r, z_reg, w_reg);
+          if (p.has_fine) {
+            const float* u = p.rp.u_rand ? p.rp.u_rand + r * p.n_fine : p.rp.u_vals;
+            resample_ray<2>(lane, 64, p.n_fine, z_reg, w_reg, u, p.rp.u_rand == nullptr, scratch,
+                            p.pass[1].z + r * (64 + p.n_fine));
+          }
+        } else {
+          float z_reg[6], w_reg[6];
+          const int V = kSec ? p.fl.n_sec_views : 0;
+          composite_ray<6>(lane, 192, ps.z + r * 192, ps.sigma + r * 192, ps.rgb + r * 576,
+                           V > 0 ? ps.vis2 + r * 192 * V : nullptr, V, p.fl.ndc, p.fl.white_bkgd, rc, p.out[1], r, z_reg, w_reg);
+        }
+      }
+      ++n_done[slot];
+      __threadfence_block();   // z_fine (global) before the count the epilogue group acquires
+      __syncwarp();
+      if (lane == 0)
+        asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(smem_u32(smem + kOffRayDone) + 4u * slot), "r"(n_done[slot]) : "memory");
     }
   }
   __syncthreads();
