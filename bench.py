@@ -278,12 +278,30 @@ def run_frame(args, rank, world, local_rank):
     lo, hi = sharding.shard_range(R, rank, world)
     keys = ('rgb_fine', 'depth_fine', 'depth_var_fine') + (('depth_ndc_fine', 'depth_var_ndc_fine') if ndc else ())
 
-    def step(i):
+    peer, gather_mode = None, 'none (1 GPU)'
+    if world > 1:
+        try:
+            if args.gather == 'nccl':
+                raise RuntimeError('--gather nccl')
+            peer = [sharding.PeerGather({k: ((3,) if k == 'rgb_fine' else ()) for k in keys}, R, device) for _ in range(2)]
+            gather_mode = 'peer stores from the render kernel into rank 0 symmetric memory + 1 device barrier (no NCCL call)'
+        except Exception as e:   # noqa: BLE001
+            gather_mode = f'NCCL grouped send/recv into preallocated arrays ({type(e).__name__}: {str(e)[:80]})'
+
+    def step(i, shard=True):
+        if not shard:     # the whole frame on this rank alone (the sharded == unsharded check)
+            out = model(dp.create_test_data(poses[i % len(poses)], preprocess_pose=False))
+            return dp.postprocess({k: out[k] for k in keys}, '_fine')
         batch = dp.create_test_data(poses[i % len(poses)], preprocess_pose=False, first_pixel=lo, n_rays=hi - lo)
-        out = model(batch)
-        maps = {k: out[k] for k in keys}
-        if world > 1:
-            maps = sharding.gather_outputs(maps, R, None, 0)
+        if peer is not None:
+            pg = peer[i & 1]
+            model(batch, out=pg.local_outputs())
+            maps = pg.finish()
+        else:
+            out = model(batch)
+            maps = {k: out[k] for k in keys}
+            if world > 1:
+                maps = sharding.gather_outputs(maps, R, None, 0)
         if rank == 0:
             return dp.postprocess(maps, '_fine')     # device post-processing + the single D2H copy (synchronises)
         return None
@@ -309,6 +327,15 @@ def run_frame(args, rank, world, local_rank):
             t_ms += s.elapsed_time(e)
         barrier()
         clocks = sampler.stop()
+        # sharded == unsharded: rank 0 renders the same frame alone; the finished frames must be identical
+        sharded_ok = None
+        if world > 1:
+            i_chk = args.steps + (args.steps & 1)
+            sharded = step(i_chk)
+            barrier()
+            if rank == 0:
+                alone = step(i_chk, shard=False)
+                sharded_ok = all(numpy.array_equal(sharded[k], alone[k]) for k in alone)
     total = torch.tensor([t_ms], dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(total, op=dist.ReduceOp.MAX)
@@ -320,9 +347,10 @@ def run_frame(args, rank, world, local_rank):
                 'scaling': 'strong', 'vs_baseline': None, 'dtype': args.precision, 'data': 'synthetic',
                 'config': {'workload': ('LLFF 504x378' if args.scene == 'fern' else 'DTU 400x300') +
                                        f' full-frame render ({R:,} rays per step), rays sharded over the GPUs, '
-                                       'on-device ray generation, one NCCL gather, device post-processing, finished frame to host',
+                                       'on-device ray generation, one gather (see gather), device post-processing, finished frame to host',
                            'rays_per_step': R, 'samples': '64+128', 'ndc': ndc, 'precision': args.precision,
-                           'frames_per_s': args.steps / (total_ms * 1e-3)},
+                           'frames_per_s': args.steps / (total_ms * 1e-3), 'gather': gather_mode},
+                'sharded_equals_unsharded': sharded_ok,
                 'clocks': clocks,
                 'e2e': {'value': value, 'unit': 'rays/s', 'h2d_bytes_per_step': 0,
                         'd2h_bytes_per_step': int(frame['image'].nbytes + sum(frame[k].nbytes for k in frame if k != 'image')),
@@ -553,6 +581,7 @@ def main():
     ap.add_argument('--rng', default='reference', choices=['reference', 'device'],
                     help='train workload: where the stratified jitter / cdf samples / density noise are drawn')
     ap.add_argument('--scene', default='fern', choices=['fern', 'dtu'], help='camera of the frame workload')
+    ap.add_argument('--gather', default='peer', choices=['peer', 'nccl'], help='N > 1: how the rendered maps reach rank 0')
     ap.add_argument('--quick', action='store_true', help='batch workload: skip the sustained / precision_modes / train sub-records')
     ap.add_argument('--no-train', action='store_true', help='batch workload: skip the train sub-record')
     args = ap.parse_args()
@@ -654,64 +683,123 @@ def run_batch(args, rank, world, local_rank):
     all_ok = max_over_ranks(0.0 if check['ok'] else 1.0) == 0.0
 
     # ------------------------------------------------------------------ e2e: plugin call with host buffers
+    # Every step: the step's rays leave PINNED HOST memory, the plugin renders them, the rendered maps (N > 1: the maps
+    # of ALL ranks, gathered on rank 0) arrive in pinned host memory.  Host side: vipnerf_b200.hostio - one pinned
+    # buffer per direction (one H2D, one D2H) and, on one GPU, the three operations replayed as one CUDA graph around
+    # `model(batch, out=...)`.  The reference's own per-tensor flow (14 small copies around `model(batch)`) is timed
+    # next to it as `plain_plugin_call`.
+    from vipnerf_b200 import hostio
     out_keys = ('rgb_fine', 'depth_fine', 'depth_var_fine', 'depth_ndc_fine', 'depth_var_ndc_fine')
-    n_host_rays = world * R if (world > 1 and rank == 0) else R
-    host_out = {k: torch.empty((n_host_rays, 3) if k == 'rgb_fine' else (n_host_rays,), dtype=torch.float32).pin_memory()
-                for k in out_keys}
-    h2d = sum(v.numel() * 4 for v in host_batch.values())
-    d2h = sum(v.numel() * 4 for v in host_out.values())
+    shapes = {k: ((3,) if k == 'rgb_fine' else ()) for k in out_keys}
+    # N > 1: the gather of the rendered pixels on rank 0.  Preferred: fused with the render - every rank's kernel stores
+    # its finished maps straight into rank 0's arrays over NVLink (sharding.PeerGather, torch symmetric memory) and one
+    # device-side barrier per step publishes them; two buffer sets alternate so that one barrier per step suffices.
+    # Fallback (no symmetric memory): one grouped NCCL send/receive into preallocated arrays (sharding.gather_outputs).
+    peer, gather_mode, graphed = None, None, None
+    inputs = hostio.FlatBuffers({k: tuple(v.shape) for k, v in host_batch.items()}, device)
+    for k, v in host_batch.items():
+        inputs.host[k].copy_(v)
+    if world > 1:
+        try:
+            if args.gather == 'nccl':
+                raise RuntimeError('--gather nccl')
+            peer = [sharding.PeerGather(shapes, world * R, device) for _ in range(2)]
+            gather_mode = 'peer stores from the render kernel into rank 0 symmetric memory + 1 device barrier (no NCCL call)'
+            host_flat = torch.empty(peer[0].total, dtype=torch.float32).pin_memory() if rank == 0 else None
+        except Exception as e:   # noqa: BLE001
+            peer = None
+            gather_mode = f'NCCL grouped send/recv into preallocated arrays ({type(e).__name__}: {str(e)[:80]})'
+        if peer is None:
+            host_out = {k: torch.empty((world * R,) + shapes[k], dtype=torch.float32).pin_memory() for k in out_keys}
+        d2h = (peer[0].total * 4) if peer is not None else sum(v.numel() * 4 for v in host_out.values())
+    else:
+        graphed = hostio.GraphedRender(model, host_batch, out_keys, device=device)
+        d2h = graphed.d2h_bytes
+    h2d = inputs.nbytes
+    step_no = [0]
 
     def e2e_step():
+        if graphed is not None:
+            return graphed()           # one cudaGraphLaunch: H2D, fused render, D2H
+        batch = inputs.upload()
+        if peer is not None:
+            pg = peer[step_no[0] & 1]
+            step_no[0] += 1
+            model(batch, out=pg.local_outputs())
+            maps = pg.finish()
+            if maps is not None:       # rank 0 brings the WHOLE gathered result to the host: one copy
+                host_flat.copy_(pg.buf, non_blocking=True)
+                return {k: pg._view(host_flat, k, 0, world * R) for k in out_keys}, maps
+            return None
+        out = model(batch)
+        maps = sharding.gather_outputs({k: out[k] for k in out_keys}, world * R, None, 0)
+        if maps is not None:
+            for k in out_keys:
+                host_out[k].copy_(maps[k], non_blocking=True)
+            return host_out, maps
+        return None
+
+    host_plain = {k: torch.empty((R,) + shapes[k], dtype=torch.float32).pin_memory() for k in out_keys}
+
+    def plain_step():                  # the reference Tester's flow: per-tensor copies around model(batch)
         batch = {k: v.to(device, non_blocking=True) for k, v in host_batch.items()}
         out = model(batch)
-        maps = {k: out[k] for k in out_keys}
-        if world > 1:   # the single collective of the path: gather the rendered pixels on rank 0
-            maps = sharding.gather_outputs(maps, world * R, None, 0)
-        if maps is not None:
-            for k in out_keys:   # rank 0 brings the WHOLE gathered result to the host
-                host_out[k].copy_(maps[k], non_blocking=True)
-        return maps
+        for k in out_keys:
+            host_plain[k].copy_(out[k], non_blocking=True)
+
+    def timed_pipelined(fn, n):
+        starts, ends, _ = time_launches(fn, n, flush)
+        barrier()
+        return max_over_ranks(sum(s.elapsed_time(e) for s, e in zip(starts, ends))) * 1e-3
+
+    def timed_synced(fn, n):
+        total = 0.0
+        for _ in range(n):
+            flush.zero_()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            fn()
+            torch.cuda.synchronize()
+            total += time.perf_counter() - t0
+        barrier()
+        return max_over_ranks(total)
 
     e2e_steps = args.steps
     with torch.no_grad():
         for _ in range(3):
             e2e_step()
+            plain_step()
         barrier()
         # (a) pipelined: steps enqueued back to back like a serving loop (no host sync per step); every step's window -
-        # its H2D copies, the render, (the gather), its D2H copies - is timed with its own event pair on the stream
-        starts, ends, _ = time_launches(e2e_step, e2e_steps, flush)
-        barrier()
-        e_total = max_over_ranks(sum(s.elapsed_time(e) for s, e in zip(starts, ends)))
-        # (b) synchronous: the host waits for every step's result before it issues the next one (wall clock per step,
-        # flush outside the window)
-        t_sync = 0.0
-        for _ in range(e2e_steps):
-            flush.zero_()
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            e2e_step()
-            torch.cuda.synchronize()
-            t_sync += time.perf_counter() - t0
-        barrier()
-        t_sync = max_over_ranks(t_sync)
-    e2e_value = world * R * e2e_steps / (e_total * 1e-3)
-    e2e_synced = world * R * e2e_steps / t_sync
+        # H2D, render, (gather), D2H - is timed with its own event pair on the stream, L2 flush outside the windows
+        e2e_value = world * R * e2e_steps / timed_pipelined(e2e_step, e2e_steps)
+        # (b) synchronous: the host waits for every step's result before it issues the next one (wall clock per step)
+        e2e_synced = world * R * e2e_steps / timed_synced(e2e_step, e2e_steps)
+        plain_value = world * R * e2e_steps / timed_pipelined(plain_step, e2e_steps)
+        plain_synced = world * R * e2e_steps / timed_synced(plain_step, e2e_steps)
+    # the e2e path delivered the right pixels: its host result against the device result of the value path (N = 1)
+    e2e_ok = True
+    if graphed is not None:
+        host_maps = graphed()
+        graphed.synchronize()
+        e2e_ok = all(torch.equal(host_maps[k], last_out[k].cpu()) for k in out_keys)
 
     # sharded == unsharded (N > 1): rank 0 re-renders every rank's batch alone and compares with what the gather
     # delivered - bit for bit (untimed)
     sharded_ok = None
     if world > 1:
         with torch.no_grad():
-            gathered = e2e_step()
+            res = e2e_step()
             barrier()
             if rank == 0:
+                on_host, gathered = res
                 sharded_ok = True
                 for r in range(world):
                     b = {k: v.to(device) for k, v in O.make_rays('fern', R, seed=2 + r).items()}
                     alone = model(b)
                     for k in out_keys:
                         sharded_ok = sharded_ok and bool(torch.equal(alone[k], gathered[k][r * R:(r + 1) * R]))
-                        sharded_ok = sharded_ok and bool(torch.equal(host_out[k][r * R:(r + 1) * R], alone[k].cpu()))
+                        sharded_ok = sharded_ok and bool(torch.equal(on_host[k][r * R:(r + 1) * R], alone[k].cpu()))
 
     # ------------------------------------------------------------------ sub-records (rank 0 of a 1-GPU run only)
     extras = {}
@@ -768,11 +856,19 @@ def run_batch(args, rank, world, local_rank):
                         'weights': 'random-init reference architecture, density head rescaled (oracle.synth_state_dict)'},
             'clocks': clocks,
             'e2e': {'value': e2e_value, 'unit': 'rays/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-                    'steps': e2e_steps, 'api': 'VipNeRFFused.forward(batch) via ModelFactory.get_model',
-                    'timing': 'per-step CUDA-event windows (H2D copies + render (+ gather) + D2H copies of the whole result), '
+                    'steps': e2e_steps,
+                    'api': 'VipNeRFFused.forward(batch, out=...) via ModelFactory.get_model, host I/O through vipnerf_b200.hostio '
+                           + ('(GraphedRender: H2D + render + D2H as one CUDA graph)' if world == 1 else
+                              '(FlatBuffers: one H2D; one D2H of the gathered result on rank 0)'),
+                    'timing': 'per-step CUDA-event windows (H2D + render (+ gather) + D2H of the whole result), '
                               'steps enqueued back to back',
+                    'gather': gather_mode,
                     'value_host_sync_per_step': e2e_synced,
-                    'timing_host_sync': 'wall clock per step with torch.cuda.synchronize() on both sides'},
+                    'timing_host_sync': 'wall clock per step with torch.cuda.synchronize() on both sides',
+                    'plain_plugin_call': {'value': plain_value, 'value_host_sync_per_step': plain_synced,
+                                          'what': 'model(batch) with the reference Tester\'s per-tensor copies (9 H2D + 5 D2H), '
+                                                  'local maps only'},
+                    'result_equals_value_path': e2e_ok},
             'gpu_launches': args.steps * (1 if precision != 'fp32' else 5),
             'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': peaks['burst'], 'unit': 'TFLOP/s',
                          'frac': achieved / peaks['burst'], 'traffic': traffic,
@@ -784,6 +880,7 @@ def run_batch(args, rank, world, local_rank):
                          'sustained': extras.get('sustained')},
             'parity_check': check,
         }
+        all_ok = all_ok and e2e_ok
         if sharded_ok is not None:
             line['sharded_equals_unsharded'] = sharded_ok
             all_ok = all_ok and sharded_ok

@@ -66,6 +66,21 @@ class RadianceMLPParams(torch.nn.Module):
         return out
 
 
+class _PackCache:
+    """Packed weight images per (MLP, precision, device).  Never copied or pickled with the module: copy.deepcopy(model)
+    and torch.save(model) get a fresh, empty cache (a lock and CUDA events are not copyable)."""
+
+    def __init__(self):
+        self.lock = threading.Lock()
+        self.entries: Dict[tuple, tuple] = {}
+
+    def __deepcopy__(self, memo):
+        return _PackCache()
+
+    def __reduce__(self):
+        return (_PackCache, ())
+
+
 class VipNeRFFused(torch.nn.Module):
     def __init__(self, configs: dict, model_configs: Optional[dict] = None):
         super().__init__()
@@ -94,15 +109,14 @@ class VipNeRFFused(torch.nn.Module):
                     raise NotImplementedError(f'{name} shape {shape}: kernels are built for (8, 256, 10, 4)')
         # Shared BY REFERENCE between nn.DataParallel replicas (replicate() copies __dict__ shallowly): entries are keyed
         # per device and validated against the tensors the calling replica actually holds, so sharing is harmless.
-        self._pack_lock = threading.Lock()
-        self._packed: Dict[tuple, tuple] = {}
+        self._pack_cache = _PackCache()
 
     # ------------------------------------------------------------------ packed-weight cache
     def invalidate_packed(self) -> None:
         """Drops the packed weight images.  Needed only after writes that bypass autograd's version counter
         (`p.data.copy_()`, `p.data.mul_()` ...); optimizer steps, load_state_dict and .to() are detected."""
-        with self._pack_lock:
-            self._packed.clear()
+        with self._pack_cache.lock:
+            self._pack_cache.entries.clear()
 
     def _packed_weights(self, which: str, precision: str, device) -> torch.Tensor:
         mlp = self.coarse_model if which == 'coarse' else self.fine_model
@@ -117,27 +131,31 @@ class VipNeRFFused(torch.nn.Module):
             # a replica's tensors live for one forward only; a later broadcast may reuse their addresses with other
             # values, so (address, version) identifies nothing there: pack per call (2.6 MB, one small kernel)
             return renderpath.pack_mlp({k: v.detach() for k, v in tensors.items()}, precision)
-        with self._pack_lock:
-            hit = self._packed.get(key)
+        with self._pack_cache.lock:
+            hit = self._pack_cache.entries.get(key)
             if hit is not None and hit[0] == version:
-                if hit[2] != stream.cuda_stream:     # packed on another stream: order this stream after the pack kernel
+                # packed on another stream: order this stream after the pack kernel (not while capturing a CUDA graph:
+                # hostio.GraphedRender synchronises the device before it captures)
+                if hit[2] != stream.cuda_stream and not torch.cuda.is_current_stream_capturing():
                     stream.wait_event(hit[3])
                 return hit[1]
             packed = renderpath.pack_mlp({k: v.detach() for k, v in tensors.items()}, precision)
             done = torch.cuda.Event()
             done.record(stream)
-            self._packed[key] = (version, packed, stream.cuda_stream, done)
+            self._pack_cache.entries[key] = (version, packed, stream.cuda_stream, done)
             return packed
 
     # ------------------------------------------------------------------ the reference's forward contract
-    def forward(self, input_batch: dict, retraw: bool = False, sec_views_vis: bool = False):
+    def forward(self, input_batch: dict, retraw: bool = False, sec_views_vis: bool = False, out: Optional[dict] = None):
+        """`out` (optional, eval mode; not part of the reference signature): name -> preallocated fp32 CUDA tensor the
+        kernel writes that output into, e.g. views of another GPU's memory (sharding.PeerGather)."""
         if 'common_data' in input_batch.keys():   # VipNeRF01.py:35-39
             for key in input_batch['common_data'].keys():
                 if isinstance(input_batch['common_data'][key], torch.Tensor):
                     input_batch['common_data'][key] = input_batch['common_data'][key][0]
         if self.training:
             return self.render_train(input_batch)
-        return self.render(input_batch, retraw=retraw, sec_views_vis=sec_views_vis)
+        return self.render(input_batch, retraw=retraw, sec_views_vis=sec_views_vis, out=out)
 
     def _ray_batch(self, input_dict: dict, sec_views_vis: bool):
         rays_o = input_dict['rays_o']
@@ -191,7 +209,7 @@ class VipNeRFFused(torch.nn.Module):
             white_bkgd=model_cfg['white_bkgd'], lindisp=model_cfg['lindisp'],
             tf32=model_cfg.get('train_precision', 'fp32') == 'tf32')
 
-    def render(self, input_dict: dict, retraw: bool, sec_views_vis: bool):
+    def render(self, input_dict: dict, retraw: bool, sec_views_vis: bool, out: Optional[dict] = None):
         batch, n_sec_views = self._ray_batch(input_dict, sec_views_vis)
         device = batch['rays_o'].device
         model_cfg = self.configs['model']
@@ -206,5 +224,6 @@ class VipNeRFFused(torch.nn.Module):
             batch, packed_c, packed_f, ndc=self.ndc, precision=precision,
             n_coarse=model_cfg['coarse_mlp']['num_samples'],
             n_fine=model_cfg['fine_mlp']['num_samples'] if self.fine_mlp_needed else 0,
-            retraw=retraw, n_sec_views=n_sec_views, white_bkgd=model_cfg['white_bkgd'], lindisp=model_cfg['lindisp'])
+            retraw=retraw, n_sec_views=n_sec_views, white_bkgd=model_cfg['white_bkgd'], lindisp=model_cfg['lindisp'],
+            out_tensors=out)
         return out

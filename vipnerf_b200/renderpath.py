@@ -105,17 +105,38 @@ def _make_rays(batch: Dict[str, torch.Tensor], ndc: bool, n_coarse: int, n_fine:
     return rays
 
 
-def _alloc_pass(out: _lib.PassOut, keys: Iterable[str], R: int, S: int, V: int, device) -> Dict[str, torch.Tensor]:
+def _alloc_pass(out: _lib.PassOut, keys: Iterable[str], R: int, S: int, V: int, device,
+                provided: Optional[Dict[str, torch.Tensor]] = None, tag: str = '') -> Dict[str, torch.Tensor]:
+    """Output tensors of one pass.  `provided` maps reference-style names (`rgb_fine`, ...) to caller-owned fp32 CUDA
+    tensors the kernel writes into instead of fresh allocations - e.g. views of another GPU's symmetric memory
+    (sharding.PeerGather): the ray warps then store the finished maps directly over NVLink."""
     shapes = {'rgb': (R, 3), 'acc': (R,), 'depth': (R,), 'depth_var': (R,), 'depth_ndc': (R,), 'depth_var_ndc': (R,),
               'visibility2': (R, V), 'alpha': (R, S), 'z_vals': (R, S), 'visibility': (R, S), 'weights': (R, S),
               'raw_sigma': (R, S, 1), 'raw_rgb': (R, S, 3), 'raw_visibility': (R, S, 1),
               'raw_visibility2': (R, S, V, 1)}
-    tensors = {}
+    tensors, fresh, total = {}, [], 0
     for k in keys:
-        t = torch.empty(shapes[k], dtype=torch.float32, device=device)
+        t = provided.get(f'{k}_{tag}') if provided else None
+        if t is None:
+            n = 1
+            for d in shapes[k]:
+                n *= int(d)
+            fresh.append((k, total, n))
+            total += (n + 3) // 4 * 4          # every array starts on a 16-byte boundary
+            continue
+        if (tuple(t.shape) != tuple(shapes[k]) or t.dtype != torch.float32 or not t.is_cuda or not t.is_contiguous()
+                or t.data_ptr() % 4 != 0):
+            raise ValueError(f'out[{k}_{tag}]: expected a contiguous fp32 CUDA tensor of shape {tuple(shapes[k])}, got '
+                             f'{tuple(t.shape)} {t.dtype} on {t.device}')
         tensors[k] = t
-        setattr(out, k, t.data_ptr())
-    return tensors
+    if fresh:
+        # ONE allocation per pass (the arrays are views of it): 14 allocator calls per eval render were ~40 us of host time
+        flat = torch.empty(max(total, 4), dtype=torch.float32, device=device)
+        for k, off, n in fresh:
+            tensors[k] = flat[off:off + n].view(shapes[k])
+    for k in keys:
+        setattr(out, k, tensors[k].data_ptr())
+    return {k: tensors[k] for k in keys}
 
 
 _workspace_cache: Dict[tuple, torch.Tensor] = {}
@@ -145,9 +166,11 @@ def pass_keys(ndc: bool, retraw: bool, n_sec_views: int) -> list:
 def render_rays(batch: Dict[str, torch.Tensor], packed_coarse: torch.Tensor, packed_fine: Optional[torch.Tensor], *,
                 ndc: bool, precision: str, n_coarse: int = 64, n_fine: int = 128, retraw: bool = False,
                 n_sec_views: int = 0, white_bkgd: bool = False, lindisp: bool = False,
-                keys: Optional[Iterable[str]] = None) -> Dict[str, torch.Tensor]:
+                keys: Optional[Iterable[str]] = None,
+                out_tensors: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
     """VipNeRF.render_rays (VipNeRF01.py:74-171) for every ray of `batch` in one library call.
-    Returns the reference's output dict (`<key>_coarse` / `<key>_fine`)."""
+    Returns the reference's output dict (`<key>_coarse` / `<key>_fine`); `out_tensors` (optional) supplies the storage
+    of some of them."""
     lib = _lib.load()
     rays_o = batch['rays_o']
     _require_cuda(rays_o, 'rays_o')
@@ -161,10 +184,10 @@ def render_rays(batch: Dict[str, torch.Tensor], packed_coarse: torch.Tensor, pac
     out = _lib.Out()
     wanted = list(keys) if keys is not None else pass_keys(ndc, retraw, n_sec_views)
     result = {}
-    tensors_c = _alloc_pass(out.coarse, wanted, R, n_coarse, n_sec_views, device)
+    tensors_c = _alloc_pass(out.coarse, wanted, R, n_coarse, n_sec_views, device, out_tensors, 'coarse')
     result.update({f'{k}_coarse': v for k, v in tensors_c.items()})
     if has_fine:
-        tensors_f = _alloc_pass(out.fine, wanted, R, n_coarse + n_fine, n_sec_views, device)
+        tensors_f = _alloc_pass(out.fine, wanted, R, n_coarse + n_fine, n_sec_views, device, out_tensors, 'fine')
         result.update({f'{k}_fine': v for k, v in tensors_f.items()})
     with torch.cuda.device(device):
         ws_bytes = lib.vipnerf_workspace_bytes(ctypes.byref(cfg), R)

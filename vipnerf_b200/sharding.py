@@ -40,39 +40,109 @@ def shard_batch(batch: Dict[str, object], rank: int, world_size: int) -> Dict[st
     return out
 
 
+_gather_buffers: Dict[tuple, Dict[str, torch.Tensor]] = {}
+
+
+def _full_buffers(local: Dict[str, torch.Tensor], per: int, world: int) -> Dict[str, torch.Tensor]:
+    """Destination arrays [world * per, ...] per key, allocated once per (keys, shapes, device) and reused."""
+    sig = tuple(sorted((k, tuple(v.shape[1:]), str(v.dtype), str(v.device)) for k, v in local.items())) + (per, world)
+    bufs = _gather_buffers.get(sig)
+    if bufs is None:
+        bufs = {k: torch.empty((world * per,) + tuple(v.shape[1:]), dtype=v.dtype, device=v.device) for k, v in local.items()}
+        _gather_buffers[sig] = bufs
+    return bufs
+
+
 def gather_outputs(local: Dict[str, torch.Tensor], n_rays: int, group: Optional[dist.ProcessGroup] = None,
                    dst: int = 0) -> Optional[Dict[str, torch.Tensor]]:
-    """The single collective of the path: concatenates the ranks' per-ray outputs on `dst` (None elsewhere).
-    All keys are packed into one [rays, width] buffer so exactly one gather is issued regardless of how many
-    maps were rendered; short last shards are padded to the common shard size."""
+    """The single collective of the path: the ranks' per-ray outputs land on `dst` (None elsewhere), every key in ONE
+    grouped exchange (NCCL: one ncclGroup of sends / receives) straight into preallocated destination arrays - no packing
+    before, no concatenation or copies after: rank r's rows of key k are received into rows [r*per, r*per + n_r) of the
+    destination array of k, which is returned as is (a view of its first n_rays rows).  The returned tensors are reused
+    by the next call with the same signature."""
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     per = (n_rays + world - 1) // world
     keys = sorted(local)
-    widths = []
-    for k in keys:
-        w = 1
-        for dim in local[k].shape[1:]:
-            w *= int(dim)
-        widths.append(w)
-    first = local[keys[0]]
-    packed = torch.zeros((per, sum(widths)), dtype=torch.float32, device=first.device)
-    n_local = first.shape[0]
-    col = 0
-    for k, w in zip(keys, widths):
-        packed[:n_local, col:col + w] = local[k].reshape(n_local, w)
-        col += w
+    if world == 1:
+        return {k: local[k] for k in keys}
+    ops = []
     if rank == dst:
-        parts = [torch.empty_like(packed) for _ in range(world)]
-        dist.gather(packed, parts, dst=dst, group=group)
-        full = torch.cat(parts, dim=0)[:n_rays]
-        out, col = {}, 0
-        for k, w in zip(keys, widths):
-            out[k] = full[:, col:col + w].reshape((n_rays,) + tuple(local[k].shape[1:])).contiguous()
-            col += w
-        return out
-    dist.gather(packed, None, dst=dst, group=group)
+        full = _full_buffers(local, per, world)
+        for r in range(world):
+            lo, hi = shard_range(n_rays, r, world)
+            if hi <= lo:
+                continue
+            for k in keys:
+                if r == rank:
+                    full[k][lo:hi].copy_(local[k])
+                else:
+                    ops.append(dist.P2POp(dist.irecv, full[k][lo:hi], dist.get_global_rank(group, r) if group is not None else r, group))
+    else:
+        lo, hi = shard_range(n_rays, rank, world)
+        if hi > lo:
+            for k in keys:
+                ops.append(dist.P2POp(dist.isend, local[k].contiguous(), dist.get_global_rank(group, dst) if group is not None else dst, group))
+    if ops:
+        for work in dist.batch_isend_irecv(ops):
+            work.wait()
+    if rank == dst:
+        return {k: full[k][:n_rays] for k in keys}
     return None
+
+
+class PeerGather:
+    """Fused compute + gather ("direct NVLink peer stores from the kernel epilogue
+    into rank 0's image buffer"): the destination arrays live in torch symmetric memory (CUDA VMM allocations every
+    rank of the node maps), every rank hands the render kernel OUTPUT POINTERS INTO `dst`'s arrays - its ray warps then
+    store the finished per-ray maps over NVLink as they composite them - and one device-side barrier on the stream
+    tells `dst` that all shards have landed.  No NCCL call, no staging copy, nothing to unpack: on `dst` the arrays are
+    the frame.
+
+        pg = PeerGather({'rgb_fine': (3,), 'depth_fine': ()}, n_rays, device)
+        out = model(shard, out=pg.local_outputs())        # rendered straight into dst's memory
+        frame = pg.finish()                                # barrier; dict of [n_rays, ...] views on dst, None elsewhere
+    """
+
+    def __init__(self, key_shapes: Dict[str, tuple], n_rays: int, device, group: Optional[dist.ProcessGroup] = None,
+                 dst: int = 0):
+        import torch.distributed._symmetric_memory as symm_mem
+        group = group if group is not None else dist.group.WORLD
+        self.world, self.rank, self.dst, self.n_rays = dist.get_world_size(group), dist.get_rank(group), dst, n_rays
+        self.per = (n_rays + self.world - 1) // self.world
+        self.keys = sorted(key_shapes)
+        self.offsets, off = {}, 0
+        for k in self.keys:
+            width = 1
+            for d in key_shapes[k]:
+                width *= int(d)
+            self.offsets[k] = (off, width, tuple(key_shapes[k]))
+            off += ((self.world * self.per * width + 63) // 64) * 64       # 256-byte aligned regions
+        self.total = max(off, 64)
+        self.buf = symm_mem.empty(self.total, dtype=torch.float32, device=device)
+        self.handle = symm_mem.rendezvous(self.buf, group)
+        # dst's buffer as seen from this rank (on dst: the local buffer itself)
+        self.dst_buf = self.buf if self.rank == dst else self.handle.get_buffer(dst, (self.total,), torch.float32)
+
+    def _view(self, base: torch.Tensor, k: str, lo: int, hi: int) -> torch.Tensor:
+        off, width, shape = self.offsets[k]
+        return base[off + lo * width: off + hi * width].view((hi - lo,) + shape)
+
+    def local_outputs(self) -> Dict[str, torch.Tensor]:
+        """This rank's rows of every key, as tensors that alias `dst`'s arrays (peer memory for rank != dst)."""
+        lo, hi = shard_range(self.n_rays, self.rank, self.world)
+        return {k: self._view(self.dst_buf, k, lo, hi) for k in self.keys}
+
+    def finish(self) -> Optional[Dict[str, torch.Tensor]]:
+        """Stream-ordered barrier over the ranks (symmetric-memory signal pads); afterwards `dst` owns the whole result."""
+        self.handle.barrier(channel=0)
+        if self.rank != self.dst:
+            return None
+        return {k: self._view(self.buf, k, 0, self.n_rays) for k in self.keys}
+
+    def release(self) -> None:
+        """Second barrier: nobody may start overwriting dst's arrays (next frame) before dst has consumed them."""
+        self.handle.barrier(channel=1)
 
 
 def render_sharded(render_fn: Callable[[Dict[str, object]], Dict[str, torch.Tensor]], batch: Dict[str, object],
