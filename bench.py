@@ -371,7 +371,7 @@ TRAIN_FLOP_PER_POINT = 2 * (593_536 + 557_056 + 593_536)   # forward + backward-
 TRAIN_TC_BYTES_PER_POINT = 22_852 + 2_672 + 26_116 + 31_012   # 82,652
 
 
-def make_train_step(device, R, rng, train_precision, seed, world=1):
+def make_train_step(device, R, rng, train_precision, seed, world=1, loss_path='fused'):
     """One training iteration of BASELINE config 3 through the plugin exactly as Trainer01.train_one_iter (:61-107)
     drives it: pinned host rays in, zero_grad, model(batch) in train mode, the four losses, backward, Adam step.
     Returns (step_fn, model, h2d_bytes)."""
@@ -390,27 +390,22 @@ def make_train_step(device, R, rng, train_precision, seed, world=1):
     host = {k: v.pin_memory() for k, v in O.make_rays('re10k', R, seed=seed, n_sec_views=V).items()}
     sup_host = O.make_supervision('re10k', R, V)
     sup = {k: (v.to(device) if isinstance(v, torch.Tensor) else v) for k, v in sup_host.items()}
-    # the reference's losses index with boolean masks (a device sync + a sort per use); the masks are fixed for the
-    # batch, so the bench resolves them to index tensors once, outside the timed region
-    m_nerf = torch.nonzero(sup['indices_mask_nerf']).squeeze(1)
-    m_depth = torch.nonzero(sup['indices_mask_sparse_depth']).squeeze(1)
-    target_nerf = sup['target_rgb'][m_nerf]
-    prior_nerf = sup['visibility_prior_masks'][m_nerf]
-    depth_gt = sup['sparse_depth_values'][:, 0][m_depth]
-
-    def losses(out):   # MSE01 + 0.1 VisibilityLoss01 + 0.001 VisibilityPriorLoss01 + 0.1 SparseDepthMSE01
-        total = 0
-        for t in ('coarse', 'fine'):
-            total = total + torch.mean(torch.square(out[f'rgb_{t}'].index_select(0, m_nerf) - target_nerf))
-            pred, tgt = out[f'raw_visibility_{t}'][..., 0], out[f'visibility_{t}']
-            total = total + 0.1 * (torch.mean(torch.abs(pred - tgt.detach())) + torch.mean(torch.abs(pred.detach() - tgt)))
-            total = total + 0.001 * torch.mean(torch.sum(prior_nerf * (1 - out[f'visibility2_{t}'].index_select(0, m_nerf)), dim=1))
-        return total + 0.1 * torch.mean(torch.square(out['depth_fine'].index_select(0, m_depth) - depth_gt))
+    # The reference's loss computer interface (LossComputer01.compute_losses) with the four losses fused into the CUDA
+    # step (vipnerf_b200/LossComputerFused01.py): loss values from one kernel, their gradients formed inside the
+    # compositing backward.  --loss-path torch evaluates the same losses with torch ops on the output tensors.
+    from vipnerf_b200.LossComputerFused01 import LossComputer
+    cfg['losses'] = [{'name': 'MSE01', 'weight': 1}, {'name': 'VisibilityLoss01', 'weight': 0.1},
+                     {'name': 'VisibilityPriorLoss01', 'iter_weights': {'0': 0, '30000': 0.001}},
+                     {'name': 'SparseDepthMSE01', 'weight': 0.1}]       # runs/training/train0012/Configs.json:69-89
+    computer = LossComputer(cfg)
 
     def step():
         batch = {k: v.to(device, non_blocking=True) for k, v in host.items()}
+        batch.update(sup)
         opt.zero_grad(set_to_none=True)
-        loss = losses(model(batch))
+        out = model(batch)
+        losses = computer.compute_losses(batch, out) if loss_path == 'fused' else computer._compute_torch(batch, out, False)
+        loss = losses['TotalLoss']
         loss.backward()
         if world > 1:
             sharding.allreduce_gradients(model, average=True)
@@ -467,7 +462,8 @@ def run_train(args, rank, world, local_rank):
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl', device_id=device)
     R, V = args.rays_per_step, 1
-    step, model, h2d = make_train_step(device, R, args.rng, args.train_precision, seed=2 + rank, world=world)
+    step, model, h2d = make_train_step(device, R, args.rng, args.train_precision, seed=2 + rank, world=world,
+                                       loss_path=args.loss_path)
 
     def barrier():
         if world > 1:
@@ -580,6 +576,7 @@ def main():
                     help='train workload: tf32 = every 256-wide product of the step on the tensor cores (tcgen05 kind::tf32)')
     ap.add_argument('--rng', default='reference', choices=['reference', 'device'],
                     help='train workload: where the stratified jitter / cdf samples / density noise are drawn')
+    ap.add_argument('--loss-path', default='fused', choices=['fused', 'torch'], help='train workload: fused CUDA losses or torch ops')
     ap.add_argument('--scene', default='fern', choices=['fern', 'dtu'], help='camera of the frame workload')
     ap.add_argument('--gather', default='peer', choices=['peer', 'nccl'], help='N > 1: how the rendered maps reach rank 0')
     ap.add_argument('--quick', action='store_true', help='batch workload: skip the sustained / precision_modes / train sub-records')

@@ -240,6 +240,35 @@ int vipnerf_train_backward(const vipnerf_cfg* cfg, const vipnerf_rays* rays, int
                            const void* saved, size_t saved_bytes, float* const param_grads_coarse[24],
                            float* const param_grads_fine[24], void* workspace, size_t workspace_bytes, void* stream);
 
+/* --- the four training losses fused into the step (second half of row f1) ---------------------------------------
+ * Replaces loss_functions/LossComputer01.py:33-51 with MSE01.py:25-67 (rgb_coarse + rgb_fine vs target_rgb on
+ * indices_mask_nerf), VisibilityLoss01.py:26-74 (MAE between raw_visibility[..., 0] and the transmittance `visibility`,
+ * each side detached in turn, :57-58), VisibilityPriorLoss01.py:25-89 (prior-masked 1 - visibility2 on
+ * indices_mask_nerf) and SparseDepthMSE01.py:26-71 (depth_fine - depth_coarse for a coarse-only model - vs
+ * sparse_depth_values[:, 0] on indices_mask_sparse_depth).  A weight of 0 switches a loss off.
+ * vipnerf_fused_losses reads the forward outputs of vipnerf_train_forward and writes losses_dev[8] (device):
+ * [0..3] the four loss values, [4] TotalLoss = sum of weight * value, [5] / [6] the mask counts the means divide by.
+ * vipnerf_train_backward_fused is vipnerf_train_backward with dTotalLoss/d(output) formed INSIDE the compositing
+ * backward from `spec` (and scaled by the device scalar *upstream_dev, NULL = 1): no per-sample gradient tensor exists.
+ * grad_out may still carry gradients of other consumers of the outputs (added on top; NULL = none).
+ * workspace of vipnerf_fused_losses: 64 * ceil(n_rays / 4) bytes, 16-byte aligned. */
+typedef struct vipnerf_loss_spec {
+  const float* target_rgb;            /* [R,3]                                                         */
+  const uint8_t* mask_nerf;           /* [R] bool (indices_mask_nerf), NULL = every ray                */
+  const uint8_t* mask_sparse_depth;   /* [R] bool (indices_mask_sparse_depth), NULL = loss off         */
+  const float* sparse_depth;          /* [R] (sparse_depth_values[:, 0])                               */
+  const float* prior;                 /* [R,V] visibility_prior_masks / _weights, NULL = ones          */
+  const float* losses_dev;            /* backward: the losses_dev[8] vipnerf_fused_losses wrote        */
+  float w_mse, w_visibility, w_prior, w_sparse_depth;
+} vipnerf_loss_spec;
+int vipnerf_fused_losses(const vipnerf_cfg* cfg, int64_t n_rays, const vipnerf_out* fwd_out, const vipnerf_loss_spec* spec,
+                         float* losses_dev, void* workspace, size_t workspace_bytes, void* stream);
+int vipnerf_train_backward_fused(const vipnerf_cfg* cfg, const vipnerf_rays* rays, int64_t n_rays, const void* packed_coarse,
+                                 const void* packed_fine, const vipnerf_out* fwd_out, const vipnerf_out* grad_out,
+                                 const vipnerf_loss_spec* spec, const float* upstream_dev,
+                                 const void* saved, size_t saved_bytes, float* const param_grads_coarse[24],
+                                 float* const param_grads_fine[24], void* workspace, size_t workspace_bytes, void* stream);
+
 /* Backward of volume_rendering alone (stage entry point of the parity tests; VipNeRF01.py:331-384 differentiated):
  * given the network outputs of one sample set (sigma [R,S] after its ReLU, rgb [R,S,3] / vis [R,S] / vis2 [R,S,V] after
  * their sigmoids) and the upstream gradients `grad_out` of the outputs, writes d_sigma_logit [R,S] (gradient w.r.t. the

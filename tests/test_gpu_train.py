@@ -270,3 +270,75 @@ def test_training_step_is_deterministic_and_optimizer_steps(built_library):
     with torch.no_grad():
         out = model(dict(rays))
     assert torch.isfinite(out['rgb_fine']).all()
+
+
+# --------------------------------------------------------------------------------------------------------------
+# loss fusion: LossComputerFused01 (vipnerf_fused_losses + the loss gradients formed inside k_composite_bwd)
+# --------------------------------------------------------------------------------------------------------------
+LOSS_CONFIGS = [{'name': 'MSE01', 'weight': 1}, {'name': 'VisibilityLoss01', 'weight': 0.1},
+                {'name': 'VisibilityPriorLoss01', 'iter_weights': {'0': 0, '30000': 0.001}},
+                {'name': 'SparseDepthMSE01', 'weight': 0.1}]       # runs/training/train0012/Configs.json:69-89
+
+
+@pytest.mark.parametrize('scene', ['fern', 'dtu'])
+def test_fused_losses_match_reference_golden_step(scene, built_library):
+    """The reference's training iteration with the loss computer swapped for LossComputerFused01: the four loss values,
+    TotalLoss and the gradients of all 48 parameter tensors against the unmodified reference's golden step
+    (its own LossComputer01 + TotalLoss.backward())."""
+    from vipnerf_b200.LossComputerFused01 import LossComputer
+    arrays = H.load_npz(f'train_{scene}.npz')
+    rays, sup, draws, outs, grads = H.split_train_golden(arrays)
+    ndc = O.SCENES[scene]['ndc']
+    cfg = _configs(ndc, chunk=32, netchunk=1000)
+    cfg['losses'] = LOSS_CONFIGS
+    model = _train_model(cfg)
+    computer = LossComputer(cfg)
+    batch = H.to_cuda(rays)
+    batch.update(_sup_cuda(sup))
+    torch.manual_seed(77)
+    out = model(dict(batch))
+    losses = computer.compute_losses(batch, out)
+    assert set(losses) == {'MSE01', 'VisibilityLoss01', 'VisibilityPriorLoss01', 'SparseDepthMSE01', 'TotalLoss'}
+    losses['TotalLoss'].backward()
+    for name in ('MSE01', 'VisibilityLoss01', 'VisibilityPriorLoss01', 'SparseDepthMSE01'):
+        ref = float(arrays[f'loss.{name}'])
+        assert abs(losses[name]['loss_value'].item() - ref) <= 2e-4 * max(abs(ref), 1e-3), (name, losses[name]['loss_value'].item(), ref)
+    assert abs(losses['TotalLoss'].item() - float(arrays['loss.total'])) <= 2e-4 * abs(float(arrays['loss.total']))
+    report = {}
+    for name, fp in grads.items():
+        g = dict(model.named_parameters())[name].grad
+        assert g is not None, name
+        H.check_grad_fingerprint(name, g, fp, GRAD_MAX_TOL, report)
+    assert len(report) == 48
+
+
+@pytest.mark.parametrize('train_precision', ['fp32', 'tf32'])
+def test_fused_losses_equal_torch_losses(train_precision, built_library):
+    """Same model, same draws: the fused path and the torch evaluation of the same four losses (autograd through the
+    dense output tensors) give the same values and - up to the re-association of sums - the same gradients; an extra
+    consumer of an output next to the fused TotalLoss adds its gradient on top."""
+    from vipnerf_b200.LossComputerFused01 import LossComputer
+    cfg = _configs(True)
+    cfg['losses'] = LOSS_CONFIGS
+    cfg['model']['train_precision'] = train_precision
+    cfg['model']['rng'] = 'device'
+    rays = O.make_rays('re10k', 301, seed=12, n_sec_views=1)
+    sup = O.make_supervision('re10k', 301, 1)
+    batch = H.to_cuda(rays)
+    batch.update(_sup_cuda(sup))
+    computer = LossComputer(cfg)
+    results = {}
+    for mode in ('fused', 'torch'):
+        model = _train_model(cfg)
+        torch.manual_seed(5)
+        out = model(dict(batch))
+        losses = computer.compute_losses(batch, out) if mode == 'fused' else computer._compute_torch(batch, out, False)
+        extra = 0.05 * out['acc_fine'].mean() + 0.01 * out['raw_sigma_coarse'].mean()
+        (losses['TotalLoss'] + extra).backward()
+        results[mode] = ({k: (v['loss_value'] if isinstance(v, dict) else v).item() for k, v in losses.items()},
+                         {k: p.grad.clone() for k, p in model.named_parameters()})
+    for k, v in results['torch'][0].items():
+        assert abs(results['fused'][0][k] - v) <= 1e-5 * max(abs(v), 1e-3), (k, results['fused'][0][k], v)
+    for k, g in results['torch'][1].items():
+        err = ((results['fused'][1][k] - g).abs().max() / g.abs().max().clamp_min(1e-30)).item()
+        assert err <= 2e-4, (k, err)

@@ -59,3 +59,27 @@ def test_plugin_draw_order_matches_oracle(n_rays, chunk, netchunk, perturb, nois
     for k in a:
         assert torch.equal(a[k], b[k]), k
     assert torch.equal(tail_a, tail_b)
+
+
+def test_loss_computer_torch_path_matches_reference_losses():
+    """LossComputerFused01's torch evaluation (used for validation batches / foreign output dicts) on the golden
+    outputs of the reference's training step reproduces the loss values of the reference's own LossComputer01."""
+    import pytest
+    from tests import helpers as H
+    from vipnerf_b200.LossComputerFused01 import LossComputer
+    cfg = {'model': {'coarse_mlp': {}, 'fine_mlp': {}},
+           'losses': [{'name': 'MSE01', 'weight': 1}, {'name': 'VisibilityLoss01', 'weight': 0.1},
+                      {'name': 'VisibilityPriorLoss01', 'iter_weights': {'0': 0, '30000': 0.001}},
+                      {'name': 'SparseDepthMSE01', 'weight': 0.1}]}
+    for scene in ('fern', 'dtu'):
+        arrays = H.load_npz(f'train_{scene}.npz')
+        rays, sup, draws, outs, grads = H.split_train_golden(arrays)
+        batch = dict(rays)
+        batch.update(sup)
+        losses = LossComputer(cfg).compute_losses(batch, outs)
+        for name in ('MSE01', 'VisibilityLoss01', 'VisibilityPriorLoss01', 'SparseDepthMSE01'):
+            ref = float(arrays[f'loss.{name}'])
+            assert abs(float(losses[name]['loss_value']) - ref) <= 2e-5 * max(abs(ref), 1e-3), (scene, name)
+        assert abs(float(losses['TotalLoss']) - float(arrays['loss.total'])) <= 2e-5 * abs(float(arrays['loss.total']))
+    with pytest.raises(RuntimeError):
+        LossComputer({'model': {}, 'losses': [{'name': 'SomethingElse01', 'weight': 1}]})

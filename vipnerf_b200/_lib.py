@@ -52,6 +52,12 @@ class Camera(Structure):   # vipnerf_camera
                 ('far_ndc', c_float), ('sx', c_float), ('sy', c_float), ('sec_origins', c_float * 24)]
 
 
+class LossSpec(Structure):   # vipnerf_loss_spec
+    _fields_ = [('target_rgb', c_void_p), ('mask_nerf', c_void_p), ('mask_sparse_depth', c_void_p),
+                ('sparse_depth', c_void_p), ('prior', c_void_p), ('losses_dev', c_void_p), ('w_mse', c_float),
+                ('w_visibility', c_float), ('w_prior', c_float), ('w_sparse_depth', c_float)]
+
+
 RAY_BUFFER_FIELDS = RAY_FIELDS[:10]
 
 
@@ -87,6 +93,11 @@ EXPORTS = {
     'vipnerf_train_backward': (c_int, [POINTER(Cfg), POINTER(Rays), c_int64, c_void_p, c_void_p, POINTER(Out),
                                        POINTER(Out), c_void_p, c_size_t, POINTER(c_void_p), POINTER(c_void_p),
                                        c_void_p, c_size_t, c_void_p]),
+    'vipnerf_fused_losses': (c_int, [POINTER(Cfg), c_int64, POINTER(Out), POINTER(LossSpec), c_void_p, c_void_p, c_size_t,
+                                     c_void_p]),
+    'vipnerf_train_backward_fused': (c_int, [POINTER(Cfg), POINTER(Rays), c_int64, c_void_p, c_void_p, POINTER(Out),
+                                             POINTER(Out), POINTER(LossSpec), c_void_p, c_void_p, c_size_t,
+                                             POINTER(c_void_p), POINTER(c_void_p), c_void_p, c_size_t, c_void_p]),
     'vipnerf_composite_backward': (c_int, [POINTER(Cfg), POINTER(Rays), c_int64, c_int32, c_void_p, c_void_p, c_void_p,
                                            c_void_p, c_void_p, POINTER(PassOut), c_void_p, c_void_p, c_void_p]),
     'vipnerf_param_gradient_gemm_workspace_bytes': (c_size_t, []),

@@ -537,11 +537,60 @@ int vipnerf_train_forward(const vipnerf_cfg* cfg, const vipnerf_rays* rays, int6
   return VIPNERF_OK;
 }
 
+namespace {
+LossGrad to_loss_grad(const vipnerf_loss_spec* spec, const float* upstream) {
+  LossGrad lg{};
+  if (spec == nullptr) return lg;
+  lg.target_rgb = spec->target_rgb; lg.mask_nerf = spec->mask_nerf; lg.mask_depth = spec->mask_sparse_depth;
+  lg.sparse_depth = spec->sparse_depth; lg.prior = spec->prior; lg.stats = spec->losses_dev; lg.upstream = upstream;
+  lg.w_mse = spec->w_mse; lg.w_vis = spec->w_visibility; lg.w_prior = spec->w_prior; lg.w_depth = spec->w_sparse_depth;
+  lg.enabled = 1;
+  return lg;
+}
+}  // namespace
+
+int vipnerf_fused_losses(const vipnerf_cfg* cfg, int64_t n_rays, const vipnerf_out* fwd_out, const vipnerf_loss_spec* spec,
+                         float* losses_dev, void* workspace, size_t workspace_bytes, void* stream) {
+  if (int rc = check_train_cfg(cfg)) return rc;
+  if (n_rays < 0) return fail(VIPNERF_EINVAL, "n_rays=%lld", (long long)n_rays);
+  if (!fwd_out || !spec || !losses_dev) return fail(VIPNERF_EINVAL, "fwd_out / spec / losses_dev is NULL");
+  if (spec->w_mse != 0.f && !spec->target_rgb) return fail(VIPNERF_EINVAL, "spec.target_rgb is NULL");
+  if (spec->mask_sparse_depth && !spec->sparse_depth) return fail(VIPNERF_EINVAL, "spec.sparse_depth is NULL");
+  const size_t need = (size_t)((n_rays + 3) / 4) * 16 * sizeof(float);
+  if (need > 0 && (!workspace || workspace_bytes < need || (reinterpret_cast<uintptr_t>(workspace) & 15u)))
+    return fail(VIPNERF_EWORKSPACE, "workspace %zu bytes (need %zu, 16-byte aligned)", workspace_bytes, need);
+  const bool has_fine = cfg->n_fine > 0;
+  const vipnerf_pass_out &c = fwd_out->coarse, &f = fwd_out->fine;
+  LossFwdArgs a{};
+  a.Sc = cfg->n_coarse; a.Sf = cfg->n_coarse + cfg->n_fine; a.V = cfg->n_sec_views;
+  a.rgb_c = c.rgb; a.pred_c = c.raw_visibility; a.trans_c = c.visibility; a.vis2_c = a.V > 0 ? c.visibility2 : nullptr;
+  if (has_fine) { a.rgb_f = f.rgb; a.pred_f = f.raw_visibility; a.trans_f = f.visibility; a.vis2_f = a.V > 0 ? f.visibility2 : nullptr; }
+  a.depth = has_fine ? f.depth : c.depth;
+  if (!a.rgb_c || !a.pred_c || !a.trans_c || (has_fine && (!a.rgb_f || !a.pred_f || !a.trans_f)) || !a.depth || (a.V > 0 && (!a.vis2_c || (has_fine && !a.vis2_f))))
+    return fail(VIPNERF_EINVAL, "fwd_out must hold rgb / raw_visibility / visibility / depth (/ visibility2) of every sample set");
+  const cudaError_t e = launch_fused_losses(a, to_loss_grad(spec, nullptr), n_rays, losses_dev, static_cast<float*>(workspace),
+                                            static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return fail_cuda(e, "fused_losses");
+  return VIPNERF_OK;
+}
+
 int vipnerf_train_backward(const vipnerf_cfg* cfg, const vipnerf_rays* rays, int64_t n_rays, const void* packed_coarse,
                            const void* packed_fine, const vipnerf_out* fwd_out, const vipnerf_out* grad_out,
                            const void* saved, size_t saved_bytes, float* const param_grads_coarse[24],
                            float* const param_grads_fine[24], void* workspace, size_t workspace_bytes, void* stream) {
+  return vipnerf_train_backward_fused(cfg, rays, n_rays, packed_coarse, packed_fine, fwd_out, grad_out, nullptr, nullptr, saved,
+                                      saved_bytes, param_grads_coarse, param_grads_fine, workspace, workspace_bytes, stream);
+}
+
+int vipnerf_train_backward_fused(const vipnerf_cfg* cfg, const vipnerf_rays* rays, int64_t n_rays, const void* packed_coarse,
+                                 const void* packed_fine, const vipnerf_out* fwd_out, const vipnerf_out* grad_out,
+                                 const vipnerf_loss_spec* spec, const float* upstream_dev,
+                                 const void* saved, size_t saved_bytes, float* const param_grads_coarse[24],
+                                 float* const param_grads_fine[24], void* workspace, size_t workspace_bytes, void* stream) {
   if (int rc = check_train_cfg(cfg)) return rc;
+  if (spec != nullptr && spec->losses_dev == nullptr) return fail(VIPNERF_EINVAL, "spec.losses_dev is NULL (run vipnerf_fused_losses first)");
+  static const vipnerf_out kNoGrads{};
+  if (grad_out == nullptr && spec != nullptr) grad_out = &kNoGrads;
   RayPtrs rp{};
   if (n_rays > 0)
     if (int rc = make_ray_ptrs(cfg, rays, &rp, false, false)) return rc;
@@ -589,10 +638,12 @@ int vipnerf_train_backward(const vipnerf_cfg* cfg, const vipnerf_rays* rays, int
     float* dsig = wf(B.dsig); float* dlogit = wf(B.dlogit); float* dpre = wf(B.dpre); float* dfeat = wf(B.dfeat);
     float* dacc9 = wf(B.dacc9); float* dhv = wf(B.dhv); float* partial = wf(B.partial);
 
-    // 1. volume_rendering backwards -> logit gradients per sample
+    // 1. volume_rendering backwards (+ the fused loss gradients) -> logit gradients per sample
+    LossGrad lgp = to_loss_grad(spec, upstream_dev);
+    lgp.depth_here = (has_fine ? pass == 1 : pass == 0) ? 1 : 0;
     e = launch_composite_bwd(rp, fl, n_rays, S, fo.z_vals, fo.raw_sigma, fo.raw_rgb, fo.raw_visibility,
                              cfg->n_sec_views ? fo.raw_visibility2 : nullptr,
-                             to_grads(pass ? &grad_out->fine : &grad_out->coarse), dsig, dlogit, s);
+                             to_grads(pass ? &grad_out->fine : &grad_out->coarse), lgp, dsig, dlogit, s);
     if (e != cudaSuccess) return fail_cuda(e, "composite_bwd");
     // 2. backward-data chain through the MLP
     MlpBwdArgs a{};
@@ -656,7 +707,7 @@ int vipnerf_composite_backward(const vipnerf_cfg* cfg, const vipnerf_rays* rays,
     return fail(VIPNERF_EINVAL, "z_vals / sigma / rgb / vis / grad_out / outputs is NULL");
   if (cfg->n_sec_views > 0 && !vis2) return fail(VIPNERF_EINVAL, "n_sec_views=%d but vis2 is NULL", cfg->n_sec_views);
   cudaError_t e = launch_composite_bwd(rp, make_flags(cfg), n_rays, n_samples, z_vals, sigma, rgb, vis, vis2,
-                                       to_grads(grad_out), d_sigma_logit, d_head_logits, static_cast<cudaStream_t>(stream));
+                                       to_grads(grad_out), LossGrad{}, d_sigma_logit, d_head_logits, static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return fail_cuda(e, "composite_bwd");
   return VIPNERF_OK;
 }

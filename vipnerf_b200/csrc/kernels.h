@@ -71,9 +71,33 @@ struct PassGradPtrs {  // upstream gradients of one sample set's outputs (null =
   const float *rgb, *acc, *depth, *depth_var, *depth_ndc, *depth_var_ndc, *visibility2;
   const float *alpha, *visibility, *weights, *raw_sigma, *raw_rgb, *raw_visibility, *raw_visibility2;
 };
+// The reference's four training losses fused into the compositing backward (loss_functions/MSE01.py:25-67,
+// VisibilityLoss01.py:26-74 with its mutual detach, VisibilityPriorLoss01.py:25-89, SparseDepthMSE01.py:26-71,
+// weighted as LossComputer01.py:33-69 does): k_composite_bwd forms dTotalLoss/d(output) analytically from the forward
+// values it re-computes anyway, so no [R,S] gradient tensor is written to or read from HBM.  enabled = 0: off.
+struct LossGrad {
+  const float* target_rgb;      // [R,3]
+  const uint8_t* mask_nerf;     // [R] bool, null = every ray
+  const uint8_t* mask_depth;    // [R] bool, null = no sparse-depth term
+  const float* sparse_depth;    // [R]
+  const float* prior;           // [R,V] visibility prior masks / weights, null = ones
+  const float* stats;           // device [8]: [5] = number of nerf rays, [6] = number of sparse-depth rays (launch_fused_losses)
+  const float* upstream;        // device scalar dL/dTotalLoss, null = 1
+  float w_mse, w_vis, w_prior, w_depth;
+  int depth_here;               // the sparse-depth loss reads THIS pass's depth map
+  int enabled;
+};
 cudaError_t launch_composite_bwd(const RayPtrs& rp, const RenderFlags& fl, int64_t n_rays, int S, const float* z,
                                  const float* sigma, const float* rgb, const float* vis, const float* vis2,
-                                 const PassGradPtrs& g, float* dsig, float* dlogit, cudaStream_t s);
+                                 const PassGradPtrs& g, const LossGrad& lg, float* dsig, float* dlogit, cudaStream_t s);
+// Loss values of one training batch from the forward outputs: losses_dev[0..4] = MSE, Visibility, VisibilityPrior,
+// SparseDepth, TotalLoss (weighted); [5], [6] = the mask counts the means divide by.  `partial`: 8 floats per 4 rays.
+struct LossFwdArgs {
+  const float *rgb_c, *rgb_f, *pred_c, *pred_f, *trans_c, *trans_f, *vis2_c, *vis2_f, *depth;   // depth: the pass SparseDepthMSE reads
+  int Sc, Sf, V;
+};
+cudaError_t launch_fused_losses(const LossFwdArgs& a, const LossGrad& lg, int64_t n_rays, float* losses_dev, float* partial,
+                                cudaStream_t s);
 // C[m][n] = sum_p A[p][m] * B[p][n] over n_rows rows (A: lda floats per row, M in {128, 256}; B: ldb floats per row,
 // N in {32, 64, 128, 256}), written to dst[m * ldc + n] for n < n_valid; bias_dst[m] = sum_p A[p][m] when non-null.
 // `partial` must hold gemm_tn_partial_floats() floats.

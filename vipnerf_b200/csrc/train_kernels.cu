@@ -27,7 +27,7 @@ template <int SPL>
 __global__ void __launch_bounds__(128)
 k_composite_bwd(RayPtrs rp, RenderFlags fl, int64_t n_rays, int S, const float* __restrict__ z,
                 const float* __restrict__ sigma, const float* __restrict__ rgb, const float* __restrict__ vis,
-                const float* __restrict__ vis2, PassGradPtrs G, float* __restrict__ dsig, float* __restrict__ dlogit) {
+                const float* __restrict__ vis2, PassGradPtrs G, LossGrad L, float* __restrict__ dsig, float* __restrict__ dlogit) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t ray = (int64_t)blockIdx.x * 4 + warp;
   if (ray >= n_rays) return;
@@ -101,9 +101,38 @@ k_composite_bwd(RayPtrs rp, RenderFlags fl, int64_t n_rays, int S, const float* 
 #pragma unroll
   for (int k = 0; k < 3; ++k) g_rgb[k] = G.rgb ? G.rgb[3 * ray + k] : 0.f;
   float g_acc = G.acc ? G.acc[ray] : 0.f;
+  // ---- fused losses: dTotalLoss/d(map) from the forward values re-computed above (LossGrad, kernels.h)
+  float lg_scale = 0.f, lg_vis = 0.f, lg_prior = 0.f, lg_depth = 0.f;
+  if (L.enabled) {
+    lg_scale = L.upstream ? *L.upstream : 1.f;
+    const bool m_nerf = L.mask_nerf ? L.mask_nerf[ray] != 0 : true;
+    const float n_nerf = L.stats[5], n_depth = L.stats[6];
+    if (m_nerf && n_nerf > 0.f && L.w_mse != 0.f) {     // MSE01: mean over rays of mean_c (rgb - target)^2
+      float cm[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+      for (int j = 0; j < SPL; ++j)
+        if (base + j < S) {
+          const float* c = rgb + (ray * S + base + j) * 3;
+          cm[0] += w[j] * c[0]; cm[1] += w[j] * c[1]; cm[2] += w[j] * c[2];
+        }
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        float m = warp_sum(cm[k]);
+        if (fl.white_bkgd) m += 1.f - acc;
+        g_rgb[k] += lg_scale * L.w_mse * 2.f * (m - L.target_rgb[3 * ray + k]) / (3.f * n_nerf);
+      }
+    }
+    // VisibilityLoss01: mean_{r,s} |pred - sg(T)| + |sg(pred) - T|  ->  +-sign / (R S) on the head output and on T
+    lg_vis = lg_scale * L.w_vis / ((float)n_rays * (float)S);
+    // VisibilityPriorLoss01: mean over nerf rays of sum_v prior (1 - visibility2)
+    lg_prior = (m_nerf && n_nerf > 0.f) ? -lg_scale * L.w_prior / n_nerf : 0.f;
+    // SparseDepthMSE01: mean over sparse-depth rays of (depth - gt)^2
+    if (L.depth_here && L.mask_depth && L.mask_depth[ray] != 0 && n_depth > 0.f)
+      lg_depth = lg_scale * L.w_depth * 2.f * (d_wld - L.sparse_depth[ray]) / n_depth;
+  }
   if (fl.white_bkgd) g_acc -= g_rgb[0] + g_rgb[1] + g_rgb[2];            // rgb += 1 - acc, :363-364
   // depth / depth_var are the world-space statistics; in NDC mode depth_ndc / depth_var_ndc are the native ones (:356-361)
-  const float gd_w = G.depth ? G.depth[ray] : 0.f;
+  const float gd_w = (G.depth ? G.depth[ray] : 0.f) + lg_depth;
   const float gv_w = G.depth_var ? G.depth_var[ray] : 0.f;
   const float gd_n = (ndc && G.depth_ndc) ? G.depth_ndc[ray] : 0.f;
   const float gv_n = (ndc && G.depth_var_ndc) ? G.depth_var_ndc[ray] : 0.f;
@@ -126,9 +155,9 @@ k_composite_bwd(RayPtrs rp, RenderFlags fl, int64_t n_rays, int S, const float* 
     gw[j] = t;
   }
   const bool has_v2 = V > 0 && vis2 != nullptr;
-  if (has_v2 && G.visibility2 != nullptr) {
+  if (has_v2 && (G.visibility2 != nullptr || lg_prior != 0.f)) {
     for (int v = 0; v < V; ++v) {
-      const float g2 = G.visibility2[ray * V + v];
+      const float g2 = (G.visibility2 ? G.visibility2[ray * V + v] : 0.f) + lg_prior * (L.prior ? L.prior[ray * V + v] : 1.f);
       float m = 0.f;
 #pragma unroll
       for (int j = 0; j < SPL; ++j)
@@ -148,7 +177,11 @@ k_composite_bwd(RayPtrs rp, RenderFlags fl, int64_t n_rays, int S, const float* 
     const int i = base + j;
     const bool valid = i < S;
     ga[j] = gw[j] * tr[j] + ((valid && G.alpha) ? G.alpha[ray * S + i] : 0.f);
-    const float gt = gw[j] * al[j] + ((valid && G.visibility) ? G.visibility[ray * S + i] : 0.f);
+    float gt = gw[j] * al[j] + ((valid && G.visibility) ? G.visibility[ray * S + i] : 0.f);
+    if (valid && lg_vis != 0.f) {   // d|sg(pred) - T| / dT
+      const float d = tr[j] - vis[ray * S + i];
+      gt += d > 0.f ? lg_vis : (d < 0.f ? -lg_vis : 0.f);
+    }
     x[j] = valid ? gt * tr[j] : 0.f;
     loc += x[j];
   }
@@ -189,13 +222,20 @@ k_composite_bwd(RayPtrs rp, RenderFlags fl, int64_t n_rays, int S, const float* 
       of[k] = gc * c * (1.f - c);
     }
     const float sv = vis[p];
-    of[3] = G.raw_visibility ? G.raw_visibility[p] * sv * (1.f - sv) : 0.f;
+    float g_sv = G.raw_visibility ? G.raw_visibility[p] : 0.f;
+    if (lg_vis != 0.f) {            // d|pred - sg(T)| / dpred
+      const float d = sv - tr[j];
+      g_sv += d > 0.f ? lg_vis : (d < 0.f ? -lg_vis : 0.f);
+    }
+    of[3] = g_sv * sv * (1.f - sv);
     *reinterpret_cast<float4*>(dlogit + p * nviews * 4) = o;
     for (int v = 0; v < V; ++v) {
       float gl = 0.f;
       if (has_v2) {
         const float s2 = vis2[p * V + v];
-        float gv = G.visibility2 ? w[j] * G.visibility2[ray * V + v] * inv : 0.f;
+        float gv = (G.visibility2 || lg_prior != 0.f)
+                       ? w[j] * ((G.visibility2 ? G.visibility2[ray * V + v] : 0.f) + lg_prior * (L.prior ? L.prior[ray * V + v] : 1.f)) * inv
+                       : 0.f;
         if (G.raw_visibility2) gv += G.raw_visibility2[p * V + v];
         gl = gv * s2 * (1.f - s2);
       }
@@ -567,14 +607,86 @@ cudaError_t launch_heads_bwd(int64_t n_points, int nviews, const void* packed, c
   return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Values of the four training losses from the forward outputs (LossGrad / LossFwdArgs, kernels.h): one warp per ray
+// accumulates the ray's terms, a block writes its nine partial sums, k_fused_losses_final adds the blocks in a fixed
+// order (bit-reproducible) and applies the means and the weights of LossComputer01.compute_losses (:33-51).
+__global__ void __launch_bounds__(128) k_fused_losses_partial(LossFwdArgs a, LossGrad L, int64_t n_rays, float* __restrict__ partial) {
+  __shared__ float sh[4][9];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t ray = (int64_t)blockIdx.x * 4 + warp;
+  float t[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) t[i] = 0.f;
+  if (ray < n_rays) {
+    const bool m_nerf = L.mask_nerf ? L.mask_nerf[ray] != 0 : true;
+    const bool m_depth = L.mask_depth ? L.mask_depth[ray] != 0 : false;
+    if (lane < 3 && m_nerf) {            // MSE01.py:52-58: sum_c (rgb - target)^2
+      const float tg = L.target_rgb[3 * ray + lane];
+      if (a.rgb_c) { const float d = a.rgb_c[3 * ray + lane] - tg; t[0] = d * d; }
+      if (a.rgb_f) { const float d = a.rgb_f[3 * ray + lane] - tg; t[1] = d * d; }
+    }
+    if (a.pred_c) for (int i = lane; i < a.Sc; i += 32) t[2] += fabsf(a.pred_c[ray * a.Sc + i] - a.trans_c[ray * a.Sc + i]);   // VisibilityLoss01.py:70-74
+    if (a.pred_f) for (int i = lane; i < a.Sf; i += 32) t[3] += fabsf(a.pred_f[ray * a.Sf + i] - a.trans_f[ray * a.Sf + i]);
+    if (m_nerf && lane < a.V) {          // VisibilityPriorLoss01.py:76-80: sum_v prior (1 - visibility2)
+      const float pr = L.prior ? L.prior[ray * a.V + lane] : 1.f;
+      if (a.vis2_c) t[4] = pr * (1.f - a.vis2_c[ray * a.V + lane]);
+      if (a.vis2_f) t[5] = pr * (1.f - a.vis2_f[ray * a.V + lane]);
+    }
+    if (lane == 0) {
+      if (m_depth && a.depth) { const float d = a.depth[ray] - L.sparse_depth[ray]; t[6] = d * d; }   // SparseDepthMSE01.py:60-63
+      t[7] = m_nerf ? 1.f : 0.f;
+      t[8] = m_depth ? 1.f : 0.f;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 9; ++i) {
+    const float v = warp_sum(t[i]);
+    if (lane == 0) sh[warp][i] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 9) partial[(int64_t)blockIdx.x * 16 + threadIdx.x] = (sh[0][threadIdx.x] + sh[1][threadIdx.x]) + (sh[2][threadIdx.x] + sh[3][threadIdx.x]);
+}
+__global__ void k_fused_losses_final(const float* __restrict__ partial, int n_blocks, LossFwdArgs a, LossGrad L, int64_t n_rays,
+                                     float* __restrict__ out) {
+  __shared__ double tot[9];
+  if (threadIdx.x < 9) {
+    double acc = 0.0;
+    for (int b = 0; b < n_blocks; ++b) acc += (double)partial[(int64_t)b * 16 + threadIdx.x];
+    tot[threadIdx.x] = acc;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const double n_nerf = tot[7], n_depth = tot[8];
+    const double mse = n_nerf > 0 ? (tot[0] + tot[1]) / (3.0 * n_nerf) : 0.0;
+    double vis = 0.0;
+    // mean|pred - sg(T)| + mean|sg(pred) - T|: the same value twice (the detaches only split the gradient, :57-58)
+    if (a.pred_c) vis += 2.0 * tot[2] / ((double)n_rays * a.Sc);
+    if (a.pred_f) vis += 2.0 * tot[3] / ((double)n_rays * a.Sf);
+    const double prior = (n_nerf > 0 && a.V > 0) ? (tot[4] + tot[5]) / n_nerf : 0.0;
+    const double depth = n_depth > 0 ? tot[6] / n_depth : 0.0;
+    out[0] = (float)mse; out[1] = (float)vis; out[2] = (float)prior; out[3] = (float)depth;
+    out[4] = (float)(L.w_mse * mse + L.w_vis * vis + L.w_prior * prior + L.w_depth * depth);
+    out[5] = (float)n_nerf; out[6] = (float)n_depth; out[7] = 0.f;
+  }
+}
+
+cudaError_t launch_fused_losses(const LossFwdArgs& a, const LossGrad& lg, int64_t n_rays, float* losses_dev, float* partial,
+                                cudaStream_t s) {
+  const int n_blocks = (int)((n_rays + 3) / 4);
+  if (n_blocks > 0) k_fused_losses_partial<<<n_blocks, 128, 0, s>>>(a, lg, n_rays, partial);
+  k_fused_losses_final<<<1, 32, 0, s>>>(partial, n_blocks, a, lg, n_rays, losses_dev);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_composite_bwd(const RayPtrs& rp, const RenderFlags& fl, int64_t n_rays, int S, const float* z,
                                  const float* sigma, const float* rgb, const float* vis, const float* vis2,
-                                 const PassGradPtrs& g, float* dsig, float* dlogit, cudaStream_t s) {
+                                 const PassGradPtrs& g, const LossGrad& lg, float* dsig, float* dlogit, cudaStream_t s) {
   if (n_rays == 0) return cudaSuccess;
   const unsigned grid = (unsigned)((n_rays + 3) / 4);
   const int spl = (S + 31) / 32;
 #define VIPNERF_LAUNCH_CBWD(SPL) \
-  k_composite_bwd<SPL><<<grid, 128, 0, s>>>(rp, fl, n_rays, S, z, sigma, rgb, vis, vis2, g, dsig, dlogit)
+  k_composite_bwd<SPL><<<grid, 128, 0, s>>>(rp, fl, n_rays, S, z, sigma, rgb, vis, vis2, g, lg, dsig, dlogit)
   if (spl <= 2) VIPNERF_LAUNCH_CBWD(2);
   else if (spl <= 6) VIPNERF_LAUNCH_CBWD(6);
   else VIPNERF_LAUNCH_CBWD(8);

@@ -53,9 +53,38 @@ def _aligned_bytes(n_bytes: int, device) -> torch.Tensor:
     return buf[off:off + n_bytes]
 
 
+class TrainOutputs(dict):
+    """The train-mode output dict of the plugin (a plain dict for every consumer) that also carries what
+    LossComputerFused needs to fuse the reference's losses into the backward: `fused` = {'token', 'state', 'cfg_kwargs'}."""
+    fused: Optional[dict] = None
+
+
+class FusedLossState:
+    """Shared between the forward's autograd node and LossComputerFused: the loss description the backward should
+    differentiate inside the compositing-backward kernel (None = only the dense upstream gradients)."""
+
+    def __init__(self):
+        self.loss_spec = None        # _lib.LossSpec
+        self.keepalive = None        # tensors the spec points into
+
+
+class _FusedTotal(torch.autograd.Function):
+    """TotalLoss of the fused losses: its value comes from vipnerf_fused_losses; its gradient travels to the render's
+    autograd node as the gradient of a scalar token - the dense dLoss/dOutput tensors never exist."""
+
+    @staticmethod
+    def forward(ctx, token: torch.Tensor, losses_dev: torch.Tensor):
+        return losses_dev[4].clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.reshape(()).to(torch.float32), None
+
+
 class _RenderTrain(torch.autograd.Function):
     """forward(spec, *params): params = the 24 tensors of the coarse MLP in renderpath.MLP_PARAM_ORDER, then the 24 of
-    the fine MLP (if any).  Returns the output tensors in spec['out_names'] order."""
+    the fine MLP (if any).  Returns the output tensors in spec['out_names'] order, then a scalar token whose gradient
+    is the upstream gradient of a fused TotalLoss (FusedLossState)."""
 
     @staticmethod
     def forward(ctx, spec: dict, *params: torch.Tensor):
@@ -95,14 +124,15 @@ class _RenderTrain(torch.autograd.Function):
                 packed_c.data_ptr(), packed_f.data_ptr() if has_fine else None, ctypes.byref(out), saved.data_ptr(),
                 saved_bytes, ws.data_ptr(), ws_bytes, renderpath._stream(device)), 'vipnerf_train_forward')
         out_names = spec['out_names']
-        outputs = tuple(tensors[n] for n in out_names)
+        token = torch.zeros((), dtype=torch.float32, device=device)
+        outputs = tuple(tensors[n] for n in out_names) + (token,)
         ctx.mark_non_differentiable(*[tensors[n] for n in out_names if n.startswith('z_vals_')])
         ctx.spec = spec
         ctx.n_params = len(params)
         ctx.param_shapes = [tuple(p.shape) for p in params]
         ctx.set_materialize_grads(False)
         # the ray tensors stay alive through spec['batch'] (a dict this module owns)
-        ctx.save_for_backward(saved, packed_c, packed_f if has_fine else packed_c, *outputs)
+        ctx.save_for_backward(saved, packed_c, packed_f if has_fine else packed_c, *outputs[:-1])
         return outputs
 
     @staticmethod
@@ -123,6 +153,12 @@ class _RenderTrain(torch.autograd.Function):
         keep: list = []
         rays = renderpath._make_rays(spec['batch'], spec['ndc'], n_coarse, n_fine, V, keep)
         fwd, gout = _lib.Out(), _lib.Out()
+        token_grad = grads[len(out_names)] if len(grads) > len(out_names) else None
+        state = spec.get('fused_state')
+        loss_spec = state.loss_spec if (state is not None and token_grad is not None) else None
+        if token_grad is not None:
+            token_grad = renderpath._f32c(token_grad, 'grad of the loss token')
+            keep.append(token_grad)
         for name, t, g in zip(out_names, outputs, grads):
             key, tag = name.rsplit('_', 1)
             setattr(getattr(fwd, tag), key, t.data_ptr())
@@ -137,10 +173,11 @@ class _RenderTrain(torch.autograd.Function):
             saved_bytes = lib.vipnerf_train_saved_bytes(ctypes.byref(cfg), R)
             ws_bytes = lib.vipnerf_train_workspace_bytes(ctypes.byref(cfg), R)
             ws = renderpath._workspace(ws_bytes, device)
-            _lib.check(lib.vipnerf_train_backward(
+            _lib.check(lib.vipnerf_train_backward_fused(
                 ctypes.byref(cfg), ctypes.byref(rays), R, packed_c.data_ptr(), packed_f.data_ptr() if has_fine else None,
-                ctypes.byref(fwd), ctypes.byref(gout), saved.data_ptr(), saved_bytes, arr_c, arr_f, ws.data_ptr(),
-                ws_bytes, renderpath._stream(device)), 'vipnerf_train_backward')
+                ctypes.byref(fwd), ctypes.byref(gout), ctypes.byref(loss_spec) if loss_spec is not None else None,
+                token_grad.data_ptr() if loss_spec is not None else None, saved.data_ptr(), saved_bytes, arr_c, arr_f,
+                ws.data_ptr(), ws_bytes, renderpath._stream(device)), 'vipnerf_train_backward_fused')
         return (None, *param_grads)
 
 
@@ -159,11 +196,15 @@ def render_rays_train(batch: Dict[str, torch.Tensor], params_coarse: Dict[str, t
     names = renderpath.MLP_PARAM_ORDER
     keys = renderpath.pass_keys(ndc, True, n_sec_views)
     out_names = [f'{k}_coarse' for k in keys] + ([f'{k}_fine' for k in keys] if has_fine else [])
+    state = FusedLossState()
     spec = dict(batch=batch, ndc=ndc, n_coarse=n_coarse, n_fine=n_fine, n_sec_views=n_sec_views, white_bkgd=white_bkgd,
-                lindisp=lindisp, has_fine=has_fine, out_names=out_names, tf32=bool(tf32))
+                lindisp=lindisp, has_fine=has_fine, out_names=out_names, tf32=bool(tf32), fused_state=state)
     params = [params_coarse[k] for k in names] + ([params_fine[k] for k in names] if has_fine else [])
     outputs = _RenderTrain.apply(spec, *params)
-    result = dict(zip(out_names, outputs))
+    result = TrainOutputs(zip(out_names, outputs[:-1]))
+    result.fused = {'token': outputs[-1], 'state': state,
+                    'cfg_kwargs': dict(n_coarse=n_coarse, n_fine=n_fine if has_fine else 0, n_sec_views=n_sec_views, ndc=ndc,
+                                       white_bkgd=white_bkgd, lindisp=lindisp, precision='fp32', train_tf32=bool(tf32))}
     for tag in ('coarse', 'fine'):
         if f'raw_rgb_{tag}' in result:   # the reference returns the same tensor under both names (:531)
             result[f'raw_rgb_view_dependent_{tag}'] = result[f'raw_rgb_{tag}']
