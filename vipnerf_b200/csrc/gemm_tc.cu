@@ -251,16 +251,19 @@ cudaError_t encode_rows_map(CUtensorMap* map, const float* base, int ld, int col
 // The TMA engine loads [128 points x 32 k] and [N x 32 k] boxes (plain 128-byte swizzle, tf32 rounding) into a 2-stage
 // ring, one thread issues four K=8 MMAs per box pair (M=128 points, N columns, accumulators in N TMEM columns), and
 // four epilogue warps drain TMEM row by row: + bias, + a rank-1 term (the density head's contribution to dL/dh8),
-// ReLU, ReLU-mask from a saved activation, 128-byte stores.  Up to two (X, W) pairs accumulate into the same tile
-// (the skip layer's cat([encoding, h4]) input).  Persistent, one CTA per SM: a 4-stage ring (192 KiB) keeps loads in
+// ReLU, ReLU-mask from a saved activation; outputs and masks move as [32 x 32] boxes through shared memory and the TMA
+// engine (bulk tensor stores / loads).  Up to two (X, W) pairs accumulate into the same tile
+// (the skip layer's cat([encoding, h4]) input).  Persistent, one CTA per SM: a 3-stage ring (144 KiB) keeps loads in
 // flight across tile boundaries and the two 256-column TMEM accumulators alternate, so the epilogue of one 128-point
 // tile overlaps the loads and MMAs of the next.
 // Roofline: HBM - K*4 bytes read and N*4 written (+ N*4 for a mask) per point; the weights come from L2.
-constexpr int kLinStages = 4;
+constexpr int kLinStages = 3;
 constexpr int kLinRows = 128;
+constexpr int kLinStageBytes = 4 * 16384;   // epilogue staging: per epilogue warp 2 output boxes + 2 mask boxes of 4 KiB
 
 struct LinearTcParams {
   CUtensorMap map_a[2], map_b[2];
+  CUtensorMap map_out, map_mask;   // [32 columns x 32 rows] boxes of the output / the mask array (plain fp32)
   int chunks[2];
   int N;
   int64_t n_rows;
@@ -291,13 +294,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_linear_tf32(const __grid_cons
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t a_bytes = kLinRows * 128, b_bytes = (uint32_t)p.N * 128;
   const uint32_t stage_bytes = a_bytes + b_bytes;
-  uint8_t* tail = smem + kLinStages * stage_bytes;
-  uint32_t* tmem_ptr_slot = reinterpret_cast<uint32_t*>(tail + 8 * (2 * kLinStages + 4));
+  uint8_t* stage_base = smem + kLinStages * stage_bytes;      // 1 KiB aligned: stage_bytes is a multiple of 16 KiB
+  uint8_t* tail = stage_base + kLinStageBytes;
+  uint32_t* tmem_ptr_slot = reinterpret_cast<uint32_t*>(tail + 8 * (2 * kLinStages + 4 + 8));
   const uint32_t bar0 = smem_u32(tail);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (kLinStages + s); };
   auto acc_full = [&](int b) { return bar0 + 8u * (2 * kLinStages + b); };
   auto acc_empty = [&](int b) { return bar0 + 8u * (2 * kLinStages + 2 + b); };
+  auto mask_full = [&](int w, int b) { return bar0 + 8u * (2 * kLinStages + 4 + 2 * w + b); };
   const int n_chunks = p.chunks[0] + p.chunks[1];
   const int n_tiles = (int)((p.n_rows + kLinRows - 1) / kLinRows);
 
@@ -305,6 +310,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_linear_tf32(const __grid_cons
     if ((smem_u32(smem) & 1023u) != 0) { printf("vipnerf linear_tc: shared memory base not 1 KiB aligned\n"); __trap(); }
     for (int s = 0; s < kLinStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(acc_full(b), 1); mbar_init(acc_empty(b), 4); }   // one arrival per epilogue warp
+    for (int w = 0; w < 4; ++w) { mbar_init(mask_full(w, 0), 1); mbar_init(mask_full(w, 1), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -362,100 +368,79 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_linear_tf32(const __grid_cons
   } else {
     const int quarter = warp & 3;
     int i = 0;
+    uint32_t mask_n = 0;    // mask boxes consumed so far by this warp (buffer = mask_n & 1, phase = (mask_n >> 1) & 1)
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++i) {
       const int buf = i & 1;
       const int64_t pg = (int64_t)tile * kLinRows + quarter * 32 + lane;
       const bool valid = pg < p.n_rows;
-      if (p.mask != nullptr && valid) {   // this row's ReLU mask (1 KiB from HBM) travels to L2 while the MMAs of the tile run
-#pragma unroll
-        for (int c = 0; c < 8; ++c)
-          if (c * 32 < p.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.mask + pg * p.ld_mask + c * 32));
-      }
       mbar_wait(acc_full(buf), (i >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#ifdef VIPNERF_LINEAR_EPILOGUE_V2
-      // EXPERIMENT (not in the default build; enable with VIPNERF_NVCC_DEFINES=VIPNERF_LINEAR_EPILOGUE_V2): each 32 x 32
-      // chunk goes through a 4 KiB shared buffer (XOR-swizzled 16-byte columns) so that every global instruction of a
-      // warp covers four full 128-byte lines instead of 32 partial ones.  A first version of this measured 2x SLOWER
-      // than the row-per-lane epilogue below because its mask loads sat behind per-row branches and were issued one
-      // DRAM latency at a time; here all eight are predicated and issued before the first use.  Unmeasured.
+      // Epilogue through shared memory and the TMA engine.  A lane owns one accumulator row, so direct global accesses
+      // touch 32 different 128-byte lines per instruction (the r01 kernel ran at 0.45 of the HBM roofline because of it).
+      // Instead every warp stages its [32 rows x 32 columns] chunk in a swizzled 4 KiB box and ONE bulk tensor store
+      // writes it (full lines, asynchronous, rows past the end clipped by the tensor map); the ReLU mask of the
+      // backward chain arrives the same way (bulk tensor load of the saved activation's box, one chunk ahead).
       {
-        float* stage = reinterpret_cast<float*>(tail + 128) + (warp - 2) * 1024;
-        const int cq = lane & 7, rsub = lane >> 3;
-        const int64_t row_base = (int64_t)tile * kLinRows + quarter * 32;
-        for (int c = 0; c < p.N / 32; ++c) {
+        uint8_t* wstage = stage_base + (warp - 2) * 16384;             // [2] output boxes, then [2] mask boxes
+        const uint32_t out_s = smem_u32(wstage), msk_s = out_s + 8192;
+        const uint32_t mfull0 = mask_full(warp - 2, 0);
+        const int row0 = tile * kLinRows + quarter * 32;
+        const int n_ch = p.N / 32;
+        const bool has_mask = p.mask != nullptr;
+        if (has_mask && lane == 0) {
+          mbar_expect_tx(mfull0 + 8u * (mask_n & 1), 4096);
+          tma_load_2d(msk_s + 4096u * (mask_n & 1), &p.map_mask, 0, row0, mfull0 + 8u * (mask_n & 1));
+        }
+        const float r1 = (p.rank1_row != nullptr && valid) ? p.rank1_row[pg] : 0.f;
+        for (int c = 0; c < n_ch; ++c, ++mask_n) {
           uint32_t v[32];
           tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * 256 + c * 32, v);
-          const int col = c * 32 + 4 * cq;
-          float4 m[8];
-          float r1[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {   // independent of the accumulator: in flight while tcgen05.ld completes
-            const int64_t row = row_base + j * 4 + rsub;
-            const bool ok = row < p.n_rows;
-            m[j] = (p.mask != nullptr && ok) ? *reinterpret_cast<const float4*>(p.mask + row * p.ld_mask + col)
-                                             : make_float4(1.f, 1.f, 1.f, 1.f);
-            r1[j] = (p.rank1_row != nullptr && ok) ? p.rank1_row[row] : 0.f;
+          if (has_mask && lane == 0 && c + 1 < n_ch) {                  // next chunk's mask box (its buffer was read at c - 1)
+            mbar_expect_tx(mfull0 + 8u * ((mask_n + 1) & 1), 4096);
+            tma_load_2d(msk_s + 4096u * ((mask_n + 1) & 1), &p.map_mask, (c + 1) * 32, row0, mfull0 + 8u * ((mask_n + 1) & 1));
           }
-          float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f), u4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (p.bias != nullptr) bias4 = *reinterpret_cast<const float4*>(p.bias + col);
-          if (p.rank1_row != nullptr) u4 = *reinterpret_cast<const float4*>(p.rank1_col + col);
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-          for (int q = 0; q < 8; ++q)
-            *reinterpret_cast<float4*>(stage + lane * 32 + 4 * (q ^ (lane & 7))) =
-                make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
-                            __uint_as_float(v[4 * q + 3]));
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the store issued two chunks ago has read its box
           __syncwarp();
+          if (has_mask) mbar_wait(mfull0 + 8u * (mask_n & 1), (mask_n >> 1) & 1);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          const uint32_t orow = out_s + 4096u * (c & 1) + lane * 128, mrow = msk_s + 4096u * (mask_n & 1) + lane * 128;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int r = j * 4 + rsub;
-            float4 o = *reinterpret_cast<const float4*>(stage + r * 32 + 4 * (cq ^ (r & 7)));
-            o.x = fmaf(r1[j], u4.x, o.x + bias4.x); o.y = fmaf(r1[j], u4.y, o.y + bias4.y);
-            o.z = fmaf(r1[j], u4.z, o.z + bias4.z); o.w = fmaf(r1[j], u4.w, o.w + bias4.w);
+          for (int q = 0; q < 8; ++q) {
+            float4 o = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
+                                   __uint_as_float(v[4 * q + 3]));
+            if (p.bias != nullptr) {
+              const float4 b = *reinterpret_cast<const float4*>(p.bias + c * 32 + 4 * q);
+              o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+            }
+            if (p.rank1_row != nullptr) {
+              const float4 u = *reinterpret_cast<const float4*>(p.rank1_col + c * 32 + 4 * q);
+              o.x = fmaf(r1, u.x, o.x); o.y = fmaf(r1, u.y, o.y); o.z = fmaf(r1, u.z, o.z); o.w = fmaf(r1, u.w, o.w);
+            }
             if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-            o.x = m[j].x > 0.f ? o.x : 0.f; o.y = m[j].y > 0.f ? o.y : 0.f; o.z = m[j].z > 0.f ? o.z : 0.f; o.w = m[j].w > 0.f ? o.w : 0.f;
-            if (row_base + r < p.n_rows) *reinterpret_cast<float4*>(p.out + (row_base + r) * p.ld_out + col) = o;
+            const uint32_t sw = (uint32_t)((q ^ (lane & 7)) << 4);    // 128-byte swizzle: 16-byte chunk index ^ (row % 8)
+            if (has_mask) {
+              float4 m;
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(m.x), "=f"(m.y), "=f"(m.z), "=f"(m.w) : "r"(mrow + sw));
+              o.x = m.x > 0.f ? o.x : 0.f; o.y = m.y > 0.f ? o.y : 0.f; o.z = m.z > 0.f ? o.z : 0.f; o.w = m.w > 0.f ? o.w : 0.f;
+            }
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(orow + sw), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w) : "memory");
           }
-          __syncwarp();   // the buffer is rewritten by the next chunk
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) {
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+                         ::"l"(&p.map_out), "r"(c * 32), "r"(row0), "r"(out_s + 4096u * (c & 1)) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
         }
       }
       (void)valid;
-#else
-      const float r1 = (p.rank1_row != nullptr && valid) ? p.rank1_row[pg] : 0.f;
-      for (int c = 0; c < p.N / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * 256 + c * 32, v);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (!valid) continue;
-        float4* dst = reinterpret_cast<float4*>(p.out + pg * p.ld_out + c * 32);
-        const float4* msk = p.mask ? reinterpret_cast<const float4*>(p.mask + pg * p.ld_mask + c * 32) : nullptr;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          float4 o = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
-                                 __uint_as_float(v[4 * q + 3]));
-          if (p.bias != nullptr) {
-            const float4 b = *reinterpret_cast<const float4*>(p.bias + c * 32 + 4 * q);
-            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
-          }
-          if (p.rank1_row != nullptr) {
-            const float4 u = *reinterpret_cast<const float4*>(p.rank1_col + c * 32 + 4 * q);
-            o.x = fmaf(r1, u.x, o.x); o.y = fmaf(r1, u.y, o.y); o.z = fmaf(r1, u.z, o.z); o.w = fmaf(r1, u.w, o.w);
-          }
-          if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-          if (msk != nullptr) {
-            const float4 m = msk[q];
-            o.x = m.x > 0.f ? o.x : 0.f; o.y = m.y > 0.f ? o.y : 0.f; o.z = m.z > 0.f ? o.z : 0.f; o.w = m.w > 0.f ? o.w : 0.f;
-          }
-          dst[q] = o;
-        }
-      }
-#endif
       // this warp's TMEM reads of the accumulator are complete: hand it back to the MMA warp
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty(buf));
     }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // shared memory outlives the last stores
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -466,14 +451,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_linear_tf32(const __grid_cons
 }
 
 // [rows][ld] fp32 row-major, first `cols` columns; box = 32 columns x box_rows rows, plain 128-byte swizzle, tf32 rounding
-cudaError_t encode_kmajor_map(CUtensorMap* map, const float* base, int ld, int cols, int64_t rows, int box_rows) {
+// (exact_fp32: no rounding - the epilogue's output / mask boxes)
+cudaError_t encode_kmajor_map(CUtensorMap* map, const float* base, int ld, int cols, int64_t rows, int box_rows,
+                              bool exact_fp32 = false) {
   EncodeTiledFn encode = get_encode_tiled();
   if (encode == nullptr) return cudaErrorNotSupported;
   const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   const cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
   const cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
   const cuuint32_t elem_strides[2] = {1, 1};
-  const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 2, const_cast<float*>(base), dims, strides, box,
+  const CUresult r = encode(map, exact_fp32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 2,
+                            const_cast<float*>(base), dims, strides, box,
                             elem_strides, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
@@ -497,11 +485,15 @@ cudaError_t launch_linear_tc(const LinearTcArgs& a, cudaStream_t s) {
   if (a.k[1] == 0) { p.map_a[1] = p.map_a[0]; p.map_b[1] = p.map_b[0]; }
   p.N = a.N; p.n_rows = a.n_rows; p.bias = a.bias; p.rank1_row = a.rank1_row; p.rank1_col = a.rank1_col;
   p.mask = a.mask; p.ld_mask = a.ld_mask; p.relu = a.relu ? 1 : 0; p.out = a.out; p.ld_out = a.ld_out;
-#ifdef VIPNERF_LINEAR_EPILOGUE_V2
-  const size_t smem = (size_t)kLinStages * (kLinRows * 128 + a.N * 128) + 128 + 4 * 4096;   // + the transpose buffers
-#else
-  const size_t smem = (size_t)kLinStages * (kLinRows * 128 + a.N * 128) + 128;
-#endif
+  if ((reinterpret_cast<uintptr_t>(a.out) & 15u) || (a.ld_out & 3) || (a.mask && ((reinterpret_cast<uintptr_t>(a.mask) & 15u) || (a.ld_mask & 3))))
+    return cudaErrorInvalidValue;
+  if ((e = encode_kmajor_map(&p.map_out, a.out, a.ld_out, a.N, a.n_rows, 32, true)) != cudaSuccess) return e;
+  if (a.mask != nullptr) {
+    if ((e = encode_kmajor_map(&p.map_mask, a.mask, a.ld_mask, a.N, a.n_rows, 32, true)) != cudaSuccess) return e;
+  } else {
+    p.map_mask = p.map_out;
+  }
+  const size_t smem = (size_t)kLinStages * (kLinRows * 128 + a.N * 128) + kLinStageBytes + 256;
   if ((e = cudaFuncSetAttribute(k_linear_tf32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
   int dev = 0, sms = 0;
   if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
