@@ -169,7 +169,7 @@ SavedLayout carve_saved(const vipnerf_cfg* cfg, int64_t n_rays) {
 // tiles (the latter: one 256 x 256 tile per SM, up to 160 SMs), followed by the column-sum partials.
 constexpr size_t kColsumPartialFloats = 4 * 148 * 256;
 size_t gemm_partial_floats() {
-  const size_t a = gemm_tn_partial_floats(), b = gemm_tn_tc_partial_floats(160);
+  const size_t a = gemm_tn_partial_floats(), b = gemm_tn_tc_partial_floats(kGemmTcMaxSplits);
   return a > b ? a : b;
 }
 

@@ -514,7 +514,8 @@ cudaError_t launch_gemm_tn_tc(const float* A, int lda, int M, const float* B, in
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
   if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
-  int64_t n_split = sms;
+  // the split-reduction scratch is sized for kGemmTcMaxSplits partial tiles (api.cu: gemm_tn_tc_partial_floats(160))
+  int64_t n_split = sms < kGemmTcMaxSplits ? sms : kGemmTcMaxSplits;
   const int64_t max_by_rows = (n_rows + 4 * kTcRows - 1) / (4 * kTcRows);
   if (n_split > max_by_rows) n_split = max_by_rows;
   int64_t rows_per_split = (n_rows + n_split - 1) / n_split;

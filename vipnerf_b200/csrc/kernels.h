@@ -109,6 +109,7 @@ cudaError_t launch_reduce_partials(const float* partial, int n_split, int M, int
 cudaError_t launch_colsum(const float* A, int lda, int M, int64_t n_rows, float* dst, float* partial, cudaStream_t s);
 // gemm_tc.cu : the same product on the tensor cores (tcgen05 kind::tf32 reading the fp32 arrays through TMA), N = 256,
 // M in {128, 256}; no bias output (launch_colsum).  `partial`: gemm_tn_tc_partial_floats(#SMs) floats.
+constexpr int kGemmTcMaxSplits = 160;   // point ranges (one CTA each) the scratch of the tensor-core product is sized for
 size_t gemm_tn_tc_partial_floats(int sms);
 cudaError_t launch_gemm_tn_tc(const float* A, int lda, int M, const float* B, int ldb, int64_t n_rows, float* dst,
                               int ldc, int n_valid, float* partial, cudaStream_t s);
