@@ -1,22 +1,29 @@
 #!/usr/bin/env python
 """Benchmark of the ViP-NeRF volumetric render path (BASELINE.json metric: rays/sec, coarse+fine 64+128).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision bf16|bf16x3|fp32]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision bf16|fp16|bf16x3|fp32]
 
 A "step" is one pass of the hot path over one 4096-ray batch (the reference's `chunk`) of the workload
 BASELINE.json quotes the metric on: LLFF 'fern' camera (NDC), 64 coarse + 128 fine samples, visibility head
 on, eval forward (retraw=False, sec_views_vis=False).  Synthetic rays from the real fern intrinsics,
 random-init weights of the reference architecture.
 
-Prints ONE JSON line (rank 0).  `value` = whole-job rays/s with inputs resident in HBM (one fused kernel per
-step, CUDA events on the launching stream, L2 flushed between steps, max over ranks); `e2e` = the same metric
-through the reference-facing plugin (`model(batch)`) with pinned HOST inputs copied in and the rendered maps
-copied back inside the timed region (+ the single NCCL gather when N > 1); `roofline` = algorithmic FLOPs of
-the fused kernel / its measured duration against the measured dense-bf16 peak; `cpu_baseline` = the CPU oracle
-(port of the reference's PyTorch path) on this box's host cores on a bounded sample.
+Prints ONE JSON line (rank 0):
+  value            whole-job rays/s with inputs resident in HBM (one fused kernel per step, CUDA events on the launching
+                   stream, L2 flushed between steps, max over ranks)
+  parity_check     the maps of the LAST TIMED launch against the CPU oracle on 512 strided rays (untimed); the run exits
+                   non-zero when a gate fails (also for precision_modes, e2e result and the sharded == unsharded check)
+  e2e              the same metric through the reference-facing plugin with pinned HOST inputs copied in and the rendered
+                   maps copied back inside the timed region (N > 1: the maps of ALL ranks, gathered on rank 0 by the render
+                   kernels' peer stores); pipelined and with a host sync per step; the per-tensor flow for comparison
+  roofline         algorithmic FLOPs of the fused kernel / its measured duration against the measured BURST dense-bf16
+                   peak (the kernel is timed alone); `sustained` = 65,536-ray launches back to back vs the sustained peak
+  precision_modes  rays/s and parity of the fp16 and bf16x3 arithmetics of the same kernel on the same batch
+  train            the 4096-ray training iteration (tensor-core chains, fused losses), ms per step and tensor roofline
+  cpu_baseline     the reference's CPU path on this box's host cores on a bounded sample
 
---impl reference times the reference's own algorithm on the host CPU (the oracle port; the reference itself is
-pure Python and is not present on the GPU box), rank 0 only.
+--impl reference times the reference's own CPU implementation of the path (the UNMODIFIED reference staged under
+oracle/_ref, else the oracle port), rank 0 only, on the same `config`.
 """
 from __future__ import annotations
 
@@ -110,21 +117,38 @@ class ClockSampler:
                 'samples': len(self.sm), 'reasons': sorted(self.reasons)}
 
 
+def reference_cpu_render():
+    """(render_fn, kind): the reference's own CPU implementation of the path - the UNMODIFIED reference model staged under
+    oracle/_ref (oracle/build_ref.py; kind 'reference') when present, else the oracle port (kind 'port')."""
+    from oracle import build_ref
+    from oracle import vipnerf_oracle as O
+    sd = O.synth_state_dict(0)
+    if build_ref.ref_available():
+        cfg = model_configs('bf16')
+        cfg['model']['name'] = 'VipNeRF01'
+        del cfg['model']['precision']
+        model = build_ref.load_ref_get_model()(cfg, None)
+        model.load_state_dict(sd)
+        model.eval()
+        return (lambda b: model(dict(b))), 'reference'
+    return (lambda b: O.render(sd, b, ndc=True)), 'port'
+
+
 def cpu_oracle_rate(n_rays, reps, threads):
-    """rays/s of the CPU oracle (port of the reference's PyTorch path) on `n_rays` rays of the workload."""
+    """(rays/s, kind) of the reference's CPU path on `n_rays` rays of the workload."""
     import torch
     from oracle import vipnerf_oracle as O
     torch.set_num_threads(threads)
-    sd = O.synth_state_dict(0)
+    render, kind = reference_cpu_render()
     batch = O.make_rays('fern', n_rays, seed=2)
     best = float('inf')
     with torch.no_grad():
-        O.render(sd, O.make_rays('fern', min(256, n_rays), seed=2), ndc=True)   # warm-up
+        render(O.make_rays('fern', min(256, n_rays), seed=2))   # warm-up
         for _ in range(reps):
             t0 = time.perf_counter()
-            O.render(sd, batch, ndc=True)
+            render(batch)
             best = min(best, time.perf_counter() - t0)
-    return n_rays / best
+    return n_rays / best, kind
 
 
 def bench_config(rays_per_step):
@@ -190,27 +214,10 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     import torch
-    from oracle import build_ref
     from oracle import vipnerf_oracle as O
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
-    sd = O.synth_state_dict(0)
-    if build_ref.ref_available():
-        kind = 'reference'
-        cfg = model_configs('bf16')
-        cfg['model']['name'] = 'VipNeRF01'
-        del cfg['model']['precision']
-        model = build_ref.load_ref_get_model()(cfg, None)
-        model.load_state_dict(sd)
-        model.eval()
-
-        def render(b):
-            return model(dict(b))
-    else:
-        kind = 'port'
-
-        def render(b):
-            return O.render(sd, b, ndc=True)
+    render, kind = reference_cpu_render()
     with torch.no_grad():
         probe = O.make_rays('fern', 256, seed=2)
         render(probe)
@@ -243,9 +250,10 @@ def run_reference(args, rank, world):
 
 def run_frame(args, rank, world, local_rank):
     """--workload frame: BASELINE config 5 - the LLFF 504x378 full-frame render (190,512 rays per step) STRONGLY
-    scaled over the ranks: every rank generates its pixel range on the device (vipnerf_generate_rays), renders it
-    with the fused kernel, ONE NCCL gather brings the per-ray maps to rank 0, which post-processes on the device and
-    copies the finished frame (uint8 image + depth maps) to the host.  All of that is inside the timed region; the
+    scaled over the ranks: every rank generates its pixel range on the device (vipnerf_generate_rays) and renders it
+    with the fused kernel, whose ray warps store the per-ray maps straight into rank 0's arrays (sharding.PeerGather;
+    fallback: one grouped NCCL send/receive); rank 0 post-processes on the device and copies the finished frame (uint8
+    image + depth maps) to the host.  All of that is inside the timed region; the
     only per-step host input is the camera pose.  Prints one JSON line (informational: the default workload is the
     4096-ray batch BASELINE.json quotes the metric on)."""
     import numpy
@@ -288,11 +296,15 @@ def run_frame(args, rank, world, local_rank):
         except Exception as e:   # noqa: BLE001
             gather_mode = f'NCCL grouped send/recv into preallocated arrays ({type(e).__name__}: {str(e)[:80]})'
 
+    # the cameras of the trajectory (4x4 pose algebra + a 3x3 inverse on the host, DataPreprocessorFused.camera) are
+    # prepared once, like the reference's tester prepares its pose list before the render loop (Tester01.py:203-211)
+    cameras = [dp.camera(pose, preprocess_pose=False) for pose in poses]
+
     def step(i, shard=True):
         if not shard:     # the whole frame on this rank alone (the sharded == unsharded check)
-            out = model(dp.create_test_data(poses[i % len(poses)], preprocess_pose=False))
+            out = model(dp.generate(cameras[i % len(cameras)]))
             return dp.postprocess({k: out[k] for k in keys}, '_fine')
-        batch = dp.create_test_data(poses[i % len(poses)], preprocess_pose=False, first_pixel=lo, n_rays=hi - lo)
+        batch = dp.generate(cameras[i % len(cameras)], lo, hi - lo)
         if peer is not None:
             pg = peer[i & 1]
             model(batch, out=pg.local_outputs())
@@ -692,7 +704,7 @@ def run_batch(args, rank, world, local_rank):
     # its finished maps straight into rank 0's arrays over NVLink (sharding.PeerGather, torch symmetric memory) and one
     # device-side barrier per step publishes them; two buffer sets alternate so that one barrier per step suffices.
     # Fallback (no symmetric memory): one grouped NCCL send/receive into preallocated arrays (sharding.gather_outputs).
-    peer, gather_mode, graphed = None, None, None
+    peer, gather_mode, graphed = None, 'none (1 GPU)', None
     inputs = hostio.FlatBuffers({k: tuple(v.shape) for k, v in host_batch.items()}, device)
     for k, v in host_batch.items():
         inputs.host[k].copy_(v)
@@ -888,9 +900,10 @@ def run_batch(args, rank, world, local_rank):
         if not args.no_cpu_baseline and world == 1:
             threads = os.cpu_count() or 1
             n_cpu = 1024
-            rate = cpu_oracle_rate(n_cpu, 3, threads)
-            line['cpu_baseline'] = {'value': rate, 'unit': 'rays/s', 'cores': threads, 'kind': 'port',
-                                    'sample': f'{n_cpu} rays of the same workload, best of 3, fp32 torch CPU oracle'}
+            rate, kind = cpu_oracle_rate(n_cpu, 3, threads)
+            line['cpu_baseline'] = {'value': rate, 'unit': 'rays/s', 'cores': threads, 'kind': kind,
+                                    'sample': f'{n_cpu} rays of the same workload, best of 3, fp32 torch CPU, '
+                                              + ('unmodified reference VipNeRF01 (oracle/_ref)' if kind == 'reference' else 'oracle port')}
         else:
             line['cpu_baseline'] = None
         print(json.dumps(line), flush=True)
