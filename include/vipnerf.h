@@ -199,6 +199,24 @@ int vipnerf_postprocess_frame(int64_t n_rays, int32_t n_sec_views, const float* 
                               int32_t n_depth_maps, const float* const* depth_in, float* const* depth_out,
                               const float* visibility2, float* visibility2_out, void* stream);
 
+/* --- training batches from the per-pixel caches (the caller side of the training step) --------------------------
+ * Replaces the data assembly of DataPreprocessor.load_cached_next_batch (src/data_preprocessors/DataPreprocessor01.py
+ * :498-530 = load_nerf_cached_batch :571-615, load_sparse_depth_cached_batch :635-683, load_visibility_prior_cached_batch
+ * :699-724): ~40 boolean-mask gathers `out = -1; out[mask] = table[indices[mask]]`, each a device sync + several
+ * launches in the reference, as ONE launch.  Row r of every output column takes table[indices[r]] when the row's class
+ * (1 = indices_mask_nerf ray, 2 = indices_mask_sparse_depth ray) is in the column's `row_classes` bit set (bit 0 = class
+ * 1, bit 1 = class 2), else the reference's fill value -1.  Tables and outputs are 4-byte elements, row-major. */
+typedef struct vipnerf_gather_column {
+  const void* table;    /* [N, width] fp32 or int32 per-pixel cache                          */
+  void* out;            /* [R, width]                                                        */
+  int32_t width;        /* elements per row (1, 3, V ...)                                    */
+  int32_t row_classes;  /* bit 0: class-1 rows gather, bit 1: class-2 rows gather            */
+  int32_t fill_is_int;  /* -1 is written as int32 (pixel_id) instead of fp32                 */
+  int32_t reserved;
+} vipnerf_gather_column;
+int vipnerf_gather_train_batch(const int64_t* indices, const uint8_t* row_class, int64_t n_rows,
+                               const vipnerf_gather_column* columns_host, int32_t n_columns, void* stream);
+
 /* --- the visibility prior generator -----------------------------------------------
  * Replaces VisibilityWeightsComputer.compute_weights
  * (src/prior_generators/visibility/VisibilityMask02_NeRF_LLFF.py:27-35 = create_psv :41-47,

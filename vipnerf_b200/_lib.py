@@ -58,6 +58,11 @@ class LossSpec(Structure):   # vipnerf_loss_spec
                 ('w_visibility', c_float), ('w_prior', c_float), ('w_sparse_depth', c_float)]
 
 
+class GatherColumn(Structure):   # vipnerf_gather_column
+    _fields_ = [('table', c_void_p), ('out', c_void_p), ('width', c_int32), ('row_classes', c_int32),
+                ('fill_is_int', c_int32), ('reserved', c_int32)]
+
+
 RAY_BUFFER_FIELDS = RAY_FIELDS[:10]
 
 
@@ -81,6 +86,7 @@ EXPORTS = {
     'vipnerf_composite': (c_int, [POINTER(Cfg), POINTER(Rays), c_int64, c_int32, c_void_p, c_void_p, c_void_p,
                                   c_void_p, POINTER(PassOut), c_void_p, c_void_p]),
     'vipnerf_generate_rays': (c_int, [POINTER(Camera), c_int64, c_int64, POINTER(RayBuffers), c_void_p]),
+    'vipnerf_gather_train_batch': (c_int, [c_void_p, c_void_p, c_int64, POINTER(GatherColumn), c_int32, c_void_p]),
     'vipnerf_postprocess_frame': (c_int, [c_int64, c_int32, c_void_p, c_void_p, c_int32, POINTER(c_void_p),
                                           POINTER(c_void_p), c_void_p, c_void_p, c_void_p]),
     'vipnerf_visibility_prior': (c_int, [c_int32, c_int32, c_void_p, c_void_p, POINTER(c_double), POINTER(c_double),

@@ -289,6 +289,22 @@ int vipnerf_generate_rays(const vipnerf_camera* camera, int64_t first_pixel, int
   return VIPNERF_OK;
 }
 
+int vipnerf_gather_train_batch(const int64_t* indices, const uint8_t* row_class, int64_t n_rows,
+                               const vipnerf_gather_column* columns_host, int32_t n_columns, void* stream) {
+  if (n_rows < 0 || n_columns < 0 || n_columns > kMaxGatherColumns)
+    return fail(VIPNERF_EINVAL, "n_rows=%lld n_columns=%d (at most %d columns)", (long long)n_rows, n_columns, kMaxGatherColumns);
+  if (n_rows == 0 || n_columns == 0) return VIPNERF_OK;
+  if (!indices || !row_class || !columns_host) return fail(VIPNERF_EINVAL, "indices / row_class / columns is NULL");
+  for (int i = 0; i < n_columns; ++i) {
+    const vipnerf_gather_column& c = columns_host[i];
+    if (!c.table || !c.out || c.width < 1 || c.width > 64)
+      return fail(VIPNERF_EINVAL, "column %d: table / out is NULL or width %d outside [1,64]", i, c.width);
+  }
+  const cudaError_t e = launch_gather_train_batch(indices, row_class, n_rows, columns_host, n_columns, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return fail_cuda(e, "gather_train_batch");
+  return VIPNERF_OK;
+}
+
 int vipnerf_postprocess_frame(int64_t n_rays, int32_t n_sec_views, const float* rgb, uint8_t* image_u8,
                               int32_t n_depth_maps, const float* const* depth_in, float* const* depth_out,
                               const float* visibility2, float* visibility2_out, void* stream) {

@@ -97,7 +97,41 @@ __global__ void k_postprocess_frame(int64_t n_rays, int V, const float* __restri
   }
 }
 
+// One thread per batch row: every column of the row is a gather from its per-pixel table or the fill value -1
+// (DataPreprocessor01.py:571-724).  HBM-bound and tiny (about 150 bytes per ray); what it buys is one launch instead of
+// ~40 masked gathers with a device synchronisation each.
+struct GatherColumns {
+  vipnerf_gather_column c[kMaxGatherColumns];
+  int n;
+};
+__global__ void k_gather_train_batch(const int64_t* __restrict__ indices, const uint8_t* __restrict__ row_class,
+                                     int64_t n_rows, GatherColumns cols) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rows) return;
+  const int64_t idx = indices[r];
+  const int cls = row_class[r];
+  for (int i = 0; i < cols.n; ++i) {
+    const vipnerf_gather_column& c = cols.c[i];
+    const bool take = ((cls == 1) && (c.row_classes & 1)) || ((cls == 2) && (c.row_classes & 2));
+    const uint32_t* tab = static_cast<const uint32_t*>(c.table) + idx * c.width;
+    uint32_t* out = static_cast<uint32_t*>(c.out) + r * c.width;
+    const uint32_t fill = c.fill_is_int ? 0xFFFFFFFFu : __float_as_uint(-1.f);
+    for (int k = 0; k < c.width; ++k) out[k] = take ? tab[k] : fill;
+  }
+}
+
 }  // namespace
+
+cudaError_t launch_gather_train_batch(const int64_t* indices, const uint8_t* row_class, int64_t n_rows,
+                                      const vipnerf_gather_column* columns, int n_columns, cudaStream_t s) {
+  if (n_rows <= 0 || n_columns <= 0) return cudaSuccess;
+  GatherColumns cols{};
+  cols.n = n_columns;
+  for (int i = 0; i < n_columns; ++i) cols.c[i] = columns[i];
+  const int threads = 128;
+  k_gather_train_batch<<<(unsigned)((n_rows + threads - 1) / threads), threads, 0, s>>>(indices, row_class, n_rows, cols);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_generate_rays(const vipnerf_camera& camera, int64_t first_pixel, int64_t n_rays,
                                  const vipnerf_ray_buffers& out, cudaStream_t s) {

@@ -90,6 +90,10 @@ struct LossGrad {
 cudaError_t launch_composite_bwd(const RayPtrs& rp, const RenderFlags& fl, int64_t n_rays, int S, const float* z,
                                  const float* sigma, const float* rgb, const float* vis, const float* vis2,
                                  const PassGradPtrs& g, const LossGrad& lg, float* dsig, float* dlogit, cudaStream_t s);
+// frame_kernels.cu : training batches from the per-pixel caches (vipnerf_gather_train_batch)
+constexpr int kMaxGatherColumns = 24;
+cudaError_t launch_gather_train_batch(const int64_t* indices, const uint8_t* row_class, int64_t n_rows,
+                                      const vipnerf_gather_column* columns, int n_columns, cudaStream_t s);
 // Loss values of one training batch from the forward outputs: losses_dev[0..4] = MSE, Visibility, VisibilityPrior,
 // SparseDepth, TotalLoss (weighted); [5], [6] = the mask counts the means divide by.  `partial`: 8 floats per 4 rays.
 struct LossFwdArgs {
