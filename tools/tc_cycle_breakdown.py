@@ -43,7 +43,7 @@ for slot in range(2):
     q = b[slot * 16: slot * 16 + 8]
     if q[6] == 0:
         continue
-    print(f'slot {slot}: tiles {q[6]}, total {q[7]} cycles = {q[7] / q[6]:.0f} / tile (MMA-only time per tile: 18432)')
+    print(f'slot {slot}: tiles {q[6]}, total {q[7]} cycles = {q[7] / q[6]:.0f} / tile (tensor time per tile: 17152 cycles = 60 chunks x 256 + 6 bias chunks x 128 + 8 M9 chunks x 128)')
     for n, v in zip(names[:6], q[:6]):
         print(f'   {n:20s} {v:10d}  {100 * v / q[7]:5.1f}%   {v / q[6]:9.0f} / tile')
 m = b[32:36]
