@@ -301,7 +301,7 @@ int vipnerf_composite_backward(const vipnerf_cfg* cfg, const vipnerf_rays* rays,
  * dw[m * ld_dw + n] = sum_p dy[p * ld_dy + m] * x[p * ld_x + n] for n < n_valid (what autograd computes for
  * nn.Linear.weight: grad_output^T @ input), db[m] = sum_p dy[p * ld_dy + m] (NULL = skip).
  * m in {128, 256}; n in {32, 64, 128, 256}.  mode 0 = fp32 CUDA-core kernel (k_gemm_tn; what vipnerf_train_backward
- * uses by default), mode 1 = tcgen05 kind::tf32 kernel (k_gemm_tn_tf32; n must be 256; operands rounded to tf32 by the
+ * uses by default), mode 1 = tcgen05 kind::tf32 kernel (k_gemm_tn_tf32; n in {32, 64, 256}; operands rounded to tf32 by the
  * TMA copy; what VIPNERF_FLAG_TRAIN_TF32 selects).  workspace: vipnerf_param_gradient_gemm_workspace_bytes() bytes, 256-byte aligned. */
 size_t vipnerf_param_gradient_gemm_workspace_bytes(void);
 int vipnerf_param_gradient_gemm(const float* dy, int32_t ld_dy, int32_t m, const float* x, int32_t ld_x, int32_t n,

@@ -36,6 +36,14 @@ def test_graphed_render_equals_plugin_call(built_library):
             for k in KEYS:
                 assert torch.equal(got[k], ref[k].cpu()), k
     assert g.h2d_bytes >= sum(v.numel() * 4 for v in a.values()) and g.d2h_bytes >= 777 * (3 + 1 + 1 + 1 + 192) * 4
+    # a weight update after the capture: the graph must not replay the stale packed weights
+    with torch.no_grad():
+        model.fine_model.pts_linears[3].weight.mul_(1.05)
+        got = g(b)
+        g.synchronize()
+        ref = model({k: v.cuda() for k, v in b.items()})
+        for k in KEYS:
+            assert torch.equal(got[k], ref[k].cpu()), k
 
 
 def test_out_tensors_are_written_in_place(built_library):

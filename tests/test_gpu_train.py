@@ -153,13 +153,12 @@ def _compare_full_grads(model, ref_grads, max_tol=GRAD_MAX_TOL, norm_tol=5 * GRA
 @pytest.mark.parametrize('mode', [0, 1])
 @pytest.mark.parametrize('P,M,N', [(4096, 256, 256), (10007, 128, 256), (96, 256, 256), (777, 256, 64), (5000, 128, 32)])
 def test_param_gradient_gemm(P, M, N, mode, built_library):
-    """dW = dY^T X and db = column sums, fp32 CUDA-core kernel (mode 0) and tcgen05 tf32 kernel (mode 1, N = 256),
+    """dW = dY^T X and db = column sums, fp32 CUDA-core kernel (mode 0) and tcgen05 tf32 kernel (mode 1, N in {32, 64, 256}),
     against an fp64 product; ragged row counts exercise the zero-filled tails of both kernels."""
     from vipnerf_b200 import training
-    if mode == 1 and N != 256:
-        with pytest.raises(NotImplementedError):
-            training.param_gradient_gemm(torch.zeros(P, M, device='cuda'), torch.zeros(P, N, device='cuda'), mode=1)
-        return
+    if mode == 1:
+        with pytest.raises(NotImplementedError):     # the tensor kernel is built for N in {32, 64, 256}
+            training.param_gradient_gemm(torch.zeros(P, M, device='cuda'), torch.zeros(P, 128, device='cuda'), mode=1)
     g = torch.Generator().manual_seed(P + M + N)
     dy = (torch.randn(P, M, generator=g) * torch.rand(P, 1, generator=g)).cuda()
     x = torch.relu(torch.randn(P, N, generator=g)).cuda()
@@ -168,9 +167,10 @@ def test_param_gradient_gemm(P, M, N, mode, built_library):
     err = ((dw.double() - ref).abs().max() / ref.abs().max()).item()
     assert err <= (1e-3 if mode == 1 else 2e-6), err          # tf32: 2^-11 per operand; fp32: summation order
     ref_b = dy.double().sum(0)
-    assert ((db.double() - ref_b).abs().max() / ref_b.abs().max()).item() <= 2e-6
-    again, _ = training.param_gradient_gemm(dy, x, mode=mode)
-    assert torch.equal(dw, again)                             # fixed-order split reduction
+    # mode 1: the column sums ride along in the tensor kernel, on the tf32-rounded boxes the TMA engine delivered
+    assert ((db.double() - ref_b).abs().max() / ref_b.abs().max()).item() <= (1e-3 if mode == 1 else 2e-6)
+    again, db_again = training.param_gradient_gemm(dy, x, mode=mode)
+    assert torch.equal(dw, again) and torch.equal(db, db_again)   # fixed-order split reduction
 
 
 @pytest.mark.parametrize('scene,n_rays,n_sec,train_precision', [

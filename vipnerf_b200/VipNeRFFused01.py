@@ -118,6 +118,13 @@ class VipNeRFFused(torch.nn.Module):
         with self._pack_cache.lock:
             self._pack_cache.entries.clear()
 
+    def weights_version(self) -> tuple:
+        """(storage address, in-place version) of every parameter tensor: changes whenever an optimizer step,
+        load_state_dict or .to() touches a weight.  hostio.GraphedRender re-captures its CUDA graph when it changes (the
+        packed weight images a captured launch points to belong to one version)."""
+        models = [self.coarse_model] + ([self.fine_model] if self.fine_mlp_needed else [])
+        return tuple((t.data_ptr(), t._version) for m in models for t in m.named_tensors().values())
+
     def _packed_weights(self, which: str, precision: str, device) -> torch.Tensor:
         mlp = self.coarse_model if which == 'coarse' else self.fine_model
         tensors = mlp.named_tensors()

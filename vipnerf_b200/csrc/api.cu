@@ -671,21 +671,24 @@ int vipnerf_train_backward_fused(const vipnerf_cfg* cfg, const vipnerf_rays* ray
     // 3. parameter gradients: dW = dY^T X over all points, db = column sums of dY
     const size_t PL = (size_t)P * 256;
     const bool tf32 = (cfg->flags & VIPNERF_FLAG_TRAIN_TF32) != 0;
-    // one 256-wide product: fp32 CUDA cores, or the tensor cores (+ a column-sum pass for the bias gradient)
+    // one 256-wide product: fp32 CUDA cores, or the tensor cores (the bias gradient = column sums of dY rides along in both)
     auto wide_gemm = [&](const float* dy, int M, const float* x, float* dw, int ldc, float* db) -> cudaError_t {
       if (!tf32) return launch_gemm_tn(dy, M, M, x, 256, 256, P, dw, ldc, 256, db, partial, s);
-      cudaError_t r = launch_gemm_tn_tc(dy, M, M, x, 256, P, dw, ldc, 256, partial, s);
-      if (r == cudaSuccess && db != nullptr) r = launch_colsum(dy, M, M, P, db, partial + gemm_partial_floats(), s);
-      return r;
+      return launch_gemm_tn_tc(dy, M, M, x, 256, 256, P, dw, ldc, 256, partial, s, db, partial + gemm_partial_floats());
     };
     for (int l = 0; l < 8 && e == cudaSuccess; ++l) {
       const float* dy = dpre + l * PL;
       float* dw = pg[2 * l];
       float* db = pg[2 * l + 1];
+      // the 64 encoding columns (+ the layer's bias gradient): a narrow product - tensor cores with N = 64 in tf32 mode
+      auto enc_gemm = [&](int ldc) -> cudaError_t {
+        if (!tf32) return launch_gemm_tn(dy, 256, 256, enc, 64, 64, P, dw, ldc, kEncPts, db, partial, s);
+        return launch_gemm_tn_tc(dy, 256, 256, enc, 64, 64, P, dw, ldc, kEncPts, partial, s, db, partial + gemm_partial_floats());
+      };
       if (l == 0) {
-        e = launch_gemm_tn(dy, 256, 256, enc, 64, 64, P, dw, kEncPts, kEncPts, db, partial, s);
+        e = enc_gemm(kEncPts);
       } else if (l == 5) {   // input = cat([encoding, h4]) (:543-544)
-        e = launch_gemm_tn(dy, 256, 256, enc, 64, 64, P, dw, kWidth + kEncPts, kEncPts, db, partial, s);
+        e = enc_gemm(kWidth + kEncPts);
         if (e == cudaSuccess)
           e = wide_gemm(dy, 256, h + 4 * PL, dw + kEncPts, kWidth + kEncPts, nullptr);
       } else {
@@ -699,8 +702,10 @@ int vipnerf_train_backward_fused(const vipnerf_cfg* cfg, const vipnerf_rays* ray
     // views_linears.0: feature columns over points, direction columns and bias over (point, view) rows
     if ((e = wide_gemm(dacc9, 128, feat, pg[16], kWidth + kEncView, nullptr)) != cudaSuccess)
       return fail_cuda(e, "gemm_tn (views_linears feature columns)");
-    if ((e = launch_gemm_tn(dhv, 128, 128, pev, 32, 32, P * nv, pg[16] + kWidth, kWidth + kEncView, kEncView, pg[17], partial, s)) != cudaSuccess)
-      return fail_cuda(e, "gemm_tn (views_linears direction columns)");
+    e = tf32 ? launch_gemm_tn_tc(dhv, 128, 128, pev, 32, 32, P * nv, pg[16] + kWidth, kWidth + kEncView, kEncView, partial, s, pg[17],
+                                 partial + gemm_partial_floats())
+             : launch_gemm_tn(dhv, 128, 128, pev, 32, 32, P * nv, pg[16] + kWidth, kWidth + kEncView, kEncView, pg[17], partial, s);
+    if (e != cudaSuccess) return fail_cuda(e, "gemm_tn (views_linears direction columns)");
     // views_output_linear [4][128] and pts_output_linear [1][256]
     if ((e = launch_small_tn(dlogit, 4, hv, 128, P * nv, pg[22], pg[23], partial, s)) != cudaSuccess)
       return fail_cuda(e, "small_tn (views_output_linear)");
@@ -746,10 +751,8 @@ int vipnerf_param_gradient_gemm(const float* dy, int32_t ld_dy, int32_t m, const
   cudaError_t e;
   if (mode != 0 && mode != 1) return fail(VIPNERF_EINVAL, "mode=%d", mode);
   if (mode == 1) {
-    if (n != 256) return fail(VIPNERF_EUNSUPPORTED, "the tensor-core product is built for n = 256 (got %d)", n);
-    e = launch_gemm_tn_tc(dy, ld_dy, m, x, ld_x, n_rows, dw, ld_dw, n_valid, partial, s);
-    if (e == cudaSuccess && db != nullptr)
-      e = launch_colsum(dy, ld_dy, m, n_rows, db, partial + gemm_partial_floats(), s);
+    if (n != 256 && n != 64 && n != 32) return fail(VIPNERF_EUNSUPPORTED, "the tensor-core product is built for n in {32, 64, 256} (got %d)", n);
+    e = launch_gemm_tn_tc(dy, ld_dy, m, x, ld_x, n, n_rows, dw, ld_dw, n_valid, partial, s, db, partial + gemm_partial_floats());
   } else {
     e = launch_gemm_tn(dy, ld_dy, m, x, ld_x, n, n_rows, dw, ld_dw, n_valid, db, partial, s);
   }

@@ -61,6 +61,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {   // 
     }
   }
 }
+__device__ __forceinline__ void mbar_arrive_cta(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
@@ -110,8 +113,10 @@ constexpr uint32_t instr_desc_tf32_mn(uint32_t n, uint32_t m) {
 struct GemmTcParams {
   CUtensorMap map_a, map_b;
   int M;                    // 128 or 256
+  int N;                    // 32, 64 or 256 (columns of B)
   int64_t n_rows, rows_per_split;
-  float* partial;           // [gridDim.x][M][256]
+  float* partial;           // [gridDim.x][M][N]
+  float* colsum_partial;    // [gridDim.x][M] column sums of A over the CTA's point range (bias gradient), or null
 };
 
 __global__ void __launch_bounds__(kTcThreads, 1) k_gemm_tn_tf32(const __grid_constant__ GemmTcParams p) {
@@ -119,7 +124,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_gemm_tn_tf32(const __grid_con
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int halves = p.M / 128;
   const int a_boxes = p.M / 32;
-  const uint32_t stage_bytes = (uint32_t)(a_boxes + 8) * kBoxBytes;
+  const int b_boxes = p.N / 32;
+  const uint32_t stage_bytes = (uint32_t)(a_boxes + b_boxes) * kBoxBytes;
   uint8_t* tail = smem + kTcStages * stage_bytes;
   uint32_t* tmem_ptr_slot = reinterpret_cast<uint32_t*>(tail + 8 * (2 * kTcStages + 1));
   const uint32_t bar0 = smem_u32(tail);
@@ -133,7 +139,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_gemm_tn_tf32(const __grid_con
 
   if (threadIdx.x == 0) {
     if ((smem_u32(smem) & 1023u) != 0) { printf("vipnerf gemm_tc: shared memory base not 1 KiB aligned\n"); __trap(); }
-    for (int s = 0; s < kTcStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    // a stage is free when its MMAs have retired (one tcgen05.commit arrival) and, with column sums, when the four
+    // epilogue warps have read its A boxes (one arrival each)
+    for (int s = 0; s < kTcStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), p.colsum_partial ? 5 : 1); }
     mbar_init(done_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -155,12 +163,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_gemm_tn_tf32(const __grid_con
         const uint32_t dst = smem_u32(smem) + (uint32_t)st * stage_bytes;
         const int row = (int)(r_begin + (int64_t)s * kTcRows);   // rows past the end of the arrays are zero-filled by the TMA
         for (int j = 0; j < a_boxes; ++j) tma_load_2d(dst + j * kBoxBytes, &p.map_a, j * 32, row, full_bar(st));
-        for (int j = 0; j < 8; ++j) tma_load_2d(dst + (a_boxes + j) * kBoxBytes, &p.map_b, j * 32, row, full_bar(st));
+        for (int j = 0; j < b_boxes; ++j) tma_load_2d(dst + (a_boxes + j) * kBoxBytes, &p.map_b, j * 32, row, full_bar(st));
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = instr_desc_tf32_mn(256, 128);
+      const uint32_t idesc = instr_desc_tf32_mn((uint32_t)p.N, 128);
       for (int s = 0; s < n_steps; ++s) {
         const int st = s % kTcStages;
         mbar_wait(full_bar(st), (s / kTcStages) & 1);
@@ -181,15 +189,41 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_gemm_tn_tf32(const __grid_con
     }
   } else {
     // epilogue warps: warp w may touch TMEM lanes [32 * (w % 4), +32)
-    float* out = p.partial + (size_t)blockIdx.x * p.M * 256;
+    float* out = p.partial + (size_t)blockIdx.x * p.M * p.N;
     const int quarter = warp & 3;
+    if (p.colsum_partial != nullptr) {
+      // While the main loop runs these 128 threads are idle: they add up the columns of the A boxes of every stage
+      // straight from shared memory (db = sum_p dY[p][m], the bias gradient) - the separate column-sum pass over the
+      // same array (k_colsum, 1 KiB per point and layer from HBM once more) is gone.  Thread t owns columns t and
+      // t + 128; box layout = SWIZZLE_128B_ATOM_32B: point k at k * 128 B, 32-byte chunk (c / 8) ^ (k % 4).
+      const int t = (warp - 2) * 32 + lane;
+      float acc0 = 0.f, acc1 = 0.f;
+      for (int s = 0; s < n_steps; ++s) {
+        const int st = s % kTcStages;
+        mbar_wait(full_bar(st), (s / kTcStages) & 1);
+        const uint8_t* a0 = smem + (size_t)st * stage_bytes;
+        for (int h = 0; h < halves; ++h) {
+          const int m = t + h * 128, c = m & 31;
+          const uint8_t* box = a0 + (size_t)(m >> 5) * kBoxBytes + (c & 7) * 4;
+          float a = 0.f;
+#pragma unroll
+          for (int k = 0; k < kTcRows; ++k)
+            a += *reinterpret_cast<const float*>(box + k * 128 + ((((c >> 3) ^ (k & 3))) << 5));
+          if (h == 0) acc0 += a; else acc1 += a;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cta(empty_bar(st));
+      }
+      p.colsum_partial[(size_t)blockIdx.x * p.M + t] = acc0;
+      if (halves == 2) p.colsum_partial[(size_t)blockIdx.x * p.M + t + 128] = acc1;
+    }
     if (n_steps > 0) {
       mbar_wait(done_bar, 0);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     }
     for (int h = 0; h < halves; ++h) {
       const int m = h * 128 + quarter * 32 + lane;
-      for (int c = 0; c < 8; ++c) {
+      for (int c = 0; c < b_boxes; ++c) {
         uint32_t v[32];
         if (n_steps > 0) {
           tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + h * 256 + c * 32, v);
@@ -198,7 +232,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_gemm_tn_tf32(const __grid_con
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = 0u;
         }
-        float4* dst = reinterpret_cast<float4*>(out + (size_t)m * 256 + c * 32);
+        float4* dst = reinterpret_cast<float4*>(out + (size_t)m * p.N + c * 32);
 #pragma unroll
         for (int i = 0; i < 8; ++i)
           dst[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
@@ -505,9 +539,10 @@ cudaError_t launch_linear_tc(const LinearTcArgs& a, cudaStream_t s) {
 
 size_t gemm_tn_tc_partial_floats(int sms) { return (size_t)sms * 256 * 256; }
 
-cudaError_t launch_gemm_tn_tc(const float* A, int lda, int M, const float* B, int ldb, int64_t n_rows, float* dst,
-                              int ldc, int n_valid, float* partial, cudaStream_t s) {
-  if ((M != 128 && M != 256) || n_rows < 1) return cudaErrorInvalidValue;
+cudaError_t launch_gemm_tn_tc(const float* A, int lda, int M, const float* B, int ldb, int N, int64_t n_rows, float* dst,
+                              int ldc, int n_valid, float* partial, cudaStream_t s, float* bias_dst,
+                              float* colsum_scratch) {
+  if ((M != 128 && M != 256) || (N != 32 && N != 64 && N != 256) || n_rows < 1) return cudaErrorInvalidValue;
   if ((reinterpret_cast<uintptr_t>(A) & 15u) || (reinterpret_cast<uintptr_t>(B) & 15u) || (lda & 3) || (ldb & 3))
     return cudaErrorInvalidValue;
   int dev = 0, sms = 0;
@@ -524,13 +559,17 @@ cudaError_t launch_gemm_tn_tc(const float* A, int lda, int M, const float* B, in
 
   GemmTcParams p{};
   if ((e = encode_rows_map(&p.map_a, A, lda, M, n_rows)) != cudaSuccess) return e;
-  if ((e = encode_rows_map(&p.map_b, B, ldb, 256, n_rows)) != cudaSuccess) return e;
-  p.M = M; p.n_rows = n_rows; p.rows_per_split = rows_per_split; p.partial = partial;
-  const size_t smem = (size_t)kTcStages * (M / 32 + 8) * kBoxBytes + 128;
+  if ((e = encode_rows_map(&p.map_b, B, ldb, N, n_rows)) != cudaSuccess) return e;
+  p.M = M; p.N = N; p.n_rows = n_rows; p.rows_per_split = rows_per_split; p.partial = partial;
+  p.colsum_partial = (bias_dst != nullptr) ? colsum_scratch : nullptr;
+  if (bias_dst != nullptr && colsum_scratch == nullptr) return cudaErrorInvalidValue;
+  const size_t smem = (size_t)kTcStages * (M / 32 + N / 32) * kBoxBytes + 128;
   if ((e = cudaFuncSetAttribute(k_gemm_tn_tf32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
   k_gemm_tn_tf32<<<(unsigned)n_split, kTcThreads, smem, s>>>(p);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
-  return launch_reduce_partials(partial, (int)n_split, M, 256, dst, ldc, n_valid, s);
+  if ((e = launch_reduce_partials(partial, (int)n_split, M, N, dst, ldc, n_valid, s)) != cudaSuccess) return e;
+  if (bias_dst != nullptr) return launch_reduce_partials(colsum_scratch, (int)n_split, M, 1, bias_dst, 1, 1, s);
+  return cudaSuccess;
 }
 
 }  // namespace vipnerf

@@ -111,12 +111,15 @@ cudaError_t launch_gemm_tn(const float* A, int lda, int M, const float* B, int l
 cudaError_t launch_reduce_partials(const float* partial, int n_split, int M, int N, float* dst, int ldc, int n_valid,
                                    cudaStream_t s);
 cudaError_t launch_colsum(const float* A, int lda, int M, int64_t n_rows, float* dst, float* partial, cudaStream_t s);
-// gemm_tc.cu : the same product on the tensor cores (tcgen05 kind::tf32 reading the fp32 arrays through TMA), N = 256,
-// M in {128, 256}; no bias output (launch_colsum).  `partial`: gemm_tn_tc_partial_floats(#SMs) floats.
+// gemm_tc.cu : the same product on the tensor cores (tcgen05 kind::tf32 reading the fp32 arrays through TMA),
+// N in {32, 64, 256}, M in {128, 256}.  `partial`: gemm_tn_tc_partial_floats(#SMs) floats.
 constexpr int kGemmTcMaxSplits = 160;   // point ranges (one CTA each) the scratch of the tensor-core product is sized for
 size_t gemm_tn_tc_partial_floats(int sms);
-cudaError_t launch_gemm_tn_tc(const float* A, int lda, int M, const float* B, int ldb, int64_t n_rows, float* dst,
-                              int ldc, int n_valid, float* partial, cudaStream_t s);
+// bias_dst (optional): column sums of A (db), accumulated by the kernel's epilogue warps from the A boxes in shared
+// memory while the main loop runs; colsum_scratch: kGemmTcMaxSplits * M floats.
+cudaError_t launch_gemm_tn_tc(const float* A, int lda, int M, const float* B, int ldb, int N, int64_t n_rows, float* dst,
+                              int ldc, int n_valid, float* partial, cudaStream_t s, float* bias_dst = nullptr,
+                              float* colsum_scratch = nullptr);
 // train_kernels.cu : the non-product pieces of the tensor-core training path (encodings, heads forward / backward)
 cudaError_t launch_encode_points(const RayPtrs& rp, const RenderFlags& fl, int64_t n_rays, int S, const float* z,
                                  float* enc, float* pev, cudaStream_t s);

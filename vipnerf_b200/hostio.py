@@ -86,6 +86,13 @@ class GraphedRender:
         self.download = download
         self.load(rays)
         self.stream = torch.cuda.Stream(device)
+        self.h2d_bytes, self.d2h_bytes = self.inputs.nbytes, self.outputs.nbytes if download else 0
+        self._capture()
+
+    def _capture(self) -> None:
+        """(Re-)captures the graph for the model's CURRENT weights: a captured launch points at the packed weight images
+        of one weights_version(); they are kept alive here for as long as the graph may replay them."""
+        device = self.device
         self.graph = torch.cuda.CUDAGraph()
         with torch.no_grad(), torch.cuda.device(device):
             self.stream.wait_stream(torch.cuda.current_stream(device))
@@ -95,7 +102,10 @@ class GraphedRender:
             torch.cuda.synchronize(device)
             with torch.cuda.graph(self.graph, stream=self.stream):
                 self._step()
-        self.h2d_bytes, self.d2h_bytes = self.inputs.nbytes, self.outputs.nbytes if download else 0
+        version = getattr(self.model, 'weights_version', None)
+        self._version = version() if version is not None else None
+        cache = getattr(self.model, '_pack_cache', None)
+        self._packed_alive = [e[1] for e in cache.entries.values()] if cache is not None else []
 
     def _step(self):
         batch = dict(self.extra)
@@ -111,6 +121,8 @@ class GraphedRender:
     def __call__(self, batch: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
         if batch is not None:
             self.load(batch)
+        if self._version is not None and self.model.weights_version() != self._version:
+            self._capture()       # the weights changed (optimizer step, load_state_dict): the old launch is stale
         self.graph.replay()
         return self.outputs.host if self.download else self.outputs.dev
 
