@@ -738,7 +738,7 @@ def run_batch(args, rank, world, local_rank):
             maps = pg.finish()
             if maps is not None:       # rank 0 brings the WHOLE gathered result to the host: one copy
                 host_flat.copy_(pg.buf, non_blocking=True)
-                return {k: pg._view(host_flat, k, 0, world * R) for k in out_keys}, maps
+                return {k: pg.view(host_flat, k, 0, world * R) for k in out_keys}, maps
             return None
         out = model(batch)
         maps = sharding.gather_outputs({k: out[k] for k in out_keys}, world * R, None, 0)

@@ -124,21 +124,22 @@ class PeerGather:
         # dst's buffer as seen from this rank (on dst: the local buffer itself)
         self.dst_buf = self.buf if self.rank == dst else self.handle.get_buffer(dst, (self.total,), torch.float32)
 
-    def _view(self, base: torch.Tensor, k: str, lo: int, hi: int) -> torch.Tensor:
+    def view(self, base: torch.Tensor, k: str, lo: int, hi: int) -> torch.Tensor:
+        """Rows [lo, hi) of key k inside a flat buffer with this object's layout (the symmetric buffer, or a host copy of it)."""
         off, width, shape = self.offsets[k]
         return base[off + lo * width: off + hi * width].view((hi - lo,) + shape)
 
     def local_outputs(self) -> Dict[str, torch.Tensor]:
         """This rank's rows of every key, as tensors that alias `dst`'s arrays (peer memory for rank != dst)."""
         lo, hi = shard_range(self.n_rays, self.rank, self.world)
-        return {k: self._view(self.dst_buf, k, lo, hi) for k in self.keys}
+        return {k: self.view(self.dst_buf, k, lo, hi) for k in self.keys}
 
     def finish(self) -> Optional[Dict[str, torch.Tensor]]:
         """Stream-ordered barrier over the ranks (symmetric-memory signal pads); afterwards `dst` owns the whole result."""
         self.handle.barrier(channel=0)
         if self.rank != self.dst:
             return None
-        return {k: self._view(self.buf, k, 0, self.n_rays) for k in self.keys}
+        return {k: self.view(self.buf, k, 0, self.n_rays) for k in self.keys}
 
     def release(self) -> None:
         """Second barrier: nobody may start overwriting dst's arrays (next frame) before dst has consumed them."""
