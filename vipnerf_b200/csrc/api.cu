@@ -224,6 +224,7 @@ cudaError_t mlp_forward_tc(const RayPtrs& rp, const RenderFlags& fl, int64_t n_r
     }
     a.bias = small + kOffBias + l * 256;
     a.relu = true;
+    if (l == 7) { a.dot_vec = small + kOffWSigma; a.dot_out = sigma; }   // the density head rides along (read back by k_heads_fwd)
     if ((e = launch_linear_tc(a, s)) != cudaSuccess) return e;
   }
   LinearTcArgs f = linear_args(sv.h + 7 * PL, 256, 256, woi + kBwdOffFeature, 256, 256, P, sv.feat, 256);
@@ -231,7 +232,7 @@ cudaError_t mlp_forward_tc(const RayPtrs& rp, const RenderFlags& fl, int64_t n_r
   if ((e = launch_linear_tc(f, s)) != cudaSuccess) return e;
   LinearTcArgs v = linear_args(sv.feat, 256, 256, woi + kBwdOffViews, 256, 128, P, acc9, 128);
   if ((e = launch_linear_tc(v, s)) != cudaSuccess) return e;
-  return launch_heads_fwd(P, 1 + fl.n_sec_views, packed, sv.h + 7 * PL, acc9, sv.pev, sv.noise, sigma, rgb, vis, vis2, sv.hv, s);
+  return launch_heads_fwd(P, 1 + fl.n_sec_views, packed, nullptr, acc9, sv.pev, sv.noise, sigma, rgb, vis, vis2, sv.hv, s);
 }
 
 // backward-data chain of one sample set on the tensor cores (same outputs as launch_mlp_bwd_fp32)

@@ -309,6 +309,8 @@ struct LinearTcParams {
   int relu;
   float* out;
   int ld_out;
+  const float* dot_vec;
+  float* dot_out;
 };
 
 // K-major SWIZZLE_128B descriptor: 128-byte rows, 8-row atoms 1 KiB apart (SBO), LBO unused (1), layout type 2
@@ -323,6 +325,9 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
+// kDot: the epilogue also reduces every output row against p.dot_vec (a separate instantiation: the plain layers must not
+// pay registers or predicated loads for it)
+template <bool kDot>
 __global__ void __launch_bounds__(kTcThreads, 1) k_linear_tf32(const __grid_constant__ LinearTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -426,6 +431,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_linear_tf32(const __grid_cons
           tma_load_2d(msk_s + 4096u * (mask_n & 1), &p.map_mask, 0, row0, mfull0 + 8u * (mask_n & 1));
         }
         const float r1 = (p.rank1_row != nullptr && valid) ? p.rank1_row[pg] : 0.f;
+        float dot = 0.f;
         for (int c = 0; c < n_ch; ++c, ++mask_n) {
           uint32_t v[32];
           tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * 256 + c * 32, v);
@@ -451,6 +457,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_linear_tf32(const __grid_cons
               o.x = fmaf(r1, u.x, o.x); o.y = fmaf(r1, u.y, o.y); o.z = fmaf(r1, u.z, o.z); o.w = fmaf(r1, u.w, o.w);
             }
             if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+            if (kDot) {
+              const float4 dv = *reinterpret_cast<const float4*>(p.dot_vec + c * 32 + 4 * q);
+              dot = fmaf(o.x, dv.x, dot); dot = fmaf(o.y, dv.y, dot); dot = fmaf(o.z, dv.z, dot); dot = fmaf(o.w, dv.w, dot);
+            }
             const uint32_t sw = (uint32_t)((q ^ (lane & 7)) << 4);    // 128-byte swizzle: 16-byte chunk index ^ (row % 8)
             if (has_mask) {
               float4 m;
@@ -467,8 +477,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_linear_tf32(const __grid_cons
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
         }
+        if (kDot && valid) p.dot_out[pg] = dot;
       }
-      (void)valid;
       // this warp's TMEM reads of the accumulator are complete: hand it back to the MMA warp
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
@@ -519,6 +529,7 @@ cudaError_t launch_linear_tc(const LinearTcArgs& a, cudaStream_t s) {
   if (a.k[1] == 0) { p.map_a[1] = p.map_a[0]; p.map_b[1] = p.map_b[0]; }
   p.N = a.N; p.n_rows = a.n_rows; p.bias = a.bias; p.rank1_row = a.rank1_row; p.rank1_col = a.rank1_col;
   p.mask = a.mask; p.ld_mask = a.ld_mask; p.relu = a.relu ? 1 : 0; p.out = a.out; p.ld_out = a.ld_out;
+  p.dot_vec = a.dot_vec; p.dot_out = a.dot_vec ? a.dot_out : nullptr;
   if ((reinterpret_cast<uintptr_t>(a.out) & 15u) || (a.ld_out & 3) || (a.mask && ((reinterpret_cast<uintptr_t>(a.mask) & 15u) || (a.ld_mask & 3))))
     return cudaErrorInvalidValue;
   if ((e = encode_kmajor_map(&p.map_out, a.out, a.ld_out, a.N, a.n_rows, 32, true)) != cudaSuccess) return e;
@@ -528,12 +539,14 @@ cudaError_t launch_linear_tc(const LinearTcArgs& a, cudaStream_t s) {
     p.map_mask = p.map_out;
   }
   const size_t smem = (size_t)kLinStages * (kLinRows * 128 + a.N * 128) + kLinStageBytes + 256;
-  if ((e = cudaFuncSetAttribute(k_linear_tf32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+  const bool dot = a.dot_vec != nullptr && a.dot_out != nullptr;
+  if ((e = cudaFuncSetAttribute(dot ? k_linear_tf32<true> : k_linear_tf32<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
   int dev = 0, sms = 0;
   if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
   if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
   const int64_t n_tiles = (a.n_rows + kLinRows - 1) / kLinRows;
-  k_linear_tf32<<<(unsigned)(n_tiles < sms ? n_tiles : sms), kTcThreads, smem, s>>>(p);
+  if (dot) k_linear_tf32<true><<<(unsigned)(n_tiles < sms ? n_tiles : sms), kTcThreads, smem, s>>>(p);
+  else k_linear_tf32<false><<<(unsigned)(n_tiles < sms ? n_tiles : sms), kTcThreads, smem, s>>>(p);
   return cudaGetLastError();
 }
 

@@ -144,6 +144,9 @@ struct LinearTcArgs {
   const float* mask; int ld_mask;
   bool relu;
   float* out; int ld_out;
+  // optional rank-1 reduction of the OUTPUT rows: dot_out[p] = sum_n Y[p][n] * dot_vec[n] (the density head on h7,
+  // VipNeRF01.py:546: it rides along in the epilogue that holds the row instead of re-reading 1 KiB per point)
+  const float* dot_vec; float* dot_out;
 };
 cudaError_t launch_linear_tc(const LinearTcArgs& a, cudaStream_t s);
 // out[m][n] = sum_p G[p][m] * H[p][n] for M <= 4 (G: M floats per row), N <= 256; gsum_dst[m] = sum_p G[p][m].

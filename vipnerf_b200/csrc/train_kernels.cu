@@ -439,18 +439,27 @@ k_small_tn(const float* __restrict__ G, const float* __restrict__ H, int N, int6
 __global__ void __launch_bounds__(128)
 k_encode_points(RayPtrs rp, RenderFlags fl, int64_t n_points, int S, const float* __restrict__ z,
                 float* __restrict__ enc, float* __restrict__ pev) {
-  const int64_t pg = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (pg >= n_points) return;
-  const int64_t ray = pg / S;
+  // A thread computes one point's row, but writing 64 (32) floats of its own row touches 32 different lines per
+  // instruction; the block's rows are contiguous in memory, so they are staged in shared memory (row stride 65 / 33:
+  // conflict-free for row-per-thread writes) and copied out with full-line stores.
+  __shared__ float tile[128 * 65];
+  const int64_t p0 = (int64_t)blockIdx.x * blockDim.x;
+  const int64_t pg = p0 + threadIdx.x;
+  const bool valid = pg < n_points;
+  const int n_here = (int)min((int64_t)blockDim.x, n_points - p0);
+  const int64_t pc = valid ? pg : n_points - 1;
+  const int64_t ray = pc / S;
   const int nviews = 1 + fl.n_sec_views;
-  const float zz = z[pg];
-  float* e = enc + pg * 64;
+  const float zz = z[pc];
+  float* e = tile + threadIdx.x * 65;
 #pragma unroll
   for (int axis = 0; axis < 3; ++axis) {
     const float x = fadd(rp.pts_o[3 * ray + axis], fmul(rp.pts_d[3 * ray + axis], zz));   // :105-107
     encode_axis<kLPts>(x, axis, [&](int col, float v) { e[col] = v; });
   }
   e[63] = 0.f;
+  __syncthreads();
+  for (int i = threadIdx.x; i < n_here * 64; i += blockDim.x) enc[p0 * 64 + i] = tile[(i >> 6) * 65 + (i & 63)];
   for (int v = 0; v < nviews; ++v) {
     float dir[3];
     if (v == 0) {
@@ -463,11 +472,16 @@ k_encode_points(RayPtrs rp, RenderFlags fl, int64_t n_points, int S, const float
       const float zw = fl.ndc ? depth_from_ndc_secondary(zz, o3[2], d3[2]) : zz;
       secondary_view_dir(o3, d3, zw, o2, dir);
     }
-    float* pe = pev + (pg * nviews + v) * 32;
+    __syncthreads();     // the previous copy-out has read the tile
+    float* pe = tile + threadIdx.x * 33;
 #pragma unroll
     for (int axis = 0; axis < 3; ++axis) encode_axis<kLView>(dir[axis], axis, [&](int col, float val) { pe[col] = val; });
 #pragma unroll
     for (int c = kEncView; c < 32; ++c) pe[c] = 0.f;
+    __syncthreads();
+    // row r of this view lives at pev[((p0 + r) * nviews + v) * 32 ...]: one full 128-byte line per row
+    for (int i = threadIdx.x; i < n_here * 32; i += blockDim.x)
+      pev[((p0 + (i >> 5)) * nviews + v) * 32 + (i & 31)] = tile[(i >> 5) * 33 + (i & 31)];
   }
 }
 
@@ -492,12 +506,16 @@ k_heads_fwd(int64_t n_points, int nviews, const float* __restrict__ small, const
   const int64_t pg = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (pg >= n_points) return;
   {
-    const float4* h = reinterpret_cast<const float4*>(h7 + pg * 256);
     float s = 0.f;
+    if (h7 == nullptr) {
+      s = out_sigma[pg];     // the producer of h7 (k_linear_tf32's epilogue, LinearTcArgs::dot_vec) left w_sigma . h7 here
+    } else {
+      const float4* h = reinterpret_cast<const float4*>(h7 + pg * 256);
 #pragma unroll 8
-    for (int i = 0; i < 64; ++i) {
-      const float4 a = h[i];
-      s = fmaf(a.x, s_ws[4 * i], s); s = fmaf(a.y, s_ws[4 * i + 1], s); s = fmaf(a.z, s_ws[4 * i + 2], s); s = fmaf(a.w, s_ws[4 * i + 3], s);
+      for (int i = 0; i < 64; ++i) {
+        const float4 a = h[i];
+        s = fmaf(a.x, s_ws[4 * i], s); s = fmaf(a.y, s_ws[4 * i + 1], s); s = fmaf(a.z, s_ws[4 * i + 2], s); s = fmaf(a.w, s_ws[4 * i + 3], s);
+      }
     }
     float pre = s + small[kOffBSigma];
     if (noise != nullptr) pre = pre + noise[pg];
