@@ -507,7 +507,7 @@ def run_train(args, rank, world, local_rank):
         sm_mhz = clocks.get('sm_mhz') or 1900.0
         peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12     # fp32 FFMA lanes x 2 FLOP x measured SM clock
         achieved = value / world * 256 * TRAIN_FLOP_PER_POINT / 1e12
-        if args.train_precision == 'tf32':
+        if args.train_precision in ('tf32', 'fp16'):
             # the tensor-core step is HBM-bound: activations and gradients make one round trip per consumer
             hbm_peak = 6464.3
             ppath = os.path.join(ROOT, 'MEASURED_PEAKS.json')
@@ -584,7 +584,7 @@ def main():
     ap.add_argument('--rays-per-step', type=int, default=RAYS_PER_STEP)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--workload', default='batch', choices=['batch', 'frame', 'train'])
-    ap.add_argument('--train-precision', default='fp32', choices=['fp32', 'tf32'],
+    ap.add_argument('--train-precision', default='fp32', choices=['fp32', 'tf32', 'fp16'],
                     help='train workload: tf32 = every 256-wide product of the step on the tensor cores (tcgen05 kind::tf32)')
     ap.add_argument('--rng', default='reference', choices=['reference', 'device'],
                     help='train workload: where the stratified jitter / cdf samples / density noise are drawn')

@@ -46,6 +46,10 @@ typedef enum vipnerf_status {
                                               (forward chain, backward-data chain, parameter gradients dW = dY^T X) runs
                                               on the tensor cores (tcgen05 kind::tf32: operands rounded to tf32, fp32
                                               accumulate) instead of fp32 CUDA cores                               */
+#define VIPNERF_FLAG_TRAIN_F16   (1u << 4) /* the same three product families on tcgen05 kind::f16 with every saved
+                                              activation and chain gradient stored as fp16 (11-bit significand like tf32,
+                                              half the HBM bytes of every stream; gradients carry per-array power-of-two
+                                              scales measured on the device, fp32 accumulate).  Exclusive with TRAIN_TF32 */
 
 /* cfg.precision: arithmetic of the 256-wide matmuls (trunk layers, feature_linear, feature columns of
  * views_linears.0).  Everything else (encodings, heads, compositing, sampling) is always fp32. */
@@ -238,7 +242,8 @@ int vipnerf_visibility_prior(int32_t height, int32_t width, const uint8_t* frame
  * sec_views_vis are forced on, :40) and the gradient of every parameter given the gradients of the outputs.
  * The losses themselves stay the caller's (loss_functions/*.py operate on the returned tensors).
  * Arithmetic: cfg->precision must be VIPNERF_PRECISION_FP32 (fp32 packed weights); fp32 CUDA-core kernels like the
- * reference's training arithmetic by default, tensor cores with VIPNERF_FLAG_TRAIN_TF32.  Random numbers are the caller's: rays->t_rand [R,Nc], rays->u_rand [R,Nf] (torch.rand) and
+ * reference's training arithmetic by default, tensor cores with VIPNERF_FLAG_TRAIN_TF32 / VIPNERF_FLAG_TRAIN_F16 (the same
+ * flag must be set for the forward, the backward and the two size queries).  Random numbers are the caller's: rays->t_rand [R,Nc], rays->u_rand [R,Nf] (torch.rand) and
  * sigma_noise_* = raw_noise_std * torch.randn, drawn exactly where the reference draws them; NULL = that source off.
  *
  * `saved` (vipnerf_train_saved_bytes, about 11 KB per sample point) receives the activations of both MLPs; the caller
@@ -301,10 +306,12 @@ int vipnerf_composite_backward(const vipnerf_cfg* cfg, const vipnerf_rays* rays,
  * dw[m * ld_dw + n] = sum_p dy[p * ld_dy + m] * x[p * ld_x + n] for n < n_valid (what autograd computes for
  * nn.Linear.weight: grad_output^T @ input), db[m] = sum_p dy[p * ld_dy + m] (NULL = skip).
  * m in {128, 256}; n in {32, 64, 128, 256}.  mode 0 = fp32 CUDA-core kernel (k_gemm_tn; what vipnerf_train_backward
- * uses by default), mode 1 = tcgen05 kind::tf32 kernel (k_gemm_tn_tf32; n in {32, 64, 256}; operands rounded to tf32 by the
- * TMA copy; what VIPNERF_FLAG_TRAIN_TF32 selects).  workspace: vipnerf_param_gradient_gemm_workspace_bytes() bytes, 256-byte aligned. */
+ * uses by default), mode 1 = tcgen05 kind::tf32 kernel (k_gemm_tn_tc<false>; n in {32, 64, 256}; operands rounded to tf32 by the
+ * TMA copy; what VIPNERF_FLAG_TRAIN_TF32 selects), mode 2 = tcgen05 kind::f16 kernel (k_gemm_tn_tc<true>; dy and x are
+ * fp16 arrays, leading dimensions in elements, n in {64, 256}; what VIPNERF_FLAG_TRAIN_F16 selects).
+ * workspace: vipnerf_param_gradient_gemm_workspace_bytes() bytes, 256-byte aligned. */
 size_t vipnerf_param_gradient_gemm_workspace_bytes(void);
-int vipnerf_param_gradient_gemm(const float* dy, int32_t ld_dy, int32_t m, const float* x, int32_t ld_x, int32_t n,
+int vipnerf_param_gradient_gemm(const void* dy, int32_t ld_dy, int32_t m, const void* x, int32_t ld_x, int32_t n,
                                 int64_t n_rows, float* dw, int32_t ld_dw, int32_t n_valid, float* db, int32_t mode,
                                 void* workspace, size_t workspace_bytes, void* stream);
 

@@ -49,12 +49,17 @@ def test_config_validation(built_library):
     x3 = _lib.make_cfg(precision='bf16x3')
     assert lib.vipnerf_packed_weight_bytes(ctypes.byref(x3)) == 27648 + 2 * ((64 + 6) * 16384 + 8192)
     f32 = _lib.make_cfg(precision='fp32')
-    assert lib.vipnerf_packed_weight_bytes(ctypes.byref(f32)) == 27648 + (589824 + 589824) * 4   # forward images + [out][in] images (backward-data chain, tensor-core forward)
+    assert lib.vipnerf_packed_weight_bytes(ctypes.byref(f32)) == 27648 + (589824 + 589824) * (4 + 2)   # forward images + [out][in] images (backward-data chain, tensor-core forward), + their fp16 mirror (fp16 training mode)
     # training buffers: fp32 only; about 11 KB of saved activations per sample point
     assert lib.vipnerf_train_saved_bytes(ctypes.byref(ok), 4096) == 0
     f32v = _lib.make_cfg(precision='fp32', n_sec_views=1)
     per_point = lib.vipnerf_train_saved_bytes(ctypes.byref(f32v), 4096) / (4096 * 256)
     assert 10500 < per_point < 11500
+    f16v = _lib.make_cfg(precision='fp32', n_sec_views=1, train_precision='fp16')   # fp16 arrays: half of everything
+    assert 5250 < lib.vipnerf_train_saved_bytes(ctypes.byref(f16v), 4096) / (4096 * 256) < 5800
+    both = _lib.make_cfg(precision='fp32', train_precision='fp16')
+    both.flags |= _lib.FLAG_TRAIN_TF32                                              # the two tensor-core modes are exclusive
+    assert lib.vipnerf_train_saved_bytes(ctypes.byref(both), 4096) == 0
     assert lib.vipnerf_train_workspace_bytes(ctypes.byref(f32v), 4096) > 4096 * 192 * 9 * 1024
     assert lib.vipnerf_train_forward(ctypes.byref(ok), None, 16, None, None, None, None, None, None, 0, None, 0, None) == -2
     assert lib.vipnerf_train_forward(ctypes.byref(f32), None, 16, None, None, None, None, None, None, 0, None, 0, None) == -1

@@ -150,32 +150,42 @@ def _compare_full_grads(model, ref_grads, max_tol=GRAD_MAX_TOL, norm_tol=5 * GRA
     return worst[0], worst[1], worst_norm
 
 
-@pytest.mark.parametrize('mode', [0, 1])
-@pytest.mark.parametrize('P,M,N', [(4096, 256, 256), (10007, 128, 256), (96, 256, 256), (777, 256, 64), (5000, 128, 32)])
+@pytest.mark.parametrize('mode', [0, 1, 2])
+@pytest.mark.parametrize('P,M,N', [(4096, 256, 256), (10007, 128, 256), (96, 256, 256), (777, 256, 64), (5000, 128, 32),
+                                   (3001, 128, 64)])
 def test_param_gradient_gemm(P, M, N, mode, built_library):
-    """dW = dY^T X and db = column sums, fp32 CUDA-core kernel (mode 0) and tcgen05 tf32 kernel (mode 1, N in {32, 64, 256}),
-    against an fp64 product; ragged row counts exercise the zero-filled tails of both kernels."""
+    """dW = dY^T X and db = column sums, fp32 CUDA-core kernel (mode 0), tcgen05 tf32 kernel (mode 1, N in {32, 64, 256})
+    and tcgen05 fp16 kernel (mode 2, fp16 arrays, N in {64, 256}), against an fp64 product; ragged row counts exercise
+    the zero-filled tails of the kernels."""
     from vipnerf_b200 import training
     if mode == 1:
         with pytest.raises(NotImplementedError):     # the tensor kernel is built for N in {32, 64, 256}
             training.param_gradient_gemm(torch.zeros(P, M, device='cuda'), torch.zeros(P, 128, device='cuda'), mode=1)
+    if mode == 2 and N == 32:
+        with pytest.raises(NotImplementedError):     # an fp16 box row is 64 columns
+            training.param_gradient_gemm(torch.zeros(P, M, device='cuda'), torch.zeros(P, 32, device='cuda'), mode=2)
+        return
     g = torch.Generator().manual_seed(P + M + N)
     dy = (torch.randn(P, M, generator=g) * torch.rand(P, 1, generator=g)).cuda()
     x = torch.relu(torch.randn(P, N, generator=g)).cuda()
     dw, db = training.param_gradient_gemm(dy, x, mode=mode)
     ref = dy.double().t() @ x.double()
     err = ((dw.double() - ref).abs().max() / ref.abs().max()).item()
-    assert err <= (1e-3 if mode == 1 else 2e-6), err          # tf32: 2^-11 per operand; fp32: summation order
+    assert err <= (1e-3 if mode else 2e-6), err          # tf32 / fp16: 2^-11 per operand; fp32: summation order
+    if mode == 2:   # against the product of the fp16-rounded operands the only difference is the summation order
+        ref16 = dy.half().double().t() @ x.half().double()
+        assert ((dw.double() - ref16).abs().max() / ref16.abs().max()).item() <= 2e-6
     ref_b = dy.double().sum(0)
-    # mode 1: the column sums ride along in the tensor kernel, on the tf32-rounded boxes the TMA engine delivered
-    assert ((db.double() - ref_b).abs().max() / ref_b.abs().max()).item() <= (1e-3 if mode == 1 else 2e-6)
+    # modes 1 / 2: the column sums ride along in the tensor kernel, on the rounded boxes the TMA engine delivered
+    assert ((db.double() - ref_b).abs().max() / ref_b.abs().max()).item() <= (1e-3 if mode else 2e-6)
     again, db_again = training.param_gradient_gemm(dy, x, mode=mode)
     assert torch.equal(dw, again) and torch.equal(db, db_again)   # fixed-order split reduction
 
 
 @pytest.mark.parametrize('scene,n_rays,n_sec,train_precision', [
     ('fern', 333, 1, 'fp32'), ('dtu', 200, 3, 'fp32'), ('re10k', 128, 1, 'fp32'),   # re10k = BASELINE config 3
-    ('fern', 333, 1, 'tf32'), ('re10k', 128, 1, 'tf32')])
+    ('fern', 333, 1, 'tf32'), ('re10k', 128, 1, 'tf32'), ('dtu', 200, 3, 'tf32'),
+    ('fern', 333, 1, 'fp16'), ('re10k', 128, 1, 'fp16'), ('dtu', 200, 3, 'fp16')])
 def test_training_gradients_vs_oracle_autograd(scene, n_rays, n_sec, train_precision, built_library):
     """Full gradient tensors against torch autograd over the oracle, with the draws of the plugin's own generator
     mirror, a ray count that is not a multiple of anything, and a different number of secondary views."""
@@ -193,14 +203,17 @@ def test_training_gradients_vs_oracle_autograd(scene, n_rays, n_sec, train_preci
     ref_out, ref_total, ref_grads = _oracle_step(O.synth_state_dict(0), rays, sup, draws, ndc, chunk=128, netchunk=5000)
     # tf32 mode: every 256-wide product of the step sees operands rounded to 10 mantissa bits (PyTorch's allow_tf32
     # arithmetic), fp32 accumulation; heads, compositing and sampling stay fp32
-    tf32 = train_precision == 'tf32'
+    # fp16 mode: the same products on fp16 copies (the same 10 mantissa bits), saved activations and chain gradients
+    # stored as fp16 (gradients with per-array power-of-two scales): the tensor-core gates apply unchanged
+    tf32 = train_precision in ('tf32', 'fp16')
     assert abs(total.item() - ref_total.item()) <= (2e-3 if tf32 else 2e-4) * abs(ref_total.item())
     for k in ('rgb_coarse', 'rgb_fine', 'visibility2_coarse', 'visibility2_fine', 'depth_coarse', 'raw_sigma_coarse',
               'raw_rgb_coarse', 'raw_visibility_coarse'):
         mx, med = H.rel_err(out[k], ref_out[k])
         print(f'{scene} {train_precision} {k}: max {mx:.2e} median {med:.2e}')
-        if tf32:   # measured: composited maps 1e-5, density logits 7e-4 (max), everything else 7e-6
-            assert mx <= (5e-3 if k.startswith('raw_sigma') else 5e-4) and med <= 5e-4, (k, mx, med)
+        if tf32:   # measured: composited maps 1e-5, density logits 7e-4 (max), everything else 7e-6; the fine maps of a
+            # few rays also see sample_pdf's sensitivity to the coarse weights (dtu: 1e-3 max at a median of 1e-5)
+            assert mx <= (5e-3 if k.startswith('raw_sigma') else (2e-3 if k.endswith('_fine') else 5e-4)) and med <= 5e-4, (k, mx, med)
         else:
             assert mx <= 1e-4, (k, mx)
     # measured in tf32 mode: worst entry 3e-3 .. 6e-3 of the tensor's max, L2 error 5e-3 .. 6e-3
@@ -312,7 +325,7 @@ def test_fused_losses_match_reference_golden_step(scene, built_library):
     assert len(report) == 48
 
 
-@pytest.mark.parametrize('train_precision', ['fp32', 'tf32'])
+@pytest.mark.parametrize('train_precision', ['fp32', 'tf32', 'fp16'])
 def test_fused_losses_equal_torch_losses(train_precision, built_library):
     """Same model, same draws: the fused path and the torch evaluation of the same four losses (autograd through the
     dense output tensors) give the same values and - up to the re-association of sums - the same gradients; an extra

@@ -95,8 +95,9 @@ class VipNeRFFused(torch.nn.Module):
         self.precision = model_cfg.get('precision', 'bf16')   # 'fp32' | 'bf16' | 'fp16' | 'bf16x3'
         if self.precision not in ('fp32', 'bf16', 'fp16', 'bf16x3'):
             raise ValueError(f"configs['model']['precision'] = {self.precision!r}")
-        # training arithmetic: 'fp32' (like the reference) or 'tf32' = the 256-wide products of the step on the tensor cores
-        if model_cfg.get('train_precision', 'fp32') not in ('fp32', 'tf32'):
+        # training arithmetic: 'fp32' (like the reference), 'tf32' = the 256-wide products of the step on the tensor cores,
+        # 'fp16' = the same products with fp16 saved activations / chain gradients (half the HBM traffic of the step)
+        if model_cfg.get('train_precision', 'fp32') not in ('fp32', 'tf32', 'fp16'):
             raise ValueError(f"configs['model']['train_precision'] = {model_cfg['train_precision']!r}")
         self.coarse_model = RadianceMLPParams(model_cfg['coarse_mlp'])
         self.fine_model = RadianceMLPParams(model_cfg['fine_mlp']) if self.fine_mlp_needed else None
@@ -214,7 +215,7 @@ class VipNeRFFused(torch.nn.Module):
             batch, self.coarse_model.named_tensors(), self.fine_model.named_tensors() if self.fine_mlp_needed else None,
             ndc=self.ndc, n_coarse=n_coarse, n_fine=n_fine, n_sec_views=n_sec_views,
             white_bkgd=model_cfg['white_bkgd'], lindisp=model_cfg['lindisp'],
-            tf32=model_cfg.get('train_precision', 'fp32') == 'tf32')
+            train_precision=model_cfg.get('train_precision', 'fp32'))
 
     def render(self, input_dict: dict, retraw: bool, sec_views_vis: bool, out: Optional[dict] = None):
         batch, n_sec_views = self._ray_batch(input_dict, sec_views_vis)

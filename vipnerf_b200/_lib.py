@@ -14,7 +14,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'libvipnerf_b200.so')
 
 ABI_VERSION = 1
-FLAG_NDC, FLAG_WHITE_BKGD, FLAG_LINDISP, FLAG_TRAIN_TF32 = 1, 2, 4, 8
+FLAG_NDC, FLAG_WHITE_BKGD, FLAG_LINDISP, FLAG_TRAIN_TF32, FLAG_TRAIN_F16 = 1, 2, 4, 8, 16
+TRAIN_PRECISIONS = ('fp32', 'tf32', 'fp16')
 PRECISION = {'fp32': 0, 'bf16': 1, 'bf16x3': 2, 'fp16': 3}
 STATUS_NAMES = {0: 'OK', -1: 'EINVAL', -2: 'EUNSUPPORTED', -3: 'ECUDA', -4: 'EWORKSPACE', -5: 'EABI'}
 
@@ -154,8 +155,14 @@ def check(status: int, what: str) -> None:
 
 
 def make_cfg(n_coarse=64, n_fine=128, n_sec_views=0, ndc=False, white_bkgd=False, lindisp=False, precision='bf16',
-             l_pts=10, l_view=4, depth=8, width=256, skip=4, train_tf32=False) -> Cfg:
+             l_pts=10, l_view=4, depth=8, width=256, skip=4, train_tf32=False, train_precision=None) -> Cfg:
+    """train_precision: arithmetic of the training entry points - 'fp32' (CUDA cores), 'tf32' or 'fp16' (tensor cores);
+    train_tf32=True is the older spelling of 'tf32'."""
+    if train_precision is None:
+        train_precision = 'tf32' if train_tf32 else 'fp32'
+    if train_precision not in TRAIN_PRECISIONS:
+        raise ValueError(f'train_precision = {train_precision!r}')
     flags = ((FLAG_NDC if ndc else 0) | (FLAG_WHITE_BKGD if white_bkgd else 0) | (FLAG_LINDISP if lindisp else 0)
-             | (FLAG_TRAIN_TF32 if train_tf32 else 0))
+             | (FLAG_TRAIN_TF32 if train_precision == 'tf32' else 0) | (FLAG_TRAIN_F16 if train_precision == 'fp16' else 0))
     return Cfg(ABI_VERSION, n_coarse, n_fine, l_pts, l_view, depth, width, skip, n_sec_views, flags,
                PRECISION[precision], 0)

@@ -148,14 +148,18 @@ PassGradPtrs to_grads(const vipnerf_pass_out* o) {
 struct SavedPass { size_t enc, h, feat, hv, pev, end; };
 struct SavedLayout { SavedPass coarse, fine; size_t total; };
 
+bool train_f16(const vipnerf_cfg* cfg) { return (cfg->flags & VIPNERF_FLAG_TRAIN_F16) != 0; }
+
+// fp32 arrays, or fp16 arrays in the fp16 mode (VIPNERF_FLAG_TRAIN_F16; a pev row is then 64 columns = 128 bytes as well)
 SavedLayout carve_saved(const vipnerf_cfg* cfg, int64_t n_rays) {
   SavedLayout L{};
   const size_t R = (size_t)(n_rays > 0 ? n_rays : 0), nv = 1 + (size_t)cfg->n_sec_views;
+  const size_t es = train_f16(cfg) ? 2 : 4;
   size_t off = 0;
-  auto take = [&](size_t floats) { size_t o = off; off = align_up(off + floats * sizeof(float), 256); return o; };
+  auto take = [&](size_t elems) { size_t o = off; off = align_up(off + elems * es, 256); return o; };
   auto pass = [&](size_t P) {
     SavedPass s{};
-    s.enc = take(P * 64); s.h = take(P * 256 * 8); s.feat = take(P * 256); s.hv = take(P * nv * 128); s.pev = take(P * nv * 32);
+    s.enc = take(P * 64); s.h = take(P * 256 * 8); s.feat = take(P * 256); s.hv = take(P * nv * 128); s.pev = take(P * nv * (es == 2 ? 64 : 32));
     s.end = off;
     return s;
   };
@@ -174,16 +178,20 @@ size_t gemm_partial_floats() {
 }
 
 // Scratch of the backward: sized for the larger sample set, reused by both
-struct BwdLayout { size_t dsig, dlogit, dpre, dfeat, dacc9, dhv, partial, total; };
+struct BwdLayout { size_t dsig, dlogit, dpre, dfeat, dacc9, dhv, partial, amax, total; };
+constexpr int kAmaxSlots = 16;   // fp16 mode: measured maxima that define the gradient scales (one set per sample set)
 
 BwdLayout carve_bwd(const vipnerf_cfg* cfg, int64_t n_rays) {
   BwdLayout L{};
   const size_t R = (size_t)(n_rays > 0 ? n_rays : 0), nv = 1 + (size_t)cfg->n_sec_views;
   const size_t P = R * ((size_t)cfg->n_coarse + cfg->n_fine);
+  const size_t es = train_f16(cfg) ? 2 : 4;     // the chain's gradient arrays are fp16 in the fp16 mode
   size_t off = 0;
-  auto take = [&](size_t floats) { size_t o = off; off = align_up(off + floats * sizeof(float), 256); return o; };
-  L.dsig = take(P); L.dlogit = take(P * nv * 4); L.dpre = take(P * 256 * 8); L.dfeat = take(P * 256);
-  L.dacc9 = take(P * 128); L.dhv = take(P * nv * 128); L.partial = take(gemm_partial_floats() + kColsumPartialFloats);
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+  L.dsig = take(P * 4); L.dlogit = take(P * nv * 4 * 4); L.dpre = take(P * 256 * 8 * es); L.dfeat = take(P * 256 * es);
+  L.dacc9 = take(P * 128 * es); L.dhv = take(P * nv * 128 * es);
+  L.partial = take((gemm_partial_floats() + kColsumPartialFloats) * sizeof(float));
+  L.amax = take(2 * kAmaxSlots * sizeof(uint32_t));
   L.total = off + 256;
   return L;
 }
@@ -195,31 +203,52 @@ const float* packed_big(const void* packed) {   // forward images Wt[in][out] (l
 }
 const float* packed_out_in(const void* packed) { return packed_big(packed) + kFp32BigFloats; }   // [out][in] images
 
-LinearTcArgs linear_args(const float* x, int ldx, int k, const float* w, int ldw, int N, int64_t P, float* out, int ld_out) {
+LinearTcArgs linear_args(const void* x, int ldx, int k, const void* w, int ldw, int N, int64_t P, void* out, int ld_out,
+                         bool half) {
   LinearTcArgs a{};
   a.x[0] = x; a.ldx[0] = ldx; a.k[0] = k; a.w[0] = w; a.ldw[0] = ldw;
   a.N = N; a.n_rows = P; a.out = out; a.ld_out = ld_out;
+  a.half_in = half; a.half_out = half;
   return a;
 }
 
-// MLP.forward of one sample set on the tensor cores: encodings -> ten products -> heads; fills the saved activations
+// byte pointers into the saved-activation / gradient arrays (element size es) and the two weight regions
+struct ElemPtr {
+  const uint8_t* base; size_t es;
+  const void* at(size_t elem) const { return base + elem * es; }
+};
+ElemPtr weights_out_in(const void* packed, bool half) {   // [out][in] images
+  if (!half) return {reinterpret_cast<const uint8_t*>(packed_out_in(packed)), 4};
+  return {reinterpret_cast<const uint8_t*>(packed_big(packed) + kFp32BigFloats + kFp32BwdFloats) + (size_t)kFp32BigFloats * 2, 2};
+}
+ElemPtr weights_in_out(const void* packed, bool half) {   // forward images Wt[in][out]
+  if (!half) return {reinterpret_cast<const uint8_t*>(packed_big(packed)), 4};
+  return {reinterpret_cast<const uint8_t*>(packed_big(packed) + kFp32BigFloats + kFp32BwdFloats), 2};
+}
+
+// what the forward keeps (kernels.h MlpSave) with the element type of the mode
+struct SavePtrs { const float* noise; uint8_t *enc, *h, *feat, *hv, *pev; };
+
+// MLP.forward of one sample set on the tensor cores: encodings -> ten products -> heads; fills the saved activations.
+// half = fp16 arrays and kind::f16 products, else fp32 arrays read as tf32.
 cudaError_t mlp_forward_tc(const RayPtrs& rp, const RenderFlags& fl, int64_t n_rays, int S, const float* z,
-                           const void* packed, const MlpSave& sv, float* acc9, float* sigma, float* rgb, float* vis,
-                           float* vis2, cudaStream_t s) {
+                           const void* packed, const SavePtrs& sv, float* acc9, float* sigma, float* rgb, float* vis,
+                           float* vis2, cudaStream_t s, bool half) {
   const int64_t P = n_rays * S;
-  const size_t PL = (size_t)P * 256;
+  const size_t es = half ? 2 : 4;
+  const size_t PL = (size_t)P * 256 * es;      // bytes of one [P][256] array
   const float* small = packed_small(packed);
-  const float* woi = packed_out_in(packed);
+  const ElemPtr woi = weights_out_in(packed, half);
   cudaError_t e;
-  if ((e = launch_encode_points(rp, fl, n_rays, S, z, sv.enc, sv.pev, s)) != cudaSuccess) return e;
+  if ((e = launch_encode_points(rp, fl, n_rays, S, z, sv.enc, sv.pev, s, half)) != cudaSuccess) return e;
   for (int l = 0; l < 8; ++l) {
     LinearTcArgs a;
     if (l == 0) {
-      a = linear_args(sv.enc, 64, 64, woi + kBwdOffEnc0, 64, 256, P, sv.h, 256);
+      a = linear_args(sv.enc, 64, 64, woi.at(kBwdOffEnc0), 64, 256, P, sv.h, 256, half);
     } else {
-      a = linear_args(sv.h + (l - 1) * PL, 256, 256, woi + kBwdOffTrunk + (size_t)(7 - l) * 65536, 256, 256, P, sv.h + l * PL, 256);
+      a = linear_args(sv.h + (l - 1) * PL, 256, 256, woi.at(kBwdOffTrunk + (size_t)(7 - l) * 65536), 256, 256, P, sv.h + l * PL, 256, half);
       if (l == 5) {   // cat([encoding, h4]) (:543-544): a second operand pair accumulates into the same tile
-        a.x[1] = sv.enc; a.ldx[1] = 64; a.k[1] = 64; a.w[1] = woi + kBwdOffEnc5; a.ldw[1] = 64;
+        a.x[1] = sv.enc; a.ldx[1] = 64; a.k[1] = 64; a.w[1] = woi.at(kBwdOffEnc5); a.ldw[1] = 64;
       }
     }
     a.bias = small + kOffBias + l * 256;
@@ -227,32 +256,62 @@ cudaError_t mlp_forward_tc(const RayPtrs& rp, const RenderFlags& fl, int64_t n_r
     if (l == 7) { a.dot_vec = small + kOffWSigma; a.dot_out = sigma; }   // the density head rides along (read back by k_heads_fwd)
     if ((e = launch_linear_tc(a, s)) != cudaSuccess) return e;
   }
-  LinearTcArgs f = linear_args(sv.h + 7 * PL, 256, 256, woi + kBwdOffFeature, 256, 256, P, sv.feat, 256);
+  LinearTcArgs f = linear_args(sv.h + 7 * PL, 256, 256, woi.at(kBwdOffFeature), 256, 256, P, sv.feat, 256, half);
   f.bias = small + kOffBias + 8 * 256;
   if ((e = launch_linear_tc(f, s)) != cudaSuccess) return e;
-  LinearTcArgs v = linear_args(sv.feat, 256, 256, woi + kBwdOffViews, 256, 128, P, acc9, 128);
+  LinearTcArgs v = linear_args(sv.feat, 256, 256, woi.at(kBwdOffViews), 256, 128, P, acc9, 128, half);
+  v.half_out = false;      // the heads add the direction term and the bias in fp32 on top of the fp32 accumulators
   if ((e = launch_linear_tc(v, s)) != cudaSuccess) return e;
-  return launch_heads_fwd(P, 1 + fl.n_sec_views, packed, nullptr, acc9, sv.pev, sv.noise, sigma, rgb, vis, vis2, sv.hv, s);
+  return launch_heads_fwd(P, 1 + fl.n_sec_views, packed, nullptr, acc9, sv.pev, sv.noise, sigma, rgb, vis, vis2, sv.hv, s, half);
 }
 
-// backward-data chain of one sample set on the tensor cores (same outputs as launch_mlp_bwd_fp32)
-cudaError_t mlp_backward_tc(const MlpBwdArgs& a, const void* packed, cudaStream_t s) {
+// Gradient scales of the fp16 mode: every fp16 gradient array is stored times a power of two derived from a maximum
+// measured on the device (grad_scale_from_amax, kernels.h).  Slot that DEFINES the scale of each array, and what the
+// producing kernel records for the next one:
+//   slot 0  max |dlogit|                       (k_grad_amax)        defines dhv, dacc9
+//   slot 1  max |dacc9|                        (k_heads_bwd)        defines dfeat
+//   slot 2  max(max |dfeat|, max |dsig| max |w_sigma|)  (k_linear_tc / k_grad_amax)  defines dpre[7]
+//   slot 10 - l  max |dpre[l + 1]|             (k_linear_tc)        defines dpre[l], l = 6 .. 0
+// A layer's output is re-centred on the maximum of its INPUT: one layer moves the magnitude by far less than the 11
+// binades of head room (and the conversions saturate), so no array needs a second pass.
+constexpr int kSlotLogit = 0, kSlotAcc9 = 1, kSlotFeat = 2;
+constexpr int dpre_slot(int l) { return l == 7 ? kSlotFeat : 10 - l; }
+
+// backward-data chain of one sample set on the tensor cores (same outputs as launch_mlp_bwd_fp32); byte pointers
+struct BwdPtrs {
+  int64_t n_points; int nviews;
+  const float *dsig, *dlogit;
+  const uint8_t *h, *hv;
+  uint8_t *dpre, *dfeat, *dacc9, *dhv;
+  uint32_t* amax;     // kAmaxSlots slots of this sample set (fp16 mode), zeroed here
+};
+cudaError_t mlp_backward_tc(const BwdPtrs& a, const void* packed, cudaStream_t s, bool half) {
   const int64_t P = a.n_points;
-  const size_t PL = (size_t)P * 256;
+  const size_t es = half ? 2 : 4;
+  const size_t PL = (size_t)P * 256 * es;
   const float* small = packed_small(packed);
-  const float* wio = packed_big(packed);
+  const ElemPtr wio = weights_in_out(packed, half);
+  uint32_t* am = half ? a.amax : nullptr;
   cudaError_t e;
-  if ((e = launch_heads_bwd(P, a.nviews, packed, a.dlogit, a.hv, a.dhv, a.dacc9, s)) != cudaSuccess) return e;
-  LinearTcArgs g = linear_args(a.dacc9, 128, 128, wio + fp32_layer_offset(9), 128, 256, P, a.dfeat, 256);
+  if (half) {
+    if ((e = cudaMemsetAsync(am, 0, kAmaxSlots * sizeof(uint32_t), s)) != cudaSuccess) return e;
+    if ((e = launch_grad_amax(P, a.nviews, packed, a.dlogit, a.dsig, am + kSlotLogit, am + kSlotFeat, s)) != cudaSuccess) return e;
+  }
+  if ((e = launch_heads_bwd(P, a.nviews, packed, a.dlogit, a.hv, a.dhv, a.dacc9, s, half, half ? am + kSlotLogit : nullptr,
+                            half ? am + kSlotAcc9 : nullptr)) != cudaSuccess) return e;
+  LinearTcArgs g = linear_args(a.dacc9, 128, 128, wio.at(fp32_layer_offset(9)), 128, 256, P, a.dfeat, 256, half);
+  if (half) { g.scale_in = am + kSlotLogit; g.scale_out = am + kSlotAcc9; g.amax_out = am + kSlotFeat; }
   if ((e = launch_linear_tc(g, s)) != cudaSuccess) return e;
-  g = linear_args(a.dfeat, 256, 256, wio + fp32_layer_offset(8), 256, 256, P, a.dpre + 7 * PL, 256);
+  g = linear_args(a.dfeat, 256, 256, wio.at(fp32_layer_offset(8)), 256, 256, P, a.dpre + 7 * PL, 256, half);
   g.rank1_row = a.dsig; g.rank1_col = small + kOffWSigma;
   g.mask = a.h + 7 * PL; g.ld_mask = 256;
+  if (half) { g.scale_in = am + kSlotAcc9; g.scale_out = am + dpre_slot(7); g.amax_out = am + dpre_slot(6); }
   if ((e = launch_linear_tc(g, s)) != cudaSuccess) return e;
   for (int l = 7; l >= 1; --l) {
-    g = linear_args(a.dpre + l * PL, 256, 256, wio + fp32_layer_offset(l) + (l == 5 ? 64 * 256 : 0), 256, 256, P,
-                    a.dpre + (l - 1) * PL, 256);
+    g = linear_args(a.dpre + l * PL, 256, 256, wio.at(fp32_layer_offset(l) + (l == 5 ? 64 * 256 : 0)), 256, 256, P,
+                    a.dpre + (l - 1) * PL, 256, half);
     g.mask = a.h + (l - 1) * PL; g.ld_mask = 256;
+    if (half) { g.scale_in = am + dpre_slot(l); g.scale_out = am + dpre_slot(l - 1); g.amax_out = l >= 2 ? am + dpre_slot(l - 2) : nullptr; }
     if ((e = launch_linear_tc(g, s)) != cudaSuccess) return e;
   }
   return cudaSuccess;
@@ -262,6 +321,8 @@ int check_train_cfg(const vipnerf_cfg* cfg) {
   if (int rc = check_cfg(cfg)) return rc;
   if (cfg->precision != VIPNERF_PRECISION_FP32)
     return fail(VIPNERF_EUNSUPPORTED, "the training path computes in fp32 (cfg.precision=%d)", cfg->precision);
+  if ((cfg->flags & VIPNERF_FLAG_TRAIN_TF32) && (cfg->flags & VIPNERF_FLAG_TRAIN_F16))
+    return fail(VIPNERF_EINVAL, "VIPNERF_FLAG_TRAIN_TF32 and VIPNERF_FLAG_TRAIN_F16 are exclusive");
   return VIPNERF_OK;
 }
 
@@ -345,7 +406,7 @@ int vipnerf_debug_set_profile_buffer(void* dev_u64x64) {
 size_t vipnerf_packed_weight_bytes(const vipnerf_cfg* cfg) {
   if (check_cfg(cfg) != VIPNERF_OK) return 0;
   switch (cfg->precision) {
-    case VIPNERF_PRECISION_FP32: return kSmallBytes + (size_t)(kFp32BigFloats + kFp32BwdFloats) * sizeof(float);
+    case VIPNERF_PRECISION_FP32: return kFp32PackBytes;
     case VIPNERF_PRECISION_BF16:
     case VIPNERF_PRECISION_FP16: return kSmallBytes + (size_t)kTcBigBytes;
     default: return kSmallBytes + (size_t)2 * kTcBigBytes;
@@ -535,11 +596,13 @@ int vipnerf_train_forward(const vipnerf_cfg* cfg, const vipnerf_rays* rays, int6
     ms.feat = reinterpret_cast<float*>(sv + sp.feat); ms.hv = reinterpret_cast<float*>(sv + sp.hv);
     ms.pev = reinterpret_cast<float*>(sv + sp.pev);
     float* vis2 = fl.n_sec_views ? o.raw_visibility2 : nullptr;
-    if (cfg->flags & VIPNERF_FLAG_TRAIN_TF32) {
-      // the feature product of the views layer lives in the backward's (idle) scratch until the heads have consumed it
-      float* acc9 = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + carve_bwd(cfg, n_rays).dacc9);
-      e = mlp_forward_tc(rp, fl, n_rays, S, o.z_vals, pass ? packed_fine : packed_coarse, ms, acc9, o.raw_sigma, o.raw_rgb,
-                         o.raw_visibility, vis2, s);
+    if (cfg->flags & (VIPNERF_FLAG_TRAIN_TF32 | VIPNERF_FLAG_TRAIN_F16)) {
+      // the feature product of the views layer (fp32 [P][128]) lives in the backward's (idle) scratch until the heads have
+      // consumed it
+      float* acc9 = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + carve_bwd(cfg, n_rays).dpre);
+      const SavePtrs sp8{ms.noise, sv + sp.enc, sv + sp.h, sv + sp.feat, sv + sp.hv, sv + sp.pev};
+      e = mlp_forward_tc(rp, fl, n_rays, S, o.z_vals, pass ? packed_fine : packed_coarse, sp8, acc9, o.raw_sigma, o.raw_rgb,
+                         o.raw_visibility, vis2, s, train_f16(cfg));
     } else {
       e = launch_mlp_fp32(rp, fl, n_rays, S, o.z_vals, pass ? packed_fine : packed_coarse, o.raw_sigma, o.raw_rgb,
                           o.raw_visibility, vis2, s, &ms);
@@ -647,13 +710,14 @@ int vipnerf_train_backward_fused(const vipnerf_cfg* cfg, const vipnerf_rays* ray
     const int64_t P = n_rays * S;
     if (!fo.z_vals || !fo.raw_sigma || !fo.raw_rgb || !fo.raw_visibility || (cfg->n_sec_views > 0 && !fo.raw_visibility2))
       return fail(VIPNERF_EINVAL, "fwd_out must hold z_vals / raw_sigma / raw_rgb / raw_visibility (/ raw_visibility2) of both sample sets");
-    const float* enc = reinterpret_cast<const float*>(sv + sp.enc);
-    const float* h = reinterpret_cast<const float*>(sv + sp.h);
-    const float* feat = reinterpret_cast<const float*>(sv + sp.feat);
-    const float* hv = reinterpret_cast<const float*>(sv + sp.hv);
-    const float* pev = reinterpret_cast<const float*>(sv + sp.pev);
-    float* dsig = wf(B.dsig); float* dlogit = wf(B.dlogit); float* dpre = wf(B.dpre); float* dfeat = wf(B.dfeat);
-    float* dacc9 = wf(B.dacc9); float* dhv = wf(B.dhv); float* partial = wf(B.partial);
+    const bool tf32 = (cfg->flags & VIPNERF_FLAG_TRAIN_TF32) != 0, f16 = train_f16(cfg);
+    const size_t es = f16 ? 2 : 4;                       // element size of the saved activations / chain gradients
+    const uint8_t* enc = sv + sp.enc; const uint8_t* h = sv + sp.h; const uint8_t* feat = sv + sp.feat;
+    const uint8_t* hv = sv + sp.hv; const uint8_t* pev = sv + sp.pev;
+    float* dsig = wf(B.dsig); float* dlogit = wf(B.dlogit); float* partial = wf(B.partial);
+    uint8_t* dpre = ws + B.dpre; uint8_t* dfeat = ws + B.dfeat; uint8_t* dacc9 = ws + B.dacc9; uint8_t* dhv = ws + B.dhv;
+    uint32_t* amax = reinterpret_cast<uint32_t*>(ws + B.amax) + pass * kAmaxSlots;
+    auto as_f = [](const uint8_t* p) { return reinterpret_cast<const float*>(p); };
 
     // 1. volume_rendering backwards (+ the fused loss gradients) -> logit gradients per sample
     LossGrad lgp = to_loss_grad(spec, upstream_dev);
@@ -663,54 +727,56 @@ int vipnerf_train_backward_fused(const vipnerf_cfg* cfg, const vipnerf_rays* ray
                              to_grads(pass ? &grad_out->fine : &grad_out->coarse), lgp, dsig, dlogit, s);
     if (e != cudaSuccess) return fail_cuda(e, "composite_bwd");
     // 2. backward-data chain through the MLP
-    MlpBwdArgs a{};
-    a.n_points = P; a.nviews = nv; a.dsig = dsig; a.dlogit = dlogit; a.h = h; a.hv = hv;
-    a.dpre = dpre; a.dfeat = dfeat; a.dacc9 = dacc9; a.dhv = dhv;
-    e = (cfg->flags & VIPNERF_FLAG_TRAIN_TF32) ? mlp_backward_tc(a, pass ? packed_fine : packed_coarse, s)
-                                               : launch_mlp_bwd_fp32(a, pass ? packed_fine : packed_coarse, s);
+    if (tf32 || f16) {
+      BwdPtrs a{};
+      a.n_points = P; a.nviews = nv; a.dsig = dsig; a.dlogit = dlogit; a.h = h; a.hv = hv;
+      a.dpre = dpre; a.dfeat = dfeat; a.dacc9 = dacc9; a.dhv = dhv; a.amax = amax;
+      e = mlp_backward_tc(a, pass ? packed_fine : packed_coarse, s, f16);
+    } else {
+      MlpBwdArgs a{};
+      a.n_points = P; a.nviews = nv; a.dsig = dsig; a.dlogit = dlogit; a.h = as_f(h); a.hv = as_f(hv);
+      a.dpre = reinterpret_cast<float*>(dpre); a.dfeat = reinterpret_cast<float*>(dfeat);
+      a.dacc9 = reinterpret_cast<float*>(dacc9); a.dhv = reinterpret_cast<float*>(dhv);
+      e = launch_mlp_bwd_fp32(a, pass ? packed_fine : packed_coarse, s);
+    }
     if (e != cudaSuccess) return fail_cuda(e, "mlp backward-data chain");
     // 3. parameter gradients: dW = dY^T X over all points, db = column sums of dY
-    const size_t PL = (size_t)P * 256;
-    const bool tf32 = (cfg->flags & VIPNERF_FLAG_TRAIN_TF32) != 0;
-    // one 256-wide product: fp32 CUDA cores, or the tensor cores (the bias gradient = column sums of dY rides along in both)
-    auto wide_gemm = [&](const float* dy, int M, const float* x, float* dw, int ldc, float* db) -> cudaError_t {
-      if (!tf32) return launch_gemm_tn(dy, M, M, x, 256, 256, P, dw, ldc, 256, db, partial, s);
-      return launch_gemm_tn_tc(dy, M, M, x, 256, 256, P, dw, ldc, 256, partial, s, db, partial + gemm_partial_floats());
+    const size_t PL = (size_t)P * 256 * es;              // bytes of one [P][256] array
+    float* colsum = partial + gemm_partial_floats();
+    // one product: fp32 CUDA cores, or the tensor cores (the bias gradient = column sums of dY rides along in both);
+    // fp16 mode: the partial sums carry the scale of dY (slot), undone by the final reduction
+    auto gemm = [&](const uint8_t* dy, int M, const uint8_t* x, int N, int64_t rows, float* dw, int ldc, int n_valid,
+                    float* db, int slot) -> cudaError_t {
+      if (!tf32 && !f16) return launch_gemm_tn(as_f(dy), M, M, as_f(x), N, N, rows, dw, ldc, n_valid, db, partial, s);
+      return launch_gemm_tn_tc(dy, M, M, x, N, N, rows, dw, ldc, n_valid, partial, s, db, colsum, f16, f16 ? amax + slot : nullptr);
     };
     for (int l = 0; l < 8 && e == cudaSuccess; ++l) {
-      const float* dy = dpre + l * PL;
+      const uint8_t* dy = dpre + l * PL;
       float* dw = pg[2 * l];
       float* db = pg[2 * l + 1];
-      // the 64 encoding columns (+ the layer's bias gradient): a narrow product - tensor cores with N = 64 in tf32 mode
-      auto enc_gemm = [&](int ldc) -> cudaError_t {
-        if (!tf32) return launch_gemm_tn(dy, 256, 256, enc, 64, 64, P, dw, ldc, kEncPts, db, partial, s);
-        return launch_gemm_tn_tc(dy, 256, 256, enc, 64, 64, P, dw, ldc, kEncPts, partial, s, db, partial + gemm_partial_floats());
-      };
-      if (l == 0) {
-        e = enc_gemm(kEncPts);
+      const int slot = dpre_slot(l);
+      if (l == 0) {          // the 64 encoding columns (+ the layer's bias gradient): a narrow product
+        e = gemm(dy, 256, enc, 64, P, dw, kEncPts, kEncPts, db, slot);
       } else if (l == 5) {   // input = cat([encoding, h4]) (:543-544)
-        e = enc_gemm(kWidth + kEncPts);
-        if (e == cudaSuccess)
-          e = wide_gemm(dy, 256, h + 4 * PL, dw + kEncPts, kWidth + kEncPts, nullptr);
+        e = gemm(dy, 256, enc, 64, P, dw, kWidth + kEncPts, kEncPts, db, slot);
+        if (e == cudaSuccess) e = gemm(dy, 256, h + 4 * PL, 256, P, dw + kEncPts, kWidth + kEncPts, 256, nullptr, slot);
       } else {
-        e = wide_gemm(dy, 256, h + (l - 1) * PL, dw, 256, db);
+        e = gemm(dy, 256, h + (l - 1) * PL, 256, P, dw, 256, 256, db, slot);
       }
     }
     if (e != cudaSuccess) return fail_cuda(e, "gemm_tn (pts_linears)");
     // feature_linear (input h7 = output of pts_linears.7)
-    if ((e = wide_gemm(dfeat, 256, h + 7 * PL, pg[20], 256, pg[21])) != cudaSuccess)
+    if ((e = gemm(dfeat, 256, h + 7 * PL, 256, P, pg[20], 256, 256, pg[21], kSlotAcc9)) != cudaSuccess)
       return fail_cuda(e, "gemm_tn (feature_linear)");
     // views_linears.0: feature columns over points, direction columns and bias over (point, view) rows
-    if ((e = wide_gemm(dacc9, 128, feat, pg[16], kWidth + kEncView, nullptr)) != cudaSuccess)
+    if ((e = gemm(dacc9, 128, feat, 256, P, pg[16], kWidth + kEncView, 256, nullptr, kSlotLogit)) != cudaSuccess)
       return fail_cuda(e, "gemm_tn (views_linears feature columns)");
-    e = tf32 ? launch_gemm_tn_tc(dhv, 128, 128, pev, 32, 32, P * nv, pg[16] + kWidth, kWidth + kEncView, kEncView, partial, s, pg[17],
-                                 partial + gemm_partial_floats())
-             : launch_gemm_tn(dhv, 128, 128, pev, 32, 32, P * nv, pg[16] + kWidth, kWidth + kEncView, kEncView, pg[17], partial, s);
-    if (e != cudaSuccess) return fail_cuda(e, "gemm_tn (views_linears direction columns)");
+    if ((e = gemm(dhv, 128, pev, f16 ? 64 : 32, P * nv, pg[16] + kWidth, kWidth + kEncView, kEncView, pg[17], kSlotLogit)) != cudaSuccess)
+      return fail_cuda(e, "gemm_tn (views_linears direction columns)");
     // views_output_linear [4][128] and pts_output_linear [1][256]
-    if ((e = launch_small_tn(dlogit, 4, hv, 128, P * nv, pg[22], pg[23], partial, s)) != cudaSuccess)
+    if ((e = launch_small_tn(dlogit, 4, hv, 128, P * nv, pg[22], pg[23], partial, s, f16)) != cudaSuccess)
       return fail_cuda(e, "small_tn (views_output_linear)");
-    if ((e = launch_small_tn(dsig, 1, h + 7 * PL, 256, P, pg[18], pg[19], partial, s)) != cudaSuccess)
+    if ((e = launch_small_tn(dsig, 1, h + 7 * PL, 256, P, pg[18], pg[19], partial, s, f16)) != cudaSuccess)
       return fail_cuda(e, "small_tn (pts_output_linear)");
   }
   return VIPNERF_OK;
@@ -736,7 +802,7 @@ int vipnerf_composite_backward(const vipnerf_cfg* cfg, const vipnerf_rays* rays,
 
 size_t vipnerf_param_gradient_gemm_workspace_bytes(void) { return (gemm_partial_floats() + kColsumPartialFloats) * sizeof(float) + 256; }
 
-int vipnerf_param_gradient_gemm(const float* dy, int32_t ld_dy, int32_t m, const float* x, int32_t ld_x, int32_t n,
+int vipnerf_param_gradient_gemm(const void* dy, int32_t ld_dy, int32_t m, const void* x, int32_t ld_x, int32_t n,
                                 int64_t n_rows, float* dw, int32_t ld_dw, int32_t n_valid, float* db, int32_t mode,
                                 void* workspace, size_t workspace_bytes, void* stream) {
   if (!dy || !x || !dw || !workspace) return fail(VIPNERF_EINVAL, "dy / x / dw / workspace is NULL");
@@ -744,18 +810,23 @@ int vipnerf_param_gradient_gemm(const float* dy, int32_t ld_dy, int32_t m, const
     return fail(VIPNERF_EUNSUPPORTED, "m=%d n=%d: m in {128, 256}, n in {32, 64, 128, 256}", m, n);
   if (n_rows < 1 || ld_dy < m || ld_x < n || n_valid < 1 || n_valid > n || ld_dw < n_valid)
     return fail(VIPNERF_EINVAL, "n_rows=%lld ld_dy=%d ld_x=%d n_valid=%d ld_dw=%d", (long long)n_rows, ld_dy, ld_x, n_valid, ld_dw);
-  if (misaligned(dy) || misaligned(x) || (ld_dy & 3) || (ld_x & 3)) return fail(VIPNERF_EINVAL, "dy / x must be 16-byte aligned with row strides that are multiples of 4 floats");
+  const int es = mode == 2 ? 2 : 4;
+  if (misaligned(dy) || misaligned(x) || ((ld_dy * es) & 15) || ((ld_x * es) & 15))
+    return fail(VIPNERF_EINVAL, "dy / x must be 16-byte aligned with row strides that are multiples of 16 bytes");
   if (workspace_bytes < vipnerf_param_gradient_gemm_workspace_bytes() || (reinterpret_cast<uintptr_t>(workspace) & 255u))
     return fail(VIPNERF_EWORKSPACE, "workspace %zu bytes (need %zu, 256-byte aligned)", workspace_bytes, vipnerf_param_gradient_gemm_workspace_bytes());
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   float* partial = static_cast<float*>(workspace);
   cudaError_t e;
-  if (mode != 0 && mode != 1) return fail(VIPNERF_EINVAL, "mode=%d", mode);
+  if (mode < 0 || mode > 2) return fail(VIPNERF_EINVAL, "mode=%d", mode);
   if (mode == 1) {
-    if (n != 256 && n != 64 && n != 32) return fail(VIPNERF_EUNSUPPORTED, "the tensor-core product is built for n in {32, 64, 256} (got %d)", n);
+    if (n != 256 && n != 64 && n != 32) return fail(VIPNERF_EUNSUPPORTED, "the tf32 tensor-core product is built for n in {32, 64, 256} (got %d)", n);
     e = launch_gemm_tn_tc(dy, ld_dy, m, x, ld_x, n, n_rows, dw, ld_dw, n_valid, partial, s, db, partial + gemm_partial_floats());
+  } else if (mode == 2) {
+    if (n != 256 && n != 64) return fail(VIPNERF_EUNSUPPORTED, "the fp16 tensor-core product is built for n in {64, 256} (got %d)", n);
+    e = launch_gemm_tn_tc(dy, ld_dy, m, x, ld_x, n, n_rows, dw, ld_dw, n_valid, partial, s, db, partial + gemm_partial_floats(), true);
   } else {
-    e = launch_gemm_tn(dy, ld_dy, m, x, ld_x, n, n_rows, dw, ld_dw, n_valid, db, partial, s);
+    e = launch_gemm_tn(static_cast<const float*>(dy), ld_dy, m, static_cast<const float*>(x), ld_x, n, n_rows, dw, ld_dw, n_valid, db, partial, s);
   }
   if (e != cudaSuccess) return fail_cuda(e, "param_gradient_gemm");
   return VIPNERF_OK;

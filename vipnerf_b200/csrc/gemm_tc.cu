@@ -23,6 +23,7 @@
 // VIPNERF_FLAG_TRAIN_TF32); the default training path stays fp32 FFMA.  The second kernel of this file, k_linear_tf32
 // (below), runs the forward and backward-data chains of that mode.
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include <cstdio>
@@ -32,9 +33,15 @@
 namespace vipnerf {
 namespace {
 
-constexpr int kTcStages = 3;
 constexpr int kTcRows = 32;                        // points per ring stage
-constexpr int kBoxBytes = kTcRows * 128;           // one [32 points][32 fp32] box
+constexpr int kBoxBytes = kTcRows * 128;           // one [32 points][128 bytes = 32 fp32 / 64 fp16] box
+// Operand geometry of the two arithmetic modes.  The BYTE geometry is the same (128-byte box rows, 4 KiB boxes); fp16
+// operands pack twice the columns into a box and twice the points into an MMA (K = 16), so every stream is half as long.
+template <bool kHalf> struct TcGeom {
+  static constexpr int kStages = kHalf ? 6 : 3;          // ring stages of k_gemm_tn (192 KiB in flight either way)
+  static constexpr int kColsPerBox = kHalf ? 64 : 32;
+  static constexpr int kKPerMma = kHalf ? 16 : 8;        // reduction elements per MMA (32 bytes of a K-major row)
+};
 constexpr int kTcThreads = 192;
 constexpr long long kTcTimeoutCycles = 4000000000ll;
 
@@ -79,6 +86,17 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+template <bool kHalf>
+__device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  if constexpr (kHalf) umma_f16(d_tmem, a_desc, b_desc, idesc, accumulate);
+  else umma_tf32(d_tmem, a_desc, b_desc, idesc, accumulate);
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -94,44 +112,53 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "memory");
 }
 
-// MN-major shared-memory matrix descriptor for 32-bit operands (cute::UMMA::SmemDescriptor).  tf32 operands whose
-// reduction index is the outer one can only be read in the SWIZZLE_128B_BASE32B layout (layout type 1): atoms of
-// [4 k] x [32 fp32 = 128 B] whose 32-byte chunks are XOR-ed with (k % 4) - what the TMA writes in the
-// CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B mode.  An MMA of K = 8 reads two atoms along K (512 B apart = the stride-dimension
-// byte offset); consecutive atoms along M / N are one TMA box (4 KiB) apart = the leading-dimension byte offset.
-// start >> 4 in [0,14), LBO >> 4 in [16,30), SBO >> 4 in [32,46), version 1 in [46,48), layout type in [61,64).
+// MN-major shared-memory matrix descriptors (cute::UMMA::SmemDescriptor): start >> 4 in [0,14), LBO >> 4 in [16,30),
+// SBO >> 4 in [32,46), version 1 in [46,48), layout type in [61,64).  Both operands of dW = dY^T X have the reduction
+// index (the point) as their OUTER index, so the 128-byte box rows run along M / N:
+//  * 32-bit operands (tf32) can only be read in the SWIZZLE_128B_BASE32B layout (layout type 1): atoms of [4 k] x
+//    [32 fp32 = 128 B] whose 32-byte chunks are XOR-ed with (k % 4) - what the TMA writes in the
+//    CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B mode; an MMA of K = 8 reads two atoms along K (SBO = 512 B).
+//  * 16-bit operands (fp16) use the plain SWIZZLE_128B layout (layout type 2): atoms of [8 k] x [64 fp16 = 128 B] with the
+//    16-byte chunks XOR-ed with (k % 8) (CU_TENSOR_MAP_SWIZZLE_128B); an MMA of K = 16 reads two atoms along K
+//    (SBO = 1 KiB).
+// Consecutive atoms along M / N are one TMA box (4 KiB) apart = the leading-dimension byte offset.
+template <bool kHalf>
 __device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr) {
-  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(kBoxBytes >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) |
-         (1ull << 46) | (1ull << 61);
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(kBoxBytes >> 4) << 16) |
+         ((uint64_t)((kHalf ? 1024 : 512) >> 4) << 32) | (1ull << 46) | ((kHalf ? 2ull : 1ull) << 61);
 }
-// Instruction descriptor: D = F32 (c_format 1 at [4,6)), A = B = TF32 (format 2 at [7,10) / [10,13)), both operands
-// MN-major (a_major bit 15, b_major bit 16), N >> 3 at [17,23), M >> 4 at [24,29).
-constexpr uint32_t instr_desc_tf32_mn(uint32_t n, uint32_t m) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((n >> 3) << 17) | ((m >> 4) << 24);
+// Instruction descriptor: D = F32 (c_format 1 at [4,6)), A / B format at [7,10) / [10,13) (TF32 = 2 for kind::tf32,
+// F16 = 0 for kind::f16), both operands MN-major (a_major bit 15, b_major bit 16), N >> 3 at [17,23), M >> 4 at [24,29).
+template <bool kHalf>
+constexpr uint32_t instr_desc_mn(uint32_t n, uint32_t m) {
+  return (1u << 4) | ((kHalf ? 0u : 2u) << 7) | ((kHalf ? 0u : 2u) << 10) | (1u << 15) | (1u << 16) | ((n >> 3) << 17) | ((m >> 4) << 24);
 }
 
 struct GemmTcParams {
   CUtensorMap map_a, map_b;
   int M;                    // 128 or 256
-  int N;                    // 32, 64 or 256 (columns of B)
+  int N;                    // tf32: 32, 64 or 256; fp16: 64 or 256 (columns of B)
   int64_t n_rows, rows_per_split;
   float* partial;           // [gridDim.x][M][N]
   float* colsum_partial;    // [gridDim.x][M] column sums of A over the CTA's point range (bias gradient), or null
 };
 
-__global__ void __launch_bounds__(kTcThreads, 1) k_gemm_tn_tf32(const __grid_constant__ GemmTcParams p) {
+template <bool kHalf>
+__global__ void __launch_bounds__(kTcThreads, 1) k_gemm_tn_tc(const __grid_constant__ GemmTcParams p) {
+  using G = TcGeom<kHalf>;
+  constexpr int kStages = G::kStages;
   extern __shared__ __align__(1024) uint8_t smem[];   // ring stages, then the mbarriers and the TMEM base slot
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int halves = p.M / 128;
-  const int a_boxes = p.M / 32;
-  const int b_boxes = p.N / 32;
+  const int a_boxes = p.M / G::kColsPerBox;
+  const int b_boxes = p.N / G::kColsPerBox;
   const uint32_t stage_bytes = (uint32_t)(a_boxes + b_boxes) * kBoxBytes;
-  uint8_t* tail = smem + kTcStages * stage_bytes;
-  uint32_t* tmem_ptr_slot = reinterpret_cast<uint32_t*>(tail + 8 * (2 * kTcStages + 1));
+  uint8_t* tail = smem + kStages * stage_bytes;
+  uint32_t* tmem_ptr_slot = reinterpret_cast<uint32_t*>(tail + 8 * (2 * kStages + 1));
   const uint32_t bar0 = smem_u32(tail);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
-  auto empty_bar = [&](int s) { return bar0 + 8u * (kTcStages + s); };
-  const uint32_t done_bar = bar0 + 8u * (2 * kTcStages);
+  auto empty_bar = [&](int s) { return bar0 + 8u * (kStages + s); };
+  const uint32_t done_bar = bar0 + 8u * (2 * kStages);
 
   const int64_t r_begin = (int64_t)blockIdx.x * p.rows_per_split;
   const int64_t r_end = min(p.n_rows, r_begin + p.rows_per_split);
@@ -141,7 +168,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_gemm_tn_tf32(const __grid_con
     if ((smem_u32(smem) & 1023u) != 0) { printf("vipnerf gemm_tc: shared memory base not 1 KiB aligned\n"); __trap(); }
     // a stage is free when its MMAs have retired (one tcgen05.commit arrival) and, with column sums, when the four
     // epilogue warps have read its A boxes (one arrival each)
-    for (int s = 0; s < kTcStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), p.colsum_partial ? 5 : 1); }
+    for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), p.colsum_partial ? 5 : 1); }
     mbar_init(done_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -157,30 +184,31 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_gemm_tn_tf32(const __grid_con
   if (warp == 0) {
     if (lane == 0) {
       for (int s = 0; s < n_steps; ++s) {
-        const int st = s % kTcStages;
-        if (s >= kTcStages) mbar_wait(empty_bar(st), ((s / kTcStages) - 1) & 1);
+        const int st = s % kStages;
+        if (s >= kStages) mbar_wait(empty_bar(st), ((s / kStages) - 1) & 1);
         mbar_expect_tx(full_bar(st), stage_bytes);
         const uint32_t dst = smem_u32(smem) + (uint32_t)st * stage_bytes;
         const int row = (int)(r_begin + (int64_t)s * kTcRows);   // rows past the end of the arrays are zero-filled by the TMA
-        for (int j = 0; j < a_boxes; ++j) tma_load_2d(dst + j * kBoxBytes, &p.map_a, j * 32, row, full_bar(st));
-        for (int j = 0; j < b_boxes; ++j) tma_load_2d(dst + (a_boxes + j) * kBoxBytes, &p.map_b, j * 32, row, full_bar(st));
+        for (int j = 0; j < a_boxes; ++j) tma_load_2d(dst + j * kBoxBytes, &p.map_a, j * G::kColsPerBox, row, full_bar(st));
+        for (int j = 0; j < b_boxes; ++j) tma_load_2d(dst + (a_boxes + j) * kBoxBytes, &p.map_b, j * G::kColsPerBox, row, full_bar(st));
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = instr_desc_tf32_mn((uint32_t)p.N, 128);
+      const uint32_t idesc = instr_desc_mn<kHalf>((uint32_t)p.N, 128);
+      constexpr int kMmaBytes = G::kKPerMma * 128;            // K points of every box = K 128-byte rows
       for (int s = 0; s < n_steps; ++s) {
-        const int st = s % kTcStages;
-        mbar_wait(full_bar(st), (s / kTcStages) & 1);
+        const int st = s % kStages;
+        mbar_wait(full_bar(st), (s / kStages) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t a0 = smem_u32(smem) + (uint32_t)st * stage_bytes;
         const uint32_t b0 = a0 + (uint32_t)a_boxes * kBoxBytes;
 #pragma unroll
-        for (int k = 0; k < kTcRows / 8; ++k) {               // K = 8 points per MMA = one 1 KiB atom row of every box
-          const uint64_t b_desc = make_desc_mn(b0 + k * 1024);
+        for (int k = 0; k < kTcRows / G::kKPerMma; ++k) {     // one MMA per K points and 128-row half of the output
+          const uint64_t b_desc = make_desc_mn<kHalf>(b0 + k * kMmaBytes);
           for (int h = 0; h < halves; ++h) {
-            const uint64_t a_desc = make_desc_mn(a0 + h * 4 * kBoxBytes + k * 1024);
-            umma_tf32(tmem_base + h * 256, a_desc, b_desc, idesc, (s > 0 || k > 0) ? 1u : 0u);
+            const uint64_t a_desc = make_desc_mn<kHalf>(a0 + h * (128 / G::kColsPerBox) * kBoxBytes + k * kMmaBytes);
+            umma<kHalf>(tmem_base + h * 256, a_desc, b_desc, idesc, (s > 0 || k > 0) ? 1u : 0u);
           }
         }
         umma_commit(empty_bar(st));     // frees the stage when its MMAs have retired
@@ -194,28 +222,50 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_gemm_tn_tf32(const __grid_con
     if (p.colsum_partial != nullptr) {
       // While the main loop runs these 128 threads are idle: they add up the columns of the A boxes of every stage
       // straight from shared memory (db = sum_p dY[p][m], the bias gradient) - the separate column-sum pass over the
-      // same array (k_colsum, 1 KiB per point and layer from HBM once more) is gone.  Thread t owns columns t and
-      // t + 128; box layout = SWIZZLE_128B_ATOM_32B: point k at k * 128 B, 32-byte chunk (c / 8) ^ (k % 4).
+      // same array (k_colsum, 1 KiB per point and layer from HBM once more) is gone.
       const int t = (warp - 2) * 32 + lane;
       float acc0 = 0.f, acc1 = 0.f;
       for (int s = 0; s < n_steps; ++s) {
-        const int st = s % kTcStages;
-        mbar_wait(full_bar(st), (s / kTcStages) & 1);
+        const int st = s % kStages;
+        mbar_wait(full_bar(st), (s / kStages) & 1);
         const uint8_t* a0 = smem + (size_t)st * stage_bytes;
-        for (int h = 0; h < halves; ++h) {
-          const int m = t + h * 128, c = m & 31;
-          const uint8_t* box = a0 + (size_t)(m >> 5) * kBoxBytes + (c & 7) * 4;
-          float a = 0.f;
+        if constexpr (kHalf) {
+          // thread t owns columns 2t, 2t + 1 (one half2); box layout = SWIZZLE_128B: point k at k * 128 B, 16-byte chunk
+          // (c / 8) ^ (k % 8).  M = 128: threads 0..63 only.
+          if (2 * t < p.M) {
+            const int m = 2 * t, c = m & 63;
+            const uint8_t* box = a0 + (size_t)(m >> 6) * kBoxBytes + (c & 7) * 2;
 #pragma unroll
-          for (int k = 0; k < kTcRows; ++k)
-            a += *reinterpret_cast<const float*>(box + k * 128 + ((((c >> 3) ^ (k & 3))) << 5));
-          if (h == 0) acc0 += a; else acc1 += a;
+            for (int k = 0; k < kTcRows; ++k) {
+              const float2 v = __half22float2(*reinterpret_cast<const __half2*>(box + k * 128 + (((c >> 3) ^ (k & 7)) << 4)));
+              acc0 += v.x; acc1 += v.y;
+            }
+          }
+        } else {
+          // thread t owns columns t and t + 128; box layout = SWIZZLE_128B_ATOM_32B: point k at k * 128 B, 32-byte chunk
+          // (c / 8) ^ (k % 4).
+          for (int h = 0; h < halves; ++h) {
+            const int m = t + h * 128, c = m & 31;
+            const uint8_t* box = a0 + (size_t)(m >> 5) * kBoxBytes + (c & 7) * 4;
+            float a = 0.f;
+#pragma unroll
+            for (int k = 0; k < kTcRows; ++k)
+              a += *reinterpret_cast<const float*>(box + k * 128 + ((((c >> 3) ^ (k & 3))) << 5));
+            if (h == 0) acc0 += a; else acc1 += a;
+          }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive_cta(empty_bar(st));
       }
-      p.colsum_partial[(size_t)blockIdx.x * p.M + t] = acc0;
-      if (halves == 2) p.colsum_partial[(size_t)blockIdx.x * p.M + t + 128] = acc1;
+      if constexpr (kHalf) {
+        if (2 * t < p.M) {
+          p.colsum_partial[(size_t)blockIdx.x * p.M + 2 * t] = acc0;
+          p.colsum_partial[(size_t)blockIdx.x * p.M + 2 * t + 1] = acc1;
+        }
+      } else {
+        p.colsum_partial[(size_t)blockIdx.x * p.M + t] = acc0;
+        if (halves == 2) p.colsum_partial[(size_t)blockIdx.x * p.M + t + 128] = acc1;
+      }
     }
     if (n_steps > 0) {
       mbar_wait(done_bar, 0);
@@ -223,7 +273,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_gemm_tn_tf32(const __grid_con
     }
     for (int h = 0; h < halves; ++h) {
       const int m = h * 128 + quarter * 32 + lane;
-      for (int c = 0; c < b_boxes; ++c) {
+      for (int c = 0; c < p.N / 32; ++c) {
         uint32_t v[32];
         if (n_steps > 0) {
           tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + h * 256 + c * 32, v);
@@ -263,72 +313,85 @@ EncodeTiledFn get_encode_tiled() {
   return fn;
 }
 
-// [n_rows][ld] fp32 row-major, first `cols` columns used; box = 32 columns x 32 rows, 128-byte swizzle with 32-byte atoms, tf32 rounding
-cudaError_t encode_rows_map(CUtensorMap* map, const float* base, int ld, int cols, int64_t n_rows) {
+// [n_rows][ld] row-major (fp32 or fp16), first `cols` columns used; box = 128 bytes of columns x 32 rows.
+// fp32: 128-byte swizzle with 32-byte atoms, tf32 rounding by the copy; fp16: plain 128-byte swizzle.
+cudaError_t encode_rows_map(CUtensorMap* map, const void* base, int ld, int cols, int64_t n_rows, bool half) {
   EncodeTiledFn encode = get_encode_tiled();
   if (encode == nullptr) return cudaErrorNotSupported;
   const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)n_rows};
-  const cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
-  const cuuint32_t box[2] = {32, (cuuint32_t)kTcRows};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld * (half ? 2 : 4)};
+  const cuuint32_t box[2] = {half ? 64u : 32u, (cuuint32_t)kTcRows};
   const cuuint32_t elem_strides[2] = {1, 1};
-  const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 2,
-                            const_cast<float*>(base), dims, strides, box, elem_strides, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                            CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  const CUresult r = encode(map, half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 2,
+                            const_cast<void*>(base), dims, strides, box, elem_strides, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            half ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // One linear layer of the training chains on the tensor cores:  Y[p][n] = epilogue( sum_k X[p][k] * W[n][k] ).
-// Both operands are K-major (k contiguous): X = a point-major fp32 activation / gradient array, W = an [N][K] fp32
-// weight matrix (nn.Linear's own orientation for the forward, the transposed image for the backward-data chain).
-// The TMA engine loads [128 points x 32 k] and [N x 32 k] boxes (plain 128-byte swizzle, tf32 rounding) into a 2-stage
-// ring, one thread issues four K=8 MMAs per box pair (M=128 points, N columns, accumulators in N TMEM columns), and
+// Both operands are K-major (k contiguous): X = a point-major activation / gradient array, W = an [N][K] weight matrix
+// (nn.Linear's own orientation for the forward, the transposed image for the backward-data chain).  Two arithmetic
+// modes with the same byte geometry (TcGeom): fp32 arrays read as tf32 (kind::tf32, 32 k per 128-byte box row) or fp16
+// arrays (kind::f16, 64 k per row - half the bytes per element of every stream).
+// The TMA engine loads [128 points x 128 B] and [N x 128 B] boxes (plain 128-byte swizzle) into a 3-stage
+// ring, one thread issues four MMAs per box pair (M=128 points, N columns, accumulators in N TMEM columns), and
 // four epilogue warps drain TMEM row by row: + bias, + a rank-1 term (the density head's contribution to dL/dh8),
-// ReLU, ReLU-mask from a saved activation; outputs and masks move as [32 x 32] boxes through shared memory and the TMA
-// engine (bulk tensor stores / loads).  Up to two (X, W) pairs accumulate into the same tile
-// (the skip layer's cat([encoding, h4]) input).  Persistent, one CTA per SM: a 3-stage ring (144 KiB) keeps loads in
+// ReLU, ReLU-mask from a saved activation; outputs and masks move as [32 rows x 128 B] boxes through shared memory and
+// the TMA engine (bulk tensor stores / loads).  Up to two (X, W) pairs accumulate into the same tile
+// (the skip layer's cat([encoding, h4]) input).  Persistent, one CTA per SM: the ring (144 KiB) keeps loads in
 // flight across tile boundaries and the two 256-column TMEM accumulators alternate, so the epilogue of one 128-point
 // tile overlaps the loads and MMAs of the next.
-// Roofline: HBM - K*4 bytes read and N*4 written (+ N*4 for a mask) per point; the weights come from L2.
+// fp16 gradient arrays carry a power-of-two scale (grad_scale_from_amax, kernels.h): the epilogue re-centres its output
+// on the measured maximum of its INPUT array and records the maximum of what it writes for the next layer.
+// Roofline: HBM - K elements read and N written (+ N for a mask) per point; the weights come from L2.
 constexpr int kLinStages = 3;
 constexpr int kLinRows = 128;
 constexpr int kLinStageBytes = 4 * 16384;   // epilogue staging: per epilogue warp 2 output boxes + 2 mask boxes of 4 KiB
 
 struct LinearTcParams {
   CUtensorMap map_a[2], map_b[2];
-  CUtensorMap map_out, map_mask;   // [32 columns x 32 rows] boxes of the output / the mask array (plain fp32)
+  CUtensorMap map_out, map_mask;   // [128 B of columns x 32 rows] boxes of the output / the mask array
   int chunks[2];
   int N;
   int64_t n_rows;
   const float* bias;
   const float* rank1_row;
   const float* rank1_col;
-  const float* mask;
-  int ld_mask;
+  const void* mask;
   int relu;
-  float* out;
-  int ld_out;
   const float* dot_vec;
   float* dot_out;
+  const uint32_t* scale_in;
+  const uint32_t* scale_out;
+  uint32_t* amax_out;
 };
 
 // K-major SWIZZLE_128B descriptor: 128-byte rows, 8-row atoms 1 KiB apart (SBO), LBO unused (1), layout type 2
 __device__ __forceinline__ uint64_t make_desc_k(uint32_t smem_addr) {
   return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
-constexpr uint32_t instr_desc_tf32_k(uint32_t n, uint32_t m) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
+template <bool kHalf>
+constexpr uint32_t instr_desc_k(uint32_t n, uint32_t m) {
+  return (1u << 4) | ((kHalf ? 0u : 2u) << 7) | ((kHalf ? 0u : 2u) << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
 }
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// two fp32 -> one packed fp16 pair (lo = a, hi = b), round to nearest, saturating at +-65504 instead of overflowing
+__device__ __forceinline__ uint32_t pack_half2_sat(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
 
 // kDot: the epilogue also reduces every output row against p.dot_vec (a separate instantiation: the plain layers must not
-// pay registers or predicated loads for it)
-template <bool kDot>
-__global__ void __launch_bounds__(kTcThreads, 1) k_linear_tf32(const __grid_constant__ LinearTcParams p) {
+// pay registers or predicated loads for it).  kHalf: fp16 operands (and masks); kOutHalf: fp16 output.
+template <bool kDot, bool kHalf, bool kOutHalf>
+__global__ void __launch_bounds__(kTcThreads, 1) k_linear_tc(const __grid_constant__ LinearTcParams p) {
+  using G = TcGeom<kHalf>;
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t a_bytes = kLinRows * 128, b_bytes = (uint32_t)p.N * 128;
@@ -374,7 +437,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_linear_tf32(const __grid_cons
           mbar_expect_tx(full_bar(st), stage_bytes);
           const uint32_t dst = smem_u32(smem) + (uint32_t)st * stage_bytes;
           const int pair = c < p.chunks[0] ? 0 : 1;
-          const int kc = (pair ? c - p.chunks[0] : c) * 32;
+          const int kc = (pair ? c - p.chunks[0] : c) * G::kColsPerBox;
           tma_load_2d(dst, &p.map_a[pair], kc, row0, full_bar(st));           // rows past the end are zero-filled
           tma_load_2d(dst + a_bytes, &p.map_b[pair], kc, 0, full_bar(st));
         }
@@ -382,7 +445,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_linear_tf32(const __grid_cons
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = instr_desc_tf32_k((uint32_t)p.N, 128);
+      const uint32_t idesc = instr_desc_k<kHalf>((uint32_t)p.N, 128);
       int g = 0, i = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++i) {
         const int buf = i & 1;
@@ -397,8 +460,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_linear_tf32(const __grid_cons
           const uint32_t a0 = smem_u32(smem) + (uint32_t)st * stage_bytes;
           const uint32_t b0 = a0 + a_bytes;
 #pragma unroll
-          for (int k = 0; k < 4; ++k)   // K = 8 fp32 = 32 bytes along the 128-byte swizzled rows
-            umma_tf32(tmem_base + buf * 256, make_desc_k(a0 + k * 32), make_desc_k(b0 + k * 32), idesc, (c > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < 4; ++k)   // one MMA per 32 bytes (8 fp32 / 16 fp16) along the 128-byte swizzled rows
+            umma<kHalf>(tmem_base + buf * 256, make_desc_k(a0 + k * 32), make_desc_k(b0 + k * 32), idesc, (c > 0 || k > 0) ? 1u : 0u);
           umma_commit(empty_bar(st));
         }
         umma_commit(acc_full(buf));
@@ -408,6 +471,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_linear_tf32(const __grid_cons
     const int quarter = warp & 3;
     int i = 0;
     uint32_t mask_n = 0;    // mask boxes consumed so far by this warp (buffer = mask_n & 1, phase = (mask_n >> 1) & 1)
+    // fp16 gradient chain: scale of the input array, scale of the output array (both powers of two)
+    const float s_in = p.scale_in ? grad_scale_from_amax(*p.scale_in) : 1.f;
+    const float s_out = p.scale_out ? grad_scale_from_amax(*p.scale_out) : 1.f;
+    const float fac = s_out / s_in;
+    float amax = 0.f;       // of the scaled output values this lane wrote
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++i) {
       const int buf = i & 1;
       const int64_t pg = (int64_t)tile * kLinRows + quarter * 32 + lane;
@@ -416,22 +484,93 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_linear_tf32(const __grid_cons
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       // Epilogue through shared memory and the TMA engine.  A lane owns one accumulator row, so direct global accesses
       // touch 32 different 128-byte lines per instruction (the r01 kernel ran at 0.45 of the HBM roofline because of it).
-      // Instead every warp stages its [32 rows x 32 columns] chunk in a swizzled 4 KiB box and ONE bulk tensor store
+      // Instead every warp stages its [32 rows x 128 B] chunk in a swizzled 4 KiB box and ONE bulk tensor store
       // writes it (full lines, asynchronous, rows past the end clipped by the tensor map); the ReLU mask of the
       // backward chain arrives the same way (bulk tensor load of the saved activation's box, one chunk ahead).
-      {
-        uint8_t* wstage = stage_base + (warp - 2) * 16384;             // [2] output boxes, then [2] mask boxes
-        const uint32_t out_s = smem_u32(wstage), msk_s = out_s + 8192;
-        const uint32_t mfull0 = mask_full(warp - 2, 0);
-        const int row0 = tile * kLinRows + quarter * 32;
-        const int n_ch = p.N / 32;
-        const bool has_mask = p.mask != nullptr;
-        if (has_mask && lane == 0) {
-          mbar_expect_tx(mfull0 + 8u * (mask_n & 1), 4096);
-          tma_load_2d(msk_s + 4096u * (mask_n & 1), &p.map_mask, 0, row0, mfull0 + 8u * (mask_n & 1));
+      uint8_t* wstage = stage_base + (warp - 2) * 16384;             // [2] output boxes, then [2] mask boxes
+      const uint32_t out_s = smem_u32(wstage), msk_s = out_s + 8192;
+      const uint32_t mfull0 = mask_full(warp - 2, 0);
+      const int row0 = tile * kLinRows + quarter * 32;
+      const bool has_mask = p.mask != nullptr;
+      if (has_mask && lane == 0) {
+        mbar_expect_tx(mfull0 + 8u * (mask_n & 1), 4096);
+        tma_load_2d(msk_s + 4096u * (mask_n & 1), &p.map_mask, 0, row0, mfull0 + 8u * (mask_n & 1));
+      }
+      float dot = 0.f;
+      if constexpr (kOutHalf) {
+        const int n_sc = p.N / 64;                                    // one box = 64 fp16 columns = two TMEM loads
+        const float r1 = (p.rank1_row != nullptr && valid) ? p.rank1_row[pg] * s_out : 0.f;
+        for (int sc = 0; sc < n_sc; ++sc, ++mask_n) {
+          uint32_t va[32], vb[32];
+          tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * 256 + sc * 64, va);
+          tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * 256 + sc * 64 + 32, vb);
+          if (has_mask && lane == 0 && sc + 1 < n_sc) {                 // next box of the mask (its buffer was read at sc - 1)
+            mbar_expect_tx(mfull0 + 8u * ((mask_n + 1) & 1), 4096);
+            tma_load_2d(msk_s + 4096u * ((mask_n + 1) & 1), &p.map_mask, (sc + 1) * 64, row0, mfull0 + 8u * ((mask_n + 1) & 1));
+          }
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the store issued two boxes ago has read its box
+          __syncwarp();
+          if (has_mask) mbar_wait(mfull0 + 8u * (mask_n & 1), (mask_n >> 1) & 1);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          const uint32_t orow = out_s + 4096u * (sc & 1) + lane * 128, mrow = msk_s + 4096u * (mask_n & 1) + lane * 128;
+          auto eight = [&](const uint32_t (&v)[32], int qq, int q) {   // columns sc * 64 + q * 8 .. + 7 = v[8 qq ..]
+            float o[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = __uint_as_float(v[8 * qq + j]);
+            const int col = sc * 64 + q * 8;
+            if (p.bias != nullptr) {
+              const float4 b0 = *reinterpret_cast<const float4*>(p.bias + col), b1 = *reinterpret_cast<const float4*>(p.bias + col + 4);
+              o[0] += b0.x; o[1] += b0.y; o[2] += b0.z; o[3] += b0.w; o[4] += b1.x; o[5] += b1.y; o[6] += b1.z; o[7] += b1.w;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] *= fac;                 // exact: a power of two (1 in the forward chain)
+            if (p.rank1_row != nullptr) {
+              const float4 u0 = *reinterpret_cast<const float4*>(p.rank1_col + col), u1 = *reinterpret_cast<const float4*>(p.rank1_col + col + 4);
+              o[0] = fmaf(r1, u0.x, o[0]); o[1] = fmaf(r1, u0.y, o[1]); o[2] = fmaf(r1, u0.z, o[2]); o[3] = fmaf(r1, u0.w, o[3]);
+              o[4] = fmaf(r1, u1.x, o[4]); o[5] = fmaf(r1, u1.y, o[5]); o[6] = fmaf(r1, u1.z, o[6]); o[7] = fmaf(r1, u1.w, o[7]);
+            }
+            if (p.relu) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) o[j] = fmaxf(o[j], 0.f);
+            }
+            if (kDot) {
+              const float4 d0 = *reinterpret_cast<const float4*>(p.dot_vec + col), d1 = *reinterpret_cast<const float4*>(p.dot_vec + col + 4);
+              dot = fmaf(o[0], d0.x, dot); dot = fmaf(o[1], d0.y, dot); dot = fmaf(o[2], d0.z, dot); dot = fmaf(o[3], d0.w, dot);
+              dot = fmaf(o[4], d1.x, dot); dot = fmaf(o[5], d1.y, dot); dot = fmaf(o[6], d1.z, dot); dot = fmaf(o[7], d1.w, dot);
+            }
+            const uint32_t sw = (uint32_t)((q ^ (lane & 7)) << 4);    // 128-byte swizzle: 16-byte chunk index ^ (row % 8)
+            if (has_mask) {   // saved post-ReLU activations (fp16): the unit was active iff its value is > 0
+              uint32_t m0, m1, m2, m3;
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(m0), "=r"(m1), "=r"(m2), "=r"(m3) : "r"(mrow + sw));
+              const uint32_t mm[4] = {m0, m1, m2, m3};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                if ((int16_t)(mm[j] & 0xffffu) <= 0) o[2 * j] = 0.f;
+                if ((int16_t)(mm[j] >> 16) <= 0) o[2 * j + 1] = 0.f;
+              }
+            }
+            if (p.amax_out != nullptr) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) amax = fmaxf(amax, fabsf(o[j]));
+            }
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(orow + sw), "r"(pack_half2_sat(o[0], o[1])),
+                         "r"(pack_half2_sat(o[2], o[3])), "r"(pack_half2_sat(o[4], o[5])), "r"(pack_half2_sat(o[6], o[7])) : "memory");
+          };
+#pragma unroll
+          for (int q = 0; q < 4; ++q) eight(va, q, q);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) eight(vb, q, q + 4);
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) {
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+                         ::"l"(&p.map_out), "r"(sc * 64), "r"(row0), "r"(out_s + 4096u * (sc & 1)) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
         }
+      } else {
+        const int n_ch = p.N / 32;
         const float r1 = (p.rank1_row != nullptr && valid) ? p.rank1_row[pg] : 0.f;
-        float dot = 0.f;
         for (int c = 0; c < n_ch; ++c, ++mask_n) {
           uint32_t v[32];
           tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * 256 + c * 32, v);
@@ -477,12 +616,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_linear_tf32(const __grid_cons
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
         }
-        if (kDot && valid) p.dot_out[pg] = dot;
       }
+      if (kDot && valid) p.dot_out[pg] = dot;
       // this warp's TMEM reads of the accumulator are complete: hand it back to the MMA warp
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty(buf));
+    }
+    if (p.amax_out != nullptr) {   // largest |value| this warp wrote, un-scaled; float bits of non-negative values order like integers
+      const uint32_t m = __reduce_max_sync(0xffffffffu, __float_as_uint(amax / s_out));
+      if (lane == 0 && m != 0u) atomicMax(p.amax_out, m);
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // shared memory outlives the last stores
   }
@@ -494,18 +637,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_linear_tf32(const __grid_cons
   }
 }
 
-// [rows][ld] fp32 row-major, first `cols` columns; box = 32 columns x box_rows rows, plain 128-byte swizzle, tf32 rounding
-// (exact_fp32: no rounding - the epilogue's output / mask boxes)
-cudaError_t encode_kmajor_map(CUtensorMap* map, const float* base, int ld, int cols, int64_t rows, int box_rows,
-                              bool exact_fp32 = false) {
+// [rows][ld] row-major, first `cols` columns; box = 128 bytes of columns x box_rows rows, plain 128-byte swizzle.
+// kind 0: fp32 read as tf32 (rounded by the copy), 1: exact fp32 (the epilogue's output / mask boxes), 2: fp16
+cudaError_t encode_kmajor_map(CUtensorMap* map, const void* base, int ld, int cols, int64_t rows, int box_rows, int kind) {
   EncodeTiledFn encode = get_encode_tiled();
   if (encode == nullptr) return cudaErrorNotSupported;
+  const bool half = kind == 2;
   const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  const cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
-  const cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld * (half ? 2 : 4)};
+  const cuuint32_t box[2] = {half ? 64u : 32u, (cuuint32_t)box_rows};
   const cuuint32_t elem_strides[2] = {1, 1};
-  const CUresult r = encode(map, exact_fp32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 2,
-                            const_cast<float*>(base), dims, strides, box,
+  const CUtensorMapDataType dt = half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+                                      : (kind == 1 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32);
+  const CUresult r = encode(map, dt, 2, const_cast<void*>(base), dims, strides, box,
                             elem_strides, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
@@ -515,48 +659,64 @@ cudaError_t encode_kmajor_map(CUtensorMap* map, const float* base, int ld, int c
 
 cudaError_t launch_linear_tc(const LinearTcArgs& a, cudaStream_t s) {
   if (a.n_rows < 1) return cudaSuccess;
-  if ((a.N != 128 && a.N != 256) || a.k[0] < 32 || (a.k[0] & 31) || (a.k[1] & 31) || a.k[1] < 0) return cudaErrorInvalidValue;
+  const int kq = a.half_in ? 64 : 32;     // reduction elements per 128-byte box row
+  if ((a.N != 128 && a.N != 256) || a.k[0] < kq || (a.k[0] % kq) || (a.k[1] % kq) || a.k[1] < 0) return cudaErrorInvalidValue;
+  if (a.half_out && !a.half_in) return cudaErrorInvalidValue;       // fp16 outputs exist in the fp16 mode only
+  if (a.mask != nullptr && a.half_in != a.half_out) return cudaErrorInvalidValue;
+  const int es_in = a.half_in ? 2 : 4, es_out = a.half_out ? 2 : 4;
   LinearTcParams p{};
   cudaError_t e;
   for (int i = 0; i < 2; ++i) {
-    p.chunks[i] = a.k[i] / 32;
+    p.chunks[i] = a.k[i] / kq;
     if (a.k[i] == 0) continue;
-    if ((reinterpret_cast<uintptr_t>(a.x[i]) & 15u) || (reinterpret_cast<uintptr_t>(a.w[i]) & 15u) || (a.ldx[i] & 3) || (a.ldw[i] & 3))
+    if ((reinterpret_cast<uintptr_t>(a.x[i]) & 15u) || (reinterpret_cast<uintptr_t>(a.w[i]) & 15u) || ((a.ldx[i] * es_in) & 15) || ((a.ldw[i] * es_in) & 15))
       return cudaErrorInvalidValue;
-    if ((e = encode_kmajor_map(&p.map_a[i], a.x[i], a.ldx[i], a.k[i], a.n_rows, kLinRows)) != cudaSuccess) return e;
-    if ((e = encode_kmajor_map(&p.map_b[i], a.w[i], a.ldw[i], a.k[i], a.N, a.N)) != cudaSuccess) return e;
+    if ((e = encode_kmajor_map(&p.map_a[i], a.x[i], a.ldx[i], a.k[i], a.n_rows, kLinRows, a.half_in ? 2 : 0)) != cudaSuccess) return e;
+    if ((e = encode_kmajor_map(&p.map_b[i], a.w[i], a.ldw[i], a.k[i], a.N, a.N, a.half_in ? 2 : 0)) != cudaSuccess) return e;
   }
   if (a.k[1] == 0) { p.map_a[1] = p.map_a[0]; p.map_b[1] = p.map_b[0]; }
   p.N = a.N; p.n_rows = a.n_rows; p.bias = a.bias; p.rank1_row = a.rank1_row; p.rank1_col = a.rank1_col;
-  p.mask = a.mask; p.ld_mask = a.ld_mask; p.relu = a.relu ? 1 : 0; p.out = a.out; p.ld_out = a.ld_out;
+  p.mask = a.mask; p.relu = a.relu ? 1 : 0;
   p.dot_vec = a.dot_vec; p.dot_out = a.dot_vec ? a.dot_out : nullptr;
-  if ((reinterpret_cast<uintptr_t>(a.out) & 15u) || (a.ld_out & 3) || (a.mask && ((reinterpret_cast<uintptr_t>(a.mask) & 15u) || (a.ld_mask & 3))))
+  p.scale_in = a.scale_in; p.scale_out = a.scale_out; p.amax_out = a.amax_out;
+  if ((reinterpret_cast<uintptr_t>(a.out) & 15u) || ((a.ld_out * es_out) & 15) ||
+      (a.mask && ((reinterpret_cast<uintptr_t>(a.mask) & 15u) || ((a.ld_mask * es_out) & 15))))
     return cudaErrorInvalidValue;
-  if ((e = encode_kmajor_map(&p.map_out, a.out, a.ld_out, a.N, a.n_rows, 32, true)) != cudaSuccess) return e;
+  if ((e = encode_kmajor_map(&p.map_out, a.out, a.ld_out, a.N, a.n_rows, 32, a.half_out ? 2 : 1)) != cudaSuccess) return e;
   if (a.mask != nullptr) {
-    if ((e = encode_kmajor_map(&p.map_mask, a.mask, a.ld_mask, a.N, a.n_rows, 32, true)) != cudaSuccess) return e;
+    if ((e = encode_kmajor_map(&p.map_mask, a.mask, a.ld_mask, a.N, a.n_rows, 32, a.half_out ? 2 : 1)) != cudaSuccess) return e;
   } else {
     p.map_mask = p.map_out;
   }
   const size_t smem = (size_t)kLinStages * (kLinRows * 128 + a.N * 128) + kLinStageBytes + 256;
   const bool dot = a.dot_vec != nullptr && a.dot_out != nullptr;
-  if ((e = cudaFuncSetAttribute(dot ? k_linear_tf32<true> : k_linear_tf32<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
   int dev = 0, sms = 0;
   if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
   if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
   const int64_t n_tiles = (a.n_rows + kLinRows - 1) / kLinRows;
-  if (dot) k_linear_tf32<true><<<(unsigned)(n_tiles < sms ? n_tiles : sms), kTcThreads, smem, s>>>(p);
-  else k_linear_tf32<false><<<(unsigned)(n_tiles < sms ? n_tiles : sms), kTcThreads, smem, s>>>(p);
+  const unsigned grid = (unsigned)(n_tiles < sms ? n_tiles : sms);
+#define VIPNERF_LAUNCH_LINEAR(DOT, HALF, OUTHALF)                                                                         \
+  do {                                                                                                                  \
+    if ((e = cudaFuncSetAttribute(k_linear_tc<DOT, HALF, OUTHALF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e; \
+    k_linear_tc<DOT, HALF, OUTHALF><<<grid, kTcThreads, smem, s>>>(p);                                                  \
+  } while (0)
+  if (!a.half_in) { if (dot) VIPNERF_LAUNCH_LINEAR(true, false, false); else VIPNERF_LAUNCH_LINEAR(false, false, false); }
+  else if (!a.half_out) { if (dot) return cudaErrorInvalidValue; VIPNERF_LAUNCH_LINEAR(false, true, false); }
+  else if (dot) VIPNERF_LAUNCH_LINEAR(true, true, true);
+  else VIPNERF_LAUNCH_LINEAR(false, true, true);
+#undef VIPNERF_LAUNCH_LINEAR
   return cudaGetLastError();
 }
 
 size_t gemm_tn_tc_partial_floats(int sms) { return (size_t)sms * 256 * 256; }
 
-cudaError_t launch_gemm_tn_tc(const float* A, int lda, int M, const float* B, int ldb, int N, int64_t n_rows, float* dst,
+cudaError_t launch_gemm_tn_tc(const void* A, int lda, int M, const void* B, int ldb, int N, int64_t n_rows, float* dst,
                               int ldc, int n_valid, float* partial, cudaStream_t s, float* bias_dst,
-                              float* colsum_scratch) {
-  if ((M != 128 && M != 256) || (N != 32 && N != 64 && N != 256) || n_rows < 1) return cudaErrorInvalidValue;
-  if ((reinterpret_cast<uintptr_t>(A) & 15u) || (reinterpret_cast<uintptr_t>(B) & 15u) || (lda & 3) || (ldb & 3))
+                              float* colsum_scratch, bool half, const uint32_t* scale_def) {
+  if ((M != 128 && M != 256) || n_rows < 1) return cudaErrorInvalidValue;
+  if (half ? (N != 64 && N != 256) : (N != 32 && N != 64 && N != 256)) return cudaErrorInvalidValue;
+  const int es = half ? 2 : 4;
+  if ((reinterpret_cast<uintptr_t>(A) & 15u) || (reinterpret_cast<uintptr_t>(B) & 15u) || ((lda * es) & 15) || ((ldb * es) & 15))
     return cudaErrorInvalidValue;
   int dev = 0, sms = 0;
   cudaError_t e = cudaGetDevice(&dev);
@@ -571,17 +731,23 @@ cudaError_t launch_gemm_tn_tc(const float* A, int lda, int M, const float* B, in
   n_split = (n_rows + rows_per_split - 1) / rows_per_split;
 
   GemmTcParams p{};
-  if ((e = encode_rows_map(&p.map_a, A, lda, M, n_rows)) != cudaSuccess) return e;
-  if ((e = encode_rows_map(&p.map_b, B, ldb, N, n_rows)) != cudaSuccess) return e;
+  if ((e = encode_rows_map(&p.map_a, A, lda, M, n_rows, half)) != cudaSuccess) return e;
+  if ((e = encode_rows_map(&p.map_b, B, ldb, N, n_rows, half)) != cudaSuccess) return e;
   p.M = M; p.N = N; p.n_rows = n_rows; p.rows_per_split = rows_per_split; p.partial = partial;
   p.colsum_partial = (bias_dst != nullptr) ? colsum_scratch : nullptr;
   if (bias_dst != nullptr && colsum_scratch == nullptr) return cudaErrorInvalidValue;
-  const size_t smem = (size_t)kTcStages * (M / 32 + N / 32) * kBoxBytes + 128;
-  if ((e = cudaFuncSetAttribute(k_gemm_tn_tf32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-  k_gemm_tn_tf32<<<(unsigned)n_split, kTcThreads, smem, s>>>(p);
+  const int cpb = half ? 64 : 32;
+  const size_t smem = (size_t)(half ? TcGeom<true>::kStages : TcGeom<false>::kStages) * (M / cpb + N / cpb) * kBoxBytes + 128;
+  if (half) {
+    if ((e = cudaFuncSetAttribute(k_gemm_tn_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+    k_gemm_tn_tc<true><<<(unsigned)n_split, kTcThreads, smem, s>>>(p);
+  } else {
+    if ((e = cudaFuncSetAttribute(k_gemm_tn_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+    k_gemm_tn_tc<false><<<(unsigned)n_split, kTcThreads, smem, s>>>(p);
+  }
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
-  if ((e = launch_reduce_partials(partial, (int)n_split, M, N, dst, ldc, n_valid, s)) != cudaSuccess) return e;
-  if (bias_dst != nullptr) return launch_reduce_partials(colsum_scratch, (int)n_split, M, 1, bias_dst, 1, 1, s);
+  if ((e = launch_reduce_partials(partial, (int)n_split, M, N, dst, ldc, n_valid, s, scale_def)) != cudaSuccess) return e;
+  if (bias_dst != nullptr) return launch_reduce_partials(colsum_scratch, (int)n_split, M, 1, bias_dst, 1, 1, s, scale_def);
   return cudaSuccess;
 }
 

@@ -108,50 +108,82 @@ cudaError_t launch_fused_losses(const LossFwdArgs& a, const LossGrad& lg, int64_
 size_t gemm_tn_partial_floats();
 cudaError_t launch_gemm_tn(const float* A, int lda, int M, const float* B, int ldb, int N, int64_t n_rows, float* dst,
                            int ldc, int n_valid, float* bias_dst, float* partial, cudaStream_t s);
+// scale_def (fp16 training mode): amax slot that defines the power-of-two scale the partial sums carry; dst = sum / scale
 cudaError_t launch_reduce_partials(const float* partial, int n_split, int M, int N, float* dst, int ldc, int n_valid,
-                                   cudaStream_t s);
+                                   cudaStream_t s, const uint32_t* scale_def = nullptr);
 cudaError_t launch_colsum(const float* A, int lda, int M, int64_t n_rows, float* dst, float* partial, cudaStream_t s);
-// gemm_tc.cu : the same product on the tensor cores (tcgen05 kind::tf32 reading the fp32 arrays through TMA),
-// N in {32, 64, 256}, M in {128, 256}.  `partial`: gemm_tn_tc_partial_floats(#SMs) floats.
+// gemm_tc.cu : the same product on the tensor cores - tcgen05 kind::tf32 reading fp32 arrays through TMA (N in {32, 64,
+// 256}), or kind::f16 reading fp16 arrays (`half`, N in {64, 256}; lda / ldb in elements) - M in {128, 256}.
+// `partial`: gemm_tn_tc_partial_floats(#SMs) floats.  scale_def: see launch_reduce_partials.
 constexpr int kGemmTcMaxSplits = 160;   // point ranges (one CTA each) the scratch of the tensor-core product is sized for
 size_t gemm_tn_tc_partial_floats(int sms);
 // bias_dst (optional): column sums of A (db), accumulated by the kernel's epilogue warps from the A boxes in shared
 // memory while the main loop runs; colsum_scratch: kGemmTcMaxSplits * M floats.
-cudaError_t launch_gemm_tn_tc(const float* A, int lda, int M, const float* B, int ldb, int N, int64_t n_rows, float* dst,
+cudaError_t launch_gemm_tn_tc(const void* A, int lda, int M, const void* B, int ldb, int N, int64_t n_rows, float* dst,
                               int ldc, int n_valid, float* partial, cudaStream_t s, float* bias_dst = nullptr,
-                              float* colsum_scratch = nullptr);
-// train_kernels.cu : the non-product pieces of the tensor-core training path (encodings, heads forward / backward)
+                              float* colsum_scratch = nullptr, bool half = false, const uint32_t* scale_def = nullptr);
+// train_kernels.cu : the non-product pieces of the tensor-core training path (encodings, heads forward / backward).
+// `half` = the fp16 mode (VIPNERF_FLAG_TRAIN_F16): enc / pev / hv / dhv / dacc9 are fp16 arrays and a row of pev has 64
+// columns (128 bytes, 27 used) instead of 32 floats; gradients carry the power-of-two scale of their amax slot.
 cudaError_t launch_encode_points(const RayPtrs& rp, const RenderFlags& fl, int64_t n_rays, int S, const float* z,
-                                 float* enc, float* pev, cudaStream_t s);
+                                 void* enc, void* pev, cudaStream_t s, bool half = false);
 cudaError_t launch_heads_fwd(int64_t n_points, int nviews, const void* packed, const float* h7, const float* acc9,
-                             const float* pev, const float* noise, float* sigma, float* rgb, float* vis, float* vis2,
-                             float* hv, cudaStream_t s);
-cudaError_t launch_heads_bwd(int64_t n_points, int nviews, const void* packed, const float* dlogit, const float* hv,
-                             float* dhv, float* dacc9, cudaStream_t s);
-// gemm_tc.cu : one linear layer of the training chains on the tensor cores (tcgen05 kind::tf32, K-major operands):
+                             const void* pev, const float* noise, float* sigma, float* rgb, float* vis, float* vis2,
+                             void* hv, cudaStream_t s, bool half = false);
+// scale_def: amax slot defining the scale of dhv / dacc9 (fp16 mode); amax_out: records max |dacc9|
+cudaError_t launch_heads_bwd(int64_t n_points, int nviews, const void* packed, const float* dlogit, const void* hv,
+                             void* dhv, void* dacc9, cudaStream_t s, bool half = false, const uint32_t* scale_def = nullptr,
+                             uint32_t* amax_out = nullptr);
+// fp16 mode: amax[slot_logit] = max |dlogit|, amax[slot_sigma] = max |dsig| * max |w_sigma| (the rank-1 term that joins
+// the chain at pts_linears.7); both slots must have been zeroed
+cudaError_t launch_grad_amax(int64_t n_points, int nviews, const void* packed, const float* dlogit, const float* dsig,
+                             uint32_t* amax_logit, uint32_t* amax_sigma, cudaStream_t s);
+// gemm_tc.cu : one linear layer of the training chains on the tensor cores (tcgen05 kind::tf32 on fp32 arrays, or
+// kind::f16 on fp16 arrays; K-major operands):
 // out[p][n] = epilogue(sum_k x0[p][k] w0[n][k] (+ sum_k x1[p][k] w1[n][k])), epilogue = + bias[n], + rank1_row[p] *
-// rank1_col[n], ReLU, ReLU-mask (mask[p][n] > 0), each optional.  k[i] = reduction length of pair i (multiple of 32; k[1]
-// may be 0), N in {128, 256}; rows are points.
+// rank1_col[n], ReLU, ReLU-mask (mask[p][n] > 0), each optional.  k[i] = reduction length of pair i (multiple of 32, of
+// 64 for fp16 operands; k[1] may be 0), N in {128, 256}; rows are points; leading dimensions in elements.
 struct LinearTcArgs {
-  const float* x[2]; int ldx[2];
-  const float* w[2]; int ldw[2];
+  const void* x[2]; int ldx[2];
+  const void* w[2]; int ldw[2];
   int k[2];
   int N;
   int64_t n_rows;
   const float* bias;
   const float* rank1_row;
   const float* rank1_col;
-  const float* mask; int ld_mask;
+  const void* mask; int ld_mask;
   bool relu;
-  float* out; int ld_out;
+  void* out; int ld_out;
+  bool half_in;     // x, w (and mask) are fp16
+  bool half_out;    // out is fp16 (fp16 operands only)
+  // fp16 gradient chain: amax slots that define the power-of-two scale of x / of out (null = unscaled), and where to
+  // record max |out| (un-scaled, float bits; atomicMax)
+  const uint32_t* scale_in;
+  const uint32_t* scale_out;
+  uint32_t* amax_out;
   // optional rank-1 reduction of the OUTPUT rows: dot_out[p] = sum_n Y[p][n] * dot_vec[n] (the density head on h7,
   // VipNeRF01.py:546: it rides along in the epilogue that holds the row instead of re-reading 1 KiB per point)
   const float* dot_vec; float* dot_out;
 };
 cudaError_t launch_linear_tc(const LinearTcArgs& a, cudaStream_t s);
 // out[m][n] = sum_p G[p][m] * H[p][n] for M <= 4 (G: M floats per row), N <= 256; gsum_dst[m] = sum_p G[p][m].
-cudaError_t launch_small_tn(const float* G, int M, const float* H, int N, int64_t n_rows, float* dst, float* gsum_dst,
-                            float* partial, cudaStream_t s);
+// half_h: H is an fp16 array.
+cudaError_t launch_small_tn(const float* G, int M, const void* H, int N, int64_t n_rows, float* dst, float* gsum_dst,
+                            float* partial, cudaStream_t s, bool half_h = false);
+
+#ifdef __CUDACC__
+// fp16 training mode: a gradient array is stored as value * 2^k with k chosen so that `amax` (float bits of a non-negative
+// maximum measured on the device) lands in [16, 32): 11 binades of head room to fp16's 65504 (conversions saturate), and
+// everything down to 2^-28 of amax stays representable.  0 / inf / nan: unscaled.
+__device__ __forceinline__ float grad_scale_from_amax(uint32_t amax_bits) {
+  const uint32_t e = (amax_bits >> 23) & 0xffu;
+  if (amax_bits == 0u || e == 0xffu) return 1.f;
+  int k = 4 - ((int)(e == 0u ? 1u : e) - 127);
+  k = k < -120 ? -120 : (k > 120 ? 120 : k);
+  return __uint_as_float((uint32_t)(k + 127) << 23);
+}
+#endif
 
 // mlp_tc.cu : tcgen05 evaluation (precision = BF16 or BF16X3)
 cudaError_t launch_mlp_tc(int precision, const RayPtrs& rp, const RenderFlags& fl, int64_t n_rays, int S,

@@ -14,6 +14,7 @@
 // plus three small fp32 heads done on CUDA cores: sigma (pts_output_linear, :546-553), the 27
 // view-encoding columns of views_linears.0, and views_output_linear (128->4, :582-594).
 #pragma once
+#include <stddef.h>
 #include <stdint.h>
 
 namespace vipnerf {
@@ -40,7 +41,7 @@ __host__ __device__ constexpr int layer_n(int l) { return l >= 9 ? 128 : 256; }
 constexpr int kOffBias = 0;                          // [9][256]: M0..M8 biases (M8 = feature_linear.bias)
 constexpr int kOffBiasViews = kOffBias + 9 * 256;    // [128]  views_linears.0.bias
 constexpr int kOffWSigma = kOffBiasViews + 128;      // [256]  pts_output_linear.weight
-constexpr int kOffBSigma = kOffWSigma + 256;         // [4]    pts_output_linear.bias (+pad)
+constexpr int kOffBSigma = kOffWSigma + 256;         // [4]    pts_output_linear.bias, max |pts_output_linear.weight|, pad
 constexpr int kOffWViewDir = kOffBSigma + 4;         // [27][128] views_linears.0.weight[:, 256+j] transposed
 constexpr int kOffWOut = kOffWViewDir + 27 * 128;    // [128][4]  views_output_linear.weight transposed
 constexpr int kOffBOut = kOffWOut + 128 * 4;         // [4]    views_output_linear.bias
@@ -68,6 +69,11 @@ constexpr int kBwdOffEnc0 = kBwdOffTrunk + 7 * 256 * 256;         // pts_linears
 constexpr int kBwdOffEnc5 = kBwdOffEnc0 + 256 * 64;               // pts_linears.5[:, :63] padded to [256][64]
 constexpr int kFp32BwdFloats = kBwdOffEnc5 + 256 * 64;            // 589,824; the two encoding blocks serve the
                                                                   // tensor-core forward, whose B operands are [out][in]
+
+// ---- fp16 mirror (training, behind the backward region): the forward and backward regions once more as fp16, element
+// for element - the B operands of the fp16 training mode (VIPNERF_FLAG_TRAIN_F16, tcgen05 kind::f16)
+constexpr int kF16MirrorHalves = kFp32BigFloats + kFp32BwdFloats;
+constexpr size_t kFp32PackBytes = (size_t)kSmallBytes + (size_t)(kFp32BigFloats + kFp32BwdFloats) * 4 + (size_t)kF16MirrorHalves * 2;
 
 // ---- tensor-core big region: "chunk images".  One chunk = ALL output rows (n) of a layer x 32 k-columns of
 // bf16 in the canonical K-major SWIZZLE_64B shared-memory layout tcgen05.mma reads (64-byte rows, 8-row / 512-byte

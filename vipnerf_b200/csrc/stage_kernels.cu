@@ -37,7 +37,11 @@ __global__ void k_pack_small(ParamPtrs pp, float* __restrict__ small) {
   } else if (i < kOffBSigma) {
     v = pp.p[18][i - kOffWSigma];
   } else if (i < kOffWViewDir) {
-    v = (i == kOffBSigma) ? pp.p[19][0] : 0.f;
+    if (i == kOffBSigma) {
+      v = pp.p[19][0];
+    } else if (i == kOffBSigma + 1) {   // max |pts_output_linear.weight|: anchors a gradient scale of the fp16 training mode
+      for (int k = 0; k < kWidth; ++k) v = fmaxf(v, fabsf(pp.p[18][k]));
+    }
   } else if (i < kOffWOut) {
     const int j = (i - kOffWViewDir) / 128, c = (i - kOffWViewDir) % 128;
     v = pp.p[16][c * (kWidth + kEncView) + kWidth + j];
@@ -91,6 +95,15 @@ __global__ void k_pack_fp32_bwd(ParamPtrs pp, float* __restrict__ bwd) {
   bwd[i] = v;
 }
 
+// fp16 mirror of the two fp32 regions (layout.cuh): weights rounded to nearest, saturating
+__global__ void k_pack_f16_mirror(const float* __restrict__ big, __half* __restrict__ mirror) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= kF16MirrorHalves) return;
+  unsigned short r;
+  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(r) : "f"(big[i]));
+  reinterpret_cast<unsigned short*>(mirror)[i] = r;
+}
+
 template <bool kSplit3, bool kHalf = false>
 __global__ void k_pack_tc(ParamPtrs pp, uint8_t* __restrict__ big) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;  // one bf16 element of the hi image set
@@ -138,6 +151,8 @@ cudaError_t launch_pack_weights(int precision, const float* const params_dev[24]
   if (precision == VIPNERF_PRECISION_FP32) {
     k_pack_fp32<<<(kFp32BigFloats + 255) / 256, 256, 0, s>>>(pp, reinterpret_cast<float*>(big));
     k_pack_fp32_bwd<<<(kFp32BwdFloats + 255) / 256, 256, 0, s>>>(pp, reinterpret_cast<float*>(big) + kFp32BigFloats);
+    k_pack_f16_mirror<<<(kF16MirrorHalves + 255) / 256, 256, 0, s>>>(
+        reinterpret_cast<const float*>(big), reinterpret_cast<__half*>(reinterpret_cast<float*>(big) + kFp32BigFloats + kFp32BwdFloats));
   } else {
     const int n = kTcBigBytes / 2;
     if (precision == VIPNERF_PRECISION_BF16X3) k_pack_tc<true><<<(n + 255) / 256, 256, 0, s>>>(pp, big);

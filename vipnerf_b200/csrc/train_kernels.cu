@@ -14,6 +14,7 @@
 //                   gradients are bit-reproducible run to run (no atomics).  Bias gradients (column sums of dY) ride
 //                   along in the threads that already hold the dY values.
 //  k_small_tn       the same for the 1- and 4-row heads (pts_output_linear, views_output_linear): HBM-bound streaming.
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include "kernels.h"
@@ -387,9 +388,11 @@ k_gemm_tn(const float* __restrict__ A, int lda, const float* __restrict__ B, int
 
 // dst[m * ldc + n] = sum_s partial[s][m][n], n < n_valid  (fixed summation order)
 __global__ void k_reduce_partials(const float* __restrict__ partial, int n_split, int M, int N, float* __restrict__ dst,
-                                  int ldc, int n_valid) {
+                                  int ldc, int n_valid, const uint32_t* __restrict__ scale_def) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= M * n_valid) return;
+  // fp16 training mode: the partial sums carry the power-of-two scale of their gradient operand (exact to undo)
+  const float inv_scale = scale_def ? 1.f / grad_scale_from_amax(*scale_def) : 1.f;
   const int m = i / n_valid, n = i % n_valid;
   float s = 0.f;
   const size_t stride = (size_t)M * N;
@@ -403,12 +406,15 @@ __global__ void k_reduce_partials(const float* __restrict__ partial, int n_split
     for (int u = 0; u < 8; ++u) s += v[u];
   }
   for (; k < n_split; ++k) s += src[(size_t)k * stride];
-  dst[(size_t)m * ldc + n] = s;
+  dst[(size_t)m * ldc + n] = s * inv_scale;
 }
 
-template <int M>
+__device__ __forceinline__ float to_f32(float v) { return v; }
+__device__ __forceinline__ float to_f32(__half v) { return __half2float(v); }
+
+template <int M, typename T>
 __global__ void __launch_bounds__(256)
-k_small_tn(const float* __restrict__ G, const float* __restrict__ H, int N, int64_t n_rows, int64_t rows_per_split,
+k_small_tn(const float* __restrict__ G, const T* __restrict__ H, int N, int64_t n_rows, int64_t rows_per_split,
            float* __restrict__ partial, float* __restrict__ gsum_partial) {
   const int n = threadIdx.x;
   const int64_t r_begin = (int64_t)blockIdx.x * rows_per_split;
@@ -420,7 +426,7 @@ k_small_tn(const float* __restrict__ G, const float* __restrict__ H, int N, int6
   if (n < N) {
 #pragma unroll 4
     for (int64_t r = r_begin; r < r_end; ++r) {
-      const float hval = H[r * N + n];
+      const float hval = to_f32(H[r * N + n]);
 #pragma unroll
       for (int m = 0; m < M; ++m) acc[m] = fmaf(G[r * M + m], hval, acc[m]);
       if (n < M) gs += G[r * M + n];
@@ -436,9 +442,23 @@ k_small_tn(const float* __restrict__ G, const float* __restrict__ H, int N, int6
 //
 // k_encode_points: sample points o + d z and their 63-d encoding (column 63 = 0), plus the 27-d view-direction encoding
 // of the primary view and of every secondary view (compute_other_view_dirs, VipNeRF01.py:218-226).  One thread per point.
+// T = float: enc [P][64], pev [P][nviews][32] fp32.  T = __half (fp16 training mode): enc [P][64], pev [P][nviews][64]
+// fp16 - 128-byte rows either way (what the TMA boxes of the parameter-gradient product want).
+__device__ __forceinline__ void store_as(float* p, float v) { *p = v; }
+__device__ __forceinline__ void store_as(__half* p, float v) { *p = __float2half_rn(v); }
+// gradients: fp16 stores saturate at +-65504 instead of overflowing to inf
+__device__ __forceinline__ void store_sat(float* p, float v) { *p = v; }
+__device__ __forceinline__ void store_sat(__half* p, float v) {
+  unsigned short r;
+  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(r) : "f"(v));
+  *reinterpret_cast<unsigned short*>(p) = r;
+}
+
+template <typename T>
 __global__ void __launch_bounds__(128)
 k_encode_points(RayPtrs rp, RenderFlags fl, int64_t n_points, int S, const float* __restrict__ z,
-                float* __restrict__ enc, float* __restrict__ pev) {
+                T* __restrict__ enc, T* __restrict__ pev) {
+  constexpr int kPevCols = sizeof(T) == 2 ? 64 : 32;
   // A thread computes one point's row, but writing 64 (32) floats of its own row touches 32 different lines per
   // instruction; the block's rows are contiguous in memory, so they are staged in shared memory (row stride 65 / 33:
   // conflict-free for row-per-thread writes) and copied out with full-line stores.
@@ -459,7 +479,7 @@ k_encode_points(RayPtrs rp, RenderFlags fl, int64_t n_points, int S, const float
   }
   e[63] = 0.f;
   __syncthreads();
-  for (int i = threadIdx.x; i < n_here * 64; i += blockDim.x) enc[p0 * 64 + i] = tile[(i >> 6) * 65 + (i & 63)];
+  for (int i = threadIdx.x; i < n_here * 64; i += blockDim.x) store_as(enc + p0 * 64 + i, tile[(i >> 6) * 65 + (i & 63)]);
   for (int v = 0; v < nviews; ++v) {
     float dir[3];
     if (v == 0) {
@@ -479,9 +499,11 @@ k_encode_points(RayPtrs rp, RenderFlags fl, int64_t n_points, int S, const float
 #pragma unroll
     for (int c = kEncView; c < 32; ++c) pe[c] = 0.f;
     __syncthreads();
-    // row r of this view lives at pev[((p0 + r) * nviews + v) * 32 ...]: one full 128-byte line per row
-    for (int i = threadIdx.x; i < n_here * 32; i += blockDim.x)
-      pev[((p0 + (i >> 5)) * nviews + v) * 32 + (i & 31)] = tile[(i >> 5) * 33 + (i & 31)];
+    // row r of this view lives at pev[((p0 + r) * nviews + v) * kPevCols ...]: one full 128-byte line per row
+    for (int i = threadIdx.x; i < n_here * kPevCols; i += blockDim.x) {
+      const int r = i / kPevCols, c = i % kPevCols;
+      store_as(pev + ((p0 + r) * nviews + v) * kPevCols + c, c < 32 ? tile[r * 33 + c] : 0.f);
+    }
   }
 }
 
@@ -489,11 +511,14 @@ k_encode_points(RayPtrs rp, RenderFlags fl, int64_t n_points, int S, const float
 // view, views_linears.0's direction columns + bias on top of the feature product (acc9), ReLU, views_output_linear and
 // the sigmoids (:576-594).  One thread per point; the 16 KiB of head weights sit in shared memory (every lane reads the
 // same word: broadcasts).  Stores the views layer's output per view for the backward.
+template <typename T>
 __global__ void __launch_bounds__(128)
 k_heads_fwd(int64_t n_points, int nviews, const float* __restrict__ small, const float* __restrict__ h7,
-            const float* __restrict__ acc9, const float* __restrict__ pev, const float* __restrict__ noise,
+            const float* __restrict__ acc9, const T* __restrict__ pev, const float* __restrict__ noise,
             float* __restrict__ out_sigma, float* __restrict__ out_rgb, float* __restrict__ out_vis,
-            float* __restrict__ out_vis2, float* __restrict__ hv) {
+            float* __restrict__ out_vis2, T* __restrict__ hv) {
+  constexpr bool kHalf = sizeof(T) == 2;
+  constexpr int kPevCols = kHalf ? 64 : 32;
   __shared__ __align__(16) float s_wvd[kEncView * 128];
   __shared__ __align__(16) float s_wout[128 * 4];
   __shared__ float s_bv[128];
@@ -525,11 +550,11 @@ k_heads_fwd(int64_t n_points, int nviews, const float* __restrict__ small, const
   const float bo[4] = {small[kOffBOut], small[kOffBOut + 1], small[kOffBOut + 2], small[kOffBOut + 3]};
   for (int v = 0; v < nviews; ++v) {
     float pe[kEncView];
-    const float* pp = pev + (pg * nviews + v) * 32;
+    const T* pp = pev + (pg * nviews + v) * kPevCols;
 #pragma unroll
-    for (int e = 0; e < kEncView; ++e) pe[e] = pp[e];
+    for (int e = 0; e < kEncView; ++e) pe[e] = to_f32(pp[e]);
     float o[4] = {0.f, 0.f, 0.f, 0.f};
-    float4* hv_row = reinterpret_cast<float4*>(hv + (pg * nviews + v) * 128);
+    T* hv_row = hv + (pg * nviews + v) * 128;
     for (int n4 = 0; n4 < 32; ++n4) {
       const float4 a = a9[n4];
       float pre[4] = {a.x + s_bv[4 * n4], a.y + s_bv[4 * n4 + 1], a.z + s_bv[4 * n4 + 2], a.w + s_bv[4 * n4 + 3]};
@@ -546,7 +571,12 @@ k_heads_fwd(int64_t n_points, int nviews, const float* __restrict__ small, const
         o[0] = fmaf(pre[q], wo.x, o[0]); o[1] = fmaf(pre[q], wo.y, o[1]);
         o[2] = fmaf(pre[q], wo.z, o[2]); o[3] = fmaf(pre[q], wo.w, o[3]);
       }
-      hv_row[n4] = make_float4(pre[0], pre[1], pre[2], pre[3]);
+      if constexpr (kHalf) {   // saved in fp16: the parameter-gradient product reads 11 significand bits either way
+        const __half2 lo = __floats2half2_rn(pre[0], pre[1]), hi = __floats2half2_rn(pre[2], pre[3]);
+        *reinterpret_cast<uint2*>(hv_row + 4 * n4) = make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+      } else {
+        *reinterpret_cast<float4*>(hv_row + 4 * n4) = make_float4(pre[0], pre[1], pre[2], pre[3]);
+      }
     }
     if (v == 0) {
       out_rgb[3 * pg + 0] = 1.f / (1.f + expf(-(o[0] + bo[0])));
@@ -562,15 +592,19 @@ k_heads_fwd(int64_t n_points, int nviews, const float* __restrict__ small, const
 // k_heads_bwd: the head part of the backward (the first phase of k_mlp_bwd_fp32 as a kernel of its own): per view
 // g_pre[p][view][n] = relu'(hv) * sum_k dlogit[p][view][k] * W_out[k][n]; their sum over views is the gradient of the
 // feature product.  64 points per block, thread = hidden unit n.
+template <typename T>
 __global__ void __launch_bounds__(128)
 k_heads_bwd(int64_t n_points, int nviews, const float* __restrict__ small, const float* __restrict__ dlogit,
-            const float* __restrict__ hv, float* __restrict__ dhv, float* __restrict__ dacc9) {
+            const T* __restrict__ hv, T* __restrict__ dhv, T* __restrict__ dacc9, const uint32_t* __restrict__ scale_def,
+            uint32_t* __restrict__ amax_out) {
   extern __shared__ __align__(16) float dl_s[];   // [64][nviews][4]
   const int64_t p0 = (int64_t)blockIdx.x * 64;
   const int n = threadIdx.x;
+  // fp16 mode: both outputs carry the power-of-two scale defined by max |dlogit| (grad_scale_from_amax)
+  const float scale = scale_def ? grad_scale_from_amax(*scale_def) : 1.f;
   for (int t = threadIdx.x; t < 64 * nviews * 4; t += blockDim.x) {
     const int64_t e = p0 * nviews * 4 + t;
-    dl_s[t] = e < n_points * nviews * 4 ? dlogit[e] : 0.f;
+    dl_s[t] = e < n_points * nviews * 4 ? dlogit[e] * scale : 0.f;
   }
   __syncthreads();
   const float4 wo = *reinterpret_cast<const float4*>(small + kOffWOut + n * 4);
@@ -581,7 +615,7 @@ k_heads_bwd(int64_t n_points, int nviews, const float* __restrict__ small, const
   for (int v = 0; v < nviews; ++v) {
     float hvv[64];
 #pragma unroll
-    for (int p = 0; p < 64; ++p) hvv[p] = hv[((p0 + min(p, n_valid - 1)) * nviews + v) * 128 + n];
+    for (int p = 0; p < 64; ++p) hvv[p] = to_f32(hv[((p0 + min(p, n_valid - 1)) * nviews + v) * 128 + n]);
 #pragma unroll
     for (int p = 0; p < 64; ++p) {
       const float4 d4 = *reinterpret_cast<const float4*>(dl_s + (p * nviews + v) * 4);
@@ -591,37 +625,75 @@ k_heads_bwd(int64_t n_points, int nviews, const float* __restrict__ small, const
     }
 #pragma unroll
     for (int p = 0; p < 64; ++p)
-      if (p < n_valid) dhv[((p0 + p) * nviews + v) * 128 + n] = hvv[p];
+      if (p < n_valid) store_sat(dhv + ((p0 + p) * nviews + v) * 128 + n, hvv[p]);
   }
+  float amax = 0.f;
 #pragma unroll
   for (int p = 0; p < 64; ++p)
-    if (p < n_valid) dacc9[(p0 + p) * 128 + n] = accp[p];
+    if (p < n_valid) {
+      store_sat(dacc9 + (p0 + p) * 128 + n, accp[p]);
+      amax = fmaxf(amax, fabsf(accp[p]));
+    }
+  if (amax_out != nullptr) {   // un-scaled maximum of what feeds the chain's first product
+    const uint32_t m = __reduce_max_sync(0xffffffffu, __float_as_uint(amax / scale));
+    if ((threadIdx.x & 31) == 0 && m != 0u) atomicMax(amax_out, m);
+  }
+}
+
+// fp16 training mode: the two maxima that anchor the gradient scales of the backward chain (kernels.h: launch_grad_amax)
+__global__ void __launch_bounds__(256)
+k_grad_amax(int64_t n_logit, int64_t n_points, const float* __restrict__ dlogit, const float* __restrict__ dsig,
+            const float* __restrict__ small, uint32_t* __restrict__ amax_logit, uint32_t* __restrict__ amax_sigma) {
+  float ml = 0.f, ms = 0.f;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_logit; i += stride) ml = fmaxf(ml, fabsf(dlogit[i]));
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_points; i += stride) ms = fmaxf(ms, fabsf(dsig[i]));
+  ms *= small[kOffBSigma + 1];      // max |pts_output_linear.weight| (k_pack_small)
+  const uint32_t bl = __reduce_max_sync(0xffffffffu, __float_as_uint(ml));
+  const uint32_t bs = __reduce_max_sync(0xffffffffu, __float_as_uint(ms));
+  if ((threadIdx.x & 31) == 0) {
+    if (bl != 0u && bl < 0x7f800000u) atomicMax(amax_logit, bl);
+    if (bs != 0u && bs < 0x7f800000u) atomicMax(amax_sigma, bs);
+  }
 }
 
 }  // namespace
 
 cudaError_t launch_encode_points(const RayPtrs& rp, const RenderFlags& fl, int64_t n_rays, int S, const float* z,
-                                 float* enc, float* pev, cudaStream_t s) {
+                                 void* enc, void* pev, cudaStream_t s, bool half) {
   const int64_t P = n_rays * S;
   if (P == 0) return cudaSuccess;
-  k_encode_points<<<(unsigned)((P + 127) / 128), 128, 0, s>>>(rp, fl, P, S, z, enc, pev);
+  if (half) k_encode_points<__half><<<(unsigned)((P + 127) / 128), 128, 0, s>>>(rp, fl, P, S, z, static_cast<__half*>(enc), static_cast<__half*>(pev));
+  else k_encode_points<float><<<(unsigned)((P + 127) / 128), 128, 0, s>>>(rp, fl, P, S, z, static_cast<float*>(enc), static_cast<float*>(pev));
   return cudaGetLastError();
 }
 
 cudaError_t launch_heads_fwd(int64_t n_points, int nviews, const void* packed, const float* h7, const float* acc9,
-                             const float* pev, const float* noise, float* sigma, float* rgb, float* vis, float* vis2,
-                             float* hv, cudaStream_t s) {
+                             const void* pev, const float* noise, float* sigma, float* rgb, float* vis, float* vis2,
+                             void* hv, cudaStream_t s, bool half) {
   if (n_points == 0) return cudaSuccess;
-  k_heads_fwd<<<(unsigned)((n_points + 127) / 128), 128, 0, s>>>(n_points, nviews, reinterpret_cast<const float*>(packed), h7,
-                                                                 acc9, pev, noise, sigma, rgb, vis, vis2, hv);
+  const unsigned grid = (unsigned)((n_points + 127) / 128);
+  const float* small = reinterpret_cast<const float*>(packed);
+  if (half) k_heads_fwd<__half><<<grid, 128, 0, s>>>(n_points, nviews, small, h7, acc9, static_cast<const __half*>(pev), noise, sigma, rgb, vis, vis2, static_cast<__half*>(hv));
+  else k_heads_fwd<float><<<grid, 128, 0, s>>>(n_points, nviews, small, h7, acc9, static_cast<const float*>(pev), noise, sigma, rgb, vis, vis2, static_cast<float*>(hv));
   return cudaGetLastError();
 }
 
-cudaError_t launch_heads_bwd(int64_t n_points, int nviews, const void* packed, const float* dlogit, const float* hv,
-                             float* dhv, float* dacc9, cudaStream_t s) {
+cudaError_t launch_heads_bwd(int64_t n_points, int nviews, const void* packed, const float* dlogit, const void* hv,
+                             void* dhv, void* dacc9, cudaStream_t s, bool half, const uint32_t* scale_def, uint32_t* amax_out) {
   if (n_points == 0) return cudaSuccess;
-  k_heads_bwd<<<(unsigned)((n_points + 63) / 64), 128, 64 * nviews * 4 * sizeof(float), s>>>(
-      n_points, nviews, reinterpret_cast<const float*>(packed), dlogit, hv, dhv, dacc9);
+  const unsigned grid = (unsigned)((n_points + 63) / 64);
+  const size_t smem = 64 * nviews * 4 * sizeof(float);
+  const float* small = reinterpret_cast<const float*>(packed);
+  if (half) k_heads_bwd<__half><<<grid, 128, smem, s>>>(n_points, nviews, small, dlogit, static_cast<const __half*>(hv), static_cast<__half*>(dhv), static_cast<__half*>(dacc9), scale_def, amax_out);
+  else k_heads_bwd<float><<<grid, 128, smem, s>>>(n_points, nviews, small, dlogit, static_cast<const float*>(hv), static_cast<float*>(dhv), static_cast<float*>(dacc9), scale_def, amax_out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_grad_amax(int64_t n_points, int nviews, const void* packed, const float* dlogit, const float* dsig,
+                             uint32_t* amax_logit, uint32_t* amax_sigma, cudaStream_t s) {
+  if (n_points == 0) return cudaSuccess;
+  k_grad_amax<<<4 * 148, 256, 0, s>>>(n_points * nviews * 4, n_points, dlogit, dsig, reinterpret_cast<const float*>(packed), amax_logit, amax_sigma);
   return cudaGetLastError();
 }
 
@@ -743,14 +815,14 @@ cudaError_t launch_gemm_tn(const float* A, int lda, int M, const float* B, int l
 #undef VIPNERF_LAUNCH_GEMM
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  k_reduce_partials<<<(M * n_valid + 255) / 256, 256, 0, s>>>(partial, (int)n_split, M, N, dst, ldc, n_valid);
-  if (bias_dst) k_reduce_partials<<<(M + 255) / 256, 256, 0, s>>>(bias_partial, (int)n_split, M, 1, bias_dst, 1, 1);
+  k_reduce_partials<<<(M * n_valid + 255) / 256, 256, 0, s>>>(partial, (int)n_split, M, N, dst, ldc, n_valid, nullptr);
+  if (bias_dst) k_reduce_partials<<<(M + 255) / 256, 256, 0, s>>>(bias_partial, (int)n_split, M, 1, bias_dst, 1, 1, nullptr);
   return cudaGetLastError();
 }
 
 cudaError_t launch_reduce_partials(const float* partial, int n_split, int M, int N, float* dst, int ldc, int n_valid,
-                                   cudaStream_t s) {
-  k_reduce_partials<<<(M * n_valid + 255) / 256, 256, 0, s>>>(partial, n_split, M, N, dst, ldc, n_valid);
+                                   cudaStream_t s, const uint32_t* scale_def) {
+  k_reduce_partials<<<(M * n_valid + 255) / 256, 256, 0, s>>>(partial, n_split, M, N, dst, ldc, n_valid, scale_def);
   return cudaGetLastError();
 }
 
@@ -782,8 +854,8 @@ cudaError_t launch_colsum(const float* A, int lda, int M, int64_t n_rows, float*
   return launch_reduce_partials(partial, (int)n_split, M, 1, dst, 1, 1, s);
 }
 
-cudaError_t launch_small_tn(const float* G, int M, const float* H, int N, int64_t n_rows, float* dst, float* gsum_dst,
-                            float* partial, cudaStream_t s) {
+cudaError_t launch_small_tn(const float* G, int M, const void* H, int N, int64_t n_rows, float* dst, float* gsum_dst,
+                            float* partial, cudaStream_t s, bool half_h) {
   if ((M != 1 && M != 4) || N < 4 || N > 256) return cudaErrorInvalidValue;
   int64_t n_split = 4 * 148;
   const int64_t max_by_rows = (n_rows + 63) / 64;
@@ -791,12 +863,16 @@ cudaError_t launch_small_tn(const float* G, int M, const float* H, int N, int64_
   if (n_split < 1) n_split = 1;
   const int64_t rows_per_split = (n_rows + n_split - 1) / n_split;
   float* gsum_partial = partial + kGemmMaxMainFloats;
-  if (M == 1) k_small_tn<1><<<(unsigned)n_split, 256, 0, s>>>(G, H, N, n_rows, rows_per_split, partial, gsum_partial);
-  else k_small_tn<4><<<(unsigned)n_split, 256, 0, s>>>(G, H, N, n_rows, rows_per_split, partial, gsum_partial);
+  const float* Hf = static_cast<const float*>(H);
+  const __half* Hh = static_cast<const __half*>(H);
+  if (M == 1 && !half_h) k_small_tn<1, float><<<(unsigned)n_split, 256, 0, s>>>(G, Hf, N, n_rows, rows_per_split, partial, gsum_partial);
+  else if (M == 1) k_small_tn<1, __half><<<(unsigned)n_split, 256, 0, s>>>(G, Hh, N, n_rows, rows_per_split, partial, gsum_partial);
+  else if (!half_h) k_small_tn<4, float><<<(unsigned)n_split, 256, 0, s>>>(G, Hf, N, n_rows, rows_per_split, partial, gsum_partial);
+  else k_small_tn<4, __half><<<(unsigned)n_split, 256, 0, s>>>(G, Hh, N, n_rows, rows_per_split, partial, gsum_partial);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  k_reduce_partials<<<(M * N + 255) / 256, 256, 0, s>>>(partial, (int)n_split, M, N, dst, N, N);
-  if (gsum_dst) k_reduce_partials<<<1, 256, 0, s>>>(gsum_partial, (int)n_split, M, 1, gsum_dst, 1, 1);
+  k_reduce_partials<<<(M * N + 255) / 256, 256, 0, s>>>(partial, (int)n_split, M, N, dst, N, N, nullptr);
+  if (gsum_dst) k_reduce_partials<<<1, 256, 0, s>>>(gsum_partial, (int)n_split, M, 1, gsum_dst, 1, 1, nullptr);
   return cudaGetLastError();
 }
 

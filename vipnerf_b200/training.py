@@ -96,7 +96,7 @@ class _RenderTrain(torch.autograd.Function):
         n_coarse, n_fine, V = spec['n_coarse'], spec['n_fine'] if has_fine else 0, spec['n_sec_views']
         cfg = _lib.make_cfg(n_coarse=n_coarse, n_fine=n_fine, n_sec_views=V, ndc=spec['ndc'],
                             white_bkgd=spec['white_bkgd'], lindisp=spec['lindisp'], precision='fp32',
-                            train_tf32=spec['tf32'])
+                            train_precision=spec['train_precision'])
         names = renderpath.MLP_PARAM_ORDER
         packed_c = renderpath.pack_mlp(dict(zip(names, [p.detach() for p in params[:24]])), 'fp32')
         packed_f = renderpath.pack_mlp(dict(zip(names, [p.detach() for p in params[24:48]])), 'fp32') if has_fine else None
@@ -149,7 +149,7 @@ class _RenderTrain(torch.autograd.Function):
         R = outputs[0].shape[0]
         cfg = _lib.make_cfg(n_coarse=n_coarse, n_fine=n_fine, n_sec_views=V, ndc=spec['ndc'],
                             white_bkgd=spec['white_bkgd'], lindisp=spec['lindisp'], precision='fp32',
-                            train_tf32=spec['tf32'])
+                            train_precision=spec['train_precision'])
         keep: list = []
         rays = renderpath._make_rays(spec['batch'], spec['ndc'], n_coarse, n_fine, V, keep)
         fwd, gout = _lib.Out(), _lib.Out()
@@ -184,13 +184,20 @@ class _RenderTrain(torch.autograd.Function):
 def render_rays_train(batch: Dict[str, torch.Tensor], params_coarse: Dict[str, torch.Tensor],
                       params_fine: Optional[Dict[str, torch.Tensor]], *, ndc: bool, n_coarse: int = 64,
                       n_fine: int = 128, n_sec_views: int = 0, white_bkgd: bool = False,
-                      lindisp: bool = False, tf32: bool = False) -> Dict[str, torch.Tensor]:
+                      lindisp: bool = False, tf32: bool = False, train_precision: Optional[str] = None) -> Dict[str, torch.Tensor]:
     """Train-mode VipNeRF.render_rays (VipNeRF01.py:74-171 with self.training: retraw and sec_views_vis on, :40),
     differentiable w.r.t. the MLP parameters.  `batch` holds the ray tensors plus the random draws (`t_rand`, `u_rand`,
     `sigma_noise_coarse`, `sigma_noise_fine`; see draw_training_randoms) - a missing draw switches that source off.
     `params_*`: the reference's state_dict names of one MLP -> parameter tensors (CUDA, fp32).
-    `tf32`: every 256-wide product of the step (forward chain, backward-data chain, parameter gradients) runs on the
-    tensor cores (tcgen05 kind::tf32: operands rounded to tf32, fp32 accumulation) instead of fp32 CUDA cores."""
+    `train_precision`: 'fp32' = CUDA cores (the reference's arithmetic); 'tf32' = every 256-wide product of the step
+    (forward chain, backward-data chain, parameter gradients) on the tensor cores (tcgen05 kind::tf32: operands rounded
+    to tf32, fp32 accumulation); 'fp16' = the same products on tcgen05 kind::f16 with every saved activation and chain
+    gradient stored as fp16 (the same 11-bit significand, half the HBM bytes; gradients carry per-array power-of-two
+    scales).  `tf32=True` is the older spelling of train_precision='tf32'."""
+    if train_precision is None:
+        train_precision = 'tf32' if tf32 else 'fp32'
+    if train_precision not in _lib.TRAIN_PRECISIONS:
+        raise ValueError(f'train_precision = {train_precision!r}')
     renderpath._require_cuda(batch['rays_o'], 'rays_o')
     has_fine = params_fine is not None and n_fine > 0
     names = renderpath.MLP_PARAM_ORDER
@@ -198,13 +205,13 @@ def render_rays_train(batch: Dict[str, torch.Tensor], params_coarse: Dict[str, t
     out_names = [f'{k}_coarse' for k in keys] + ([f'{k}_fine' for k in keys] if has_fine else [])
     state = FusedLossState()
     spec = dict(batch=batch, ndc=ndc, n_coarse=n_coarse, n_fine=n_fine, n_sec_views=n_sec_views, white_bkgd=white_bkgd,
-                lindisp=lindisp, has_fine=has_fine, out_names=out_names, tf32=bool(tf32), fused_state=state)
+                lindisp=lindisp, has_fine=has_fine, out_names=out_names, train_precision=train_precision, fused_state=state)
     params = [params_coarse[k] for k in names] + ([params_fine[k] for k in names] if has_fine else [])
     outputs = _RenderTrain.apply(spec, *params)
     result = TrainOutputs(zip(out_names, outputs[:-1]))
     result.fused = {'token': outputs[-1], 'state': state,
                     'cfg_kwargs': dict(n_coarse=n_coarse, n_fine=n_fine if has_fine else 0, n_sec_views=n_sec_views, ndc=ndc,
-                                       white_bkgd=white_bkgd, lindisp=lindisp, precision='fp32', train_tf32=bool(tf32))}
+                                       white_bkgd=white_bkgd, lindisp=lindisp, precision='fp32', train_precision=train_precision)}
     for tag in ('coarse', 'fine'):
         if f'raw_rgb_{tag}' in result:   # the reference returns the same tensor under both names (:531)
             result[f'raw_rgb_view_dependent_{tag}'] = result[f'raw_rgb_{tag}']
@@ -246,10 +253,15 @@ def volume_rendering_backward(batch: Dict[str, torch.Tensor], z_vals: torch.Tens
 
 
 def param_gradient_gemm(dy: torch.Tensor, x: torch.Tensor, *, mode: int = 0, with_bias: bool = True):
-    """dW = dy^T x and db = column sums of dy over all rows (vipnerf_param_gradient_gemm).  dy [P,M], x [P,N] fp32 CUDA;
-    mode 0 = fp32 CUDA cores, 1 = tcgen05 tf32 (N = 256)."""
+    """dW = dy^T x and db = column sums of dy over all rows (vipnerf_param_gradient_gemm).  dy [P,M], x [P,N] CUDA;
+    mode 0 = fp32 CUDA cores, 1 = tcgen05 tf32 (fp32 arrays, N in {32, 64, 256}), 2 = tcgen05 fp16 (the arrays are
+    converted to fp16 here; N in {64, 256})."""
     lib = _lib.load()
-    dy, x = renderpath._f32c(dy, 'dy'), renderpath._f32c(x, 'x')
+    if mode == 2:
+        renderpath._require_cuda(dy, 'dy')
+        dy, x = dy.to(torch.float16).contiguous(), x.to(torch.float16).contiguous()
+    else:
+        dy, x = renderpath._f32c(dy, 'dy'), renderpath._f32c(x, 'x')
     P, M = dy.shape
     N = x.shape[1]
     device = dy.device
