@@ -383,9 +383,10 @@ TRAIN_FLOP_PER_POINT = 2 * (593_536 + 557_056 + 593_536)   # forward + backward-
 TRAIN_TC_BYTES_PER_POINT = 22_852 + 2_672 + 26_116 + 31_012   # 82,652
 
 
-def make_train_step(device, R, rng, train_precision, seed, world=1, loss_path='fused'):
+def make_train_step(device, R, rng, train_precision, seed, world=1, loss_path='fused', graph=False):
     """One training iteration of BASELINE config 3 through the plugin exactly as Trainer01.train_one_iter (:61-107)
     drives it: pinned host rays in, zero_grad, model(batch) in train mode, the four losses, backward, Adam step.
+    graph=True: the same iteration captured once as a CUDA graph (vipnerf_b200.training.GraphedTrainStep) and replayed.
     Returns (step_fn, model, h2d_bytes)."""
     import torch
     from oracle import vipnerf_oracle as O
@@ -398,7 +399,7 @@ def make_train_step(device, R, rng, train_precision, seed, world=1, loss_path='f
     model = get_model(cfg, None)
     model.load_state_dict(O.synth_state_dict(0))
     model = model.to(device).train()
-    opt = torch.optim.Adam(model.parameters(), lr=5e-4, betas=(0.9, 0.999))
+    opt = torch.optim.Adam(model.parameters(), lr=5e-4, betas=(0.9, 0.999), capturable=bool(graph))
     host = {k: v.pin_memory() for k, v in O.make_rays('re10k', R, seed=seed, n_sec_views=V).items()}
     sup_host = O.make_supervision('re10k', R, V)
     sup = {k: (v.to(device) if isinstance(v, torch.Tensor) else v) for k, v in sup_host.items()}
@@ -410,6 +411,19 @@ def make_train_step(device, R, rng, train_precision, seed, world=1, loss_path='f
                      {'name': 'VisibilityPriorLoss01', 'iter_weights': {'0': 0, '30000': 0.001}},
                      {'name': 'SparseDepthMSE01', 'weight': 0.1}]       # runs/training/train0012/Configs.json:69-89
     computer = LossComputer(cfg)
+
+    if graph:
+        if world > 1 or loss_path != 'fused' or rng != 'device':
+            raise SystemExit('--graph: one GPU, the fused losses and --rng device')
+        from vipnerf_b200.training import GraphedTrainStep
+        example = dict(host)
+        example.update(sup)
+        graphed = GraphedTrainStep(model, computer, opt, example, device)
+
+        def graphed_step():
+            return graphed(host)        # batch -> pinned staging buffers, one graph launch; returns the device loss
+
+        return graphed_step, model, graphed.h2d_bytes
 
     def step():
         batch = {k: v.to(device, non_blocking=True) for k, v in host.items()}
@@ -475,7 +489,7 @@ def run_train(args, rank, world, local_rank):
         dist.init_process_group('nccl', device_id=device)
     R, V = args.rays_per_step, 1
     step, model, h2d = make_train_step(device, R, args.rng, args.train_precision, seed=2 + rank, world=world,
-                                       loss_path=args.loss_path)
+                                       loss_path=args.loss_path, graph=args.graph)
 
     def barrier():
         if world > 1:
@@ -589,6 +603,7 @@ def main():
     ap.add_argument('--rng', default='reference', choices=['reference', 'device'],
                     help='train workload: where the stratified jitter / cdf samples / density noise are drawn')
     ap.add_argument('--loss-path', default='fused', choices=['fused', 'torch'], help='train workload: fused CUDA losses or torch ops')
+    ap.add_argument('--graph', action='store_true', help='train workload: the iteration captured once as a CUDA graph and replayed')
     ap.add_argument('--scene', default='fern', choices=['fern', 'dtu'], help='camera of the frame workload')
     ap.add_argument('--gather', default='peer', choices=['peer', 'nccl'], help='N > 1: how the rendered maps reach rank 0')
     ap.add_argument('--quick', action='store_true', help='batch workload: skip the sustained / precision_modes / train sub-records')

@@ -355,3 +355,48 @@ def test_fused_losses_equal_torch_losses(train_precision, built_library):
     for k, g in results['torch'][1].items():
         err = ((results['fused'][1][k] - g).abs().max() / g.abs().max().clamp_min(1e-30)).item()
         assert err <= 2e-4, (k, err)
+
+
+@pytest.mark.parametrize('train_precision', ['tf32', 'fp16'])
+def test_graphed_train_step_equals_eager_iterations(train_precision, built_library):
+    """training.GraphedTrainStep (the whole iteration - upload, zero_grad, forward, fused losses, backward, Adam - as one
+    CUDA graph) against the same iterations run eagerly: with the random sources off every kernel of the step is
+    deterministic, so after the same number of iterations the weights must be bit-identical; and the graph refuses the
+    configurations it cannot capture."""
+    from vipnerf_b200 import training
+    from vipnerf_b200.LossComputerFused01 import LossComputer
+    cfg = _configs(True, perturb=False, raw_noise_std=0.0, train_precision=train_precision)
+    cfg['losses'] = LOSS_CONFIGS
+    cfg['model']['rng'] = 'device'
+    rays = O.make_rays('re10k', 192, seed=4, n_sec_views=1)
+    sup = _sup_cuda(O.make_supervision('re10k', 192, 1))
+    n_iter = 5
+    # eager
+    eager = _train_model(cfg)
+    opt = torch.optim.Adam(eager.parameters(), lr=5e-4, capturable=True)
+    computer = LossComputer(cfg)
+    for _ in range(n_iter):
+        batch = H.to_cuda(rays)
+        batch.update(sup)
+        opt.zero_grad(set_to_none=True)
+        loss = computer.compute_losses(batch, eager(batch))['TotalLoss']
+        loss.backward()
+        opt.step()
+    # graphed: the constructor runs `warmup` real iterations, every call one more
+    graphed_model = _train_model(cfg)
+    gopt = torch.optim.Adam(graphed_model.parameters(), lr=5e-4, capturable=True)
+    example = dict(rays)
+    example.update(sup)
+    step = training.GraphedTrainStep(graphed_model, LossComputer(cfg), gopt, example, warmup=3)
+    for _ in range(n_iter - 3):
+        gloss = step(rays)
+    step.synchronize()
+    assert abs(step.loss_host.item() - loss.item()) <= 1e-6 * abs(loss.item()), (step.loss_host.item(), loss.item())
+    assert gloss.item() == step.loss_host.item()
+    for (k, a), (_, b) in zip(eager.named_parameters(), graphed_model.named_parameters()):
+        assert torch.equal(a, b), k
+    with pytest.raises(ValueError):      # CPU draws cannot be captured
+        bad = _configs(True, train_precision=train_precision)
+        training.GraphedTrainStep(_train_model(bad), LossComputer(cfg), gopt, example)
+    with pytest.raises(ValueError):      # the optimizer must be capturable
+        training.GraphedTrainStep(graphed_model, LossComputer(cfg), torch.optim.Adam(graphed_model.parameters()), example)

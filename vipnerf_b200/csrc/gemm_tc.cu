@@ -387,9 +387,24 @@ __device__ __forceinline__ uint32_t pack_half2_sat(float a, float b) {
   return r;
 }
 
+// What the fp16-output epilogue does per element is a compile-time choice (the fp16 step is epilogue-bound as soon as
+// its per-tile work is more than ~5 k cycles: every runtime flag removed is instructions and branches saved 256 times
+// per row): forward layers add a bias and apply ReLU inside the fp16 conversion; backward layers re-scale, add the
+// density head's rank-1 term, apply the ReLU mask on the packed halves and track the maximum on the packed halves.
+enum : int { kEpiGeneric = 0, kEpiFwdRelu, kEpiFwdLinear, kEpiBwdPlain, kEpiBwdMask, kEpiBwdMaskRank1 };
+constexpr int kVecBytes = 3 * 1024;   // bias / rank-1 column / dot vector staged in shared memory (256 floats each)
+
+// two fp32 -> one packed fp16 pair with the ReLU inside the conversion (F2FP.RELU)
+__device__ __forceinline__ uint32_t pack_half2_relu_sat(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+
 // kDot: the epilogue also reduces every output row against p.dot_vec (a separate instantiation: the plain layers must not
-// pay registers or predicated loads for it).  kHalf: fp16 operands (and masks); kOutHalf: fp16 output.
-template <bool kDot, bool kHalf, bool kOutHalf>
+// pay registers or predicated loads for it).  kHalf: fp16 operands (and masks); kOutHalf: fp16 output, with the
+// per-element work selected by kEpi.
+template <bool kDot, bool kHalf, bool kOutHalf, int kEpi>
 __global__ void __launch_bounds__(kTcThreads, 1) k_linear_tc(const __grid_constant__ LinearTcParams p) {
   using G = TcGeom<kHalf>;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -399,6 +414,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_linear_tc(const __grid_consta
   uint8_t* stage_base = smem + kLinStages * stage_bytes;      // 1 KiB aligned: stage_bytes is a multiple of 16 KiB
   uint8_t* tail = stage_base + kLinStageBytes;
   uint32_t* tmem_ptr_slot = reinterpret_cast<uint32_t*>(tail + 8 * (2 * kLinStages + 4 + 8));
+  float* vec_s = reinterpret_cast<float*>(tail + 256);        // [3][256]: bias, rank-1 column, dot vector (fp16-output epilogue)
   const uint32_t bar0 = smem_u32(tail);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (kLinStages + s); };
@@ -475,7 +491,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_linear_tc(const __grid_consta
     const float s_in = p.scale_in ? grad_scale_from_amax(*p.scale_in) : 1.f;
     const float s_out = p.scale_out ? grad_scale_from_amax(*p.scale_out) : 1.f;
     const float fac = s_out / s_in;
-    float amax = 0.f;       // of the scaled output values this lane wrote
+    uint32_t amax16 = 0u;   // fp16-output backward epilogues: largest |stored value| of this lane, as two packed fp16 bit patterns
+    if constexpr (kOutHalf) {   // the per-column vectors of the epilogue: one copy in shared memory (broadcast reads)
+      const int t = (warp - 2) * 32 + lane;
+      for (int c = t; c < p.N; c += 128) {
+        vec_s[c] = p.bias ? p.bias[c] : 0.f;
+        vec_s[256 + c] = p.rank1_col ? p.rank1_col[c] : 0.f;
+        vec_s[512 + c] = p.dot_vec ? p.dot_vec[c] : 0.f;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++i) {
       const int buf = i & 1;
       const int64_t pg = (int64_t)tile * kLinRows + quarter * 32 + lane;
@@ -499,67 +524,77 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_linear_tc(const __grid_consta
       float dot = 0.f;
       if constexpr (kOutHalf) {
         const int n_sc = p.N / 64;                                    // one box = 64 fp16 columns = two TMEM loads
-        const float r1 = (p.rank1_row != nullptr && valid) ? p.rank1_row[pg] * s_out : 0.f;
+        constexpr bool kMask = kEpi == kEpiBwdMask || kEpi == kEpiBwdMaskRank1;
+        constexpr bool kBwd = kEpi == kEpiBwdPlain || kMask;
+        float r1 = 0.f;
+        if constexpr (kEpi == kEpiBwdMaskRank1) r1 = valid ? p.rank1_row[pg] * s_out : 0.f;
+        const uint32_t tm0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * 256;
+        // eight columns: v[8 qq ..] -> one 16-byte chunk (index q) of the output box
+        auto eight = [&](const uint32_t (&v)[32], int qq, int q, int sc, uint32_t orow, uint32_t mrow) {
+          float o[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = __uint_as_float(v[8 * qq + j]);
+          const int col = sc * 64 + q * 8;
+          if constexpr (kEpi == kEpiFwdRelu || kEpi == kEpiFwdLinear) {
+            const float4 b0 = *reinterpret_cast<const float4*>(vec_s + col), b1 = *reinterpret_cast<const float4*>(vec_s + col + 4);
+            o[0] += b0.x; o[1] += b0.y; o[2] += b0.z; o[3] += b0.w; o[4] += b1.x; o[5] += b1.y; o[6] += b1.z; o[7] += b1.w;
+          }
+          if constexpr (kBwd) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] *= fac;                 // exact: a power of two
+          }
+          if constexpr (kEpi == kEpiBwdMaskRank1) {
+            const float4 u0 = *reinterpret_cast<const float4*>(vec_s + 256 + col), u1 = *reinterpret_cast<const float4*>(vec_s + 256 + col + 4);
+            o[0] = fmaf(r1, u0.x, o[0]); o[1] = fmaf(r1, u0.y, o[1]); o[2] = fmaf(r1, u0.z, o[2]); o[3] = fmaf(r1, u0.w, o[3]);
+            o[4] = fmaf(r1, u1.x, o[4]); o[5] = fmaf(r1, u1.y, o[5]); o[6] = fmaf(r1, u1.z, o[6]); o[7] = fmaf(r1, u1.w, o[7]);
+          }
+          if constexpr (kDot) {   // the density head reads the fp32 post-ReLU values
+            const float4 d0 = *reinterpret_cast<const float4*>(vec_s + 512 + col), d1 = *reinterpret_cast<const float4*>(vec_s + 512 + col + 4);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = fmaxf(o[j], 0.f);
+            dot = fmaf(o[0], d0.x, dot); dot = fmaf(o[1], d0.y, dot); dot = fmaf(o[2], d0.z, dot); dot = fmaf(o[3], d0.w, dot);
+            dot = fmaf(o[4], d1.x, dot); dot = fmaf(o[5], d1.y, dot); dot = fmaf(o[6], d1.z, dot); dot = fmaf(o[7], d1.w, dot);
+          }
+          uint32_t h[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            h[j] = kEpi == kEpiFwdRelu ? pack_half2_relu_sat(o[2 * j], o[2 * j + 1]) : pack_half2_sat(o[2 * j], o[2 * j + 1]);
+          const uint32_t sw = (uint32_t)((q ^ (lane & 7)) << 4);      // 128-byte swizzle: 16-byte chunk index ^ (row % 8)
+          if constexpr (kMask) {   // saved post-ReLU activations (fp16, never negative): the unit was active iff its value is > 0
+            uint32_t m[4];
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(m[0]), "=r"(m[1]), "=r"(m[2]), "=r"(m[3]) : "r"(mrow + sw));
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              h[j] &= __hgt2_mask(*reinterpret_cast<const __half2*>(&m[j]), __half2(__ushort_as_half(0), __ushort_as_half(0)));
+          }
+          if constexpr (kBwd) {    // maximum of |stored value|: fp16 bit patterns of non-negative values order like integers
+            amax16 = __vimax3_u16x2(amax16, h[0] & 0x7fff7fffu, h[1] & 0x7fff7fffu);
+            amax16 = __vimax3_u16x2(amax16, h[2] & 0x7fff7fffu, h[3] & 0x7fff7fffu);
+          }
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(orow + sw), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
+        };
+        // TMEM loads run one 32-column chunk ahead of the arithmetic (tcgen05.wait::ld waits for ALL of a thread's loads,
+        // so the next load is issued right after the wait and lands while the current chunk is processed)
+        uint32_t va[32], vb[32];
+        tmem_ld32(tm0, va);
+#pragma unroll 1
         for (int sc = 0; sc < n_sc; ++sc, ++mask_n) {
-          uint32_t va[32], vb[32];
-          tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * 256 + sc * 64, va);
-          tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * 256 + sc * 64 + 32, vb);
-          if (has_mask && lane == 0 && sc + 1 < n_sc) {                 // next box of the mask (its buffer was read at sc - 1)
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          tmem_ld32(tm0 + sc * 64 + 32, vb);
+          if (kMask && lane == 0 && sc + 1 < n_sc) {                    // next box of the mask (its buffer was read at sc - 1)
             mbar_expect_tx(mfull0 + 8u * ((mask_n + 1) & 1), 4096);
             tma_load_2d(msk_s + 4096u * ((mask_n + 1) & 1), &p.map_mask, (sc + 1) * 64, row0, mfull0 + 8u * ((mask_n + 1) & 1));
           }
           if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the store issued two boxes ago has read its box
           __syncwarp();
-          if (has_mask) mbar_wait(mfull0 + 8u * (mask_n & 1), (mask_n >> 1) & 1);
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (kMask) mbar_wait(mfull0 + 8u * (mask_n & 1), (mask_n >> 1) & 1);
           const uint32_t orow = out_s + 4096u * (sc & 1) + lane * 128, mrow = msk_s + 4096u * (mask_n & 1) + lane * 128;
-          auto eight = [&](const uint32_t (&v)[32], int qq, int q) {   // columns sc * 64 + q * 8 .. + 7 = v[8 qq ..]
-            float o[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) o[j] = __uint_as_float(v[8 * qq + j]);
-            const int col = sc * 64 + q * 8;
-            if (p.bias != nullptr) {
-              const float4 b0 = *reinterpret_cast<const float4*>(p.bias + col), b1 = *reinterpret_cast<const float4*>(p.bias + col + 4);
-              o[0] += b0.x; o[1] += b0.y; o[2] += b0.z; o[3] += b0.w; o[4] += b1.x; o[5] += b1.y; o[6] += b1.z; o[7] += b1.w;
-            }
+          for (int q = 0; q < 4; ++q) eight(va, q, q, sc, orow, mrow);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (sc + 1 < n_sc) tmem_ld32(tm0 + (sc + 1) * 64, va);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) o[j] *= fac;                 // exact: a power of two (1 in the forward chain)
-            if (p.rank1_row != nullptr) {
-              const float4 u0 = *reinterpret_cast<const float4*>(p.rank1_col + col), u1 = *reinterpret_cast<const float4*>(p.rank1_col + col + 4);
-              o[0] = fmaf(r1, u0.x, o[0]); o[1] = fmaf(r1, u0.y, o[1]); o[2] = fmaf(r1, u0.z, o[2]); o[3] = fmaf(r1, u0.w, o[3]);
-              o[4] = fmaf(r1, u1.x, o[4]); o[5] = fmaf(r1, u1.y, o[5]); o[6] = fmaf(r1, u1.z, o[6]); o[7] = fmaf(r1, u1.w, o[7]);
-            }
-            if (p.relu) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) o[j] = fmaxf(o[j], 0.f);
-            }
-            if (kDot) {
-              const float4 d0 = *reinterpret_cast<const float4*>(p.dot_vec + col), d1 = *reinterpret_cast<const float4*>(p.dot_vec + col + 4);
-              dot = fmaf(o[0], d0.x, dot); dot = fmaf(o[1], d0.y, dot); dot = fmaf(o[2], d0.z, dot); dot = fmaf(o[3], d0.w, dot);
-              dot = fmaf(o[4], d1.x, dot); dot = fmaf(o[5], d1.y, dot); dot = fmaf(o[6], d1.z, dot); dot = fmaf(o[7], d1.w, dot);
-            }
-            const uint32_t sw = (uint32_t)((q ^ (lane & 7)) << 4);    // 128-byte swizzle: 16-byte chunk index ^ (row % 8)
-            if (has_mask) {   // saved post-ReLU activations (fp16): the unit was active iff its value is > 0
-              uint32_t m0, m1, m2, m3;
-              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(m0), "=r"(m1), "=r"(m2), "=r"(m3) : "r"(mrow + sw));
-              const uint32_t mm[4] = {m0, m1, m2, m3};
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                if ((int16_t)(mm[j] & 0xffffu) <= 0) o[2 * j] = 0.f;
-                if ((int16_t)(mm[j] >> 16) <= 0) o[2 * j + 1] = 0.f;
-              }
-            }
-            if (p.amax_out != nullptr) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) amax = fmaxf(amax, fabsf(o[j]));
-            }
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(orow + sw), "r"(pack_half2_sat(o[0], o[1])),
-                         "r"(pack_half2_sat(o[2], o[3])), "r"(pack_half2_sat(o[4], o[5])), "r"(pack_half2_sat(o[6], o[7])) : "memory");
-          };
-#pragma unroll
-          for (int q = 0; q < 4; ++q) eight(va, q, q);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) eight(vb, q, q + 4);
+          for (int q = 0; q < 4; ++q) eight(vb, q, q + 4, sc, orow, mrow);
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
           if (lane == 0) {
@@ -623,9 +658,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_linear_tc(const __grid_consta
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty(buf));
     }
-    if (p.amax_out != nullptr) {   // largest |value| this warp wrote, un-scaled; float bits of non-negative values order like integers
-      const uint32_t m = __reduce_max_sync(0xffffffffu, __float_as_uint(amax / s_out));
-      if (lane == 0 && m != 0u) atomicMax(p.amax_out, m);
+    if (kOutHalf && p.amax_out != nullptr) {   // largest |value| this warp wrote, un-scaled; float bits of non-negative values order like integers
+      const uint32_t m16 = __reduce_max_sync(0xffffffffu, max(amax16 & 0xffffu, amax16 >> 16));
+      const float mv = __half2float(__ushort_as_half((unsigned short)m16)) / s_out;
+      if (lane == 0 && m16 != 0u) atomicMax(p.amax_out, __float_as_uint(mv));
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // shared memory outlives the last stores
   }
@@ -688,22 +724,41 @@ cudaError_t launch_linear_tc(const LinearTcArgs& a, cudaStream_t s) {
   } else {
     p.map_mask = p.map_out;
   }
-  const size_t smem = (size_t)kLinStages * (kLinRows * 128 + a.N * 128) + kLinStageBytes + 256;
+  const size_t smem = (size_t)kLinStages * (kLinRows * 128 + a.N * 128) + kLinStageBytes + 256 + kVecBytes;
   const bool dot = a.dot_vec != nullptr && a.dot_out != nullptr;
   int dev = 0, sms = 0;
   if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
   if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
   const int64_t n_tiles = (a.n_rows + kLinRows - 1) / kLinRows;
   const unsigned grid = (unsigned)(n_tiles < sms ? n_tiles : sms);
-#define VIPNERF_LAUNCH_LINEAR(DOT, HALF, OUTHALF)                                                                         \
+#define VIPNERF_LAUNCH_LINEAR(DOT, HALF, OUTHALF, EPI)                                                                    \
   do {                                                                                                                  \
-    if ((e = cudaFuncSetAttribute(k_linear_tc<DOT, HALF, OUTHALF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e; \
-    k_linear_tc<DOT, HALF, OUTHALF><<<grid, kTcThreads, smem, s>>>(p);                                                  \
+    if ((e = cudaFuncSetAttribute(k_linear_tc<DOT, HALF, OUTHALF, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e; \
+    k_linear_tc<DOT, HALF, OUTHALF, EPI><<<grid, kTcThreads, smem, s>>>(p);                                             \
   } while (0)
-  if (!a.half_in) { if (dot) VIPNERF_LAUNCH_LINEAR(true, false, false); else VIPNERF_LAUNCH_LINEAR(false, false, false); }
-  else if (!a.half_out) { if (dot) return cudaErrorInvalidValue; VIPNERF_LAUNCH_LINEAR(false, true, false); }
-  else if (dot) VIPNERF_LAUNCH_LINEAR(true, true, true);
-  else VIPNERF_LAUNCH_LINEAR(false, true, true);
+  if (!a.half_in) {
+    if (dot) VIPNERF_LAUNCH_LINEAR(true, false, false, kEpiGeneric); else VIPNERF_LAUNCH_LINEAR(false, false, false, kEpiGeneric);
+  } else if (!a.half_out) {
+    if (dot) return cudaErrorInvalidValue;
+    VIPNERF_LAUNCH_LINEAR(false, true, false, kEpiGeneric);
+  } else {
+    // the fp16-output epilogue is specialised at compile time: the combinations the training chains use
+    const bool scaled = a.scale_in != nullptr || a.scale_out != nullptr;
+    const bool rank1 = a.rank1_row != nullptr && a.rank1_col != nullptr;
+    if (!scaled && a.bias != nullptr && !rank1 && a.mask == nullptr) {            // forward layers
+      if (a.relu && dot) VIPNERF_LAUNCH_LINEAR(true, true, true, kEpiFwdRelu);
+      else if (a.relu) VIPNERF_LAUNCH_LINEAR(false, true, true, kEpiFwdRelu);
+      else if (!dot) VIPNERF_LAUNCH_LINEAR(false, true, true, kEpiFwdLinear);
+      else return cudaErrorInvalidValue;
+    } else if (scaled && a.bias == nullptr && !a.relu && !dot) {                  // backward-data layers
+      if (a.mask != nullptr && rank1) VIPNERF_LAUNCH_LINEAR(false, true, true, kEpiBwdMaskRank1);
+      else if (a.mask != nullptr) VIPNERF_LAUNCH_LINEAR(false, true, true, kEpiBwdMask);
+      else if (!rank1) VIPNERF_LAUNCH_LINEAR(false, true, true, kEpiBwdPlain);
+      else return cudaErrorInvalidValue;
+    } else {
+      return cudaErrorInvalidValue;
+    }
+  }
 #undef VIPNERF_LAUNCH_LINEAR
   return cudaGetLastError();
 }

@@ -274,3 +274,83 @@ def param_gradient_gemm(dy: torch.Tensor, x: torch.Tensor, *, mode: int = 0, wit
                                                    renderpath._ptr(db), mode, ws.data_ptr(), ws_bytes,
                                                    renderpath._stream(device)), 'vipnerf_param_gradient_gemm')
     return dw, db
+
+
+class GraphedTrainStep:
+    """One training iteration of the reference's Trainer (Trainer01.py:61-107: batch to the device, `zero_grad`,
+    `model(batch)` in train mode, `compute_losses`, `TotalLoss.backward()`, `optimizer.step()`) captured ONCE as a CUDA
+    graph and replayed with a single launch per iteration: the ~170 kernel launches, ~50 tensor-map encodes and the
+    Python between them leave the critical path (the fp16 step is otherwise host-bound: ~11 ms of GPU work behind
+    ~14 ms of host work).
+
+        step = GraphedTrainStep(model, loss_computer, optimizer, example_batch)
+        loss = step(batch)           # pinned-host copy of the batch -> replay -> device scalar TotalLoss
+        step.loss_host               # pinned host copy of the same value, valid after step.synchronize()
+
+    Requirements (checked): configs['model']['rng'] = 'device' (the reference's CPU draws cannot be captured), an
+    optimizer built with `capturable=True`, a fixed ray count and fixed batch keys.  Non-tensor batch entries
+    (`iter_num`, ...) and the loss weights derived from them are baked in at capture time: call `recapture()` when an
+    `iter_weights` threshold of the loss configs is crossed."""
+
+    def __init__(self, model, loss_computer, optimizer, example_batch: Dict, device=None, warmup: int = 3):
+        cfg = getattr(model, 'configs', {}).get('model', {})
+        if cfg.get('rng', 'reference') != 'device':
+            raise ValueError("GraphedTrainStep needs configs['model']['rng'] = 'device': draws from the CPU generator "
+                             "cannot be part of a CUDA graph")
+        if not optimizer.defaults.get('capturable', False):
+            raise ValueError('GraphedTrainStep needs an optimizer built with capturable=True')
+        self.model, self.computer, self.optimizer = model, loss_computer, optimizer
+        self.device = torch.device(device if device is not None else next(model.parameters()).device)
+        # CPU tensors are the per-iteration inputs (pinned staging copy + upload inside the graph); tensors that already
+        # live on the device and non-tensor entries are used in place
+        self.extra = {k: v for k, v in example_batch.items() if not (isinstance(v, torch.Tensor) and v.device.type == 'cpu')}
+        self.host = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in example_batch.items()
+                     if isinstance(v, torch.Tensor) and v.device.type == 'cpu'}
+        self.dev = {k: torch.empty(v.shape, dtype=v.dtype, device=self.device) for k, v in self.host.items()}
+        self.h2d_bytes = sum(v.numel() * v.element_size() for v in self.host.values())
+        self.loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
+        self.loss = torch.zeros((), dtype=torch.float32, device=self.device)
+        self.stream = torch.cuda.Stream(self.device)
+        self.warmup = warmup
+        self.load(example_batch)
+        self.recapture()
+
+    def load(self, batch: Dict) -> None:
+        for k, v in self.host.items():
+            v.copy_(batch[k])
+
+    def _iteration(self):  # noqa: D401 - the captured body
+        batch = dict(self.extra)
+        for k, v in self.host.items():
+            self.dev[k].copy_(v, non_blocking=True)
+        batch.update(self.dev)
+        self.optimizer.zero_grad(set_to_none=True)
+        out = self.model(batch)
+        total = self.computer.compute_losses(batch, out)['TotalLoss']
+        total.backward()
+        self.optimizer.step()
+        self.loss.copy_(total.detach())
+        self.loss_host.copy_(self.loss, non_blocking=True)
+
+    def recapture(self) -> None:
+        """Warm-up iterations on the capture stream (module load, allocator pools, lazily created optimizer state - these
+        are REAL training iterations), then the capture."""
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.device(self.device):
+            self.stream.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(self.stream):
+                for _ in range(self.warmup):
+                    self._iteration()
+            torch.cuda.synchronize(self.device)
+            with torch.cuda.graph(self.graph, stream=self.stream):
+                self._iteration()
+            torch.cuda.current_stream(self.device).wait_stream(self.stream)
+
+    def __call__(self, batch: Optional[Dict] = None) -> torch.Tensor:
+        if batch is not None:
+            self.load(batch)
+        self.graph.replay()
+        return self.loss
+
+    def synchronize(self) -> None:
+        torch.cuda.current_stream(self.device).synchronize()
