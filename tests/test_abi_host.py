@@ -49,7 +49,7 @@ def test_config_validation(built_library):
     x3 = _lib.make_cfg(precision='bf16x3')
     assert lib.vipnerf_packed_weight_bytes(ctypes.byref(x3)) == 27648 + 2 * ((64 + 6) * 16384 + 8192)
     f32 = _lib.make_cfg(precision='fp32')
-    assert lib.vipnerf_packed_weight_bytes(ctypes.byref(f32)) == 27648 + (589824 + 589824) * (4 + 2)   # forward images + [out][in] images (backward-data chain, tensor-core forward), + their fp16 mirror (fp16 training mode)
+    assert lib.vipnerf_packed_weight_bytes(ctypes.byref(f32)) == 27648 + (589824 + 589824) * (4 + 2) + 128 * 64 * 2   # forward images + [out][in] images (backward-data chain, tensor-core forward), + their fp16 mirror and the fp16 view-direction columns (fp16 training mode)
     # training buffers: fp32 only; about 11 KB of saved activations per sample point
     assert lib.vipnerf_train_saved_bytes(ctypes.byref(ok), 4096) == 0
     f32v = _lib.make_cfg(precision='fp32', n_sec_views=1)

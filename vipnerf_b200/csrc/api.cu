@@ -253,16 +253,36 @@ cudaError_t mlp_forward_tc(const RayPtrs& rp, const RenderFlags& fl, int64_t n_r
     }
     a.bias = small + kOffBias + l * 256;
     a.relu = true;
-    if (l == 7) { a.dot_vec = small + kOffWSigma; a.dot_out = sigma; }   // the density head rides along (read back by k_heads_fwd)
+    if (l == 7) {   // the density head rides along: the raw dot product (finished by k_heads_fwd), or all of it in the fp16 mode
+      a.dot_vec = small + kOffWSigma; a.dot_out = sigma;
+      if (half) { a.dot_bias = small + kOffBSigma; a.dot_noise = sv.noise; }
+    }
     if ((e = launch_linear_tc(a, s)) != cudaSuccess) return e;
   }
   LinearTcArgs f = linear_args(sv.h + 7 * PL, 256, 256, woi.at(kBwdOffFeature), 256, 256, P, sv.feat, 256, half);
   f.bias = small + kOffBias + 8 * 256;
   if ((e = launch_linear_tc(f, s)) != cudaSuccess) return e;
+  const int nv = 1 + fl.n_sec_views;
+  if (half) {
+    // fp16 mode: the whole views branch of a view direction is ONE product launch - [feature | direction encoding] against
+    // [views_linears.0 feature columns | direction columns] (two operand pairs into the same accumulator), + bias, ReLU,
+    // and views_output_linear + the sigmoids in the epilogue that holds the row (VipNeRF01.py:576-594).  hv / pev are
+    // point-major [P][nv][.]: view v is a strided 2-D view for the TMA engine.
+    const uint8_t* wvd = reinterpret_cast<const uint8_t*>(packed_big(packed) + kFp32BigFloats + kFp32BwdFloats) + (size_t)kF16MirrorHalves * 2;
+    for (int view = 0; view < nv; ++view) {
+      LinearTcArgs v = linear_args(sv.feat, 256, 256, woi.at(kBwdOffViews), 256, 128, P, sv.hv + (size_t)view * 128 * es, nv * 128, true);
+      v.x[1] = sv.pev + (size_t)view * 64 * es; v.ldx[1] = nv * 64; v.k[1] = 64; v.w[1] = wvd; v.ldw[1] = 64;
+      v.bias = small + kOffBiasViews; v.relu = true;
+      v.head_wout = small + kOffWOut; v.head_bout = small + kOffBOut;
+      if (view == 0) { v.head_rgb = rgb; v.head_vis = vis; v.head_vis_stride = 1; }
+      else { v.head_vis = vis2 + (view - 1); v.head_vis_stride = nv - 1; }
+      if ((e = launch_linear_tc(v, s)) != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+  }
   LinearTcArgs v = linear_args(sv.feat, 256, 256, woi.at(kBwdOffViews), 256, 128, P, acc9, 128, half);
-  v.half_out = false;      // the heads add the direction term and the bias in fp32 on top of the fp32 accumulators
   if ((e = launch_linear_tc(v, s)) != cudaSuccess) return e;
-  return launch_heads_fwd(P, 1 + fl.n_sec_views, packed, nullptr, acc9, sv.pev, sv.noise, sigma, rgb, vis, vis2, sv.hv, s, half);
+  return launch_heads_fwd(P, nv, packed, nullptr, acc9, sv.pev, sv.noise, sigma, rgb, vis, vis2, sv.hv, s, half);
 }
 
 // Gradient scales of the fp16 mode: every fp16 gradient array is stored times a power of two derived from a maximum

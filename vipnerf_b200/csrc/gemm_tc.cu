@@ -363,6 +363,13 @@ struct LinearTcParams {
   int relu;
   const float* dot_vec;
   float* dot_out;
+  const float* dot_bias;
+  const float* dot_noise;
+  const float* head_wout;
+  const float* head_bout;
+  float* head_rgb;
+  float* head_vis;
+  int head_vis_stride;
   const uint32_t* scale_in;
   const uint32_t* scale_out;
   uint32_t* amax_out;
@@ -390,8 +397,9 @@ __device__ __forceinline__ uint32_t pack_half2_sat(float a, float b) {
 // What the fp16-output epilogue does per element is a compile-time choice (the fp16 step is epilogue-bound as soon as
 // its per-tile work is more than ~5 k cycles: every runtime flag removed is instructions and branches saved 256 times
 // per row): forward layers add a bias and apply ReLU inside the fp16 conversion; backward layers re-scale, add the
-// density head's rank-1 term, apply the ReLU mask on the packed halves and track the maximum on the packed halves.
-enum : int { kEpiGeneric = 0, kEpiFwdRelu, kEpiFwdLinear, kEpiBwdPlain, kEpiBwdMask, kEpiBwdMaskRank1 };
+// density head's rank-1 term, apply the ReLU mask on the packed halves and track the maximum on the packed halves; the
+// views layer (kEpiFwdHead) also evaluates views_output_linear (128 -> 4) and the sigmoids on the row it holds.
+enum : int { kEpiGeneric = 0, kEpiFwdRelu, kEpiFwdLinear, kEpiBwdPlain, kEpiBwdMask, kEpiBwdMaskRank1, kEpiFwdHead };
 constexpr int kVecBytes = 3 * 1024;   // bias / rank-1 column / dot vector staged in shared memory (256 floats each)
 
 // two fp32 -> one packed fp16 pair with the ReLU inside the conversion (F2FP.RELU)
@@ -496,9 +504,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_linear_tc(const __grid_consta
       const int t = (warp - 2) * 32 + lane;
       for (int c = t; c < p.N; c += 128) {
         vec_s[c] = p.bias ? p.bias[c] : 0.f;
-        vec_s[256 + c] = p.rank1_col ? p.rank1_col[c] : 0.f;
-        vec_s[512 + c] = p.dot_vec ? p.dot_vec[c] : 0.f;
+        if constexpr (kEpi != kEpiFwdHead) {
+          vec_s[256 + c] = p.rank1_col ? p.rank1_col[c] : 0.f;
+          vec_s[512 + c] = p.dot_vec ? p.dot_vec[c] : 0.f;
+        }
       }
+      if constexpr (kEpi == kEpiFwdHead)     // views_output_linear transposed: [128 hidden units][4 outputs]
+        for (int c = t; c < 512; c += 128) vec_s[256 + c] = p.head_wout[c];
       asm volatile("bar.sync 1, 128;" ::: "memory");
     }
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++i) {
@@ -528,6 +540,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_linear_tc(const __grid_consta
         constexpr bool kBwd = kEpi == kEpiBwdPlain || kMask;
         float r1 = 0.f;
         if constexpr (kEpi == kEpiBwdMaskRank1) r1 = valid ? p.rank1_row[pg] * s_out : 0.f;
+        float hd[4] = {0.f, 0.f, 0.f, 0.f};     // kEpiFwdHead: the four views_output_linear logits of this row
         const uint32_t tm0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * 256;
         // eight columns: v[8 qq ..] -> one 16-byte chunk (index q) of the output box
         auto eight = [&](const uint32_t (&v)[32], int qq, int q, int sc, uint32_t orow, uint32_t mrow) {
@@ -535,7 +548,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_linear_tc(const __grid_consta
 #pragma unroll
           for (int j = 0; j < 8; ++j) o[j] = __uint_as_float(v[8 * qq + j]);
           const int col = sc * 64 + q * 8;
-          if constexpr (kEpi == kEpiFwdRelu || kEpi == kEpiFwdLinear) {
+          if constexpr (kEpi == kEpiFwdRelu || kEpi == kEpiFwdLinear || kEpi == kEpiFwdHead) {
             const float4 b0 = *reinterpret_cast<const float4*>(vec_s + col), b1 = *reinterpret_cast<const float4*>(vec_s + col + 4);
             o[0] += b0.x; o[1] += b0.y; o[2] += b0.z; o[3] += b0.w; o[4] += b1.x; o[5] += b1.y; o[6] += b1.z; o[7] += b1.w;
           }
@@ -554,6 +567,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_linear_tc(const __grid_consta
             for (int j = 0; j < 8; ++j) o[j] = fmaxf(o[j], 0.f);
             dot = fmaf(o[0], d0.x, dot); dot = fmaf(o[1], d0.y, dot); dot = fmaf(o[2], d0.z, dot); dot = fmaf(o[3], d0.w, dot);
             dot = fmaf(o[4], d1.x, dot); dot = fmaf(o[5], d1.y, dot); dot = fmaf(o[6], d1.z, dot); dot = fmaf(o[7], d1.w, dot);
+          }
+          if constexpr (kEpi == kEpiFwdHead) {   // views_output_linear reads the fp32 post-ReLU values (VipNeRF01.py:580-582)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              o[j] = fmaxf(o[j], 0.f);
+              const float4 w = *reinterpret_cast<const float4*>(vec_s + 256 + 4 * (col + j));
+              hd[0] = fmaf(o[j], w.x, hd[0]); hd[1] = fmaf(o[j], w.y, hd[1]); hd[2] = fmaf(o[j], w.z, hd[2]); hd[3] = fmaf(o[j], w.w, hd[3]);
+            }
           }
           uint32_t h[4];
 #pragma unroll
@@ -601,6 +622,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_linear_tc(const __grid_consta
             asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
                          ::"l"(&p.map_out), "r"(sc * 64), "r"(row0), "r"(out_s + 4096u * (sc & 1)) : "memory");
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        }
+        if constexpr (kEpi == kEpiFwdHead) {
+          if (valid) {
+            const float4 bo = *reinterpret_cast<const float4*>(p.head_bout);
+            if (p.head_rgb != nullptr) {
+              p.head_rgb[3 * pg + 0] = 1.f / (1.f + expf(-(hd[0] + bo.x)));
+              p.head_rgb[3 * pg + 1] = 1.f / (1.f + expf(-(hd[1] + bo.y)));
+              p.head_rgb[3 * pg + 2] = 1.f / (1.f + expf(-(hd[2] + bo.z)));
+            }
+            p.head_vis[pg * p.head_vis_stride] = 1.f / (1.f + expf(-(hd[3] + bo.w)));
           }
         }
       } else {
@@ -652,7 +684,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_linear_tc(const __grid_consta
           }
         }
       }
-      if (kDot && valid) p.dot_out[pg] = dot;
+      if (kDot && valid) {
+        if (p.dot_bias != nullptr) {   // the density head finished here: + bias, + noise, ReLU (VipNeRF01.py:546-553)
+          float pre = dot + *p.dot_bias;
+          if (p.dot_noise != nullptr) pre = pre + p.dot_noise[pg];
+          dot = fmaxf(pre, 0.f);
+        }
+        p.dot_out[pg] = dot;
+      }
       // this warp's TMEM reads of the accumulator are complete: hand it back to the MMA warp
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
@@ -714,6 +753,9 @@ cudaError_t launch_linear_tc(const LinearTcArgs& a, cudaStream_t s) {
   p.N = a.N; p.n_rows = a.n_rows; p.bias = a.bias; p.rank1_row = a.rank1_row; p.rank1_col = a.rank1_col;
   p.mask = a.mask; p.relu = a.relu ? 1 : 0;
   p.dot_vec = a.dot_vec; p.dot_out = a.dot_vec ? a.dot_out : nullptr;
+  p.dot_bias = a.dot_bias; p.dot_noise = a.dot_noise;
+  p.head_wout = a.head_wout; p.head_bout = a.head_bout; p.head_rgb = a.head_rgb; p.head_vis = a.head_vis;
+  p.head_vis_stride = a.head_vis_stride;
   p.scale_in = a.scale_in; p.scale_out = a.scale_out; p.amax_out = a.amax_out;
   if ((reinterpret_cast<uintptr_t>(a.out) & 15u) || ((a.ld_out * es_out) & 15) ||
       (a.mask && ((reinterpret_cast<uintptr_t>(a.mask) & 15u) || ((a.ld_mask * es_out) & 15))))
@@ -745,8 +787,12 @@ cudaError_t launch_linear_tc(const LinearTcArgs& a, cudaStream_t s) {
     // the fp16-output epilogue is specialised at compile time: the combinations the training chains use
     const bool scaled = a.scale_in != nullptr || a.scale_out != nullptr;
     const bool rank1 = a.rank1_row != nullptr && a.rank1_col != nullptr;
+    const bool head = a.head_wout != nullptr;
+    if (head && (a.N != 128 || !a.head_bout || !a.head_vis || dot || !a.relu || (reinterpret_cast<uintptr_t>(a.head_bout) & 15u)))
+      return cudaErrorInvalidValue;
     if (!scaled && a.bias != nullptr && !rank1 && a.mask == nullptr) {            // forward layers
-      if (a.relu && dot) VIPNERF_LAUNCH_LINEAR(true, true, true, kEpiFwdRelu);
+      if (head) VIPNERF_LAUNCH_LINEAR(false, true, true, kEpiFwdHead);
+      else if (a.relu && dot) VIPNERF_LAUNCH_LINEAR(true, true, true, kEpiFwdRelu);
       else if (a.relu) VIPNERF_LAUNCH_LINEAR(false, true, true, kEpiFwdRelu);
       else if (!dot) VIPNERF_LAUNCH_LINEAR(false, true, true, kEpiFwdLinear);
       else return cudaErrorInvalidValue;

@@ -165,6 +165,14 @@ struct LinearTcArgs {
   // optional rank-1 reduction of the OUTPUT rows: dot_out[p] = sum_n Y[p][n] * dot_vec[n] (the density head on h7,
   // VipNeRF01.py:546: it rides along in the epilogue that holds the row instead of re-reading 1 KiB per point)
   const float* dot_vec; float* dot_out;
+  // fp16 forward: the density head is finished where the row is held - dot_out[p] = relu(dot + *dot_bias + dot_noise[p])
+  // (VipNeRF01.py:546-553; dot_bias null = the raw dot product)
+  const float* dot_bias; const float* dot_noise;
+  // fp16 forward, views layer (N = 128, bias + ReLU): views_output_linear and the sigmoids ride along (:582-594) -
+  // logits[k] = sum_n out[p][n] * head_wout[n * 4 + k] + head_bout[k]; head_rgb[p][3] (null for a secondary view) and
+  // head_vis[p * head_vis_stride] receive the sigmoids
+  const float* head_wout; const float* head_bout;
+  float* head_rgb; float* head_vis; int head_vis_stride;
 };
 cudaError_t launch_linear_tc(const LinearTcArgs& a, cudaStream_t s);
 // out[m][n] = sum_p G[p][m] * H[p][n] for M <= 4 (G: M floats per row), N <= 256; gsum_dst[m] = sum_p G[p][m].

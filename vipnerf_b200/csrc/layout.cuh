@@ -73,7 +73,11 @@ constexpr int kFp32BwdFloats = kBwdOffEnc5 + 256 * 64;            // 589,824; th
 // ---- fp16 mirror (training, behind the backward region): the forward and backward regions once more as fp16, element
 // for element - the B operands of the fp16 training mode (VIPNERF_FLAG_TRAIN_F16, tcgen05 kind::f16)
 constexpr int kF16MirrorHalves = kFp32BigFloats + kFp32BwdFloats;
-constexpr size_t kFp32PackBytes = (size_t)kSmallBytes + (size_t)(kFp32BigFloats + kFp32BwdFloats) * 4 + (size_t)kF16MirrorHalves * 2;
+// ... followed by the 27 view-direction columns of views_linears.0 as an fp16 [128][64] matrix (columns 27..63 zero): the
+// second operand pair of the fp16 forward's views layer, whose A rows are the 64-column direction encodings
+constexpr int kF16ViewDirHalves = 128 * 64;
+constexpr size_t kFp32PackBytes = (size_t)kSmallBytes + (size_t)(kFp32BigFloats + kFp32BwdFloats) * 4 +
+                                  (size_t)(kF16MirrorHalves + kF16ViewDirHalves) * 2;
 
 // ---- tensor-core big region: "chunk images".  One chunk = ALL output rows (n) of a layer x 32 k-columns of
 // bf16 in the canonical K-major SWIZZLE_64B shared-memory layout tcgen05.mma reads (64-byte rows, 8-row / 512-byte

@@ -104,6 +104,16 @@ __global__ void k_pack_f16_mirror(const float* __restrict__ big, __half* __restr
   reinterpret_cast<unsigned short*>(mirror)[i] = r;
 }
 
+__global__ void k_pack_f16_viewdir(ParamPtrs pp, __half* __restrict__ dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= kF16ViewDirHalves) return;
+  const int n = i / 64, e = i % 64;
+  const float w = e < kEncView ? pp.p[16][n * (kWidth + kEncView) + kWidth + e] : 0.f;
+  unsigned short r;
+  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(r) : "f"(w));
+  reinterpret_cast<unsigned short*>(dst)[i] = r;
+}
+
 template <bool kSplit3, bool kHalf = false>
 __global__ void k_pack_tc(ParamPtrs pp, uint8_t* __restrict__ big) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;  // one bf16 element of the hi image set
@@ -151,8 +161,9 @@ cudaError_t launch_pack_weights(int precision, const float* const params_dev[24]
   if (precision == VIPNERF_PRECISION_FP32) {
     k_pack_fp32<<<(kFp32BigFloats + 255) / 256, 256, 0, s>>>(pp, reinterpret_cast<float*>(big));
     k_pack_fp32_bwd<<<(kFp32BwdFloats + 255) / 256, 256, 0, s>>>(pp, reinterpret_cast<float*>(big) + kFp32BigFloats);
-    k_pack_f16_mirror<<<(kF16MirrorHalves + 255) / 256, 256, 0, s>>>(
-        reinterpret_cast<const float*>(big), reinterpret_cast<__half*>(reinterpret_cast<float*>(big) + kFp32BigFloats + kFp32BwdFloats));
+    __half* mirror = reinterpret_cast<__half*>(reinterpret_cast<float*>(big) + kFp32BigFloats + kFp32BwdFloats);
+    k_pack_f16_mirror<<<(kF16MirrorHalves + 255) / 256, 256, 0, s>>>(reinterpret_cast<const float*>(big), mirror);
+    k_pack_f16_viewdir<<<(kF16ViewDirHalves + 255) / 256, 256, 0, s>>>(pp, mirror + kF16MirrorHalves);
   } else {
     const int n = kTcBigBytes / 2;
     if (precision == VIPNERF_PRECISION_BF16X3) k_pack_tc<true><<<(n + 255) / 256, 256, 0, s>>>(pp, big);

@@ -386,54 +386,113 @@ k_gemm_tn(const float* __restrict__ A, int lda, const float* __restrict__ B, int
   }
 }
 
-// dst[m * ldc + n] = sum_s partial[s][m][n], n < n_valid  (fixed summation order)
-__global__ void k_reduce_partials(const float* __restrict__ partial, int n_split, int M, int N, float* __restrict__ dst,
-                                  int ldc, int n_valid, const uint32_t* __restrict__ scale_def) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= M * n_valid) return;
-  // fp16 training mode: the partial sums carry the power-of-two scale of their gradient operand (exact to undo)
-  const float inv_scale = scale_def ? 1.f / grad_scale_from_amax(*scale_def) : 1.f;
-  const int m = i / n_valid, n = i % n_valid;
+// dst[m * ldc + n] = sum_s partial[s][m][n], n < n_valid  (fixed summation order: bit-reproducible).
+// A block owns 64 output elements; its four warp pairs each add every fourth partial tile (eight independent loads in
+// flight per thread, 128-byte rows per warp), and the four slice sums are combined in a fixed order through shared memory
+// - 4 x the parallelism of one thread per element, which left the 38 MB of a 256 x 256 product's partials latency-bound.
+__global__ void __launch_bounds__(256)
+k_reduce_partials(const float* __restrict__ partial, int n_split, int M, int N, float* __restrict__ dst,
+                  int ldc, int n_valid, const uint32_t* __restrict__ scale_def) {
+  __shared__ float slice_sum[4][64];
+  const int e = threadIdx.x & 63, slice = threadIdx.x >> 6;
+  const int i = blockIdx.x * 64 + e;
+  const bool valid = i < M * n_valid;
+  const int m = valid ? i / n_valid : 0, n = valid ? i % n_valid : 0;
   float s = 0.f;
   const size_t stride = (size_t)M * N;
   const float* src = partial + (size_t)m * N + n;
-  int k = 0;
-  for (; k + 8 <= n_split; k += 8) {   // eight independent loads in flight, summed in index order
-    float v[8];
+  if (valid) {
+    int k = slice;
+    for (; k + 28 < n_split; k += 32) {   // eight independent loads in flight, summed in index order
+      float v[8];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) v[u] = src[(size_t)(k + u) * stride];
+      for (int u = 0; u < 8; ++u) v[u] = src[(size_t)(k + 4 * u) * stride];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) s += v[u];
+      for (int u = 0; u < 8; ++u) s += v[u];
+    }
+    for (; k < n_split; k += 4) s += src[(size_t)k * stride];
   }
-  for (; k < n_split; ++k) s += src[(size_t)k * stride];
-  dst[(size_t)m * ldc + n] = s * inv_scale;
+  slice_sum[slice][e] = s;
+  __syncthreads();
+  if (slice == 0 && valid) {
+    // fp16 training mode: the partial sums carry the power-of-two scale of their gradient operand (exact to undo)
+    const float inv_scale = scale_def ? 1.f / grad_scale_from_amax(*scale_def) : 1.f;
+    dst[(size_t)m * ldc + n] = ((slice_sum[0][e] + slice_sum[1][e]) + (slice_sum[2][e] + slice_sum[3][e])) * inv_scale;
+  }
 }
 
 __device__ __forceinline__ float to_f32(float v) { return v; }
 __device__ __forceinline__ float to_f32(__half v) { return __half2float(v); }
 
+__device__ __forceinline__ float2 load_pair(const float* p) { return *reinterpret_cast<const float2*>(p); }
+__device__ __forceinline__ float2 load_pair(const __half* p) { return __half22float2(*reinterpret_cast<const __half2*>(p)); }
+
+// out[m][n] = sum_r G[r][m] * H[r][n], gsum[m] = sum_r G[r][m] for the 1- and 4-row heads: an HBM stream over H.
+// A thread owns two adjacent columns, so N / 2 threads cover a row and a 256-thread block works on 512 / N rows at a time
+// with eight row groups in flight (the r01 kernel - one row per block iteration, half of its threads idle at N = 128 -
+// ran at a tenth of the HBM roofline); the row groups' sums are combined in a fixed order through shared memory.
 template <int M, typename T>
 __global__ void __launch_bounds__(256)
 k_small_tn(const float* __restrict__ G, const T* __restrict__ H, int N, int64_t n_rows, int64_t rows_per_split,
            float* __restrict__ partial, float* __restrict__ gsum_partial) {
-  const int n = threadIdx.x;
+  __shared__ float red[256 * (2 * M + 1)];
+  const int tpr = N / 2;                         // threads per row
+  const int rpp = 256 / tpr;                     // rows per pass of the block
+  const int rg = threadIdx.x / tpr, c = threadIdx.x % tpr;
   const int64_t r_begin = (int64_t)blockIdx.x * rows_per_split;
   const int64_t r_end = min(n_rows, r_begin + rows_per_split);
-  float acc[M];
+  float acc[M][2];
 #pragma unroll
-  for (int m = 0; m < M; ++m) acc[m] = 0.f;
-  float gs = 0.f;
-  if (n < N) {
-#pragma unroll 4
-    for (int64_t r = r_begin; r < r_end; ++r) {
-      const float hval = to_f32(H[r * N + n]);
+  for (int m = 0; m < M; ++m) acc[m][0] = acc[m][1] = 0.f;
+  float gs = 0.f;                                // thread c < M of every row group sums G's column c
+  constexpr int kU = 8;
+  int64_t r = r_begin + rg;
+  for (; r + (kU - 1) * rpp < r_end; r += kU * rpp) {
+    float2 hv[kU];
+    float g[kU][M];
+    float gc[kU];
 #pragma unroll
-      for (int m = 0; m < M; ++m) acc[m] = fmaf(G[r * M + m], hval, acc[m]);
-      if (n < M) gs += G[r * M + n];
+    for (int u = 0; u < kU; ++u) {
+      const int64_t rr = r + u * rpp;
+      hv[u] = load_pair(H + rr * N + 2 * c);
+#pragma unroll
+      for (int m = 0; m < M; ++m) g[u][m] = G[rr * M + m];
+      gc[u] = c < M ? G[rr * M + c] : 0.f;
     }
 #pragma unroll
-    for (int m = 0; m < M; ++m) partial[((size_t)blockIdx.x * M + m) * N + n] = acc[m];
-    if (n < M) gsum_partial[(size_t)blockIdx.x * M + n] = gs;
+    for (int u = 0; u < kU; ++u) {
+#pragma unroll
+      for (int m = 0; m < M; ++m) { acc[m][0] = fmaf(g[u][m], hv[u].x, acc[m][0]); acc[m][1] = fmaf(g[u][m], hv[u].y, acc[m][1]); }
+      gs += gc[u];
+    }
+  }
+  for (; r < r_end; r += rpp) {
+    const float2 h2 = load_pair(H + r * N + 2 * c);
+#pragma unroll
+    for (int m = 0; m < M; ++m) { const float gv = G[r * M + m]; acc[m][0] = fmaf(gv, h2.x, acc[m][0]); acc[m][1] = fmaf(gv, h2.y, acc[m][1]); }
+    if (c < M) gs += G[r * M + c];
+  }
+  // combine the row groups in index order
+  float* mine = red + threadIdx.x * (2 * M + 1);
+#pragma unroll
+  for (int m = 0; m < M; ++m) { mine[2 * m] = acc[m][0]; mine[2 * m + 1] = acc[m][1]; }
+  mine[2 * M] = gs;
+  __syncthreads();
+  if (rg == 0) {
+    float tot[2 * M + 1];
+#pragma unroll
+    for (int j = 0; j < 2 * M + 1; ++j) tot[j] = 0.f;
+    for (int q = 0; q < rpp; ++q) {
+      const float* other = red + (q * tpr + c) * (2 * M + 1);
+#pragma unroll
+      for (int j = 0; j < 2 * M + 1; ++j) tot[j] += other[j];
+    }
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+      partial[((size_t)blockIdx.x * M + m) * N + 2 * c] = tot[2 * m];
+      partial[((size_t)blockIdx.x * M + m) * N + 2 * c + 1] = tot[2 * m + 1];
+    }
+    if (c < M) gsum_partial[(size_t)blockIdx.x * M + c] = tot[2 * M];
   }
 }
 
@@ -591,52 +650,82 @@ k_heads_fwd(int64_t n_points, int nviews, const float* __restrict__ small, const
 
 // k_heads_bwd: the head part of the backward (the first phase of k_mlp_bwd_fp32 as a kernel of its own): per view
 // g_pre[p][view][n] = relu'(hv) * sum_k dlogit[p][view][k] * W_out[k][n]; their sum over views is the gradient of the
-// feature product.  64 points per block, thread = hidden unit n.
+// feature product.
+__device__ __forceinline__ void load4(const float* p, float (&v)[4]) {
+  const float4 t = *reinterpret_cast<const float4*>(p);
+  v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+__device__ __forceinline__ void load4(const __half* p, float (&v)[4]) {
+  const uint2 t = *reinterpret_cast<const uint2*>(p);
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&t.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&t.y));
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+__device__ __forceinline__ void store4_sat(float* p, const float (&v)[4]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+__device__ __forceinline__ void store4_sat(__half* p, const float (&v)[4]) {   // saturating at +-65504
+  uint32_t lo, hi;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(v[1]), "f"(v[0]));
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(v[3]), "f"(v[2]));
+  *reinterpret_cast<uint2*>(p) = make_uint2(lo, hi);
+}
+
+// One warp per (point, view) row: a lane owns four adjacent hidden units, so every load and store of a warp is one full
+// 256- / 512-byte row (the r01 kernel moved 2 - 4 bytes per lane and instruction and ran at a third of the HBM
+// roofline).  kPts points per warp are in flight at once.
 template <typename T>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 k_heads_bwd(int64_t n_points, int nviews, const float* __restrict__ small, const float* __restrict__ dlogit,
             const T* __restrict__ hv, T* __restrict__ dhv, T* __restrict__ dacc9, const uint32_t* __restrict__ scale_def,
             uint32_t* __restrict__ amax_out) {
-  extern __shared__ __align__(16) float dl_s[];   // [64][nviews][4]
-  const int64_t p0 = (int64_t)blockIdx.x * 64;
-  const int n = threadIdx.x;
+  constexpr int kPts = 4;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // fp16 mode: both outputs carry the power-of-two scale defined by max |dlogit| (grad_scale_from_amax)
   const float scale = scale_def ? grad_scale_from_amax(*scale_def) : 1.f;
-  for (int t = threadIdx.x; t < 64 * nviews * 4; t += blockDim.x) {
-    const int64_t e = p0 * nviews * 4 + t;
-    dl_s[t] = e < n_points * nviews * 4 ? dlogit[e] * scale : 0.f;
-  }
-  __syncthreads();
-  const float4 wo = *reinterpret_cast<const float4*>(small + kOffWOut + n * 4);
-  const int n_valid = (int)min((int64_t)64, n_points - p0);
-  float accp[64];
+  float wo[4][4];          // views_output_linear.weight[k][4 lane + j] (small: transposed [128][4])
 #pragma unroll
-  for (int p = 0; p < 64; ++p) accp[p] = 0.f;
-  for (int v = 0; v < nviews; ++v) {
-    float hvv[64];
-#pragma unroll
-    for (int p = 0; p < 64; ++p) hvv[p] = to_f32(hv[((p0 + min(p, n_valid - 1)) * nviews + v) * 128 + n]);
-#pragma unroll
-    for (int p = 0; p < 64; ++p) {
-      const float4 d4 = *reinterpret_cast<const float4*>(dl_s + (p * nviews + v) * 4);
-      const float gsum = fmaf(d4.x, wo.x, fmaf(d4.y, wo.y, fmaf(d4.z, wo.z, d4.w * wo.w)));
-      hvv[p] = hvv[p] > 0.f ? gsum : 0.f;
-      accp[p] += hvv[p];
-    }
-#pragma unroll
-    for (int p = 0; p < 64; ++p)
-      if (p < n_valid) store_sat(dhv + ((p0 + p) * nviews + v) * 128 + n, hvv[p]);
+  for (int j = 0; j < 4; ++j) {
+    const float4 w = *reinterpret_cast<const float4*>(small + kOffWOut + (4 * lane + j) * 4);
+    wo[j][0] = w.x * scale; wo[j][1] = w.y * scale; wo[j][2] = w.z * scale; wo[j][3] = w.w * scale;   // exact: a power of two
   }
   float amax = 0.f;
+  const int64_t p0 = ((int64_t)blockIdx.x * 8 + warp) * kPts;
+  if (p0 < n_points) {
+    float acc[kPts][4];
 #pragma unroll
-  for (int p = 0; p < 64; ++p)
-    if (p < n_valid) {
-      store_sat(dacc9 + (p0 + p) * 128 + n, accp[p]);
-      amax = fmaxf(amax, fabsf(accp[p]));
+    for (int i = 0; i < kPts; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+    for (int v = 0; v < nviews; ++v) {
+      float h[kPts][4];
+      float4 d4[kPts];
+#pragma unroll
+      for (int i = 0; i < kPts; ++i) {
+        const int64_t row = (min(p0 + i, n_points - 1)) * nviews + v;
+        load4(hv + row * 128 + 4 * lane, h[i]);
+        d4[i] = *reinterpret_cast<const float4*>(dlogit + row * 4);
+      }
+#pragma unroll
+      for (int i = 0; i < kPts; ++i) {
+        float g[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float gsum = fmaf(d4[i].x, wo[j][0], fmaf(d4[i].y, wo[j][1], fmaf(d4[i].z, wo[j][2], d4[i].w * wo[j][3])));
+          g[j] = h[i][j] > 0.f ? gsum : 0.f;
+          acc[i][j] += g[j];
+        }
+        if (p0 + i < n_points) store4_sat(dhv + ((p0 + i) * nviews + v) * 128 + 4 * lane, g);
+      }
     }
+#pragma unroll
+    for (int i = 0; i < kPts; ++i)
+      if (p0 + i < n_points) {
+        store4_sat(dacc9 + (p0 + i) * 128 + 4 * lane, acc[i]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) amax = fmaxf(amax, fabsf(acc[i][j]));
+      }
+  }
   if (amax_out != nullptr) {   // un-scaled maximum of what feeds the chain's first product
     const uint32_t m = __reduce_max_sync(0xffffffffu, __float_as_uint(amax / scale));
-    if ((threadIdx.x & 31) == 0 && m != 0u) atomicMax(amax_out, m);
+    if (lane == 0 && m != 0u) atomicMax(amax_out, m);
   }
 }
 
@@ -682,11 +771,11 @@ cudaError_t launch_heads_fwd(int64_t n_points, int nviews, const void* packed, c
 cudaError_t launch_heads_bwd(int64_t n_points, int nviews, const void* packed, const float* dlogit, const void* hv,
                              void* dhv, void* dacc9, cudaStream_t s, bool half, const uint32_t* scale_def, uint32_t* amax_out) {
   if (n_points == 0) return cudaSuccess;
-  const unsigned grid = (unsigned)((n_points + 63) / 64);
-  const size_t smem = 64 * nviews * 4 * sizeof(float);
+  const unsigned grid = (unsigned)((n_points + 31) / 32);      // 8 warps x 4 points
+  const size_t smem = 0;
   const float* small = reinterpret_cast<const float*>(packed);
-  if (half) k_heads_bwd<__half><<<grid, 128, smem, s>>>(n_points, nviews, small, dlogit, static_cast<const __half*>(hv), static_cast<__half*>(dhv), static_cast<__half*>(dacc9), scale_def, amax_out);
-  else k_heads_bwd<float><<<grid, 128, smem, s>>>(n_points, nviews, small, dlogit, static_cast<const float*>(hv), static_cast<float*>(dhv), static_cast<float*>(dacc9), scale_def, amax_out);
+  if (half) k_heads_bwd<__half><<<grid, 256, smem, s>>>(n_points, nviews, small, dlogit, static_cast<const __half*>(hv), static_cast<__half*>(dhv), static_cast<__half*>(dacc9), scale_def, amax_out);
+  else k_heads_bwd<float><<<grid, 256, smem, s>>>(n_points, nviews, small, dlogit, static_cast<const float*>(hv), static_cast<float*>(dhv), static_cast<float*>(dacc9), scale_def, amax_out);
   return cudaGetLastError();
 }
 
@@ -815,14 +904,14 @@ cudaError_t launch_gemm_tn(const float* A, int lda, int M, const float* B, int l
 #undef VIPNERF_LAUNCH_GEMM
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  k_reduce_partials<<<(M * n_valid + 255) / 256, 256, 0, s>>>(partial, (int)n_split, M, N, dst, ldc, n_valid, nullptr);
-  if (bias_dst) k_reduce_partials<<<(M + 255) / 256, 256, 0, s>>>(bias_partial, (int)n_split, M, 1, bias_dst, 1, 1, nullptr);
+  k_reduce_partials<<<(M * n_valid + 63) / 64, 256, 0, s>>>(partial, (int)n_split, M, N, dst, ldc, n_valid, nullptr);
+  if (bias_dst) k_reduce_partials<<<(M + 63) / 64, 256, 0, s>>>(bias_partial, (int)n_split, M, 1, bias_dst, 1, 1, nullptr);
   return cudaGetLastError();
 }
 
 cudaError_t launch_reduce_partials(const float* partial, int n_split, int M, int N, float* dst, int ldc, int n_valid,
                                    cudaStream_t s, const uint32_t* scale_def) {
-  k_reduce_partials<<<(M * n_valid + 255) / 256, 256, 0, s>>>(partial, n_split, M, N, dst, ldc, n_valid, scale_def);
+  k_reduce_partials<<<(M * n_valid + 63) / 64, 256, 0, s>>>(partial, n_split, M, N, dst, ldc, n_valid, scale_def);
   return cudaGetLastError();
 }
 
@@ -856,7 +945,7 @@ cudaError_t launch_colsum(const float* A, int lda, int M, int64_t n_rows, float*
 
 cudaError_t launch_small_tn(const float* G, int M, const void* H, int N, int64_t n_rows, float* dst, float* gsum_dst,
                             float* partial, cudaStream_t s, bool half_h) {
-  if ((M != 1 && M != 4) || N < 4 || N > 256) return cudaErrorInvalidValue;
+  if ((M != 1 && M != 4) || (N != 128 && N != 256)) return cudaErrorInvalidValue;   // a row = 64 or 128 column pairs
   int64_t n_split = 4 * 148;
   const int64_t max_by_rows = (n_rows + 63) / 64;
   if (n_split > max_by_rows) n_split = max_by_rows;
@@ -871,7 +960,7 @@ cudaError_t launch_small_tn(const float* G, int M, const void* H, int N, int64_t
   else k_small_tn<4, __half><<<(unsigned)n_split, 256, 0, s>>>(G, Hh, N, n_rows, rows_per_split, partial, gsum_partial);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  k_reduce_partials<<<(M * N + 255) / 256, 256, 0, s>>>(partial, (int)n_split, M, N, dst, N, N, nullptr);
+  k_reduce_partials<<<(M * N + 63) / 64, 256, 0, s>>>(partial, (int)n_split, M, N, dst, N, N, nullptr);
   if (gsum_dst) k_reduce_partials<<<1, 256, 0, s>>>(gsum_partial, (int)n_split, M, 1, gsum_dst, 1, 1, nullptr);
   return cudaGetLastError();
 }
