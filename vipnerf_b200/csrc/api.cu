@@ -145,7 +145,7 @@ PassGradPtrs to_grads(const vipnerf_pass_out* o) {
 }
 
 // Activations the training forward keeps per sample set (floats; P points, nv = 1 + V views): kernels.h MlpSave
-struct SavedPass { size_t enc, h, feat, hv, pev, end; };
+struct SavedPass { size_t enc, h, feat, hv, pev, bits, end; };
 struct SavedLayout { SavedPass coarse, fine; size_t total; };
 
 bool train_f16(const vipnerf_cfg* cfg) { return (cfg->flags & VIPNERF_FLAG_TRAIN_F16) != 0; }
@@ -160,6 +160,7 @@ SavedLayout carve_saved(const vipnerf_cfg* cfg, int64_t n_rays) {
   auto pass = [&](size_t P) {
     SavedPass s{};
     s.enc = take(P * 64); s.h = take(P * 256 * 8); s.feat = take(P * 256); s.hv = take(P * nv * 128); s.pev = take(P * nv * (es == 2 ? 64 : 32));
+    s.bits = es == 2 ? take(P * 8 * 8 * 2) : off;   // fp16 mode: ReLU masks of pts_linears.0..7 as bits, [8][P][8] words
     s.end = off;
     return s;
   };
@@ -227,7 +228,7 @@ ElemPtr weights_in_out(const void* packed, bool half) {   // forward images Wt[i
 }
 
 // what the forward keeps (kernels.h MlpSave) with the element type of the mode
-struct SavePtrs { const float* noise; uint8_t *enc, *h, *feat, *hv, *pev; };
+struct SavePtrs { const float* noise; uint8_t *enc, *h, *feat, *hv, *pev; uint32_t* bits; };
 
 // MLP.forward of one sample set on the tensor cores: encodings -> ten products -> heads; fills the saved activations.
 // half = fp16 arrays and kind::f16 products, else fp32 arrays read as tf32.
@@ -253,6 +254,7 @@ cudaError_t mlp_forward_tc(const RayPtrs& rp, const RenderFlags& fl, int64_t n_r
     }
     a.bias = small + kOffBias + l * 256;
     a.relu = true;
+    if (half) a.relu_bits_out = sv.bits + (size_t)l * P * 8;
     if (l == 7) {   // the density head rides along: the raw dot product (finished by k_heads_fwd), or all of it in the fp16 mode
       a.dot_vec = small + kOffWSigma; a.dot_out = sigma;
       if (half) { a.dot_bias = small + kOffBSigma; a.dot_noise = sv.noise; }
@@ -302,6 +304,7 @@ struct BwdPtrs {
   int64_t n_points; int nviews;
   const float *dsig, *dlogit;
   const uint8_t *h, *hv;
+  const uint32_t* bits;   // fp16 mode: ReLU masks as bits [8][P][8]
   uint8_t *dpre, *dfeat, *dacc9, *dhv;
   uint32_t* amax;     // kAmaxSlots slots of this sample set (fp16 mode), zeroed here
 };
@@ -324,13 +327,13 @@ cudaError_t mlp_backward_tc(const BwdPtrs& a, const void* packed, cudaStream_t s
   if ((e = launch_linear_tc(g, s)) != cudaSuccess) return e;
   g = linear_args(a.dfeat, 256, 256, wio.at(fp32_layer_offset(8)), 256, 256, P, a.dpre + 7 * PL, 256, half);
   g.rank1_row = a.dsig; g.rank1_col = small + kOffWSigma;
-  g.mask = a.h + 7 * PL; g.ld_mask = 256;
+  if (half) g.relu_bits = a.bits + (size_t)7 * P * 8; else { g.mask = a.h + 7 * PL; g.ld_mask = 256; }
   if (half) { g.scale_in = am + kSlotAcc9; g.scale_out = am + dpre_slot(7); g.amax_out = am + dpre_slot(6); }
   if ((e = launch_linear_tc(g, s)) != cudaSuccess) return e;
   for (int l = 7; l >= 1; --l) {
     g = linear_args(a.dpre + l * PL, 256, 256, wio.at(fp32_layer_offset(l) + (l == 5 ? 64 * 256 : 0)), 256, 256, P,
                     a.dpre + (l - 1) * PL, 256, half);
-    g.mask = a.h + (l - 1) * PL; g.ld_mask = 256;
+    if (half) g.relu_bits = a.bits + (size_t)(l - 1) * P * 8; else { g.mask = a.h + (l - 1) * PL; g.ld_mask = 256; }
     if (half) { g.scale_in = am + dpre_slot(l); g.scale_out = am + dpre_slot(l - 1); g.amax_out = l >= 2 ? am + dpre_slot(l - 2) : nullptr; }
     if ((e = launch_linear_tc(g, s)) != cudaSuccess) return e;
   }
@@ -620,7 +623,8 @@ int vipnerf_train_forward(const vipnerf_cfg* cfg, const vipnerf_rays* rays, int6
       // the feature product of the views layer (fp32 [P][128]) lives in the backward's (idle) scratch until the heads have
       // consumed it
       float* acc9 = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + carve_bwd(cfg, n_rays).dpre);
-      const SavePtrs sp8{ms.noise, sv + sp.enc, sv + sp.h, sv + sp.feat, sv + sp.hv, sv + sp.pev};
+      const SavePtrs sp8{ms.noise, sv + sp.enc, sv + sp.h, sv + sp.feat, sv + sp.hv, sv + sp.pev,
+                         reinterpret_cast<uint32_t*>(sv + sp.bits)};
       e = mlp_forward_tc(rp, fl, n_rays, S, o.z_vals, pass ? packed_fine : packed_coarse, sp8, acc9, o.raw_sigma, o.raw_rgb,
                          o.raw_visibility, vis2, s, train_f16(cfg));
     } else {
@@ -750,6 +754,7 @@ int vipnerf_train_backward_fused(const vipnerf_cfg* cfg, const vipnerf_rays* ray
     if (tf32 || f16) {
       BwdPtrs a{};
       a.n_points = P; a.nviews = nv; a.dsig = dsig; a.dlogit = dlogit; a.h = h; a.hv = hv;
+      a.bits = reinterpret_cast<const uint32_t*>(sv + sp.bits);
       a.dpre = dpre; a.dfeat = dfeat; a.dacc9 = dacc9; a.dhv = dhv; a.amax = amax;
       e = mlp_backward_tc(a, pass ? packed_fine : packed_coarse, s, f16);
     } else {

@@ -360,6 +360,8 @@ struct LinearTcParams {
   const float* rank1_row;
   const float* rank1_col;
   const void* mask;
+  const uint32_t* relu_bits;     // fp16 backward: ReLU masks as bits, [rows][8] words (bit c % 32 of word c / 32 = unit c was active)
+  uint32_t* relu_bits_out;       // fp16 forward: where kEpiFwdRelu leaves them
   int relu;
   const float* dot_vec;
   float* dot_out;
@@ -517,6 +519,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_linear_tc(const __grid_consta
       const int buf = i & 1;
       const int64_t pg = (int64_t)tile * kLinRows + quarter * 32 + lane;
       const bool valid = pg < p.n_rows;
+      uint4 mw0 = make_uint4(0u, 0u, 0u, 0u), mw1 = mw0;   // fp16 backward: this row's 256 ReLU-mask bits (32 bytes; the
+      if constexpr (kOutHalf && (kEpi == kEpiBwdMask || kEpi == kEpiBwdMaskRank1)) {   // loads fly while the MMAs finish)
+        if (valid) {
+          mw0 = *reinterpret_cast<const uint4*>(p.relu_bits + pg * 8);
+          mw1 = *reinterpret_cast<const uint4*>(p.relu_bits + pg * 8 + 4);
+        }
+      }
       mbar_wait(acc_full(buf), (i >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       // Epilogue through shared memory and the TMA engine.  A lane owns one accumulator row, so direct global accesses
@@ -543,7 +552,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_linear_tc(const __grid_consta
         float hd[4] = {0.f, 0.f, 0.f, 0.f};     // kEpiFwdHead: the four views_output_linear logits of this row
         const uint32_t tm0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * 256;
         // eight columns: v[8 qq ..] -> one 16-byte chunk (index q) of the output box
-        auto eight = [&](const uint32_t (&v)[32], int qq, int q, int sc, uint32_t orow, uint32_t mrow) {
+        uint32_t wb0 = 0u, wb1 = 0u;    // mask bits of the current box: columns [0,32) and [32,64) (read backward, written forward)
+        auto eight = [&](const uint32_t (&v)[32], int qq, int q, int sc, uint32_t orow) {
           float o[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) o[j] = __uint_as_float(v[8 * qq + j]);
@@ -560,6 +570,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_linear_tc(const __grid_consta
             const float4 u0 = *reinterpret_cast<const float4*>(vec_s + 256 + col), u1 = *reinterpret_cast<const float4*>(vec_s + 256 + col + 4);
             o[0] = fmaf(r1, u0.x, o[0]); o[1] = fmaf(r1, u0.y, o[1]); o[2] = fmaf(r1, u0.z, o[2]); o[3] = fmaf(r1, u0.w, o[3]);
             o[4] = fmaf(r1, u1.x, o[4]); o[5] = fmaf(r1, u1.y, o[5]); o[6] = fmaf(r1, u1.z, o[6]); o[7] = fmaf(r1, u1.w, o[7]);
+          }
+          if constexpr (kEpi == kEpiFwdRelu) {   // ReLU mask for the backward chain: one bit per unit
+            uint32_t byte = 0u;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) byte |= (o[j] > 0.f ? 1u : 0u) << j;
+            if (q < 4) wb0 |= byte << (8 * (q & 3)); else wb1 |= byte << (8 * (q & 3));
+          }
+          if constexpr (kMask) {                 // the unit was active in the forward iff its bit is set
+            const uint32_t byte = (q < 4 ? wb0 : wb1) >> (8 * (q & 3));
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (!((byte >> j) & 1u)) o[j] = 0.f;
           }
           if constexpr (kDot) {   // the density head reads the fp32 post-ReLU values
             const float4 d0 = *reinterpret_cast<const float4*>(vec_s + 512 + col), d1 = *reinterpret_cast<const float4*>(vec_s + 512 + col + 4);
@@ -581,13 +603,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_linear_tc(const __grid_consta
           for (int j = 0; j < 4; ++j)
             h[j] = kEpi == kEpiFwdRelu ? pack_half2_relu_sat(o[2 * j], o[2 * j + 1]) : pack_half2_sat(o[2 * j], o[2 * j + 1]);
           const uint32_t sw = (uint32_t)((q ^ (lane & 7)) << 4);      // 128-byte swizzle: 16-byte chunk index ^ (row % 8)
-          if constexpr (kMask) {   // saved post-ReLU activations (fp16, never negative): the unit was active iff its value is > 0
-            uint32_t m[4];
-            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(m[0]), "=r"(m[1]), "=r"(m[2]), "=r"(m[3]) : "r"(mrow + sw));
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              h[j] &= __hgt2_mask(*reinterpret_cast<const __half2*>(&m[j]), __half2(__ushort_as_half(0), __ushort_as_half(0)));
-          }
           if constexpr (kBwd) {    // maximum of |stored value|: fp16 bit patterns of non-negative values order like integers
             amax16 = __vimax3_u16x2(amax16, h[0] & 0x7fff7fffu, h[1] & 0x7fff7fffu);
             amax16 = __vimax3_u16x2(amax16, h[2] & 0x7fff7fffu, h[3] & 0x7fff7fffu);
@@ -599,23 +614,26 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_linear_tc(const __grid_consta
         uint32_t va[32], vb[32];
         tmem_ld32(tm0, va);
 #pragma unroll 1
-        for (int sc = 0; sc < n_sc; ++sc, ++mask_n) {
+        for (int sc = 0; sc < n_sc; ++sc) {
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           tmem_ld32(tm0 + sc * 64 + 32, vb);
-          if (kMask && lane == 0 && sc + 1 < n_sc) {                    // next box of the mask (its buffer was read at sc - 1)
-            mbar_expect_tx(mfull0 + 8u * ((mask_n + 1) & 1), 4096);
-            tma_load_2d(msk_s + 4096u * ((mask_n + 1) & 1), &p.map_mask, (sc + 1) * 64, row0, mfull0 + 8u * ((mask_n + 1) & 1));
-          }
           if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the store issued two boxes ago has read its box
           __syncwarp();
-          if (kMask) mbar_wait(mfull0 + 8u * (mask_n & 1), (mask_n >> 1) & 1);
-          const uint32_t orow = out_s + 4096u * (sc & 1) + lane * 128, mrow = msk_s + 4096u * (mask_n & 1) + lane * 128;
+          if constexpr (kMask) {          // words 2 sc, 2 sc + 1 of the row's mask
+            wb0 = sc == 0 ? mw0.x : (sc == 1 ? mw0.z : (sc == 2 ? mw1.x : mw1.z));
+            wb1 = sc == 0 ? mw0.y : (sc == 1 ? mw0.w : (sc == 2 ? mw1.y : mw1.w));
+          }
+          if constexpr (kEpi == kEpiFwdRelu) wb0 = wb1 = 0u;
+          const uint32_t orow = out_s + 4096u * (sc & 1) + lane * 128;
 #pragma unroll
-          for (int q = 0; q < 4; ++q) eight(va, q, q, sc, orow, mrow);
+          for (int q = 0; q < 4; ++q) eight(va, q, q, sc, orow);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           if (sc + 1 < n_sc) tmem_ld32(tm0 + (sc + 1) * 64, va);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) eight(vb, q, q + 4, sc, orow, mrow);
+          for (int q = 0; q < 4; ++q) eight(vb, q, q + 4, sc, orow);
+          if constexpr (kEpi == kEpiFwdRelu) {
+            if (valid && p.relu_bits_out != nullptr) *reinterpret_cast<uint2*>(p.relu_bits_out + pg * 8 + 2 * sc) = make_uint2(wb0, wb1);
+          }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
           if (lane == 0) {
@@ -737,7 +755,7 @@ cudaError_t launch_linear_tc(const LinearTcArgs& a, cudaStream_t s) {
   const int kq = a.half_in ? 64 : 32;     // reduction elements per 128-byte box row
   if ((a.N != 128 && a.N != 256) || a.k[0] < kq || (a.k[0] % kq) || (a.k[1] % kq) || a.k[1] < 0) return cudaErrorInvalidValue;
   if (a.half_out && !a.half_in) return cudaErrorInvalidValue;       // fp16 outputs exist in the fp16 mode only
-  if (a.mask != nullptr && a.half_in != a.half_out) return cudaErrorInvalidValue;
+  if (a.mask != nullptr && a.half_in) return cudaErrorInvalidValue;    // fp16 chains take their ReLU masks as bits (relu_bits)
   const int es_in = a.half_in ? 2 : 4, es_out = a.half_out ? 2 : 4;
   LinearTcParams p{};
   cudaError_t e;
@@ -752,6 +770,9 @@ cudaError_t launch_linear_tc(const LinearTcArgs& a, cudaStream_t s) {
   if (a.k[1] == 0) { p.map_a[1] = p.map_a[0]; p.map_b[1] = p.map_b[0]; }
   p.N = a.N; p.n_rows = a.n_rows; p.bias = a.bias; p.rank1_row = a.rank1_row; p.rank1_col = a.rank1_col;
   p.mask = a.mask; p.relu = a.relu ? 1 : 0;
+  p.relu_bits = a.relu_bits; p.relu_bits_out = a.relu_bits_out;
+  if ((reinterpret_cast<uintptr_t>(a.relu_bits) & 15u) || (reinterpret_cast<uintptr_t>(a.relu_bits_out) & 7u)) return cudaErrorInvalidValue;
+  if ((a.relu_bits || a.relu_bits_out) && (!a.half_out || a.N != 256)) return cudaErrorInvalidValue;
   p.dot_vec = a.dot_vec; p.dot_out = a.dot_vec ? a.dot_out : nullptr;
   p.dot_bias = a.dot_bias; p.dot_noise = a.dot_noise;
   p.head_wout = a.head_wout; p.head_bout = a.head_bout; p.head_rgb = a.head_rgb; p.head_vis = a.head_vis;
@@ -797,8 +818,8 @@ cudaError_t launch_linear_tc(const LinearTcArgs& a, cudaStream_t s) {
       else if (!dot) VIPNERF_LAUNCH_LINEAR(false, true, true, kEpiFwdLinear);
       else return cudaErrorInvalidValue;
     } else if (scaled && a.bias == nullptr && !a.relu && !dot) {                  // backward-data layers
-      if (a.mask != nullptr && rank1) VIPNERF_LAUNCH_LINEAR(false, true, true, kEpiBwdMaskRank1);
-      else if (a.mask != nullptr) VIPNERF_LAUNCH_LINEAR(false, true, true, kEpiBwdMask);
+      if (a.relu_bits != nullptr && rank1) VIPNERF_LAUNCH_LINEAR(false, true, true, kEpiBwdMaskRank1);
+      else if (a.relu_bits != nullptr) VIPNERF_LAUNCH_LINEAR(false, true, true, kEpiBwdMask);
       else if (!rank1) VIPNERF_LAUNCH_LINEAR(false, true, true, kEpiBwdPlain);
       else return cudaErrorInvalidValue;
     } else {

@@ -153,6 +153,9 @@ struct LinearTcArgs {
   const float* rank1_row;
   const float* rank1_col;
   const void* mask; int ld_mask;
+  // fp16 chains: the ReLU masks travel as bits, [rows][8] words for a 256-wide layer (32 bytes per row instead of the 512
+  // bytes of the saved activation): written by a forward layer (bias + ReLU), read by the backward layer through it
+  const uint32_t* relu_bits; uint32_t* relu_bits_out;
   bool relu;
   void* out; int ld_out;
   bool half_in;     // x, w (and mask) are fp16

@@ -672,14 +672,16 @@ __device__ __forceinline__ void store4_sat(__half* p, const float (&v)[4]) {   /
 
 // One warp per (point, view) row: a lane owns four adjacent hidden units, so every load and store of a warp is one full
 // 256- / 512-byte row (the r01 kernel moved 2 - 4 bytes per lane and instruction and ran at a third of the HBM
-// roofline).  kPts points per warp are in flight at once.
-template <typename T>
-__global__ void __launch_bounds__(256)
-k_heads_bwd(int64_t n_points, int nviews, const float* __restrict__ small, const float* __restrict__ dlogit,
+// roofline).  A warp walks point pairs with all 2 * NV rows of a pair loaded before the arithmetic; NV = 0 = any count.
+template <typename T, int NV>
+__global__ void __launch_bounds__(256, 3)
+k_heads_bwd(int64_t n_points, int nviews_rt, const float* __restrict__ small, const float* __restrict__ dlogit,
             const T* __restrict__ hv, T* __restrict__ dhv, T* __restrict__ dacc9, const uint32_t* __restrict__ scale_def,
             uint32_t* __restrict__ amax_out) {
-  constexpr int kPts = 4;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int kPts = 2;
+  constexpr int kMaxV = NV > 0 ? NV : 1;
+  const int nviews = NV > 0 ? NV : nviews_rt;
+  const int lane = threadIdx.x & 31;
   // fp16 mode: both outputs carry the power-of-two scale defined by max |dlogit| (grad_scale_from_amax)
   const float scale = scale_def ? grad_scale_from_amax(*scale_def) : 1.f;
   float wo[4][4];          // views_output_linear.weight[k][4 lane + j] (small: transposed [128][4])
@@ -689,31 +691,45 @@ k_heads_bwd(int64_t n_points, int nviews, const float* __restrict__ small, const
     wo[j][0] = w.x * scale; wo[j][1] = w.y * scale; wo[j][2] = w.z * scale; wo[j][3] = w.w * scale;   // exact: a power of two
   }
   float amax = 0.f;
-  const int64_t p0 = ((int64_t)blockIdx.x * 8 + warp) * kPts;
-  if (p0 < n_points) {
+  const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t p0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * kPts; p0 < n_points; p0 += n_warps * kPts) {
     float acc[kPts][4];
 #pragma unroll
     for (int i = 0; i < kPts; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
-    for (int v = 0; v < nviews; ++v) {
-      float h[kPts][4];
-      float4 d4[kPts];
+    auto one_view = [&](const float (&h)[4], const float4& d, int i, int v) {
+      float g[4];
 #pragma unroll
-      for (int i = 0; i < kPts; ++i) {
-        const int64_t row = (min(p0 + i, n_points - 1)) * nviews + v;
-        load4(hv + row * 128 + 4 * lane, h[i]);
-        d4[i] = *reinterpret_cast<const float4*>(dlogit + row * 4);
+      for (int j = 0; j < 4; ++j) {
+        const float gsum = fmaf(d.x, wo[j][0], fmaf(d.y, wo[j][1], fmaf(d.z, wo[j][2], d.w * wo[j][3])));
+        g[j] = h[j] > 0.f ? gsum : 0.f;
+        acc[i][j] += g[j];
       }
+      if (p0 + i < n_points) store4_sat(dhv + ((p0 + i) * nviews + v) * 128 + 4 * lane, g);
+    };
+    if constexpr (NV > 0) {
+      float h[kPts][kMaxV][4];
+      float4 d4[kPts][kMaxV];
 #pragma unroll
-      for (int i = 0; i < kPts; ++i) {
-        float g[4];
+      for (int i = 0; i < kPts; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float gsum = fmaf(d4[i].x, wo[j][0], fmaf(d4[i].y, wo[j][1], fmaf(d4[i].z, wo[j][2], d4[i].w * wo[j][3])));
-          g[j] = h[i][j] > 0.f ? gsum : 0.f;
-          acc[i][j] += g[j];
+        for (int v = 0; v < NV; ++v) {
+          const int64_t row = min(p0 + i, n_points - 1) * NV + v;
+          load4(hv + row * 128 + 4 * lane, h[i][v]);
+          d4[i][v] = *reinterpret_cast<const float4*>(dlogit + row * 4);
         }
-        if (p0 + i < n_points) store4_sat(dhv + ((p0 + i) * nviews + v) * 128 + 4 * lane, g);
-      }
+#pragma unroll
+      for (int i = 0; i < kPts; ++i)
+#pragma unroll
+        for (int v = 0; v < NV; ++v) one_view(h[i][v], d4[i][v], i, v);
+    } else {
+      for (int v = 0; v < nviews; ++v)
+#pragma unroll
+        for (int i = 0; i < kPts; ++i) {
+          const int64_t row = min(p0 + i, n_points - 1) * nviews + v;
+          float h[4];
+          load4(hv + row * 128 + 4 * lane, h);
+          one_view(h, *reinterpret_cast<const float4*>(dlogit + row * 4), i, v);
+        }
     }
 #pragma unroll
     for (int i = 0; i < kPts; ++i)
@@ -768,14 +784,32 @@ cudaError_t launch_heads_fwd(int64_t n_points, int nviews, const void* packed, c
   return cudaGetLastError();
 }
 
+template <typename T>
+void launch_heads_bwd_t(int64_t n_points, int nviews, const float* small, const float* dlogit, const void* hv, void* dhv,
+                        void* dacc9, const uint32_t* scale_def, uint32_t* amax_out, cudaStream_t s) {
+  // 8 warps per block, a point pair per warp and pass; the grid is capped and the warps loop
+  int64_t blocks = (n_points + 15) / 16;
+  if (blocks > 148 * 12) blocks = 148 * 12;
+  const T* h = static_cast<const T*>(hv);
+  T* dh = static_cast<T*>(dhv);
+  T* da = static_cast<T*>(dacc9);
+#define VIPNERF_HEADS_BWD(NV) k_heads_bwd<T, NV><<<(unsigned)blocks, 256, 0, s>>>(n_points, nviews, small, dlogit, h, dh, da, scale_def, amax_out)
+  switch (nviews) {
+    case 1: VIPNERF_HEADS_BWD(1); break;
+    case 2: VIPNERF_HEADS_BWD(2); break;
+    case 3: VIPNERF_HEADS_BWD(3); break;
+    case 4: VIPNERF_HEADS_BWD(4); break;
+    default: VIPNERF_HEADS_BWD(0); break;
+  }
+#undef VIPNERF_HEADS_BWD
+}
+
 cudaError_t launch_heads_bwd(int64_t n_points, int nviews, const void* packed, const float* dlogit, const void* hv,
                              void* dhv, void* dacc9, cudaStream_t s, bool half, const uint32_t* scale_def, uint32_t* amax_out) {
   if (n_points == 0) return cudaSuccess;
-  const unsigned grid = (unsigned)((n_points + 31) / 32);      // 8 warps x 4 points
-  const size_t smem = 0;
   const float* small = reinterpret_cast<const float*>(packed);
-  if (half) k_heads_bwd<__half><<<grid, 256, smem, s>>>(n_points, nviews, small, dlogit, static_cast<const __half*>(hv), static_cast<__half*>(dhv), static_cast<__half*>(dacc9), scale_def, amax_out);
-  else k_heads_bwd<float><<<grid, 256, smem, s>>>(n_points, nviews, small, dlogit, static_cast<const float*>(hv), static_cast<float*>(dhv), static_cast<float*>(dacc9), scale_def, amax_out);
+  if (half) launch_heads_bwd_t<__half>(n_points, nviews, small, dlogit, hv, dhv, dacc9, scale_def, amax_out, s);
+  else launch_heads_bwd_t<float>(n_points, nviews, small, dlogit, hv, dhv, dacc9, scale_def, amax_out, s);
   return cudaGetLastError();
 }
 
