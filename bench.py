@@ -381,6 +381,12 @@ TRAIN_FLOP_PER_POINT = 2 * (593_536 + 557_056 + 593_536)   # forward + backward-
 #   + compositing backward and heads backward 2,672 + backward-data chain 26,116
 #   + parameter gradients 31,012 (nine tensor-core products 17,920, three FFMA products 3,840, heads 2,084, column sums 7,168)
 TRAIN_TC_BYTES_PER_POINT = 22_852 + 2_672 + 26_116 + 31_012   # 82,652
+# The fp16 mode (train_precision='fp16'; derivation: DESIGN.md section 4.6): every saved activation and chain gradient is
+# an fp16 array, the ReLU masks are bits, the views branch is one product launch per view direction
+#   forward 11,460 (encodings 384, eight trunk layers 8,192 + 256 of mask bits, feature 1,024, views 2 x 896, heads / compositing 68)
+#   + compositing backward 100 + heads backward 1,312 + backward-data chain 9,220
+#   + parameter gradients 12,068 (eleven tensor-core products 11,008, heads 1,060)
+TRAIN_F16_BYTES_PER_POINT = 11_460 + 100 + 1_312 + 9_220 + 12_068   # 34,160
 
 
 def make_train_step(device, R, rng, train_precision, seed, world=1, loss_path='fused', graph=False):
@@ -441,33 +447,54 @@ def make_train_step(device, R, rng, train_precision, seed, world=1, loss_path='f
     return step, model, sum(v.numel() * 4 for v in host.values())
 
 
+def hbm_peak_gbs():
+    ppath = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.isfile(ppath):
+        with open(ppath) as f:
+            return json.load(f).get('hbm_gbs', 6464.3)
+    return 6464.3
+
+
 def train_record(device, steps=5, warmup=3, R=4096):
-    """`train` sub-record of the default bench line: the 4096-ray training iteration in tensor-core mode (device-side
-    random draws), ms per step and the fraction of the TENSOR roofline (3.66 TFLOP per iteration)."""
+    """`train` sub-record of the default bench line: the 4096-ray training iteration of BASELINE config 3 in the fp16
+    tensor-core mode, captured as one CUDA graph (device-side random draws), ms per step, the fraction of the HBM
+    roofline of the step's own algorithmic traffic and of the TENSOR roofline (3.66 TFLOP per iteration); the tf32 mode
+    (eager launches, the r02 mid-round state) next to it."""
     import torch
-    step, _, h2d = make_train_step(device, R, 'device', 'tf32', seed=2)
-    for _ in range(warmup):
-        step()
-    torch.cuda.synchronize()
-    t_ms, loss_value = 0.0, None
-    for _ in range(steps):
-        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s.record()
-        loss_value = step().item()
-        e.record()
-        torch.cuda.synchronize()
-        t_ms += s.elapsed_time(e)
-    ms = t_ms / steps
     peaks = measured_peaks()
+
+    def measure(train_precision, graph):
+        step, _, h2d = make_train_step(device, R, 'device', train_precision, seed=2, graph=graph)
+        for _ in range(warmup):
+            step()
+        torch.cuda.synchronize()
+        t_ms, loss_value = 0.0, None
+        for _ in range(steps):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            loss_value = step().item()          # the step's result comes back to the host
+            e.record()
+            torch.cuda.synchronize()
+            t_ms += s.elapsed_time(e)
+        return t_ms / steps, loss_value, h2d
+
+    ms, loss_value, h2d = measure('fp16', True)
+    ms_tf32, _, _ = measure('tf32', False)
     tflops = R * 256 * TRAIN_FLOP_PER_POINT / (ms * 1e-3) / 1e12
+    gbs = R * 256 * TRAIN_F16_BYTES_PER_POINT / (ms * 1e-3) / 1e9
     return {'workload': 'RealEstate-10K camera, 1 secondary view, 4096-ray training iteration: pinned host rays in, train-mode '
                         'forward, the four ViP-NeRF losses, backward, Adam, loss value out',
-            'train_precision': 'tf32 (tcgen05 kind::tf32 chains + parameter gradients)', 'rng': 'device',
+            'train_precision': 'fp16 (tcgen05 kind::f16 chains + parameter gradients on fp16 saved activations / scaled fp16 '
+                               'gradients; the tf32 mode\'s gradient accuracy)', 'rng': 'device',
+            'launch': 'one CUDA graph per iteration (vipnerf_b200.training.GraphedTrainStep)',
             'ms_per_step': ms, 'value': R / (ms * 1e-3), 'unit': 'rays/s', 'steps': steps,
             'flop_per_step': R * 256 * TRAIN_FLOP_PER_POINT, 'achieved_tflops': tflops,
-            'roofline': {'bound': 'tensor', 'achieved': tflops, 'peak': peaks['sustained'] / 2, 'unit': 'TFLOP/s',
-                         'frac': tflops / (peaks['sustained'] / 2),
-                         'peak_kind': 'dense tf32 = half the measured sustained bf16 rate'},
+            'roofline': {'bound': 'hbm', 'achieved': gbs, 'peak': hbm_peak_gbs(), 'unit': 'GB/s', 'frac': gbs / hbm_peak_gbs(),
+                         'bytes_per_point': TRAIN_F16_BYTES_PER_POINT,
+                         'peak_kind': 'measured HBM copy bandwidth (MEASURED_PEAKS.json); algorithmic bytes of the whole step',
+                         'tensor_frac': tflops / peaks['sustained'],
+                         'tensor_peak_kind': 'dense fp16 = the measured sustained bf16 rate'},
+            'tf32_eager_ms_per_step': ms_tf32,
             'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4, 'final_loss': loss_value}
 
 
@@ -523,18 +550,15 @@ def run_train(args, rank, world, local_rank):
         achieved = value / world * 256 * TRAIN_FLOP_PER_POINT / 1e12
         if args.train_precision in ('tf32', 'fp16'):
             # the tensor-core step is HBM-bound: activations and gradients make one round trip per consumer
-            hbm_peak = 6464.3
-            ppath = os.path.join(ROOT, 'MEASURED_PEAKS.json')
-            if os.path.isfile(ppath):
-                with open(ppath) as f:
-                    hbm_peak = json.load(f).get('hbm_gbs', hbm_peak)
-            gbs = value / world * 256 * TRAIN_TC_BYTES_PER_POINT / 1e9
+            hbm_peak = hbm_peak_gbs()
+            bpp = TRAIN_F16_BYTES_PER_POINT if args.train_precision == 'fp16' else TRAIN_TC_BYTES_PER_POINT
+            gbs = value / world * 256 * bpp / 1e9
             roofline = {'bound': 'hbm', 'achieved': gbs, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': gbs / hbm_peak,
                         'traffic': None,
                         'peak_kind': 'measured HBM copy bandwidth (MEASURED_PEAKS.json), whole step',
-                        'bytes_per_ray': 256 * TRAIN_TC_BYTES_PER_POINT,
-                        'note': 'algorithmic bytes of all kernels of the step / step time; k_gemm_tn_tf32 alone: 1.61 GB in '
-                                '256 us under ncu = 0.97 of the peak (profiles/r01_train_ncu_summary.md)',
+                        'bytes_per_ray': 256 * bpp,
+                        'note': 'algorithmic bytes of all kernels of the step / step time (per-kernel figures: '
+                                'profiles/r02_ncu_summary.md)',
                         'tensor_tflops_algorithmic': achieved}
         else:
             roofline = {'bound': 'fp32-ffma', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
@@ -544,23 +568,26 @@ def run_train(args, rank, world, local_rank):
         line = {'metric': 'training rays/s (forward + 4 losses + backward + Adam), 64+128 samples', 'value': value,
                 'unit': 'rays/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
                 'ms_per_step': total_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-                'dtype': 'f32' if args.train_precision == 'fp32' else 'tf32', 'data': 'synthetic',
+                'dtype': {'fp32': 'f32', 'tf32': 'tf32', 'fp16': 'f16'}[args.train_precision], 'data': 'synthetic',
                 'config': {'workload': 'RealEstate-10K camera, 2 input views (1 secondary view), full ViP-NeRF visibility + '
                                        'sparse-depth losses, one training iteration per step',
                            'rays_per_step_per_gpu': R, 'samples': '64+128', 'ndc': True,
                            'rng': args.rng + (' (torch CPU generator in the reference\'s draw order, uploaded per step)'
                                               if args.rng == 'reference' else ' (torch CUDA generator, same distributions)'),
                            'train_precision': args.train_precision,
-                           'kernels': 'fp32 CUDA-core training path (k_mlp_fp32<save>, k_composite_bwd, k_mlp_bwd_fp32, k_gemm_tn)'
-                                      if args.train_precision == 'fp32' else
-                                      'tensor-core training path: k_linear_tf32 (forward and backward-data chains) + k_gemm_tn_tf32 '
-                                      '(parameter gradients) on tcgen05 kind::tf32; encodings, heads, compositing and its backward fp32',
-                           'l2': 'working set (about 22 KB per sample point, > 20 GB per step) exceeds L2 by construction',
+                           'launch': 'one CUDA graph per iteration' if args.graph else 'eager launches',
+                           'kernels': {'fp32': 'fp32 CUDA-core training path (k_mlp_fp32<save>, k_composite_bwd, k_mlp_bwd_fp32, k_gemm_tn)',
+                                       'tf32': 'tensor-core training path: k_linear_tc (forward and backward-data chains) + k_gemm_tn_tc '
+                                               '(parameter gradients) on tcgen05 kind::tf32; encodings, heads, compositing and its backward fp32',
+                                       'fp16': 'tensor-core training path on fp16 arrays: k_linear_tc (chains; the views branch and both heads in '
+                                               'its epilogues, ReLU masks as bits) + k_gemm_tn_tc (parameter gradients) on tcgen05 kind::f16, '
+                                               'scaled fp16 gradients; encodings, compositing and its backward fp32'}[args.train_precision],
+                           'l2': 'working set (5.6 - 11 KB per sample point saved, > 10 GB per step) exceeds L2 by construction',
                            'final_loss': loss_value},
                 'clocks': clocks,
                 'e2e': {'value': value, 'unit': 'rays/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4,
                         'note': 'the timed region IS end to end: pinned host rays in, loss value out'},
-                'gpu_launches': args.steps * (149 if args.train_precision == 'tf32' else 95),   # counted in the ncu launch lists (profiles/)
+                'gpu_launches': args.steps * {'tf32': 149, 'fp16': 143, 'fp32': 95}[args.train_precision],   # counted in the ncu launch lists (profiles/)
                 'roofline': roofline}
         if not args.no_cpu_baseline and world == 1:
             threads = os.cpu_count() or 1
