@@ -197,7 +197,7 @@ BwdLayout carve_bwd(const vipnerf_cfg* cfg, int64_t n_rays) {
   return L;
 }
 
-// ---- tensor-core training chains (VIPNERF_FLAG_TRAIN_TF32): every 256-wide product is one k_linear_tf32 launch
+// ---- tensor-core training chains (VIPNERF_FLAG_TRAIN_TF32 / _F16): every 256-wide product is one k_linear_tc launch
 const float* packed_small(const void* packed) { return reinterpret_cast<const float*>(packed); }
 const float* packed_big(const void* packed) {   // forward images Wt[in][out] (layout.cuh)
   return reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(packed) + kSmallBytes);
@@ -775,6 +775,10 @@ int vipnerf_train_backward_fused(const vipnerf_cfg* cfg, const vipnerf_rays* ray
       if (!tf32 && !f16) return launch_gemm_tn(as_f(dy), M, M, as_f(x), N, N, rows, dw, ldc, n_valid, db, partial, s);
       return launch_gemm_tn_tc(dy, M, M, x, N, N, rows, dw, ldc, n_valid, partial, s, db, colsum, f16, f16 ? amax + slot : nullptr);
     };
+    // the eight 256 x 256 products of the sample set (pts_linears.1-7 incl. the hidden columns of the skip layer,
+    // feature_linear): ONE launch on the tensor cores, the CTAs split between the problems
+    GemmProblem wide[kGemmGroupMax];
+    int n_wide = 0;
     for (int l = 0; l < 8 && e == cudaSuccess; ++l) {
       const uint8_t* dy = dpre + l * PL;
       float* dw = pg[2 * l];
@@ -784,15 +788,23 @@ int vipnerf_train_backward_fused(const vipnerf_cfg* cfg, const vipnerf_rays* ray
         e = gemm(dy, 256, enc, 64, P, dw, kEncPts, kEncPts, db, slot);
       } else if (l == 5) {   // input = cat([encoding, h4]) (:543-544)
         e = gemm(dy, 256, enc, 64, P, dw, kWidth + kEncPts, kEncPts, db, slot);
-        if (e == cudaSuccess) e = gemm(dy, 256, h + 4 * PL, 256, P, dw + kEncPts, kWidth + kEncPts, 256, nullptr, slot);
+        if (tf32 || f16) wide[n_wide++] = GemmProblem{dy, 256, h + 4 * PL, 256, dw + kEncPts, kWidth + kEncPts, 256, nullptr, f16 ? amax + slot : nullptr};
+        else if (e == cudaSuccess) e = gemm(dy, 256, h + 4 * PL, 256, P, dw + kEncPts, kWidth + kEncPts, 256, nullptr, slot);
+      } else if (tf32 || f16) {
+        wide[n_wide++] = GemmProblem{dy, 256, h + (l - 1) * PL, 256, dw, 256, 256, db, f16 ? amax + slot : nullptr};
       } else {
         e = gemm(dy, 256, h + (l - 1) * PL, 256, P, dw, 256, 256, db, slot);
       }
     }
     if (e != cudaSuccess) return fail_cuda(e, "gemm_tn (pts_linears)");
     // feature_linear (input h7 = output of pts_linears.7)
-    if ((e = gemm(dfeat, 256, h + 7 * PL, 256, P, pg[20], 256, 256, pg[21], kSlotAcc9)) != cudaSuccess)
+    if (tf32 || f16) {
+      wide[n_wide++] = GemmProblem{dfeat, 256, h + 7 * PL, 256, pg[20], 256, 256, pg[21], f16 ? amax + kSlotAcc9 : nullptr};
+      if ((e = launch_gemm_tn_tc_group(wide, n_wide, 256, 256, P, partial, colsum, f16, s)) != cudaSuccess)
+        return fail_cuda(e, "gemm_tn (grouped 256 x 256 products)");
+    } else if ((e = gemm(dfeat, 256, h + 7 * PL, 256, P, pg[20], 256, 256, pg[21], kSlotAcc9)) != cudaSuccess) {
       return fail_cuda(e, "gemm_tn (feature_linear)");
+    }
     // views_linears.0: feature columns over points, direction columns and bias over (point, view) rows
     if ((e = gemm(dacc9, 128, feat, 256, P, pg[16], kWidth + kEncView, 256, nullptr, kSlotLogit)) != cudaSuccess)
       return fail_cuda(e, "gemm_tn (views_linears feature columns)");

@@ -1,27 +1,31 @@
-// Parameter-gradient GEMM on the tensor cores:  C[m][n] = sum_p A[p][m] * B[p][n]  (dW = dY^T X, training row f1).
+// The two tensor-core kernels of the training step (row f1), each in two arithmetic modes with the same byte geometry:
+// fp32 arrays read as tf32 (tcgen05 kind::tf32; VIPNERF_FLAG_TRAIN_TF32) or fp16 arrays (kind::f16; VIPNERF_FLAG_TRAIN_F16,
+// half the bytes of every stream).
 //
-// Both operands are the fp32 point-major arrays the chain kernels already write (A = pre-activation gradients
-// [P][M], B = layer inputs [P][256]); the reduction index p is the OUTER index of both, i.e. both are "MN-major"
-// operands for the MMA.  tcgen05.mma kind::tf32 reads fp32 words from shared memory directly, so no conversion or
-// transposition pass exists: the TMA engine drops [32 points] x [32 columns] fp32 boxes (128-byte rows, 128-byte
-// swizzle with 32-byte atoms - the only layout tcgen05 reads MN-major 32-bit operands from) into a 3-stage ring, one elected thread issues M=128, N=256, K=8 MMAs (one per 8 points and 128-row half of the
-// output) that accumulate the CTA's whole 256 x 256 (or 128 x 256) fp32 tile in TMEM (all 512 columns), and after
-// the CTA's point range is exhausted four warps drain TMEM into a partial tile that k_reduce_partials (train_kernels.cu)
-// sums over the CTAs in a fixed order.  One CTA per SM, 148 point ranges.
+// k_gemm_tn_tc<half> - parameter gradients:  C[m][n] = sum_p A[p][m] * B[p][n]  (dW = dY^T X).
+// Both operands are the point-major arrays the chain kernels already write (A = pre-activation gradients [P][M],
+// B = layer inputs [P][256]); the reduction index p is the OUTER index of both, i.e. both are "MN-major" operands for
+// the MMA.  tcgen05.mma reads them from shared memory directly, so no conversion or transposition pass exists: the TMA
+// engine drops [32 points] x [128 bytes of columns] boxes into a ring (fp32: 128-byte swizzle with 32-byte atoms - the
+// only layout tcgen05 reads MN-major 32-bit operands from; fp16: the plain 128-byte swizzle), one elected thread issues
+// M=128, N=256 MMAs (K = 8 / 16 points each, one per 128-row half of the output) that accumulate the CTA's whole
+// 256 x 256 (or 128 x 256) fp32 tile in TMEM (all 512 columns), and after the CTA's point range is exhausted four warps
+// drain TMEM into a partial tile that k_reduce_partials (train_kernels.cu) sums over the CTAs in a fixed order.
+// One CTA per SM, 148 point ranges.
 //
 //   warp 0      TMA producer (one lane)
 //   warp 1      TMEM allocation, MMA issue (one lane), commits that free ring stages
-//   warps 2..5  epilogue: TMEM -> registers -> global partial tile (warp w owns TMEM lanes 32*(w%4)..)
+//   warps 2..5  epilogue: column sums of A (the bias gradient) from the staged boxes while the main loop runs, then
+//               TMEM -> registers -> global partial tile (warp w owns TMEM lanes 32*(w%4)..)
 //
-// Roofline: HBM.  Each CTA reads every A and B row of its point range once: (M + 256) * 4 bytes per point and layer,
-// i.e. 2 KiB/point for the 256 x 256 layers -> 2.1 GB per layer at 10^6 points, 0.33 ms at 6.4 TB/s; the tf32 tensor
-// time of the same layer is 0.2 ms.  Measured: 256 us for 786,432 points (0.97 of the HBM peak); the FFMA kernel it
-// replaces needs 1.7 ms.
+// Roofline: HBM.  Each CTA reads every A and B row of its point range once: (M + 256) elements per point and layer,
+// i.e. 2 KiB/point (tf32) or 1 KiB/point (fp16) for the 256 x 256 layers.  Measured (tf32): 256 us for 786,432 points
+// (0.97 of the HBM peak); the FFMA kernel it replaces needs 1.7 ms.
 //
-// Numerics: operands are rounded to tf32 (10-bit mantissa) by the TMA copy (CU_TENSOR_MAP_DATA_TYPE_TFLOAT32),
-// products accumulate in fp32.  The tensor-core training mode is opt-in (configs['model']['train_precision'] = 'tf32',
-// VIPNERF_FLAG_TRAIN_TF32); the default training path stays fp32 FFMA.  The second kernel of this file, k_linear_tf32
-// (below), runs the forward and backward-data chains of that mode.
+// Numerics: tf32 operands are rounded (10-bit mantissa) by the TMA copy (CU_TENSOR_MAP_DATA_TYPE_TFLOAT32); fp16
+// operands were rounded to the same 10-bit mantissa when they were stored; products accumulate in fp32.  The tensor-core
+// training modes are opt-in (configs['model']['train_precision'] = 'tf32' | 'fp16'); the default path stays fp32 FFMA.
+// The second kernel of this file, k_linear_tc (below), runs the forward and backward-data chains of both modes.
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -134,13 +138,19 @@ constexpr uint32_t instr_desc_mn(uint32_t n, uint32_t m) {
   return (1u << 4) | ((kHalf ? 0u : 2u) << 7) | ((kHalf ? 0u : 2u) << 10) | (1u << 15) | (1u << 16) | ((n >> 3) << 17) | ((m >> 4) << 24);
 }
 
+// Up to kGemmGroupMax products of the same shape over the same point count share a launch (the eight 256 x 256
+// products of a sample set: trunk layers + feature_linear): CTA b works on problem b / splits, point range b % splits.
+// With 148 / 8 = 18 CTAs per problem every SM still streams its share of the rows, but a problem leaves 18 partial tiles
+// instead of 148 - the partial-tile writes at the end of a launch and the reductions behind it shrink eightfold.
 struct GemmTcParams {
-  CUtensorMap map_a, map_b;
+  CUtensorMap map_a[kGemmGroupMax], map_b[kGemmGroupMax];
+  int n_problems, splits;   // grid = n_problems * splits
   int M;                    // 128 or 256
   int N;                    // tf32: 32, 64 or 256; fp16: 64 or 256 (columns of B)
   int64_t n_rows, rows_per_split;
   float* partial;           // [gridDim.x][M][N]
-  float* colsum_partial;    // [gridDim.x][M] column sums of A over the CTA's point range (bias gradient), or null
+  float* colsum_partial;    // [gridDim.x][M] column sums of A over the CTA's point range (bias gradient)
+  uint32_t colsum_mask;     // bit g: problem g wants them
 };
 
 template <bool kHalf>
@@ -160,7 +170,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_gemm_tn_tc(const __grid_const
   auto empty_bar = [&](int s) { return bar0 + 8u * (kStages + s); };
   const uint32_t done_bar = bar0 + 8u * (2 * kStages);
 
-  const int64_t r_begin = (int64_t)blockIdx.x * p.rows_per_split;
+  const int prob = (int)blockIdx.x / p.splits;
+  const CUtensorMap* map_a = &p.map_a[prob];
+  const CUtensorMap* map_b = &p.map_b[prob];
+  const bool want_colsum = (p.colsum_mask >> prob) & 1u;
+  const int64_t r_begin = (int64_t)((int)blockIdx.x % p.splits) * p.rows_per_split;
   const int64_t r_end = min(p.n_rows, r_begin + p.rows_per_split);
   const int n_steps = r_end > r_begin ? (int)((r_end - r_begin + kTcRows - 1) / kTcRows) : 0;
 
@@ -168,7 +182,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_gemm_tn_tc(const __grid_const
     if ((smem_u32(smem) & 1023u) != 0) { printf("vipnerf gemm_tc: shared memory base not 1 KiB aligned\n"); __trap(); }
     // a stage is free when its MMAs have retired (one tcgen05.commit arrival) and, with column sums, when the four
     // epilogue warps have read its A boxes (one arrival each)
-    for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), p.colsum_partial ? 5 : 1); }
+    for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), want_colsum ? 5 : 1); }
     mbar_init(done_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -189,8 +203,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_gemm_tn_tc(const __grid_const
         mbar_expect_tx(full_bar(st), stage_bytes);
         const uint32_t dst = smem_u32(smem) + (uint32_t)st * stage_bytes;
         const int row = (int)(r_begin + (int64_t)s * kTcRows);   // rows past the end of the arrays are zero-filled by the TMA
-        for (int j = 0; j < a_boxes; ++j) tma_load_2d(dst + j * kBoxBytes, &p.map_a, j * G::kColsPerBox, row, full_bar(st));
-        for (int j = 0; j < b_boxes; ++j) tma_load_2d(dst + (a_boxes + j) * kBoxBytes, &p.map_b, j * G::kColsPerBox, row, full_bar(st));
+        for (int j = 0; j < a_boxes; ++j) tma_load_2d(dst + j * kBoxBytes, map_a, j * G::kColsPerBox, row, full_bar(st));
+        for (int j = 0; j < b_boxes; ++j) tma_load_2d(dst + (a_boxes + j) * kBoxBytes, map_b, j * G::kColsPerBox, row, full_bar(st));
       }
     }
   } else if (warp == 1) {
@@ -219,7 +233,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_gemm_tn_tc(const __grid_const
     // epilogue warps: warp w may touch TMEM lanes [32 * (w % 4), +32)
     float* out = p.partial + (size_t)blockIdx.x * p.M * p.N;
     const int quarter = warp & 3;
-    if (p.colsum_partial != nullptr) {
+    if (want_colsum) {
       // While the main loop runs these 128 threads are idle: they add up the columns of the A boxes of every stage
       // straight from shared memory (db = sum_p dY[p][m], the bias gradient) - the separate column-sum pass over the
       // same array (k_colsum, 1 KiB per point and layer from HBM once more) is gone.
@@ -832,45 +846,63 @@ cudaError_t launch_linear_tc(const LinearTcArgs& a, cudaStream_t s) {
 
 size_t gemm_tn_tc_partial_floats(int sms) { return (size_t)sms * 256 * 256; }
 
-cudaError_t launch_gemm_tn_tc(const void* A, int lda, int M, const void* B, int ldb, int N, int64_t n_rows, float* dst,
-                              int ldc, int n_valid, float* partial, cudaStream_t s, float* bias_dst,
-                              float* colsum_scratch, bool half, const uint32_t* scale_def) {
-  if ((M != 128 && M != 256) || n_rows < 1) return cudaErrorInvalidValue;
+cudaError_t launch_gemm_tn_tc_group(const GemmProblem* problems, int n_problems, int M, int N, int64_t n_rows,
+                                    float* partial, float* colsum_scratch, bool half, cudaStream_t s) {
+  if (n_problems < 1 || n_problems > kGemmGroupMax || (M != 128 && M != 256) || n_rows < 1) return cudaErrorInvalidValue;
   if (half ? (N != 64 && N != 256) : (N != 32 && N != 64 && N != 256)) return cudaErrorInvalidValue;
   const int es = half ? 2 : 4;
-  if ((reinterpret_cast<uintptr_t>(A) & 15u) || (reinterpret_cast<uintptr_t>(B) & 15u) || ((lda * es) & 15) || ((ldb * es) & 15))
-    return cudaErrorInvalidValue;
   int dev = 0, sms = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
   if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
   // the split-reduction scratch is sized for kGemmTcMaxSplits partial tiles (api.cu: gemm_tn_tc_partial_floats(160))
-  int64_t n_split = sms < kGemmTcMaxSplits ? sms : kGemmTcMaxSplits;
+  int64_t n_split = (sms < kGemmTcMaxSplits ? sms : kGemmTcMaxSplits) / n_problems;      // point ranges per problem
   const int64_t max_by_rows = (n_rows + 4 * kTcRows - 1) / (4 * kTcRows);
   if (n_split > max_by_rows) n_split = max_by_rows;
+  if (n_split < 1) n_split = 1;
   int64_t rows_per_split = (n_rows + n_split - 1) / n_split;
   rows_per_split = (rows_per_split + kTcRows - 1) / kTcRows * kTcRows;
   n_split = (n_rows + rows_per_split - 1) / rows_per_split;
 
   GemmTcParams p{};
-  if ((e = encode_rows_map(&p.map_a, A, lda, M, n_rows, half)) != cudaSuccess) return e;
-  if ((e = encode_rows_map(&p.map_b, B, ldb, N, n_rows, half)) != cudaSuccess) return e;
+  for (int g = 0; g < n_problems; ++g) {
+    const GemmProblem& q = problems[g];
+    if ((reinterpret_cast<uintptr_t>(q.A) & 15u) || (reinterpret_cast<uintptr_t>(q.B) & 15u) || ((q.lda * es) & 15) || ((q.ldb * es) & 15))
+      return cudaErrorInvalidValue;
+    if (q.bias_dst != nullptr && colsum_scratch == nullptr) return cudaErrorInvalidValue;
+    if ((e = encode_rows_map(&p.map_a[g], q.A, q.lda, M, n_rows, half)) != cudaSuccess) return e;
+    if ((e = encode_rows_map(&p.map_b[g], q.B, q.ldb, N, n_rows, half)) != cudaSuccess) return e;
+    if (q.bias_dst != nullptr) p.colsum_mask |= 1u << g;
+  }
+  p.n_problems = n_problems; p.splits = (int)n_split;
   p.M = M; p.N = N; p.n_rows = n_rows; p.rows_per_split = rows_per_split; p.partial = partial;
-  p.colsum_partial = (bias_dst != nullptr) ? colsum_scratch : nullptr;
-  if (bias_dst != nullptr && colsum_scratch == nullptr) return cudaErrorInvalidValue;
+  p.colsum_partial = colsum_scratch;
   const int cpb = half ? 64 : 32;
   const size_t smem = (size_t)(half ? TcGeom<true>::kStages : TcGeom<false>::kStages) * (M / cpb + N / cpb) * kBoxBytes + 128;
+  const unsigned grid = (unsigned)(n_problems * n_split);
   if (half) {
     if ((e = cudaFuncSetAttribute(k_gemm_tn_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-    k_gemm_tn_tc<true><<<(unsigned)n_split, kTcThreads, smem, s>>>(p);
+    k_gemm_tn_tc<true><<<grid, kTcThreads, smem, s>>>(p);
   } else {
     if ((e = cudaFuncSetAttribute(k_gemm_tn_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-    k_gemm_tn_tc<false><<<(unsigned)n_split, kTcThreads, smem, s>>>(p);
+    k_gemm_tn_tc<false><<<grid, kTcThreads, smem, s>>>(p);
   }
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
-  if ((e = launch_reduce_partials(partial, (int)n_split, M, N, dst, ldc, n_valid, s, scale_def)) != cudaSuccess) return e;
-  if (bias_dst != nullptr) return launch_reduce_partials(colsum_scratch, (int)n_split, M, 1, bias_dst, 1, 1, s, scale_def);
+  for (int g = 0; g < n_problems; ++g) {
+    const GemmProblem& q = problems[g];
+    if ((e = launch_reduce_partials(partial + (size_t)g * n_split * M * N, (int)n_split, M, N, q.dst, q.ldc, q.n_valid, s, q.scale_def)) != cudaSuccess) return e;
+    if (q.bias_dst != nullptr &&
+        (e = launch_reduce_partials(colsum_scratch + (size_t)g * n_split * M, (int)n_split, M, 1, q.bias_dst, 1, 1, s, q.scale_def)) != cudaSuccess)
+      return e;
+  }
   return cudaSuccess;
+}
+
+cudaError_t launch_gemm_tn_tc(const void* A, int lda, int M, const void* B, int ldb, int N, int64_t n_rows, float* dst,
+                              int ldc, int n_valid, float* partial, cudaStream_t s, float* bias_dst,
+                              float* colsum_scratch, bool half, const uint32_t* scale_def) {
+  const GemmProblem q{A, lda, B, ldb, dst, ldc, n_valid, bias_dst, scale_def};
+  return launch_gemm_tn_tc_group(&q, 1, M, N, n_rows, partial, colsum_scratch, half, s);
 }
 
 }  // namespace vipnerf

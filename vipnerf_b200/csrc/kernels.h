@@ -122,6 +122,18 @@ size_t gemm_tn_tc_partial_floats(int sms);
 cudaError_t launch_gemm_tn_tc(const void* A, int lda, int M, const void* B, int ldb, int N, int64_t n_rows, float* dst,
                               int ldc, int n_valid, float* partial, cudaStream_t s, float* bias_dst = nullptr,
                               float* colsum_scratch = nullptr, bool half = false, const uint32_t* scale_def = nullptr);
+// Up to kGemmGroupMax products of the same M x N over the same n_rows in ONE launch (CTAs split between the problems):
+// the eight 256 x 256 products of a sample set leave 18 instead of 148 partial tiles each.
+constexpr int kGemmGroupMax = 8;
+struct GemmProblem {
+  const void* A; int lda;
+  const void* B; int ldb;
+  float* dst; int ldc; int n_valid;
+  float* bias_dst;              // column sums of A, or null
+  const uint32_t* scale_def;    // see launch_reduce_partials
+};
+cudaError_t launch_gemm_tn_tc_group(const GemmProblem* problems, int n_problems, int M, int N, int64_t n_rows,
+                                    float* partial, float* colsum_scratch, bool half, cudaStream_t s);
 // train_kernels.cu : the non-product pieces of the tensor-core training path (encodings, heads forward / backward).
 // `half` = the fp16 mode (VIPNERF_FLAG_TRAIN_F16): enc / pev / hv / dhv / dacc9 are fp16 arrays and a row of pev has 64
 // columns (128 bytes, 27 used) instead of 32 floats; gradients carry the power-of-two scale of their amax slot.

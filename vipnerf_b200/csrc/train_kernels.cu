@@ -592,7 +592,7 @@ k_heads_fwd(int64_t n_points, int nviews, const float* __restrict__ small, const
   {
     float s = 0.f;
     if (h7 == nullptr) {
-      s = out_sigma[pg];     // the producer of h7 (k_linear_tf32's epilogue, LinearTcArgs::dot_vec) left w_sigma . h7 here
+      s = out_sigma[pg];     // the producer of h7 (k_linear_tc's epilogue, LinearTcArgs::dot_vec) left w_sigma . h7 here
     } else {
       const float4* h = reinterpret_cast<const float4*>(h7 + pg * 256);
 #pragma unroll 8
@@ -980,7 +980,7 @@ cudaError_t launch_colsum(const float* A, int lda, int M, int64_t n_rows, float*
 cudaError_t launch_small_tn(const float* G, int M, const void* H, int N, int64_t n_rows, float* dst, float* gsum_dst,
                             float* partial, cudaStream_t s, bool half_h) {
   if ((M != 1 && M != 4) || (N != 128 && N != 256)) return cudaErrorInvalidValue;   // a row = 64 or 128 column pairs
-  int64_t n_split = 4 * 148;
+  int64_t n_split = 8 * 148;       // 8 blocks of 256 threads per SM: the loads in flight are what bounds this stream
   const int64_t max_by_rows = (n_rows + 63) / 64;
   if (n_split > max_by_rows) n_split = max_by_rows;
   if (n_split < 1) n_split = 1;
