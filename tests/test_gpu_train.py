@@ -185,7 +185,7 @@ def test_param_gradient_gemm(P, M, N, mode, built_library):
 @pytest.mark.parametrize('scene,n_rays,n_sec,train_precision', [
     ('fern', 333, 1, 'fp32'), ('dtu', 200, 3, 'fp32'), ('re10k', 128, 1, 'fp32'),   # re10k = BASELINE config 3
     ('fern', 333, 1, 'tf32'), ('re10k', 128, 1, 'tf32'), ('dtu', 200, 3, 'tf32'),
-    ('fern', 333, 1, 'fp16'), ('re10k', 128, 1, 'fp16'), ('dtu', 200, 3, 'fp16')])
+    ('fern', 333, 1, 'fp16'), ('re10k', 128, 1, 'fp16'), ('dtu', 200, 3, 'fp16')])   # nv = 2, 2, 4 view directions
 def test_training_gradients_vs_oracle_autograd(scene, n_rays, n_sec, train_precision, built_library):
     """Full gradient tensors against torch autograd over the oracle, with the draws of the plugin's own generator
     mirror, a ray count that is not a multiple of anything, and a different number of secondary views."""
@@ -221,22 +221,26 @@ def test_training_gradients_vs_oracle_autograd(scene, n_rays, n_sec, train_preci
     print(f'{scene} {train_precision}: worst gradient error {worst[0]:.2e} ({worst[1]}), worst L2 error {worst[2]:.2e}')
 
 
-def test_training_without_random_sources_and_coarse_only(built_library):
-    """perturb off and raw_noise_std 0 (NULL random inputs), white background, and a coarse-only model."""
+@pytest.mark.parametrize('train_precision', ['fp32', 'fp16'])
+def test_training_without_random_sources_and_coarse_only(train_precision, built_library):
+    """perturb off and raw_noise_std 0 (NULL random inputs), white background, and a coarse-only model - on the CUDA cores
+    and in the fp16 tensor-core mode (its gates: the tensor-core gates of test_training_gradients_vs_oracle_autograd)."""
     scene, n_rays, n_sec = 'dtu', 96, 2
+    tc = train_precision != 'fp32'
+    gates = dict(max_tol=3e-2, norm_tol=3e-2) if tc else {}
     rays = O.make_rays(scene, n_rays, seed=8, n_sec_views=n_sec)
     sup = O.make_supervision(scene, n_rays, n_sec)
-    cfg = _configs(False, perturb=False, raw_noise_std=0.0, white_bkgd=True)
+    cfg = _configs(False, perturb=False, raw_noise_std=0.0, white_bkgd=True, train_precision=train_precision)
     model = _train_model(cfg)
     out = model(dict(H.to_cuda(rays)))
     total, _ = H.training_loss(out, _sup_cuda(sup))
     total.backward()
     ref_out, ref_total, ref_grads = _oracle_step(O.synth_state_dict(0), rays, sup, {}, False, white_bkgd=True)
-    assert abs(total.item() - ref_total.item()) <= 2e-4 * abs(ref_total.item())
-    _compare_full_grads(model, ref_grads)
+    assert abs(total.item() - ref_total.item()) <= (2e-3 if tc else 2e-4) * abs(ref_total.item())
+    _compare_full_grads(model, ref_grads, **gates)
 
     # coarse-only: loss on the coarse outputs alone
-    cfg = _configs(False, fine=False)
+    cfg = _configs(False, fine=False, train_precision=train_precision)
     model = _train_model(cfg)
     torch.manual_seed(3)
     out = model(dict(H.to_cuda(rays)))
@@ -251,8 +255,8 @@ def test_training_without_random_sources_and_coarse_only(built_library):
     ref_loss = torch.mean(torch.square(ref['rgb_coarse'] - sup['target_rgb'])) + 0.1 * ref['depth_coarse'].mean() \
         + 0.01 * ref['visibility2_coarse'].sum()
     ref_loss.backward()
-    assert abs(loss.item() - ref_loss.item()) <= 2e-4 * abs(ref_loss.item())
-    _compare_full_grads(model, {k: v.grad for k, v in sd.items()})
+    assert abs(loss.item() - ref_loss.item()) <= (2e-3 if tc else 2e-4) * abs(ref_loss.item())
+    _compare_full_grads(model, {k: v.grad for k, v in sd.items()}, **gates)
 
 
 def test_training_step_is_deterministic_and_optimizer_steps(built_library):

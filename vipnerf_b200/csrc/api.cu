@@ -777,25 +777,33 @@ int vipnerf_train_backward_fused(const vipnerf_cfg* cfg, const vipnerf_rays* ray
     };
     // the eight 256 x 256 products of the sample set (pts_linears.1-7 incl. the hidden columns of the skip layer,
     // feature_linear): ONE launch on the tensor cores, the CTAs split between the problems
-    GemmProblem wide[kGemmGroupMax];
-    int n_wide = 0;
+    GemmProblem wide[kGemmGroupMax], narrow[2];
+    int n_wide = 0, n_narrow = 0;
+    const bool tc = tf32 || f16;
     for (int l = 0; l < 8 && e == cudaSuccess; ++l) {
       const uint8_t* dy = dpre + l * PL;
       float* dw = pg[2 * l];
       float* db = pg[2 * l + 1];
       const int slot = dpre_slot(l);
+      const uint32_t* sd = f16 ? amax + slot : nullptr;
       if (l == 0) {          // the 64 encoding columns (+ the layer's bias gradient): a narrow product
-        e = gemm(dy, 256, enc, 64, P, dw, kEncPts, kEncPts, db, slot);
+        if (tc) narrow[n_narrow++] = GemmProblem{dy, 256, enc, 64, dw, kEncPts, kEncPts, db, sd};
+        else e = gemm(dy, 256, enc, 64, P, dw, kEncPts, kEncPts, db, slot);
       } else if (l == 5) {   // input = cat([encoding, h4]) (:543-544)
-        e = gemm(dy, 256, enc, 64, P, dw, kWidth + kEncPts, kEncPts, db, slot);
-        if (tf32 || f16) wide[n_wide++] = GemmProblem{dy, 256, h + 4 * PL, 256, dw + kEncPts, kWidth + kEncPts, 256, nullptr, f16 ? amax + slot : nullptr};
-        else if (e == cudaSuccess) e = gemm(dy, 256, h + 4 * PL, 256, P, dw + kEncPts, kWidth + kEncPts, 256, nullptr, slot);
-      } else if (tf32 || f16) {
-        wide[n_wide++] = GemmProblem{dy, 256, h + (l - 1) * PL, 256, dw, 256, 256, db, f16 ? amax + slot : nullptr};
+        if (tc) {
+          narrow[n_narrow++] = GemmProblem{dy, 256, enc, 64, dw, kWidth + kEncPts, kEncPts, db, sd};
+          wide[n_wide++] = GemmProblem{dy, 256, h + 4 * PL, 256, dw + kEncPts, kWidth + kEncPts, 256, nullptr, sd};
+        } else {
+          e = gemm(dy, 256, enc, 64, P, dw, kWidth + kEncPts, kEncPts, db, slot);
+          if (e == cudaSuccess) e = gemm(dy, 256, h + 4 * PL, 256, P, dw + kEncPts, kWidth + kEncPts, 256, nullptr, slot);
+        }
+      } else if (tc) {
+        wide[n_wide++] = GemmProblem{dy, 256, h + (l - 1) * PL, 256, dw, 256, 256, db, sd};
       } else {
         e = gemm(dy, 256, h + (l - 1) * PL, 256, P, dw, 256, 256, db, slot);
       }
     }
+    if (e == cudaSuccess && tc) e = launch_gemm_tn_tc_group(narrow, n_narrow, 256, 64, P, partial, colsum, f16, s);   // both encoding-column products
     if (e != cudaSuccess) return fail_cuda(e, "gemm_tn (pts_linears)");
     // feature_linear (input h7 = output of pts_linears.7)
     if (tf32 || f16) {

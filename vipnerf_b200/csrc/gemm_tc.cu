@@ -888,14 +888,15 @@ cudaError_t launch_gemm_tn_tc_group(const GemmProblem* problems, int n_problems,
     k_gemm_tn_tc<false><<<grid, kTcThreads, smem, s>>>(p);
   }
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  ReduceJob jobs[2 * kGemmGroupMax];      // weights and bias reductions of all problems: one launch
+  int n_jobs = 0;
   for (int g = 0; g < n_problems; ++g) {
     const GemmProblem& q = problems[g];
-    if ((e = launch_reduce_partials(partial + (size_t)g * n_split * M * N, (int)n_split, M, N, q.dst, q.ldc, q.n_valid, s, q.scale_def)) != cudaSuccess) return e;
-    if (q.bias_dst != nullptr &&
-        (e = launch_reduce_partials(colsum_scratch + (size_t)g * n_split * M, (int)n_split, M, 1, q.bias_dst, 1, 1, s, q.scale_def)) != cudaSuccess)
-      return e;
+    jobs[n_jobs++] = ReduceJob{partial + (size_t)g * n_split * M * N, (int)n_split, M, N, q.dst, q.ldc, q.n_valid, q.scale_def};
+    if (q.bias_dst != nullptr)
+      jobs[n_jobs++] = ReduceJob{colsum_scratch + (size_t)g * n_split * M, (int)n_split, M, 1, q.bias_dst, 1, 1, q.scale_def};
   }
-  return cudaSuccess;
+  return launch_reduce_jobs(jobs, n_jobs, s);
 }
 
 cudaError_t launch_gemm_tn_tc(const void* A, int lda, int M, const void* B, int ldb, int N, int64_t n_rows, float* dst,

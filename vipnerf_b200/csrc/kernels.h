@@ -108,6 +108,14 @@ cudaError_t launch_fused_losses(const LossFwdArgs& a, const LossGrad& lg, int64_
 size_t gemm_tn_partial_floats();
 cudaError_t launch_gemm_tn(const float* A, int lda, int M, const float* B, int ldb, int N, int64_t n_rows, float* dst,
                            int ldc, int n_valid, float* bias_dst, float* partial, cudaStream_t s);
+constexpr int kGemmGroupMax = 8;   // products per grouped launch (launch_gemm_tn_tc_group)
+// several reductions in one launch (the weights and bias reductions behind a grouped product launch)
+struct ReduceJob {
+  const float* partial; int n_split, M, N;
+  float* dst; int ldc, n_valid;
+  const uint32_t* scale_def;
+};
+cudaError_t launch_reduce_jobs(const ReduceJob* jobs, int n_jobs, cudaStream_t s);
 // scale_def (fp16 training mode): amax slot that defines the power-of-two scale the partial sums carry; dst = sum / scale
 cudaError_t launch_reduce_partials(const float* partial, int n_split, int M, int N, float* dst, int ldc, int n_valid,
                                    cudaStream_t s, const uint32_t* scale_def = nullptr);
@@ -124,7 +132,6 @@ cudaError_t launch_gemm_tn_tc(const void* A, int lda, int M, const void* B, int 
                               float* colsum_scratch = nullptr, bool half = false, const uint32_t* scale_def = nullptr);
 // Up to kGemmGroupMax products of the same M x N over the same n_rows in ONE launch (CTAs split between the problems):
 // the eight 256 x 256 products of a sample set leave 18 instead of 148 partial tiles each.
-constexpr int kGemmGroupMax = 8;
 struct GemmProblem {
   const void* A; int lda;
   const void* B; int ldb;

@@ -390,12 +390,12 @@ k_gemm_tn(const float* __restrict__ A, int lda, const float* __restrict__ B, int
 // A block owns 64 output elements; its four warp pairs each add every fourth partial tile (eight independent loads in
 // flight per thread, 128-byte rows per warp), and the four slice sums are combined in a fixed order through shared memory
 // - 4 x the parallelism of one thread per element, which left the 38 MB of a 256 x 256 product's partials latency-bound.
-__global__ void __launch_bounds__(256)
-k_reduce_partials(const float* __restrict__ partial, int n_split, int M, int N, float* __restrict__ dst,
-                  int ldc, int n_valid, const uint32_t* __restrict__ scale_def) {
+__device__ __forceinline__ void reduce_partials_block(const float* __restrict__ partial, int n_split, int M, int N,
+                                                      float* __restrict__ dst, int ldc, int n_valid,
+                                                      const uint32_t* __restrict__ scale_def, int block) {
   __shared__ float slice_sum[4][64];
   const int e = threadIdx.x & 63, slice = threadIdx.x >> 6;
-  const int i = blockIdx.x * 64 + e;
+  const int i = block * 64 + e;
   const bool valid = i < M * n_valid;
   const int m = valid ? i / n_valid : 0, n = valid ? i % n_valid : 0;
   float s = 0.f;
@@ -421,6 +421,21 @@ k_reduce_partials(const float* __restrict__ partial, int n_split, int M, int N, 
   }
 }
 
+__global__ void __launch_bounds__(256)
+k_reduce_partials(const float* __restrict__ partial, int n_split, int M, int N, float* __restrict__ dst,
+                  int ldc, int n_valid, const uint32_t* __restrict__ scale_def) {
+  reduce_partials_block(partial, n_split, M, N, dst, ldc, n_valid, scale_def, blockIdx.x);
+}
+
+// the reductions behind a grouped product launch (weights and bias of up to kGemmGroupMax problems) as ONE launch:
+// blockIdx.y = job
+struct ReduceJobs { ReduceJob job[2 * kGemmGroupMax]; };
+__global__ void __launch_bounds__(256) k_reduce_partials_jobs(const __grid_constant__ ReduceJobs jobs) {
+  const ReduceJob& j = jobs.job[blockIdx.y];
+  if ((int)blockIdx.x * 64 >= j.M * j.n_valid) return;
+  reduce_partials_block(j.partial, j.n_split, j.M, j.N, j.dst, j.ldc, j.n_valid, j.scale_def, blockIdx.x);
+}
+
 __device__ __forceinline__ float to_f32(float v) { return v; }
 __device__ __forceinline__ float to_f32(__half v) { return __half2float(v); }
 
@@ -442,41 +457,55 @@ k_small_tn(const float* __restrict__ G, const T* __restrict__ H, int N, int64_t 
   const int64_t r_begin = (int64_t)blockIdx.x * rows_per_split;
   const int64_t r_end = min(n_rows, r_begin + rows_per_split);
   float acc[M][2];
+  float gs[M];      // column sums of G, kept by every thread (the row's G values are in its registers anyway); thread
+                    // c < M of a row group publishes column c
 #pragma unroll
-  for (int m = 0; m < M; ++m) acc[m][0] = acc[m][1] = 0.f;
-  float gs = 0.f;                                // thread c < M of every row group sums G's column c
+  for (int m = 0; m < M; ++m) { acc[m][0] = acc[m][1] = 0.f; gs[m] = 0.f; }
+  auto load_g = [&](int64_t rr, float (&g)[M]) {   // one row of G: a single 16-byte load for the 4-row head
+    if constexpr (M == 4) {
+      const float4 t = *reinterpret_cast<const float4*>(G + rr * 4);
+      g[0] = t.x; g[1] = t.y; g[2] = t.z; g[3] = t.w;
+    } else {
+#pragma unroll
+      for (int m = 0; m < M; ++m) g[m] = G[rr * M + m];
+    }
+  };
   constexpr int kU = 8;
   int64_t r = r_begin + rg;
   for (; r + (kU - 1) * rpp < r_end; r += kU * rpp) {
     float2 hv[kU];
     float g[kU][M];
-    float gc[kU];
 #pragma unroll
     for (int u = 0; u < kU; ++u) {
       const int64_t rr = r + u * rpp;
       hv[u] = load_pair(H + rr * N + 2 * c);
-#pragma unroll
-      for (int m = 0; m < M; ++m) g[u][m] = G[rr * M + m];
-      gc[u] = c < M ? G[rr * M + c] : 0.f;
+      load_g(rr, g[u]);
     }
 #pragma unroll
     for (int u = 0; u < kU; ++u) {
 #pragma unroll
-      for (int m = 0; m < M; ++m) { acc[m][0] = fmaf(g[u][m], hv[u].x, acc[m][0]); acc[m][1] = fmaf(g[u][m], hv[u].y, acc[m][1]); }
-      gs += gc[u];
+      for (int m = 0; m < M; ++m) {
+        acc[m][0] = fmaf(g[u][m], hv[u].x, acc[m][0]); acc[m][1] = fmaf(g[u][m], hv[u].y, acc[m][1]);
+        gs[m] += g[u][m];
+      }
     }
   }
   for (; r < r_end; r += rpp) {
     const float2 h2 = load_pair(H + r * N + 2 * c);
+    float g[M];
+    load_g(r, g);
 #pragma unroll
-    for (int m = 0; m < M; ++m) { const float gv = G[r * M + m]; acc[m][0] = fmaf(gv, h2.x, acc[m][0]); acc[m][1] = fmaf(gv, h2.y, acc[m][1]); }
-    if (c < M) gs += G[r * M + c];
+    for (int m = 0; m < M; ++m) { acc[m][0] = fmaf(g[m], h2.x, acc[m][0]); acc[m][1] = fmaf(g[m], h2.y, acc[m][1]); gs[m] += g[m]; }
   }
+  float gsel = 0.f;
+#pragma unroll
+  for (int m = 0; m < M; ++m)
+    if (c == m) gsel = gs[m];
   // combine the row groups in index order
   float* mine = red + threadIdx.x * (2 * M + 1);
 #pragma unroll
   for (int m = 0; m < M; ++m) { mine[2 * m] = acc[m][0]; mine[2 * m + 1] = acc[m][1]; }
-  mine[2 * M] = gs;
+  mine[2 * M] = gsel;
   __syncthreads();
   if (rg == 0) {
     float tot[2 * M + 1];
@@ -940,6 +969,19 @@ cudaError_t launch_gemm_tn(const float* A, int lda, int M, const float* B, int l
   if (e != cudaSuccess) return e;
   k_reduce_partials<<<(M * n_valid + 63) / 64, 256, 0, s>>>(partial, (int)n_split, M, N, dst, ldc, n_valid, nullptr);
   if (bias_dst) k_reduce_partials<<<(M + 63) / 64, 256, 0, s>>>(bias_partial, (int)n_split, M, 1, bias_dst, 1, 1, nullptr);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_reduce_jobs(const ReduceJob* jobs, int n_jobs, cudaStream_t s) {
+  if (n_jobs < 1 || n_jobs > 2 * kGemmGroupMax) return cudaErrorInvalidValue;
+  ReduceJobs all{};
+  int max_blocks = 1;
+  for (int i = 0; i < n_jobs; ++i) {
+    all.job[i] = jobs[i];
+    const int blocks = (jobs[i].M * jobs[i].n_valid + 63) / 64;
+    if (blocks > max_blocks) max_blocks = blocks;
+  }
+  k_reduce_partials_jobs<<<dim3((unsigned)max_blocks, (unsigned)n_jobs), 256, 0, s>>>(all);
   return cudaGetLastError();
 }
 
