@@ -587,7 +587,7 @@ def run_train(args, rank, world, local_rank):
                 'clocks': clocks,
                 'e2e': {'value': value, 'unit': 'rays/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4,
                         'note': 'the timed region IS end to end: pinned host rays in, loss value out'},
-                'gpu_launches': args.steps * {'tf32': 149, 'fp16': 143, 'fp32': 95}[args.train_precision],   # counted in the ncu launch lists (profiles/)
+                'gpu_launches': args.steps * {'tf32': 89, 'fp16': 91, 'fp32': 95}[args.train_precision],   # counted in the ncu launch lists (profiles/)
                 'roofline': roofline}
         if not args.no_cpu_baseline and world == 1:
             threads = os.cpu_count() or 1
