@@ -11,6 +11,8 @@ cancel.  The fp32 CUDA path (fp32 FFMA, different summation order) is gated at 1
 and at 1e-2 on the tensor's L2 norm.  The tensor-core mode (`train_precision='tf32'`: operands of every 256-wide
 product rounded to tf32) has its own, looser gates next to its measured errors.
 """
+import os
+
 import pytest
 import torch
 
@@ -404,3 +406,33 @@ def test_graphed_train_step_equals_eager_iterations(train_precision, built_libra
         training.GraphedTrainStep(_train_model(bad), LossComputer(cfg), gopt, example)
     with pytest.raises(ValueError):      # the optimizer must be capturable
         training.GraphedTrainStep(graphed_model, LossComputer(cfg), torch.optim.Adam(graphed_model.parameters()), example)
+
+
+def test_training_gradients_at_the_benchmarked_shape(built_library):
+    """The iteration bench.py times - RealEstate-10K camera, 1 secondary view, 4096 rays x (64 + 192) samples = 1,048,576
+    sample points per step (55 tiles per SM in the chain kernels, 18 point ranges per grouped product) - against torch
+    autograd over the CPU oracle on ALL rays, from the same CPU draws: the fp32 CUDA-core mode at its gate, the fp16
+    tensor-core mode at the tensor-core gate.  Every smaller fixture has at most 333 rays = 3 tiles per SM."""
+    n_rays, n_sec = 4096, 1
+    rays = O.make_rays('re10k', n_rays, seed=2, n_sec_views=n_sec)
+    sup = O.make_supervision('re10k', n_rays, n_sec)
+    torch.manual_seed(5)
+    draws = O.draw_training_randoms(n_rays, 64, 128, 4096, 16384, True, 1.0)
+    torch.set_num_threads(max(1, (os.cpu_count() or 1)))
+    ref_out, ref_total, ref_grads = _oracle_step(O.synth_state_dict(0), rays, sup, draws, True)
+    for train_precision in ('fp32', 'fp16'):
+        tc = train_precision != 'fp32'
+        model = _train_model(_configs(True, train_precision=train_precision))
+        torch.manual_seed(5)
+        out = model(dict(H.to_cuda(rays)))
+        total, _ = H.training_loss(out, _sup_cuda(sup))
+        total.backward()
+        assert abs(total.item() - ref_total.item()) <= (2e-3 if tc else 2e-4) * abs(ref_total.item()), (train_precision, total.item(), ref_total.item())
+        for k in ('rgb_coarse', 'rgb_fine', 'visibility2_coarse', 'depth_coarse'):
+            mx, med = H.rel_err(out[k], ref_out[k])
+            assert mx <= (2e-3 if tc and k.endswith('_fine') else (5e-4 if tc else 1e-4)), (train_precision, k, mx, med)
+        worst = _compare_full_grads(model, ref_grads, max_tol=3e-2 if tc else GRAD_MAX_TOL, norm_tol=3e-2 if tc else 5 * GRAD_NORM_TOL)
+        print(f'4096 rays {train_precision}: TotalLoss {total.item():.6f} (oracle {ref_total.item():.6f}), worst gradient error '
+              f'{worst[0]:.2e} ({worst[1]}), worst L2 error {worst[2]:.2e}')
+        del model, out, total
+        torch.cuda.empty_cache()
