@@ -401,6 +401,22 @@ def test_graphed_train_step_equals_eager_iterations(train_precision, built_libra
     assert gloss.item() == step.loss_host.item()
     for (k, a), (_, b) in zip(eager.named_parameters(), graphed_model.named_parameters()):
         assert torch.equal(a, b), k
+    with pytest.raises(ValueError):      # a float learning rate is baked into the graph
+        step.set_lr(1e-4)
+    if train_precision == 'fp16':
+        # the reference's per-iteration learning-rate decay (Trainer01.py:293-295) without a re-capture: lr as a device tensor
+        lr_model = _train_model(cfg)
+        lr_opt = torch.optim.Adam(lr_model.parameters(), lr=torch.tensor(5e-4, device='cuda'), capturable=True)
+        lr_step = training.GraphedTrainStep(lr_model, LossComputer(cfg), lr_opt, example, warmup=3)
+        before = [p.detach().clone() for p in lr_model.parameters()]
+        lr_step.set_lr(0.0)
+        lr_step(rays)
+        lr_step.synchronize()
+        assert all(torch.equal(a, b) for a, b in zip(before, lr_model.parameters()))
+        lr_step.set_lr(1e-3)
+        lr_step(rays)
+        lr_step.synchronize()
+        assert any(not torch.equal(a, b) for a, b in zip(before, lr_model.parameters()))
     with pytest.raises(ValueError):      # CPU draws cannot be captured
         bad = _configs(True, train_precision=train_precision)
         training.GraphedTrainStep(_train_model(bad), LossComputer(cfg), gopt, example)

@@ -346,6 +346,16 @@ class GraphedTrainStep:
                 self._iteration()
             torch.cuda.current_stream(self.device).wait_stream(self.stream)
 
+    def set_lr(self, lr: float) -> None:
+        """The reference trainer writes the decayed rate into `param_group['lr']` every iteration
+        (Trainer01.py:293-295).  A Python float there is baked into the captured step; build the optimizer with the rate as
+        a device tensor (`Adam(..., lr=torch.tensor(lr0, device=...), capturable=True)`) and the replayed step reads it."""
+        for group in self.optimizer.param_groups:
+            if not isinstance(group['lr'], torch.Tensor):
+                raise ValueError("set_lr needs an optimizer whose lr is a device tensor (lr=torch.tensor(..., device=...)); "
+                                 "a float lr is part of the captured graph - recapture() after changing it")
+            group['lr'].fill_(lr)
+
     def __call__(self, batch: Optional[Dict] = None) -> torch.Tensor:
         if batch is not None:
             self.load(batch)
