@@ -290,7 +290,9 @@ class GraphedTrainStep:
     Requirements (checked): configs['model']['rng'] = 'device' (the reference's CPU draws cannot be captured), an
     optimizer built with `capturable=True`, a fixed ray count and fixed batch keys.  Non-tensor batch entries
     (`iter_num`, ...) and the loss weights derived from them are baked in at capture time: call `recapture()` when an
-    `iter_weights` threshold of the loss configs is crossed."""
+    `iter_weights` threshold of the loss configs is crossed.  One GPU: data-parallel training (one process per GPU with
+    sharding.allreduce_gradients between backward and step) uses eager launches - capturing the NCCL all-reduce with the
+    iteration hung in the 2-GPU trial of r02 and is not supported."""
 
     def __init__(self, model, loss_computer, optimizer, example_batch: Dict, device=None, warmup: int = 3):
         cfg = getattr(model, 'configs', {}).get('model', {})
