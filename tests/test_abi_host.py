@@ -127,3 +127,33 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, 'LIB_PATH', str(tmp_path / 'libvipnerf_b200.so'))
     with pytest.raises(_lib.VipNeRFLibraryError, match='no CPU fallback'):
         _lib.load()
+
+
+def test_training_modes_host_logic():
+    """The training arithmetic is a config key and a cfg flag: 'fp32' / 'tf32' / 'fp16' map to the header's flags, anything
+    else is refused where the reference would refuse an unknown config value; GraphedTrainStep refuses the set-ups it
+    cannot capture before it touches the device; the bench's algorithmic byte counts are the sums DESIGN.md derives."""
+    import bench
+    from vipnerf_b200 import _lib, training
+    from vipnerf_b200.ModelFactory import get_model
+    header = open(os.path.join(ROOT, 'include', 'vipnerf.h')).read()
+    for name, value in (('VIPNERF_FLAG_TRAIN_TF32', _lib.FLAG_TRAIN_TF32), ('VIPNERF_FLAG_TRAIN_F16', _lib.FLAG_TRAIN_F16)):
+        m = re.search(rf'#define\s+{name}\s+\(1u << (\d+)\)', header)
+        assert m and (1 << int(m.group(1))) == value, name
+    assert _lib.make_cfg(precision='fp32', train_precision='fp16').flags & _lib.FLAG_TRAIN_F16
+    assert _lib.make_cfg(precision='fp32', train_tf32=True).flags & _lib.FLAG_TRAIN_TF32        # the older spelling
+    assert _lib.make_cfg(precision='fp32').flags & (_lib.FLAG_TRAIN_TF32 | _lib.FLAG_TRAIN_F16) == 0
+    with pytest.raises(ValueError):
+        _lib.make_cfg(train_precision='bf16')
+    for tp in ('fp32', 'tf32', 'fp16'):
+        get_model(_configs(train_precision=tp), None)
+    with pytest.raises(ValueError):
+        get_model(_configs(train_precision='fp8'), None)
+    model = get_model(_configs(train_precision='fp16'), None)          # rng defaults to the reference's CPU draws
+    opt = torch.optim.Adam(model.parameters(), capturable=True)
+    with pytest.raises(ValueError, match='rng'):
+        training.GraphedTrainStep(model, None, opt, {})
+    model = get_model(_configs(train_precision='fp16', rng='device'), None)
+    with pytest.raises(ValueError, match='capturable'):
+        training.GraphedTrainStep(model, None, torch.optim.Adam(model.parameters()), {})
+    assert bench.TRAIN_F16_BYTES_PER_POINT == 34_160 and bench.TRAIN_TC_BYTES_PER_POINT == 82_652
