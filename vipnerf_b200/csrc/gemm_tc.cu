@@ -533,8 +533,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_linear_tc(const __grid_consta
       const int buf = i & 1;
       const int64_t pg = (int64_t)tile * kLinRows + quarter * 32 + lane;
       const bool valid = pg < p.n_rows;
-      uint4 mw0 = make_uint4(0u, 0u, 0u, 0u), mw1 = mw0;   // fp16 backward: this row's 256 ReLU-mask bits (32 bytes; the
-      if constexpr (kOutHalf && (kEpi == kEpiBwdMask || kEpi == kEpiBwdMaskRank1)) {   // loads fly while the MMAs finish)
+      // fp16 backward: this row's 256 ReLU-mask bits (32 bytes), requested before the wait for the accumulator so that
+      // the loads fly while the tile's MMAs finish
+      uint4 mw0 = make_uint4(0u, 0u, 0u, 0u), mw1 = mw0;
+      if constexpr (kOutHalf && (kEpi == kEpiBwdMask || kEpi == kEpiBwdMaskRank1)) {
         if (valid) {
           mw0 = *reinterpret_cast<const uint4*>(p.relu_bits + pg * 8);
           mw1 = *reinterpret_cast<const uint4*>(p.relu_bits + pg * 8 + 4);
@@ -545,13 +547,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_linear_tc(const __grid_consta
       // Epilogue through shared memory and the TMA engine.  A lane owns one accumulator row, so direct global accesses
       // touch 32 different 128-byte lines per instruction (the r01 kernel ran at 0.45 of the HBM roofline because of it).
       // Instead every warp stages its [32 rows x 128 B] chunk in a swizzled 4 KiB box and ONE bulk tensor store
-      // writes it (full lines, asynchronous, rows past the end clipped by the tensor map); the ReLU mask of the
-      // backward chain arrives the same way (bulk tensor load of the saved activation's box, one chunk ahead).
-      uint8_t* wstage = stage_base + (warp - 2) * 16384;             // [2] output boxes, then [2] mask boxes
+      // writes it (full lines, asynchronous, rows past the end clipped by the tensor map); the tf32 backward chain's ReLU
+      // mask arrives the same way (bulk tensor load of the saved activation's box, one chunk ahead; the fp16 chains carry
+      // their masks as bits instead).
+      uint8_t* wstage = stage_base + (warp - 2) * 16384;             // [2] output boxes, then [2] mask boxes (tf32)
       const uint32_t out_s = smem_u32(wstage), msk_s = out_s + 8192;
       const uint32_t mfull0 = mask_full(warp - 2, 0);
       const int row0 = tile * kLinRows + quarter * 32;
-      const bool has_mask = p.mask != nullptr;
+      const bool has_mask = !kOutHalf && p.mask != nullptr;
       if (has_mask && lane == 0) {
         mbar_expect_tx(mfull0 + 8u * (mask_n & 1), 4096);
         tma_load_2d(msk_s + 4096u * (mask_n & 1), &p.map_mask, 0, row0, mfull0 + 8u * (mask_n & 1));
