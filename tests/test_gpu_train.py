@@ -454,7 +454,7 @@ def test_training_gradients_at_the_benchmarked_shape(built_library):
         torch.cuda.empty_cache()
 
 
-@pytest.mark.parametrize('n_rays,n_sec', [(1, 0), (3, 1), (130, 0), (257, 2)])
+@pytest.mark.parametrize('n_rays,n_sec', [(1, 0), (3, 1), (130, 0), (257, 2), (66, 5)])   # 5 secondary views: the generic view-count path of k_heads_bwd
 def test_fp16_mode_edge_shapes(n_rays, n_sec, built_library):
     """The fp16 tensor-core mode on shapes around its tile sizes - fewer points than one 128-point tile, no secondary view
     (one view direction per point), point counts that are not multiples of anything - against the fp32 CUDA-core mode and
