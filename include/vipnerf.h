@@ -246,7 +246,8 @@ int vipnerf_visibility_prior(int32_t height, int32_t width, const uint8_t* frame
  * flag must be set for the forward, the backward and the two size queries).  Random numbers are the caller's: rays->t_rand [R,Nc], rays->u_rand [R,Nf] (torch.rand) and
  * sigma_noise_* = raw_noise_std * torch.randn, drawn exactly where the reference draws them; NULL = that source off.
  *
- * `saved` (vipnerf_train_saved_bytes, about 11 KB per sample point) receives the activations of both MLPs; the caller
+ * `saved` (vipnerf_train_saved_bytes, about 11 KB per sample point; 5.6 KB with VIPNERF_FLAG_TRAIN_F16: fp16 arrays + the
+ * ReLU masks as bits) receives the activations of both MLPs; the caller
  * keeps it, together with the forward outputs z_vals / raw_sigma / raw_rgb / raw_visibility (/ raw_visibility2) of
  * both sample sets, until vipnerf_train_backward.  `grad_out` has the layout of vipnerf_out and holds the upstream
  * gradient of each output (NULL = zero; z_vals carries no gradient: sample positions are detached, :213).
