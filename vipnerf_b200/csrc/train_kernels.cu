@@ -439,28 +439,47 @@ __global__ void __launch_bounds__(256) k_reduce_partials_jobs(const __grid_const
 __device__ __forceinline__ float to_f32(float v) { return v; }
 __device__ __forceinline__ float to_f32(__half v) { return __half2float(v); }
 
-__device__ __forceinline__ float2 load_pair(const float* p) { return *reinterpret_cast<const float2*>(p); }
-__device__ __forceinline__ float2 load_pair(const __half* p) { return __half22float2(*reinterpret_cast<const __half2*>(p)); }
+__device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void load8(const __half* p, float (&v)[8]) {
+  const uint4 t = *reinterpret_cast<const uint4*>(p);
+  const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[j]));
+    v[2 * j] = f.x; v[2 * j + 1] = f.y;
+  }
+}
 
 // out[m][n] = sum_r G[r][m] * H[r][n], gsum[m] = sum_r G[r][m] for the 1- and 4-row heads: an HBM stream over H.
-// A thread owns two adjacent columns, so N / 2 threads cover a row and a 256-thread block works on 512 / N rows at a time
-// with eight row groups in flight (the r01 kernel - one row per block iteration, half of its threads idle at N = 128 -
-// ran at a tenth of the HBM roofline); the row groups' sums are combined in a fixed order through shared memory.
+// A thread owns EIGHT adjacent columns (one 16-byte load of an fp16 row, two of an fp32 row), so N / 8 threads cover a row
+// and a 256-thread block works on 2048 / N rows at a time.  The wide loads are what keeps enough bytes in flight: with
+// column pairs per thread the compiler kept only two 4-byte loads per thread outstanding and the stream ran at 0.3 of
+// the HBM roofline (the r01 kernel - one row per block iteration, half of its threads idle at N = 128 - at a tenth).
+// The row groups' sums are combined in a fixed order through shared memory.
 template <int M, typename T>
 __global__ void __launch_bounds__(256)
 k_small_tn(const float* __restrict__ G, const T* __restrict__ H, int N, int64_t n_rows, int64_t rows_per_split,
            float* __restrict__ partial, float* __restrict__ gsum_partial) {
-  __shared__ float red[256 * (2 * M + 1)];
-  const int tpr = N / 2;                         // threads per row
+  constexpr int kC = 8;                          // columns per thread
+  constexpr int kStride = kC * M + 1;            // floats a thread publishes (+ its share of the column sums of G)
+  __shared__ float red[256 * kStride];
+  const int tpr = N / kC;                        // threads per row
   const int rpp = 256 / tpr;                     // rows per pass of the block
   const int rg = threadIdx.x / tpr, c = threadIdx.x % tpr;
   const int64_t r_begin = (int64_t)blockIdx.x * rows_per_split;
   const int64_t r_end = min(n_rows, r_begin + rows_per_split);
-  float acc[M][2];
+  float acc[M][kC];
   float gs[M];      // column sums of G, kept by every thread (the row's G values are in its registers anyway); thread
                     // c < M of a row group publishes column c
 #pragma unroll
-  for (int m = 0; m < M; ++m) { acc[m][0] = acc[m][1] = 0.f; gs[m] = 0.f; }
+  for (int m = 0; m < M; ++m) {
+    gs[m] = 0.f;
+#pragma unroll
+    for (int j = 0; j < kC; ++j) acc[m][j] = 0.f;
+  }
   auto load_g = [&](int64_t rr, float (&g)[M]) {   // one row of G: a single 16-byte load for the 4-row head
     if constexpr (M == 4) {
       const float4 t = *reinterpret_cast<const float4*>(G + rr * 4);
@@ -470,58 +489,64 @@ k_small_tn(const float* __restrict__ G, const T* __restrict__ H, int N, int64_t 
       for (int m = 0; m < M; ++m) g[m] = G[rr * M + m];
     }
   };
-  constexpr int kU = 8;
+  constexpr int kU = 4;
   int64_t r = r_begin + rg;
   for (; r + (kU - 1) * rpp < r_end; r += kU * rpp) {
-    float2 hv[kU];
+    float h[kU][kC];
     float g[kU][M];
 #pragma unroll
     for (int u = 0; u < kU; ++u) {
       const int64_t rr = r + u * rpp;
-      hv[u] = load_pair(H + rr * N + 2 * c);
+      load8(H + rr * N + kC * c, h[u]);
       load_g(rr, g[u]);
     }
 #pragma unroll
     for (int u = 0; u < kU; ++u) {
 #pragma unroll
       for (int m = 0; m < M; ++m) {
-        acc[m][0] = fmaf(g[u][m], hv[u].x, acc[m][0]); acc[m][1] = fmaf(g[u][m], hv[u].y, acc[m][1]);
+#pragma unroll
+        for (int j = 0; j < kC; ++j) acc[m][j] = fmaf(g[u][m], h[u][j], acc[m][j]);
         gs[m] += g[u][m];
       }
     }
   }
   for (; r < r_end; r += rpp) {
-    const float2 h2 = load_pair(H + r * N + 2 * c);
-    float g[M];
+    float h[kC], g[M];
+    load8(H + r * N + kC * c, h);
     load_g(r, g);
 #pragma unroll
-    for (int m = 0; m < M; ++m) { acc[m][0] = fmaf(g[m], h2.x, acc[m][0]); acc[m][1] = fmaf(g[m], h2.y, acc[m][1]); gs[m] += g[m]; }
+    for (int m = 0; m < M; ++m) {
+#pragma unroll
+      for (int j = 0; j < kC; ++j) acc[m][j] = fmaf(g[m], h[j], acc[m][j]);
+      gs[m] += g[m];
+    }
   }
   float gsel = 0.f;
 #pragma unroll
   for (int m = 0; m < M; ++m)
     if (c == m) gsel = gs[m];
   // combine the row groups in index order
-  float* mine = red + threadIdx.x * (2 * M + 1);
+  float* mine = red + threadIdx.x * kStride;
 #pragma unroll
-  for (int m = 0; m < M; ++m) { mine[2 * m] = acc[m][0]; mine[2 * m + 1] = acc[m][1]; }
-  mine[2 * M] = gsel;
+  for (int m = 0; m < M; ++m)
+#pragma unroll
+    for (int j = 0; j < kC; ++j) mine[kC * m + j] = acc[m][j];
+  mine[kC * M] = gsel;
   __syncthreads();
   if (rg == 0) {
-    float tot[2 * M + 1];
+    float tot[kStride];
 #pragma unroll
-    for (int j = 0; j < 2 * M + 1; ++j) tot[j] = 0.f;
+    for (int j = 0; j < kStride; ++j) tot[j] = 0.f;
     for (int q = 0; q < rpp; ++q) {
-      const float* other = red + (q * tpr + c) * (2 * M + 1);
+      const float* other = red + (q * tpr + c) * kStride;
 #pragma unroll
-      for (int j = 0; j < 2 * M + 1; ++j) tot[j] += other[j];
+      for (int j = 0; j < kStride; ++j) tot[j] += other[j];
     }
 #pragma unroll
-    for (int m = 0; m < M; ++m) {
-      partial[((size_t)blockIdx.x * M + m) * N + 2 * c] = tot[2 * m];
-      partial[((size_t)blockIdx.x * M + m) * N + 2 * c + 1] = tot[2 * m + 1];
-    }
-    if (c < M) gsum_partial[(size_t)blockIdx.x * M + c] = tot[2 * M];
+    for (int m = 0; m < M; ++m)
+#pragma unroll
+      for (int j = 0; j < kC; ++j) partial[((size_t)blockIdx.x * M + m) * N + kC * c + j] = tot[kC * m + j];
+    if (c < M) gsum_partial[(size_t)blockIdx.x * M + c] = tot[kC * M];
   }
 }
 
@@ -567,7 +592,18 @@ k_encode_points(RayPtrs rp, RenderFlags fl, int64_t n_points, int S, const float
   }
   e[63] = 0.f;
   __syncthreads();
-  for (int i = threadIdx.x; i < n_here * 64; i += blockDim.x) store_as(enc + p0 * 64 + i, tile[(i >> 6) * 65 + (i & 63)]);
+  if constexpr (sizeof(T) == 2) {   // fp16: eight columns = one 16-byte store per item
+    for (int i = threadIdx.x; i < n_here * 8; i += blockDim.x) {
+      const float* src = tile + (i >> 3) * 65 + (i & 7) * 8;
+      const __half2 a = __floats2half2_rn(src[0], src[1]), b = __floats2half2_rn(src[2], src[3]),
+                    c2 = __floats2half2_rn(src[4], src[5]), d = __floats2half2_rn(src[6], src[7]);
+      *reinterpret_cast<uint4*>(enc + p0 * 64 + (int64_t)i * 8) =
+          make_uint4(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b),
+                     *reinterpret_cast<const uint32_t*>(&c2), *reinterpret_cast<const uint32_t*>(&d));
+    }
+  } else {
+    for (int i = threadIdx.x; i < n_here * 64; i += blockDim.x) store_as(enc + p0 * 64 + i, tile[(i >> 6) * 65 + (i & 63)]);
+  }
   for (int v = 0; v < nviews; ++v) {
     float dir[3];
     if (v == 0) {
@@ -588,9 +624,24 @@ k_encode_points(RayPtrs rp, RenderFlags fl, int64_t n_points, int S, const float
     for (int c = kEncView; c < 32; ++c) pe[c] = 0.f;
     __syncthreads();
     // row r of this view lives at pev[((p0 + r) * nviews + v) * kPevCols ...]: one full 128-byte line per row
-    for (int i = threadIdx.x; i < n_here * kPevCols; i += blockDim.x) {
-      const int r = i / kPevCols, c = i % kPevCols;
-      store_as(pev + ((p0 + r) * nviews + v) * kPevCols + c, c < 32 ? tile[r * 33 + c] : 0.f);
+    if constexpr (sizeof(T) == 2) {   // fp16 rows: 8 x 16 bytes, the upper four all zero (columns 32..63)
+      for (int i = threadIdx.x; i < n_here * 8; i += blockDim.x) {
+        const int r = i >> 3, q = i & 7;
+        uint4 w = make_uint4(0u, 0u, 0u, 0u);
+        if (q < 4) {
+          const float* src = tile + r * 33 + q * 8;
+          const __half2 a = __floats2half2_rn(src[0], src[1]), b = __floats2half2_rn(src[2], src[3]),
+                        c2 = __floats2half2_rn(src[4], src[5]), d = __floats2half2_rn(src[6], src[7]);
+          w = make_uint4(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b),
+                         *reinterpret_cast<const uint32_t*>(&c2), *reinterpret_cast<const uint32_t*>(&d));
+        }
+        *reinterpret_cast<uint4*>(pev + ((p0 + r) * nviews + v) * kPevCols + q * 8) = w;
+      }
+    } else {
+      for (int i = threadIdx.x; i < n_here * kPevCols; i += blockDim.x) {
+        const int r = i / kPevCols, c = i % kPevCols;
+        store_as(pev + ((p0 + r) * nviews + v) * kPevCols + c, c < 32 ? tile[r * 33 + c] : 0.f);
+      }
     }
   }
 }
@@ -1022,7 +1073,7 @@ cudaError_t launch_colsum(const float* A, int lda, int M, int64_t n_rows, float*
 cudaError_t launch_small_tn(const float* G, int M, const void* H, int N, int64_t n_rows, float* dst, float* gsum_dst,
                             float* partial, cudaStream_t s, bool half_h) {
   if ((M != 1 && M != 4) || (N != 128 && N != 256)) return cudaErrorInvalidValue;   // a row = 64 or 128 column pairs
-  int64_t n_split = 8 * 148;       // 8 blocks of 256 threads per SM: the loads in flight are what bounds this stream
+  int64_t n_split = 6 * 148;       // 6 blocks of 256 threads per SM (33 KiB of shared memory each)
   const int64_t max_by_rows = (n_rows + 63) / 64;
   if (n_split > max_by_rows) n_split = max_by_rows;
   if (n_split < 1) n_split = 1;
