@@ -316,6 +316,11 @@ int vipnerf_param_gradient_gemm(const void* dy, int32_t ld_dy, int32_t m, const 
                                 int64_t n_rows, float* dw, int32_t ld_dw, int32_t n_valid, float* db, int32_t mode,
                                 void* workspace, size_t workspace_bytes, void* stream);
 
+/* The gradient-scale rule of VIPNERF_FLAG_TRAIN_F16 (host-side evaluation of the device function, for tests and
+ * documentation): every fp16 gradient array of the backward-data chain is stored times the power of two that moves the
+ * measured maximum `amax` of its defining array into [16, 32); 0, negative, inf and nan give 1. */
+float vipnerf_grad_scale(float amax);
+
 /* --- profiling aid (not part of the reference-facing path): a device buffer of 64 uint64 that CTA 0 of every
  * subsequent tensor-core launch fills with cycle counters of its warp roles (see tools/tc_cycle_breakdown.py);
  * NULL switches it off.  Process-global. */

@@ -157,3 +157,21 @@ def test_training_modes_host_logic():
     with pytest.raises(ValueError, match='capturable'):
         training.GraphedTrainStep(model, None, torch.optim.Adam(model.parameters()), {})
     assert bench.TRAIN_F16_BYTES_PER_POINT == 34_160 and bench.TRAIN_TC_BYTES_PER_POINT == 82_652
+
+
+def test_gradient_scale_rule(built_library):
+    """vipnerf_grad_scale = the device function that scales the fp16 gradient arrays: a power of two that moves the
+    measured maximum into [16, 32) (11 binades below fp16's 65504), 1 for the values no maximum can define a scale from."""
+    import math
+    from vipnerf_b200 import _lib
+    lib = _lib.load()
+    assert lib.vipnerf_grad_scale(20.0) == 1.0 and lib.vipnerf_grad_scale(16.0) == 1.0 and lib.vipnerf_grad_scale(31.9) == 1.0
+    assert lib.vipnerf_grad_scale(1.0) == 16.0 and lib.vipnerf_grad_scale(32.0) == 0.5
+    for bad in (0.0, -3.0, float('inf'), float('nan')):
+        assert lib.vipnerf_grad_scale(bad) == 1.0
+    g = torch.Generator().manual_seed(0)
+    for amax in torch.exp(torch.empty(200).uniform_(-60.0, 60.0, generator=g)).tolist():
+        s = lib.vipnerf_grad_scale(amax)
+        assert s > 0 and math.log2(s) == round(math.log2(s)), (amax, s)       # a power of two: exact to apply and to undo
+        assert 16.0 <= float(torch.tensor(amax, dtype=torch.float32)) * s < 32.0, (amax, s)
+    assert lib.vipnerf_grad_scale(1e-45) == 2.0 ** 120                        # subnormal maxima: the exponent is clamped

@@ -110,6 +110,7 @@ EXPORTS = {
     'vipnerf_param_gradient_gemm_workspace_bytes': (c_size_t, []),
     'vipnerf_param_gradient_gemm': (c_int, [c_void_p, c_int32, c_int32, c_void_p, c_int32, c_int32, c_int64, c_void_p,
                                             c_int32, c_int32, c_void_p, c_int32, c_void_p, c_size_t, c_void_p]),
+    'vipnerf_grad_scale': (c_float, [c_float]),
     'vipnerf_debug_set_profile_buffer': (c_int, [c_void_p]),
 }
 

@@ -845,6 +845,12 @@ int vipnerf_composite_backward(const vipnerf_cfg* cfg, const vipnerf_rays* rays,
   return VIPNERF_OK;
 }
 
+float vipnerf_grad_scale(float amax) {
+  uint32_t bits;
+  memcpy(&bits, &amax, sizeof(bits));
+  return grad_scale_from_amax(bits);
+}
+
 size_t vipnerf_param_gradient_gemm_workspace_bytes(void) { return (gemm_partial_floats() + kColsumPartialFloats) * sizeof(float) + 256; }
 
 int vipnerf_param_gradient_gemm(const void* dy, int32_t ld_dy, int32_t m, const void* x, int32_t ld_x, int32_t n,

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "../../include/vipnerf.h"
 #include "stages.cuh"
@@ -205,13 +206,22 @@ cudaError_t launch_small_tn(const float* G, int M, const void* H, int N, int64_t
 #ifdef __CUDACC__
 // fp16 training mode: a gradient array is stored as value * 2^k with k chosen so that `amax` (float bits of a non-negative
 // maximum measured on the device) lands in [16, 32): 11 binades of head room to fp16's 65504 (conversions saturate), and
-// everything down to 2^-28 of amax stays representable.  0 / inf / nan: unscaled.
-__device__ __forceinline__ float grad_scale_from_amax(uint32_t amax_bits) {
+// everything down to 2^-28 of amax stays representable.  0 / inf / nan: unscaled.  (Host-callable for the C ABI's
+// vipnerf_grad_scale, which the CPU tests hold to this specification.)
+__host__ __device__ __forceinline__ float grad_scale_from_amax(uint32_t amax_bits) {
   const uint32_t e = (amax_bits >> 23) & 0xffu;
-  if (amax_bits == 0u || e == 0xffu) return 1.f;
+  float one = 1.f;
+  if (amax_bits == 0u || e == 0xffu || (amax_bits >> 31)) return one;
   int k = 4 - ((int)(e == 0u ? 1u : e) - 127);
   k = k < -120 ? -120 : (k > 120 ? 120 : k);
-  return __uint_as_float((uint32_t)(k + 127) << 23);
+  const uint32_t out = (uint32_t)(k + 127) << 23;
+#ifdef __CUDA_ARCH__
+  return __uint_as_float(out);
+#else
+  float f;
+  memcpy(&f, &out, sizeof(f));
+  return f;
+#endif
 }
 #endif
 
