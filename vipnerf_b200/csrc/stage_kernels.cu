@@ -25,7 +25,8 @@ __device__ __forceinline__ float fused_views_weight(const ParamPtrs& pp, int n, 
   return (float)acc;
 }
 
-__global__ void k_pack_small(ParamPtrs pp, float* __restrict__ small) {
+// with_fused: the folded views bias (128 double-precision dot products) is read by the tensor-core eval kernels only
+__global__ void k_pack_small(ParamPtrs pp, float* __restrict__ small, bool with_fused) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= kSmallFloats) return;
   float v = 0.f;
@@ -51,7 +52,7 @@ __global__ void k_pack_small(ParamPtrs pp, float* __restrict__ small) {
   } else if (i < kOffBiasViewsFused) {
     v = pp.p[23][i - kOffBOut];
   } else {
-    v = fused_views_bias(pp, i - kOffBiasViewsFused);
+    v = with_fused ? fused_views_bias(pp, i - kOffBiasViewsFused) : 0.f;
   }
   small[i] = v;
 }
@@ -157,7 +158,7 @@ cudaError_t launch_pack_weights(int precision, const float* const params_dev[24]
   for (int i = 0; i < 24; ++i) pp.p[i] = params_dev[i];
   float* small = reinterpret_cast<float*>(packed);
   uint8_t* big = reinterpret_cast<uint8_t*>(packed) + kSmallBytes;
-  k_pack_small<<<(kSmallFloats + 255) / 256, 256, 0, s>>>(pp, small);
+  k_pack_small<<<(kSmallFloats + 255) / 256, 256, 0, s>>>(pp, small, precision != VIPNERF_PRECISION_FP32);
   if (precision == VIPNERF_PRECISION_FP32) {
     k_pack_fp32<<<(kFp32BigFloats + 255) / 256, 256, 0, s>>>(pp, reinterpret_cast<float*>(big));
     k_pack_fp32_bwd<<<(kFp32BwdFloats + 255) / 256, 256, 0, s>>>(pp, reinterpret_cast<float*>(big) + kFp32BigFloats);
